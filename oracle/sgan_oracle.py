@@ -1,0 +1,650 @@
+"""CPU ORACLE for the ScrabbleGAN train-step hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain torch-CPU (fp64 or fp32) restatement of the arithmetic the reference
+(UtkuKaradeniz/scrabble-gan, TensorFlow 2.x / Keras) performs on its hot path.  It exists to CHECK the
+CUDA path.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+leg may import it.  The product package (`scrabble-gan_b200/`) never imports anything from `oracle/`.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
+TensorFlow cannot be installed in this image, so this restatement is pinned only by (i) the reference
+source it follows line by line (cited below as file:line relative to /root/reference/src) and (ii) the
+math-only known-answer tests in tests/test_oracle_kat.py (brute-force CTC path enumeration, 7-loop
+convolution, SVD for spectral norm, finite differences for the closed-form gradient-balance derivative).
+
+Layouts are TensorFlow's: activations NHWC, Conv2D kernels HWIO, Conv2DTranspose kernels
+(kh, kw, Cout, Cin), Dense kernels (in, out), labels int.
+
+Reference quirks encoded here:
+  Q1  hinge is called with 5 positional args by train_step but takes 4 -> oracle drops the 5th.
+  Q2  spectral_norm is a kernel_regularizer whose loss is never read -> weights are used un-normalised.
+  Q4  NonLocalBlock builds fresh 1x1 convs per call -> oracle takes theta/phi/g/o as explicit weights.
+  Q5  R (and D, W) run with trainable=False during the forward -> R's BatchNorm is inference mode.
+  Q6  "gradient balancing" is on loss values with differentiable population std.
+  Q7  tape.gradient of a (B,1) target = gradient of the SUM over the batch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+BN_EPS = 1e-3          # Keras BatchNormalization default epsilon
+BN_MOMENTUM = 0.99     # Keras BatchNormalization default momentum
+KERAS_EPS = 1e-7       # K.epsilon()
+
+
+# ----------------------------------------------------------------------------------------------------
+# channel tables                                                   bigacgan/net_architecture.py:565-586
+# ----------------------------------------------------------------------------------------------------
+def get_in_out_channels_gen(resolution=32):
+    ch = 64
+    if resolution != 32:
+        raise ValueError("Unsupported resolution: {}".format(resolution))
+    mult = [8, 4, 2, 1]
+    return [ch * c for c in mult[:-1]], [ch * c for c in mult[1:]]
+
+
+def get_in_out_channels_disc(colors=1, resolution=32):
+    ch = 64
+    if colors not in (1, 3):
+        raise ValueError("Unsupported color channels: {}".format(colors))
+    if resolution != 32:
+        raise ValueError("Unsupported resolution: {}".format(resolution))
+    out = [ch * c for c in [1, 8, 16, 16]]
+    return [colors] + out[:-1], out
+
+
+# ----------------------------------------------------------------------------------------------------
+# TF op restatements
+# ----------------------------------------------------------------------------------------------------
+def _same_pad(n: int, k: int, s: int) -> Tuple[int, int]:
+    """TF SAME padding: total = max((ceil(n/s)-1)*s + k - n, 0); before = total//2 (extra at the end)."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+def conv2d(x: Tensor, w: Tensor, b: Optional[Tensor] = None, padding: str = "same") -> Tensor:
+    """tf.keras.layers.Conv2D, stride 1.  x NHWC, w HWIO.  (resnet_ops.py:65,98,103,109; net_architecture.py:28-49)"""
+    kh, kw = w.shape[0], w.shape[1]
+    xt = x.permute(0, 3, 1, 2)
+    if padding == "same":
+        pt, pb = _same_pad(x.shape[1], kh, 1)
+        pl, pr = _same_pad(x.shape[2], kw, 1)
+        xt = F.pad(xt, (pl, pr, pt, pb))
+    y = F.conv2d(xt, w.permute(3, 2, 0, 1), b)
+    return y.permute(0, 2, 3, 1)
+
+
+def conv2d_transpose(x: Tensor, w: Tensor, b: Optional[Tensor], strides: Tuple[int, int]) -> Tensor:
+    """tf.keras.layers.Conv2DTranspose(padding='same').  w is (kh, kw, Cout, Cin).  (resnet_ops.py:57,69)
+
+    TF defines it as the input-gradient of the SAME forward conv with the same kernel/stride, so
+    out[y] = sum_{i,k : i*s + k - pad_before = y} x[i] w[k] with pad_before of the *forward* conv on an input of
+    size n*s; the output is cropped to n*s.
+    """
+    kh, kw = w.shape[0], w.shape[1]
+    sh, sw = strides
+    n_h, n_w = x.shape[1], x.shape[2]
+    full = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), None, stride=(sh, sw), padding=0)
+    pb_h, _ = _same_pad(n_h * sh, kh, sh)
+    pb_w, _ = _same_pad(n_w * sw, kw, sw)
+    y = full[:, :, pb_h:pb_h + n_h * sh, pb_w:pb_w + n_w * sw]
+    # the full transposed conv can be shorter than pb + n*s when k < s (1x1 stride 2): pad with zeros at the end
+    ph = n_h * sh - y.shape[2]
+    pw = n_w * sw - y.shape[3]
+    if ph > 0 or pw > 0:
+        y = F.pad(y, (0, pw, 0, ph))
+    if b is not None:
+        y = y + b.view(1, -1, 1, 1)
+    return y.permute(0, 2, 3, 1)
+
+
+def avg_pool_2x2_same(x: Tensor) -> Tensor:
+    """tf.nn.pool(AVG, [2,2], SAME, strides [2,2]) (resnet_ops.py:106,113).  Even dims -> plain mean;
+    odd dims: TF averages over the valid elements only."""
+    xt = x.permute(0, 3, 1, 2)
+    return F.avg_pool2d(xt, 2, 2, ceil_mode=True, count_include_pad=False).permute(0, 2, 3, 1)
+
+
+def max_pool(x: Tensor, ph: int, pw: int) -> Tensor:
+    """layers.MaxPool2D(pool_size=(ph,pw)) => VALID, strides = pool size (net_architecture.py:29-47; arch_ops.py:47,58)."""
+    return F.max_pool2d(x.permute(0, 3, 1, 2), (ph, pw), (ph, pw)).permute(0, 2, 3, 1)
+
+
+def batchnorm_train(x: Tensor, mov_mean: Tensor, mov_var: Tensor):
+    """Keras BatchNormalization(scale=False, center=False) training=True: biased batch variance for the
+    normalisation, moving stats updated with momentum .99 (the fused kernel feeds the Bessel-corrected
+    variance into the moving average).  Returns (x_hat, new_moving_mean, new_moving_var)."""
+    dims = (0, 1, 2)
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    n = x.shape[0] * x.shape[1] * x.shape[2]
+    x_hat = (x - mean) * torch.rsqrt(var + BN_EPS)
+    unbiased = var * (n / max(n - 1, 1))
+    new_mean = mov_mean * BN_MOMENTUM + mean.detach() * (1 - BN_MOMENTUM)
+    new_var = mov_var * BN_MOMENTUM + unbiased.detach() * (1 - BN_MOMENTUM)
+    return x_hat, new_mean, new_var
+
+
+def batchnorm_infer(x: Tensor, mov_mean: Tensor, mov_var: Tensor) -> Tensor:
+    return (x - mov_mean) * torch.rsqrt(mov_var + BN_EPS)
+
+
+def dense(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    y = x @ w
+    return y if b is None else y + b
+
+
+# ----------------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------------
+def conditional_batchnorm(x, z, p: Dict[str, Tensor], pre: str, training: bool, new_stats: Dict[str, Tensor]):
+    """ConditionalBatchNorm.call (resnet_ops.py:13-28): BN(scale=False, center=False) then * gamma(z) + beta(z),
+    gamma/beta = Dense(32 -> C, no bias).  Note: NOT 1 + gamma."""
+    mm, mv = p[pre + ".moving_mean"], p[pre + ".moving_var"]
+    if training:
+        xh, nm, nv = batchnorm_train(x, mm, mv)
+        new_stats[pre + ".moving_mean"] = nm
+        new_stats[pre + ".moving_var"] = nv
+    else:
+        xh = batchnorm_infer(x, mm, mv)
+    gamma = dense(z, p[pre + ".gamma.w"]).view(-1, 1, 1, x.shape[-1])
+    beta = dense(z, p[pre + ".beta.w"]).view(-1, 1, 1, x.shape[-1])
+    return xh * gamma + beta
+
+
+def resnet_block_up(x, z, p, pre: str, is_last: bool, training: bool, new_stats):
+    """ResNetBlockUp.call (resnet_ops.py:46-74)."""
+    stride = (2, 1) if is_last else (2, 2)
+    net = conditional_batchnorm(x, z, p, pre + ".cbn1", training, new_stats)
+    net = torch.relu(net)
+    net = conv2d_transpose(net, p[pre + ".up.w"], p[pre + ".up.b"], stride)
+    net = conditional_batchnorm(net, z, p, pre + ".cbn2", training, new_stats)
+    net = torch.relu(net)
+    net = conv2d(net, p[pre + ".conv.w"], p[pre + ".conv.b"])
+    shortcut = conv2d_transpose(x, p[pre + ".short.w"], p[pre + ".short.b"], stride)
+    return net + shortcut
+
+
+def resnet_block_down(x, p, pre: str, is_last: bool):
+    """ResNetBlockDown.call (resnet_ops.py:93-115).  ReLU is applied to the raw input of *every* block (Q11)."""
+    net = torch.relu(x)
+    net = conv2d(net, p[pre + ".conv1.w"], p[pre + ".conv1.b"])
+    net = torch.relu(net)
+    net = conv2d(net, p[pre + ".conv2.w"], p[pre + ".conv2.b"])
+    if not is_last:
+        net = avg_pool_2x2_same(net)
+    shortcut = conv2d(x, p[pre + ".short.w"], p[pre + ".short.b"])
+    if not is_last:
+        shortcut = avg_pool_2x2_same(shortcut)
+    return net + shortcut
+
+
+def non_local_block(x, p, pre: str):
+    """NonLocalBlock.call (arch_ops.py:32-67) with persistent theta/phi/g/o kernels (deviation D2, Q4).
+    No 1/sqrt(d) scaling; softmax over the (max-pooled) key axis."""
+    n, h, w, c = x.shape
+    theta = conv2d(x, p[pre + ".theta.w"]).reshape(n, h * w, c // 8)
+    phi = max_pool(conv2d(x, p[pre + ".phi.w"]), 2, 2).reshape(n, -1, c // 8)
+    attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+    g = max_pool(conv2d(x, p[pre + ".g.w"]), 2, 2).reshape(n, -1, c // 2)
+    attn_g = (attn @ g).reshape(n, h, w, c // 2)
+    attn_g = conv2d(attn_g, p[pre + ".o.w"])
+    return p[pre + ".sigma"] * attn_g + x
+
+
+def filter_bank(z0: Tensor, y: Tensor, bank: Tensor, seed: int = 4, ch: int = 512) -> Tensor:
+    """SpatialEmbedding + assembly (arch_ops.py:84-90; net_architecture.py:230-231, 260-271), literally:
+    gather bank[y] -> (B,L,32,8192); (1x32)@(32x8192) per char; reshape, reshape, transpose -> (B,4,4L,512)."""
+    b, l = y.shape
+    se = bank[y.long()]                                     # (B, L, 32, 8192)   embedding_lookup
+    z0 = z0.view(b, 1, 1, z0.shape[1])
+    net = torch.matmul(z0.expand(b, l, 1, z0.shape[-1]), se)  # (B, L, 1, 8192)     tile + matmul
+    net = net.squeeze(2)                                    # (B, L, 8192)
+    net = net.reshape(b, ch, seed, seed, -1)                # net_architecture.py:269
+    net = net.reshape(b, -1, ch, seed)                      # net_architecture.py:270
+    return net.permute(0, 3, 1, 2)                          # (B, 4, 4L, 512)     :271
+
+
+def filter_bank_index_map(l: int, k: int) -> Tuple[int, int, int]:
+    """Closed form of the reshape/reshape/transpose above: element k of character l lands at (h, w, c)."""
+    return k % 4, 4 * l + k // 2048, (k % 2048) // 4
+
+
+# ----------------------------------------------------------------------------------------------------
+# networks
+# ----------------------------------------------------------------------------------------------------
+def discriminator_features(x, p, attention_blocks: str = "B1", prefix: str = "B", attn_after: Optional[str] = None):
+    """Shared trunk of make_discriminator / make_style_promoter / the in-G style encoder
+    (net_architecture.py:299-355, 358-414, 233-249)."""
+    _, out_ch = get_in_out_channels_disc(colors=x.shape[-1], resolution=x.shape[1])
+    net = x
+    for i in range(len(out_ch)):
+        name = "{}{}".format(prefix, i + 1)
+        net = resnet_block_down(net, p, name, i == len(out_ch) - 1)
+        has_attn = (name == attn_after) if attn_after is not None else (name in attention_blocks)
+        if has_attn:
+            net = non_local_block(net, p, name + ".attn")
+    net = torch.relu(net)
+    return net.mean(dim=(1, 2))                             # GlobalAveragePooling2D
+
+
+def discriminator(x, p, attention_blocks: str = "B1"):
+    """make_discriminator / make_style_promoter: -> (B,1) logits, Dense(1024->1, no bias)."""
+    return dense(discriminator_features(x, p, attention_blocks), p["dense.w"])
+
+
+def style_encoder(imgs, p):
+    """Front-end of this fork's make_generator (net_architecture.py:233-257): z = Dense(1024->128)(GAP(relu(trunk)))."""
+    feats = discriminator_features(imgs, p, prefix="B_style", attn_after="B_style1")
+    return dense(feats, p["style_dense.w"])
+
+
+def generator_core(z, y, p, attention_blocks: str = "B3", training: bool = True,
+                   new_stats: Optional[Dict[str, Tensor]] = None):
+    """G from z (B,128) and labels y (B,L) (net_architecture.py:259-289)."""
+    if new_stats is None:
+        new_stats = {}
+    in_ch, out_ch = get_in_out_channels_gen(32)
+    nb = len(in_ch)
+    zs = torch.split(z, z.shape[1] // (nb + 1), dim=1)
+    net = filter_bank(zs[0], y, p["filter_bank"])
+    for i in range(nb):
+        name = "B{}".format(i + 1)
+        net = resnet_block_up(net, zs[i + 1], p, name, i == nb - 1, training, new_stats)
+        if name in attention_blocks:
+            net = non_local_block(net, p, name + ".attn")
+    mm, mv = p["bn.moving_mean"], p["bn.moving_var"]
+    if training:
+        xh, nm, nv = batchnorm_train(net, mm, mv)
+        new_stats["bn.moving_mean"], new_stats["bn.moving_var"] = nm, nv
+    else:
+        xh = batchnorm_infer(net, mm, mv)
+    net = xh * p["bn.gamma"] + p["bn.beta"]
+    net = torch.relu(net)
+    net = conv2d(net, p["out.w"], p["out.b"])
+    return torch.tanh(net)
+
+
+def generator(inputs, y, p, attention_blocks="B3", training=True, new_stats=None, use_style_encoder=False):
+    """make_generator: inputs is a style image batch (fork, Q8) or z (upstream / run_inference.py:35)."""
+    z = style_encoder(inputs, p) if use_style_encoder else inputs
+    return generator_core(z, y, p, attention_blocks, training, new_stats)
+
+
+def recognizer_probs(x, p):
+    """CRNN trunk of make_recognizer (net_architecture.py:28-55); BN in inference mode (Q5).  -> (B, T, C) softmax."""
+    net = torch.relu(conv2d(x, p["conv1.w"], p["conv1.b"]))
+    net = max_pool(net, 2, 2)
+    net = torch.relu(conv2d(net, p["conv2.w"], p["conv2.b"]))
+    net = max_pool(net, 2, 2)
+    net = torch.relu(conv2d(net, p["conv3.w"], p["conv3.b"]))
+    net = torch.relu(conv2d(net, p["conv4.w"], p["conv4.b"]))
+    net = max_pool(net, 2, 1)
+    net = torch.relu(conv2d(net, p["conv5.w"], p["conv5.b"]))
+    net = batchnorm_infer(net, p["bn5.moving_mean"], p["bn5.moving_var"]) * p["bn5.gamma"] + p["bn5.beta"]
+    net = torch.relu(conv2d(net, p["conv6.w"], p["conv6.b"]))
+    net = batchnorm_infer(net, p["bn6.moving_mean"], p["bn6.moving_var"]) * p["bn6.gamma"] + p["bn6.beta"]
+    net = max_pool(net, 2, 1)
+    net = torch.relu(conv2d(net, p["conv7.w"], p["conv7.b"], padding="valid"))
+    net = net.squeeze(1)                                    # (B, T, 512)
+    logits = dense(net, p["dense.w"], p["dense.b"])
+    return torch.softmax(logits, dim=-1)
+
+
+def ctc_batch_cost(y_true: Tensor, y_pred: Tensor, input_length: Tensor, label_length: Tensor) -> Tensor:
+    """tf.keras.backend.ctc_batch_cost (net_architecture.py:57-72): log(y_pred + eps) is fed to tf.nn.ctc_loss,
+    which applies its own softmax; blank = C-1; ctc_merge_repeated=True.  -> (B,1) = -log p(l|x)."""
+    b, t, c = y_pred.shape
+    logp = torch.log_softmax(torch.log(y_pred + KERAS_EPS), dim=-1).permute(1, 0, 2)     # (T, B, C)
+    il = input_length.reshape(-1).long()
+    ll = label_length.reshape(-1).long()
+    loss = F.ctc_loss(logp, y_true.long(), il, ll, blank=c - 1, reduction="none", zero_infinity=False)
+    return loss.view(b, 1)
+
+
+def recognizer(x, labels, input_length, label_length, p):
+    """make_recognizer model output: the CTC loss itself, (B,1)."""
+    return ctc_batch_cost(labels, recognizer_probs(x, p), input_length, label_length)
+
+
+# ----------------------------------------------------------------------------------------------------
+# losses, gradient balancing                                   bigacgan/net_loss.py; data_utils.py:476-490
+# ----------------------------------------------------------------------------------------------------
+def hinge(d_real, d_fake, s_real, s_fake):
+    d_loss_real = torch.relu(1.0 - d_real)
+    d_loss_fake = torch.relu(1.0 + d_fake)
+    s_loss_real = torch.relu(1.0 - s_real)
+    s_loss_fake = torch.relu(1.0 + s_fake)
+    g_loss = -(d_fake + s_fake)
+    return (d_loss_real + d_loss_fake, d_loss_real, d_loss_fake, g_loss,
+            s_loss_real + s_loss_fake, s_loss_real, s_loss_fake)
+
+
+def _sce(logits, label_one: bool):
+    # tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log(1+exp(-|x|))
+    z = 1.0 if label_one else 0.0
+    return torch.clamp(logits, min=0) - logits * z + torch.log1p(torch.exp(-logits.abs()))
+
+
+def not_saturating(d_real, d_fake, s_styleimgs, s_trainingimgs, s_fake):
+    d_loss_real = _sce(d_real, True)
+    d_loss_fake = _sce(d_fake, False)
+    s_style = _sce(s_styleimgs, True)
+    s_iam = _sce(s_trainingimgs, False)
+    g_loss = _sce(d_fake, True) + _sce(s_fake, True)
+    return d_loss_real + d_loss_fake, d_loss_real, d_loss_fake, g_loss, s_style + s_iam, s_style, s_iam
+
+
+def apply_gradient_balancing(r_fake, g_loss, alpha=1.0):
+    """data_utils.py:476-490: population std, no stop_gradient, no zero guard."""
+    r_std = r_fake.std(unbiased=False)
+    g_std = g_loss.std(unbiased=False)
+    r_bal = alpha * ((g_std / r_std) * r_fake)
+    return g_loss + r_bal, r_bal, alpha, r_std, g_std
+
+
+def spectral_norm(w: Tensor, u: Tensor, power_iteration: int = 1) -> Tensor:
+    """arch_ops.py:99-126 with the random u made an explicit input (Q3).  l2_normalize = x*rsqrt(max(sum x^2, 1e-12))."""
+    shape = w.shape
+    w2 = w.reshape(-1, shape[-1])
+
+    def l2n(v):
+        return v * torch.rsqrt(torch.clamp((v * v).sum(), min=1e-12))
+    u_hat, v_hat = u, None
+    for _ in range(power_iteration):
+        v_hat = l2n(u_hat @ w2.t())
+        u_hat = l2n(v_hat @ w2)
+    sigma = (v_hat @ w2) @ u_hat.t()
+    return (w2 / sigma).reshape(shape)
+
+
+# ----------------------------------------------------------------------------------------------------
+# optimizers (Keras semantics)                                                       main.py:25-35
+# ----------------------------------------------------------------------------------------------------
+def adam_update(w, g, m, v, step: int, lr=2e-4, beta1=0.0, beta2=0.999, eps=1e-7):
+    """Keras Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t * m / (sqrt(v) + eps).  step is 1-based."""
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    lr_t = lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
+    return w - lr_t * m / (v.sqrt() + eps), m, v
+
+
+def rmsprop_update(w, g, ms, lr=2e-4, rho=0.9, eps=1e-7):
+    """Keras RMSprop (momentum 0, not centred): ms = rho*ms + (1-rho) g^2; w -= lr * g / (sqrt(ms) + eps)."""
+    ms = rho * ms + (1 - rho) * g * g
+    return w - lr * g / (ms.sqrt() + eps), ms
+
+
+# ----------------------------------------------------------------------------------------------------
+# parameter construction (shapes follow the Keras layers; initialisers per SURVEY Appendix B)
+# ----------------------------------------------------------------------------------------------------
+def _orth(gen, shape, dtype):
+    rows = 1
+    for s in shape[:-1]:
+        rows *= s
+    cols = shape[-1]
+    a = torch.randn(max(rows, cols), min(rows, cols), generator=gen, dtype=torch.float64)
+    q, r = torch.linalg.qr(a)
+    q = q * torch.sign(torch.diagonal(r))
+    if rows < cols:
+        q = q.t()
+    return q.reshape(shape).to(dtype).contiguous()
+
+
+def _glorot(gen, shape, dtype, fan_in=None, fan_out=None):
+    if fan_in is None:
+        rf = 1
+        for s in shape[:-2]:
+            rf *= s
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim).to(dtype)
+
+
+def _attn_params(gen, p, pre, c, dtype, sigma):
+    p[pre + ".theta.w"] = _orth(gen, (1, 1, c, c // 8), dtype)
+    p[pre + ".phi.w"] = _orth(gen, (1, 1, c, c // 8), dtype)
+    p[pre + ".g.w"] = _orth(gen, (1, 1, c, c // 2), dtype)
+    p[pre + ".o.w"] = _orth(gen, (1, 1, c // 2, c), dtype)
+    p[pre + ".sigma"] = torch.tensor(sigma, dtype=dtype)
+
+
+def _down_params(gen, p, prefix, colors, dtype, sigma, attn_block, bias_scale):
+    in_ch, out_ch = get_in_out_channels_disc(colors, 32)
+    for i, (ci, co) in enumerate(zip(in_ch, out_ch)):
+        pre = "{}{}".format(prefix, i + 1)
+        p[pre + ".conv1.w"] = _orth(gen, (3, 3, ci, co), dtype)
+        p[pre + ".conv1.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        p[pre + ".conv2.w"] = _orth(gen, (3, 3, co, co), dtype)
+        p[pre + ".conv2.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        p[pre + ".short.w"] = _orth(gen, (1, 1, ci, co), dtype)
+        p[pre + ".short.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        if pre == attn_block:
+            _attn_params(gen, p, pre + ".attn", co, dtype, sigma)
+
+
+def make_discriminator_params(seed=0, dtype=torch.float64, sigma=0.0, attention_blocks="B1", bias_scale=0.0):
+    """Weights of make_discriminator / make_style_promoter (37 336 384 trainable + attention projections)."""
+    gen = torch.Generator().manual_seed(seed)
+    p: Dict[str, Tensor] = {}
+    _down_params(gen, p, "B", 1, dtype, sigma, attention_blocks if attention_blocks in ("B1", "B2", "B3", "B4") else None,
+                 bias_scale)
+    p["dense.w"] = _orth(gen, (1024, 1), dtype)
+    return p
+
+
+def make_generator_params(seed=0, dtype=torch.float64, sigma=0.0, vocab=52, attention_blocks="B3", bias_scale=0.0,
+                          style_encoder_too=False):
+    gen = torch.Generator().manual_seed(seed)
+    p: Dict[str, Tensor] = {}
+    p["filter_bank"] = _glorot(gen, (vocab, 32, 8192), dtype, fan_in=32 * 8192, fan_out=vocab * 8192)
+    in_ch, out_ch = get_in_out_channels_gen(32)
+    for i, (ci, co) in enumerate(zip(in_ch, out_ch)):
+        pre = "B{}".format(i + 1)
+        for j, c in ((1, ci), (2, co)):
+            p["{}.cbn{}.gamma.w".format(pre, j)] = _orth(gen, (32, c), dtype)
+            p["{}.cbn{}.beta.w".format(pre, j)] = _orth(gen, (32, c), dtype)
+            p["{}.cbn{}.moving_mean".format(pre, j)] = torch.zeros(c, dtype=dtype)
+            p["{}.cbn{}.moving_var".format(pre, j)] = torch.ones(c, dtype=dtype)
+        p[pre + ".up.w"] = _orth(gen, (3, 3, co, ci), dtype)
+        p[pre + ".up.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        p[pre + ".conv.w"] = _orth(gen, (3, 3, co, co), dtype)
+        p[pre + ".conv.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        p[pre + ".short.w"] = _orth(gen, (1, 1, co, ci), dtype)
+        p[pre + ".short.b"] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+        if pre in attention_blocks:
+            _attn_params(gen, p, pre + ".attn", co, dtype, sigma)
+    c = out_ch[-1]
+    p["bn.gamma"] = torch.ones(c, dtype=dtype)
+    p["bn.beta"] = torch.zeros(c, dtype=dtype)
+    p["bn.moving_mean"] = torch.zeros(c, dtype=dtype)
+    p["bn.moving_var"] = torch.ones(c, dtype=dtype)
+    p["out.w"] = _orth(gen, (3, 3, c, 1), dtype)
+    p["out.b"] = torch.randn(1, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+    if style_encoder_too:
+        _down_params(gen, p, "B_style", 1, dtype, sigma, "B_style1", bias_scale)
+        p["style_dense.w"] = _orth(gen, (1024, 128), dtype)
+    return p
+
+
+def make_recognizer_params(seed=0, dtype=torch.float64, output_classes=53, bias_scale=0.0):
+    gen = torch.Generator().manual_seed(seed)
+    p: Dict[str, Tensor] = {}
+    chans = [(1, 64, 3), (64, 128, 3), (128, 256, 3), (256, 256, 3), (256, 512, 3), (512, 512, 3), (512, 512, 2)]
+    for i, (ci, co, k) in enumerate(chans):
+        p["conv{}.w".format(i + 1)] = _glorot(gen, (k, k, ci, co), dtype)
+        p["conv{}.b".format(i + 1)] = torch.randn(co, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+    for n in ("bn5", "bn6"):
+        p[n + ".gamma"] = torch.ones(512, dtype=dtype)
+        p[n + ".beta"] = torch.zeros(512, dtype=dtype)
+        p[n + ".moving_mean"] = torch.zeros(512, dtype=dtype)
+        p[n + ".moving_var"] = torch.ones(512, dtype=dtype)
+    p["dense.w"] = _glorot(gen, (512, output_classes), dtype)
+    p["dense.b"] = torch.randn(output_classes, generator=gen, dtype=torch.float64).to(dtype) * bias_scale
+    return p
+
+
+NON_TRAINABLE_SUFFIXES = (".moving_mean", ".moving_var")
+
+
+def trainable_names(p: Dict[str, Tensor]) -> List[str]:
+    return [k for k in p if not k.endswith(NON_TRAINABLE_SUFFIXES)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# the train step                                                           data_utils.py:358-473
+# ----------------------------------------------------------------------------------------------------
+STAT_NAMES = ("r_loss_fake", "r_loss_real", "r_loss_balanced", "g_loss", "g_loss_added", "g_loss_balanced",
+              "d_loss", "d_loss_real", "d_loss_fake", "g_loss_final", "alpha", "r_loss_fake_std", "g_loss_std",
+              "s_loss", "s_loss_real", "s_loss_fake")
+
+
+def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict], images: Tensor, labels: Tensor,
+               fake_labels: Tensor, z_or_style: Tensor, *, loss_fn: str = "hinge", apply_gradient_balance: bool = True,
+               use_style_encoder: bool = False, use_style_promoter: bool = False, update_g: bool = True,
+               lr: float = 2e-4, beta1: float = 0.0, beta2: float = 0.999, g_attn="B3", d_attn="B1",
+               return_grads: bool = False):
+    """One G + D + R (+ W) step following data_utils.py:385-473.
+
+    params = {"G": {...}, "D": {...}, "R": {...}, ["W": {...}]}; tensors are updated functionally (new dicts
+    are returned).  `z_or_style` is z (B,128) in G+D+R mode (Mode A) or the style-image batch (B,32,160,1)
+    in fork mode (Mode B, use_style_encoder=True).  Returns (stats dict, new params, new opt_state[, grads]).
+    """
+    leaf = {}
+    for net, d in params.items():
+        leaf[net] = {}
+        for k, v in d.items():
+            t = v.detach().clone()
+            if not k.endswith(NON_TRAINABLE_SUFFIXES):
+                t.requires_grad_(True)
+            leaf[net][k] = t
+    G, D, R = leaf["G"], leaf["D"], leaf["R"]
+    Wn = leaf.get("W") if use_style_promoter else None
+    b = images.shape[0]
+    l_r = labels.shape[1]
+    l_f = fake_labels.shape[1]
+    new_stats: Dict[str, Tensor] = {}
+
+    # composite_gan([...], training=True)                                    data_utils.py:399-403
+    gen_images = generator(z_or_style, fake_labels, G, g_attn, True, new_stats, use_style_encoder)
+    d_fake = discriminator(gen_images, D, d_attn)
+    il_f = torch.full((b, 1), 4 * l_f - 1, dtype=torch.long)
+    ll_f = torch.full((b, 1), l_f, dtype=torch.long)
+    r_fake = recognizer(gen_images, fake_labels, il_f, ll_f, R)
+    d_real = discriminator(images, D, d_attn)                                  # :406
+    if Wn is not None:
+        s_fake = discriminator(gen_images, Wn, d_attn)
+        s_real = discriminator(z_or_style, Wn, d_attn)                         # :409
+        s_real_real_imgs = discriminator(images, Wn, d_attn)                   # :410
+    else:
+        s_fake = torch.zeros_like(d_fake)
+        s_real = torch.zeros_like(d_real)
+        s_real_real_imgs = torch.zeros_like(d_real)
+    il_r = torch.full((b, 1), 4 * l_r - 1, dtype=torch.long)
+    ll_r = torch.full((b, 1), l_r, dtype=torch.long)
+    r_real = recognizer(images, labels, il_r, ll_r, R)                         # :413-415
+
+    if loss_fn == "hinge":                                                     # :418 (Q1: 5th arg dropped)
+        d_loss, d_lr, d_lf, g_loss, s_loss, s_l1, s_l2 = hinge(d_real, d_fake, s_real, s_fake)
+        if Wn is None:
+            g_loss = -d_fake
+    else:                                                                      # positional, bug-compatible
+        d_loss, d_lr, d_lf, g_loss, s_loss, s_l1, s_l2 = not_saturating(d_real, d_fake, s_real, s_fake,
+                                                                        s_real_real_imgs)
+        if Wn is None:
+            g_loss = _sce(d_fake, True)
+    if Wn is None:                                                             # G+D+R mode: no style-promoter terms
+        s_loss, s_l1, s_l2 = torch.zeros_like(d_loss), torch.zeros_like(d_loss), torch.zeros_like(d_loss)
+    g_bal, r_bal, alpha, r_std, g_std = apply_gradient_balancing(r_fake, g_loss, 1.0)     # :421
+    g_added = g_loss + r_fake
+    g_final = g_bal if apply_gradient_balance else g_added
+
+    stats = dict(r_loss_fake=r_fake.mean(), r_loss_real=r_real.mean(), r_loss_balanced=r_bal.mean(),
+                 g_loss=g_loss.mean(), g_loss_added=g_added.mean(), g_loss_balanced=g_bal.mean(),
+                 d_loss=d_loss.mean(), d_loss_real=d_lr.mean(), d_loss_fake=d_lf.mean(),
+                 g_loss_final=g_final.mean(), alpha=torch.tensor(float(alpha)), r_loss_fake_std=r_std,
+                 g_loss_std=g_std, s_loss=s_loss.mean(), s_loss_real=s_l1.mean(), s_loss_fake=s_l2.mean())
+    stats = {k: float(v.detach()) for k, v in stats.items()}
+
+    grads: Dict[str, Dict[str, Tensor]] = {}
+
+    def grad_of(target, net):
+        names = [k for k in trainable_names(leaf[net])]
+        gs = torch.autograd.grad(target.sum(), [leaf[net][k] for k in names], retain_graph=True, allow_unused=True)
+        return {k: (g if g is not None else torch.zeros_like(leaf[net][k])) for k, g in zip(names, gs)}
+
+    grads["D"] = grad_of(d_loss, "D")                                          # :449-451  (Q7: sum)
+    grads["R"] = grad_of(r_real, "R")                                          # :453-455
+    if Wn is not None:
+        grads["W"] = grad_of(s_loss, "W")                                      # :457-459
+    if update_g:
+        grads["G"] = grad_of(g_final, "G")                                     # :462-468
+
+    new_params = {net: {k: v.detach().clone() for k, v in d.items()} for net, d in params.items()}
+    new_opt = {}
+    for net in grads:
+        st = opt_state.get(net) or {"step": 0, "m": {}, "v": {}}
+        step = st["step"] + 1
+        nm, nv = {}, {}
+        for k, g in grads[net].items():
+            m0 = st["m"].get(k, torch.zeros_like(g))
+            v0 = st["v"].get(k, torch.zeros_like(g))
+            w1, m1, v1 = adam_update(params[net][k].detach(), g, m0, v0, step, lr, beta1, beta2)
+            new_params[net][k] = w1
+            nm[k], nv[k] = m1, v1
+        new_opt[net] = {"step": step, "m": nm, "v": nv}
+    for net in opt_state:
+        if net not in new_opt:
+            new_opt[net] = opt_state[net]
+    for k, v in new_stats.items():          # G's BN moving statistics
+        new_params["G"][k] = v.detach()
+    out = (stats, new_params, new_opt)
+    if return_grads:
+        extra = dict(gen_images=gen_images.detach(), d_fake=d_fake.detach(), d_real=d_real.detach(),
+                     r_fake=r_fake.detach(), r_real=r_real.detach())
+        out = out + (grads, extra)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# independent (math-only) references used by the KATs
+# ----------------------------------------------------------------------------------------------------
+def ctc_brute_force(probs, labels: Sequence[int], blank: int) -> float:
+    """-log sum over all alignments pi in C^T with B(pi) = labels of prod_t probs[t, pi_t].  T small only."""
+    import itertools
+    t_len, c = probs.shape
+    total = 0.0
+    for path in itertools.product(range(c), repeat=t_len):
+        col, prev = [], None
+        for s in path:
+            if s != prev and s != blank:
+                col.append(s)
+            prev = s
+        if col == list(labels):
+            pr = 1.0
+            for t, s in enumerate(path):
+                pr *= float(probs[t, s])
+            total += pr
+    return -math.log(total)
+
+
+def conv2d_loops(x, w, b, pad_top: int, pad_left: int, out_h: int, out_w: int):
+    """7-loop direct convolution (numpy), stride 1, explicit padding offsets."""
+    import numpy as np
+    n, h, wd, ci = x.shape
+    kh, kw, _, co = w.shape
+    y = np.zeros((n, out_h, out_w, co), dtype=np.float64)
+    for ni in range(n):
+        for oy in range(out_h):
+            for ox in range(out_w):
+                for a in range(kh):
+                    for c in range(kw):
+                        iy, ix = oy + a - pad_top, ox + c - pad_left
+                        if 0 <= iy < h and 0 <= ix < wd:
+                            y[ni, oy, ox, :] += x[ni, iy, ix, :] @ w[a, c]
+    return y + (0 if b is None else b)
