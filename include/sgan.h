@@ -1,0 +1,195 @@
+/* libsgan -- C ABI of the B200-native ScrabbleGAN train-step kernels.
+ *
+ * The reference (UtkuKaradeniz/scrabble-gan) has NO native/FFI layer: its hot path is Python calling
+ * TensorFlow ops.  Every entry point below therefore replaces the TF op(s) a given reference line
+ * dispatches to; the citation after each prototype is `file:line` under /root/reference/src/bigacgan
+ * (SURVEY.md section 2.2 maps K1..K21 to these).  The host side stays Python and binds these with ctypes
+ * (scrabble-gan_b200/_abi.py); see INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless stated.
+ *   - every function returns int: SG_OK (0) or a negative error class; text via sg_last_error().
+ *   - all launches are asynchronous on the context's stream; nothing synchronises except sg_ctx_sync.
+ *   - no hidden allocation: scratch memory is passed in by the caller.
+ *   - layouts are TensorFlow's: activations NHWC contiguous, Conv2D kernels HWIO, Conv2DTranspose
+ *     kernels (kh,kw,Cout,Cin), Dense kernels (in,out), labels int32.
+ *   - "operand" tensors (inputs of convolutions) are SG_F32 or SG_BF16; reductions, residual streams,
+ *     gradients of parameters and optimizer state are always fp32.
+ */
+#ifndef SGAN_H_
+#define SGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sg_ctx sg_ctx;
+
+enum { SG_OK = 0, SG_ERR_ARG = -1, SG_ERR_CUDA = -2, SG_ERR_UNSUPPORTED = -3 };
+enum { SG_F32 = 0, SG_BF16 = 1 };
+#define SG_MAX_TAPS 16
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int sg_version(void);
+const char* sg_last_error(void);
+int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out);
+int sg_ctx_destroy(sg_ctx* ctx);
+int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
+int sg_ctx_sync(sg_ctx* ctx);
+long long sg_ctx_launch_count(sg_ctx* ctx);      /* kernels launched through this context so far */
+
+/* ---- convolution family (K1-K8) ------------------------------------------------------------------
+ * One descriptor covers Conv2D forward, its dgrad (a conv with swapped channel roles), Conv2DTranspose
+ * (phase-decomposed: one call per output phase, strided output placement) and its dgrad (strided input
+ * sampling).  out[n, oy*out_sy+out_py, ox*out_sx+out_px, co] (+)= act( bias[co] +
+ *      sum_t sum_ci in[n, oy*in_sy+tap_dy[t], ox*in_sx+tap_dx[t], ci] * W_t[ci,co] ) * (mask > 0)
+ * with W_t[ci,co] = w_master[tap_w_off[t] + ci*w_ci_stride + co*w_co_stride]; out-of-range input = 0.
+ * Replaces tf Conv2D / Conv2DBackpropInput / Conv2DTranspose: resnet_ops.py:57,65,69,98,103,109;
+ * net_architecture.py:28-49,283; arch_ops.py:38-65. */
+typedef struct sg_conv_desc {
+  int n;
+  int in_h, in_w, c_in;
+  int out_h, out_w, c_out;
+  int grid_h, grid_w;
+  int in_sy, in_sx;
+  int out_sy, out_sx, out_py, out_px;
+  int ntaps;
+  int tap_dy[SG_MAX_TAPS];
+  int tap_dx[SG_MAX_TAPS];
+  long long tap_w_off[SG_MAX_TAPS];
+  long long w_ci_stride, w_co_stride;
+  int in_dt, out_dt;
+  int relu;
+  int accumulate;
+  int mask_dt;
+} sg_conv_desc;
+
+/* exact-fp32 direct convolution (any shape; used for Cin=1 / Cout=1 edge layers and as the fp32 mode) */
+int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const float* w_master,
+                     const float* bias, const void* mask, void* out);
+/* filter gradient of the conv described by d: dw_master[tap_w_off[t] + ci*.. + co*..] += sum in * dy.
+ * `dy` is indexed like `out` (dtype d->out_dt).  Replaces Conv2DBackpropFilter (tapes, data_utils.py:450-467). */
+int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master);
+
+/* tcgen05/TMEM/TMA implicit-GEMM path (operands bf16 or fp32-as-tf32, fp32 accumulate in TMEM) */
+int sg_conv_tc_supported(const sg_conv_desc* d);
+size_t sg_conv_packed_weight_elems(const sg_conv_desc* d);     /* c_out * ntaps * c_in */
+int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_master, void* w_packed);
+int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
+                   const float* bias, const void* mask, void* out);
+size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms);
+int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master,
+                     void* workspace, size_t workspace_bytes);
+
+/* ---- element-wise glue --------------------------------------------------------------------------- */
+/* relu_out = relu(x), copy_out = x, both cast to out_dt (either may be NULL).  resnet_ops.py:97,101 */
+int sg_act_prep(sg_ctx* ctx, const float* x, long long n, void* relu_out, void* copy_out, int out_dt);
+/* out (+)= dy * (act > 0)   (ReLU backward) */
+int sg_mask_mul(sg_ctx* ctx, const float* dy, const void* act, int act_dt, void* out, int out_dt,
+                long long n, int accumulate);
+/* out = a*x + b*y (y may be NULL)   -- residual adds, resnet_ops.py:73,114 */
+int sg_axpby(sg_ctx* ctx, float a, const float* x, float b, const float* y, float* out, long long n);
+/* out = (*sigma)*a + x  (x may be NULL => out = sigma*a)   -- arch_ops.py:67 */
+int sg_scale_add(sg_ctx* ctx, const float* sigma, const float* a, const float* x, float* out, long long n);
+int sg_tanh_fwd(sg_ctx* ctx, const float* x, float* y, long long n);                  /* net_architecture.py:289 */
+int sg_tanh_bwd(sg_ctx* ctx, const float* dy, const float* y, float* dx, long long n);
+/* x[r, :] *= w[r] */
+int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long cols);
+/* out[0] (+)= sum a*b */
+int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out, int accumulate);
+/* out[c] (+)= sum_r x[r,c]   (bias gradients) */
+int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, float* out, int accumulate);
+int sg_cast(sg_ctx* ctx, const float* x, void* out, int out_dt, long long n);
+
+/* ---- pooling (K11) ------------------------------------------------------------------------------- */
+int sg_avgpool2_fwd(sg_ctx* ctx, const float* x, int n, int h, int w, int c, float* out);   /* resnet_ops.py:106,113 */
+int sg_avgpool2_bwd(sg_ctx* ctx, const float* dout, int n, int h, int w, int c, void* dx, int dx_dt);
+int sg_maxpool_fwd(sg_ctx* ctx, const void* x, int dt, int n, int h, int w, int c, int ph, int pw,
+                   void* out);                                                          /* net_architecture.py:29-47; arch_ops.py:47,58 */
+int sg_maxpool_bwd(sg_ctx* ctx, const float* dout, const void* x, int x_dt, int n, int h, int w, int c,
+                   int ph, int pw, int relu_mask, void* dx, int dx_dt);
+int sg_gap_relu_fwd(sg_ctx* ctx, const float* x, int n, long long hw, int c, float* out);   /* net_architecture.py:249-250,340-341 */
+int sg_gap_relu_bwd(sg_ctx* ctx, const float* dfeat, const float* x, int n, long long hw, int c, float* dx);
+
+/* ---- batch norm / conditional batch norm (K9, K10) ------------------------------------------------
+ * resnet_ops.py:13-28 (CBN), net_architecture.py:42,46,281 (BN).  Statistics are exchanged as raw sums
+ * so that the caller can all-reduce them across data-parallel replicas between the two calls. */
+size_t sg_bn_stats_scratch_bytes(long long rows, int c);
+int sg_bn_stats(sg_ctx* ctx, const float* x, long long rows, int c, float* sums /*[2c]*/, void* scratch,
+                size_t scratch_bytes);
+int sg_bn_finalize(sg_ctx* ctx, const float* sums, double count, int c, float eps, float momentum,
+                   float* mean, float* rstd, float* moving_mean, float* moving_var);
+int sg_bn_infer_prepare(sg_ctx* ctx, const float* moving_mean, const float* moving_var, int c, float eps,
+                        float* mean, float* rstd);
+/* out = act( (x-mean)*rstd*gamma + beta ); gamma/beta are [n,c] (gb_stride=c) or [c] (gb_stride=0), NULL => 1 / 0 */
+int sg_bn_apply(sg_ctx* ctx, const float* x, int n, long long hw, int c, const float* mean,
+                const float* rstd, const float* gamma, const float* beta, long long gb_stride, int relu,
+                void* out, int out_dt);
+/* s1[n,c] = sum_hw dyr, s2[n,c] = sum_hw dyr*xhat, dyr = dy*(act>0) (act NULL => no mask) */
+int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, const float* x, int n,
+                     long long hw, int c, const float* mean, const float* rstd, float* s1, float* s2);
+/* ab[0:c] = sum_n gamma*s1, ab[c:2c] = sum_n gamma*s2  (per-channel terms of the BN backward; all-reduce me) */
+int sg_bn_bwd_combine(sg_ctx* ctx, const float* s1, const float* s2, const float* gamma,
+                      long long gb_stride, int n, int c, float* ab);
+/* dx (+)= rstd*(gamma*dyr - [ab0 + xhat*ab1]/count) [* (x > 0) if mask_by_x]
+ * (batch terms dropped when use_batch_terms==0: inference-mode BN) */
+int sg_bn_bwd_apply(sg_ctx* ctx, const float* dy, const void* act, int act_dt, const float* x, int n,
+                    long long hw, int c, const float* mean, const float* rstd, const float* gamma,
+                    long long gb_stride, const float* ab, double count, int use_batch_terms, int mask_by_x,
+                    void* dx, int dx_dt, int accumulate);
+
+/* ---- small dense GEMM (K14): C (+)= op(A) op(B) + bias;  row-major, fp32 -------------------------- */
+int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, const float* a, int lda,
+            const float* b, int ldb, float* c, int ldc, const float* bias, int accumulate);
+
+/* ---- filter bank (K13) -- arch_ops.py:84-90; net_architecture.py:230-231,260-271 ------------------
+ * out[b, k%4, 4l + k/2048, (k%2048)/4] = sum_j z[b*z_stride + j] * bank[y[b,l], j, k]   (bit-exact index map) */
+int sg_filterbank_fwd(sg_ctx* ctx, const float* z, int z_stride, const int* y, int b, int l, int vocab,
+                      const float* bank, float* out);
+int sg_filterbank_bwd(sg_ctx* ctx, const float* dout, const float* z, int z_stride, const int* y, int b,
+                      int l, int vocab, const float* bank, float* dbank, float* dz0 /*[b,32] or NULL*/);
+
+/* ---- non-local block core (K12) -- arch_ops.py:51-61: o = softmax(theta phi^T) g, no scaling ------- */
+int sg_attn_fwd(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv,
+                int dk, int dv, float* o, float* lse);
+int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* g, const float* o,
+                const float* lse, const float* d_o, int n, int q, int kv, int dk, int dv, float* dtheta,
+                float* dphi, float* dg);
+
+/* ---- CTC (K15) -- net_architecture.py:55-72: softmax -> log(p+1e-7) -> tf.nn.ctc_loss --------------
+ * loss[b] = -log p(labels_b | x_b); grad_logits = d loss / d (Dense pre-activations), blank = c-1 */
+int sg_ctc(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, float* loss,
+           float* grad_logits);
+
+/* ---- GAN losses + gradient balancing (K16, K17) -- net_loss.py:4-54; data_utils.py:418-442,476-490 --
+ * sums is double[SG_LOSS_NSUMS]; all-reduce it across replicas between the two calls. */
+#define SG_LOSS_NSUMS 16
+#define SG_LOSS_NSTATS 16
+enum { SG_LOSS_HINGE = 0, SG_LOSS_NOT_SATURATING = 1 };
+int sg_loss_sums(sg_ctx* ctx, int kind, int use_w, const float* d_real, const float* d_fake,
+                 const float* s_real, const float* s_fake, const float* s_slot5, const float* r_fake,
+                 const float* r_real, int b, double* sums);
+/* up_*: per-sample upstream weights d(sum target)/d(logit) for each backward pass; stats: the 16-tuple
+ * returned by train_step (data_utils.py:470-473 order). */
+int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, const float* d_real,
+                   const float* d_fake, const float* s_real, const float* s_fake, const float* s_slot5,
+                   const float* r_fake, int b, const double* sums, float* up_d_real, float* up_d_fake_d,
+                   float* up_s_real, float* up_s_fake_w, float* up_s_slot5, float* up_d_fake_g,
+                   float* up_s_fake_g, float* up_r_fake_g, float* stats);
+
+/* ---- optimizers (K19) -- main.py:25-35: Keras Adam / RMSprop --------------------------------------- */
+int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t,
+            float beta1, float beta2, float eps);
+int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps);
+
+/* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */
+int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
+                     float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGAN_H_ */

@@ -1,0 +1,278 @@
+// Exact-fp32 direct convolution family on the FFMA pipe (generic sg_conv_desc; see include/sgan.h).
+// Used for (a) the edge layers that are not tensor-core shaped (K8: Cin=1 first convs, Cout=1 output conv,
+// the C/8-channel attention projections) and (b) the "fp32" parity mode of the whole network.
+// Reference ops replaced: Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter / Conv2DTranspose
+// (resnet_ops.py:57,65,69,98,103,109; net_architecture.py:28-49,283).
+// Implicit GEMM with 64 x TN x 16 shared-memory tiles; K is the flattened (tap, ci) index so that Cin=1
+// layers (K = 9) do not waste a 16-wide chunk per tap.
+#include "common.cuh"
+
+#define CS_TM 64
+#define CS_TK 16
+
+__device__ __forceinline__ float ld_any(const void* p, long long i, int dt) {
+  return dt == SG_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, long long i, int dt, float v) {
+  if (dt == SG_F32) reinterpret_cast<float*>(p)[i] = v;
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward.  M = n*grid_h*grid_w output positions, N = c_out, K = ntaps*c_in.
+// TN = 64: thread (tx,ty) computes 4 rows x 4 cols;  TN = 16: 4 rows x 1 col.
+// ---------------------------------------------------------------------------------------------------
+template <int TN, int RN>
+__global__ void __launch_bounds__(256) k_conv_fwd_simt(sg_conv_desc d, const void* __restrict__ in,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const void* __restrict__ mask, void* __restrict__ out) {
+  __shared__ float As[CS_TK][CS_TM + 4];
+  __shared__ float Bs[CS_TK][TN + 4];
+  constexpr int TX = TN / RN;                  // threads along N (16)
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;      // ty in [0,16)
+  const long long M = (long long)d.n * d.grid_h * d.grid_w;
+  const int K = d.ntaps * d.c_in;
+  const long long m0 = (long long)blockIdx.x * CS_TM;
+  const int n0 = blockIdx.y * TN;
+
+  float acc[4][RN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+
+  // each thread loads 4 A elements per chunk: fixed (row, k-offset) assignment -> decode the pixel once
+  // assignment: idx = tid + i*256, kk = idx % 16, mm = idx / 16  => mm = tid/16 + 16*i, kk = tid%16
+  const int a_kk = tid % CS_TK;
+  int a_n[4], a_y[4], a_x[4];
+  bool a_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long gm = m0 + tid / CS_TK + 16 * i;
+    a_ok[i] = gm < M;
+    long long g = a_ok[i] ? gm : 0;
+    a_x[i] = (int)(g % d.grid_w);
+    g /= d.grid_w;
+    a_y[i] = (int)(g % d.grid_h);
+    a_n[i] = (int)(g / d.grid_h);
+  }
+
+  for (int k0 = 0; k0 < K; k0 += CS_TK) {
+    {
+      int gk = k0 + a_kk;
+      bool kok = gk < K;
+      int t = kok ? gk / d.c_in : 0, ci = kok ? gk % d.c_in : 0;
+      int dy = d.tap_dy[t], dx = d.tap_dx[t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+        if (kok && a_ok[i]) {
+          int iy = a_y[i] * d.in_sy + dy, ix = a_x[i] * d.in_sx + dx;
+          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
+            v = ld_any(in, (((long long)a_n[i] * d.in_h + iy) * d.in_w + ix) * d.c_in + ci, d.in_dt);
+        }
+        As[a_kk][tid / CS_TK + 16 * i] = v;
+      }
+    }
+    for (int idx = tid; idx < CS_TK * TN; idx += 256) {
+      int nn = idx % TN, kk = idx / TN;
+      int gk = k0 + kk, gn = n0 + nn;
+      float v = 0.f;
+      if (gk < K && gn < d.c_out) {
+        int t = gk / d.c_in, ci = gk % d.c_in;
+        v = w[d.tap_w_off[t] + (long long)ci * d.w_ci_stride + (long long)gn * d.w_co_stride];
+      }
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CS_TK; ++kk) {
+      float a[4], b[RN];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < RN; ++j) b[j] = Bs[kk][tx * RN + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+    long long g = gm;
+    int ox = (int)(g % d.grid_w);
+    g /= d.grid_w;
+    int oy = (int)(g % d.grid_h);
+    int ni = (int)(g / d.grid_h);
+    long long base = (((long long)ni * d.out_h + oy * d.out_sy + d.out_py) * d.out_w + ox * d.out_sx + d.out_px) * d.c_out;
+#pragma unroll
+    for (int j = 0; j < RN; ++j) {
+      int gn = n0 + tx * RN + j;
+      if (gn >= d.c_out) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (d.relu) v = fmaxf(v, 0.f);
+      if (mask) v = ld_any(mask, base + gn, d.mask_dt) > 0.f ? v : 0.f;
+      if (d.accumulate) v += ld_any(out, base + gn, d.out_dt);
+      st_any(out, base + gn, d.out_dt, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// filter gradient.  M' = ntaps*c_in (flattened k index), N = c_out, reduction over output positions,
+// split across gridDim.z with atomicAdd into dw (dw is accumulated into: caller zeroes it).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const void* __restrict__ in,
+                                                          const void* __restrict__ dy, float* __restrict__ dw,
+                                                          long long pos_per_split) {
+  __shared__ float As[CS_TK][CS_TM + 4];   // [pos][kflat]
+  __shared__ float Bs[CS_TK][64 + 4];      // [pos][co]
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const long long P = (long long)d.n * d.grid_h * d.grid_w;
+  const int KF = d.ntaps * d.c_in;
+  const int kf0 = blockIdx.x * CS_TM;
+  const int n0 = blockIdx.y * 64;
+  const long long pbeg = (long long)blockIdx.z * pos_per_split;
+  const long long pend = pbeg + pos_per_split < P ? pbeg + pos_per_split : P;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // A loads: idx = tid + i*256 -> kf = idx % 64, pp = idx / 64 (4 positions per thread, fixed kf)
+  const int a_kf = tid % CS_TM;
+  const int gkf = kf0 + a_kf;
+  const bool kf_ok = gkf < KF;
+  const int a_t = kf_ok ? gkf / d.c_in : 0, a_ci = kf_ok ? gkf % d.c_in : 0;
+  const int a_dy = d.tap_dy[a_t], a_dx = d.tap_dx[a_t];
+
+  for (long long p0 = pbeg; p0 < pend; p0 += CS_TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int pp = tid / CS_TM + 4 * i;
+      long long gp = p0 + pp;
+      float v = 0.f;
+      if (kf_ok && gp < pend) {
+        long long g = gp;
+        int ox = (int)(g % d.grid_w);
+        g /= d.grid_w;
+        int oy = (int)(g % d.grid_h);
+        int ni = (int)(g / d.grid_h);
+        int iy = oy * d.in_sy + a_dy, ix = ox * d.in_sx + a_dx;
+        if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
+          v = ld_any(in, (((long long)ni * d.in_h + iy) * d.in_w + ix) * d.c_in + a_ci, d.in_dt);
+      }
+      As[pp][a_kf] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int nn = idx % 64, pp = idx / 64;
+      long long gp = p0 + pp;
+      int gn = n0 + nn;
+      float v = 0.f;
+      if (gp < pend && gn < d.c_out) {
+        long long g = gp;
+        int ox = (int)(g % d.grid_w);
+        g /= d.grid_w;
+        int oy = (int)(g % d.grid_h);
+        int ni = (int)(g / d.grid_h);
+        v = ld_any(dy, (((long long)ni * d.out_h + oy * d.out_sy + d.out_py) * d.out_w + ox * d.out_sx + d.out_px) * d.c_out + gn,
+                   d.out_dt);
+      }
+      Bs[pp][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CS_TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kf = kf0 + ty * 4 + i;
+    if (kf >= KF) continue;
+    int t = kf / d.c_in, ci = kf % d.c_in;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= d.c_out) continue;
+      atomicAdd(dw + d.tap_w_off[t] + (long long)ci * d.w_ci_stride + (long long)gn * d.w_co_stride, acc[i][j]);
+    }
+  }
+}
+
+static int check_desc(const sg_conv_desc* d, const char* who) {
+  SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
+  SG_REQUIRE(d->n >= 0 && d->in_h > 0 && d->in_w > 0 && d->c_in > 0 && d->out_h > 0 && d->out_w > 0 && d->c_out > 0,
+             "%s: bad tensor dims", who);
+  SG_REQUIRE(d->grid_h > 0 && d->grid_w > 0 && d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "%s: bad grid/taps", who);
+  SG_REQUIRE(d->in_sy >= 1 && d->in_sx >= 1 && d->out_sy >= 1 && d->out_sx >= 1, "%s: bad strides", who);
+  SG_REQUIRE((d->grid_h - 1) * d->out_sy + d->out_py < d->out_h && (d->grid_w - 1) * d->out_sx + d->out_px < d->out_w &&
+                 d->out_py >= 0 && d->out_px >= 0,
+             "%s: output placement exceeds the output tensor", who);
+  SG_REQUIRE((d->in_dt == SG_F32 || d->in_dt == SG_BF16) && (d->out_dt == SG_F32 || d->out_dt == SG_BF16), "%s: bad dtype", who);
+  return SG_OK;
+}
+
+extern "C" {
+
+int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const float* w_master, const float* bias,
+                     const void* mask, void* out) {
+  SG_REQUIRE(ctx && in && w_master && out, "sg_conv_fwd_simt: NULL");
+  int rc = check_desc(d, "sg_conv_fwd_simt");
+  if (rc != SG_OK) return rc;
+  long long M = (long long)d->n * d->grid_h * d->grid_w;
+  if (M == 0) return SG_OK;
+  if (d->c_out > 16) {
+    dim3 grid(sg_div_up(M, CS_TM), sg_div_up(d->c_out, 64));
+    k_conv_fwd_simt<64, 4><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
+  } else {
+    dim3 grid(sg_div_up(M, CS_TM), 1);
+    k_conv_fwd_simt<16, 1><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
+  }
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master) {
+  SG_REQUIRE(ctx && in && dy && dw_master, "sg_conv_wgrad_simt: NULL");
+  int rc = check_desc(d, "sg_conv_wgrad_simt");
+  if (rc != SG_OK) return rc;
+  long long P = (long long)d->n * d->grid_h * d->grid_w;
+  if (P == 0) return SG_OK;
+  int gx = sg_div_up(d->ntaps * d->c_in, CS_TM), gy = sg_div_up(d->c_out, 64);
+  long long tiles = (long long)gx * gy;
+  long long splits = (2LL * ctx->num_sms + tiles - 1) / tiles;
+  long long max_splits = (P + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long pps = ((P + splits - 1) / splits + CS_TK - 1) / CS_TK * CS_TK;
+  splits = (P + pps - 1) / pps;
+  dim3 grid(gx, gy, (unsigned)splits);
+  k_conv_wgrad_simt<<<grid, 256, 0, ctx->stream>>>(*d, in, dy, dw_master, pps);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,840 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (K1-K7: the >=99% of step FLOPs).
+//
+// Reference ops replaced: Conv2D, Conv2DBackpropInput, Conv2DBackpropFilter, Conv2DTranspose as dispatched by
+// resnet_ops.py:57,65,69,98,103,109 and net_architecture.py:28-49.
+//
+// Forward-type kernel (also serves dgrad and the transposed convs through the generic sg_conv_desc):
+//   D[128 pixels, BN channels] = sum over (tap, 128-byte channel chunk) A_tap[128 pixels, KC] * W[BN, KC]^T
+//   * A tile: ONE 4-D tiled TMA box (KC channels x TW x TH x TN pixels) per k-block, at the tap-shifted
+//     coordinate; out-of-image pixels (SAME padding halo, ragged edges) are zero-filled by the TMA unit, so
+//     there is no im2col buffer and no predication in the main loop.  Strided sampling (transposed-conv
+//     dgrad) uses one tensor map per sampling phase.
+//   * B tile: 2-D TMA box of the pre-packed K-major weight matrix [c_out][ntaps*c_in].
+//   * both tiles land in 128B-swizzled shared memory and are consumed by tcgen05.mma (cta_group::1,
+//     M=128, N=BN<=256, K=32 bytes) issued by one thread; fp32 accumulators live in TMEM, double-buffered so
+//     the epilogue of tile i overlaps the main loop of tile i+1.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (tcgen05.ld -> bias / ReLU / mask / accumulate -> vectorised global stores, NHWC, optional strided
+//     placement for transposed-conv phases).
+//   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule, N-tile fastest so that CTAs
+//     running concurrently share the same activation tile through L2.
+// Filter-gradient kernel: D[128 c_out, BN c_in] += dy_tile^T[128, P] * in_tile[P, BN] with BOTH operands
+// MN-major (pixels are the reduction dim and the slow smem dim), split over pixel ranges with fp32 red.add.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) __trap();     // a protocol bug must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 @4, a/b format @7/@10 (BF16=1, TF32=2),
+// a_major @15, b_major @16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24
+__host__ __device__ inline uint32_t make_idesc(bool tf32, bool a_mn, bool b_mn, int m, int n) {
+  uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+#define TC_MAX_STAGES 8
+#define TC_THREADS 192
+#define TC_TMEM_COLS 512
+
+// ---------------------------------------------------------------------------------------------------
+// forward-type kernel
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) TcFwdParams {
+  CUtensorMap map_a[4];
+  CUtensorMap map_b;
+  int tap_view[SG_MAX_TAPS], tap_oy[SG_MAX_TAPS], tap_ox[SG_MAX_TAPS];
+  int ntaps, c_in, c_out, n, grid_h, grid_w;
+  int out_h, out_w, out_sy, out_sx, out_py, out_px;
+  int TW, TH, TN, tiles_x, tiles_y, tiles_n, tiles_col, BN;
+  int kc_per_tap, stages;
+  uint32_t a_bytes, b_bytes, a_stage_stride, b_stage_stride;
+  int relu, accumulate, out_dt, mask_dt;
+  const float* bias;
+  const void* mask;
+  void* out;
+};
+
+template <typename TIn>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcFwdParams p) {
+  constexpr bool kTf32 = sizeof(TIn) == 4;
+  constexpr int KC = 128 / sizeof(TIn);            // elements per 128-byte swizzle row
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_stage_stride;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.map_a[v]);
+    tma_prefetch_desc(&p.map_b);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = m_tiles * p.tiles_col;
+  const int nkb = p.ntaps * p.kc_per_tap;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
+        int tx = mt % p.tiles_x;
+        int r = mt / p.tiles_x;
+        int ty = r % p.tiles_y, tn = r / p.tiles_y;
+        int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, col0 = col_t * p.BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const CUtensorMap* ma = &p.map_a[p.tap_view[t]];
+          int cx = x0 + p.tap_ox[t], cy = y0 + p.tap_oy[t];
+          for (int c = 0; c < p.kc_per_tap; ++c) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+            tma_load_4d(a_base + s * p.a_stage_stride, ma, bar_full + 8 * s, c * KC, cx, cy, n0);
+            tma_load_2d(b_base + s * p.b_stage_stride, &p.map_b, bar_full + 8 * s, t * p.c_in + c * KC, col0);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(kTf32, false, false, 128, p.BN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          uint64_t da = make_smem_desc(a_base + s * p.a_stage_stride, 16, 1024);
+          uint64_t db = make_smem_desc(b_base + s * p.b_stage_stride, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)      // 4 x 32 bytes of K per 128-byte swizzle row
+            umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+          if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;           // accumulator row = pixel index inside the tile
+    const int rows_in_tile = p.TW * p.TH * p.TN;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
+      int tx = mt % p.tiles_x;
+      int r = mt / p.tiles_x;
+      int ty = r % p.tiles_y, tn = r / p.tiles_y;
+      int ln = row / (p.TH * p.TW), rem = row % (p.TH * p.TW);
+      int ly = rem / p.TW, lx = rem % p.TW;
+      int ni = tn * p.TN + ln, oy = ty * p.TH + ly, ox = tx * p.TW + lx;
+      bool valid = row < rows_in_tile && ni < p.n && oy < p.grid_h && ox < p.grid_w;
+      long long base = 0;
+      if (valid)
+        base = (((long long)ni * p.out_h + oy * p.out_sy + p.out_py) * p.out_w + ox * p.out_sx + p.out_px) * p.c_out +
+               col_t * p.BN;
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
+      for (int ch = 0; ch < p.BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float* bp = p.bias + col_t * p.BN + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(bp + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          long long off = base + ch * 32;
+          if (p.mask) {
+            if (p.mask_dt == SG_F32) {
+              const float* mp = reinterpret_cast<const float*>(p.mask) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 m = sg_ld4(mp + j);
+                f[j] = m.x > 0.f ? f[j] : 0.f; f[j + 1] = m.y > 0.f ? f[j + 1] : 0.f;
+                f[j + 2] = m.z > 0.f ? f[j + 2] : 0.f; f[j + 3] = m.w > 0.f ? f[j + 3] : 0.f;
+              }
+            } else {
+              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 m = sg_ld4(mp + j);
+                f[j] = m.x > 0.f ? f[j] : 0.f; f[j + 1] = m.y > 0.f ? f[j + 1] : 0.f;
+                f[j + 2] = m.z > 0.f ? f[j + 2] : 0.f; f[j + 3] = m.w > 0.f ? f[j + 3] : 0.f;
+              }
+            }
+          }
+          if (p.out_dt == SG_F32) {
+            float* op = reinterpret_cast<float*>(p.out) + off;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = sg_ld4(op + j);
+                f[j] += o.x; f[j + 1] += o.y; f[j + 2] += o.z; f[j + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) sg_st4(op + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) sg_st4(op + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * as);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// filter-gradient kernel
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) TcWgradParams {
+  CUtensorMap map_dy;           // phase view of dy selected by (out_py, out_px, out_sy, out_sx)
+  CUtensorMap map_in[4];        // sampling-phase views of the layer input
+  int tap_view[SG_MAX_TAPS], tap_oy[SG_MAX_TAPS], tap_ox[SG_MAX_TAPS];
+  long long tap_w_off[SG_MAX_TAPS];
+  long long w_ci_stride, w_co_stride;
+  int ntaps, c_in, c_out;
+  int TW, TH, TN, tiles_x, tiles_y, tiles_n;      // pixel boxes; PR = TW*TH*TN pixels per k-block
+  int co_tiles, ci_tiles, BN, splits, ptiles_per_split;
+  int a_chunks, b_chunks, stages;
+  uint32_t chunk_bytes, stage_stride;
+  float* dw;
+};
+
+template <typename TIn>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constant__ TcWgradParams p) {
+  constexpr bool kTf32 = sizeof(TIn) == 4;
+  constexpr int KC = 128 / sizeof(TIn);
+  constexpr int UK = 32 / sizeof(TIn);             // pixels consumed per tcgen05.mma
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_dy);
+    for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.map_in[v]);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int units = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+  const int PR = p.TW * p.TH * p.TN;
+
+  // unit -> (split fastest, then ci tile, co tile, tap)
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int sp = u % p.splits, r = u / p.splits;
+        int cit = r % p.ci_tiles; r /= p.ci_tiles;
+        int cot = r % p.co_tiles;
+        int t = r / p.co_tiles;
+        int pt0 = sp * p.ptiles_per_split, pt1 = pt0 + p.ptiles_per_split;
+        if (pt1 > ptiles) pt1 = ptiles;
+        const CUtensorMap* mi = &p.map_in[p.tap_view[t]];
+        for (int pt = pt0; pt < pt1; ++pt) {
+          int tx = pt % p.tiles_x, q = pt / p.tiles_x;
+          int ty = q % p.tiles_y, tn = q / p.tiles_y;
+          int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, (p.a_chunks + p.b_chunks) * p.chunk_bytes);
+          uint32_t dst = smem_base + s * p.stage_stride;
+          for (int j = 0; j < p.a_chunks; ++j)
+            tma_load_4d(dst + j * p.chunk_bytes, &p.map_dy, bar_full + 8 * s, cot * 128 + j * KC, x0, y0, n0);
+          dst += p.a_chunks * p.chunk_bytes;
+          for (int j = 0; j < p.b_chunks; ++j)
+            tma_load_4d(dst + j * p.chunk_bytes, mi, bar_full + 8 * s, cit * p.BN + j * KC, x0 + p.tap_ox[t], y0 + p.tap_oy[t], n0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(kTf32, true, true, 128, p.BN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int sp = u % p.splits;
+      int pt0 = sp * p.ptiles_per_split, pt1 = pt0 + p.ptiles_per_split;
+      if (pt1 > ptiles) pt1 = ptiles;
+      mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t a_addr = smem_base + s * p.stage_stride;
+          uint32_t b_addr = a_addr + p.a_chunks * p.chunk_bytes;
+          // MN-major, 128B swizzle: LBO = distance between 128-byte channel chunks, SBO = 8 pixel rows = 1024 B
+          uint64_t da = make_smem_desc(a_addr, p.chunk_bytes, 1024);
+          uint64_t db = make_smem_desc(b_addr, p.chunk_bytes, 1024);
+          const int ksteps = PR / UK;
+          const uint32_t kadv = (UK * 128) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma<kTf32>(d_tmem, da + (uint64_t)(k * kadv), db + (uint64_t)(k * kadv), idesc, (pt != pt0 || k != 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+          if (pt == pt1 - 1) umma_commit(bar_tfull + 8 * as);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;           // accumulator row = output channel inside the co tile
+    int as = 0;
+    uint32_t aph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int r = u / p.splits;
+      int cit = r % p.ci_tiles; r /= p.ci_tiles;
+      int cot = r % p.co_tiles;
+      int t = r / p.co_tiles;
+      int co = cot * 128 + row;
+      bool valid = co < p.c_out;
+      float* wbase = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride;
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
+      for (int ch = 0; ch < p.BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (valid) {
+          int ci0 = cit * p.BN + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int ci = ci0 + j;
+            if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * as);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing: w_packed[co][t*c_in + ci] = cast(w_master[tap_w_off[t] + ci*s_ci + co*s_co])
+// ---------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void k_pack_weights(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  const long long ktot = (long long)d.ntaps * d.c_in;
+  const long long total = ktot * d.c_out;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int co = (int)(i / ktot);
+    int k = (int)(i % ktot);
+    int t = k / d.c_in, ci = k % d.c_in;
+    sg_st(out + i, w[d.tap_w_off[t] + (long long)ci * d.w_ci_stride + (long long)co * d.w_co_stride]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(sg_ctx* ctx, PFN_encodeTiled* fn) {
+  if (!ctx->encode_tiled) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    SG_REQUIRE(f != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    ctx->encode_tiled = f;
+  }
+  *fn = (PFN_encodeTiled)ctx->encode_tiled;
+  return SG_OK;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int posmod(int a, int b) { return a - floordiv(a, b) * b; }
+
+// 4-D NHWC view (optionally a stride-phase view): dims {c, wv, hv, n}
+static int encode_nhwc_view(PFN_encodeTiled enc, CUtensorMap* m, int dt, const void* base, int n, int h, int w, int c, int sy,
+                            int sx, int py, int px, int box_c, int box_w, int box_h, int box_n) {
+  size_t e = dt == SG_F32 ? 4 : 2;
+  int hv = (h - py + sy - 1) / sy, wv = (w - px + sx - 1) / sx;
+  if (hv < 1) hv = 1;
+  if (wv < 1) wv = 1;
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)wv, (cuuint64_t)hv, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)sx * c * e, (cuuint64_t)sy * w * c * e, (cuuint64_t)h * w * c * e};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const char* addr = (const char*)base + ((size_t)py * w + px) * c * e;
+  CUresult r = enc(m, dt == SG_F32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)addr, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("cuTensorMapEncodeTiled(4d) failed: %d (dims %d,%d,%d,%d box %d,%d,%d,%d)", (int)r, c, wv, hv, n, box_c, box_w,
+                 box_h, box_n);
+    return SG_ERR_CUDA;
+  }
+  return SG_OK;
+}
+
+static int encode_2d(PFN_encodeTiled enc, CUtensorMap* m, int dt, const void* base, long long inner, long long outer, int box_in,
+                     int box_out) {
+  size_t e = dt == SG_F32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)inner * e};
+  cuuint32_t box[2] = {(cuuint32_t)box_in, (cuuint32_t)box_out};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dt == SG_F32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("cuTensorMapEncodeTiled(2d) failed: %d (dims %lld,%lld box %d,%d)", (int)r, inner, outer, box_in, box_out);
+    return SG_ERR_CUDA;
+  }
+  return SG_OK;
+}
+
+// choose a pixel box TW x TH x TN (<= max_rows pixels, product a multiple of `mult`) minimising the padded MMA
+// work.  Boxes may overhang the image: the overhang is TMA zero-fill on load and predicated off on store.
+static void choose_box(int gw, int gh, int n, int max_rows, int mult, int* TW, int* TH, int* TN) {
+  struct Key { int gw, gh, n, mr, mu, tw, th, tn; };
+  static thread_local Key cache[64];
+  static thread_local int cache_n = 0;
+  for (int i = 0; i < cache_n; ++i)
+    if (cache[i].gw == gw && cache[i].gh == gh && cache[i].n == n && cache[i].mr == max_rows && cache[i].mu == mult) {
+      *TW = cache[i].tw; *TH = cache[i].th; *TN = cache[i].tn;
+      return;
+    }
+  long long best = -1;
+  int bw = mult, bh = 1, bn = 1;
+  int last_tw = -1;
+  for (int kx = 1; kx <= gw; ++kx) {
+    int tw = (gw + kx - 1) / kx;
+    if (tw == last_tw) continue;
+    last_tw = tw;
+    if (tw > max_rows || tw > 256) continue;
+    int last_th = -1;
+    for (int ky = 1; ky <= gh; ++ky) {
+      int th = (gh + ky - 1) / ky;
+      if (th == last_th) continue;
+      last_th = th;
+      if ((long long)tw * th > max_rows) continue;
+      int tn = 1;
+      if (tw >= gw && th >= gh) {
+        tn = max_rows / (tw * th);
+        if (tn > n) tn = n;
+        if (tn < 1) tn = 1;
+      }
+      int tw2 = tw, tn2 = tn;
+      bool ok = false;
+      for (; tn2 >= 1; --tn2)
+        if (((long long)tw2 * th * tn2) % mult == 0) { ok = true; break; }
+      if (!ok) {
+        tn2 = 1;
+        for (tw2 = tw; (long long)tw2 * th <= max_rows && tw2 <= 256; ++tw2)
+          if (((long long)tw2 * th) % mult == 0) { ok = true; break; }
+      }
+      if (!ok) continue;
+      long long pr = (long long)tw2 * th * tn2;
+      long long tiles = (long long)((gw + tw2 - 1) / tw2) * ((gh + th - 1) / th) * ((n + tn2 - 1) / tn2);
+      long long cost = tiles * ((pr + 31) / 32 * 32) + tiles;     // padded MMA work + a per-tile overhead
+      if (best < 0 || cost < best) { best = cost; bw = tw2; bh = th; bn = tn2; }
+    }
+  }
+  if (cache_n < 64) { Key k = {gw, gh, n, max_rows, mult, bw, bh, bn}; cache[cache_n++] = k; }
+  *TW = bw; *TH = bh; *TN = bn;
+}
+
+static int tc_check(const sg_conv_desc* d, const char* who) {
+  SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
+  int kc = d->in_dt == SG_F32 ? 32 : 64;
+  SG_REQUIRE(d->in_dt == SG_F32 || d->in_dt == SG_BF16, "%s: bad in_dt", who);
+  SG_REQUIRE(d->c_in % kc == 0, "%s: c_in=%d must be a multiple of %d for the tensor-core path", who, d->c_in, kc);
+  SG_REQUIRE(d->c_out % 32 == 0, "%s: c_out=%d must be a multiple of 32 for the tensor-core path", who, d->c_out);
+  SG_REQUIRE(d->ntaps >= 1 && d->ntaps <= SG_MAX_TAPS, "%s: bad ntaps", who);
+  SG_REQUIRE(d->in_sy >= 1 && d->in_sy <= 2 && d->in_sx >= 1 && d->in_sx <= 2, "%s: input sampling stride must be 1 or 2", who);
+  SG_REQUIRE(d->n > 0 && d->grid_h > 0 && d->grid_w > 0, "%s: empty problem", who);
+  return SG_OK;
+}
+
+extern "C" {
+
+int sg_conv_tc_supported(const sg_conv_desc* d) {
+  if (!d) return 0;
+  int kc = d->in_dt == SG_F32 ? 32 : 64;
+  return (d->c_in % kc == 0) && (d->c_out % 32 == 0) && d->in_sy <= 2 && d->in_sx <= 2 && d->ntaps >= 1 &&
+         d->ntaps <= SG_MAX_TAPS && d->n > 0;
+}
+
+size_t sg_conv_packed_weight_elems(const sg_conv_desc* d) {
+  return d ? (size_t)d->c_out * d->ntaps * d->c_in : 0;
+}
+
+int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_master, void* w_packed) {
+  SG_REQUIRE(ctx && d && w_master && w_packed, "sg_conv_pack_weights: NULL");
+  long long total = (long long)d->c_out * d->ntaps * d->c_in;
+  if (total == 0) return SG_OK;
+  long long need = (total + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  int grid = (int)(need < cap ? need : cap);
+  SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
+                   const void* mask, void* out) {
+  SG_REQUIRE(ctx && in && w_packed && out, "sg_conv_fwd_tc: NULL");
+  int rc = tc_check(d, "sg_conv_fwd_tc");
+  if (rc != SG_OK) return rc;
+  SG_REQUIRE(!d->accumulate || d->out_dt == SG_F32, "sg_conv_fwd_tc: accumulate needs an fp32 output");
+  SG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                 ((uintptr_t)bias & 15) == 0 && ((uintptr_t)mask & 15) == 0,
+             "sg_conv_fwd_tc: pointers must be 16-byte aligned");
+  PFN_encodeTiled enc;
+  rc = get_encode(ctx, &enc);
+  if (rc != SG_OK) return rc;
+
+  static_assert(sizeof(TcFwdParams) < 4000, "kernel parameter block too large");
+  TcFwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int es = d->in_dt == SG_F32 ? 4 : 2;
+  const int KC = 128 / es;
+  p.ntaps = d->ntaps; p.c_in = d->c_in; p.c_out = d->c_out; p.n = d->n; p.grid_h = d->grid_h; p.grid_w = d->grid_w;
+  p.out_h = d->out_h; p.out_w = d->out_w; p.out_sy = d->out_sy; p.out_sx = d->out_sx; p.out_py = d->out_py; p.out_px = d->out_px;
+  p.relu = d->relu; p.accumulate = d->accumulate; p.out_dt = d->out_dt; p.mask_dt = d->mask_dt;
+  p.bias = bias; p.mask = mask; p.out = out;
+  choose_box(d->grid_w, d->grid_h, d->n, 128, 1, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = sg_div_up(d->grid_w, p.TW); p.tiles_y = sg_div_up(d->grid_h, p.TH); p.tiles_n = sg_div_up(d->n, p.TN);
+  p.BN = d->c_out % 256 == 0 ? 256 : (d->c_out % 128 == 0 ? 128 : (d->c_out % 64 == 0 ? 64 : 32));
+  p.tiles_col = d->c_out / p.BN;
+  p.kc_per_tap = d->c_in / KC;
+  const int PR = p.TW * p.TH * p.TN;
+  p.a_bytes = (uint32_t)PR * 128u;
+  p.b_bytes = (uint32_t)p.BN * 128u;
+  p.a_stage_stride = 128u * 128u;                  // always reserve a full 128-row tile (1024-byte aligned)
+  p.b_stage_stride = (uint32_t)p.BN * 128u;
+  int stages = (int)((220u * 1024u) / (p.a_stage_stride + p.b_stage_stride));
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  SG_REQUIRE(stages >= 2, "sg_conv_fwd_tc: not enough shared memory for 2 stages");
+  p.stages = stages;
+
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < d->ntaps; ++t) {
+    int py = posmod(d->tap_dy[t], d->in_sy), px = posmod(d->tap_dx[t], d->in_sx);
+    int v = py * 2 + px;
+    p.tap_view[t] = v;
+    p.tap_oy[t] = floordiv(d->tap_dy[t], d->in_sy);
+    p.tap_ox[t] = floordiv(d->tap_dx[t], d->in_sx);
+    used[v] = true;
+  }
+  int first_used = -1;
+  for (int v = 0; v < 4; ++v) {
+    if (!used[v]) continue;
+    if (first_used < 0) first_used = v;
+    rc = encode_nhwc_view(enc, &p.map_a[v], d->in_dt, in, d->n, d->in_h, d->in_w, d->c_in, d->in_sy, d->in_sx, v / 2, v % 2, KC,
+                          p.TW, p.TH, p.TN);
+    if (rc != SG_OK) return rc;
+  }
+  for (int v = 0; v < 4; ++v)
+    if (!used[v]) p.map_a[v] = p.map_a[first_used];
+  rc = encode_2d(enc, &p.map_b, d->in_dt, w_packed, (long long)d->ntaps * d->c_in, d->c_out, KC, p.BN);
+  if (rc != SG_OK) return rc;
+
+  long long total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
+  int grid = (int)(total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms);
+  size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024;
+  if (d->in_dt == SG_F32) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<float><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+  } else {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<__nv_bfloat16><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+  }
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms) {
+  (void)d; (void)num_sms;
+  return 0;      // split partials are combined with red.global.add.f32 straight into dw: no workspace
+}
+
+int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, void* workspace,
+                     size_t workspace_bytes) {
+  (void)workspace; (void)workspace_bytes;
+  SG_REQUIRE(ctx && in && dy && dw_master, "sg_conv_wgrad_tc: NULL");
+  int rc = tc_check(d, "sg_conv_wgrad_tc");
+  if (rc != SG_OK) return rc;
+  SG_REQUIRE(d->out_dt == d->in_dt, "sg_conv_wgrad_tc: dy must have the operand dtype (in_dt)");
+  SG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)dy & 15) == 0, "sg_conv_wgrad_tc: pointers must be 16-byte aligned");
+  PFN_encodeTiled enc;
+  rc = get_encode(ctx, &enc);
+  if (rc != SG_OK) return rc;
+
+  static_assert(sizeof(TcWgradParams) < 4000, "kernel parameter block too large");
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  const int es = d->in_dt == SG_F32 ? 4 : 2;
+  const int KC = 128 / es, UK = 32 / es;
+  p.ntaps = d->ntaps; p.c_in = d->c_in; p.c_out = d->c_out;
+  p.w_ci_stride = d->w_ci_stride; p.w_co_stride = d->w_co_stride;
+  p.dw = dw_master;
+  p.BN = d->c_in % 256 == 0 ? 256 : (d->c_in % 128 == 0 ? 128 : (d->c_in % 64 == 0 ? 64 : 32));
+  p.ci_tiles = d->c_in / p.BN;
+  p.co_tiles = sg_div_up(d->c_out, 128);
+  p.a_chunks = 128 / KC;
+  p.b_chunks = p.BN / KC;
+  // pixels per k-block: keep a stage <= 48 KB so that >= 4 stages fit
+  int max_rows = (48 * 1024) / (128 * (p.a_chunks + p.b_chunks));
+  if (max_rows > 128) max_rows = 128;
+  max_rows = max_rows / UK * UK;
+  SG_REQUIRE(max_rows >= UK, "sg_conv_wgrad_tc: tile does not fit");
+  choose_box(d->grid_w, d->grid_h, d->n, max_rows, UK, &p.TW, &p.TH, &p.TN);
+  const int PR = p.TW * p.TH * p.TN;
+  SG_REQUIRE(PR % UK == 0 && PR <= max_rows, "sg_conv_wgrad_tc: internal box choice error (%d)", PR);
+  p.tiles_x = sg_div_up(d->grid_w, p.TW); p.tiles_y = sg_div_up(d->grid_h, p.TH); p.tiles_n = sg_div_up(d->n, p.TN);
+  p.chunk_bytes = (uint32_t)PR * 128u;
+  p.stage_stride = (uint32_t)(p.a_chunks + p.b_chunks) * p.chunk_bytes;
+  p.stage_stride = (p.stage_stride + 1023u) & ~1023u;
+  int stages = (int)((220u * 1024u) / p.stage_stride);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  SG_REQUIRE(stages >= 2, "sg_conv_wgrad_tc: not enough shared memory for 2 stages");
+  p.stages = stages;
+
+  const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  long long base_units = (long long)d->ntaps * p.co_tiles * p.ci_tiles;
+  int splits = (int)((2LL * ctx->num_sms + base_units - 1) / base_units);
+  int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.ptiles_per_split = sg_div_up(ptiles, splits);
+  p.splits = sg_div_up(ptiles, p.ptiles_per_split);
+
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < d->ntaps; ++t) {
+    int py = posmod(d->tap_dy[t], d->in_sy), px = posmod(d->tap_dx[t], d->in_sx);
+    int v = py * 2 + px;
+    p.tap_view[t] = v;
+    p.tap_oy[t] = floordiv(d->tap_dy[t], d->in_sy);
+    p.tap_ox[t] = floordiv(d->tap_dx[t], d->in_sx);
+    p.tap_w_off[t] = d->tap_w_off[t];
+    used[v] = true;
+  }
+  int first_used = -1;
+  for (int v = 0; v < 4; ++v) {
+    if (!used[v]) continue;
+    if (first_used < 0) first_used = v;
+    rc = encode_nhwc_view(enc, &p.map_in[v], d->in_dt, in, d->n, d->in_h, d->in_w, d->c_in, d->in_sy, d->in_sx, v / 2, v % 2, KC,
+                          p.TW, p.TH, p.TN);
+    if (rc != SG_OK) return rc;
+  }
+  for (int v = 0; v < 4; ++v)
+    if (!used[v]) p.map_in[v] = p.map_in[first_used];
+  rc = encode_nhwc_view(enc, &p.map_dy, d->in_dt, dy, d->n, d->out_h, d->out_w, d->c_out, d->out_sy, d->out_sx, d->out_py,
+                        d->out_px, KC, p.TW, p.TH, p.TN);
+  if (rc != SG_OK) return rc;
+
+  long long units = base_units * p.splits;
+  int grid = (int)(units < ctx->num_sms ? units : ctx->num_sms);
+  size_t smem = (size_t)stages * p.stage_stride + 1024;
+  if (d->in_dt == SG_F32) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad_tc<float><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+  } else {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad_tc<__nv_bfloat16><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+  }
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

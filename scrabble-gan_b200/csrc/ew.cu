@@ -1,0 +1,411 @@
+// Element-wise glue and pooling kernels: HBM-bound, float4-vectorised grid-stride loops,
+// grids sized as a multiple of the SM count.
+#include "common.cuh"
+
+static inline int ew_grid(sg_ctx* ctx, long long work_items, int threads) {
+  long long need = (work_items + threads - 1) / threads;
+  long long cap = (long long)ctx->num_sms * 8;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void k_act_prep(const float* __restrict__ x, long long n4, long long n, TO* __restrict__ relu_out,
+                           TO* __restrict__ copy_out) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = sg_ld4(x + 4 * i);
+    if (copy_out) sg_st4(copy_out + 4 * i, v);
+    if (relu_out) sg_st4(relu_out + 4 * i, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
+  }
+  // tail
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = x[i];
+    if (copy_out) sg_st(copy_out + i, v);
+    if (relu_out) sg_st(relu_out + i, fmaxf(v, 0.f));
+  }
+}
+
+template <typename TA, typename TO>
+__global__ void k_mask_mul(const float* __restrict__ dy, const TA* __restrict__ act, TO* __restrict__ out,
+                           long long n4, long long n, int accumulate) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 d = sg_ld4(dy + 4 * i);
+    float4 a = sg_ld4(act + 4 * i);
+    float4 r = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+    if (accumulate) {
+      float4 o = sg_ld4(out + 4 * i);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    sg_st4(out + 4 * i, r);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float r = sg_ld(act + i) > 0.f ? dy[i] : 0.f;
+    if (accumulate) r += sg_ld(out + i);
+    sg_st(out + i, r);
+  }
+}
+
+__global__ void k_axpby(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
+                        float* __restrict__ out, long long n4, long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = sg_ld4(x + 4 * i);
+    float4 r = make_float4(a * v.x, a * v.y, a * v.z, a * v.w);
+    if (y) {
+      float4 w = sg_ld4(y + 4 * i);
+      r.x += b * w.x; r.y += b * w.y; r.z += b * w.z; r.w += b * w.w;
+    }
+    sg_st4(out + 4 * i, r);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float r = a * x[i];
+    if (y) r += b * y[i];
+    out[i] = r;
+  }
+}
+
+__global__ void k_scale_add(const float* __restrict__ sigma, const float* __restrict__ a,
+                            const float* __restrict__ x, float* __restrict__ out, long long n4, long long n) {
+  const float s = *sigma;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = sg_ld4(a + 4 * i), w = x ? sg_ld4(x + 4 * i) : make_float4(0, 0, 0, 0);
+    sg_st4(out + 4 * i, make_float4(s * v.x + w.x, s * v.y + w.y, s * v.z + w.z, s * v.w + w.w));
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = s * a[i] + (x ? x[i] : 0.f);
+}
+
+__global__ void k_tanh_fwd(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = tanhf(x[i]);
+}
+__global__ void k_tanh_bwd(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                           long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float t = y[i];
+    dx[i] = dy[i] * (1.f - t * t);
+  }
+}
+__global__ void k_scale_rows(float* __restrict__ x, const float* __restrict__ w, int rows, long long cols) {
+  long long n = (long long)rows * cols;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= w[i / cols];
+}
+
+__global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, float* partial) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += a[i] * b[i];
+  float t = sg_block_sum(acc, sm);
+  if (threadIdx.x == 0) atomicAdd(partial, t);
+}
+
+// column sums of a [rows, cols] matrix: block handles a row-slab, thread t handles columns t, t+blockDim...
+// partial results are combined with one atomicAdd per (block, column).
+template <typename T>
+__global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
+                         float* __restrict__ out) {
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += sg_ld(x + r * cols + c);
+    atomicAdd(out + c, acc);
+  }
+}
+
+template <typename TO>
+__global__ void k_cast(const float* __restrict__ x, TO* __restrict__ out, long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) sg_st(out + i, x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pooling (NHWC, c % 4 == 0)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_avgpool2_fwd(const float* __restrict__ x, int n, int h, int w, int c4, float* __restrict__ out) {
+  int ho = h / 2, wo = w / 2;
+  long long total = (long long)n * ho * wo * c4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4);
+    long long p = i / c4;
+    int ox = (int)(p % wo);
+    p /= wo;
+    int oy = (int)(p % ho);
+    int ni = (int)(p / ho);
+    const float* base = x + (((long long)ni * h + 2 * oy) * w + 2 * ox) * (4LL * c4) + 4 * cc;
+    float4 a = sg_ld4(base), b = sg_ld4(base + 4LL * c4), cq = sg_ld4(base + (long long)w * 4 * c4),
+           d = sg_ld4(base + (long long)w * 4 * c4 + 4LL * c4);
+    sg_st4(out + 4 * i, make_float4(0.25f * (a.x + b.x + cq.x + d.x), 0.25f * (a.y + b.y + cq.y + d.y),
+                                    0.25f * (a.z + b.z + cq.z + d.z), 0.25f * (a.w + b.w + cq.w + d.w)));
+  }
+}
+
+template <typename TO>
+__global__ void k_avgpool2_bwd(const float* __restrict__ dout, int n, int h, int w, int c4, TO* __restrict__ dx) {
+  int ho = h / 2, wo = w / 2;
+  long long total = (long long)n * h * w * c4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4);
+    long long p = i / c4;
+    int x_ = (int)(p % w);
+    p /= w;
+    int y_ = (int)(p % h);
+    int ni = (int)(p / h);
+    float4 v = sg_ld4(dout + ((((long long)ni * ho + y_ / 2) * wo + x_ / 2) * c4 + cc) * 4);
+    sg_st4(dx + 4 * i, make_float4(0.25f * v.x, 0.25f * v.y, 0.25f * v.z, 0.25f * v.w));
+  }
+}
+
+template <typename T>
+__global__ void k_maxpool_fwd(const T* __restrict__ x, int n, int h, int w, int c, int ph, int pw,
+                              T* __restrict__ out) {
+  int ho = h / ph, wo = w / pw;
+  long long total = (long long)n * ho * wo * c;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c);
+    long long p = i / c;
+    int ox = (int)(p % wo);
+    p /= wo;
+    int oy = (int)(p % ho);
+    int ni = (int)(p / ho);
+    float m = -INFINITY;
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b)
+        m = fmaxf(m, sg_ld(x + (((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c + cc));
+    sg_st(out + i, m);
+  }
+}
+
+// gradient goes to the FIRST maximal element of the window (row-major window order), optionally gated by x > 0
+template <typename TX, typename TO>
+__global__ void k_maxpool_bwd(const float* __restrict__ dout, const TX* __restrict__ x, int n, int h, int w, int c,
+                              int ph, int pw, int relu_mask, TO* __restrict__ dx) {
+  int ho = h / ph, wo = w / pw;
+  long long total = (long long)n * ho * wo * c;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c);
+    long long p = i / c;
+    int ox = (int)(p % wo);
+    p /= wo;
+    int oy = (int)(p % ho);
+    int ni = (int)(p / ho);
+    float m = -INFINITY;
+    int best = 0;
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b) {
+        float v = sg_ld(x + (((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c + cc);
+        if (v > m) { m = v; best = a * pw + b; }
+      }
+    float g = dout[i];
+    if (relu_mask && !(m > 0.f)) g = 0.f;
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b)
+        sg_st(dx + (((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c + cc, (a * pw + b == best) ? g : 0.f);
+  }
+}
+
+// global average pool of relu(x): one block per (image, 128-channel slab); threads split (pixel-slices x channels)
+__global__ void k_gap_relu_fwd(const float* __restrict__ x, long long hw, int c, float* __restrict__ out) {
+  __shared__ float sm[8][128];
+  int ni = blockIdx.y;
+  int c0 = blockIdx.x * 128;
+  int cl = threadIdx.x & 127, slice = threadIdx.x >> 7;     // 1024 threads: 8 slices
+  int cc = c0 + cl;
+  float acc = 0.f;
+  if (cc < c)
+    for (long long p = slice; p < hw; p += 8) acc += fmaxf(x[((long long)ni * hw + p) * c + cc], 0.f);
+  sm[slice][cl] = acc;
+  __syncthreads();
+  if (slice == 0 && cc < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) t += sm[s][cl];
+    out[(long long)ni * c + cc] = t / (float)hw;
+  }
+}
+
+__global__ void k_gap_relu_bwd(const float* __restrict__ dfeat, const float* __restrict__ x, long long hw, int c,
+                               long long total, float* __restrict__ dx) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  float inv = 1.f / (float)hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c);
+    long long ni = i / ((long long)hw * c);
+    dx[i] = x[i] > 0.f ? dfeat[ni * c + cc] * inv : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sg_act_prep(sg_ctx* ctx, const float* x, long long n, void* relu_out, void* copy_out, int out_dt) {
+  SG_REQUIRE(ctx && x && n >= 0, "sg_act_prep: bad args");
+  if (n == 0) return SG_OK;
+  long long n4 = (((uintptr_t)x | (uintptr_t)relu_out | (uintptr_t)copy_out) & 15) == 0 ? n / 4 : 0;
+  SG_DISPATCH_DT(out_dt, TO,
+                 k_act_prep<TO><<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(x, n4, n, (TO*)relu_out, (TO*)copy_out));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_mask_mul(sg_ctx* ctx, const float* dy, const void* act, int act_dt, void* out, int out_dt, long long n,
+                int accumulate) {
+  SG_REQUIRE(ctx && dy && act && out && n >= 0, "sg_mask_mul: bad args");
+  if (n == 0) return SG_OK;
+  long long n4 = (((uintptr_t)dy | (uintptr_t)act | (uintptr_t)out) & 15) == 0 ? n / 4 : 0;
+  int grid = ew_grid(ctx, n / 4 + 1, 256);
+  SG_DISPATCH_DT(act_dt, TA,
+                 SG_DISPATCH_DT(out_dt, TO,
+                                k_mask_mul<TA, TO><<<grid, 256, 0, ctx->stream>>>(dy, (const TA*)act, (TO*)out, n4, n, accumulate)));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_axpby(sg_ctx* ctx, float a, const float* x, float b, const float* y, float* out, long long n) {
+  SG_REQUIRE(ctx && x && out && n >= 0, "sg_axpby: bad args");
+  if (n == 0) return SG_OK;
+  long long n4 = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out) & 15) == 0 ? n / 4 : 0;
+  k_axpby<<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(a, x, b, y, out, n4, n);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_scale_add(sg_ctx* ctx, const float* sigma, const float* a, const float* x, float* out, long long n) {
+  SG_REQUIRE(ctx && sigma && a && out && n >= 0, "sg_scale_add: bad args");
+  if (n == 0) return SG_OK;
+  long long n4 = (((uintptr_t)a | (uintptr_t)x | (uintptr_t)out) & 15) == 0 ? n / 4 : 0;
+  k_scale_add<<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(sigma, a, x, out, n4, n);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_tanh_fwd(sg_ctx* ctx, const float* x, float* y, long long n) {
+  SG_REQUIRE(ctx && x && y && n >= 0, "sg_tanh_fwd: bad args");
+  if (n == 0) return SG_OK;
+  k_tanh_fwd<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(x, y, n);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_tanh_bwd(sg_ctx* ctx, const float* dy, const float* y, float* dx, long long n) {
+  SG_REQUIRE(ctx && dy && y && dx && n >= 0, "sg_tanh_bwd: bad args");
+  if (n == 0) return SG_OK;
+  k_tanh_bwd<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(dy, y, dx, n);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long cols) {
+  SG_REQUIRE(ctx && x && w && rows >= 0 && cols >= 0, "sg_scale_rows: bad args");
+  if ((long long)rows * cols == 0) return SG_OK;
+  k_scale_rows<<<ew_grid(ctx, (long long)rows * cols, 256), 256, 0, ctx->stream>>>(x, w, rows, cols);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out, int accumulate) {
+  SG_REQUIRE(ctx && a && b && out && n >= 0, "sg_dot: bad args");
+  if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ctx->stream));
+  if (n == 0) return SG_OK;
+  k_dot<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(a, b, n, out);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, float* out, int accumulate) {
+  SG_REQUIRE(ctx && x && out && rows >= 0 && cols > 0, "sg_colsum: bad args");
+  if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ctx->stream));
+  if (rows == 0) return SG_OK;
+  long long blocks = (long long)ctx->num_sms * 4;
+  if (blocks > rows) blocks = rows;
+  long long rpb = (rows + blocks - 1) / blocks;
+  blocks = (rows + rpb - 1) / rpb;
+  int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
+  SG_DISPATCH_DT(dt, T, k_colsum<T><<<(int)blocks, threads, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_cast(sg_ctx* ctx, const float* x, void* out, int out_dt, long long n) {
+  SG_REQUIRE(ctx && x && out && n >= 0, "sg_cast: bad args");
+  if (n == 0) return SG_OK;
+  SG_DISPATCH_DT(out_dt, TO, k_cast<TO><<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(x, (TO*)out, n));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_avgpool2_fwd(sg_ctx* ctx, const float* x, int n, int h, int w, int c, float* out) {
+  SG_REQUIRE(ctx && x && out, "sg_avgpool2_fwd: NULL");
+  SG_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "sg_avgpool2_fwd: needs even h,w and c%%4==0 (h=%d w=%d c=%d)", h, w, c);
+  long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
+  if (total == 0) return SG_OK;
+  k_avgpool2_fwd<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(x, n, h, w, c / 4, out);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_avgpool2_bwd(sg_ctx* ctx, const float* dout, int n, int h, int w, int c, void* dx, int dx_dt) {
+  SG_REQUIRE(ctx && dout && dx, "sg_avgpool2_bwd: NULL");
+  SG_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "sg_avgpool2_bwd: needs even h,w and c%%4==0");
+  long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return SG_OK;
+  SG_DISPATCH_DT(dx_dt, TO, k_avgpool2_bwd<TO><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(dout, n, h, w, c / 4, (TO*)dx));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_maxpool_fwd(sg_ctx* ctx, const void* x, int dt, int n, int h, int w, int c, int ph, int pw, void* out) {
+  SG_REQUIRE(ctx && x && out, "sg_maxpool_fwd: NULL");
+  SG_REQUIRE(ph >= 1 && pw >= 1 && h % ph == 0 && w % pw == 0, "sg_maxpool_fwd: h,w must be divisible by the window");
+  long long total = (long long)n * (h / ph) * (w / pw) * c;
+  if (total == 0) return SG_OK;
+  SG_DISPATCH_DT(dt, T, k_maxpool_fwd<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c, ph, pw, (T*)out));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_maxpool_bwd(sg_ctx* ctx, const float* dout, const void* x, int x_dt, int n, int h, int w, int c, int ph,
+                   int pw, int relu_mask, void* dx, int dx_dt) {
+  SG_REQUIRE(ctx && dout && x && dx, "sg_maxpool_bwd: NULL");
+  SG_REQUIRE(ph >= 1 && pw >= 1 && h % ph == 0 && w % pw == 0, "sg_maxpool_bwd: h,w must be divisible by the window");
+  long long total = (long long)n * (h / ph) * (w / pw) * c;
+  if (total == 0) return SG_OK;
+  int grid = ew_grid(ctx, total, 256);
+  SG_DISPATCH_DT(x_dt, TX,
+                 SG_DISPATCH_DT(dx_dt, TO,
+                                k_maxpool_bwd<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c, ph, pw, relu_mask, (TO*)dx)));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_gap_relu_fwd(sg_ctx* ctx, const float* x, int n, long long hw, int c, float* out) {
+  SG_REQUIRE(ctx && x && out && n >= 0 && hw > 0 && c > 0, "sg_gap_relu_fwd: bad args");
+  if (n == 0) return SG_OK;
+  dim3 grid(sg_div_up(c, 128), n);
+  k_gap_relu_fwd<<<grid, 1024, 0, ctx->stream>>>(x, hw, c, out);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_gap_relu_bwd(sg_ctx* ctx, const float* dfeat, const float* x, int n, long long hw, int c, float* dx) {
+  SG_REQUIRE(ctx && dfeat && x && dx && n >= 0 && hw > 0 && c > 0, "sg_gap_relu_bwd: bad args");
+  long long total = (long long)n * hw * c;
+  if (total == 0) return SG_OK;
+  k_gap_relu_bwd<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(dfeat, x, hw, c, total, dx);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Small fp32 GEMM for the Dense layers (K14) and the attention 1x1 projections:
+//   C[m,n] (+)= sum_k opA(m,k) * opB(k,n) + bias[n]      row-major, arbitrary sizes.
+// Reference call sites: resnet_ops.py:18,24 (CBN gamma/beta), net_architecture.py:55,251,342,401.
+// 64x64x16 shared-memory tiles, 256 threads, 4x4 register blocking.  These GEMMs are tiny (<0.1% of step
+// FLOPs) or HBM-bound (K <= 64), so they stay on the FFMA pipe by design.
+#include "common.cuh"
+
+#define GT_M 64
+#define GT_N 64
+#define GT_K 16
+
+__global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                               const float* __restrict__ bias, int accumulate, int k_per_split) {
+  __shared__ float As[GT_K][GT_M + 4];
+  __shared__ float Bs[GT_K][GT_N + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GT_M, n0 = blockIdx.x * GT_N;
+  const int tx = tid % 16, ty = tid / 16;      // thread computes rows ty*4..+3, cols tx*4..+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  const bool split = gridDim.z > 1;
+  for (int k0 = kbeg; k0 < kend; k0 += GT_K) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int mm, kk;
+      if (ta) { mm = idx % GT_M; kk = idx / GT_M; } else { kk = idx % GT_K; mm = idx / GT_K; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int nn, kk;
+      if (tb) { kk = idx % GT_K; nn = idx / GT_K; } else { nn = idx % GT_N; kk = idx / GT_N; }
+      int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = tb ? B[(long long)gn * ldb + gk] : B[(long long)gk * ldb + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GT_K; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias && blockIdx.z == 0) v += bias[gn];
+      float* p = C + (long long)gm * ldc + gn;
+      if (split) { atomicAdd(p, v); continue; }
+      if (accumulate) v += *p;
+      *p = v;
+    }
+  }
+}
+
+extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, const float* a, int lda,
+                       const float* b, int ldb, float* c, int ldc, const float* bias, int accumulate) {
+  SG_REQUIRE(ctx && a && b && c, "sg_gemm: NULL");
+  SG_REQUIRE(m >= 0 && n >= 0 && k >= 0, "sg_gemm: negative dims");
+  if (m == 0 || n == 0) return SG_OK;
+  dim3 grid(sg_div_up(n, GT_N), sg_div_up(m, GT_M));
+  SG_REQUIRE(grid.y <= 65535, "sg_gemm: m=%d too large for one launch", m);
+  // split-K (atomic accumulation) for skinny-output / long-reduction shapes such as dW = X^T dY
+  int splits = 1, k_per_split = k > 0 ? k : 1;
+  long long tiles = (long long)grid.x * grid.y;
+  if (k >= 4096 && tiles < ctx->num_sms) {
+    splits = (int)((2LL * ctx->num_sms + tiles - 1) / tiles);
+    int max_splits = k / 1024;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    k_per_split = ((k + splits - 1) / splits + GT_K - 1) / GT_K * GT_K;
+    splits = (k + k_per_split - 1) / k_per_split;
+  }
+  if (splits > 1 && !accumulate) {
+    SG_REQUIRE(ldc == n, "sg_gemm: split-K without accumulate needs a contiguous C");
+    SG_CHECK_CUDA(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, ctx->stream));
+  }
+  grid.z = splits;
+  k_gemm<<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}

@@ -1,0 +1,171 @@
+// GAN losses + ScrabbleGAN "gradient balancing" (K16, K17).
+// Reference: net_loss.py:38-54 (hinge), :4-35 (not_saturating), data_utils.py:418-442 (13 means) and
+// :476-490 (apply_gradient_balancing: population std of the per-sample losses, differentiable, no guards).
+// The per-sample upstream weights for every backward pass are produced in closed form:
+//   S = sum_i g_i + alpha (sd_g/sd_r) r_i   =>   dS/dg_i = 1 + alpha (R/sd_r)(g_i - mean_g)/(N sd_g)
+//                                                dS/dr_i = alpha [ sd_g/sd_r - sd_g R (r_i - mean_r)/(N sd_r^3) ]
+// Sums are kept in double and exchanged between the two kernels so that data-parallel replicas can
+// all-reduce them (the std is then over the GLOBAL batch).
+#include "common.cuh"
+
+enum { SUM_G = 0, SUM_G2, SUM_R, SUM_R2, SUM_RREAL, SUM_DLR, SUM_DLF, SUM_SL1, SUM_SL2, SUM_N };
+
+__device__ __forceinline__ float sce(float x, float z) {   // tf.nn.sigmoid_cross_entropy_with_logits
+  return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float g_of(int kind, int use_w, float d_fake, float s_fake, float s5) {
+  if (kind == SG_LOSS_HINGE) return use_w ? -(d_fake + s_fake) : -d_fake;
+  return use_w ? sce(d_fake, 1.f) + sce(s5, 1.f) : sce(d_fake, 1.f);
+}
+
+__device__ double block_sum_d(double v, double* sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) r += sm[i];
+  return r;
+}
+
+__global__ void k_loss_sums(int kind, int use_w, const float* d_real, const float* d_fake, const float* s_real,
+                            const float* s_fake, const float* s5, const float* r_fake, const float* r_real, int b,
+                            double* sums) {
+  __shared__ double sm[32];
+  double acc[SUM_N];
+  for (int j = 0; j < SUM_N; ++j) acc[j] = 0.0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float dr = d_real[i], df = d_fake[i];
+    float sr = use_w ? s_real[i] : 0.f, sf = use_w ? s_fake[i] : 0.f, sx = (use_w && s5) ? s5[i] : 0.f;
+    float g = g_of(kind, use_w, df, sf, sx);
+    float r = r_fake[i];
+    acc[SUM_G] += g;
+    acc[SUM_G2] += (double)g * g;
+    acc[SUM_R] += r;
+    acc[SUM_R2] += (double)r * r;
+    acc[SUM_RREAL] += r_real[i];
+    if (kind == SG_LOSS_HINGE) {
+      acc[SUM_DLR] += fmaxf(1.f - dr, 0.f);
+      acc[SUM_DLF] += fmaxf(1.f + df, 0.f);
+      if (use_w) { acc[SUM_SL1] += fmaxf(1.f - sr, 0.f); acc[SUM_SL2] += fmaxf(1.f + sf, 0.f); }
+    } else {
+      acc[SUM_DLR] += sce(dr, 1.f);
+      acc[SUM_DLF] += sce(df, 0.f);
+      if (use_w) { acc[SUM_SL1] += sce(sr, 1.f); acc[SUM_SL2] += sce(sf, 0.f); }
+    }
+  }
+  for (int j = 0; j < SUM_N; ++j) {
+    double t = block_sum_d(acc[j], sm);
+    if (threadIdx.x == 0) sums[j] = t;
+  }
+  if (threadIdx.x == 0) {
+    sums[SUM_N] = (double)b;
+    for (int j = SUM_N + 1; j < SG_LOSS_NSUMS; ++j) sums[j] = 0.0;
+  }
+}
+
+__global__ void k_loss_finish(int kind, int use_w, int balance, float alpha, const float* d_real, const float* d_fake,
+                              const float* s_real, const float* s_fake, const float* s5, const float* r_fake, int b,
+                              const double* sums, float* up_d_real, float* up_d_fake_d, float* up_s_real,
+                              float* up_s_fake_w, float* up_s_slot5, float* up_d_fake_g, float* up_s_fake_g,
+                              float* up_r_fake_g, float* stats) {
+  const double N = sums[SUM_N];
+  const double mean_g = sums[SUM_G] / N, mean_r = sums[SUM_R] / N;
+  double var_g = sums[SUM_G2] / N - mean_g * mean_g, var_r = sums[SUM_R2] / N - mean_r * mean_r;
+  if (var_g < 0) var_g = 0;
+  if (var_r < 0) var_r = 0;
+  const double sd_g = sqrt(var_g), sd_r = sqrt(var_r);
+  const double R = sums[SUM_R];
+  const double ratio = sd_g / sd_r;          // no zero guard: the reference has none (data_utils.py:488)
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float dr = d_real[i], df = d_fake[i];
+    float sr = use_w ? s_real[i] : 0.f, sf = use_w ? s_fake[i] : 0.f, sx = (use_w && s5) ? s5[i] : 0.f;
+    float g = g_of(kind, use_w, df, sf, sx);
+    float r = r_fake[i];
+    double cg = 1.0, cr = 1.0;
+    if (balance) {
+      cg = 1.0 + (double)alpha * (R / sd_r) * ((double)g - mean_g) / (N * sd_g);
+      cr = (double)alpha * (ratio - sd_g * R * ((double)r - mean_r) / (N * sd_r * sd_r * sd_r));
+    }
+    float dg_dd, dg_ds;
+    if (kind == SG_LOSS_HINGE) {
+      up_d_real[i] = (1.f - dr > 0.f) ? -1.f : 0.f;
+      up_d_fake_d[i] = (1.f + df > 0.f) ? 1.f : 0.f;
+      if (use_w) {
+        up_s_real[i] = (1.f - sr > 0.f) ? -1.f : 0.f;
+        up_s_fake_w[i] = (1.f + sf > 0.f) ? 1.f : 0.f;
+        if (up_s_slot5) up_s_slot5[i] = 0.f;
+      }
+      dg_dd = -1.f;
+      dg_ds = use_w ? -1.f : 0.f;
+    } else {
+      up_d_real[i] = sigmoidf_(dr) - 1.f;
+      up_d_fake_d[i] = sigmoidf_(df);
+      if (use_w) {
+        up_s_real[i] = sigmoidf_(sr) - 1.f;
+        up_s_fake_w[i] = sigmoidf_(sf);
+        if (up_s_slot5) up_s_slot5[i] = 0.f;
+      }
+      dg_dd = sigmoidf_(df) - 1.f;
+      dg_ds = 0.f;       // bug-compatible: g uses the 5th slot (W(real images)), not W(G(z))  
+    }
+    up_d_fake_g[i] = (float)(cg * dg_dd);
+    if (use_w && up_s_fake_g) up_s_fake_g[i] = (float)(cg * dg_ds);
+    up_r_fake_g[i] = (float)cr;
+  }
+  if (threadIdx.x == 0) {
+    double mean_rreal = sums[SUM_RREAL] / N;
+    double r_bal = (double)alpha * ratio * mean_r;
+    double g_added = mean_g + mean_r, g_bal = mean_g + r_bal;
+    double dlr = sums[SUM_DLR] / N, dlf = sums[SUM_DLF] / N, s1 = sums[SUM_SL1] / N, s2 = sums[SUM_SL2] / N;
+    stats[0] = (float)mean_r;        // r_loss_fake
+    stats[1] = (float)mean_rreal;    // r_loss_real
+    stats[2] = (float)r_bal;         // r_loss_balanced
+    stats[3] = (float)mean_g;        // g_loss
+    stats[4] = (float)g_added;       // g_loss_added
+    stats[5] = (float)g_bal;         // g_loss_balanced
+    stats[6] = (float)(dlr + dlf);   // d_loss
+    stats[7] = (float)dlr;
+    stats[8] = (float)dlf;
+    stats[9] = (float)(balance ? g_bal : g_added);   // g_loss_final
+    stats[10] = alpha;
+    stats[11] = (float)sd_r;         // r_loss_fake_std
+    stats[12] = (float)sd_g;         // g_loss_std
+    stats[13] = (float)(s1 + s2);    // s_loss
+    stats[14] = (float)s1;
+    stats[15] = (float)s2;
+  }
+}
+
+extern "C" {
+
+int sg_loss_sums(sg_ctx* ctx, int kind, int use_w, const float* d_real, const float* d_fake, const float* s_real,
+                 const float* s_fake, const float* s_slot5, const float* r_fake, const float* r_real, int b,
+                 double* sums) {
+  SG_REQUIRE(ctx && d_real && d_fake && r_fake && r_real && sums && b > 0, "sg_loss_sums: bad args");
+  SG_REQUIRE(!use_w || (s_real && s_fake), "sg_loss_sums: use_w needs s_real and s_fake");
+  SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_sums: bad loss kind %d", kind);
+  k_loss_sums<<<1, 256, 0, ctx->stream>>>(kind, use_w, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, r_real, b, sums);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, const float* d_real, const float* d_fake,
+                   const float* s_real, const float* s_fake, const float* s_slot5, const float* r_fake, int b,
+                   const double* sums, float* up_d_real, float* up_d_fake_d, float* up_s_real, float* up_s_fake_w,
+                   float* up_s_slot5, float* up_d_fake_g, float* up_s_fake_g, float* up_r_fake_g, float* stats) {
+  SG_REQUIRE(ctx && d_real && d_fake && r_fake && sums && up_d_real && up_d_fake_d && up_d_fake_g && up_r_fake_g && stats && b > 0,
+             "sg_loss_finish: bad args");
+  SG_REQUIRE(!use_w || (s_real && s_fake && up_s_real && up_s_fake_w), "sg_loss_finish: use_w needs the s_* buffers");
+  SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_finish: bad loss kind %d", kind);
+  k_loss_finish<<<1, 256, 0, ctx->stream>>>(kind, use_w, balance, alpha, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, b,
+                                            sums, up_d_real, up_d_fake_d, up_s_real, up_s_fake_w, up_s_slot5, up_d_fake_g,
+                                            up_s_fake_g, up_r_fake_g, stats);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

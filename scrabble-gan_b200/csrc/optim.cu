@@ -1,0 +1,158 @@
+// Fused optimizer updates over flat parameter buffers (K19) and spectral norm (K18).
+// Reference: main.py:25-35 (tf.keras.optimizers.Adam(lr, beta_1, beta_2) x4, optional RMSprop for R),
+// data_utils.py:451-468 (apply_gradients), arch_ops.py:99-126 (spectral_norm).
+// Keras Adam:    m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr_t m / (sqrt(v) + eps),
+//                lr_t = lr sqrt(1-b2^t)/(1-b1^t) (computed on the host), eps = 1e-7 OUTSIDE the sqrt.
+// Keras RMSprop: ms = rho ms + (1-rho) g^2;  w -= lr g / (sqrt(ms) + eps).
+// HBM-bound: 4 reads + 3 writes per parameter, float4-vectorised.
+#include "common.cuh"
+
+__global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       long long n4, long long n, float lr_t, float b1, float b2, float eps) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gw = sg_ld4(g + 4 * i), mw = sg_ld4(m + 4 * i), vw = sg_ld4(v + 4 * i), ww = sg_ld4(w + 4 * i);
+    mw.x = b1 * mw.x + c1 * gw.x; mw.y = b1 * mw.y + c1 * gw.y; mw.z = b1 * mw.z + c1 * gw.z; mw.w = b1 * mw.w + c1 * gw.w;
+    vw.x = b2 * vw.x + c2 * gw.x * gw.x; vw.y = b2 * vw.y + c2 * gw.y * gw.y;
+    vw.z = b2 * vw.z + c2 * gw.z * gw.z; vw.w = b2 * vw.w + c2 * gw.w * gw.w;
+    ww.x -= lr_t * mw.x / (sqrtf(vw.x) + eps); ww.y -= lr_t * mw.y / (sqrtf(vw.y) + eps);
+    ww.z -= lr_t * mw.z / (sqrtf(vw.z) + eps); ww.w -= lr_t * mw.w / (sqrtf(vw.w) + eps);
+    sg_st4(m + 4 * i, mw); sg_st4(v + 4 * i, vw); sg_st4(w + 4 * i, ww);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    float mi = b1 * m[i] + c1 * gi, vi = b2 * v[i] + c2 * gi * gi;
+    m[i] = mi; v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+__global__ void k_rmsprop(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ ms, long long n,
+                          float lr, float rho, float eps) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    float s = rho * ms[i] + (1.f - rho) * gi * gi;
+    ms[i] = s;
+    w[i] -= lr * gi / (sqrtf(s) + eps);
+  }
+}
+
+// ---- spectral norm ----------------------------------------------------------------------------------
+// v_raw[r] = sum_c u[c] W[r,c]  (one warp per row)
+__global__ void k_sn_rowdot(const float* __restrict__ w, int rows, int cols, const float* __restrict__ u,
+                            const float* __restrict__ u_scale, float* __restrict__ v) {
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) acc += u[c] * w[(long long)r * cols + c];
+  acc = sg_warp_sum(acc);
+  if (lane == 0) v[r] = acc * (u_scale ? *u_scale : 1.f);
+}
+// t[c] += sum_{r in slab} v[r] * v_scale * W[r,c]
+__global__ void k_sn_coldot(const float* __restrict__ w, int rows, int cols, const float* __restrict__ v,
+                            const float* __restrict__ v_scale, int rows_per_block, float* __restrict__ t) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  int r0 = blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += v[r] * w[(long long)r * cols + c];
+  atomicAdd(t + c, acc * (*v_scale));
+}
+// out[0] = rsqrt(max(sum x^2, 1e-12))   (tf.nn.l2_normalize scale), out[1] = sum x^2
+__global__ void k_sn_invnorm(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += x[i] * x[i];
+  float t = sg_block_sum(acc, sm);
+  if (threadIdx.x == 0) { out[0] = rsqrtf(fmaxf(t, 1e-12f)); out[1] = t; }
+}
+// sigma = (v W) . u_hat = sum_c t[c] * (t[c]*inv_t) ; u_out = t*inv_t
+__global__ void k_sn_sigma(const float* __restrict__ t, int cols, const float* __restrict__ inv_t, float* __restrict__ u_out,
+                           float* __restrict__ sigma) {
+  __shared__ float sm[32];
+  float s = *inv_t, acc = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    float uh = t[i] * s;
+    if (u_out) u_out[i] = uh;
+    acc += t[i] * uh;
+  }
+  float r = sg_block_sum(acc, sm);
+  if (threadIdx.x == 0) *sigma = r;
+}
+__global__ void k_sn_scale(const float* __restrict__ w, long long n, const float* __restrict__ sigma, float* __restrict__ out) {
+  float inv = 1.f / *sigma;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = w[i] * inv;
+}
+
+extern "C" {
+
+int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+            float eps) {
+  SG_REQUIRE(ctx && w && g && m && v && n >= 0, "sg_adam: bad args");
+  if (n == 0) return SG_OK;
+  long long n4 = (((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 ? n / 4 : 0;
+  long long need = (n / 4 + 256) / 256, cap = (long long)ctx->num_sms * 8;
+  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps) {
+  SG_REQUIRE(ctx && w && g && ms && n >= 0, "sg_rmsprop: bad args");
+  if (n == 0) return SG_OK;
+  long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  k_rmsprop<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, ms, n, lr, rho, eps);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration, float* w_out,
+                     float* u_out, float* sigma_out, float* scratch) {
+  SG_REQUIRE(ctx && w && u && w_out && sigma_out && scratch, "sg_spectral_norm: NULL");
+  SG_REQUIRE(rows > 0 && cols > 0 && power_iteration >= 1, "sg_spectral_norm: bad sizes");
+  float* v = scratch;                 // [rows]
+  float* t = scratch + rows;          // [cols]
+  float* sc = scratch + rows + cols;  // [4]: inv_v, |v|^2, inv_t, |t|^2
+  const float* u_cur = u;
+  const float* u_scale = nullptr;
+  for (int it = 0; it < power_iteration; ++it) {
+    k_sn_rowdot<<<sg_div_up(rows, 8), 256, 0, ctx->stream>>>(w, rows, cols, u_cur, u_scale, v);
+    SG_POST_LAUNCH(ctx);
+    k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(v, rows, sc);
+    SG_POST_LAUNCH(ctx);
+    SG_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, ctx->stream));
+    int slabs = sg_div_up(rows, 64);
+    if (slabs > 4 * ctx->num_sms) slabs = 4 * ctx->num_sms;
+    int rpb = sg_div_up(rows, slabs);
+    slabs = sg_div_up(rows, rpb);
+    dim3 grid(sg_div_up(cols, 128), slabs);
+    k_sn_coldot<<<grid, 128, 0, ctx->stream>>>(w, rows, cols, v, sc, rpb, t);
+    SG_POST_LAUNCH(ctx);
+    k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2);
+    SG_POST_LAUNCH(ctx);
+    u_cur = t;            // next iteration uses u_hat = t * inv_t
+    u_scale = sc + 2;
+    if (it + 1 < power_iteration) {
+      // materialise u_hat so that t can be reused
+      SG_REQUIRE(u_out != nullptr, "sg_spectral_norm: power_iteration > 1 needs u_out as a staging buffer");
+      k_sn_sigma<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2, u_out, sigma_out);
+      SG_POST_LAUNCH(ctx);
+      u_cur = u_out;
+      u_scale = nullptr;
+    }
+  }
+  k_sn_sigma<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2, u_out, sigma_out);
+  SG_POST_LAUNCH(ctx);
+  long long n = (long long)rows * cols;
+  long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  k_sn_scale<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, n, sigma_out, w_out);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"
