@@ -1,0 +1,405 @@
+"""Functional wrappers over the libsgan C ABI operating on torch CUDA tensors (memory only), plus the
+sg_conv_desc builders that express Conv2D / its dgrad / Conv2DTranspose phases / its dgrad with TensorFlow's
+SAME / VALID padding rules.
+
+Nothing in this file computes on the host or with torch ops: every function is one (or a few) libsgan launches."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _abi
+from ._abi import SG_BF16, SG_F32, ConvDesc, call, ptr
+from .runtime import Runtime, dt_of
+
+_V = C.c_void_p
+
+
+def _p(t) -> _V:
+    return _V(None if t is None else t.data_ptr())
+
+
+# ----------------------------------------------------------------------------------------------------
+# descriptor builders
+# ----------------------------------------------------------------------------------------------------
+def _same_pad_before(k: int, s: int = 1) -> int:
+    """TF SAME: pad_total = max(k - s, 0) when the size is a multiple of s; pad_before = total // 2."""
+    return max(k - s, 0) // 2
+
+
+def _fill_taps(d: ConvDesc, taps) -> None:
+    assert 1 <= len(taps) <= _abi.SG_MAX_TAPS, "too many taps"
+    d.ntaps = len(taps)
+    for i, (dy, dx, off) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i], d.tap_w_off[i] = dy, dx, off
+
+
+def desc_conv_fwd(n, h, w, ci, co, kh, kw, padding="same", in_dt=SG_F32, out_dt=SG_F32, relu=0, accumulate=0,
+                  mask_dt=SG_F32) -> ConvDesc:
+    """tf.keras.layers.Conv2D stride 1, kernel HWIO."""
+    d = ConvDesc()
+    if padding == "same":
+        pt, pl, ho, wo = _same_pad_before(kh), _same_pad_before(kw), h, w
+    else:
+        pt, pl, ho, wo = 0, 0, h - kh + 1, w - kw + 1
+    d.n, d.in_h, d.in_w, d.c_in = n, h, w, ci
+    d.out_h, d.out_w, d.c_out = ho, wo, co
+    d.grid_h, d.grid_w = ho, wo
+    d.in_sy = d.in_sx = d.out_sy = d.out_sx = 1
+    d.out_py = d.out_px = 0
+    _fill_taps(d, [(a - pt, b - pl, (a * kw + b) * ci * co) for a in range(kh) for b in range(kw)])
+    d.w_ci_stride, d.w_co_stride = co, 1
+    d.in_dt, d.out_dt, d.relu, d.accumulate, d.mask_dt = in_dt, out_dt, relu, accumulate, mask_dt
+    return d
+
+
+def desc_conv_dgrad(n, h, w, ci, co, kh, kw, padding="same", in_dt=SG_F32, out_dt=SG_F32, accumulate=0,
+                    mask_dt=SG_F32) -> ConvDesc:
+    """Input gradient of the Conv2D above: `in` = dy [n,ho,wo,co], `out` = dx [n,h,w,ci]; same HWIO master weights."""
+    d = ConvDesc()
+    if padding == "same":
+        pt, pl, ho, wo = _same_pad_before(kh), _same_pad_before(kw), h, w
+    else:
+        pt, pl, ho, wo = 0, 0, h - kh + 1, w - kw + 1
+    d.n, d.in_h, d.in_w, d.c_in = n, ho, wo, co
+    d.out_h, d.out_w, d.c_out = h, w, ci
+    d.grid_h, d.grid_w = h, w
+    d.in_sy = d.in_sx = d.out_sy = d.out_sx = 1
+    d.out_py = d.out_px = 0
+    _fill_taps(d, [(pt - a, pl - b, (a * kw + b) * ci * co) for a in range(kh) for b in range(kw)])
+    d.w_ci_stride, d.w_co_stride = 1, co          # desc "ci" runs over the conv's co and vice versa
+    d.in_dt, d.out_dt, d.relu, d.accumulate, d.mask_dt = in_dt, out_dt, 0, accumulate, mask_dt
+    return d
+
+
+def convT_phases(k: int, sy: int, sx: int):
+    """Output phases (py, px) of a k x k Conv2DTranspose with strides (sy, sx) that receive at least one tap."""
+    pby, pbx = _same_pad_before(k, sy), _same_pad_before(k, sx)
+    out = []
+    for py in range(sy):
+        for px in range(sx):
+            ta = [a for a in range(k) if (py + pby - a) % sy == 0]
+            tb = [b for b in range(k) if (px + pbx - b) % sx == 0]
+            if ta and tb:
+                out.append((py, px))
+    return out
+
+
+def desc_convT_phase(n, h, w, ci, co, k, sy, sx, py, px, in_dt=SG_F32, out_dt=SG_F32, relu=0, accumulate=0) -> ConvDesc:
+    """One output phase of tf.keras.layers.Conv2DTranspose(k, strides=(sy,sx), 'same'), kernel (kh,kw,Cout,Cin):
+    out[n, oy*sy+py, ox*sx+px, :] = sum over taps a == py+pb (mod sy) of in[n, oy + (py+pb-a)/sy, ...] W[a,b]."""
+    d = ConvDesc()
+    pby, pbx = _same_pad_before(k, sy), _same_pad_before(k, sx)
+    d.n, d.in_h, d.in_w, d.c_in = n, h, w, ci
+    d.out_h, d.out_w, d.c_out = h * sy, w * sx, co
+    d.grid_h, d.grid_w = h, w
+    d.in_sy = d.in_sx = 1
+    d.out_sy, d.out_sx, d.out_py, d.out_px = sy, sx, py, px
+    taps = []
+    for a in range(k):
+        if (py + pby - a) % sy:
+            continue
+        for b in range(k):
+            if (px + pbx - b) % sx:
+                continue
+            taps.append(((py + pby - a) // sy, (px + pbx - b) // sx, (a * k + b) * co * ci))
+    _fill_taps(d, taps)
+    d.w_ci_stride, d.w_co_stride = 1, ci
+    d.in_dt, d.out_dt, d.relu, d.accumulate, d.mask_dt = in_dt, out_dt, relu, accumulate, SG_F32
+    return d
+
+
+def desc_convT_dgrad(n, h, w, ci, co, k, sy, sx, in_dt=SG_F32, out_dt=SG_F32, accumulate=0, mask_dt=SG_F32) -> ConvDesc:
+    """Input gradient of the Conv2DTranspose: `in` = dout [n,h*sy,w*sx,co] sampled with stride, `out` = dx [n,h,w,ci].
+    The filter gradient of the transposed conv is sg_conv_wgrad on THIS descriptor with (in=dout, dy=layer input)."""
+    d = ConvDesc()
+    pby, pbx = _same_pad_before(k, sy), _same_pad_before(k, sx)
+    d.n, d.in_h, d.in_w, d.c_in = n, h * sy, w * sx, co
+    d.out_h, d.out_w, d.c_out = h, w, ci
+    d.grid_h, d.grid_w = h, w
+    d.in_sy, d.in_sx = sy, sx
+    d.out_sy = d.out_sx = 1
+    d.out_py = d.out_px = 0
+    _fill_taps(d, [(a - pby, b - pbx, (a * k + b) * co * ci) for a in range(k) for b in range(k)])
+    d.w_ci_stride, d.w_co_stride = ci, 1
+    d.in_dt, d.out_dt, d.relu, d.accumulate, d.mask_dt = in_dt, out_dt, 0, accumulate, mask_dt
+    return d
+
+
+# ----------------------------------------------------------------------------------------------------
+# convolution launches
+# ----------------------------------------------------------------------------------------------------
+def tc_ok(rt: Runtime, d: ConvDesc) -> bool:
+    return bool(rt.use_tc and _abi.load().sg_conv_tc_supported(C.byref(d)))
+
+
+def pack_weights(rt: Runtime, d: ConvDesc, w_master: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = d.c_out * d.ntaps * d.c_in
+    if out is None:
+        out = rt.empty((n,), d.in_dt)
+    call.sg_conv_pack_weights(rt.ctx, C.byref(d), _p(w_master), _p(out))
+    return out
+
+
+def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out) -> None:
+    """Launch the conv described by d on the tensor-core path when possible, else the fp32 direct path."""
+    if w_packed is not None and tc_ok(rt, d):
+        call.sg_conv_fwd_tc(rt.ctx, C.byref(d), _p(x), _p(w_packed), _p(bias), _p(mask), _p(out))
+    else:
+        call.sg_conv_fwd_simt(rt.ctx, C.byref(d), _p(x), _p(w_master), _p(bias), _p(mask), _p(out))
+
+
+def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False) -> None:
+    """dw_master += filter gradient of the conv described by d."""
+    if not force_simt and tc_ok(rt, d) and d.in_dt == d.out_dt:
+        call.sg_conv_wgrad_tc(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _V(None), 0)
+    else:
+        call.sg_conv_wgrad_simt(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master))
+
+
+# ----------------------------------------------------------------------------------------------------
+# element-wise, pooling
+# ----------------------------------------------------------------------------------------------------
+def act_prep(rt, x, want_relu=True, want_copy=False, out_dt=None):
+    out_dt = rt.op_dt if out_dt is None else out_dt
+    r = rt.empty(x.shape, out_dt) if want_relu else None
+    c = rt.empty(x.shape, out_dt) if want_copy else None
+    call.sg_act_prep(rt.ctx, _p(x), x.numel(), _p(r), _p(c), out_dt)
+    return r, c
+
+
+def cast(rt, x, out_dt):
+    if dt_of(x) == out_dt:
+        return x
+    out = rt.empty(x.shape, out_dt)
+    call.sg_cast(rt.ctx, _p(x), _p(out), out_dt, x.numel())
+    return out
+
+
+def mask_mul(rt, dy, act, out_dt=SG_F32, out=None, accumulate=0):
+    if out is None:
+        out = rt.empty(dy.shape, out_dt)
+    call.sg_mask_mul(rt.ctx, _p(dy), _p(act), dt_of(act), _p(out), dt_of(out), dy.numel(), accumulate)
+    return out
+
+
+def axpby(rt, a, x, b=0.0, y=None, out=None):
+    if out is None:
+        out = rt.empty(x.shape, SG_F32)
+    call.sg_axpby(rt.ctx, float(a), _p(x), float(b), _p(y), _p(out), x.numel())
+    return out
+
+
+def scale_add(rt, sigma, a, x=None, out=None):
+    if out is None:
+        out = rt.empty(a.shape, SG_F32)
+    call.sg_scale_add(rt.ctx, _p(sigma), _p(a), _p(x), _p(out), a.numel())
+    return out
+
+
+def tanh_fwd(rt, x):
+    y = rt.empty(x.shape, SG_F32)
+    call.sg_tanh_fwd(rt.ctx, _p(x), _p(y), x.numel())
+    return y
+
+
+def tanh_bwd(rt, dy, y):
+    dx = rt.empty(y.shape, SG_F32)
+    call.sg_tanh_bwd(rt.ctx, _p(dy), _p(y), _p(dx), y.numel())
+    return dx
+
+
+def scale_rows_(rt, x, w):
+    rows = w.numel()
+    call.sg_scale_rows(rt.ctx, _p(x), _p(w), rows, x.numel() // rows)
+    return x
+
+
+def dot_into(rt, a, b, out, accumulate=1):
+    call.sg_dot(rt.ctx, _p(a), _p(b), a.numel(), _p(out), accumulate)
+
+
+def colsum_into(rt, x, cols, out, accumulate=1):
+    call.sg_colsum(rt.ctx, _p(x), dt_of(x), x.numel() // cols, cols, _p(out), accumulate)
+
+
+def avgpool2_fwd(rt, x):
+    n, h, w, c = x.shape
+    out = rt.empty((n, h // 2, w // 2, c), SG_F32)
+    call.sg_avgpool2_fwd(rt.ctx, _p(x), n, h, w, c, _p(out))
+    return out
+
+
+def avgpool2_bwd(rt, dout, out_dt):
+    n, ho, wo, c = dout.shape
+    dx = rt.empty((n, ho * 2, wo * 2, c), out_dt)
+    call.sg_avgpool2_bwd(rt.ctx, _p(dout), n, ho * 2, wo * 2, c, _p(dx), out_dt)
+    return dx
+
+
+def maxpool_fwd(rt, x, ph, pw):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // ph, w // pw, c), device=x.device, dtype=x.dtype)
+    call.sg_maxpool_fwd(rt.ctx, _p(x), dt_of(x), n, h, w, c, ph, pw, _p(out))
+    return out
+
+
+def maxpool_bwd(rt, dout, x, ph, pw, relu_mask, out_dt):
+    n, h, w, c = x.shape
+    dx = rt.empty(x.shape, out_dt)
+    call.sg_maxpool_bwd(rt.ctx, _p(dout), _p(x), dt_of(x), n, h, w, c, ph, pw, int(relu_mask), _p(dx), out_dt)
+    return dx
+
+
+def gap_relu_fwd(rt, x):
+    n, h, w, c = x.shape
+    out = rt.empty((n, c), SG_F32)
+    call.sg_gap_relu_fwd(rt.ctx, _p(x), n, h * w, c, _p(out))
+    return out
+
+
+def gap_relu_bwd(rt, dfeat, x):
+    n, h, w, c = x.shape
+    dx = rt.empty(x.shape, SG_F32)
+    call.sg_gap_relu_bwd(rt.ctx, _p(dfeat), _p(x), n, h * w, c, _p(dx))
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------------
+# batch norm
+# ----------------------------------------------------------------------------------------------------
+def bn_stats(rt, x) -> torch.Tensor:
+    """[2C] raw sums (sum x, sum x^2) over all rows of x [.., C]; all-reduced across replicas by the caller."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    nbytes = _abi.load().sg_bn_stats_scratch_bytes(rows, c)
+    scratch = rt.scratch("bn", nbytes)
+    sums = rt.empty((2 * c,), SG_F32)
+    call.sg_bn_stats(rt.ctx, _p(x), rows, c, _p(sums), _p(scratch), nbytes)
+    return sums
+
+
+def bn_finalize(rt, sums, count, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
+    mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
+    call.sg_bn_finalize(rt.ctx, _p(sums), float(count), c, eps, momentum, _p(mean), _p(rstd), _p(moving_mean), _p(moving_var))
+    return mean, rstd
+
+
+def bn_infer_prepare(rt, moving_mean, moving_var, eps=1e-3):
+    c = moving_mean.numel()
+    mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
+    call.sg_bn_infer_prepare(rt.ctx, _p(moving_mean), _p(moving_var), c, eps, _p(mean), _p(rstd))
+    return mean, rstd
+
+
+def bn_apply(rt, x, mean, rstd, gamma, beta, per_sample: bool, relu: bool, out_dt):
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    out = rt.empty(x.shape, out_dt)
+    call.sg_bn_apply(rt.ctx, _p(x), n, hw, c, _p(mean), _p(rstd), _p(gamma), _p(beta), c if per_sample else 0, int(relu),
+                     _p(out), out_dt)
+    return out
+
+
+def bn_bwd_reduce(rt, dy, act, x, mean, rstd):
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    s1, s2 = rt.empty((n, c), SG_F32), rt.empty((n, c), SG_F32)
+    call.sg_bn_bwd_reduce(rt.ctx, _p(dy), _p(act), dt_of(act) if act is not None else SG_F32, _p(x), n, hw, c, _p(mean),
+                          _p(rstd), _p(s1), _p(s2))
+    return s1, s2
+
+
+def bn_bwd_combine(rt, s1, s2, gamma, per_sample: bool):
+    n, c = s1.shape
+    ab = rt.empty((2 * c,), SG_F32)
+    call.sg_bn_bwd_combine(rt.ctx, _p(s1), _p(s2), _p(gamma), c if per_sample else 0, n, c, _p(ab))
+    return ab
+
+
+def bn_bwd_apply(rt, dy, act, x, mean, rstd, gamma, per_sample, ab, count, use_batch_terms, mask_by_x, out_dt, out=None,
+                 accumulate=0):
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    if out is None:
+        out = rt.empty(x.shape, out_dt)
+    call.sg_bn_bwd_apply(rt.ctx, _p(dy), _p(act), dt_of(act) if act is not None else SG_F32, _p(x), n, hw, c, _p(mean), _p(rstd),
+                         _p(gamma), c if per_sample else 0, _p(ab), float(count), int(use_batch_terms), int(mask_by_x), _p(out),
+                         dt_of(out), accumulate)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# dense, filter bank, attention, CTC, losses, optimizers, spectral norm
+# ----------------------------------------------------------------------------------------------------
+def gemm(rt, a, b, m, n, k, trans_a=False, trans_b=False, lda=None, ldb=None, out=None, ldc=None, bias=None, accumulate=0):
+    """out[m,n] (+)= op(a)[m,k] @ op(b)[k,n] + bias; row-major with explicit leading dimensions."""
+    if lda is None:
+        lda = m if trans_a else k
+    if ldb is None:
+        ldb = k if trans_b else n
+    if out is None:
+        out = rt.empty((m, n), SG_F32)
+    if ldc is None:
+        ldc = n
+    call.sg_gemm(rt.ctx, int(trans_a), int(trans_b), m, n, k, _p(a), lda, _p(b), ldb, _p(out), ldc, _p(bias), accumulate)
+    return out
+
+
+def filterbank_fwd(rt, z, z_stride, y, bank):
+    b, l = y.shape
+    out = rt.empty((b, 4, 4 * l, 512), SG_F32)
+    call.sg_filterbank_fwd(rt.ctx, _p(z), z_stride, _p(y), b, l, bank.shape[0], _p(bank), _p(out))
+    return out
+
+
+def filterbank_bwd(rt, dout, z, z_stride, y, bank, dbank, want_dz):
+    b, l = y.shape
+    dz0 = rt.empty((b, 32), SG_F32) if want_dz else None
+    call.sg_filterbank_bwd(rt.ctx, _p(dout), _p(z), z_stride, _p(y), b, l, bank.shape[0], _p(bank), _p(dbank), _p(dz0))
+    return dz0
+
+
+def attn_fwd(rt, theta, phi, g):
+    n, q, dk = theta.shape
+    kv, dv = g.shape[1], g.shape[2]
+    o, lse = rt.empty((n, q, dv), SG_F32), rt.empty((n, q), SG_F32)
+    call.sg_attn_fwd(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, _p(o), _p(lse))
+    return o, lse
+
+
+def attn_bwd(rt, theta, phi, g, o, lse, d_o):
+    n, q, dk = theta.shape
+    kv, dv = g.shape[1], g.shape[2]
+    dtheta, dphi, dg = rt.empty(theta.shape, SG_F32), rt.empty(phi.shape, SG_F32), rt.empty(g.shape, SG_F32)
+    call.sg_attn_bwd(rt.ctx, _p(theta), _p(phi), _p(g), _p(o), _p(lse), _p(d_o), n, q, kv, dk, dv, _p(dtheta), _p(dphi), _p(dg))
+    return dtheta, dphi, dg
+
+
+def ctc(rt, logits, labels, want_grad=True):
+    b, t, c = logits.shape
+    l = labels.shape[1]
+    loss = rt.empty((b,), SG_F32)
+    grad = rt.empty(logits.shape, SG_F32) if want_grad else None
+    call.sg_ctc(rt.ctx, _p(logits), _p(labels), b, t, c, l, _p(loss), _p(grad))
+    return loss, grad
+
+
+def adam_(rt, w, g, m, v, lr_t, beta1, beta2, eps):
+    call.sg_adam(rt.ctx, _p(w), _p(g), _p(m), _p(v), w.numel(), lr_t, beta1, beta2, eps)
+
+
+def rmsprop_(rt, w, g, ms, lr, rho, eps):
+    call.sg_rmsprop(rt.ctx, _p(w), _p(g), _p(ms), w.numel(), lr, rho, eps)
+
+
+def spectral_norm(rt, w, u, power_iteration=1):
+    """arch_ops.py:99-126 with explicit u [cols]; returns (w / sigma, u_hat, sigma)."""
+    cols = w.shape[-1]
+    rows = w.numel() // cols
+    w_out, u_out, sigma = rt.empty(w.shape, SG_F32), rt.empty((cols,), SG_F32), rt.empty((1,), SG_F32)
+    scratch = rt.empty((rows + cols + 4,), SG_F32)
+    call.sg_spectral_norm(rt.ctx, _p(w), rows, cols, _p(u), power_iteration, _p(w_out), _p(u_out), _p(sigma), _p(scratch))
+    return w_out, u_out, sigma

@@ -1,0 +1,113 @@
+"""Per-process runtime: one sg_ctx bound to one GPU and torch's current stream.
+
+PyTorch is used here for plumbing only: device memory (torch.empty), streams and torch.distributed (NCCL).
+All arithmetic is done by libsgan kernels.  Precision modes:
+    "bf16"  conv operands bf16, tcgen05 kind::f16, fp32 accumulate            (speed mode, 1e-2 parity)
+    "tf32"  conv operands fp32 read as tf32 by tcgen05 kind::tf32             (fp32 storage, ~1e-3 parity)
+    "fp32"  exact fp32 FFMA direct convolutions (no tensor cores)            (parity/debug mode)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import SG_BF16, SG_F32, call
+
+_MODES = ("bf16", "tf32", "fp32")
+
+
+class Runtime:
+    def __init__(self, device: Optional[int] = None, mode: Optional[str] = None):
+        if not torch.cuda.is_available():
+            raise _abi.SganError("no CUDA device visible: scrabble-gan_b200 has no CPU path")
+        _abi.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", torch.cuda.current_device()))
+        mode = mode or os.environ.get("SGAN_MODE", "bf16")
+        if mode not in _MODES:
+            raise ValueError("mode must be one of {}".format(_MODES))
+        self.device_index = device
+        torch.cuda.set_device(device)
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.current_stream(self.device)
+        handle = C.c_void_p()
+        call.sg_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(handle))
+        self.ctx = handle
+        self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.set_mode(mode)
+        # data-parallel state (see dp.py)
+        self.world_size = 1
+        self.rank = 0
+        self.process_group = None
+        self._scratch = {}
+
+    # ---- precision mode -----------------------------------------------------------------------------
+    def set_mode(self, mode: str) -> None:
+        if mode not in _MODES:
+            raise ValueError("mode must be one of {}".format(_MODES))
+        self.mode = mode
+        self.use_tc = mode in ("bf16", "tf32")
+        self.op_dt = SG_BF16 if mode == "bf16" else SG_F32
+        self.op_torch = torch.bfloat16 if mode == "bf16" else torch.float32
+
+    # ---- memory helpers (torch = allocator only) ------------------------------------------------------
+    def empty(self, shape, dt: int = SG_F32) -> torch.Tensor:
+        return torch.empty(shape, device=self.device, dtype=torch.float32 if dt == SG_F32 else torch.bfloat16)
+
+    def empty_op(self, shape) -> torch.Tensor:
+        return torch.empty(shape, device=self.device, dtype=self.op_torch)
+
+    def zeros(self, shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.zeros(shape, device=self.device, dtype=dtype)
+
+    def scratch(self, key: str, nbytes: int) -> torch.Tensor:
+        t = self._scratch.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 1), device=self.device, dtype=torch.uint8)
+            self._scratch[key] = t
+        return t
+
+    # ---- misc ---------------------------------------------------------------------------------------
+    def sync(self) -> None:
+        call.sg_ctx_sync(self.ctx)
+
+    def launch_count(self) -> int:
+        return int(_abi.load().sg_ctx_launch_count(self.ctx))
+
+    def use_current_stream(self) -> None:
+        self.stream = torch.cuda.current_stream(self.device)
+        call.sg_ctx_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream))
+
+    # ---- data parallel (sum all-reduce of small statistic vectors and of gradient buckets) -------------
+    def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+        return t
+
+
+_default: Optional[Runtime] = None
+
+
+def get_runtime() -> Runtime:
+    global _default
+    if _default is None:
+        _default = Runtime()
+    return _default
+
+
+def set_runtime(rt: Optional[Runtime]) -> None:
+    global _default
+    _default = rt
+
+
+def dt_of(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return SG_F32
+    if t.dtype == torch.bfloat16:
+        return SG_BF16
+    raise TypeError("unsupported tensor dtype {}".format(t.dtype))

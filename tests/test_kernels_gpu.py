@@ -1,0 +1,513 @@
+"""GPU parity tests of every libsgan primitive, called through the C ABI, against the CPU oracle
+(oracle/sgan_oracle.py, fp64) on the same seeded inputs.  Tolerances are written next to each check:
+exact-fp32 kernels 1e-4 relative (to the max magnitude of the expected tensor); tensor-core kernels are compared
+on inputs already rounded to the operand precision, so only accumulation order differs (2e-3)."""
+import importlib
+
+import pytest
+import torch
+
+import sgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ops = importlib.import_module("scrabble-gan_b200.ops")
+abi = importlib.import_module("scrabble-gan_b200._abi")
+F32, BF16 = abi.SG_F32, abi.SG_BF16
+
+
+def rel_err(got, exp):
+    got = got.detach().double().cpu()
+    exp = exp.detach().double().cpu()
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert torch.isfinite(got).all(), "non-finite values in result"
+    return float((got - exp).abs().max() / (exp.abs().max() + 1e-30))
+
+
+def check(got, exp, tol, what=""):
+    e = rel_err(got, exp)
+    assert e <= tol, "{}: rel err {:.3e} > {:.1e}".format(what, e, tol)
+
+
+def rnd(gen, *shape):
+    return torch.randn(*shape, generator=gen, dtype=torch.float64)
+
+
+def dev(rt, t, dt=F32):
+    return t.to(device=rt.device, dtype=torch.float32 if dt == F32 else torch.bfloat16).contiguous()
+
+
+def quant(t, mode):
+    """Round to the operand precision of a tensor-core mode (bf16: RN to 8 bits; tf32: RN to 11 bits)."""
+    if mode == "bf16":
+        return t.float().bfloat16().double()
+    if mode == "tf32":
+        f = t.float().contiguous()
+        i = f.view(torch.int32)
+        i = ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF)
+        return i.view(torch.float32).double()
+    return t.float().double()
+
+
+# ----------------------------------------------------------------------------------------------------
+# convolutions
+# ----------------------------------------------------------------------------------------------------
+CONV_CASES_SIMT = [
+    # n, h, w, ci, co, k, padding
+    (2, 8, 12, 1, 64, 3, "same"),
+    (2, 6, 10, 64, 1, 3, "same"),
+    (2, 8, 8, 64, 8, 1, "same"),
+    (3, 4, 10, 32, 64, 1, "same"),
+    (2, 2, 9, 16, 24, 2, "valid"),
+    (1, 5, 7, 3, 5, 3, "same"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES_SIMT)
+def test_conv_simt_fwd_dgrad_wgrad(rt, case):
+    n, h, w, ci, co, k, padding = case
+    g = torch.Generator().manual_seed(1)
+    x = rnd(g, n, h, w, ci).requires_grad_(True)
+    wt = (rnd(g, k, k, ci, co) * 0.2).requires_grad_(True)
+    b = rnd(g, co).requires_grad_(True)
+    y = O.conv2d(x, wt, b, padding)
+    dy = rnd(g, *y.shape)
+    y.backward(dy)
+
+    d = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding)
+    out = rt.empty(y.shape)
+    ops.conv_run(rt, d, dev(rt, x), dev(rt, wt), None, dev(rt, b), None, out)
+    check(out, y, 1e-4, "fwd")
+
+    # relu + mask + accumulate epilogue
+    d2 = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, relu=1, accumulate=1)
+    m = rnd(g, *y.shape)
+    out2 = dev(rt, torch.ones_like(y))
+    ops.conv_run(rt, d2, dev(rt, x), dev(rt, wt), None, dev(rt, b), dev(rt, m), out2)
+    check(out2, 1 + torch.relu(y) * (m > 0), 1e-4, "fwd epilogue")
+
+    dd = ops.desc_conv_dgrad(n, h, w, ci, co, k, k, padding)
+    dx = rt.empty(x.shape)
+    ops.conv_run(rt, dd, dev(rt, dy), dev(rt, wt), None, None, None, dx)
+    check(dx, x.grad, 1e-4, "dgrad")
+
+    dw = rt.zeros(wt.shape)
+    ops.conv_wgrad(rt, d, dev(rt, x), dev(rt, dy), dw, force_simt=True)
+    check(dw, wt.grad, 1e-4, "wgrad")
+
+    db = rt.zeros((co,))
+    ops.colsum_into(rt, dev(rt, dy), co, db)
+    check(db, b.grad, 1e-4, "dbias")
+
+
+CONV_CASES_TC = [
+    # n, h, w, ci, co, k, padding
+    (4, 8, 20, 64, 64, 3, "same"),
+    (3, 4, 10, 128, 256, 3, "same"),      # multi-image boxes
+    (2, 16, 40, 64, 512, 3, "same"),
+    (5, 8, 14, 64, 128, 3, "same"),       # ragged width (L = 7)
+    (2, 4, 10, 1024, 1024, 3, "same"),    # K = 9216
+    (3, 8, 20, 512, 1024, 1, "same"),     # 1x1 shortcut
+    (2, 2, 19, 512, 512, 2, "valid"),     # R.conv7
+    (1, 32, 160, 64, 64, 3, "same"),      # wide image, rows split across tiles
+    (7, 4, 2, 256, 128, 3, "same"),       # L = 1 deepest block
+]
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+@pytest.mark.parametrize("case", CONV_CASES_TC)
+def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
+    n, h, w, ci, co, k, padding = case
+    rt.set_mode(mode)
+    try:
+        dt = rt.op_dt
+        g = torch.Generator().manual_seed(2)
+        x = quant(rnd(g, n, h, w, ci), mode).requires_grad_(True)
+        wt = quant(rnd(g, k, k, ci, co) * (1.0 / (k * k * ci) ** 0.5), mode).requires_grad_(True)
+        b = rnd(g, co)
+        y = O.conv2d(x, wt, b, padding)
+        dy = quant(rnd(g, *y.shape), mode)
+        y.backward(dy)
+        xd, wd, dyd = dev(rt, x, dt), dev(rt, wt), dev(rt, dy, dt)
+
+        d = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, in_dt=dt)
+        assert ops.tc_ok(rt, d)
+        wp = ops.pack_weights(rt, d, wd)
+        out = rt.empty(y.shape)
+        ops.conv_run(rt, d, xd, wd, wp, dev(rt, b), None, out)
+        check(out, y, 2e-3, "tc fwd")
+
+        # bf16/relu/mask epilogue + accumulate variant
+        d2 = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, in_dt=dt, out_dt=dt, relu=1, mask_dt=dt)
+        m = rnd(g, *y.shape)
+        out2 = rt.empty(y.shape, dt)
+        ops.conv_run(rt, d2, xd, wd, wp, dev(rt, b), dev(rt, m, dt), out2)
+        check(out2, torch.relu(y) * (m > 0), 1e-2 if mode == "bf16" else 2e-3, "tc fwd epilogue")
+        d3 = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, in_dt=dt, accumulate=1)
+        out3 = dev(rt, torch.ones_like(y))
+        ops.conv_run(rt, d3, xd, wd, wp, None, None, out3)
+        check(out3, 1 + y - b, 2e-3, "tc fwd accumulate")
+
+        dd = ops.desc_conv_dgrad(n, h, w, ci, co, k, k, padding, in_dt=dt)
+        assert ops.tc_ok(rt, dd)
+        wpd = ops.pack_weights(rt, dd, wd)
+        dx = rt.empty(x.shape)
+        ops.conv_run(rt, dd, dyd, wd, wpd, None, None, dx)
+        check(dx, x.grad, 2e-3, "tc dgrad")
+
+        dw = rt.zeros(wt.shape)
+        dwg = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, in_dt=dt, out_dt=dt)
+        ops.conv_wgrad(rt, dwg, xd, dyd, dw)
+        check(dw, wt.grad, 2e-3, "tc wgrad")
+    finally:
+        rt.set_mode("fp32")
+
+
+CONVT_CASES = [
+    # n, h, w, ci, co, k, sy, sx
+    (2, 4, 8, 128, 64, 3, 2, 2),
+    (3, 4, 20, 512, 256, 3, 2, 2),
+    (2, 16, 20, 128, 64, 3, 2, 1),
+    (2, 4, 8, 128, 64, 1, 2, 2),
+    (2, 8, 12, 64, 64, 1, 2, 1),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "tf32"])
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose(rt, case, mode):
+    n, h, w, ci, co, k, sy, sx = case
+    rt.set_mode(mode)
+    try:
+        dt = rt.op_dt
+        tol = 1e-4 if mode == "fp32" else 2e-3
+        g = torch.Generator().manual_seed(3)
+        x = quant(rnd(g, n, h, w, ci), mode).requires_grad_(True)
+        wt = quant(rnd(g, k, k, co, ci) * (1.0 / (k * k * ci) ** 0.5), mode).requires_grad_(True)
+        b = rnd(g, co)
+        y = O.conv2d_transpose(x, wt, b, (sy, sx))
+        dy = quant(rnd(g, *y.shape), mode)
+        y.backward(dy)
+        xd, wd, dyd = dev(rt, x, dt), dev(rt, wt), dev(rt, dy, dt)
+
+        # forward: bias everywhere, then one accumulate launch per phase that has taps
+        out = dev(rt, (b.view(1, 1, 1, co)).expand(n, h * sy, w * sx, co).clone())
+        for (py, px) in ops.convT_phases(k, sy, sx):
+            d = ops.desc_convT_phase(n, h, w, ci, co, k, sy, sx, py, px, in_dt=dt, accumulate=1)
+            wp = ops.pack_weights(rt, d, wd) if ops.tc_ok(rt, d) else None
+            ops.conv_run(rt, d, xd, wd, wp, None, None, out)
+        check(out, y, tol, "convT fwd")
+
+        dd = ops.desc_convT_dgrad(n, h, w, ci, co, k, sy, sx, in_dt=dt)
+        wpd = ops.pack_weights(rt, dd, wd) if ops.tc_ok(rt, dd) else None
+        dx = rt.empty(x.shape)
+        ops.conv_run(rt, dd, dyd, wd, wpd, None, None, dx)
+        check(dx, x.grad, tol, "convT dgrad")
+
+        dw = rt.zeros(wt.shape)
+        dwg = ops.desc_convT_dgrad(n, h, w, ci, co, k, sy, sx, in_dt=dt, out_dt=dt)
+        ops.conv_wgrad(rt, dwg, dyd, xd, dw)
+        check(dw, wt.grad, tol, "convT wgrad")
+    finally:
+        rt.set_mode("fp32")
+
+
+# ----------------------------------------------------------------------------------------------------
+# element-wise, pooling
+# ----------------------------------------------------------------------------------------------------
+def test_elementwise(rt):
+    g = torch.Generator().manual_seed(4)
+    x = rnd(g, 3, 5, 7, 12)
+    xd = dev(rt, x)
+    r, c = ops.act_prep(rt, xd, True, True, BF16)
+    check(r, torch.relu(x), 1e-2, "relu bf16")
+    check(c, x, 1e-2, "copy bf16")
+    r, _ = ops.act_prep(rt, xd, True, False, F32)
+    assert torch.equal(r.cpu().double(), torch.relu(x.float()).double())
+    dy = rnd(g, *x.shape)
+    out = ops.mask_mul(rt, dev(rt, dy), r, F32)
+    assert torch.equal(out.cpu(), (dy.float() * (x.float() > 0)))
+    out = ops.mask_mul(rt, dev(rt, dy), r, F32, out=out, accumulate=1)
+    check(out, 2 * dy * (x > 0), 1e-6, "mask_mul accumulate")
+    y = rnd(g, *x.shape)
+    check(ops.axpby(rt, 0.5, xd, -2.0, dev(rt, y)), 0.5 * x - 2 * y, 1e-6, "axpby")
+    sig = dev(rt, torch.tensor([0.37], dtype=torch.float64))
+    check(ops.scale_add(rt, sig, xd, dev(rt, y)), 0.37 * x + y, 1e-6, "scale_add")
+    check(ops.scale_add(rt, sig, xd, None), 0.37 * x, 1e-6, "scale")
+    t = ops.tanh_fwd(rt, xd)
+    check(t, torch.tanh(x), 1e-5, "tanh")
+    check(ops.tanh_bwd(rt, dev(rt, dy), t), dy * (1 - torch.tanh(x) ** 2), 1e-5, "tanh bwd")
+    w = rnd(g, 3)
+    z = dev(rt, x.clone())
+    ops.scale_rows_(rt, z, dev(rt, w))
+    check(z, x * w.view(3, 1, 1, 1), 1e-6, "scale_rows")
+    acc = rt.zeros((1,))
+    ops.dot_into(rt, xd, dev(rt, y), acc, accumulate=0)
+    check(acc, (x * y).sum().view(1), 1e-5, "dot")
+
+
+def test_pooling(rt):
+    g = torch.Generator().manual_seed(5)
+    x = rnd(g, 2, 8, 12, 16).requires_grad_(True)
+    y = O.avg_pool_2x2_same(x)
+    dy = rnd(g, *y.shape)
+    y.backward(dy)
+    check(ops.avgpool2_fwd(rt, dev(rt, x)), y, 1e-6, "avgpool fwd")
+    check(ops.avgpool2_bwd(rt, dev(rt, dy), F32), x.grad, 1e-6, "avgpool bwd")
+    for ph, pw in ((2, 2), (2, 1)):
+        x = rnd(g, 2, 8, 12, 16).requires_grad_(True)
+        a = torch.relu(x)
+        y = O.max_pool(a, ph, pw)
+        dy = rnd(g, *y.shape)
+        y.backward(dy)
+        ad = dev(rt, a)
+        check(ops.maxpool_fwd(rt, ad, ph, pw), y, 1e-6, "maxpool fwd")
+        check(ops.maxpool_bwd(rt, dev(rt, dy), ad, ph, pw, True, F32), x.grad, 1e-6, "maxpool bwd (relu gated)")
+    x = rnd(g, 3, 4, 10, 256).requires_grad_(True)
+    y = torch.relu(x).mean(dim=(1, 2))
+    dy = rnd(g, *y.shape)
+    y.backward(dy)
+    check(ops.gap_relu_fwd(rt, dev(rt, x)), y, 1e-5, "gap fwd")
+    check(ops.gap_relu_bwd(rt, dev(rt, dy), dev(rt, x)), x.grad, 1e-6, "gap bwd")
+
+
+# ----------------------------------------------------------------------------------------------------
+# batch norm
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,per_sample", [(64, True), (512, True), (64, False), (256, True)])
+def test_batchnorm_train_fwd_bwd(rt, c, per_sample):
+    g = torch.Generator().manual_seed(6)
+    n, h, w = 3, 4, 6
+    x = (rnd(g, n, h, w, c) * 1.7 + 0.4).requires_grad_(True)
+    gamma = (rnd(g, n, c) if per_sample else rnd(g, c)).requires_grad_(True)
+    beta = (rnd(g, n, c) if per_sample else rnd(g, c)).requires_grad_(True)
+    mm, mv = rnd(g, c) * 0.1, rnd(g, c).abs() + 0.5
+    xh, nm, nv = O.batchnorm_train(x, mm, mv)
+    gb = (lambda t: t.view(n, 1, 1, c)) if per_sample else (lambda t: t)
+    y = torch.relu(xh * gb(gamma) + gb(beta))
+    dy = rnd(g, *y.shape)
+    y.backward(dy)
+
+    xd = dev(rt, x)
+    sums = ops.bn_stats(rt, xd)
+    mmd, mvd = dev(rt, mm), dev(rt, mv)
+    mean, rstd = ops.bn_finalize(rt, sums, n * h * w, c, mmd, mvd)
+    check(mmd, nm, 1e-5, "moving mean")
+    check(mvd, nv, 1e-5, "moving var")
+    gd, bd = dev(rt, gamma), dev(rt, beta)
+    act = ops.bn_apply(rt, xd, mean, rstd, gd, bd, per_sample, True, F32)
+    check(act, y, 1e-5, "bn apply")
+    s1, s2 = ops.bn_bwd_reduce(rt, dev(rt, dy), act, xd, mean, rstd)
+    ab = ops.bn_bwd_combine(rt, s1, s2, gd, per_sample)
+    dx = ops.bn_bwd_apply(rt, dev(rt, dy), act, xd, mean, rstd, gd, per_sample, ab, n * h * w, True, False, F32)
+    check(dx, x.grad, 1e-4, "bn dx")
+    if per_sample:
+        check(s2, gamma.grad, 1e-4, "dgamma")
+        check(s1, beta.grad, 1e-4, "dbeta")
+    else:
+        check(s2.sum(0), gamma.grad, 1e-4, "dgamma")
+        check(s1.sum(0), beta.grad, 1e-4, "dbeta")
+
+
+def test_batchnorm_inference_bwd(rt):
+    """R's BN: x = relu(conv) -> inference-mode BN with gamma/beta; dx gated by x > 0."""
+    g = torch.Generator().manual_seed(7)
+    n, h, w, c = 2, 4, 9, 512
+    pre = rnd(g, n, h, w, c).requires_grad_(True)
+    gamma, beta = rnd(g, c).requires_grad_(True), rnd(g, c).requires_grad_(True)
+    mm, mv = rnd(g, c) * 0.1, rnd(g, c).abs() + 0.5
+    x = torch.relu(pre)
+    y = O.batchnorm_infer(x, mm, mv) * gamma + beta
+    dy = rnd(g, *y.shape)
+    y.backward(dy)
+    xd = dev(rt, x)
+    mean, rstd = ops.bn_infer_prepare(rt, dev(rt, mm), dev(rt, mv))
+    out = ops.bn_apply(rt, xd, mean, rstd, dev(rt, gamma), dev(rt, beta), False, False, BF16)
+    check(out, y, 1e-2, "bn infer apply (bf16 out)")
+    s1, s2 = ops.bn_bwd_reduce(rt, dev(rt, dy), None, xd, mean, rstd)
+    check(s2.sum(0), gamma.grad, 1e-4, "dgamma")
+    check(s1.sum(0), beta.grad, 1e-4, "dbeta")
+    dx = ops.bn_bwd_apply(rt, dev(rt, dy), None, xd, mean, rstd, dev(rt, gamma), False, None, 1.0, False, True, F32)
+    check(dx, pre.grad, 1e-5, "dx gated")
+
+
+# ----------------------------------------------------------------------------------------------------
+# dense / filter bank / attention / CTC / losses / optimizers / spectral norm
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k,ta,tb", [(64, 128, 1024, 0, 0), (7, 81, 512, 0, 0), (64, 8, 20000, 1, 0), (33, 32, 64, 0, 1),
+                                         (5, 1, 1024, 0, 0), (1024, 1, 5, 1, 0)])
+def test_gemm(rt, m, n, k, ta, tb):
+    g = torch.Generator().manual_seed(8)
+    a = rnd(g, k, m) if ta else rnd(g, m, k)
+    b = rnd(g, n, k) if tb else rnd(g, k, n)
+    bias = rnd(g, n)
+    exp = (a.t() if ta else a) @ (b.t() if tb else b) + bias
+    out = ops.gemm(rt, dev(rt, a), dev(rt, b), m, n, k, bool(ta), bool(tb), bias=dev(rt, bias))
+    check(out, exp, 2e-5, "gemm")
+    out = ops.gemm(rt, dev(rt, a), dev(rt, b), m, n, k, bool(ta), bool(tb), out=out, accumulate=1)
+    check(out, 2 * exp - bias, 2e-5, "gemm accumulate")
+
+
+def test_filterbank(rt):
+    g = torch.Generator().manual_seed(9)
+    b, l, vocab = 3, 4, 11
+    bank = (rnd(g, vocab, 32, 8192) * 0.05).requires_grad_(True)
+    z = rnd(g, b, 128).requires_grad_(True)
+    y = torch.randint(0, vocab, (b, l), generator=g)
+    y[0, 1] = y[0, 0]        # repeated character
+    out = O.filter_bank(z[:, :32], y, bank)
+    dout = rnd(g, *out.shape)
+    out.backward(dout)
+    yd = y.to(rt.device, torch.int32)
+    got = ops.filterbank_fwd(rt, dev(rt, z), 128, yd, dev(rt, bank))
+    check(got, out, 1e-5, "filterbank fwd")
+    # bit-exact character -> filter indexing: a one-hot z picks single bank rows which must land unrounded
+    zi = torch.zeros(b, 128, dtype=torch.float64)
+    zi[:, 5] = 1.0
+    got1 = ops.filterbank_fwd(rt, dev(rt, zi), 128, yd, dev(rt, bank)).cpu()
+    bank32 = bank.detach().float()
+    for bi in range(b):
+        for li in range(l):
+            for k in range(0, 8192, 61):
+                hh, ww, cc = O.filter_bank_index_map(li, k)
+                assert got1[bi, hh, ww, cc].item() == bank32[y[bi, li], 5, k].item()
+    dbank = rt.empty(bank.shape)
+    dz0 = ops.filterbank_bwd(rt, dev(rt, dout), dev(rt, z), 128, yd, dev(rt, bank), dbank, True)
+    check(dbank, bank.grad, 1e-5, "dbank")
+    check(dz0, z.grad[:, :32], 1e-5, "dz0")
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 8, 12), (1, 32, 80), (3, 16, 40)])
+def test_attention(rt, n, h, w):
+    g = torch.Generator().manual_seed(10)
+    q, kv = h * w, (h // 2) * (w // 2)
+    theta = (rnd(g, n, q, 8) * 0.7).requires_grad_(True)
+    phi = (rnd(g, n, kv, 8) * 0.7).requires_grad_(True)
+    gg = rnd(g, n, kv, 32).requires_grad_(True)
+    attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+    o = attn @ gg
+    do = rnd(g, *o.shape)
+    o.backward(do)
+    td, pd, gd = dev(rt, theta), dev(rt, phi), dev(rt, gg)
+    od, lse = ops.attn_fwd(rt, td, pd, gd)
+    check(od, o, 1e-4, "attn fwd")
+    check(lse, torch.logsumexp(theta @ phi.transpose(1, 2), dim=-1), 1e-5, "lse")
+    dt_, dp_, dg_ = ops.attn_bwd(rt, td, pd, gd, od, lse, dev(rt, do))
+    check(dt_, theta.grad, 2e-4, "dtheta")
+    check(dp_, phi.grad, 2e-4, "dphi")
+    check(dg_, gg.grad, 2e-4, "dg")
+
+
+@pytest.mark.parametrize("b,l,c", [(4, 5, 53), (3, 10, 81), (2, 1, 53), (5, 3, 7)])
+def test_ctc(rt, b, l, c):
+    g = torch.Generator().manual_seed(11)
+    t = 4 * l - 1
+    logits = (rnd(g, b, t, c) * 2.0).requires_grad_(True)
+    labels = torch.randint(0, c - 1, (b, l), generator=g)
+    if l >= 3:
+        labels[0, 1] = labels[0, 0]      # repeated label forces a blank between them
+        labels[1, :] = labels[1, 0]      # a word of one repeated letter
+    probs = torch.softmax(logits, dim=-1)
+    loss = O.ctc_batch_cost(labels, probs, torch.full((b, 1), t), torch.full((b, 1), l))
+    loss.sum().backward()
+    got, grad = ops.ctc(rt, dev(rt, logits), labels.to(rt.device, torch.int32))
+    # north_star: CTC loss within 1e-4 relative
+    assert float(((got.cpu().double() - loss.view(-1)).abs() / loss.view(-1).abs()).max()) <= 1e-4
+    check(grad, logits.grad, 1e-3, "ctc grad wrt dense pre-activations")
+
+
+def test_ctc_brute_force(rt):
+    g = torch.Generator().manual_seed(12)
+    t, c = 5, 4
+    logits = rnd(g, 1, t, c)
+    labels = torch.tensor([[1, 1]])
+    probs = torch.softmax(logits, -1)[0]
+    q = (probs + 1e-7) / (1 + c * 1e-7)
+    exp = O.ctc_brute_force(q, [1, 1], c - 1)
+    got, _ = ops.ctc(rt, dev(rt, logits), labels.to(rt.device, torch.int32))
+    assert abs(got.item() - exp) / exp <= 1e-4
+
+
+@pytest.mark.parametrize("kind,use_w,balance", [("hinge", 0, 1), ("hinge", 1, 1), ("hinge", 0, 0), ("not_saturating", 1, 1),
+                                                ("not_saturating", 0, 1)])
+def test_losses_and_gradient_balance(rt, kind, use_w, balance):
+    g = torch.Generator().manual_seed(13)
+    b = 37
+    names = ["d_real", "d_fake", "s_real", "s_fake", "s5", "r_fake", "r_real"]
+    v = {k: rnd(g, b, 1).requires_grad_(True) for k in names}
+    with torch.no_grad():
+        v["r_fake"].mul_(0.5).add_(30.0)
+        v["r_real"].add_(20.0)
+    zero = torch.zeros(b, 1, dtype=torch.float64)
+    sr, sf, s5 = (v["s_real"], v["s_fake"], v["s5"]) if use_w else (zero, zero, zero)
+    if kind == "hinge":
+        d_loss, dlr, dlf, g_loss, s_loss, s1, s2 = O.hinge(v["d_real"], v["d_fake"], sr, sf)
+        if not use_w:
+            g_loss = -v["d_fake"]
+    else:
+        d_loss, dlr, dlf, g_loss, s_loss, s1, s2 = O.not_saturating(v["d_real"], v["d_fake"], sr, sf, s5)
+        if not use_w:
+            g_loss = O._sce(v["d_fake"], True)
+    g_bal, r_bal, alpha, r_std, g_std = O.apply_gradient_balancing(v["r_fake"], g_loss, 1.0)
+    g_added = g_loss + v["r_fake"]
+    g_final = g_bal if balance else g_added
+    gd = torch.autograd.grad(d_loss.sum(), [v["d_real"], v["d_fake"]], retain_graph=True)
+    gg = torch.autograd.grad(g_final.sum(), [v["d_fake"], v["r_fake"]] + ([v["s_fake"]] if use_w else []), retain_graph=True,
+                             allow_unused=True)
+    kid = abi.SG_LOSS_HINGE if kind == "hinge" else abi.SG_LOSS_NOT_SATURATING
+    D = {k: dev(rt, t.detach().view(-1)) for k, t in v.items()}
+    sums = torch.empty(abi.SG_LOSS_NSUMS, device=rt.device, dtype=torch.float64)
+    P = ops._p
+    abi.call.sg_loss_sums(rt.ctx, kid, use_w, P(D["d_real"]), P(D["d_fake"]), P(D["s_real"]), P(D["s_fake"]), P(D["s5"]),
+                          P(D["r_fake"]), P(D["r_real"]), b, P(sums))
+    ups = [rt.empty((b,)) for _ in range(8)]
+    stats = rt.empty((16,))
+    abi.call.sg_loss_finish(rt.ctx, kid, use_w, balance, 1.0, P(D["d_real"]), P(D["d_fake"]), P(D["s_real"]), P(D["s_fake"]),
+                            P(D["s5"]), P(D["r_fake"]), b, P(sums), *[P(u) for u in ups], P(stats))
+    up_d_real, up_d_fake_d, up_s_real, up_s_fake_w, up_s5, up_d_fake_g, up_s_fake_g, up_r_fake_g = ups
+    check(up_d_real, gd[0].view(-1), 1e-5, "d/d d_real")
+    check(up_d_fake_d, gd[1].view(-1), 1e-5, "d/d d_fake (D loss)")
+    check(up_d_fake_g, gg[0].view(-1), 1e-4, "d/d d_fake (G loss)")
+    check(up_r_fake_g, gg[1].view(-1), 1e-4, "d/d r_fake (G loss)")
+    if use_w:
+        gw = torch.autograd.grad(s_loss.sum(), [v["s_real"], v["s_fake"]], retain_graph=True)
+        check(up_s_real, gw[0].view(-1), 1e-5, "d/d s_real")
+        check(up_s_fake_w, gw[1].view(-1), 1e-5, "d/d s_fake (W loss)")
+        exp_sg = gg[2].view(-1) if gg[2] is not None else torch.zeros(b, dtype=torch.float64)
+        check(up_s_fake_g, exp_sg, 1e-4, "d/d s_fake (G loss)")
+    exp_stats = [v["r_fake"].mean(), v["r_real"].mean(), r_bal.mean(), g_loss.mean(), g_added.mean(), g_bal.mean(),
+                 d_loss.mean(), dlr.mean(), dlf.mean(), g_final.mean(), torch.tensor(1.0), r_std, g_std]
+    exp_stats += [s_loss.mean(), s1.mean(), s2.mean()] if use_w else [torch.tensor(0.0)] * 3
+    exp_stats = torch.stack([t.detach().double().reshape(()) for t in exp_stats])
+    got = stats.cpu().double()
+    assert float(((got - exp_stats).abs() / (exp_stats.abs() + 1e-3)).max()) <= 1e-4
+
+
+def test_adam_rmsprop(rt):
+    g = torch.Generator().manual_seed(14)
+    n = 100003
+    w, gr, m, v = rnd(g, n), rnd(g, n), rnd(g, n) * 0.1, rnd(g, n).abs() * 0.1
+    import math
+    for step, (b1, b2) in ((1, (0.0, 0.999)), (7, (0.5, 0.999))):
+        w1, m1, v1 = O.adam_update(w, gr, m, v, step, 2e-4, b1, b2)
+        lr_t = 2e-4 * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        wd, md, vd = dev(rt, w), dev(rt, m), dev(rt, v)
+        ops.adam_(rt, wd, dev(rt, gr), md, vd, lr_t, b1, b2, 1e-7)
+        check(wd, w1, 1e-6, "adam w")
+        check(md, m1, 1e-6, "adam m")
+        check(vd, v1, 1e-6, "adam v")
+    w1, ms1 = O.rmsprop_update(w, gr, v, 2e-4)
+    wd, msd = dev(rt, w), dev(rt, v)
+    ops.rmsprop_(rt, wd, dev(rt, gr), msd, 2e-4, 0.9, 1e-7)
+    check(wd, w1, 1e-6, "rmsprop w")
+    check(msd, ms1, 1e-6, "rmsprop ms")
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 64, 128), (32, 512), (1, 1, 1024, 1024)])
+def test_spectral_norm(rt, shape):
+    g = torch.Generator().manual_seed(15)
+    w = rnd(g, *shape)
+    u = rnd(g, 1, shape[-1])
+    exp = O.spectral_norm(w, u, 1)
+    got, u_hat, sigma = ops.spectral_norm(rt, dev(rt, w), dev(rt, u.view(-1)), 1)
+    check(got, exp, 1e-4, "spectral norm")
