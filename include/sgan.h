@@ -150,7 +150,8 @@ int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, const fl
 int sg_filterbank_fwd(sg_ctx* ctx, const float* z, int z_stride, const int* y, int b, int l, int vocab,
                       const float* bank, float* out);
 int sg_filterbank_bwd(sg_ctx* ctx, const float* dout, const float* z, int z_stride, const int* y, int b,
-                      int l, int vocab, const float* bank, float* dbank, float* dz0 /*[b,32] or NULL*/);
+                      int l, int vocab, const float* bank, float* dbank /*overwritten*/,
+                      float* dz0 /*dz0[b*dz_stride + j], j<32; or NULL*/, int dz_stride);
 
 /* ---- non-local block core (K12) -- arch_ops.py:51-61: o = softmax(theta phi^T) g, no scaling ------- */
 int sg_attn_fwd(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv,
@@ -179,6 +180,14 @@ int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, c
                    const float* r_fake, int b, const double* sums, float* up_d_real, float* up_d_fake_d,
                    float* up_s_real, float* up_s_fake_w, float* up_s_slot5, float* up_d_fake_g,
                    float* up_s_fake_g, float* up_r_fake_g, float* stats);
+
+/* stand-alone forms of the reference's public loss functions: terms is float[7][b] in net_loss.py's return order
+ * (d_loss, d_loss_real, d_loss_fake, g_loss, s_loss, s_loss_1, s_loss_2); s_c may be NULL for hinge. */
+int sg_loss_terms(sg_ctx* ctx, int kind, const float* d_real, const float* d_fake, const float* s_a,
+                  const float* s_b, const float* s_c, int b, float* terms);
+/* apply_gradient_balancing (data_utils.py:476-490): g_balanced, r_balanced [b]; stds = {std(r_fake), std(g_loss)} */
+int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b, float alpha,
+                    float* g_balanced, float* r_balanced, float* stds);
 
 /* ---- optimizers (K19) -- main.py:25-35: Keras Adam / RMSprop --------------------------------------- */
 int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t,

@@ -75,7 +75,7 @@ def conv2d(x: Tensor, w: Tensor, b: Optional[Tensor] = None, padding: str = "sam
         pt, pb = _same_pad(x.shape[1], kh, 1)
         pl, pr = _same_pad(x.shape[2], kw, 1)
         xt = F.pad(xt, (pl, pr, pt, pb))
-    y = F.conv2d(xt, w.permute(3, 2, 0, 1), b)
+    y = F.conv2d(xt, w.permute(3, 2, 0, 1).contiguous(), b)
     return y.permute(0, 2, 3, 1)
 
 
@@ -89,7 +89,7 @@ def conv2d_transpose(x: Tensor, w: Tensor, b: Optional[Tensor], strides: Tuple[i
     kh, kw = w.shape[0], w.shape[1]
     sh, sw = strides
     n_h, n_w = x.shape[1], x.shape[2]
-    full = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), None, stride=(sh, sw), padding=0)
+    full = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1).contiguous(), None, stride=(sh, sw), padding=0)
     pb_h, _ = _same_pad(n_h * sh, kh, sh)
     pb_w, _ = _same_pad(n_w * sw, kw, sw)
     y = full[:, :, pb_h:pb_h + n_h * sh, pb_w:pb_w + n_w * sw]
@@ -508,7 +508,7 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
                fake_labels: Tensor, z_or_style: Tensor, *, loss_fn: str = "hinge", apply_gradient_balance: bool = True,
                use_style_encoder: bool = False, use_style_promoter: bool = False, update_g: bool = True,
                lr: float = 2e-4, beta1: float = 0.0, beta2: float = 0.999, g_attn="B3", d_attn="B1",
-               return_grads: bool = False):
+               return_grads: bool = False, style_images: Optional[Tensor] = None):
     """One G + D + R (+ W) step following data_utils.py:385-473.
 
     params = {"G": {...}, "D": {...}, "R": {...}, ["W": {...}]}; tensors are updated functionally (new dicts
@@ -539,7 +539,7 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
     d_real = discriminator(images, D, d_attn)                                  # :406
     if Wn is not None:
         s_fake = discriminator(gen_images, Wn, d_attn)
-        s_real = discriminator(z_or_style, Wn, d_attn)                         # :409
+        s_real = discriminator(z_or_style if style_images is None else style_images, Wn, d_attn)   # :409
         s_real_real_imgs = discriminator(images, Wn, d_attn)                   # :410
     else:
         s_fake = torch.zeros_like(d_fake)

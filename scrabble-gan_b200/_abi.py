@@ -85,12 +85,14 @@ _PROTOS = {
     "sg_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _I, _L, _I, _P, _P, _P, _L, _P, _D, _I, _I, _P, _I, _I]),
     "sg_gemm": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I]),
     "sg_filterbank_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
-    "sg_filterbank_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "sg_filterbank_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I]),
     "sg_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sg_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "sg_ctc": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "sg_loss_sums": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "sg_loss_finish": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sg_loss_terms": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "sg_grad_balance": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "sg_adam": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_rmsprop": (_I, [_P, _P, _P, _P, _L, _F, _F, _F]),
     "sg_spectral_norm": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),

@@ -1,0 +1,239 @@
+"""train_step / apply_gradient_balancing / train shell with the reference's signatures
+(src/bigacgan/data_utils.py: train :198-352, train_step :358-473, apply_gradient_balancing :476-490,
+generate_and_save_images :493-519).
+
+train_step does what the reference's four GradientTapes + four apply_gradients do, as explicit forward and backward
+passes over libsgan kernels:
+    forward   G(z|style, fake labels);  D(fake), R(fake) [, W(fake)];  D(real) [, W(style), W(real)];  R(real)
+    losses    hinge | not_saturating, gradient balancing (loss-level, differentiable std), 16 statistics
+    backward  D: d_loss -> D (real + fake branches, dgrad + wgrad);  R: r_real -> R;  W: s_loss -> W;
+              G: g_final -> image through the frozen D, R (, W) (dgrad only) -> G (dgrad + wgrad)
+    update    Adam x4 (one fused launch per network); gradients are of SUMS over the batch
+Under data parallelism (runtime.world_size > 1) BN statistics, the loss sums and the gradient buckets are
+sum-all-reduced over NCCL so that N replicas on shards equal one replica on the concatenated batch."""
+from __future__ import annotations
+
+import os
+import random
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._abi import SG_F32, SG_LOSS_NSUMS, call
+from ..ops import _p
+from ..runtime import Runtime, get_runtime
+from . import net_loss
+from .net_architecture import _nhwc, to_device_f32, to_device_i32
+
+STAT_NAMES = ("r_loss_fake", "r_loss_real", "r_loss_balanced", "g_loss", "g_loss_added", "g_loss_balanced", "d_loss",
+              "d_loss_real", "d_loss_fake", "g_loss_final", "alpha", "r_loss_fake_std", "g_loss_std", "s_loss", "s_loss_real",
+              "s_loss_fake")
+
+
+def apply_gradient_balancing(r_fake_logits, g_loss, alpha=1):
+    """Reference data_utils.py:476-490: returns (g_balanced, r_loss_balanced, alpha, std(r_fake), std(g_loss));
+    population std, no zero guard.  Inputs are (B,1) device tensors (or DLPack producers)."""
+    from .._abi import from_dlpack
+    rt = get_runtime()
+    r = from_dlpack(r_fake_logits).to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
+    g = from_dlpack(g_loss).to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
+    b = r.numel()
+    g_bal, r_bal, stds = rt.empty((b,)), rt.empty((b,)), rt.empty((2,))
+    call.sg_grad_balance(rt.ctx, _p(r), _p(g), b, float(alpha), _p(g_bal), _p(r_bal), _p(stds))
+    return g_bal.view(b, 1), r_bal.view(b, 1), alpha, stds[0], stds[1]
+
+
+def _loss_kind(loss_fn) -> int:
+    kind = getattr(loss_fn, "sg_kind", None)
+    if kind is None:
+        name = getattr(loss_fn, "__name__", str(loss_fn))
+        if name in ("hinge", "not_saturating"):
+            return getattr(net_loss, name).sg_kind
+        raise ValueError("loss_fn must be net_loss.hinge or net_loss.not_saturating (got {!r})".format(loss_fn))
+    return kind
+
+
+def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discriminator, recognizer, style_promoter, composite_gan,
+               generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer, my_imgs, batch_size,
+               latent_dim, loss_fn, disc_iters, apply_gradient_balance, random_words, bucket_size, gen_path, *,
+               fake_labels=None, noise=None, verbose: bool = False, return_device_stats: bool = False):
+    """One G + D + R (+ W) training step.  Positional signature = the reference's (data_utils.py:358-360); returns the
+    same 16-tuple of Python floats in the same order (:470-473).
+
+    images (B,32,16*L_r[,1]) and labels (B,L_r) may be host numpy arrays (copied H2D here), torch tensors or DLPack
+    producers.  `style_promoter` may be None (G+D+R mode).  Keyword extensions: `fake_labels` (B,L_f) int and `noise`
+    (B,latent_dim) make the step deterministic (the reference samples both internally)."""
+    generator = composite_gan.generator
+    rt: Runtime = generator.rt
+    use_w = style_promoter is not None
+    kind = _loss_kind(loss_fn)
+
+    # ---- inputs (data_utils.py:385-395) ---------------------------------------------------------------------------
+    if fake_labels is None:
+        random_bucket_idx = random.randint(0, bucket_size - 1)
+        fake_labels = np.array([random.choice(random_words[random_bucket_idx]) for _ in range(batch_size)], np.int32)
+    x_real = _nhwc(to_device_f32(rt, images))
+    y_real = to_device_i32(rt, labels)
+    y_fake = to_device_i32(rt, fake_labels)
+    b = x_real.shape[0]
+    if generator.style is not None or use_w:
+        style_imgs = _nhwc(to_device_f32(rt, my_imgs))
+    if generator.style is not None:
+        g_in = style_imgs
+    else:
+        g_in = to_device_f32(rt, noise) if noise is not None else torch.randn(batch_size, latent_dim, device=rt.device)
+    assert g_in.shape[0] == b == y_fake.shape[0], "real and fake batches must have the same size (net_loss.py:49)"
+
+    # R's BatchNorm mode follows the Keras `trainable` flag at forward time
+    recognizer.bn_training = bool(recognizer.trainable)
+
+    nets = [discriminator, recognizer, generator] + ([style_promoter] if use_w else [])
+    for m in nets:
+        m.store.zero_grad()
+
+    # ---- forward passes (data_utils.py:398-415) -------------------------------------------------------------------
+    gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True)
+    d_fake, dfc = discriminator.forward(rt, gen_images)
+    r_fake, rfc = recognizer.forward(rt, gen_images, y_fake)
+    d_real, drc = discriminator.forward(rt, x_real)
+    r_real, rrc = recognizer.forward(rt, x_real, y_real)
+    s_fake = s_real = s_slot5 = None
+    if use_w:
+        s_fake, sfc = style_promoter.forward(rt, gen_images)
+        s_real, src = style_promoter.forward(rt, style_imgs)
+        if kind == net_loss.not_saturating.sg_kind:
+            s_slot5, _ = style_promoter.forward(rt, x_real)      # dead code under hinge: skipped there
+
+    # ---- losses, gradient balancing, statistics (data_utils.py:418-442) -------------------------------------------
+    sums = torch.empty(SG_LOSS_NSUMS, device=rt.device, dtype=torch.float64)
+    call.sg_loss_sums(rt.ctx, kind, int(use_w), _p(d_real), _p(d_fake), _p(s_real), _p(s_fake), _p(s_slot5), _p(r_fake),
+                      _p(r_real), b, _p(sums))
+    rt.allreduce_(sums)
+    ups = rt.empty((8, b))
+    stats = rt.empty((16,))
+    call.sg_loss_finish(rt.ctx, kind, int(use_w), int(bool(apply_gradient_balance)), 1.0, _p(d_real), _p(d_fake), _p(s_real),
+                        _p(s_fake), _p(s_slot5), _p(r_fake), b, _p(sums), _p(ups[0]), _p(ups[1]), _p(ups[2]), _p(ups[3]),
+                        _p(ups[4]), _p(ups[5]), _p(ups[6]), _p(ups[7]), _p(stats))
+    up_d_real, up_d_fake_d, up_s_real, up_s_fake_w, _up_s5, up_d_fake_g, up_s_fake_g, up_r_fake_g = ups
+
+    # ---- D, R, W gradients (data_utils.py:449-459) ----------------------------------------------------------------
+    discriminator.trainable = True
+    discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
+    discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
+    recognizer.trainable = True
+    recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
+    if use_w:
+        style_promoter.trainable = True
+        style_promoter.backward(rt, src, up_s_real, wgrad=True, want_dx=False)
+        style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
+
+    # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
+    update_g = (batch_idx + 1) % disc_iters == 0
+    if update_g:
+        recognizer.trainable = False
+        discriminator.trainable = False
+        dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
+        dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
+        ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
+        if use_w:
+            style_promoter.trainable = False
+            if kind == net_loss.hinge.sg_kind:
+                dimg_w = style_promoter.backward(rt, sfc, up_s_fake_g, wgrad=False, want_dx=True)
+                ops.axpby(rt, 1.0, dimg, 1.0, dimg_w, out=dimg)
+        generator.backward(rt, g_cache, dimg)
+
+    # ---- data-parallel gradient exchange: SUM (not mean), one bucket per network ------------------------------------
+    if rt.world_size > 1:
+        for m in nets:
+            if m is generator and not update_g:
+                continue
+            rt.allreduce_(m.store.g)
+
+    # ---- optimizer steps (same call shape as the reference) -------------------------------------------------------
+    def _apply(opt, model):
+        tv = model.store.trainable_variables
+        opt.apply_gradients(zip([v.grad for v in tv], tv))
+
+    _apply(discriminator_optimizer, discriminator)
+    _apply(recognizer_optimizer, recognizer)
+    if use_w:
+        _apply(stylepromoter_optimizer, style_promoter)
+    if update_g:
+        _apply(generator_optimizer, generator)
+
+    if return_device_stats:
+        return stats
+    host = stats.cpu().tolist()          # the reference's 16 .numpy() calls: one D2H copy + sync here
+    if verbose:
+        print('>%d, %d/%d, d=%.3f, d_real=%.3f, d_fake=%.3f, g_trad=%.3f, r_loss_fake=%.3f, g_loss=%.3f, r=%.3f, s=%.3f' % (
+            epoch_idx + 1, batch_idx + 1, batch_per_epoch, host[6], host[7], host[8], host[3], host[0], host[9], host[1], host[14]))
+    return tuple(host)
+
+
+def generate_and_save_images(model, epoch, test_input, gen_path, char_vector):
+    """Reference data_utils.py:493-519: G forward with training=False, (x+1)/2, dumped to disk (an .npy of the batch;
+    a PNG grid as well when matplotlib is importable)."""
+    predictions = model(test_input, training=False)
+    predictions = ((predictions + 1) / 2.0).cpu().numpy()
+    labels = np.asarray(test_input[1])
+    os.makedirs(gen_path, exist_ok=True)
+    np.save(os.path.join(gen_path, 'image_at_epoch_{:04d}.npy'.format(epoch)), predictions)
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        for i in range(min(predictions.shape[0], 16)):
+            plt.subplot(4, 4, i + 1)
+            plt.imshow(predictions[i, :, :, 0], cmap='gray')
+            plt.text(0, -1, "".join([char_vector[int(l)] for l in labels[i]]))
+            plt.axis('off')
+        plt.savefig(os.path.join(gen_path, 'image_at_epoch_{:04d}.png'.format(epoch)))
+        plt.close()
+    except Exception:
+        pass
+    return predictions
+
+
+def train(dataset, generator, discriminator, recognizer, style_promoter, composite_gan, checkpoint, checkpoint_prefix,
+          generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer, my_imgs, seed_labels,
+          buffer_size, batch_size, epochs, model_path, latent_dim, gen_path, loss_fn, disc_iters, apply_gradient_balance,
+          random_words, bucket_size, char_vector):
+    """Thin re-use of the reference's training shell (data_utils.py:198-352): same 26 positional arguments, same
+    summary-file columns, per-epoch save_weights of G and R.  `dataset` is any iterator of (images, labels)."""
+    generator_save_dir = os.path.join(checkpoint_prefix, 'generator/')
+    recognizer_save_dir = os.path.join(checkpoint_prefix, 'recognizer/')
+    os.makedirs(generator_save_dir, exist_ok=True)
+    os.makedirs(recognizer_save_dir, exist_ok=True)
+    os.makedirs(gen_path, exist_ok=True)
+    batch_per_epoch = int(buffer_size / batch_size) + 1
+    header = "disc_loss;disc_loss_real;disc_loss_fake;r_loss_real;r_loss_fake;r_loss_balanced;g_loss;g_lossT;g_lossS;" \
+             "g_loss_final;alpha;r_loss_fake_std;g_loss_std;s_loss;s_loss_real;s_loss_fake\n"
+    order = ("d_loss", "d_loss_real", "d_loss_fake", "r_loss_real", "r_loss_fake", "r_loss_balanced", "g_loss", "g_loss_added",
+             "g_loss_balanced", "g_loss_final", "alpha", "r_loss_fake_std", "g_loss_std", "s_loss", "s_loss_real", "s_loss_fake")
+    with open(os.path.join(gen_path, "batch_summary.txt"), "w") as batch_summary, \
+            open(os.path.join(gen_path, "epoch_summary.txt"), "w") as epoch_summary:
+        epoch_summary.write(header)
+        batch_summary.write(header)
+        for epoch_idx in range(epochs):
+            start = time.time()
+            totals = dict.fromkeys(STAT_NAMES, 0.0)
+            for batch_idx in range(batch_per_epoch):
+                image_batch, label_batch = next(dataset)
+                my_img_batch = random.choices(my_imgs, k=batch_size) if my_imgs is not None else None
+                out = train_step(epoch_idx, batch_idx, batch_per_epoch, image_batch, label_batch, discriminator, recognizer,
+                                 style_promoter, composite_gan, generator_optimizer, discriminator_optimizer,
+                                 recognizer_optimizer, stylepromoter_optimizer, my_img_batch, batch_size, latent_dim, loss_fn,
+                                 disc_iters, apply_gradient_balance, random_words, bucket_size, gen_path)
+                st = dict(zip(STAT_NAMES, out))
+                batch_summary.write(";".join(str(st[k]) for k in order) + "\n")
+                for k in STAT_NAMES:
+                    totals[k] += st[k]
+            epoch_summary.write(";".join(str(totals[k] / batch_per_epoch) for k in order) + "\n")
+            if seed_labels is not None:
+                generate_and_save_images(generator, epoch_idx + 1, seed_labels, gen_path, char_vector)
+            print('Time for epoch {} is {} sec'.format(epoch_idx + 1, time.time() - start))
+            generator.save_weights(os.path.join(generator_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))
+            recognizer.save_weights(os.path.join(recognizer_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))

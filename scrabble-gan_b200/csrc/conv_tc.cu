@@ -755,6 +755,11 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   int rc = tc_check(d, "sg_conv_wgrad_tc");
   if (rc != SG_OK) return rc;
   SG_REQUIRE(d->out_dt == d->in_dt, "sg_conv_wgrad_tc: dy must have the operand dtype (in_dt)");
+  if (d->in_dt != SG_BF16) {
+    // MN-major tf32 operands need the 128B-swizzle/32B-atom shared-memory layout, which is not built yet
+    sg_set_error("sg_conv_wgrad_tc: only bf16 operands are supported (tf32 filter gradients use sg_conv_wgrad_simt)");
+    return SG_ERR_UNSUPPORTED;
+  }
   SG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)dy & 15) == 0, "sg_conv_wgrad_tc: pointers must be 16-byte aligned");
   PFN_encodeTiled enc;
   rc = get_encode(ctx, &enc);

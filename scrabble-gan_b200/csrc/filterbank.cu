@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(128) k_fb_bwd_bank(const float* __restrict__ d
 
 // dz0[b, j] = sum_l sum_k bank[y[b,l], j, k] * dout[b,l,k].   grid: (FB_J, B), block 256
 __global__ void __launch_bounds__(256) k_fb_bwd_z(const float* __restrict__ dout, const int* __restrict__ y, int L,
-                                                   int vocab, const float* __restrict__ bank, float* __restrict__ dz0) {
+                                                   int vocab, const float* __restrict__ bank, float* __restrict__ dz0,
+                                                   int dz_stride) {
   __shared__ float sm[32];
   int j = blockIdx.x, b = blockIdx.y;
   float acc = 0.f;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) k_fb_bwd_z(const float* __restrict__ dout
     for (int k = threadIdx.x; k < FB_K; k += 256) acc = fmaf(bp[k], dout[fb_out_index(b, l, L, k)], acc);
   }
   float t = sg_block_sum(acc, sm);
-  if (threadIdx.x == 0) dz0[(long long)b * FB_J + j] = t;
+  if (threadIdx.x == 0) dz0[(long long)b * dz_stride + j] = t;
 }
 
 extern "C" {
@@ -89,7 +90,7 @@ int sg_filterbank_fwd(sg_ctx* ctx, const float* z, int z_stride, const int* y, i
 }
 
 int sg_filterbank_bwd(sg_ctx* ctx, const float* dout, const float* z, int z_stride, const int* y, int b, int l,
-                      int vocab, const float* bank, float* dbank, float* dz0) {
+                      int vocab, const float* bank, float* dbank, float* dz0, int dz_stride) {
   SG_REQUIRE(ctx && dout && z && y && bank && dbank, "sg_filterbank_bwd: NULL");
   SG_REQUIRE(b >= 0 && l >= 0 && vocab > 0 && z_stride >= FB_J, "sg_filterbank_bwd: bad sizes");
   dim3 grid(FB_K / 128, vocab);
@@ -97,7 +98,7 @@ int sg_filterbank_bwd(sg_ctx* ctx, const float* dout, const float* z, int z_stri
   SG_POST_LAUNCH(ctx);
   if (dz0 && b * l > 0) {
     dim3 g2(FB_J, b);
-    k_fb_bwd_z<<<g2, 256, 0, ctx->stream>>>(dout, y, l, vocab, bank, dz0);
+    k_fb_bwd_z<<<g2, 256, 0, ctx->stream>>>(dout, y, l, vocab, bank, dz0, dz_stride);
     SG_POST_LAUNCH(ctx);
   }
   return SG_OK;

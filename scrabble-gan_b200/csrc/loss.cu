@@ -169,3 +169,69 @@ int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone forms of the reference's public functions (used when callers invoke hinge / not_saturating /
+// apply_gradient_balancing directly rather than through train_step's fused path)
+// ---------------------------------------------------------------------------------------------------
+// terms[7][b]: d_loss, d_loss_real, d_loss_fake, g_loss, s_loss, s_loss_1, s_loss_2   (net_loss.py return order)
+__global__ void k_loss_terms(int kind, const float* d_real, const float* d_fake, const float* s_a, const float* s_b,
+                             const float* s_c, int b, float* terms) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
+    float dr = d_real[i], df = d_fake[i], sa = s_a[i], sb = s_b[i], sc = s_c ? s_c[i] : 0.f;
+    float dlr, dlf, g, s1, s2;
+    if (kind == SG_LOSS_HINGE) {
+      dlr = fmaxf(1.f - dr, 0.f); dlf = fmaxf(1.f + df, 0.f);
+      s1 = fmaxf(1.f - sa, 0.f); s2 = fmaxf(1.f + sb, 0.f);
+      g = -(df + sb);
+    } else {
+      dlr = sce(dr, 1.f); dlf = sce(df, 0.f);
+      s1 = sce(sa, 1.f); s2 = sce(sb, 0.f);
+      g = sce(df, 1.f) + sce(sc, 1.f);
+    }
+    terms[0 * b + i] = dlr + dlf; terms[1 * b + i] = dlr; terms[2 * b + i] = dlf; terms[3 * b + i] = g;
+    terms[4 * b + i] = s1 + s2; terms[5 * b + i] = s1; terms[6 * b + i] = s2;
+  }
+}
+
+// g_bal = g + alpha (sd_g / sd_r) r ; r_bal = alpha (sd_g / sd_r) r ; stds = {sd_r, sd_g}   (single CTA)
+__global__ void k_grad_balance(const float* r, const float* g, int b, float alpha, float* g_bal, float* r_bal, float* stds) {
+  __shared__ double sm[32];
+  double sr = 0, sr2 = 0, sg = 0, sg2 = 0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    double rv = r[i], gv = g[i];
+    sr += rv; sr2 += rv * rv; sg += gv; sg2 += gv * gv;
+  }
+  sr = block_sum_d(sr, sm); sr2 = block_sum_d(sr2, sm); sg = block_sum_d(sg, sm); sg2 = block_sum_d(sg2, sm);
+  double mr = sr / b, mg = sg / b;
+  double vr = sr2 / b - mr * mr, vg = sg2 / b - mg * mg;
+  double sdr = sqrt(vr > 0 ? vr : 0), sdg = sqrt(vg > 0 ? vg : 0);
+  float ratio = (float)(sdg / sdr);
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float rb = alpha * (ratio * r[i]);
+    r_bal[i] = rb;
+    g_bal[i] = g[i] + rb;
+  }
+  if (threadIdx.x == 0) { stds[0] = (float)sdr; stds[1] = (float)sdg; }
+}
+
+extern "C" {
+
+int sg_loss_terms(sg_ctx* ctx, int kind, const float* d_real, const float* d_fake, const float* s_a, const float* s_b,
+                  const float* s_c, int b, float* terms) {
+  SG_REQUIRE(ctx && d_real && d_fake && s_a && s_b && terms && b > 0, "sg_loss_terms: bad args");
+  SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_terms: bad loss kind %d", kind);
+  k_loss_terms<<<sg_div_up(b, 256), 256, 0, ctx->stream>>>(kind, d_real, d_fake, s_a, s_b, s_c, b, terms);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b, float alpha, float* g_balanced,
+                    float* r_balanced, float* stds) {
+  SG_REQUIRE(ctx && r_fake && g_loss && g_balanced && r_balanced && stds && b > 0, "sg_grad_balance: bad args");
+  k_grad_balance<<<1, 256, 0, ctx->stream>>>(r_fake, g_loss, b, alpha, g_balanced, r_balanced, stds);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -153,7 +153,7 @@ def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out) -
 
 def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False) -> None:
     """dw_master += filter gradient of the conv described by d."""
-    if not force_simt and tc_ok(rt, d) and d.in_dt == d.out_dt:
+    if not force_simt and tc_ok(rt, d) and d.in_dt == SG_BF16 and d.out_dt == SG_BF16:
         call.sg_conv_wgrad_tc(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _V(None), 0)
     else:
         call.sg_conv_wgrad_simt(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master))
@@ -355,10 +355,11 @@ def filterbank_fwd(rt, z, z_stride, y, bank):
     return out
 
 
-def filterbank_bwd(rt, dout, z, z_stride, y, bank, dbank, want_dz):
+def filterbank_bwd(rt, dout, z, z_stride, y, bank, dbank, dz0=None, dz_stride=32):
+    """dbank is overwritten; dz0[b*dz_stride + j] (j < 32) is written when given."""
     b, l = y.shape
-    dz0 = rt.empty((b, 32), SG_F32) if want_dz else None
-    call.sg_filterbank_bwd(rt.ctx, _p(dout), _p(z), z_stride, _p(y), b, l, bank.shape[0], _p(bank), _p(dbank), _p(dz0))
+    call.sg_filterbank_bwd(rt.ctx, _p(dout), _p(z), z_stride, _p(y), b, l, bank.shape[0], _p(bank), _p(dbank), _p(dz0),
+                           dz_stride)
     return dz0
 
 

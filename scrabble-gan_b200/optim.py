@@ -1,0 +1,106 @@
+"""Keras-semantics optimizers over flat parameter stores (reference main.py:25-35, data_utils.py:451-468).
+
+    Adam:    lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  w -= lr_t * m / (sqrt(v) + 1e-7)
+    RMSprop: ms = 0.9 ms + 0.1 g^2;  w -= lr * g / (sqrt(ms) + 1e-7)
+
+apply_gradients(zip(grads, vars)) keeps the reference's call shape.  When the variables are exactly the trainable
+variables of one ParamStore (the only way train_step calls it) the update is ONE fused launch over the flat
+buffers; otherwise it falls back to one launch per variable."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, Tuple
+
+import torch
+
+from . import ops
+from .params import ParamStore, Variable
+from .runtime import get_runtime
+
+
+class _FlatState:
+    def __init__(self, store: ParamStore, n_slots: int):
+        self.slots = [torch.zeros_like(store.w) for _ in range(n_slots)]
+
+
+class Adam:
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.iterations = 0
+        self._state: Dict[int, _FlatState] = {}
+
+    def _lr_t(self) -> float:
+        t = self.iterations
+        return self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+
+    def _slots(self, store: ParamStore) -> _FlatState:
+        st = self._state.get(id(store))
+        if st is None:
+            st = self._state[id(store)] = _FlatState(store, 2)
+        return st
+
+    def apply_gradients(self, grads_and_vars: Iterable[Tuple[torch.Tensor, Variable]]) -> None:
+        pairs = list(grads_and_vars)
+        if not pairs:
+            return
+        self.iterations += 1
+        lr_t = self._lr_t()
+        store = pairs[0][1].store
+        rt = store.rt
+        st = self._slots(store)
+        tv = store.trainable_variables
+        fused = len(pairs) == len(tv) and all(v is tv[i] and g.data_ptr() == v.grad.data_ptr() for i, (g, v) in enumerate(pairs))
+        if fused:
+            ops.adam_(rt, store.w, store.g, st.slots[0], st.slots[1], lr_t, self.beta_1, self.beta_2, self.epsilon)
+        else:
+            for g, v in pairs:
+                assert v.store is store, "one optimizer serves one network"
+                sl = slice(v.offset, v.offset + v.numel)
+                gg = g if isinstance(g, torch.Tensor) else torch.as_tensor(g)
+                gg = gg.to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
+                ops.adam_(rt, store.w[sl], gg, st.slots[0][sl], st.slots[1][sl], lr_t, self.beta_1, self.beta_2, self.epsilon)
+        store.version += 1
+
+    def state_dict(self):
+        return {"iterations": self.iterations, "slots": {k: [s.clone() for s in v.slots] for k, v in self._state.items()}}
+
+
+class RMSprop:
+    def __init__(self, learning_rate=0.001, rho=0.9, epsilon=1e-7):
+        self.learning_rate, self.rho, self.epsilon = float(learning_rate), float(rho), float(epsilon)
+        self.iterations = 0
+        self._state: Dict[int, _FlatState] = {}
+
+    def apply_gradients(self, grads_and_vars) -> None:
+        pairs = list(grads_and_vars)
+        if not pairs:
+            return
+        self.iterations += 1
+        store = pairs[0][1].store
+        rt = store.rt
+        st = self._state.get(id(store))
+        if st is None:
+            st = self._state[id(store)] = _FlatState(store, 1)
+        tv = store.trainable_variables
+        fused = len(pairs) == len(tv) and all(v is tv[i] and g.data_ptr() == v.grad.data_ptr() for i, (g, v) in enumerate(pairs))
+        if fused:
+            ops.rmsprop_(rt, store.w, store.g, st.slots[0], self.learning_rate, self.rho, self.epsilon)
+        else:
+            for g, v in pairs:
+                sl = slice(v.offset, v.offset + v.numel)
+                gg = g.to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
+                ops.rmsprop_(rt, store.w[sl], gg, st.slots[0][sl], self.learning_rate, self.rho, self.epsilon)
+        store.version += 1
+
+
+def setup_optimizer(g_lr, d_lr, r_lr, w_lr, beta_1, beta_2, loss_fn, disc_iters, apply_gradient_balance, rmsprop):
+    """Same signature and return tuple as the reference's gin-configurable setup_optimizer (main.py:25-35)."""
+    generator_optimizer = Adam(learning_rate=g_lr, beta_1=beta_1, beta_2=beta_2)
+    discriminator_optimizer = Adam(learning_rate=d_lr, beta_1=beta_1, beta_2=beta_2)
+    if rmsprop:
+        recognizer_optimizer = RMSprop(learning_rate=r_lr)
+    else:
+        recognizer_optimizer = Adam(learning_rate=r_lr, beta_1=beta_1, beta_2=beta_2)
+    stylepromoter_optimizer = Adam(learning_rate=w_lr, beta_1=beta_1, beta_2=beta_2)
+    return (generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer, loss_fn, disc_iters,
+            apply_gradient_balance)

@@ -372,7 +372,8 @@ def test_filterbank(rt):
                 hh, ww, cc = O.filter_bank_index_map(li, k)
                 assert got1[bi, hh, ww, cc].item() == bank32[y[bi, li], 5, k].item()
     dbank = rt.empty(bank.shape)
-    dz0 = ops.filterbank_bwd(rt, dev(rt, dout), dev(rt, z), 128, yd, dev(rt, bank), dbank, True)
+    dz0 = rt.empty((b, 32))
+    ops.filterbank_bwd(rt, dev(rt, dout), dev(rt, z), 128, yd, dev(rt, bank), dbank, dz0, 32)
     check(dbank, bank.grad, 1e-5, "dbank")
     check(dz0, z.grad[:, :32], 1e-5, "dz0")
 

@@ -1,0 +1,218 @@
+"""GPU parity tests of the networks and of the full train step against the CPU oracle (fp64) on identical weights
+and inputs.  Tolerances (BASELINE.json north_star): outputs, losses and gradients within 1e-3 relative in fp32
+mode, 1e-2..3e-2 in bf16 mode (relative to the largest magnitude of each tensor); CTC within 1e-4 (fp32)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import sgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+optim = importlib.import_module("scrabble-gan_b200.optim")
+
+IN_DIM = (32, 160, 1)
+
+
+def rel(got, exp):
+    got = torch.as_tensor(got).detach().double().cpu().reshape(-1)
+    exp = torch.as_tensor(exp).detach().double().cpu().reshape(-1)
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert torch.isfinite(got).all(), "non-finite values"
+    return float((got - exp).abs().max() / (exp.abs().max() + 1e-30))
+
+
+def check_dict(got, exp, tol, what, skip=()):
+    worst = ("", 0.0)
+    for k, e in exp.items():
+        if k in skip or k.endswith(O.NON_TRAINABLE_SUFFIXES):
+            continue
+        r = rel(got[k], e)
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] <= tol, "{}: worst tensor {} rel err {:.3e} > {:.1e}".format(what, worst[0], worst[1], tol)
+    return worst
+
+
+def load(model, params):
+    model.load_state_dict({k: v for k, v in params.items()})
+
+
+def test_discriminator_fwd_bwd(rt):
+    rt.set_mode("fp32")
+    P = O.make_discriminator_params(11, torch.float64, sigma=0.3, bias_scale=0.1)
+    D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt)
+    load(D, P)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(3, 32, 48, 1, generator=g, dtype=torch.float64) * 2 - 1).requires_grad_(True)
+    up = torch.randn(3, generator=g, dtype=torch.float64)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    logits = O.discriminator(x, leaf, "B1")
+    (logits.view(-1) * up).sum().backward()
+
+    xd = x.detach().float().to(rt.device)
+    D.store.zero_grad()
+    got, cache = D.forward(rt, xd)
+    assert rel(got, logits) <= 1e-3
+    dx = D.backward(rt, cache, up.float().to(rt.device), wgrad=True, want_dx=True)
+    assert rel(dx, x.grad) <= 1e-3
+    check_dict(D.store.grad_dict(), {k: v.grad for k, v in leaf.items()}, 1e-3, "D grads")
+
+
+def test_recognizer_fwd_bwd(rt):
+    rt.set_mode("fp32")
+    P = O.make_recognizer_params(12, torch.float64, output_classes=53, bias_scale=0.1)
+    g = torch.Generator().manual_seed(1)
+    for k in ("bn5", "bn6"):      # exercise non-trivial moving statistics / affine
+        P[k + ".moving_mean"] = torch.randn(512, generator=g, dtype=torch.float64) * 0.1
+        P[k + ".moving_var"] = torch.rand(512, generator=g, dtype=torch.float64) + 0.5
+        P[k + ".gamma"] = torch.rand(512, generator=g, dtype=torch.float64) + 0.5
+        P[k + ".beta"] = torch.randn(512, generator=g, dtype=torch.float64) * 0.1
+    R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt)
+    load(R, P)
+    b, l = 3, 3
+    x = (torch.rand(b, 32, 16 * l, 1, generator=g, dtype=torch.float64) * 2 - 1).requires_grad_(True)
+    y = torch.randint(0, 52, (b, l), generator=g)
+    up = torch.rand(b, generator=g, dtype=torch.float64) + 0.5
+    leaf = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    loss = O.recognizer(x, y, torch.full((b, 1), 4 * l - 1), torch.full((b, 1), l), leaf)
+    (loss.view(-1) * up).sum().backward()
+
+    R.store.zero_grad()
+    got, cache = R.forward(rt, x.detach().float().to(rt.device), y.to(rt.device, torch.int32))
+    assert float(((got.cpu().double() - loss.view(-1).detach()).abs() / loss.view(-1).detach().abs()).max()) <= 1e-4
+    dx = R.backward(rt, cache, up.float().to(rt.device), wgrad=True, want_dx=True)
+    assert rel(dx, x.grad) <= 1e-3
+    check_dict(R.store.grad_dict(), {k: v.grad for k, v in leaf.items() if v.grad is not None}, 1e-3, "R grads")
+
+
+def test_generator_fwd_bwd_and_inference(rt):
+    rt.set_mode("fp32")
+    P = O.make_generator_params(13, torch.float64, sigma=0.3, bias_scale=0.1)
+    G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt)
+    load(G, P)
+    g = torch.Generator().manual_seed(2)
+    b, l = 3, 2
+    z = torch.randn(b, 128, generator=g, dtype=torch.float64)
+    y = torch.randint(0, 52, (b, l), generator=g)
+    leaf = {k: (v.clone().requires_grad_(True) if not k.endswith(O.NON_TRAINABLE_SUFFIXES) else v.clone()) for k, v in P.items()}
+    new_stats = {}
+    img = O.generator_core(z, y, leaf, "B3", True, new_stats)
+    dimg = torch.randn(img.shape, generator=g, dtype=torch.float64)
+    (img * dimg).sum().backward()
+
+    G.store.zero_grad()
+    got, cache = G.forward(rt, z.float().to(rt.device), y.to(rt.device, torch.int32), training=True)
+    assert rel(got, img) <= 1e-3
+    G.backward(rt, cache, dimg.float().to(rt.device))
+    check_dict(G.store.grad_dict(), {k: v.grad for k, v in leaf.items() if v.requires_grad}, 1e-3, "G grads")
+    sd = G.state_dict()
+    for k, v in new_stats.items():
+        assert rel(sd[k], v) <= 1e-4, k
+    # inference path (run_inference.py:35 / generate_and_save_images): moving statistics, training=False
+    P2 = dict(P)
+    P2.update({k: v.detach() for k, v in new_stats.items()})
+    img_inf = O.generator_core(z, y, P2, "B3", False)
+    got_inf = G([z.float().numpy(), y.numpy()], training=False)
+    assert rel(got_inf, img_inf) <= 1e-3
+
+
+def _train_step_case(rt, mode, use_w, loss_name, balance, tol_out, tol_grad, b=3, l_r=2, l_f=3, style_encoder=False):
+    rt.set_mode(mode)
+    dt = torch.float64
+    g = torch.Generator().manual_seed(5)
+    P = {"G": O.make_generator_params(21, dt, sigma=0.2, bias_scale=0.05, style_encoder_too=style_encoder),
+         "D": O.make_discriminator_params(22, dt, sigma=0.2, bias_scale=0.05),
+         "R": O.make_recognizer_params(23, dt, bias_scale=0.05)}
+    if use_w:
+        P["W"] = O.make_discriminator_params(24, dt, sigma=0.2, bias_scale=0.05)
+    images = torch.rand(b, 32, 16 * l_r, 1, generator=g, dtype=dt) * 2 - 1
+    labels = torch.randint(0, 52, (b, l_r), generator=g)
+    fake_labels = torch.randint(0, 52, (b, l_f), generator=g)
+    z = torch.randn(b, 128, generator=g, dtype=dt)
+    style = torch.rand(b, 32, 160, 1, generator=g, dtype=dt) * 2 - 1
+    g_in = style if style_encoder else z
+    stats, newp, newo, grads, extra = O.train_step(P, {}, images, labels, fake_labels, g_in, loss_fn=loss_name,
+                                                   apply_gradient_balance=balance, use_style_encoder=style_encoder,
+                                                   use_style_promoter=use_w, return_grads=True, style_images=style)
+
+    G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, style_encoder=style_encoder)
+    D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt)
+    R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt)
+    W = na.make_style_promoter(IN_DIM, None, "B1", vis_model=False, rt=rt) if use_w else None
+    load(G, P["G"]); load(D, P["D"]); load(R, P["R"])
+    if use_w:
+        load(W, P["W"])
+    gan = na.make_gan(G, D, R, W, vis_model=False)
+    opts = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, getattr(nl, loss_name), 1, int(balance), 0)
+    g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = opts
+    before = {n: m.state_dict() for n, m in (("G", G), ("D", D), ("R", R))}
+    out = du.train_step(0, 0, 1, images.float().numpy(), labels.numpy(), D, R, W, gan, g_opt, d_opt, r_opt, w_opt,
+                        [s.numpy() for s in style.float()] if (style_encoder or use_w) else None, b, 128, loss_fn, disc_iters, agb,
+                        None, 10, "", fake_labels=fake_labels.numpy(), noise=None if style_encoder else z.float().numpy())
+    assert len(out) == 16
+    got = dict(zip(du.STAT_NAMES, out))
+    for k in O.STAT_NAMES:
+        e = stats[k]
+        assert abs(got[k] - e) <= tol_out * max(abs(e), 1e-2), "stat {}: {} vs {}".format(k, got[k], e)
+    models = {"G": G, "D": D, "R": R}
+    if use_w:
+        models["W"] = W
+    worst = {}
+    for n, m in models.items():
+        worst[n] = check_dict(m.store.grad_dict(), grads[n], tol_grad, n + " grads")
+    # weights after the Adam step: compare the update where the gradient is not vanishing (sign-of-zero ambiguity)
+    for n in ("G", "D", "R"):
+        after = models[n].state_dict()
+        for k, gexp in grads[n].items():
+            mask = gexp.abs() > 1e-3 * gexp.abs().max()
+            if mask.sum() == 0:
+                continue
+            d_got = (after[k].double().cpu() - before[n][k].double().cpu())[mask.reshape(after[k].shape)]
+            d_exp = (newp[n][k] - P[n][k])[mask]
+            assert rel(d_got, d_exp) <= max(tol_grad, 5e-3), "{}.{} update".format(n, k)
+    return worst
+
+
+def test_train_step_fp32_hinge_balanced(rt):
+    _train_step_case(rt, "fp32", False, "hinge", True, 1e-3, 1e-3)
+
+
+def test_train_step_fp32_style_promoter_not_saturating(rt):
+    _train_step_case(rt, "fp32", True, "not_saturating", False, 1e-3, 1e-3, b=2, l_r=2, l_f=2)
+
+
+def test_train_step_fp32_fork_mode_style_encoder(rt):
+    _train_step_case(rt, "fp32", True, "hinge", True, 1e-3, 1e-3, b=2, l_r=2, l_f=2, style_encoder=True)
+
+
+def test_train_step_tf32(rt):
+    _train_step_case(rt, "tf32", False, "hinge", True, 5e-3, 1e-2)
+
+
+def test_train_step_bf16(rt):
+    # bf16 operands (8-bit mantissa) through ~20 stacked convolutions: 1e-2 on outputs/losses, 3e-2 on the worst
+    # gradient tensor relative to its largest entry
+    _train_step_case(rt, "bf16", False, "hinge", True, 1e-2, 3e-2)
+    rt.set_mode("fp32")
+
+
+def test_public_loss_functions(rt):
+    rt.set_mode("fp32")
+    g = torch.Generator().manual_seed(7)
+    v = [torch.randn(9, 1, generator=g, dtype=torch.float64) for _ in range(5)]
+    dv = [t.float().to(rt.device) for t in v]
+    for name, args in (("hinge", 4), ("not_saturating", 5)):
+        exp = getattr(O, name)(*v[:args])
+        got = getattr(nl, name)(*dv[:args])
+        for a, e in zip(got, exp):
+            assert rel(a, e) <= 1e-5
+    gb, rb, alpha, rs, gs = du.apply_gradient_balancing(dv[0] + 30, dv[1])
+    egb, erb, _, ers, egs = O.apply_gradient_balancing(v[0] + 30, v[1])
+    assert rel(gb, egb) <= 1e-4 and rel(rb, erb) <= 1e-4
+    assert abs(float(rs) - float(ers)) <= 1e-4 * float(ers) and abs(float(gs) - float(egs)) <= 1e-4 * float(egs)
