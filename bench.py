@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the ScrabbleGAN train step (BASELINE.json metric: train images/sec on 32 x 16*len word batches).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype bf16|tf32|fp32] [--length L] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+    python bench.py --impl reference ...      # the reference's own CPU path (torch-CPU restatement, see below)
+
+Workload (BASELINE.json configs[3]): one full G + D + R train step with gradient balancing
+(hinge loss, Adam x3, z from noise), batch 64 PER GPU, fixed 5-character synthetic words for both the real and the
+fake batch (32x80 images, i.e. also the shape of configs[0], so both arms run the same config), data-parallel
+(weak scaling) with NCCL gradient sum-all-reduce and cross-replica BN statistics.  Synthetic data, random-init
+weights (there is no network for datasets / checkpoints).
+
+One JSON line is printed by rank 0:
+  value        images/s, whole job, inputs already resident in HBM, K steps timed with CUDA events, max over ranks
+  e2e          the same metric through the public train_step API with HOST (pinned numpy) inputs: H2D copies of
+               images / labels / noise and the D2H read of the 16 statistics are inside the timed region
+  roofline     the dominant kernel (tcgen05 implicit-GEMM conv) on its largest launch shape, timed live with CUDA
+               events inside the timed region; `step` adds the whole-step algorithmic TFLOP/s
+  cpu_baseline the reference's CPU path on this box's host cores (bounded sample), rank 0 only
+
+The reference arm (--impl reference): TensorFlow / Keras / gin are not installable in this image (no network, not
+in the wheelhouse), so `baseline/_ref` cannot be produced; following the tier contract the arm times the torch-CPU
+restatement of the reference step (oracle/sgan_oracle.py, "port") with all host threads on a bounded sample."""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# forward GFLOP per image (BASELINE.md section 3 / SURVEY.md section 8d), linear in L except attention
+GF_GC = {1: 0.326, 5: 1.736, 10: 3.734}
+GF_D = {1: 1.986, 5: 9.938, 10: 19.891}
+GF_R = {1: 0.196, 5: 0.988, 10: 1.977}
+
+
+def _interp(tab, l):
+    if l in tab:
+        return tab[l]
+    ks = sorted(tab)
+    lo = max(k for k in ks if k <= l) if l >= ks[0] else ks[0]
+    hi = min(k for k in ks if k >= l) if l <= ks[-1] else ks[-1]
+    if lo == hi:
+        return tab[lo] * l / lo
+    return tab[lo] + (tab[hi] - tab[lo]) * (l - lo) / (hi - lo)
+
+
+def step_gflop_per_image(lr, lf):
+    """Mode A (G+D+R) algorithmic FLOPs of one step per image: fwd + 2x fwd for trainable backward + 1x for frozen."""
+    gc, dlf, dlr, rlf, rlr = _interp(GF_GC, lf), _interp(GF_D, lf), _interp(GF_D, lr), _interp(GF_R, lf), _interp(GF_R, lr)
+    return (gc + dlf + rlf + dlr + rlr) + 2 * (dlr + dlf) + 2 * rlr + (dlf + rlf) + 2 * gc
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the torch-CPU restatement of the reference step
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(batch, length, steps, warmup, threads=None):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sgan_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    dt = torch.float32
+    g = torch.Generator().manual_seed(1234)
+    P = {"G": O.make_generator_params(1, dt), "D": O.make_discriminator_params(2, dt), "R": O.make_recognizer_params(3, dt)}
+    images = torch.rand(batch, 32, 16 * length, 1, generator=g) * 2 - 1
+    labels = torch.randint(0, 52, (batch, length), generator=g)
+    fake = torch.randint(0, 52, (batch, length), generator=g)
+    z = torch.randn(batch, 128, generator=g)
+    opt = {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, P, opt = O.train_step(P, opt, images, labels, fake, z, loss_fn="hinge", apply_gradient_balance=True)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    return sum(times) / len(times), threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = args.ref_batch
+    t, threads = cpu_reference_step_time(sample_b, args.length, args.steps, max(args.warmup, 1))
+    value = sample_b / t
+    line = {"impl": "reference", "metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ScrabbleGAN G+D+R train step, hinge + gradient balancing, fixed %d-char words (32x%d)"
+                                   % (args.length, 16 * args.length), "batch_per_gpu": args.batch, "word_len": args.length},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "batch %d of the same 32x%d workload per step (torch-CPU restatement of the reference "
+                                       "step; TensorFlow is not installable here)" % (sample_b, 16 * args.length)},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("SGAN_MODE", "bf16"), choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--length", type=int, default=5, help="word length (real and fake)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample batch for the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    runtime = importlib.import_module("scrabble-gan_b200.runtime")
+    na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+    du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+    nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+    optim = importlib.import_module("scrabble-gan_b200.optim")
+    dp = importlib.import_module("scrabble-gan_b200.dp")
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rt = runtime.Runtime(device=local_rank, mode=args.dtype)
+    runtime.set_runtime(rt)
+    dp.init_data_parallel(rt)
+    world, rank = rt.world_size, rt.rank
+    assert world == max(args.gpus, 1) or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    B, L = args.batch, args.length
+    in_dim = (32, 160, 1)
+    G = na.make_generator(128, in_dim, (32, 8192), None, "B3", 52, vis_model=False, rt=rt)
+    D = na.make_discriminator(in_dim, None, "B1", vis_model=False, rt=rt)
+    R = na.make_recognizer(in_dim, None, 53, vis_model=False, rt=rt)
+    gan = na.make_gan(G, D, R, None, vis_model=False)
+    dp.broadcast_parameters(rt, [G, D, R])
+    g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+
+    rng = np.random.RandomState(1234 + rank)
+    nbuf = 4       # rotate a few distinct synthetic batches
+    host = []
+    for _ in range(nbuf):
+        imgs = torch.from_numpy(rng.uniform(-1, 1, size=(B, 32, 16 * L, 1)).astype(np.float32)).pin_memory()
+        labels = torch.from_numpy(rng.randint(0, 52, size=(B, L)).astype(np.int32)).pin_memory()
+        fake = torch.from_numpy(rng.randint(0, 52, size=(B, L)).astype(np.int32)).pin_memory()
+        z = torch.from_numpy(rng.standard_normal(size=(B, 128)).astype(np.float32)).pin_memory()
+        host.append((imgs, labels, fake, z))
+    dev = [tuple(t.to(rt.device) for t in h) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    d2h_bytes = 16 * 4
+
+    def step(i, bufs, device_stats):
+        imgs, labels, fake, z = bufs[i % nbuf]
+        return du.train_step(0, i, 1, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, B, 128, loss_fn, disc_iters,
+                             agb, None, 10, "", fake_labels=fake, noise=z, return_device_stats=device_stats)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # live timing of the dominant kernel on its largest launch shape: D.B3.conv2 (fwd and dgrad), M = B*8*2L... K = 9216
+    ops = importlib.import_module("scrabble-gan_b200.ops")
+    prof = {"events": [], "on": False}
+    orig_conv_run = ops.conv_run
+
+    def conv_run_timed(rt_, d, x, w_master, w_packed, bias, mask, out):
+        hit = prof["on"] and w_packed is not None and d.c_in == 1024 and d.c_out == 1024 and d.ntaps == 9 and d.grid_h == 8
+        if hit:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_conv_run(rt_, d, x, w_master, w_packed, bias, mask, out)
+            e1.record()
+            prof["events"].append((e0, e1, 2.0 * d.n * d.grid_h * d.grid_w * d.ntaps * d.c_in * d.c_out))
+        else:
+            orig_conv_run(rt_, d, x, w_master, w_packed, bias, mask, out)
+    ops.conv_run = conv_run_timed
+
+    for i in range(args.warmup):
+        step(i, dev, True)
+    barrier()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = rt.launch_count()
+    prof["on"] = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i, dev, True)
+    e1.record()
+    barrier()
+    prof["on"] = False
+    launches = rt.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = e0.elapsed_time(e1)
+
+    # ---- end-to-end timing through the public API with host buffers ------------------------------------------------
+    for i in range(2):
+        step(i, host, False)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, host, False)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+
+    tt = torch.tensor([ms_dev, t_e2e * 1e3], device=rt.device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        images = B * world * args.steps
+        value = images / (ms_dev * 1e-3)
+        e2e = images / (ms_e2e * 1e-3)
+        gf_img = step_gflop_per_image(L, L)
+        step_tflops = gf_img * 1e-3 * B / (ms_dev / args.steps * 1e-3)          # per GPU
+        kern_ms = [a.elapsed_time(b) for a, b, _ in prof["events"]]
+        kern_fl = [f for _, _, f in prof["events"]]
+        if kern_ms:
+            avg_ms = sum(kern_ms) / len(kern_ms)
+            achieved = (sum(kern_fl) / len(kern_fl)) / (avg_ms * 1e-3) / 1e12
+        else:
+            avg_ms, achieved = None, None
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": "k_conv_tc<bf16> (tcgen05 implicit-GEMM conv), largest launch: D.B3.conv2 fwd/dgrad "
+                    "M=%d K=9216 N=1024" % (B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                    "launches_timed": len(kern_ms), "avg_launch_ms": avg_ms,
+                    "step": {"achieved": step_tflops, "frac": step_tflops / peak, "gflop_per_image": gf_img}}
+        line = {"metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "ScrabbleGAN G+D+R train step, hinge + gradient balancing, Adam x3, fixed %d-char words (32x%d), "
+                                       "batch %d per GPU" % (L, 16 * L, B), "batch_per_gpu": B, "global_batch": B * world, "word_len": L,
+                           "parallelism": "dp%d" % world,
+                           "l2": "no explicit flush: the per-step working set (>1 GB of activations, 0.7 GB weights+optimizer state) "
+                                 "exceeds the 126 MB L2 and input batches rotate"},
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                t, threads = cpu_reference_step_time(args.ref_batch, L, 1, 1)
+                line["cpu_baseline"] = {"value": args.ref_batch / t, "unit": "images/s", "cores": threads, "kind": "port",
+                                        "sample": "1 step at batch %d of the same 32x%d workload (torch-CPU restatement of the "
+                                                  "reference train step; TensorFlow is not installable here)" % (args.ref_batch, 16 * L)}
+            except Exception as ex:      # the baseline is a report, never a reason to lose the GPU numbers
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,22 +56,23 @@ def get_in_out_channels_disc(colors=1, resolution=32):
 # ----------------------------------------------------------------------------------------------------
 # input marshalling (host buffers / DLPack producers -> device tensors; plumbing only)
 # ----------------------------------------------------------------------------------------------------
-def to_device_f32(rt: Runtime, x) -> torch.Tensor:
+def _as_tensor(x, np_dtype):
+    if isinstance(x, torch.Tensor):
+        return x
     if isinstance(x, (list, tuple)) and len(x) > 0 and not np.isscalar(x[0]):
         x = np.stack([np.asarray(t.cpu() if isinstance(t, torch.Tensor) else t) for t in x], axis=0)
-    if isinstance(x, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        return t.to(rt.device, non_blocking=True)
-    t = from_dlpack(x)
-    return t.to(device=rt.device, dtype=torch.float32).contiguous()
+    if isinstance(x, (np.ndarray, list, tuple)):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np_dtype))
+    return from_dlpack(x)
+
+
+def to_device_f32(rt: Runtime, x) -> torch.Tensor:
+    """Host numpy / pinned torch / device torch / DLPack producer -> contiguous fp32 tensor on the runtime's GPU."""
+    return _as_tensor(x, np.float32).to(device=rt.device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
 def to_device_i32(rt: Runtime, x) -> torch.Tensor:
-    if isinstance(x, np.ndarray) or isinstance(x, (list, tuple)):
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int32))
-        return t.to(rt.device, non_blocking=True)
-    t = from_dlpack(x)
-    return t.to(device=rt.device, dtype=torch.int32).contiguous()
+    return _as_tensor(x, np.int32).to(device=rt.device, dtype=torch.int32, non_blocking=True).contiguous()
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
