@@ -9,15 +9,19 @@
 #define CTC_EPS 1e-7f
 #define NEG_INF (-INFINITY)
 
+// accurate (not fast-intrinsic) log-sum-exp: the recursion runs T steps in the log domain and its output is
+// differenced against log q when forming posteriors, so absolute log-domain error matters (CTC parity 1e-4)
 __device__ __forceinline__ float lse2(float a, float b) {
   float m = fmaxf(a, b);
   if (m == NEG_INF) return NEG_INF;
-  return m + __logf(__expf(a - m) + __expf(b - m));
+  return m + log1pf(expf(fminf(a, b) - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   float m = fmaxf(fmaxf(a, b), c);
   if (m == NEG_INF) return NEG_INF;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  // sum of the two non-max terms, then log1p
+  float s = expf(a - m) + expf(b - m) + expf(c - m) - 1.f;
+  return m + log1pf(s);
 }
 
 // dynamic smem: logq[T*C] | alpha[T*S] | beta[T*S] | occ[C] | ext[S] (int)
@@ -107,7 +111,7 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
       float ab = alpha[t * S + s] + beta[t * S + s];
       if (ab != NEG_INF) {
         int k = ext[s];
-        atomicAdd(&occ[k], __expf(ab - 2.f * logq[t * C + k] - logp));   // alpha*beta/q^2/P  (beta includes one q)
+        atomicAdd(&occ[k], expf(ab - 2.f * logq[t * C + k] - logp));   // alpha*beta/q^2/P  (beta includes one q)
       }
     }
     __syncthreads();
@@ -115,7 +119,7 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
     //   dL/du_k = q_k - (1/P) sum_s alpha_t(s) beta_t(s) / q_k = q_k - q_k * occ[k]
     float partial = 0.f;
     for (int k = tid; k < C; k += blockDim.x) {
-      float q = __expf(logq[t * C + k]);
+      float q = expf(logq[t * C + k]);
       float gu = q - q * occ[k];
       float p = q * (1.f + (float)C * CTC_EPS) - CTC_EPS;
       if (p < 0.f) p = 0.f;
@@ -125,7 +129,7 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
     }
     float dot = sg_block_sum(partial, red);
     for (int k = tid; k < C; k += blockDim.x) {
-      float q = __expf(logq[t * C + k]);
+      float q = expf(logq[t * C + k]);
       float p = q * (1.f + (float)C * CTC_EPS) - CTC_EPS;
       if (p < 0.f) p = 0.f;
       gz[t * C + k] = p * (occ[k] - dot);
