@@ -40,6 +40,7 @@ int sg_ctx_destroy(sg_ctx* ctx);
 int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
 int sg_ctx_sync(sg_ctx* ctx);
 long long sg_ctx_launch_count(sg_ctx* ctx);      /* kernels launched through this context so far */
+int sg_sizeof_conv_desc(void);                    /* sizeof(sg_conv_desc): layout guard for FFI mirrors */
 
 /* ---- convolution family (K1-K8) ------------------------------------------------------------------
  * One descriptor covers Conv2D forward, its dgrad (a conv with swapped channel roles), Conv2DTranspose

@@ -61,3 +61,6 @@ int sg_ctx_sync(sg_ctx* ctx) {
 long long sg_ctx_launch_count(sg_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 }  // extern "C"
+
+// layout guard for the ctypes mirror of sg_conv_desc
+extern "C" int sg_sizeof_conv_desc(void) { return (int)sizeof(sg_conv_desc); }

@@ -59,7 +59,7 @@ def run(mode, use_w, loss_name, balance, b, l_r, l_f, style_encoder, seed=5, bri
             print("  net %s worst maxrel %.2e (%s) worst l2rel %.2e" % (n, rows[0][0], rows[0][4], max(r[1] for r in rows)))
             continue
         print(" net", n, "worst tensors (maxrel, l2rel, fp32-oracle maxrel, max|exp|):")
-        for r in rows[:6]:
+        for r in rows[:14]:
             print("   %.3e %.3e %.3e %.3e %s" % r)
 
 if __name__ == "__main__":
@@ -68,6 +68,10 @@ if __name__ == "__main__":
     if "fork" in which: run("fp32", True, "hinge", True, 2, 2, 2, True)
     if "tf32" in which: run("tf32", False, "hinge", True, 3, 2, 3, False)
     if "bf16" in which: run("bf16", False, "hinge", True, 3, 2, 3, False)
+    if "matrix" in which:
+        run("fp32", True, "hinge", True, 2, 2, 2, False, seed=8)      # W, no style encoder
+        run("fp32", False, "hinge", True, 2, 2, 2, True, seed=8)      # style encoder, no W
+        run("fp32", True, "hinge", False, 2, 2, 2, False, seed=8)     # W, no balancing
     if "seeds" in which:
         for sd in (6, 7, 8, 9):
             run("fp32", True, "not_saturating", False, 2, 2, 2, False, seed=sd, brief=True)
