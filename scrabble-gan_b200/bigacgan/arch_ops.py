@@ -39,7 +39,12 @@ class NonLocalBlock:
         o, lse = ops.attn_fwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv))
         og = ops.gemm(rt, o, self.o.data, p, c, self.dv)
         out = ops.scale_add(rt, self.sigma.data, og, x)
-        return out.view(n, h, w, c), (x, theta, phi_f, phi, g_f, g, o, lse, og)
+        # every cached tensor keeps the image index as its first dimension so that sub-batches can be sliced
+        return out.view(n, h, w, c), (x, theta.view(n, q, self.dk), phi_f, phi, g_f, g, o, lse, og.view(n, h, w, c))
+
+    @staticmethod
+    def slice_cache(cache, a: int, b: int):
+        return tuple(t[a:b] for t in cache)
 
     def backward(self, rt: Runtime, cache, dout, wgrad: bool = True):
         """Returns dx; `dout` is consumed (the identity-path gradient is accumulated in place)."""

@@ -26,7 +26,7 @@ from .._abi import SG_F32, SG_LOSS_NSUMS, call
 from ..ops import _p
 from ..runtime import Runtime, get_runtime
 from . import net_loss
-from .net_architecture import _nhwc, to_device_f32, to_device_i32
+from .net_architecture import _as_tensor, _nhwc, to_device_f32, to_device_i32
 
 STAT_NAMES = ("r_loss_fake", "r_loss_real", "r_loss_balanced", "g_loss", "g_loss_added", "g_loss_balanced", "d_loss",
               "d_loss_real", "d_loss_fake", "g_loss_final", "alpha", "r_loss_fake_std", "g_loss_std", "s_loss", "s_loss_real",
@@ -75,10 +75,27 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     if fake_labels is None:
         random_bucket_idx = random.randint(0, bucket_size - 1)
         fake_labels = np.array([random.choice(random_words[random_bucket_idx]) for _ in range(batch_size)], np.int32)
-    x_real = _nhwc(to_device_f32(rt, images))
     y_real = to_device_i32(rt, labels)
     y_fake = to_device_i32(rt, fake_labels)
-    b = x_real.shape[0]
+    b = y_real.shape[0]
+    l_r, l_f = y_real.shape[1], y_fake.shape[1]
+    # R's BatchNorm mode follows the Keras `trainable` flag at forward time (SURVEY Q5)
+    recognizer.bn_training = bool(recognizer.trainable)
+    # When the real and the fake words have the same length, D and R see both batches in ONE pass over a
+    # [fake ; real] batch of 2B images (they have no cross-sample coupling: no batch-stat BN), which doubles the
+    # GEMM M of every layer; G writes its tanh output straight into the first half, the H2D copy of the real
+    # images lands in the second half.
+    fused = (l_r == l_f) and not recognizer.bn_training and os.environ.get("SGAN_NO_FUSED_BATCH", "0") != "1"
+    if fused:
+        xcat = rt.empty((2 * b, 32, 16 * l_r, 1))
+        src = _as_tensor(images, np.float32)
+        xcat[b:].copy_(src.reshape(b, 32, 16 * l_r, 1), non_blocking=True)
+        x_real = xcat[b:]
+        ycat = torch.empty((2 * b, l_r), device=rt.device, dtype=torch.int32)
+        ycat[:b].copy_(y_fake)
+        ycat[b:].copy_(y_real)
+    else:
+        x_real = _nhwc(to_device_f32(rt, images))
     if generator.style is not None or use_w:
         style_imgs = _nhwc(to_device_f32(rt, my_imgs))
     if generator.style is not None:
@@ -87,23 +104,27 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
         g_in = to_device_f32(rt, noise) if noise is not None else torch.randn(batch_size, latent_dim, device=rt.device)
     assert g_in.shape[0] == b == y_fake.shape[0], "real and fake batches must have the same size (net_loss.py:49)"
 
-    # R's BatchNorm mode follows the Keras `trainable` flag at forward time (SURVEY Q5)
-    recognizer.bn_training = bool(recognizer.trainable)
-
     nets = [discriminator, recognizer, generator] + ([style_promoter] if use_w else [])
     for m in nets:
         m.store.zero_grad()
 
     # ---- forward passes (data_utils.py:398-415) -------------------------------------------------------------------
-    gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True)
-    d_fake, dfc = discriminator.forward(rt, gen_images)
-    r_fake, rfc = recognizer.forward(rt, gen_images, y_fake)
-    d_real, drc = discriminator.forward(rt, x_real)
-    r_real, rrc = recognizer.forward(rt, x_real, y_real)
+    if fused:
+        gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True, img_out=xcat[:b])
+        d_cat, dcc = discriminator.forward(rt, xcat)
+        r_cat, rcc = recognizer.forward(rt, xcat, ycat)
+        d_fake, d_real = d_cat.view(-1)[:b], d_cat.view(-1)[b:]
+        r_fake, r_real = r_cat[:b], r_cat[b:]
+    else:
+        gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True)
+        d_fake, dfc = discriminator.forward(rt, gen_images)
+        r_fake, rfc = recognizer.forward(rt, gen_images, y_fake)
+        d_real, drc = discriminator.forward(rt, x_real)
+        r_real, rrc = recognizer.forward(rt, x_real, y_real)
     s_fake = s_real = s_slot5 = None
     if use_w:
         s_fake, sfc = style_promoter.forward(rt, gen_images)
-        s_real, src = style_promoter.forward(rt, style_imgs)
+        s_real, src_c = style_promoter.forward(rt, style_imgs)
         if kind == net_loss.not_saturating.sg_kind:
             s_slot5, _ = style_promoter.forward(rt, x_real)      # dead code under hinge: skipped there
 
@@ -114,20 +135,27 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     rt.allreduce_(sums)
     ups = rt.empty((8, b))
     stats = rt.empty((16,))
+    # rows 0,1 = (up_d_fake_d, up_d_real): adjacent and in [fake ; real] order for the fused D backward
+    up_d_fake_d, up_d_real, up_s_real, up_s_fake_w, _up_s5, up_d_fake_g, up_s_fake_g, up_r_fake_g = ups
     call.sg_loss_finish(rt.ctx, kind, int(use_w), int(bool(apply_gradient_balance)), 1.0, _p(d_real), _p(d_fake), _p(s_real),
-                        _p(s_fake), _p(s_slot5), _p(r_fake), b, _p(sums), _p(ups[0]), _p(ups[1]), _p(ups[2]), _p(ups[3]),
-                        _p(ups[4]), _p(ups[5]), _p(ups[6]), _p(ups[7]), _p(stats))
-    up_d_real, up_d_fake_d, up_s_real, up_s_fake_w, _up_s5, up_d_fake_g, up_s_fake_g, up_r_fake_g = ups
+                        _p(s_fake), _p(s_slot5), _p(r_fake), b, _p(sums), _p(up_d_real), _p(up_d_fake_d), _p(up_s_real),
+                        _p(up_s_fake_w), _p(_up_s5), _p(up_d_fake_g), _p(up_s_fake_g), _p(up_r_fake_g), _p(stats))
 
     # ---- D, R, W gradients (data_utils.py:449-459) ----------------------------------------------------------------
     discriminator.trainable = True
-    discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
-    discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
     recognizer.trainable = True
-    recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
+    if fused:
+        discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
+        dfc = discriminator.slice_cache(dcc, 0, b)
+        recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
+        rfc = recognizer.slice_cache(rcc, 0, b)
+    else:
+        discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
+        discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
+        recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
     if use_w:
         style_promoter.trainable = True
-        style_promoter.backward(rt, src, up_s_real, wgrad=True, want_dx=False)
+        style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
         style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
 
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------

@@ -151,6 +151,13 @@ class _DownTrunk:
         feats = ops.gap_relu_fwd(rt, net)                     # relu -> GlobalAveragePooling2D
         return feats, (caches, net)
 
+    def slice_cache(self, cache, a: int, b: int):
+        caches, net = cache
+        out = []
+        for i, (c, ca) in enumerate(caches):
+            out.append((ResNetBlockDown.slice_cache(c, a, b), NonLocalBlock.slice_cache(ca, a, b) if ca is not None else None))
+        return (out, net[a:b])
+
     def backward(self, rt: Runtime, cache, dfeats, wgrad: bool, want_dx: bool):
         caches, net = cache
         d = ops.gap_relu_bwd(rt, dfeats, net)
@@ -178,6 +185,10 @@ class Discriminator(_Model):
         feats, c = self.trunk.forward(rt, x)
         logits = self.dense.forward(rt, feats, x.shape[0])
         return logits, (feats, c)
+
+    def slice_cache(self, cache, a: int, b: int):
+        feats, c = cache
+        return (feats[a:b], self.trunk.slice_cache(c, a, b))
 
     def backward(self, rt, cache, up, wgrad: bool = True, want_dx: bool = False):
         """up [n] = d(sum target)/d(logit).  Accumulates parameter gradients when wgrad; returns d/d(image) or None."""
@@ -264,6 +275,13 @@ class Recognizer(_Model):
         cache = (x, a1, p1, a2, p2, a3, a4, p4, a5, b5, bc5, a6, b6, bc6, p6, a7, glogits)
         return loss, cache
 
+    @staticmethod
+    def slice_cache(cache, a: int, b: int):
+        x, a1, p1, a2, p2, a3, a4, p4, a5, b5, bc5, a6, b6, bc6, p6, a7, glogits = cache
+        sl = lambda t: t[a:b]
+        return (sl(x), sl(a1), sl(p1), sl(a2), sl(p2), sl(a3), sl(a4), sl(p4), sl(a5), sl(b5), bc5, sl(a6), sl(b6), bc6, sl(p6),
+                sl(a7), sl(glogits) if glogits is not None else None)
+
     def backward(self, rt, cache, up, wgrad: bool = True, want_dx: bool = False):
         x, a1, p1, a2, p2, a3, a4, p4, a5, b5, bc5, a6, b6, bc6, p6, a7, glogits = cache
         T = rt.op_dt
@@ -346,7 +364,7 @@ class Generator(_Model):
             self.style_dense = DenseLayer(self.store, "style_dense", self.style.out_channels, latent_dim)
         self.store.finalize()
 
-    def forward(self, rt, z_or_imgs, y, training: bool = True):
+    def forward(self, rt, z_or_imgs, y, training: bool = True, img_out=None):
         sc = None
         if self.style is not None:
             feats, tc = self.style.forward(rt, z_or_imgs)
@@ -371,7 +389,7 @@ class Generator(_Model):
             count = 1
         act = ops.bn_apply(rt, net, mean, rstd, self.bn.gamma.data, self.bn.beta.data, False, True, rt.op_dt)
         pre = self.out.forward(rt, act)
-        img = ops.tanh_fwd(rt, pre)
+        img = ops.tanh_fwd(rt, pre, img_out)
         return img, (sc, z, ec, caches, net, mean, rstd, count, act, training, img)
 
     def backward(self, rt, cache, dimg):

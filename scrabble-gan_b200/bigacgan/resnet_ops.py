@@ -127,6 +127,12 @@ class ResNetBlockDown:
         out = h2 if self.is_last else ops.avgpool2_fwd(rt, h2)
         return out, (xr, xs, h1, (h, w))
 
+    @staticmethod
+    def slice_cache(cache, a: int, b: int):
+        """Cache of the sub-batch [a, b) of a forward pass (views, no copies)."""
+        xr, xs, h1, hw = cache
+        return (xr[a:b], xs[a:b], h1[a:b], hw)
+
     def backward(self, rt: Runtime, cache, dout, wgrad: bool = True, want_dx: bool = True):
         xr, xs, h1, (h, w) = cache
         dpre = ops.cast(rt, dout, rt.op_dt) if self.is_last else ops.avgpool2_bwd(rt, dout, rt.op_dt)

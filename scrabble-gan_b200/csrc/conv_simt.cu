@@ -221,6 +221,126 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const v
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Edge-layer specialisations (K8).  The image-side layers (Cin = 1: D/W/style B1.conv1 + shortcut, R.conv1) and the
+// single-channel output conv (Cout = 1: G.out, and the input gradients of the Cin = 1 layers) have a huge pixel
+// count but K = 9 or N = 1: they are HBM-bound streaming kernels, not GEMMs.
+// ---------------------------------------------------------------------------------------------------
+struct Pix { int n, y, x; };
+__device__ __forceinline__ Pix decode_pix(long long p, int gh, int gw) {
+  Pix r;
+  r.x = (int)(p % gw);
+  p /= gw;
+  r.y = (int)(p % gh);
+  r.n = (int)(p / gh);
+  return r;
+}
+
+// filter gradient with ONE narrow side: WIDE = number of channels on the wide side (<= 256, divides 256).
+//   NARROW_IN  (c_in == 1): dW[t][co] += sum_p in[p + tap_t] * dy[p, co]      thread <-> co
+//   !NARROW_IN (c_out == 1): dW[t][ci] += sum_p in[p + tap_t, ci] * dy[p]     thread <-> ci
+template <bool NARROW_IN>
+__global__ void __launch_bounds__(256) k_wgrad_narrow(sg_conv_desc d, const void* __restrict__ in, const void* __restrict__ dy,
+                                                       float* __restrict__ dw, long long pos_per_block) {
+  extern __shared__ float red[];                       // [lanes][ntaps][wide]
+  const int wide = NARROW_IN ? d.c_out : d.c_in;
+  const int lanes = 256 / wide;
+  const int ch = threadIdx.x % wide, lane = threadIdx.x / wide;
+  const long long P = (long long)d.n * d.grid_h * d.grid_w;
+  const long long p0 = (long long)blockIdx.x * pos_per_block;
+  const long long p1 = p0 + pos_per_block < P ? p0 + pos_per_block : P;
+  float acc[SG_MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < SG_MAX_TAPS; ++t) acc[t] = 0.f;
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      Pix q = decode_pix(p, d.grid_h, d.grid_w);
+      long long opix = ((long long)q.n * d.out_h + q.y) * d.out_w + q.x;
+      float dyv = NARROW_IN ? ld_any(dy, opix * d.c_out + ch, d.out_dt) : ld_any(dy, opix, d.out_dt);
+#pragma unroll
+      for (int t = 0; t < SG_MAX_TAPS; ++t) {
+        if (t < d.ntaps) {
+          int iy = q.y + d.tap_dy[t], ix = q.x + d.tap_dx[t];
+          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
+            long long ipix = ((long long)q.n * d.in_h + iy) * d.in_w + ix;
+            float xv = NARROW_IN ? ld_any(in, ipix, d.in_dt) : ld_any(in, ipix * d.c_in + ch, d.in_dt);
+            acc[t] = fmaf(xv, dyv, acc[t]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < SG_MAX_TAPS; ++t)
+      if (t < d.ntaps) red[((long long)lane * d.ntaps + t) * wide + ch] = acc[t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.ntaps * wide; i += 256) {
+    int t = i / wide, c = i % wide;
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += red[((long long)l * d.ntaps + t) * wide + c];
+    long long off = d.tap_w_off[t] + (NARROW_IN ? (long long)c * d.w_co_stride : (long long)c * d.w_ci_stride);
+    atomicAdd(dw + off, sum);
+  }
+}
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = sg_ld4(p), b = sg_ld4(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  float4 a = sg_ld4(p), b = sg_ld4(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// forward-type conv with c_out == 1 and c_in % 8 == 0 (c_in/8 a power of two <= 32): c_in/8 threads per output
+// pixel, each holding its 8 channels x ntaps weights in registers; shuffle reduction; full epilogue.
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_conv_fwd_cout1(sg_conv_desc d, const TIn* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const void* __restrict__ mask,
+                                                         void* __restrict__ out) {
+  const int tpp = d.c_in / 8;                            // threads per pixel
+  const int sub = threadIdx.x % tpp;
+  const int pix_per_block = 256 / tpp;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      wr[t][j] = (t < d.ntaps) ? w[d.tap_w_off[t] + (long long)(sub * 8 + j) * d.w_ci_stride] : 0.f;
+  const long long P = (long long)d.n * d.grid_h * d.grid_w;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long long p = (long long)blockIdx.x * pix_per_block + threadIdx.x / tpp; p < P + pix_per_block;
+       p += (long long)gridDim.x * pix_per_block) {
+    const bool live = p < P;
+    float acc = 0.f;
+    Pix q = decode_pix(live ? p : 0, d.grid_h, d.grid_w);
+    if (live) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t < d.ntaps) {
+          int iy = q.y * d.in_sy + d.tap_dy[t], ix = q.x * d.in_sx + d.tap_dx[t];
+          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
+            float v[8];
+            load8(in + (((long long)q.n * d.in_h + iy) * d.in_w + ix) * d.c_in + sub * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wr[t][j], acc);
+          }
+        }
+      }
+    }
+    for (int o = tpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) {
+      long long idx = ((long long)q.n * d.out_h + q.y * d.out_sy + d.out_py) * d.out_w + q.x * d.out_sx + d.out_px;
+      float v = acc + b0;
+      if (d.relu) v = fmaxf(v, 0.f);
+      if (mask) v = ld_any(mask, idx, d.mask_dt) > 0.f ? v : 0.f;
+      if (d.accumulate) v += ld_any(out, idx, d.out_dt);
+      st_any(out, idx, d.out_dt, v);
+    }
+    if (p >= P) break;
+  }
+}
+
 static int check_desc(const sg_conv_desc* d, const char* who) {
   SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   SG_REQUIRE(d->n >= 0 && d->in_h > 0 && d->in_w > 0 && d->c_in > 0 && d->out_h > 0 && d->out_w > 0 && d->c_out > 0,
@@ -243,6 +363,21 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
   if (rc != SG_OK) return rc;
   long long M = (long long)d->n * d->grid_h * d->grid_w;
   if (M == 0) return SG_OK;
+  {
+    int tpp = d->c_in / 8;
+    bool pow2 = tpp >= 1 && tpp <= 32 && (tpp & (tpp - 1)) == 0;
+    if (d->c_out == 1 && d->c_in % 8 == 0 && pow2 && d->ntaps <= 9 && ((uintptr_t)in & 15) == 0) {
+      int ppb = 256 / tpp;
+      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 8;
+      int grid = (int)(need < cap ? need : cap);
+      if (d->in_dt == SG_F32)
+        k_conv_fwd_cout1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, mask, out);
+      else
+        k_conv_fwd_cout1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const __nv_bfloat16*)in, w_master, bias, mask, out);
+      SG_POST_LAUNCH(ctx);
+      return SG_OK;
+    }
+  }
   if (d->c_out > 16) {
     dim3 grid(sg_div_up(M, CS_TM), sg_div_up(d->c_out, 64));
     k_conv_fwd_simt<64, 4><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
@@ -260,6 +395,25 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
   if (rc != SG_OK) return rc;
   long long P = (long long)d->n * d->grid_h * d->grid_w;
   if (P == 0) return SG_OK;
+  {
+    bool unit = d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0;
+    bool narrow_in = d->c_in == 1 && d->c_out <= 256 && 256 % d->c_out == 0;
+    bool narrow_out = d->c_out == 1 && d->c_in <= 256 && 256 % d->c_in == 0;
+    if (unit && (narrow_in || narrow_out)) {
+      int wide = narrow_in ? d->c_out : d->c_in;
+      int lanes = 256 / wide;
+      long long blocks = (long long)ctx->num_sms * 4;
+      long long min_pos = 8LL * lanes;
+      if (blocks > (P + min_pos - 1) / min_pos) blocks = (P + min_pos - 1) / min_pos;
+      long long ppb = (P + blocks - 1) / blocks;
+      blocks = (P + ppb - 1) / ppb;
+      size_t smem = sizeof(float) * (size_t)lanes * d->ntaps * wide;
+      if (narrow_in) k_wgrad_narrow<true><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb);
+      else k_wgrad_narrow<false><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb);
+      SG_POST_LAUNCH(ctx);
+      return SG_OK;
+    }
+  }
   int gx = sg_div_up(d->ntaps * d->c_in, CS_TM), gy = sg_div_up(d->c_out, 64);
   long long tiles = (long long)gx * gy;
   long long splits = (2LL * ctx->num_sms + tiles - 1) / tiles;

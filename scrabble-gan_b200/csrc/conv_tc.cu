@@ -608,12 +608,11 @@ static void choose_box(int gw, int gh, int n, int max_rows, int mult, int* TW, i
       if (th == last_th) continue;
       last_th = th;
       if ((long long)tw * th > max_rows) continue;
-      int tn = 1;
-      if (tw >= gw && th >= gh) {
-        tn = max_rows / (tw * th);
-        if (tn > n) tn = n;
-        if (tn < 1) tn = 1;
-      }
+      // a box is any rectangle in (x, y, image) space: several images may share a box even when it covers only
+      // part of each image (e.g. 20 x 2 rows x 3 images = 120 of 128 accumulator rows for an 8 x 20 map)
+      int tn = max_rows / (tw * th);
+      if (tn > n) tn = n;
+      if (tn < 1) tn = 1;
       int tw2 = tw, tn2 = tn;
       bool ok = false;
       for (; tn2 >= 1; --tn2)
@@ -626,7 +625,9 @@ static void choose_box(int gw, int gh, int n, int max_rows, int mult, int* TW, i
       if (!ok) continue;
       long long pr = (long long)tw2 * th * tn2;
       long long tiles = (long long)((gw + tw2 - 1) / tw2) * ((gh + th - 1) / th) * ((n + tn2 - 1) / tn2);
-      long long cost = tiles * ((pr + 31) / 32 * 32) + tiles;     // padded MMA work + a per-tile overhead
+      // forward kernel (mult == 1): every tile costs one full M=128 accumulation, so minimise the tile count;
+      // filter-gradient kernel: pixels are the reduction dim, so minimise the padded pixel count
+      long long cost = (mult == 1) ? tiles * 1024 - pr : tiles * pr + tiles;
       if (best < 0 || cost < best) { best = cost; bw = tw2; bh = th; bn = tn2; }
     }
   }

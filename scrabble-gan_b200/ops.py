@@ -199,8 +199,8 @@ def scale_add(rt, sigma, a, x=None, out=None):
     return out
 
 
-def tanh_fwd(rt, x):
-    y = rt.empty(x.shape, SG_F32)
+def tanh_fwd(rt, x, out=None):
+    y = rt.empty(x.shape, SG_F32) if out is None else out
     call.sg_tanh_fwd(rt.ctx, _p(x), _p(y), x.numel())
     return y
 
