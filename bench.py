@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--length", type=int, default=5, help="word length (real and fake)")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample batch for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -262,11 +264,15 @@ def main():
     prof["on"] = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step(i, dev, True)
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     prof["on"] = False
     launches = rt.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
