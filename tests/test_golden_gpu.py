@@ -1,0 +1,166 @@
+"""CUDA path (through the C ABI) against the committed golden fixtures of tests/golden/ -- no /root/reference and no
+oracle arithmetic needed at run time except the seeded parameter initialisers (parameters are regenerated from the
+seeds stored in the fixture and checked against the stored fingerprints).
+
+Tolerances: fp32-mode kernels 1e-4 (relative to the largest magnitude of the expected tensor), full-step outputs and
+losses 1e-3 (north_star: 1e-3 relative in fp32), CTC 1e-4, integer indexing bit exact."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ops = importlib.import_module("scrabble-gan_b200.ops")
+abi = importlib.import_module("scrabble-gan_b200._abi")
+na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+optim = importlib.import_module("scrabble-gan_b200.optim")
+F32 = abi.SG_F32
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with np.load(os.path.join(GOLD, name)) as f:
+        return {k: f[k] for k in f.files}
+
+
+def dev(rt, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=rt.device, dtype=torch.float32).contiguous()
+
+
+def rel(got, exp):
+    got = torch.as_tensor(got).detach().double().cpu().reshape(-1)
+    exp = torch.as_tensor(np.asarray(exp)).double().reshape(-1)
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert torch.isfinite(got).all()
+    return float((got - exp).abs().max() / max(float(exp.abs().max()), 1e-30))
+
+
+def test_golden_convs(rt):
+    rt.set_mode("fp32")
+    G = load("ops_small.npz")
+    x, b = dev(rt, G["conv_x"]), dev(rt, G["conv_b"])
+    n, h, w, ci = x.shape
+    for key, wk, k, pad in (("conv_same", "conv_w", 3, "same"), ("conv_valid", "conv_w2", 2, "valid")):
+        wd = dev(rt, G[wk])
+        co = wd.shape[-1]
+        d = ops.desc_conv_fwd(n, h, w, ci, co, k, k, pad)
+        out = rt.empty(G[key].shape)
+        ops.conv_run(rt, d, x, wd, None, b, None, out)
+        assert rel(out, G[key]) <= 1e-4, key
+    for key, wk, k, (sy, sx) in (("convT_22", "convT_w", 3, (2, 2)), ("convT_21", "convT_w", 3, (2, 1)),
+                                 ("convT1_22", "convT_w1", 1, (2, 2)), ("convT1_21", "convT_w1", 1, (2, 1))):
+        wd = dev(rt, G[wk])
+        co = wd.shape[2]
+        out = b.view(1, 1, 1, co).expand(n, h * sy, w * sx, co).contiguous()
+        for (py, px) in ops.convT_phases(k, sy, sx):
+            d = ops.desc_convT_phase(n, h, w, ci, co, k, sy, sx, py, px, accumulate=1)
+            ops.conv_run(rt, d, x, wd, None, None, None, out)
+        assert rel(out, G[key]) <= 1e-4, key
+
+
+def test_golden_filterbank_ctc_losses(rt):
+    rt.set_mode("fp32")
+    G = load("ops_small.npz")
+    # the bank itself is regenerated from its seed (same draw order as make_golden.ops_vectors is not reproducible
+    # piecemeal), so the forward check uses a one-hot z against the stored thin slice: bit-exact row selection
+    y = torch.from_numpy(G["fb_y"]).to(rt.device, torch.int32)
+    thin = torch.from_numpy(G["fb_bank"]).float()                     # bank[:, :, ::64]
+    bank = torch.zeros(thin.shape[0], 32, 8192)
+    bank[:, :, ::64] = thin
+    j = 9
+    z = torch.zeros(y.shape[0], 32)
+    z[:, j] = 1.0
+    out = ops.filterbank_fwd(rt, z.to(rt.device), 32, y, bank.to(rt.device)).cpu()
+    for bi in range(y.shape[0]):
+        for li in range(y.shape[1]):
+            for k in range(0, 8192, 64):
+                hh, ww, cc = k % 4, 4 * li + k // 2048, (k % 2048) // 4
+                assert out[bi, hh, ww, cc].item() == bank[int(y[bi, li]), j, k].item()
+    # CTC through the fused softmax -> +eps -> CTC kernel; the kernel takes the Dense pre-activations (logits)
+    probs = torch.from_numpy(G["ctc_probs"])
+    logits = torch.log(probs)                                        # softmax(log p) == p
+    loss, _ = ops.ctc(rt, logits.float().to(rt.device), torch.from_numpy(G["ctc_labels"]).to(rt.device, torch.int32))
+    exp = torch.from_numpy(G["ctc_loss"]).view(-1)
+    assert float(((loss.cpu().double() - exp).abs() / exp.abs()).max()) <= 1e-4
+    # public loss functions + gradient balancing
+    li = G["loss_in"]
+    cols = [dev(rt, li[:, i:i + 1]) for i in range(5)]
+    got = torch.cat([t.view(-1, 1) for t in nl.hinge(*cols[:4])], 1)
+    assert rel(got, G["hinge"]) <= 1e-6
+    got = torch.cat([t.view(-1, 1) for t in nl.not_saturating(*cols)], 1)
+    assert rel(got, G["not_saturating"]) <= 1e-6
+    bi = G["bal_in"]
+    gb, rb, _, rs, gs = du.apply_gradient_balancing(dev(rt, bi[:, 0:1]), dev(rt, bi[:, 1:2]))
+    assert rel(torch.cat([gb, rb], 1), G["bal_out"]) <= 1e-5
+    assert rel(torch.stack([rs, gs]), G["bal_std"]) <= 1e-5
+
+
+def test_golden_spectral_norm_adam(rt):
+    rt.set_mode("fp32")
+    G = load("ops_small.npz")
+    w_out, _, _ = ops.spectral_norm(rt, dev(rt, G["sn_w"]), dev(rt, G["sn_u"]).view(-1), 1)
+    assert rel(w_out, G["sn_out"]) <= 1e-5
+    w0, g1, g2 = (dev(rt, a) for a in G["adam_in"])
+    w, m, v = w0.clone(), torch.zeros_like(w0), torch.zeros_like(w0)
+    import math
+    for step, g in ((1, g1), (2, g2)):
+        lr_t = 2e-4 * math.sqrt(1 - 0.999 ** step)
+        ops.adam_(rt, w, g, m, v, lr_t, 0.0, 0.999, 1e-7)
+        if step == 1:
+            assert rel(w, G["adam_out"][0]) <= 1e-6
+    assert rel(w, G["adam_out"][1]) <= 1e-6
+    assert rel(m, G["adam_out"][2]) <= 1e-6 and rel(v, G["adam_out"][3]) <= 1e-5
+    w, ms = w0.clone(), torch.zeros_like(w0)
+    ops.rmsprop_(rt, w, g1, ms, 2e-4, 0.9, 1e-7)
+    assert rel(w, G["rmsprop_out"][0]) <= 1e-6 and rel(ms, G["rmsprop_out"][1]) <= 1e-5
+
+
+@pytest.mark.parametrize("fname,mode,tol", [("train_step_b2_l2_hinge.npz", "fp32", 1e-3), ("train_step_b2_l3x1_hinge.npz", "fp32", 1e-3),
+                                            ("train_step_b2_l2_hinge.npz", "bf16", 3e-2)])
+def test_golden_train_step(rt, fname, mode, tol):
+    G = load(fname)
+    rt.set_mode(mode)
+    try:
+        sg, sd, sr = (int(s) for s in G["seeds"])
+        sigma = float(G["sigma"][0])
+        P = {"G": O.make_generator_params(sg, torch.float64, sigma=sigma), "D": O.make_discriminator_params(sd, torch.float64, sigma=sigma),
+             "R": O.make_recognizer_params(sr, torch.float64)}
+        for net in "GDR":       # the regenerated parameters are the ones the fixture was made with
+            names = sorted(P[net])
+            fp = np.array([[float(P[net][k].sum()), float(P[net][k].norm())] for k in names])
+            assert np.allclose(fp, G["param_fp_" + net], rtol=1e-9, atol=1e-12), "parameter initialisers drifted: " + net
+        Gm = na.make_generator(128, (32, 160, 1), (32, 8192), None, "B3", 52, vis_model=False, rt=rt)
+        Dm = na.make_discriminator((32, 160, 1), None, "B1", vis_model=False, rt=rt)
+        Rm = na.make_recognizer((32, 160, 1), None, 53, vis_model=False, rt=rt)
+        Gm.load_state_dict(P["G"]); Dm.load_state_dict(P["D"]); Rm.load_state_dict(P["R"])
+        gan = na.make_gan(Gm, Dm, Rm, None, vis_model=False)
+        g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+        b = G["images"].shape[0]
+        out = du.train_step(0, 0, 1, G["images"].astype(np.float32), G["labels"].astype(np.int32), Dm, Rm, None, gan, g_opt, d_opt,
+                            r_opt, w_opt, None, b, 128, loss_fn, disc_iters, agb, None, 10, "",
+                            fake_labels=G["fake_labels"].astype(np.int32), noise=G["z"].astype(np.float32))
+        got = dict(zip(du.STAT_NAMES, out))
+        exp = dict(zip(O.STAT_NAMES, G["stats"]))
+        for k in ("r_loss_fake", "r_loss_real", "d_loss", "d_loss_real", "d_loss_fake", "g_loss", "g_loss_final", "r_loss_balanced",
+                  "r_loss_fake_std", "g_loss_std"):
+            t = tol * (10 if k.endswith("_std") or k in ("r_loss_balanced", "g_loss_final") else 1)   # std of B=2 values amplifies
+            assert abs(got[k] - exp[k]) <= t * max(abs(exp[k]), 0.1), "{} {}: {} vs golden {}".format(mode, k, got[k], exp[k])
+        # a few small gradients stored in full (biases, dense heads, attention sigma): element-wise parity
+        for key in [k for k in G if k.startswith("grad_D_") or k.startswith("grad_R_") or k.startswith("grad_G_")]:
+            net, name = key.split("_", 2)[1:]
+            model = {"G": Gm, "D": Dm, "R": Rm}[net]
+            g = model.store.by_name[name].grad
+            e = G[key]
+            gt = mode == "fp32" and 2e-2 or 1e-1
+            if np.abs(e).max() < 1e-12:
+                continue
+            assert rel(g, e) <= gt, "{} grad {}: rel err {}".format(mode, key, rel(g, e))
+    finally:
+        rt.set_mode("fp32")
