@@ -521,6 +521,29 @@ __global__ void k_pack_weights(sg_conv_desc d, const float* __restrict__ w, TO* 
   }
 }
 
+// same packing when the master layout has c_out fastest (w_co_stride == 1, i.e. HWIO forward convs): a 32 x 32
+// shared-memory tile transpose per tap so that both the fp32 reads (along co) and the packed writes (along ci) are
+// coalesced.  grid = (ci tiles, co tiles, taps), block = 32 x 8.
+template <typename TO>
+__global__ void __launch_bounds__(256) k_pack_weights_t(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const float* src = w + d.tap_w_off[t];
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int ci = ci0 + threadIdx.y + j, co = co0 + threadIdx.x;
+    tile[threadIdx.y + j][threadIdx.x] = (ci < d.c_in && co < d.c_out) ? src[(long long)ci * d.w_ci_stride + co] : 0.f;
+  }
+  __syncthreads();
+  const long long ktot = (long long)d.ntaps * d.c_in;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int co = co0 + threadIdx.y + j, ci = ci0 + threadIdx.x;
+    if (ci < d.c_in && co < d.c_out) sg_st(out + (long long)co * ktot + (long long)t * d.c_in + ci, tile[threadIdx.x][threadIdx.y + j]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -664,9 +687,14 @@ int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_mast
   SG_REQUIRE(ctx && d && w_master && w_packed, "sg_conv_pack_weights: NULL");
   long long total = (long long)d->c_out * d->ntaps * d->c_in;
   if (total == 0) return SG_OK;
-  long long need = (total + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  int grid = (int)(need < cap ? need : cap);
-  SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+  if (d->w_co_stride == 1 && d->w_ci_stride != 1 && d->c_out >= 32) {
+    dim3 grid(sg_div_up(d->c_in, 32), sg_div_up(d->c_out, 32), d->ntaps), block(32, 8);
+    SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights_t<TO><<<grid, block, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+  } else {
+    long long need = (total + 255) / 256, cap = (long long)ctx->num_sms * 8;
+    int grid = (int)(need < cap ? need : cap);
+    SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+  }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

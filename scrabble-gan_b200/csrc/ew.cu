@@ -106,8 +106,52 @@ __global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, 
   if (threadIdx.x == 0) atomicAdd(partial, t);
 }
 
-// column sums of a [rows, cols] matrix: block handles a row-slab, thread t handles columns t, t+blockDim...
-// partial results are combined with one atomicAdd per (block, column).
+// column sums of a [rows, cols] matrix (bias gradients): a block owns a slab of rows; its 256 threads are arranged as
+// (cols/4 column groups) x (row lanes), every thread streams 4 adjacent columns with one 8/16-byte load per row, the
+// row lanes are combined through shared memory and the block adds its partial sums with one atomicAdd per column.
+template <typename T>
+__global__ void __launch_bounds__(256) k_colsum_v4(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
+                                                    float* __restrict__ out) {
+  __shared__ float4 sm[256];
+  const int cgs = cols >> 2;                          // column groups of 4
+  const int cg_per_pass = cgs < 256 ? cgs : 256;
+  const int lanes_r = 256 / cg_per_pass;              // row lanes (>= 1)
+  const int cgi = threadIdx.x % cg_per_pass, rl = threadIdx.x / cg_per_pass;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int cg0 = 0; cg0 < cgs; cg0 += cg_per_pass) {
+    const int cg = cg0 + cgi;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes_r && cg < cgs) {
+      const T* p = x + (long long)cg * 4;
+      long long r = r0 + rl;
+      for (; r + 3LL * lanes_r < r1; r += 4LL * lanes_r) {
+        float4 a = sg_ld4(p + r * cols), b = sg_ld4(p + (r + lanes_r) * cols), c = sg_ld4(p + (r + 2LL * lanes_r) * cols),
+               d = sg_ld4(p + (r + 3LL * lanes_r) * cols);
+        acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+        acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+      }
+      for (; r < r1; r += lanes_r) {
+        float4 a = sg_ld4(p + r * cols);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+    }
+    __syncthreads();
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && cg < cgs) {
+      for (int j = 1; j < lanes_r; ++j) {
+        float4 o = sm[j * cg_per_pass + cgi];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      float* op = out + (long long)cg * 4;
+      atomicAdd(op, acc.x); atomicAdd(op + 1, acc.y); atomicAdd(op + 2, acc.z); atomicAdd(op + 3, acc.w);
+    }
+  }
+}
+
+// generic fallback (cols not a multiple of 4): thread t handles columns t, t+blockDim...
 template <typename T>
 __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
                          float* __restrict__ out) {
@@ -328,6 +372,18 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
   SG_REQUIRE(ctx && x && out && rows >= 0 && cols > 0, "sg_colsum: bad args");
   if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ctx->stream));
   if (rows == 0) return SG_OK;
+  if (cols % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+    int cgs = cols / 4, cg_per_pass = cgs < 256 ? cgs : 256, lanes_r = 256 / cg_per_pass;
+    long long blocks = (long long)ctx->num_sms * 8;
+    long long min_rpb = 8LL * lanes_r;                  // at least 8 rows per row lane
+    long long rpb = (rows + blocks - 1) / blocks;
+    if (rpb < min_rpb) rpb = min_rpb;
+    rpb = (rpb + lanes_r - 1) / lanes_r * lanes_r;
+    blocks = (rows + rpb - 1) / rpb;
+    SG_DISPATCH_DT(dt, T, k_colsum_v4<T><<<(int)blocks, 256, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out));
+    SG_POST_LAUNCH(ctx);
+    return SG_OK;
+  }
   long long blocks = (long long)ctx->num_sms * 4;
   if (blocks > rows) blocks = rows;
   long long rpb = (rows + blocks - 1) / blocks;

@@ -246,6 +246,22 @@ def test_elementwise(rt):
     check(acc, (x * y).sum().view(1), 1e-5, "dot")
 
 
+@pytest.mark.parametrize("rows,cols", [(5000, 64), (777, 1024), (1283, 512), (9, 8), (300, 53), (4096, 1), (70001, 32), (33, 2048)])
+@pytest.mark.parametrize("dt", [F32, BF16])
+def test_colsum(rt, rows, cols, dt):
+    """Bias gradients: out[c] (+)= sum_r x[r,c]; vectorised path (cols % 4 == 0) and the generic fallback."""
+    g = torch.Generator().manual_seed(44)
+    x = rnd(g, rows, cols)
+    if dt == BF16:
+        x = x.float().bfloat16().double()
+    out = rt.zeros((cols,))
+    ops.colsum_into(rt, dev(rt, x, dt), cols, out, accumulate=0)
+    exp = x.sum(0)
+    assert float((out.cpu().double() - exp).abs().max()) <= 1e-5 * float(x.abs().sum(0).max()), "colsum"
+    ops.colsum_into(rt, dev(rt, x, dt), cols, out, accumulate=1)
+    assert float((out.cpu().double() - 2 * exp).abs().max()) <= 2e-5 * float(x.abs().sum(0).max()), "colsum accumulate"
+
+
 def test_pooling(rt):
     g = torch.Generator().manual_seed(5)
     x = rnd(g, 2, 8, 12, 16).requires_grad_(True)
