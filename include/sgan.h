@@ -161,6 +161,22 @@ int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
                 const float* lse, const float* d_o, int n, int q, int kv, int dk, int dv, float* dtheta,
                 float* dphi, float* dg);
 
+/* 1x1 projections of the non-local block, one pass over the pixels per data-flow step (arch_ops.py:38-46,55-57,63-67).
+ * C = 64 channels, dk = 8, dv = 32; x, dx, og, out, dout are [rows,64]; theta/phi_f [rows,8]; g_f, o, d_o [rows,32];
+ * kernels w_theta, w_phi [64,8], w_g [64,32], w_o [32,64] (1x1 HWIO).  Filter gradients are accumulated (+=). */
+int sg_nonlocal_proj_fwd(sg_ctx* ctx, const float* x, long long rows, const float* w_theta, const float* w_phi,
+                         const float* w_g, float* theta, float* phi_f, float* g_f);
+/* og = o . w_o (kept for d sigma = <dout, og>);  out = (*sigma) * og + x */
+int sg_nonlocal_out_fwd(sg_ctx* ctx, const float* o, long long rows, const float* w_o, const float* sigma,
+                        const float* x, float* og, float* out);
+/* d_o = (*sigma) * dout . w_o^T;  dw_o += (*sigma) * o^T . dout  (dw_o may be NULL) */
+int sg_nonlocal_out_bwd(sg_ctx* ctx, const float* dout, const float* o, long long rows, const float* w_o,
+                        const float* sigma, float* d_o, float* dw_o);
+/* dx += dtheta . w_theta^T + dphi_f . w_phi^T + dg_f . w_g^T;  dw_* += x^T . d*  (all three dw_* or none) */
+int sg_nonlocal_proj_bwd(sg_ctx* ctx, const float* x, const float* dtheta, const float* dphi_f, const float* dg_f,
+                         long long rows, const float* w_theta, const float* w_phi, const float* w_g, float* dx,
+                         float* dw_theta, float* dw_phi, float* dw_g);
+
 /* ---- CTC (K15) -- net_architecture.py:55-72: softmax -> log(p+1e-7) -> tf.nn.ctc_loss --------------
  * loss[b] = -log p(labels_b | x_b); grad_logits = d loss / d (Dense pre-activations), blank = c-1 */
 int sg_ctc(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, float* loss,

@@ -29,16 +29,13 @@ class NonLocalBlock:
 
     def forward(self, rt: Runtime, x):
         n, h, w, c = x.shape
-        p = n * h * w
-        theta = ops.gemm(rt, x, self.theta.data, p, self.dk, c)
-        phi_f = ops.gemm(rt, x, self.phi.data, p, self.dk, c).view(n, h, w, self.dk)
-        g_f = ops.gemm(rt, x, self.g.data, p, self.dv, c).view(n, h, w, self.dv)
+        theta, phi_f, g_f = ops.nonlocal_proj_fwd(rt, x, self.theta.data, self.phi.data, self.g.data)
+        phi_f, g_f = phi_f.view(n, h, w, self.dk), g_f.view(n, h, w, self.dv)
         phi = ops.maxpool_fwd(rt, phi_f, 2, 2)
         g = ops.maxpool_fwd(rt, g_f, 2, 2)
         q, kv = h * w, (h // 2) * (w // 2)
         o, lse = ops.attn_fwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv))
-        og = ops.gemm(rt, o, self.o.data, p, c, self.dv)
-        out = ops.scale_add(rt, self.sigma.data, og, x)
+        og, out = ops.nonlocal_out_fwd(rt, o, self.o.data, self.sigma.data, x)
         # every cached tensor keeps the image index as its first dimension so that sub-batches can be sliced
         return out.view(n, h, w, c), (x, theta.view(n, q, self.dk), phi_f, phi, g_f, g, o, lse, og.view(n, h, w, c))
 
@@ -50,26 +47,16 @@ class NonLocalBlock:
         """Returns dx; `dout` is consumed (the identity-path gradient is accumulated in place)."""
         x, theta, phi_f, phi, g_f, g, o, lse, og = cache
         n, h, w, c = x.shape
-        p, q, kv = n * h * w, h * w, (h // 2) * (w // 2)
+        q, kv = h * w, (h // 2) * (w // 2)
         if wgrad:
             ops.dot_into(rt, dout, og, self.sigma.grad, accumulate=1)
-        dog = ops.scale_add(rt, self.sigma.data, dout, None)                       # sigma * dout
-        d_o = ops.gemm(rt, dog, self.o.data, p, self.dv, c, trans_b=True)
-        if wgrad:
-            ops.gemm(rt, o, dog, self.dv, c, p, trans_a=True, lda=self.dv, out=self.o.grad, accumulate=1)
+        d_o = ops.nonlocal_out_bwd(rt, dout, o, self.o.data, self.sigma.data, self.o.grad if wgrad else None)
         dtheta, dphi, dg = ops.attn_bwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv),
                                         o.view(n, q, self.dv), lse, d_o.view(n, q, self.dv))
         dphi_f = ops.maxpool_bwd(rt, dphi.view(n, h // 2, w // 2, self.dk), phi_f, 2, 2, False, SG_F32)
         dg_f = ops.maxpool_bwd(rt, dg.view(n, h // 2, w // 2, self.dv), g_f, 2, 2, False, SG_F32)
-        if wgrad:
-            ops.gemm(rt, x, dtheta, c, self.dk, p, trans_a=True, lda=c, out=self.theta.grad, accumulate=1)
-            ops.gemm(rt, x, dphi_f, c, self.dk, p, trans_a=True, lda=c, out=self.phi.grad, accumulate=1)
-            ops.gemm(rt, x, dg_f, c, self.dv, p, trans_a=True, lda=c, out=self.g.grad, accumulate=1)
-        dx = dout
-        ops.gemm(rt, dtheta, self.theta.data, p, c, self.dk, trans_b=True, out=dx, accumulate=1)
-        ops.gemm(rt, dphi_f, self.phi.data, p, c, self.dk, trans_b=True, out=dx, accumulate=1)
-        ops.gemm(rt, dg_f, self.g.data, p, c, self.dv, trans_b=True, out=dx, accumulate=1)
-        return dx
+        gr = (self.theta.grad, self.phi.grad, self.g.grad) if wgrad else (None, None, None)
+        return ops.nonlocal_proj_bwd(rt, x, dtheta, dphi_f, dg_f, self.theta.data, self.phi.data, self.g.data, dout, *gr)
 
 
 class SpatialEmbedding:

@@ -43,12 +43,23 @@ __global__ void k_bn_stats(const float* __restrict__ x, long long rows, int c, i
   }
 }
 
-__global__ void k_bn_stats_reduce(const float* __restrict__ partial, int nblocks, int c2, float* __restrict__ sums) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= c2) return;
+// second stage of the statistics: block = 32 columns x 16 slices of the per-block partials (double accumulation),
+// slices combined through shared memory -- the serial chain per thread is nblocks/16 loads instead of nblocks.
+__global__ void __launch_bounds__(512) k_bn_stats_reduce(const float* __restrict__ partial, int nblocks, int c2,
+                                                          float* __restrict__ sums) {
+  __shared__ double sm[16][33];
+  const int jx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx;
   double t = 0.0;
-  for (int b = 0; b < nblocks; ++b) t += (double)partial[(long long)b * c2 + j];
-  sums[j] = (float)t;
+  if (j < c2)
+    for (int b = sl; b < nblocks; b += 16) t += (double)partial[(long long)b * c2 + j];
+  sm[sl][jx] = t;
+  __syncthreads();
+  if (sl == 0 && j < c2) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) t += sm[k][jx];
+    sums[j] = (float)t;
+  }
 }
 
 __global__ void k_bn_finalize(const float* __restrict__ sums, double count, int c, float eps, float momentum,
@@ -134,19 +145,29 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restri
   }
 }
 
-__global__ void k_bn_bwd_combine(const float* __restrict__ s1, const float* __restrict__ s2,
-                                 const float* __restrict__ gamma, long long gb_stride, int n, int c,
-                                 float* __restrict__ ab) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= c) return;
+// block = 32 channels x 8 sample slices, slices combined through shared memory
+__global__ void __launch_bounds__(256) k_bn_bwd_combine(const float* __restrict__ s1, const float* __restrict__ s2,
+                                                         const float* __restrict__ gamma, long long gb_stride, int n, int c,
+                                                         float* __restrict__ ab) {
+  __shared__ float sa[8][33], sb[8][33];
+  const int jx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx;
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < n; ++i) {
-    float g = gamma ? gamma[(long long)i * gb_stride + j] : 1.f;
-    a += g * s1[(long long)i * c + j];
-    b += g * s2[(long long)i * c + j];
+  if (j < c)
+    for (int i = sl; i < n; i += 8) {
+      float g = gamma ? gamma[(long long)i * gb_stride + j] : 1.f;
+      a += g * s1[(long long)i * c + j];
+      b += g * s2[(long long)i * c + j];
+    }
+  sa[sl][jx] = a;
+  sb[sl][jx] = b;
+  __syncthreads();
+  if (sl == 0 && j < c) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a += sa[k][jx]; b += sb[k][jx]; }
+    ab[j] = a;
+    ab[c + j] = b;
   }
-  ab[j] = a;
-  ab[c + j] = b;
 }
 
 template <typename TA, typename TO>
@@ -218,7 +239,7 @@ int sg_bn_stats(sg_ctx* ctx, const float* x, long long rows, int c, float* sums,
   size_t smem = (size_t)l.lanes * 2 * c * sizeof(float);
   k_bn_stats<<<(int)blocks, 256, smem, ctx->stream>>>(x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
   SG_POST_LAUNCH(ctx);
-  k_bn_stats_reduce<<<sg_div_up(2 * c, 128), 128, 0, ctx->stream>>>((const float*)scratch, (int)blocks, 2 * c, sums);
+  k_bn_stats_reduce<<<sg_div_up(2 * c, 32), 512, 0, ctx->stream>>>((const float*)scratch, (int)blocks, 2 * c, sums);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -281,7 +302,7 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
 int sg_bn_bwd_combine(sg_ctx* ctx, const float* s1, const float* s2, const float* gamma, long long gb_stride, int n,
                       int c, float* ab) {
   SG_REQUIRE(ctx && s1 && s2 && ab && c > 0, "sg_bn_bwd_combine: bad args");
-  k_bn_bwd_combine<<<sg_div_up(c, 128), 128, 0, ctx->stream>>>(s1, s2, gamma, gb_stride, n, c, ab);
+  k_bn_bwd_combine<<<sg_div_up(c, 32), 256, 0, ctx->stream>>>(s1, s2, gamma, gb_stride, n, c, ab);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -90,9 +90,9 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
   // split-K (atomic accumulation) for skinny-output / long-reduction shapes such as dW = X^T dY
   int splits = 1, k_per_split = k > 0 ? k : 1;
   long long tiles = (long long)grid.x * grid.y;
-  if (k >= 4096 && tiles < ctx->num_sms) {
+  if (k >= 256 && tiles < ctx->num_sms / 2 && (accumulate || ldc == n)) {
     splits = (int)((2LL * ctx->num_sms + tiles - 1) / tiles);
-    int max_splits = k / 1024;
+    int max_splits = k >= 8192 ? k / 512 : k / 64;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     k_per_split = ((k + splits - 1) / splits + GT_K - 1) / GT_K * GT_K;

@@ -379,6 +379,37 @@ def attn_bwd(rt, theta, phi, g, o, lse, d_o):
     return dtheta, dphi, dg
 
 
+def nonlocal_proj_fwd(rt, x, w_theta, w_phi, w_g):
+    """theta [p,8], phi_f [p,8], g_f [p,32] from ONE pass over x [p,64] (arch_ops.py:38-46,55-57)."""
+    p = x.numel() // 64
+    theta, phi_f, g_f = rt.empty((p, 8)), rt.empty((p, 8)), rt.empty((p, 32))
+    call.sg_nonlocal_proj_fwd(rt.ctx, _p(x), p, _p(w_theta), _p(w_phi), _p(w_g), _p(theta), _p(phi_f), _p(g_f))
+    return theta, phi_f, g_f
+
+
+def nonlocal_out_fwd(rt, o, w_o, sigma, x):
+    """og = o @ w_o, out = sigma * og + x (arch_ops.py:63-67)."""
+    p = x.numel() // 64
+    og, out = rt.empty((p, 64)), rt.empty((p, 64))
+    call.sg_nonlocal_out_fwd(rt.ctx, _p(o), p, _p(w_o), _p(sigma), _p(x), _p(og), _p(out))
+    return og, out
+
+
+def nonlocal_out_bwd(rt, dout, o, w_o, sigma, dw_o=None):
+    p = dout.numel() // 64
+    d_o = rt.empty((p, 32))
+    call.sg_nonlocal_out_bwd(rt.ctx, _p(dout), _p(o), p, _p(w_o), _p(sigma), _p(d_o), _p(dw_o))
+    return d_o
+
+
+def nonlocal_proj_bwd(rt, x, dtheta, dphi_f, dg_f, w_theta, w_phi, w_g, dx, dw_theta=None, dw_phi=None, dw_g=None):
+    """dx += the three input gradients; dw_* += the three filter gradients (one pass over x each)."""
+    p = x.numel() // 64
+    call.sg_nonlocal_proj_bwd(rt.ctx, _p(x), _p(dtheta), _p(dphi_f), _p(dg_f), p, _p(w_theta), _p(w_phi), _p(w_g), _p(dx),
+                              _p(dw_theta), _p(dw_phi), _p(dw_g))
+    return dx
+
+
 def ctc(rt, logits, labels, want_grad=True):
     b, t, c = logits.shape
     l = labels.shape[1]

@@ -1,0 +1,100 @@
+"""Data-parallel equivalence on real GPUs (needs >= 2; run with `gpurun --gpus 2 -- python -m pytest tests/test_dp_gpu.py -m gpu`):
+a 2-GPU train step on the two halves of a batch must equal the 1-GPU step on the concatenated batch -- losses /
+statistics (global means, global population std for the balancing), BN moving statistics (sync-BN) and the
+all-reduced (SUM) gradient buckets of G, D and R.  fp32 mode, tolerance 1e-3 on the whole-gradient rel L2."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(rt):
+    na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+    nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+    optim = importlib.import_module("scrabble-gan_b200.optim")
+    G = na.make_generator(128, (32, 160, 1), (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=21)
+    D = na.make_discriminator((32, 160, 1), None, "B1", vis_model=False, rt=rt, seed=22)
+    R = na.make_recognizer((32, 160, 1), None, 53, vis_model=False, rt=rt, seed=23)
+    for m in (G, D):                     # exercise attention: sigma != 0
+        for v in m.store.vars:
+            if v.name.endswith(".sigma"):
+                v.assign(np.array([0.1], np.float32))
+    gan = na.make_gan(G, D, R, None, vis_model=False)
+    opts = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+    return G, D, R, gan, opts
+
+
+def _step(rt, nets, batch):
+    du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+    G, D, R, gan, (g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb) = nets
+    imgs, labels, fake, z = batch
+    out = du.train_step(0, 0, 1, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, imgs.shape[0], 128, loss_fn,
+                        disc_iters, agb, None, 10, "", fake_labels=fake, noise=z)
+    grads = {n: m.store.g.detach().cpu().double() for n, m in (("G", G), ("D", D), ("R", R))}
+    mov = G.store.s.detach().cpu().double()
+    return np.array(out), grads, mov
+
+
+def _worker(rank, world, port, tmp):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    runtime = importlib.import_module("scrabble-gan_b200.runtime")
+    dp = importlib.import_module("scrabble-gan_b200.dp")
+    rt = runtime.Runtime(device=rank, mode="fp32")
+    runtime.set_runtime(rt)
+    dp.init_data_parallel(rt)
+    assert rt.world_size == world
+    rng = np.random.RandomState(99)
+    B, L = 4, 2
+    imgs = rng.uniform(-1, 1, size=(B, 32, 16 * L, 1)).astype(np.float32)
+    labels = rng.randint(0, 52, size=(B, L)).astype(np.int32)
+    fake = rng.randint(0, 52, size=(B, L)).astype(np.int32)
+    z = rng.standard_normal(size=(B, 128)).astype(np.float32)
+
+    nets = _build(rt)
+    dp.broadcast_parameters(rt, nets[:3])
+    a, b = dp.shard_batch(B, world, rank)
+    stats_dp, grads_dp, mov_dp = _step(rt, nets, (imgs[a:b], labels[a:b], fake[a:b], z[a:b]))
+
+    import torch.distributed as dist
+    dist.barrier()
+    if rank == 0:
+        rt.world_size = 1                      # same process, no exchange: the concatenated batch on one GPU
+        nets1 = _build(rt)
+        stats_1, grads_1, mov_1 = _step(rt, nets1, (imgs, labels, fake, z))
+        rt.world_size = world
+        for i, (x, y) in enumerate(zip(stats_dp, stats_1)):
+            assert abs(x - y) <= 1e-3 * max(abs(y), 0.1), "stat {}: dp {} vs single {}".format(i, x, y)
+        for n in ("G", "D", "R"):
+            num = float(((grads_dp[n] - grads_1[n]) ** 2).sum()) ** 0.5
+            den = float((grads_1[n] ** 2).sum()) ** 0.5
+            assert den > 0 and num / den <= 1e-3, "{} gradient bucket: rel L2 {}".format(n, num / den)
+        assert float((mov_dp - mov_1).abs().max()) <= 1e-5, "sync-BN moving statistics differ"
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_step_equals_single_gpu_big_batch(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok"))

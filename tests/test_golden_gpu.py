@@ -116,7 +116,7 @@ def test_golden_spectral_norm_adam(rt):
         if step == 1:
             assert rel(w, G["adam_out"][0]) <= 1e-6
     assert rel(w, G["adam_out"][1]) <= 1e-6
-    assert rel(m, G["adam_out"][2]) <= 1e-6 and rel(v, G["adam_out"][3]) <= 1e-5
+    assert rel(m, G["adam_out"][2]) <= 1e-6 and rel(v, G["adam_out"][3]) <= 5e-5
     w, ms = w0.clone(), torch.zeros_like(w0)
     ops.rmsprop_(rt, w, g1, ms, 2e-4, 0.9, 1e-7)
     assert rel(w, G["rmsprop_out"][0]) <= 1e-6 and rel(ms, G["rmsprop_out"][1]) <= 1e-5
