@@ -341,6 +341,126 @@ __global__ void __launch_bounds__(256) k_conv_fwd_cout1(sg_conv_desc d, const TI
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Edge layers, second generation: C = 64 on the wide side, shared-memory staged.
+// ---------------------------------------------------------------------------------------------------
+// Filter gradient with one single-channel side as a skinny GEMM over pixels:
+//     dW[t][c] += sum_p wide[p, c] * narrow[p + off_t]            (c < 64, t < ntaps <= 9)
+//   c_in == 1 : wide = dy [n,H,W,64], narrow = layer input,  off_t = +tap_t
+//   c_out == 1: wide = layer input [n,H,W,64], narrow = dy,   off_t = -tap_t
+// Block = 192 threads = 64 channels x 3 tap groups; a chunk of 64 pixels of the wide tensor is staged in shared memory
+// (coalesced 16-byte loads) together with the 9 x 64 patch of the narrow tensor; each thread then runs 4 pixels per
+// step (4 scalar LDS of its channel + 3 broadcast LDS.128 of the patch -> 12 FMA).
+#define WN_PIX 64
+template <typename TW>
+__global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ wide, const void* __restrict__ narrow, int narrow_dt,
+                                                         int n, int H, int W, int nH, int nW, int ntaps, sg_conv_desc d,
+                                                         int sign, float* __restrict__ dw, long long chunks_per_block,
+                                                         int narrow_in) {
+  __shared__ float Bs[WN_PIX][64];
+  __shared__ __align__(16) float As[9][WN_PIX];
+  const int tid = threadIdx.x;
+  const int c = tid & 63, tg = tid >> 6;
+  const long long P = (long long)n * H * W;
+  const long long nchunks = (P + WN_PIX - 1) / WN_PIX;
+  long long ch0 = (long long)blockIdx.x * chunks_per_block, ch1 = ch0 + chunks_per_block;
+  if (ch1 > nchunks) ch1 = nchunks;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (long long chk = ch0; chk < ch1; ++chk) {
+    const long long p0 = chk * WN_PIX;
+    const int cnt = P - p0 < WN_PIX ? (int)(P - p0) : WN_PIX;
+    __syncthreads();
+    // wide tile: cnt x 64 contiguous elements
+    {
+      const TW* src = wide + p0 * 64;
+      for (int i = tid; i < WN_PIX * 64 / 4; i += 192) {
+        int e = i * 4, px = e >> 6, cc = e & 63;
+        float4 v = px < cnt ? sg_ld4(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&Bs[px][cc]) = v;
+      }
+    }
+    // narrow patch: 9 x 64 values
+    for (int i = tid; i < 9 * WN_PIX; i += 192) {
+      int t = i / WN_PIX, px = i % WN_PIX;
+      float v = 0.f;
+      if (t < ntaps && px < cnt) {
+        Pix q = decode_pix(p0 + px, H, W);
+        int y = q.y + sign * d.tap_dy[t], x = q.x + sign * d.tap_dx[t];
+        if (y >= 0 && y < nH && x >= 0 && x < nW) v = ld_any(narrow, ((long long)q.n * nH + y) * nW + x, narrow_dt);
+      }
+      As[t][px] = v;
+    }
+    __syncthreads();
+    if (3 * tg < ntaps) {
+#pragma unroll 4
+      for (int px = 0; px < WN_PIX; px += 4) {
+        float b0 = Bs[px][c], b1 = Bs[px + 1][c], b2 = Bs[px + 2][c], b3 = Bs[px + 3][c];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float4 a = *reinterpret_cast<const float4*>(&As[3 * tg + j][px]);
+          acc[j] = fmaf(a.x, b0, acc[j]); acc[j] = fmaf(a.y, b1, acc[j]);
+          acc[j] = fmaf(a.z, b2, acc[j]); acc[j] = fmaf(a.w, b3, acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    int t = 3 * tg + j;
+    if (t < ntaps) {
+      long long off = d.tap_w_off[t] + (narrow_in ? (long long)c * d.w_co_stride : (long long)c * d.w_ci_stride);
+      atomicAdd(dw + off, acc[j]);
+    }
+  }
+}
+
+// forward conv with c_in == 1, c_out % 8 == 0 (<= 64 per pixel group), unit strides: 8 output channels per thread with
+// their ntaps x 8 weights in registers; the input patch comes through L1 (neighbouring threads share it); 16/32-byte
+// vector stores.  out = act(bias + sum_t x[p + tap_t] * w[t, :]) (+ out when accumulate).
+template <typename TOut>
+__global__ void __launch_bounds__(256) k_conv_fwd_cin1(sg_conv_desc d, const float* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, TOut* __restrict__ out) {
+  const int groups = d.c_out / 8;                      // threads per pixel
+  const int sub = threadIdx.x % groups;
+  const int pix_per_block = 256 / groups;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = (t < d.ntaps) ? w[d.tap_w_off[t] + (long long)(sub * 8 + j) * d.w_co_stride] : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) br[j] = bias ? bias[sub * 8 + j] : 0.f;
+  const long long P = (long long)d.n * d.grid_h * d.grid_w;
+  for (long long p = (long long)blockIdx.x * pix_per_block + threadIdx.x / groups; p < P; p += (long long)gridDim.x * pix_per_block) {
+    Pix q = decode_pix(p, d.grid_h, d.grid_w);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t < d.ntaps) {
+        int iy = q.y + d.tap_dy[t], ix = q.x + d.tap_dx[t];
+        if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
+          float xv = __ldg(in + ((long long)q.n * d.in_h + iy) * d.in_w + ix);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t][j], acc[j]);
+        }
+      }
+    }
+    if (d.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    TOut* op = out + (((long long)q.n * d.out_h + q.y) * d.out_w + q.x) * d.c_out + sub * 8;
+    if (d.accumulate) {
+      float4 a = sg_ld4(op), b = sg_ld4(op + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    sg_st4(op, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    sg_st4(op + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+  }
+}
+
 static int check_desc(const sg_conv_desc* d, const char* who) {
   SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   SG_REQUIRE(d->n >= 0 && d->in_h > 0 && d->in_w > 0 && d->c_in > 0 && d->out_h > 0 && d->out_w > 0 && d->c_out > 0,
@@ -378,6 +498,20 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
       return SG_OK;
     }
   }
+  {
+    bool unit = d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0;
+    int groups = d->c_out / 8;
+    bool g_ok = d->c_out % 8 == 0 && groups >= 1 && groups <= 32 && 256 % groups == 0;
+    if (unit && d->c_in == 1 && g_ok && d->ntaps <= 9 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0) {
+      int ppb = 256 / groups;
+      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 16;
+      int grid = (int)(need < cap ? need : cap);
+      if (d->out_dt == SG_F32) k_conv_fwd_cin1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
+      else k_conv_fwd_cin1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+      SG_POST_LAUNCH(ctx);
+      return SG_OK;
+    }
+  }
   if (d->c_out > 16) {
     dim3 grid(sg_div_up(M, CS_TM), sg_div_up(d->c_out, 64));
     k_conv_fwd_simt<64, 4><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
@@ -399,6 +533,33 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
     bool unit = d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0;
     bool narrow_in = d->c_in == 1 && d->c_out <= 256 && 256 % d->c_out == 0;
     bool narrow_out = d->c_out == 1 && d->c_in <= 256 && 256 % d->c_in == 0;
+    if (unit && d->ntaps <= 9 && ((narrow_in && d->c_out == 64) || (narrow_out && d->c_in == 64))) {
+      // wide side = 64 channels: shared-memory staged skinny GEMM over pixels
+      const void* wide = narrow_in ? dy : in;
+      const void* nar = narrow_in ? in : dy;
+      int wide_dt = narrow_in ? d->out_dt : d->in_dt, nar_dt = narrow_in ? d->in_dt : d->out_dt;
+      int H = narrow_in ? d->out_h : d->in_h, W = narrow_in ? d->out_w : d->in_w;
+      int nH = narrow_in ? d->in_h : d->out_h, nW = narrow_in ? d->in_w : d->out_w;
+      // the pixel loop runs over the WIDE tensor; for c_in == 1 that must be exactly the output grid
+      if ((!narrow_in || (d->grid_h == d->out_h && d->grid_w == d->out_w)) && (narrow_in || (d->grid_h == d->out_h && d->grid_w == d->out_w)) &&
+          ((uintptr_t)wide & 15) == 0) {
+        long long Pw = (long long)d->n * H * W;
+        long long nchunks = (Pw + WN_PIX - 1) / WN_PIX;
+        long long blocks = (long long)ctx->num_sms * 4;
+        if (blocks > nchunks) blocks = nchunks;
+        long long cpb = (nchunks + blocks - 1) / blocks;
+        blocks = (nchunks + cpb - 1) / cpb;
+        if (wide_dt == SG_F32)
+          k_wgrad_narrow64<float><<<(int)blocks, 192, 0, ctx->stream>>>((const float*)wide, nar, nar_dt, d->n, H, W, nH, nW, d->ntaps, *d,
+                                                                       narrow_in ? 1 : -1, dw_master, cpb, narrow_in ? 1 : 0);
+        else
+          k_wgrad_narrow64<__nv_bfloat16><<<(int)blocks, 192, 0, ctx->stream>>>((const __nv_bfloat16*)wide, nar, nar_dt, d->n, H, W, nH,
+                                                                               nW, d->ntaps, *d, narrow_in ? 1 : -1, dw_master, cpb,
+                                                                               narrow_in ? 1 : 0);
+        SG_POST_LAUNCH(ctx);
+        return SG_OK;
+      }
+    }
     if (unit && (narrow_in || narrow_out)) {
       int wide = narrow_in ? d->c_out : d->c_in;
       int lanes = 256 / wide;

@@ -60,6 +60,10 @@ CONV_CASES_SIMT = [
     (3, 4, 10, 32, 64, 1, "same"),
     (2, 2, 9, 16, 24, 2, "valid"),
     (1, 5, 7, 3, 5, 3, "same"),
+    (2, 8, 12, 1, 64, 1, "same"),      # Cin = 1 shortcut (1 tap)
+    (3, 5, 7, 1, 64, 3, "same"),       # pixel count not a multiple of the 64-pixel chunk
+    (3, 5, 7, 64, 1, 3, "same"),
+    (2, 4, 9, 1, 32, 3, "same"),       # Cin = 1, 4 channel groups
 ]
 
 
