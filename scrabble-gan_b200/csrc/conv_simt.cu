@@ -488,7 +488,7 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
     bool pow2 = tpp >= 1 && tpp <= 32 && (tpp & (tpp - 1)) == 0;
     if (d->c_out == 1 && d->c_in % 8 == 0 && pow2 && d->ntaps <= 9 && ((uintptr_t)in & 15) == 0) {
       int ppb = 256 / tpp;
-      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 8;
+      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 3;   // 72 weights live in registers per thread
       int grid = (int)(need < cap ? need : cap);
       if (d->in_dt == SG_F32)
         k_conv_fwd_cout1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, mask, out);
@@ -504,7 +504,7 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
     bool g_ok = d->c_out % 8 == 0 && groups >= 1 && groups <= 32 && 256 % groups == 0;
     if (unit && d->c_in == 1 && g_ok && d->ntaps <= 9 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0) {
       int ppb = 256 / groups;
-      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 16;
+      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 3;
       int grid = (int)(need < cap ? need : cap);
       if (d->out_dt == SG_F32) k_conv_fwd_cin1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
       else k_conv_fwd_cin1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);

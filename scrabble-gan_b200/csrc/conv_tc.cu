@@ -521,6 +521,26 @@ __global__ void k_pack_weights(sg_conv_desc d, const float* __restrict__ w, TO* 
   }
 }
 
+// master layout with the descriptor's c_in fastest (w_ci_stride == 1, c_in % 8 == 0): 8 consecutive ci per thread,
+// two float4 loads -> one 16/32-byte store
+template <typename TO>
+__global__ void __launch_bounds__(256) k_pack_weights_v8(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  const int c8 = d.c_in / 8;
+  const long long total8 = (long long)d.c_out * d.ntaps * c8;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+    int g = (int)(i % c8);
+    long long r = i / c8;
+    int t = (int)(r % d.ntaps);
+    int co = (int)(r / d.ntaps);
+    const float* src = w + d.tap_w_off[t] + (long long)co * d.w_co_stride + 8 * g;
+    float4 a = sg_ld4(src), b = sg_ld4(src + 4);
+    TO* dst = out + i * 8;
+    sg_st4(dst, a);
+    sg_st4(dst + 4, b);
+  }
+}
+
 // same packing when the master layout has c_out fastest (w_co_stride == 1, i.e. HWIO forward convs): a 32 x 32
 // shared-memory tile transpose per tap so that both the fp32 reads (along co) and the packed writes (along ci) are
 // coalesced.  grid = (ci tiles, co tiles, taps), block = 32 x 8.
@@ -690,6 +710,16 @@ int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_mast
   if (d->w_co_stride == 1 && d->w_ci_stride != 1 && d->c_out >= 32) {
     dim3 grid(sg_div_up(d->c_in, 32), sg_div_up(d->c_out, 32), d->ntaps), block(32, 8);
     SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights_t<TO><<<grid, block, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+  } else if (d->w_ci_stride == 1 && d->c_in % 8 == 0 && d->w_co_stride % 4 == 0 && ((uintptr_t)w_master & 15) == 0) {
+    bool taps_ok = true;
+    for (int t = 0; t < d->ntaps; ++t) taps_ok = taps_ok && (d->tap_w_off[t] % 4 == 0);
+    long long need = (total / 8 + 255) / 256, cap = (long long)ctx->num_sms * 8;
+    int grid = (int)(need < cap ? need : cap);
+    if (taps_ok) {
+      SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights_v8<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+    } else {
+      SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+    }
   } else {
     long long need = (total + 255) / 256, cap = (long long)ctx->num_sms * 8;
     int grid = (int)(need < cap ? need : cap);

@@ -109,13 +109,13 @@ __global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, 
 // column sums of a [rows, cols] matrix (bias gradients): a block owns a slab of rows; its 256 threads are arranged as
 // (cols/4 column groups) x (row lanes), every thread streams 4 adjacent columns with one 8/16-byte load per row, the
 // row lanes are combined through shared memory and the block adds its partial sums with one atomicAdd per column.
-template <typename T>
-__global__ void __launch_bounds__(256) k_colsum_v4(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
                                                     float* __restrict__ out) {
-  __shared__ float4 sm[256];
+  __shared__ float4 sm[NT];
   const int cgs = cols >> 2;                          // column groups of 4
-  const int cg_per_pass = cgs < 256 ? cgs : 256;
-  const int lanes_r = 256 / cg_per_pass;              // row lanes (>= 1)
+  const int cg_per_pass = cgs < NT ? cgs : NT;
+  const int lanes_r = NT / cg_per_pass;              // row lanes (>= 1)
   const int cgi = threadIdx.x % cg_per_pass, rl = threadIdx.x / cg_per_pass;
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
@@ -228,6 +228,68 @@ __global__ void k_maxpool_fwd(const T* __restrict__ x, int n, int h, int w, int 
       for (int b = 0; b < pw; ++b)
         m = fmaxf(m, sg_ld(x + (((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c + cc));
     sg_st(out + i, m);
+  }
+}
+
+// 4 channels per thread (c % 4 == 0): 8/16-byte loads and stores
+template <typename T>
+__global__ void k_maxpool_fwd_v4(const T* __restrict__ x, int n, int h, int w, int c4, int ph, int pw, T* __restrict__ out) {
+  int ho = h / ph, wo = w / pw;
+  long long total = (long long)n * ho * wo * c4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4);
+    long long p = i / c4;
+    int ox = (int)(p % wo);
+    p /= wo;
+    int oy = (int)(p % ho);
+    int ni = (int)(p / ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b) {
+        float4 v = sg_ld4(x + ((((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c4 + cc) * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    sg_st4(out + 4 * i, m);
+  }
+}
+
+template <typename TX, typename TO>
+__global__ void k_maxpool_bwd_v4(const float* __restrict__ dout, const TX* __restrict__ x, int n, int h, int w, int c4,
+                                 int ph, int pw, int relu_mask, TO* __restrict__ dx) {
+  int ho = h / ph, wo = w / pw;
+  long long total = (long long)n * ho * wo * c4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4);
+    long long p = i / c4;
+    int ox = (int)(p % wo);
+    p /= wo;
+    int oy = (int)(p % ho);
+    int ni = (int)(p / ho);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int best[4] = {0, 0, 0, 0};
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b) {
+        float4 v4 = sg_ld4(x + ((((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c4 + cc) * 4);
+        float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (v[j] > m[j]) { m[j] = v[j]; best[j] = a * pw + b; }
+      }
+    float4 g4 = sg_ld4(dout + 4 * i);
+    float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    if (relu_mask) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(m[j] > 0.f)) g[j] = 0.f;
+    }
+    for (int a = 0; a < ph; ++a)
+      for (int b = 0; b < pw; ++b) {
+        int k = a * pw + b;
+        sg_st4(dx + ((((long long)ni * h + oy * ph + a) * w + ox * pw + b) * c4 + cc) * 4,
+               make_float4(k == best[0] ? g[0] : 0.f, k == best[1] ? g[1] : 0.f, k == best[2] ? g[2] : 0.f, k == best[3] ? g[3] : 0.f));
+      }
   }
 }
 
@@ -372,15 +434,23 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
   SG_REQUIRE(ctx && x && out && rows >= 0 && cols > 0, "sg_colsum: bad args");
   if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ctx->stream));
   if (rows == 0) return SG_OK;
+  SG_REQUIRE(dt == SG_F32 || dt == SG_BF16, "sg_colsum: bad dtype %d", dt);
   if (cols % 4 == 0 && ((uintptr_t)x & 15) == 0) {
-    int cgs = cols / 4, cg_per_pass = cgs < 256 ? cgs : 256, lanes_r = 256 / cg_per_pass;
-    long long blocks = (long long)ctx->num_sms * 8;
-    long long min_rpb = 8LL * lanes_r;                  // at least 8 rows per row lane
+    // same-address float atomics serialise in L2 (~45 ns each, measured): bound blocks * cols, i.e. the atomics per
+    // output address, and use 1024-thread blocks so that few blocks still keep enough loads in flight
+    constexpr int NT = 1024;
+    int cgs = cols / 4, cg_per_pass = cgs < NT ? cgs : NT, lanes_r = NT / cg_per_pass;
+    long long blocks = (long long)ctx->num_sms * 2;
+    long long cap = 65536 / cols;
+    if (cap < 8) cap = 8;
+    if (blocks > cap) blocks = cap;
+    long long min_rpb = 4LL * lanes_r;
     long long rpb = (rows + blocks - 1) / blocks;
     if (rpb < min_rpb) rpb = min_rpb;
     rpb = (rpb + lanes_r - 1) / lanes_r * lanes_r;
     blocks = (rows + rpb - 1) / rpb;
-    SG_DISPATCH_DT(dt, T, k_colsum_v4<T><<<(int)blocks, 256, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out));
+    if (dt == SG_F32) k_colsum_v4<float, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const float*)x, rows, cols, rpb, out);
+    else k_colsum_v4<__nv_bfloat16, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const __nv_bfloat16*)x, rows, cols, rpb, out);
     SG_POST_LAUNCH(ctx);
     return SG_OK;
   }
@@ -427,7 +497,11 @@ int sg_maxpool_fwd(sg_ctx* ctx, const void* x, int dt, int n, int h, int w, int 
   SG_REQUIRE(ph >= 1 && pw >= 1 && h % ph == 0 && w % pw == 0, "sg_maxpool_fwd: h,w must be divisible by the window");
   long long total = (long long)n * (h / ph) * (w / pw) * c;
   if (total == 0) return SG_OK;
-  SG_DISPATCH_DT(dt, T, k_maxpool_fwd<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c, ph, pw, (T*)out));
+  if (c % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    SG_DISPATCH_DT(dt, T, k_maxpool_fwd_v4<T><<<ew_grid(ctx, total / 4, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c / 4, ph, pw, (T*)out));
+  } else {
+    SG_DISPATCH_DT(dt, T, k_maxpool_fwd<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c, ph, pw, (T*)out));
+  }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -438,10 +512,17 @@ int sg_maxpool_bwd(sg_ctx* ctx, const float* dout, const void* x, int x_dt, int 
   SG_REQUIRE(ph >= 1 && pw >= 1 && h % ph == 0 && w % pw == 0, "sg_maxpool_bwd: h,w must be divisible by the window");
   long long total = (long long)n * (h / ph) * (w / pw) * c;
   if (total == 0) return SG_OK;
-  int grid = ew_grid(ctx, total, 256);
-  SG_DISPATCH_DT(x_dt, TX,
-                 SG_DISPATCH_DT(dx_dt, TO,
-                                k_maxpool_bwd<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c, ph, pw, relu_mask, (TO*)dx)));
+  if (c % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dout & 15) == 0) {
+    int grid = ew_grid(ctx, total / 4, 256);
+    SG_DISPATCH_DT(x_dt, TX,
+                   SG_DISPATCH_DT(dx_dt, TO,
+                                  k_maxpool_bwd_v4<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c / 4, ph, pw, relu_mask, (TO*)dx)));
+  } else {
+    int grid = ew_grid(ctx, total, 256);
+    SG_DISPATCH_DT(x_dt, TX,
+                   SG_DISPATCH_DT(dx_dt, TO,
+                                  k_maxpool_bwd<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c, ph, pw, relu_mask, (TO*)dx)));
+  }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
