@@ -161,6 +161,15 @@ int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
                 const float* lse, const float* d_o, int n, int q, int kv, int dk, int dv, float* dtheta,
                 float* dphi, float* dg);
 
+/* tensor-core variant for the speed (bf16) mode: theta.phi^T in tf32, P.g in bf16 (mma.sync register chaining), fp32
+ * softmax; same arguments and results within bf16 tolerance.  scratch: n*q floats (D = rowsum(dO o O)). */
+int sg_attn_tc_supported(int q, int kv, int dk, int dv);
+int sg_attn_fwd_tc(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv,
+                   int dk, int dv, float* o, float* lse);
+int sg_attn_bwd_tc(sg_ctx* ctx, const float* theta, const float* phi, const float* g, const float* o,
+                   const float* lse, const float* d_o, int n, int q, int kv, int dk, int dv, float* dtheta,
+                   float* dphi, float* dg, float* scratch);
+
 /* 1x1 projections of the non-local block, one pass over the pixels per data-flow step (arch_ops.py:38-46,55-57,63-67).
  * C = 64 channels, dk = 8, dv = 32; x, dx, og, out, dout are [rows,64]; theta/phi_f [rows,8]; g_f, o, d_o [rows,32];
  * kernels w_theta, w_phi [64,8], w_g [64,32], w_o [32,64] (1x1 HWIO).  Filter gradients are accumulated (+=). */

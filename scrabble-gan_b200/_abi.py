@@ -89,6 +89,9 @@ _PROTOS = {
     "sg_filterbank_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I]),
     "sg_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sg_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "sg_attn_tc_supported": (_I, [_I, _I, _I, _I]),
+    "sg_attn_fwd_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "sg_attn_bwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "sg_nonlocal_proj_fwd": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "sg_nonlocal_out_fwd": (_I, [_P, _P, _L, _P, _P, _P, _P, _P]),
     "sg_nonlocal_out_bwd": (_I, [_P, _P, _P, _L, _P, _P, _P, _P]),

@@ -753,7 +753,22 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
   p.bias = bias; p.mask = mask; p.out = out;
   choose_box(d->grid_w, d->grid_h, d->n, 128, 1, &p.TW, &p.TH, &p.TN);
   p.tiles_x = sg_div_up(d->grid_w, p.TW); p.tiles_y = sg_div_up(d->grid_h, p.TH); p.tiles_n = sg_div_up(d->n, p.TN);
-  p.BN = d->c_out % 256 == 0 ? 256 : (d->c_out % 128 == 0 ? 128 : (d->c_out % 64 == 0 ? 64 : 32));
+  {
+    // N tile: the widest tile has the best operand reuse, but with a static persistent schedule a launch costs
+    // ceil(tiles / #SMs) tile-times, so narrower tiles win when the wide ones leave the last wave mostly empty
+    // (e.g. D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs).  Relative tile times are estimates (A-tile reloads make narrow tiles a little more than proportionally cheaper).
+    const int cand[4] = {256, 128, 64, 32};
+    const double rel[4] = {1.0, 0.56, 0.34, 0.25};
+    const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+    double best = -1.0;
+    p.BN = 32;
+    for (int i = 0; i < 4; ++i) {
+      if (d->c_out % cand[i]) continue;
+      long long tiles = m_tiles * (d->c_out / cand[i]);
+      double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * rel[i];
+      if (best < 0 || cost < best * 0.97) { best = cost; p.BN = cand[i]; }
+    }
+  }
   p.tiles_col = d->c_out / p.BN;
   p.kc_per_tap = d->c_in / KC;
   const int PR = p.TW * p.TH * p.TN;

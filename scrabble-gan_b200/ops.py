@@ -363,19 +363,34 @@ def filterbank_bwd(rt, dout, z, z_stride, y, bank, dbank, dz0=None, dz_stride=32
     return dz0
 
 
-def attn_fwd(rt, theta, phi, g):
+def _attn_tc(rt, q, kv, dk, dv, tc) -> bool:
+    """Tensor-core attention is the speed-mode ("bf16") path; "fp32"/"tf32" modes keep the exact FFMA kernels."""
+    if tc is None:
+        tc = rt.mode == "bf16"
+    return bool(tc and _abi.load().sg_attn_tc_supported(q, kv, dk, dv))
+
+
+def attn_fwd(rt, theta, phi, g, tc=None):
     n, q, dk = theta.shape
     kv, dv = g.shape[1], g.shape[2]
     o, lse = rt.empty((n, q, dv), SG_F32), rt.empty((n, q), SG_F32)
-    call.sg_attn_fwd(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, _p(o), _p(lse))
+    if _attn_tc(rt, q, kv, dk, dv, tc):
+        call.sg_attn_fwd_tc(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, _p(o), _p(lse))
+    else:
+        call.sg_attn_fwd(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, _p(o), _p(lse))
     return o, lse
 
 
-def attn_bwd(rt, theta, phi, g, o, lse, d_o):
+def attn_bwd(rt, theta, phi, g, o, lse, d_o, tc=None):
     n, q, dk = theta.shape
     kv, dv = g.shape[1], g.shape[2]
     dtheta, dphi, dg = rt.empty(theta.shape, SG_F32), rt.empty(phi.shape, SG_F32), rt.empty(g.shape, SG_F32)
-    call.sg_attn_bwd(rt.ctx, _p(theta), _p(phi), _p(g), _p(o), _p(lse), _p(d_o), n, q, kv, dk, dv, _p(dtheta), _p(dphi), _p(dg))
+    if _attn_tc(rt, q, kv, dk, dv, tc):
+        scratch = rt.empty((n, q), SG_F32)
+        call.sg_attn_bwd_tc(rt.ctx, _p(theta), _p(phi), _p(g), _p(o), _p(lse), _p(d_o), n, q, kv, dk, dv, _p(dtheta), _p(dphi),
+                            _p(dg), _p(scratch))
+    else:
+        call.sg_attn_bwd(rt.ctx, _p(theta), _p(phi), _p(g), _p(o), _p(lse), _p(d_o), n, q, kv, dk, dv, _p(dtheta), _p(dphi), _p(dg))
     return dtheta, dphi, dg
 
 

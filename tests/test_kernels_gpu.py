@@ -456,6 +456,30 @@ def test_attention(rt, n, h, w):
     check(dg_, gg.grad, 2e-4, "dg")
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 8, 12), (1, 32, 80), (3, 16, 40), (2, 6, 10), (1, 32, 160)])
+def test_attention_tensor_core(rt, n, h, w):
+    """Speed-mode attention (tf32 theta.phi^T, bf16 P.g via mma.sync) against the fp64 oracle: bf16 tolerance 1e-2 relative
+    to the largest magnitude of each tensor (north_star: 1e-2 in bf16)."""
+    g = torch.Generator().manual_seed(10)
+    q, kv = h * w, (h // 2) * (w // 2)
+    theta = (rnd(g, n, q, 8) * 0.7).requires_grad_(True)
+    phi = (rnd(g, n, kv, 8) * 0.7).requires_grad_(True)
+    gg = rnd(g, n, kv, 32).requires_grad_(True)
+    attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+    o = attn @ gg
+    do = rnd(g, *o.shape)
+    o.backward(do)
+    td, pd, gd = dev(rt, theta), dev(rt, phi), dev(rt, gg)
+    assert abi.load().sg_attn_tc_supported(q, kv, 8, 32)
+    od, lse = ops.attn_fwd(rt, td, pd, gd, tc=True)
+    check(od, o, 1e-2, "attn fwd (tc)")
+    check(lse, torch.logsumexp(theta @ phi.transpose(1, 2), dim=-1), 2e-3, "lse (tc)")
+    dt_, dp_, dg_ = ops.attn_bwd(rt, td, pd, gd, od, lse, dev(rt, do), tc=True)
+    check(dt_, theta.grad, 1e-2, "dtheta (tc)")
+    check(dp_, phi.grad, 1e-2, "dphi (tc)")
+    check(dg_, gg.grad, 1e-2, "dg (tc)")
+
+
 @pytest.mark.parametrize("b,l,c", [(4, 5, 53), (3, 10, 81), (2, 1, 53), (5, 3, 7)])
 def test_ctc(rt, b, l, c):
     g = torch.Generator().manual_seed(11)
