@@ -756,9 +756,10 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
   {
     // N tile: the widest tile has the best operand reuse, but with a static persistent schedule a launch costs
     // ceil(tiles / #SMs) tile-times, so narrower tiles win when the wide ones leave the last wave mostly empty
-    // (e.g. D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs).  Relative tile times are estimates (A-tile reloads make narrow tiles a little more than proportionally cheaper).
+    // (e.g. D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs).  Relative tile times from tools/bench_conv.py on B200: the main loop is operand-load bound, so a 128-column
+    // tile costs ~0.85 of a 256-column one (D.B4.conv1: 127 us with 256 columns vs 164 us with 128).
     const int cand[4] = {256, 128, 64, 32};
-    const double rel[4] = {1.0, 0.56, 0.34, 0.25};
+    const double rel[4] = {1.0, 0.85, 0.75, 0.7};
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
     double best = -1.0;
     p.BN = 32;
