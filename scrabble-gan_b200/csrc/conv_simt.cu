@@ -307,37 +307,43 @@ __global__ void __launch_bounds__(256) k_conv_fwd_cout1(sg_conv_desc d, const TI
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       wr[t][j] = (t < d.ntaps) ? w[d.tap_w_off[t] + (long long)(sub * 8 + j) * d.w_ci_stride] : 0.f;
-  const long long P = (long long)d.n * d.grid_h * d.grid_w;
   const float b0 = bias ? bias[0] : 0.f;
-  for (long long p = (long long)blockIdx.x * pix_per_block + threadIdx.x / tpp; p < P + pix_per_block;
-       p += (long long)gridDim.x * pix_per_block) {
-    const bool live = p < P;
-    float acc = 0.f;
-    Pix q = decode_pix(live ? p : 0, d.grid_h, d.grid_w);
-    if (live) {
+  // one output row per block iteration (no per-pixel integer division); all lanes of a warp stay in the loop together
+  // because the shuffle reduction needs the full c_in/8 group
+  const int nrows = d.n * d.grid_h;
+  const int px_lane = threadIdx.x / tpp;
+  const int xsteps = (d.grid_w + pix_per_block - 1) / pix_per_block;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int ni = row / d.grid_h, y = row - ni * d.grid_h;
+    const TIn* img = in + (long long)ni * d.in_h * d.in_w * d.c_in + sub * 8;
+    for (int xs = 0; xs < xsteps; ++xs) {
+      const int x = px_lane + xs * pix_per_block;
+      const bool live = x < d.grid_w;
+      float acc = 0.f;
+      if (live) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        if (t < d.ntaps) {
-          int iy = q.y * d.in_sy + d.tap_dy[t], ix = q.x * d.in_sx + d.tap_dx[t];
-          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
-            float v[8];
-            load8(in + (((long long)q.n * d.in_h + iy) * d.in_w + ix) * d.c_in + sub * 8, v);
+        for (int t = 0; t < 9; ++t) {
+          if (t < d.ntaps) {
+            int iy = y * d.in_sy + d.tap_dy[t], ix = x * d.in_sx + d.tap_dx[t];
+            if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
+              float v[8];
+              load8(img + (iy * d.in_w + ix) * d.c_in, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wr[t][j], acc);
+              for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wr[t][j], acc);
+            }
           }
         }
       }
+      for (int o = tpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (live && sub == 0) {
+        long long idx = ((long long)ni * d.out_h + y * d.out_sy + d.out_py) * d.out_w + x * d.out_sx + d.out_px;
+        float v = acc + b0;
+        if (d.relu) v = fmaxf(v, 0.f);
+        if (mask) v = ld_any(mask, idx, d.mask_dt) > 0.f ? v : 0.f;
+        if (d.accumulate) v += ld_any(out, idx, d.out_dt);
+        st_any(out, idx, d.out_dt, v);
+      }
     }
-    for (int o = tpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (live && sub == 0) {
-      long long idx = ((long long)q.n * d.out_h + q.y * d.out_sy + d.out_py) * d.out_w + q.x * d.out_sx + d.out_px;
-      float v = acc + b0;
-      if (d.relu) v = fmaxf(v, 0.f);
-      if (mask) v = ld_any(mask, idx, d.mask_dt) > 0.f ? v : 0.f;
-      if (d.accumulate) v += ld_any(out, idx, d.out_dt);
-      st_any(out, idx, d.out_dt, v);
-    }
-    if (p >= P) break;
   }
 }
 
@@ -430,34 +436,40 @@ __global__ void __launch_bounds__(256) k_conv_fwd_cin1(sg_conv_desc d, const flo
     for (int j = 0; j < 8; ++j) wr[t][j] = (t < d.ntaps) ? w[d.tap_w_off[t] + (long long)(sub * 8 + j) * d.w_co_stride] : 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) br[j] = bias ? bias[sub * 8 + j] : 0.f;
-  const long long P = (long long)d.n * d.grid_h * d.grid_w;
-  for (long long p = (long long)blockIdx.x * pix_per_block + threadIdx.x / groups; p < P; p += (long long)gridDim.x * pix_per_block) {
-    Pix q = decode_pix(p, d.grid_h, d.grid_w);
-    float acc[8];
+  // one image row per block iteration (no per-pixel integer division)
+  const int nrows = d.n * d.grid_h;
+  const int px_lane = threadIdx.x / groups;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int ni = row / d.grid_h, y = row - ni * d.grid_h;
+    const float* img = in + (long long)ni * d.in_h * d.in_w;
+    TOut* orow = out + ((long long)ni * d.out_h + y) * d.out_w * d.c_out;
+    for (int x = px_lane; x < d.grid_w; x += pix_per_block) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+      for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (t < d.ntaps) {
-        int iy = q.y + d.tap_dy[t], ix = q.x + d.tap_dx[t];
-        if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
-          float xv = __ldg(in + ((long long)q.n * d.in_h + iy) * d.in_w + ix);
+      for (int t = 0; t < 9; ++t) {
+        if (t < d.ntaps) {
+          int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
+          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
+            float xv = __ldg(img + iy * d.in_w + ix);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t][j], acc[j]);
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t][j], acc[j]);
+          }
         }
       }
-    }
-    if (d.relu) {
+      if (d.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      }
+      TOut* op = orow + x * d.c_out + sub * 8;
+      if (d.accumulate) {
+        float4 a = sg_ld4(op), b = sg_ld4(op + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+      sg_st4(op, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      sg_st4(op + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
-    TOut* op = out + (((long long)q.n * d.out_h + q.y) * d.out_w + q.x) * d.c_out + sub * 8;
-    if (d.accumulate) {
-      float4 a = sg_ld4(op), b = sg_ld4(op + 4);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-    }
-    sg_st4(op, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    sg_st4(op + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
   }
 }
 
@@ -487,8 +499,7 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
     int tpp = d->c_in / 8;
     bool pow2 = tpp >= 1 && tpp <= 32 && (tpp & (tpp - 1)) == 0;
     if (d->c_out == 1 && d->c_in % 8 == 0 && pow2 && d->ntaps <= 9 && ((uintptr_t)in & 15) == 0) {
-      int ppb = 256 / tpp;
-      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 3;   // 72 weights live in registers per thread
+      long long need = (long long)d->n * d->grid_h, cap = (long long)ctx->num_sms * 4;   // one image row per block iteration
       int grid = (int)(need < cap ? need : cap);
       if (d->in_dt == SG_F32)
         k_conv_fwd_cout1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, mask, out);
@@ -503,8 +514,7 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
     int groups = d->c_out / 8;
     bool g_ok = d->c_out % 8 == 0 && groups >= 1 && groups <= 32 && 256 % groups == 0;
     if (unit && d->c_in == 1 && g_ok && d->ntaps <= 9 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0) {
-      int ppb = 256 / groups;
-      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 3;
+      long long need = (long long)d->n * d->grid_h, cap = (long long)ctx->num_sms * 4;   // one image row per block iteration
       int grid = (int)(need < cap ? need : cap);
       if (d->out_dt == SG_F32) k_conv_fwd_cin1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
       else k_conv_fwd_cin1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);

@@ -193,20 +193,26 @@ __global__ void k_avgpool2_fwd(const float* __restrict__ x, int n, int h, int w,
   }
 }
 
+// one thread per (output-row pair, x pair, 4 channels): reads one float4 of dout, writes the 2 x 2 window (32-bit index
+// math: one division chain per 4 stores instead of per store)
 template <typename TO>
 __global__ void k_avgpool2_bwd(const float* __restrict__ dout, int n, int h, int w, int c4, TO* __restrict__ dx) {
-  int ho = h / 2, wo = w / 2;
-  long long total = (long long)n * h * w * c4;
-  long long stride = (long long)gridDim.x * blockDim.x;
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * c4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long row_e = (long long)w * c4 * 4;       // elements per input row
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int cc = (int)(i % c4);
-    long long p = i / c4;
-    int x_ = (int)(p % w);
-    p /= w;
-    int y_ = (int)(p % h);
-    int ni = (int)(p / h);
-    float4 v = sg_ld4(dout + ((((long long)ni * ho + y_ / 2) * wo + x_ / 2) * c4 + cc) * 4);
-    sg_st4(dx + 4 * i, make_float4(0.25f * v.x, 0.25f * v.y, 0.25f * v.z, 0.25f * v.w));
+    const int cc = (int)(i % c4);
+    const long long p = i / c4;                         // (ni*ho + oy)*wo + ox
+    const int ox = (int)(p % wo);
+    const long long r = p / wo;                         // ni*ho + oy  ->  input row 2*r (h = 2*ho)
+    float4 v = sg_ld4(dout + 4 * i);
+    v = make_float4(0.25f * v.x, 0.25f * v.y, 0.25f * v.z, 0.25f * v.w);
+    TO* o = dx + 2 * r * row_e + ((long long)(2 * ox) * c4 + cc) * 4;
+    sg_st4(o, v);
+    sg_st4(o + 4LL * c4, v);
+    sg_st4(o + row_e, v);
+    sg_st4(o + row_e + 4LL * c4, v);
   }
 }
 
@@ -487,7 +493,7 @@ int sg_avgpool2_bwd(sg_ctx* ctx, const float* dout, int n, int h, int w, int c, 
   SG_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "sg_avgpool2_bwd: needs even h,w and c%%4==0");
   long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return SG_OK;
-  SG_DISPATCH_DT(dx_dt, TO, k_avgpool2_bwd<TO><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(dout, n, h, w, c / 4, (TO*)dx));
+  SG_DISPATCH_DT(dx_dt, TO, k_avgpool2_bwd<TO><<<ew_grid(ctx, total / 4, 256), 256, 0, ctx->stream>>>(dout, n, h, w, c / 4, (TO*)dx));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -24,17 +24,25 @@ __device__ __forceinline__ void seg_find(const SegMat& m, int col, int& s, int& 
   if (off >= m.w[0]) { off -= m.w[0]; s = 1; if (off >= m.w[1]) { off -= m.w[1]; s = 2; } }
 }
 
-#define NL_ROWS 128
-
 // W logical [K,N]; if TRANS_W the stored matrix is the column-segmented [N, K] one and is read transposed.
+// Thread tile 4 rows x 4 columns: per k one LDS.128 of the (transposed) A tile and one LDS.128 of W feed 16 FMAs;
+// a warp's stores cover whole 256-byte rows of C.
+template <int K, int N>
+struct NlTile {
+  static constexpr int NCG = N / 4;                 // column groups
+  static constexpr int RG = 256 / NCG;              // row groups per block
+  static constexpr int TR = 4 * RG;                 // rows per tile
+  static constexpr int TRP = (TR + 31) / 32 * 32 + 4;   // == 4 (mod 32): conflict-free STS.128 of the transposed tile
+};
+
 template <int K, int N, bool TRANS_W>
 __global__ void __launch_bounds__(256) k_nl_rowgemm(long long rows, SegMat A, SegMat W, SegMat C, const float* __restrict__ alpha_p,
                                                      int accumulate, const float* __restrict__ resid_scale_p,
                                                      const float* __restrict__ resid_x, float* __restrict__ resid_out) {
-  __shared__ float As[NL_ROWS][K + 1];
+  using T = NlTile<K, N>;
+  __shared__ __align__(16) float As[K][T::TRP];     // transposed: As[k][row]
   __shared__ __align__(16) float Ws[K][N];
   const int tid = threadIdx.x;
-  // ---- weights -> smem (once per block) ----
   for (int i = tid; i < K * N; i += 256) {
     int k = i / N, n = i % N;
     int s, off;
@@ -50,75 +58,84 @@ __global__ void __launch_bounds__(256) k_nl_rowgemm(long long rows, SegMat A, Se
   }
   const float alpha = alpha_p ? *alpha_p : 1.f;
   const float rscale = resid_scale_p ? *resid_scale_p : 1.f;
-  const int r = tid & (NL_ROWS - 1), half = tid >> 7;
-  constexpr int NH = N / 2;
+  const int cg = tid % T::NCG, rg = tid / T::NCG;
+  const bool active = rg < T::RG;
 
-  for (long long row0 = (long long)blockIdx.x * NL_ROWS; row0 < rows; row0 += (long long)gridDim.x * NL_ROWS) {
-    const int cnt = rows - row0 < NL_ROWS ? (int)(rows - row0) : NL_ROWS;
+  for (long long row0 = (long long)blockIdx.x * T::TR; row0 < rows; row0 += (long long)gridDim.x * T::TR) {
+    const int cnt = rows - row0 < T::TR ? (int)(rows - row0) : T::TR;
     __syncthreads();
-    // ---- A tile -> smem: every segment's tile is one contiguous chunk of cnt * w floats ----
+    // ---- A tile -> smem, transposed: item = (row quad, k); 4 coalesced row reads -> one STS.128 ----
     int koff = 0;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       const int w = A.w[s];
       if (w == 0) continue;
-      const float4* src = reinterpret_cast<const float4*>(A.p[s] + row0 * w);
-      const int n4 = cnt * w / 4;
-      for (int i = tid; i < n4; i += 256) {
-        float4 v = src[i];
-        int e = i * 4, rr = e / w, cc = e % w + koff;
-        As[rr][cc] = v.x; As[rr][cc + 1] = v.y; As[rr][cc + 2] = v.z; As[rr][cc + 3] = v.w;
+      const float* src = A.p[s] + row0 * w;
+      for (int i = tid; i < T::RG * w; i += 256) {
+        const int kk = i % w, rq = i / w;
+        float4 v;
+        const int r = 4 * rq;
+        v.x = r < cnt ? src[(long long)r * w + kk] : 0.f;
+        v.y = r + 1 < cnt ? src[(long long)(r + 1) * w + kk] : 0.f;
+        v.z = r + 2 < cnt ? src[(long long)(r + 2) * w + kk] : 0.f;
+        v.w = r + 3 < cnt ? src[(long long)(r + 3) * w + kk] : 0.f;
+        *reinterpret_cast<float4*>(&As[koff + kk][r]) = v;
       }
       koff += w;
     }
     __syncthreads();
-    if (r < cnt) {
-      float acc[NH];
+    if (active && 4 * rg < cnt) {
+      float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 8
       for (int k = 0; k < K; ++k) {
-        const float a = As[r][k];
-        const float4* wp = reinterpret_cast<const float4*>(&Ws[k][half * NH]);
-#pragma unroll
-        for (int j = 0; j < NH / 4; ++j) {
-          float4 w4 = wp[j];
-          acc[4 * j] = fmaf(a, w4.x, acc[4 * j]);
-          acc[4 * j + 1] = fmaf(a, w4.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(a, w4.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(a, w4.w, acc[4 * j + 3]);
-        }
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][4 * rg]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ws[k][4 * cg]);
+        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]); acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]); acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]); acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]); acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
       }
-      const long long row = row0 + r;
+      int s, off;
+      seg_find(C, 4 * cg, s, off);
 #pragma unroll
-      for (int j = 0; j < NH; j += 4) {
-        int col = half * NH + j, s, off;
-        seg_find(C, col, s, off);
-        float4 v = make_float4(alpha * acc[j], alpha * acc[j + 1], alpha * acc[j + 2], alpha * acc[j + 3]);
-        float* cp = C.p[s] + row * C.w[s] + off;
-        if (accumulate) {
-          float4 o = sg_ld4(cp);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        sg_st4(cp, v);
-        if (resid_out) {       // second output: resid_out = rscale * C + x   (sigma * og + x, arch_ops.py:67)
-          float4 x = sg_ld4(resid_x + row * N + col);
-          sg_st4(resid_out + row * N + col, make_float4(fmaf(rscale, v.x, x.x), fmaf(rscale, v.y, x.y), fmaf(rscale, v.z, x.z),
-                                                        fmaf(rscale, v.w, x.w)));
+      for (int i = 0; i < 4; ++i) {
+        if (4 * rg + i < cnt) {
+          const long long row = row0 + 4 * rg + i;
+          float4 v = make_float4(alpha * acc[i][0], alpha * acc[i][1], alpha * acc[i][2], alpha * acc[i][3]);
+          float* cp = C.p[s] + row * C.w[s] + off;
+          if (accumulate) {
+            float4 o = sg_ld4(cp);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          sg_st4(cp, v);
+          if (resid_out) {     // second output: resid_out = rscale * C + x   (sigma * og + x, arch_ops.py:67)
+            float4 x = sg_ld4(resid_x + row * N + 4 * cg);
+            sg_st4(resid_out + row * N + 4 * cg, make_float4(fmaf(rscale, v.x, x.x), fmaf(rscale, v.y, x.y), fmaf(rscale, v.z, x.z),
+                                                             fmaf(rscale, v.w, x.w)));
+          }
         }
       }
     }
   }
 }
 
-#define NLW_ROWS 64
+// dW[KA,KB] += alpha * A^T . B over rows.  A block is SUB sub-blocks of (KA/4)*(KB/4) threads; every sub-block streams its
+// own 32-row chunks through its own shared-memory buffers (more warps per SM to hide the load -> sync -> FMA latency
+// chain), the sub-block partials are combined through shared memory and the block issues ONE atomicAdd per element.
+#define NLW_ROWS 32
+#define NLW_SUB 4
 template <int KA, int KB>
-__global__ void __launch_bounds__((KA / 4) * (KB / 4)) k_nl_wgrad(long long rows, long long rows_per_block, SegMat A, SegMat B,
-                                                                   SegMat DW, const float* __restrict__ alpha_p) {
+__global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long long rows, long long rows_per_block, SegMat A, SegMat B,
+                                                                             SegMat DW, const float* __restrict__ alpha_p) {
   constexpr int TA = KA / 4, TB = KB / 4, NT = TA * TB;
-  __shared__ __align__(16) float As[NLW_ROWS][KA];
-  __shared__ __align__(16) float Bs[NLW_ROWS][KB];
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) float nlw_smem[];
+  const int sub = threadIdx.x / NT, tid = threadIdx.x % NT;
+  float (*As)[KA] = reinterpret_cast<float (*)[KA]>(nlw_smem + (size_t)sub * NLW_ROWS * (KA + KB));
+  float (*Bs)[KB] = reinterpret_cast<float (*)[KB]>(nlw_smem + (size_t)sub * NLW_ROWS * (KA + KB) + NLW_ROWS * KA);
   const int ti = tid % TA, tj = tid / TA;
   float acc[4][4];
 #pragma unroll
@@ -128,8 +145,10 @@ __global__ void __launch_bounds__((KA / 4) * (KB / 4)) k_nl_wgrad(long long rows
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  for (long long row0 = r0; row0 < r1; row0 += NLW_ROWS) {
-    const int cnt = r1 - row0 < NLW_ROWS ? (int)(r1 - row0) : NLW_ROWS;
+  for (long long base = r0; base < r1; base += (long long)NLW_SUB * NLW_ROWS) {
+    const long long row0 = base + (long long)sub * NLW_ROWS;
+    int cnt = 0;
+    if (row0 < r1) cnt = r1 - row0 < NLW_ROWS ? (int)(r1 - row0) : NLW_ROWS;
     __syncthreads();
     int koff = 0;
 #pragma unroll
@@ -166,14 +185,29 @@ __global__ void __launch_bounds__((KA / 4) * (KB / 4)) k_nl_wgrad(long long rows
       acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]); acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
     }
   }
-  const float alpha = alpha_p ? *alpha_p : 1.f;
-  int s, off;
-  seg_find(DW, 4 * tj, s, off);
+  // combine the sub-block partials: red[sub][16][NT] (re-using the staging buffers; NLW_SUB*16*NT <= NLW_SUB*NLW_ROWS*(KA+KB))
+  __syncthreads();
+  float* red = nlw_smem;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float* dp = DW.p[s] + (long long)(4 * ti + i) * DW.w[s] + off;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dp + j, alpha * acc[i][j]);
+    for (int j = 0; j < 4; ++j) red[((size_t)sub * 16 + i * 4 + j) * NT + tid] = acc[i][j];
+  __syncthreads();
+  if (sub == 0) {
+    const float alpha = alpha_p ? *alpha_p : 1.f;
+    int s, off;
+    seg_find(DW, 4 * tj, s, off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* dp = DW.p[s] + (long long)(4 * ti + i) * DW.w[s] + off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i][j];
+#pragma unroll
+        for (int u = 1; u < NLW_SUB; ++u) v += red[((size_t)u * 16 + i * 4 + j) * NT + tid];
+        atomicAdd(dp + j, alpha * v);
+      }
+    }
   }
 }
 
@@ -189,16 +223,30 @@ static SegMat seg3(const float* a, int wa, const float* b, int wb, const float* 
   m.w[0] = wa; m.w[1] = wb; m.w[2] = wc;
   return m;
 }
+template <int K, int N>
 static int nl_grid(sg_ctx* ctx, long long rows) {
-  long long need = (rows + NL_ROWS - 1) / NL_ROWS, cap = (long long)ctx->num_sms * 4;
+  long long need = (rows + NlTile<K, N>::TR - 1) / NlTile<K, N>::TR, cap = (long long)ctx->num_sms * 6;
   return (int)(need < cap ? need : cap);
 }
 static void nl_wgrad_grid(sg_ctx* ctx, long long rows, int* grid, long long* rpb) {
   long long blocks = (long long)ctx->num_sms * 2;
+  const long long step = (long long)NLW_SUB * NLW_ROWS;
   long long r = (rows + blocks - 1) / blocks;
-  r = (r + NLW_ROWS - 1) / NLW_ROWS * NLW_ROWS;
+  r = (r + step - 1) / step * step;
   *rpb = r;
   *grid = (int)((rows + r - 1) / r);
+}
+template <int KA, int KB>
+static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegMat DW, const float* alpha) {
+  int grid;
+  long long rpb;
+  nl_wgrad_grid(ctx, rows, &grid, &rpb);
+  size_t smem = sizeof(float) * (size_t)NLW_SUB * NLW_ROWS * (KA + KB);
+  static_assert(NLW_SUB * 16 * (KA / 4) * (KB / 4) <= NLW_SUB * NLW_ROWS * (KA + KB), "reduction buffer does not fit");
+  SG_CHECK_CUDA(cudaFuncSetAttribute(k_nl_wgrad<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_nl_wgrad<KA, KB><<<grid, NLW_SUB * (KA / 4) * (KB / 4), smem, ctx->stream>>>(rows, rpb, A, B, DW, alpha);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
 }
 
 #define NL_C 64
@@ -213,7 +261,7 @@ int sg_nonlocal_proj_fwd(sg_ctx* ctx, const float* x, long long rows, const floa
   SG_REQUIRE(ctx && x && w_theta && w_phi && w_g && theta && phi_f && g_f, "sg_nonlocal_proj_fwd: NULL");
   SG_REQUIRE(NL_ALIGNED(x) && NL_ALIGNED(theta) && NL_ALIGNED(phi_f) && NL_ALIGNED(g_f), "sg_nonlocal_proj_fwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
-  k_nl_rowgemm<NL_C, 2 * NL_DK + NL_DV, false><<<nl_grid(ctx, rows), 256, 0, ctx->stream>>>(
+  k_nl_rowgemm<NL_C, 2 * NL_DK + NL_DV, false><<<nl_grid<NL_C, 2 * NL_DK + NL_DV>(ctx, rows), 256, 0, ctx->stream>>>(
       rows, seg1(x, NL_C), seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV), seg3(theta, NL_DK, phi_f, NL_DK, g_f, NL_DV), nullptr, 0,
       nullptr, nullptr, nullptr);
   SG_POST_LAUNCH(ctx);
@@ -226,7 +274,7 @@ int sg_nonlocal_out_fwd(sg_ctx* ctx, const float* o, long long rows, const float
   SG_REQUIRE(NL_ALIGNED(o) && NL_ALIGNED(x) && NL_ALIGNED(og) && NL_ALIGNED(out), "sg_nonlocal_out_fwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
   // og = o . Wo (kept un-scaled for d sigma = <dout, og>);  out = sigma * og + x
-  k_nl_rowgemm<NL_DV, NL_C, false><<<nl_grid(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(o, NL_DV), seg1(w_o, NL_C), seg1(og, NL_C),
+  k_nl_rowgemm<NL_DV, NL_C, false><<<nl_grid<NL_DV, NL_C>(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(o, NL_DV), seg1(w_o, NL_C), seg1(og, NL_C),
                                                                                  nullptr, 0, sigma, x, out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -238,17 +286,11 @@ int sg_nonlocal_out_bwd(sg_ctx* ctx, const float* dout, const float* o, long lon
   SG_REQUIRE(NL_ALIGNED(dout) && NL_ALIGNED(o) && NL_ALIGNED(d_o), "sg_nonlocal_out_bwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
   // d_o = sigma * dout . Wo^T
-  k_nl_rowgemm<NL_C, NL_DV, true><<<nl_grid(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(dout, NL_C), seg1(w_o, NL_C), seg1(d_o, NL_DV),
+  k_nl_rowgemm<NL_C, NL_DV, true><<<nl_grid<NL_C, NL_DV>(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(dout, NL_C), seg1(w_o, NL_C), seg1(d_o, NL_DV),
                                                                                 sigma, 0, nullptr, nullptr, nullptr);
   SG_POST_LAUNCH(ctx);
-  if (dw_o) {                  // dWo[32,64] += sigma * o^T . dout
-    int grid;
-    long long rpb;
-    nl_wgrad_grid(ctx, rows, &grid, &rpb);
-    k_nl_wgrad<NL_DV, NL_C><<<grid, (NL_DV / 4) * (NL_C / 4), 0, ctx->stream>>>(rows, rpb, seg1(o, NL_DV), seg1(dout, NL_C),
-                                                                                 seg1(dw_o, NL_C), sigma);
-    SG_POST_LAUNCH(ctx);
-  }
+  if (dw_o)                    // dWo[32,64] += sigma * o^T . dout
+    return nl_wgrad_launch<NL_DV, NL_C>(ctx, rows, seg1(o, NL_DV), seg1(dout, NL_C), seg1(dw_o, NL_C), sigma);
   return SG_OK;
 }
 
@@ -263,17 +305,11 @@ int sg_nonlocal_proj_bwd(sg_ctx* ctx, const float* x, const float* dtheta, const
   if (rows == 0) return SG_OK;
   SegMat d = seg3(dtheta, NL_DK, dphi_f, NL_DK, dg_f, NL_DV);
   // dx += [dtheta | dphi | dg] . [Wtheta | Wphi | Wg]^T
-  k_nl_rowgemm<2 * NL_DK + NL_DV, NL_C, true><<<nl_grid(ctx, rows), 256, 0, ctx->stream>>>(
+  k_nl_rowgemm<2 * NL_DK + NL_DV, NL_C, true><<<nl_grid<2 * NL_DK + NL_DV, NL_C>(ctx, rows), 256, 0, ctx->stream>>>(
       rows, d, seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV), seg1(dx, NL_C), nullptr, 1, nullptr, nullptr, nullptr);
   SG_POST_LAUNCH(ctx);
-  if (dw_theta) {              // [dWtheta | dWphi | dWg] += x^T . [dtheta | dphi | dg]
-    int grid;
-    long long rpb;
-    nl_wgrad_grid(ctx, rows, &grid, &rpb);
-    k_nl_wgrad<NL_C, 2 * NL_DK + NL_DV><<<grid, (NL_C / 4) * ((2 * NL_DK + NL_DV) / 4), 0, ctx->stream>>>(
-        rows, rpb, seg1(x, NL_C), d, seg3(dw_theta, NL_DK, dw_phi, NL_DK, dw_g, NL_DV), nullptr);
-    SG_POST_LAUNCH(ctx);
-  }
+  if (dw_theta)                // [dWtheta | dWphi | dWg] += x^T . [dtheta | dphi | dg]
+    return nl_wgrad_launch<NL_C, 2 * NL_DK + NL_DV>(ctx, rows, seg1(x, NL_C), d, seg3(dw_theta, NL_DK, dw_phi, NL_DK, dw_g, NL_DV), nullptr);
   return SG_OK;
 }
 
