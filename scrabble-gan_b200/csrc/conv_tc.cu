@@ -130,7 +130,13 @@ __host__ __device__ inline uint32_t make_idesc(bool tf32, bool a_mn, bool b_mn, 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 #define TC_MAX_STAGES 8
+#define TC_EPI_STAGING (4 * 32 * 33 * 4)      // per-warp 32 x 33 fp32 transpose buffers of the 4 epilogue warps
 #define TC_THREADS 192
 #define TC_TMEM_COLS 512
 
@@ -248,9 +254,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // tcgen05.ld hands every lane ONE accumulator row (pixel) x 32 consecutive channels.  Storing that directly would
+    // make each warp store touch 32 different pixels (32 sectors, 8..16 useful bytes each), so the 32 x 32 chunk goes
+    // through a per-warp shared-memory transpose: afterwards 4 adjacent lanes own 32 consecutive channels of one pixel
+    // (64 B of bf16 / 128 B of fp32 contiguous) and every store / mask load / accumulate load is sector-exact.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;           // accumulator row = pixel index inside the tile
     const int rows_in_tile = p.TW * p.TH * p.TN;
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * (p.a_stage_stride + p.b_stage_stride)) +
+                 (warp - 2) * (32 * 33);
+    const int tr0 = lane >> 2, c0 = (lane & 3) * 8;      // transposed ownership: rows tr0 + 8 i, channels c0 .. c0 + 7
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -262,17 +275,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       int ly = rem / p.TW, lx = rem % p.TW;
       int ni = tn * p.TN + ln, oy = ty * p.TH + ly, ox = tx * p.TW + lx;
       bool valid = row < rows_in_tile && ni < p.n && oy < p.grid_h && ox < p.grid_w;
-      long long base = 0;
+      long long base = -1;                                  // < 0 = no such output pixel
       if (valid)
         base = (((long long)ni * p.out_h + oy * p.out_sy + p.out_py) * p.out_w + ox * p.out_sx + p.out_px) * p.c_out +
                col_t * p.BN;
+      long long rbase[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rbase[i] = __shfl_sync(0xffffffffu, base, tr0 + 8 * i);
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
       for (int ch = 0; ch < p.BN / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
-        if (valid) {
+        {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -288,41 +304,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          long long off = base + ch * 32;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = f[j];
+          __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (rbase[i] < 0) continue;
+          const float* sp = stg + (tr0 + 8 * i) * 33 + c0;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = sp[j];
+          const long long off = rbase[i] + ch * 32 + c0;
           if (p.mask) {
+            float m[8];
             if (p.mask_dt == SG_F32) {
               const float* mp = reinterpret_cast<const float*>(p.mask) + off;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 m = sg_ld4(mp + j);
-                f[j] = m.x > 0.f ? f[j] : 0.f; f[j + 1] = m.y > 0.f ? f[j + 1] : 0.f;
-                f[j + 2] = m.z > 0.f ? f[j + 2] : 0.f; f[j + 3] = m.w > 0.f ? f[j + 3] : 0.f;
-              }
+              float4 a = sg_ld4(mp), b = sg_ld4(mp + 4);
+              m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
             } else {
               const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + off;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 m = sg_ld4(mp + j);
-                f[j] = m.x > 0.f ? f[j] : 0.f; f[j + 1] = m.y > 0.f ? f[j + 1] : 0.f;
-                f[j + 2] = m.z > 0.f ? f[j + 2] : 0.f; f[j + 3] = m.w > 0.f ? f[j + 3] : 0.f;
-              }
+              float4 a = sg_ld4(mp), b = sg_ld4(mp + 4);
+              m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
           }
           if (p.out_dt == SG_F32) {
             float* op = reinterpret_cast<float*>(p.out) + off;
             if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = sg_ld4(op + j);
-                f[j] += o.x; f[j + 1] += o.y; f[j + 2] += o.z; f[j + 3] += o.w;
-              }
+              float4 a = sg_ld4(op), b = sg_ld4(op + 4);
+              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) sg_st4(op + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+            sg_st4(op, make_float4(f[0], f[1], f[2], f[3]));
+            sg_st4(op + 4, make_float4(f[4], f[5], f[6], f[7]));
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) sg_st4(op + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+            uint4 pk;
+            pk.x = pack2(f[0], f[1]); pk.y = pack2(f[2], f[3]); pk.z = pack2(f[4], f[5]); pk.w = pack2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(op) = pk;
           }
         }
       }
@@ -400,13 +421,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   const int units = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
   const int PR = p.TW * p.TH * p.TN;
 
-  // unit -> (split fastest, then ci tile, co tile, tap)
+  // unit -> (ci tile fastest, co tile, tap, pixel split slowest): the CTAs of one wave work on the SAME pixel range with
+  // different (tap, co, ci) tiles, so every dy / input tile is fetched from HBM once and shared through L2
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int sp = u % p.splits, r = u / p.splits;
+        const int base_units = p.ntaps * p.co_tiles * p.ci_tiles;
+        int sp = u / base_units, r = u % base_units;
         int cit = r % p.ci_tiles; r /= p.ci_tiles;
         int cot = r % p.co_tiles;
         int t = r / p.co_tiles;
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int sp = u % p.splits;
+      int sp = u / (p.ntaps * p.co_tiles * p.ci_tiles);
       int pt0 = sp * p.ptiles_per_split, pt1 = pt0 + p.ptiles_per_split;
       if (pt1 > ptiles) pt1 = ptiles;
       mbar_wait(bar_tempty + 8 * as, aph ^ 1);
@@ -468,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     int as = 0;
     uint32_t aph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int r = u / p.splits;
+      int r = u % (p.ntaps * p.co_tiles * p.ci_tiles);
       int cit = r % p.ci_tiles; r /= p.ci_tiles;
       int cot = r % p.co_tiles;
       int t = r / p.co_tiles;
@@ -777,7 +800,7 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
   p.b_bytes = (uint32_t)p.BN * 128u;
   p.a_stage_stride = 128u * 128u;                  // always reserve a full 128-row tile (1024-byte aligned)
   p.b_stage_stride = (uint32_t)p.BN * 128u;
-  int stages = (int)((220u * 1024u) / (p.a_stage_stride + p.b_stage_stride));
+  int stages = (int)((204u * 1024u) / (p.a_stage_stride + p.b_stage_stride));
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SG_REQUIRE(stages >= 2, "sg_conv_fwd_tc: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -806,7 +829,7 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
 
   long long total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
   int grid = (int)(total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms);
-  size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024;
+  size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024 + TC_EPI_STAGING;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_conv_tc<float><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
@@ -872,10 +895,23 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
 
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
   long long base_units = (long long)d->ntaps * p.co_tiles * p.ci_tiles;
-  int splits = (int)((2LL * ctx->num_sms + base_units - 1) / base_units);
+  // pixel splits: static round-robin over #SMs persistent CTAs costs ceil(units / #SMs) unit-times, so pick the split
+  // count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43 waves)
   int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (max_splits > 32) max_splits = 32;
+  int splits = 1;
+  double best_eff = -1.0;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    int pps = sg_div_up(ptiles, sp);
+    int eff_sp = sg_div_up(ptiles, pps);
+    if (eff_sp != sp) continue;
+    long long units_sp = base_units * sp;
+    long long waves = (units_sp + ctx->num_sms - 1) / ctx->num_sms;
+    // work per CTA in k-blocks: waves * pps (plus one epilogue per unit, ~ 4 k-blocks worth)
+    double cost = (double)waves * (pps + 4.0);
+    double eff = 1.0 / cost;
+    if (eff > best_eff * 1.02) { best_eff = eff; splits = sp; }
+  }
   p.ptiles_per_split = sg_div_up(ptiles, splits);
   p.splits = sg_div_up(ptiles, p.ptiles_per_split);
 
