@@ -286,6 +286,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
       for (int ch = 0; ch < p.BN / 32; ++ch) {
+        // issue every global read of this chunk (ReLU mask, accumulate operand) up front: all of them are in flight while
+        // the accumulators come out of TMEM and go through the transpose
+        float mk[4][8], prev[4][8];
+        const bool want_prev = p.accumulate && p.out_dt == SG_F32;
+        if (p.mask) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rbase[i] < 0) continue;
+            const long long off = rbase[i] + ch * 32 + c0;
+            float4 a, b;
+            if (p.mask_dt == SG_F32) {
+              const float* mp = reinterpret_cast<const float*>(p.mask) + off;
+              a = sg_ld4(mp); b = sg_ld4(mp + 4);
+            } else {
+              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + off;
+              a = sg_ld4(mp); b = sg_ld4(mp + 4);
+            }
+            mk[i][0] = a.x; mk[i][1] = a.y; mk[i][2] = a.z; mk[i][3] = a.w; mk[i][4] = b.x; mk[i][5] = b.y; mk[i][6] = b.z; mk[i][7] = b.w;
+          }
+        }
+        if (want_prev) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (rbase[i] < 0) continue;
+            const float* op = reinterpret_cast<const float*>(p.out) + rbase[i] + ch * 32 + c0;
+            float4 a = sg_ld4(op), b = sg_ld4(op + 4);
+            prev[i][0] = a.x; prev[i][1] = a.y; prev[i][2] = a.z; prev[i][3] = a.w; prev[i][4] = b.x; prev[i][5] = b.y; prev[i][6] = b.z; prev[i][7] = b.w;
+          }
+        }
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
         {
@@ -318,24 +347,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           for (int j = 0; j < 8; ++j) f[j] = sp[j];
           const long long off = rbase[i] + ch * 32 + c0;
           if (p.mask) {
-            float m[8];
-            if (p.mask_dt == SG_F32) {
-              const float* mp = reinterpret_cast<const float*>(p.mask) + off;
-              float4 a = sg_ld4(mp), b = sg_ld4(mp + 4);
-              m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
-            } else {
-              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + off;
-              float4 a = sg_ld4(mp), b = sg_ld4(mp + 4);
-              m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
-            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+            for (int j = 0; j < 8; ++j) f[j] = mk[i][j] > 0.f ? f[j] : 0.f;
           }
           if (p.out_dt == SG_F32) {
             float* op = reinterpret_cast<float*>(p.out) + off;
-            if (p.accumulate) {
-              float4 a = sg_ld4(op), b = sg_ld4(op + 4);
-              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+            if (want_prev) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += prev[i][j];
             }
             sg_st4(op, make_float4(f[0], f[1], f[2], f[3]));
             sg_st4(op + 4, make_float4(f[4], f[5], f[6], f[7]));

@@ -65,6 +65,9 @@ def main():
         df = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", BF16, BF16, relu=1)
         dd = ops.desc_conv_dgrad(n, h, w, ci, co, k, k, "same", BF16, BF16)
         dwg = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", BF16, BF16)
+        dacc = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", BF16, F32, accumulate=1)      # shortcut: += into the fp32 stream
+        dmask = ops.desc_conv_dgrad(n, h, w, ci, co, k, k, "same", BF16, BF16, mask_dt=BF16)  # dgrad gated by the ReLU mask
+        out_acc = torch.zeros(n, h, w, co, device=rt.device)
         wf, wd = ops.pack_weights(rt, df, wm), ops.pack_weights(rt, dd, wm)
         bias = torch.zeros(co, device=rt.device)
 
@@ -73,6 +76,10 @@ def main():
                 ops.conv_run(rt, df, xs[i % nbuf], wm, wf, bias, None, out_f)
             elif role == "dgrad":
                 ops.conv_run(rt, dd, dys[i % nbuf], wm, wd, None, None, out_d)
+            elif role == "acc":
+                ops.conv_run(rt, dacc, xs[i % nbuf], wm, wf, None, None, out_acc)
+            elif role == "dmask":
+                ops.conv_run(rt, dmask, dys[i % nbuf], wm, wd, None, xs[(i + 1) % nbuf], out_d)
             else:
                 ops.conv_wgrad(rt, dwg, xs[i % nbuf], dys[i % nbuf], dw)
         for role in args.roles.split(","):
