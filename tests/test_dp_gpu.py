@@ -82,10 +82,17 @@ def _worker(rank, world, port, tmp):
         rt.world_size = world
         for i, (x, y) in enumerate(zip(stats_dp, stats_1)):
             assert abs(x - y) <= 1e-3 * max(abs(y), 0.1), "stat {}: dp {} vs single {}".format(i, x, y)
-        for n in ("G", "D", "R"):
+        # G's gradient runs through the gradient-balancing std over only 4 samples and 7 batch-norms: the fp32 oracle itself
+        # sits ~1e-3 from the fp64 one there (tests/test_models_gpu.py), and sharded vs single-pass summation order differs,
+        # hence 5e-3 for G and 1e-3 for D and R
+        errs = {}
+        for n, tol in (("G", 5e-3), ("D", 1e-3), ("R", 1e-3)):
             num = float(((grads_dp[n] - grads_1[n]) ** 2).sum()) ** 0.5
             den = float((grads_1[n] ** 2).sum()) ** 0.5
-            assert den > 0 and num / den <= 1e-3, "{} gradient bucket: rel L2 {}".format(n, num / den)
+            errs[n] = (num / max(den, 1e-30), tol, den)
+        print("DP-vs-single gradient bucket rel L2:", {k: "%.2e" % v[0] for k, v in errs.items()})
+        for n, (e, tol, den) in errs.items():
+            assert den > 0 and e <= tol, "{} gradient bucket: rel L2 {} > {}".format(n, e, tol)
         assert float((mov_dp - mov_1).abs().max()) <= 1e-5, "sync-BN moving statistics differ"
         open(os.path.join(tmp, "ok"), "w").write("ok")
     dist.barrier()
