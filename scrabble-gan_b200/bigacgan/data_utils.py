@@ -142,21 +142,29 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
                         _p(up_s_fake_w), _p(_up_s5), _p(up_d_fake_g), _p(up_s_fake_g), _p(up_r_fake_g), _p(stats))
 
     # ---- D, R, W gradients (data_utils.py:449-459) ----------------------------------------------------------------
+    # Data parallel: each network's flat gradient bucket is SUM-all-reduced (not averaged: SURVEY Q7) as soon as its
+    # filter gradients are complete, on NCCL's stream, overlapping with the backward passes that follow.
+    pending = []
     discriminator.trainable = True
     recognizer.trainable = True
     if fused:
         discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
+        pending.append(rt.allreduce_async_(discriminator.store.g))
         dfc = discriminator.slice_cache(dcc, 0, b)
         recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
+        pending.append(rt.allreduce_async_(recognizer.store.g))
         rfc = recognizer.slice_cache(rcc, 0, b)
     else:
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
+        pending.append(rt.allreduce_async_(discriminator.store.g))
         recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
+        pending.append(rt.allreduce_async_(recognizer.store.g))
     if use_w:
         style_promoter.trainable = True
         style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
         style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
+        pending.append(rt.allreduce_async_(style_promoter.store.g))
 
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
     update_g = (batch_idx + 1) % disc_iters == 0
@@ -172,13 +180,10 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
                 dimg_w = style_promoter.backward(rt, sfc, up_s_fake_g, wgrad=False, want_dx=True)
                 ops.axpby(rt, 1.0, dimg, 1.0, dimg_w, out=dimg)
         generator.backward(rt, g_cache, dimg)
-
-    # ---- data-parallel gradient exchange: SUM (not mean), one bucket per network ------------------------------------
-    if rt.world_size > 1:
-        for m in nets:
-            if m is generator and not update_g:
-                continue
-            rt.allreduce_(m.store.g)
+        pending.append(rt.allreduce_async_(generator.store.g))
+    for work in pending:
+        if work is not None:
+            work.wait()
 
     # ---- optimizer steps (same call shape as the reference) -------------------------------------------------------
     def _apply(opt, model):

@@ -89,6 +89,15 @@ class Runtime:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
         return t
 
+    def allreduce_async_(self, t: torch.Tensor):
+        """Start a SUM all-reduce of `t` on NCCL's own stream (ordered after everything already enqueued on the compute
+        stream) and return a handle; compute enqueued afterwards overlaps with the transfer.  `wait()` orders the compute
+        stream after the collective.  Returns None on a single replica."""
+        if self.world_size <= 1:
+            return None
+        import torch.distributed as dist
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+
 
 _default: Optional[Runtime] = None
 
