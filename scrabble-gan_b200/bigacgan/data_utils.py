@@ -132,7 +132,7 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     sums = torch.empty(SG_LOSS_NSUMS, device=rt.device, dtype=torch.float64)
     call.sg_loss_sums(rt.ctx, kind, int(use_w), _p(d_real), _p(d_fake), _p(s_real), _p(s_fake), _p(s_slot5), _p(r_fake),
                       _p(r_real), b, _p(sums))
-    rt.allreduce_(sums)
+    rt.allreduce_small_(sums)
     ups = rt.empty((8, b))
     stats = rt.empty((16,))
     # rows 0,1 = (up_d_fake_d, up_d_real): adjacent and in [fake ; real] order for the fused D backward

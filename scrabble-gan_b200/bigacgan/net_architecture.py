@@ -249,7 +249,7 @@ class Recognizer(_Model):
         ab = None
         if training:
             ab = ops.bn_bwd_combine(rt, s1, s2, bn.gamma.data, False)
-            rt.allreduce_(ab)
+            rt.allreduce_small_(ab)
         return ops.bn_bwd_apply(rt, dy, None, x, mean, rstd, bn.gamma.data, False, ab, count, training, True, out_dt)
 
     def forward(self, rt, x, labels, want_grad: bool = True):
@@ -406,7 +406,7 @@ class Generator(_Model):
         ab = None
         if training:
             ab = ops.bn_bwd_combine(rt, s1, s2, self.bn.gamma.data, False)
-            rt.allreduce_(ab)
+            rt.allreduce_small_(ab)
         d = ops.bn_bwd_apply(rt, dact, act, net, mean, rstd, self.bn.gamma.data, False, ab, count, training, False, SG_F32)
         dz = rt.zeros((n, self.latent_dim)) if want_dz else None
         for i in reversed(range(self.num_blocks)):

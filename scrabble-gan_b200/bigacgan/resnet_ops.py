@@ -50,7 +50,7 @@ class ConditionalBatchNorm:
         ab = None
         if training:
             ab = ops.bn_bwd_combine(rt, s1, s2, g, True)
-            rt.allreduce_(ab)                                           # sync-BN backward statistics
+            rt.allreduce_small_(ab)                                           # sync-BN backward statistics
         dx = ops.bn_bwd_apply(rt, dy, act, x, mean, rstd, g, True, ab, count, training, False, out_dt, out, int(accumulate))
         self.gamma.backward(rt, z, s2, n, ldx=z_stride, want_dx=False)
         self.beta.backward(rt, z, s1, n, ldx=z_stride, want_dx=False)

@@ -244,6 +244,26 @@ int sg_bn_stats(sg_ctx* ctx, const float* x, long long rows, int c, float* sums,
   return SG_OK;
 }
 
+/* stage 1 only (per-block partial sums into scratch, at most one block per SM): the second stage, the cross-replica
+ * exchange and the finalisation are fused in sg_bn_finalize_peer (peer.cu) */
+int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void* scratch, size_t scratch_bytes, int* nblocks_out) {
+  SG_REQUIRE(ctx && x && scratch && nblocks_out, "sg_bn_stats_partial: NULL");
+  SG_REQUIRE(c % 4 == 0 && c >= 4 && c <= 1024, "sg_bn_stats_partial: c=%d must be a multiple of 4 in [4,1024]", c);
+  SG_REQUIRE(rows > 0, "sg_bn_stats_partial: rows must be > 0");
+  BnLayout l = bn_layout(c);
+  long long blocks = ctx->num_sms;
+  long long min_rows = 4LL * l.lanes;
+  if (blocks > (rows + min_rows - 1) / min_rows) blocks = (rows + min_rows - 1) / min_rows;
+  long long rpb = (rows + blocks - 1) / blocks;
+  blocks = (rows + rpb - 1) / rpb;
+  SG_REQUIRE(scratch_bytes >= (size_t)blocks * 2 * c * sizeof(float), "sg_bn_stats_partial: scratch too small");
+  size_t smem = (size_t)l.lanes * 2 * c * sizeof(float);
+  k_bn_stats<<<(int)blocks, 256, smem, ctx->stream>>>(x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
+  SG_POST_LAUNCH(ctx);
+  *nblocks_out = (int)blocks;
+  return SG_OK;
+}
+
 int sg_bn_finalize(sg_ctx* ctx, const float* sums, double count, int c, float eps, float momentum, float* mean,
                    float* rstd, float* moving_mean, float* moving_var) {
   SG_REQUIRE(ctx && sums && mean && rstd && count > 0 && c > 0, "sg_bn_finalize: bad args");

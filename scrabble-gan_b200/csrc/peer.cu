@@ -1,0 +1,169 @@
+// One-shot SUM all-reduce of SMALL vectors over NVLink peer memory, fused into the kernels that produce / consume them.
+//
+// The data-parallel train step has two latency-bound exchange points: batch-norm raw sums
+// ([2C] floats, 7 layers forward + 7 backward) and the loss / gradient-balance sums (16 doubles).  A NCCL call costs
+// 25-40 us each there (launch + stream hand-shakes), ~15 times per step.  Here every rank owns one buffer in
+// symmetric memory (torch.distributed._symmetric_memory: same allocation on every GPU, peers mapped into this
+// process' address space, full NVLink 5 bandwidth to any peer through NVSwitch):
+//     [2 slots][SG_PEER_SLOT_BYTES]  payload, double buffered by the call sequence number
+//     [SG_PEER_MAX_WORLD] uint32     flags: flags[r] = last sequence number rank r has published to me
+// One launch: (1) write my payload into my slot, (2) system-scope release + store my sequence number into every
+// peer's flag word (a remote NVLink write), (3) spin until every peer's flag in MY buffer reached the sequence number,
+// (4) read all ranks' payloads (remote NVLink reads, .cv so a stale L1 line is never used) and sum them in RANK ORDER,
+// so every replica gets bit-identical results.  Double buffering is safe because a rank can only publish call s+1
+// after it finished reading in call s, and nobody overwrites slot (s & 1) before call s+2, which needs all flags of s+1.
+// A spin that never completes traps (a protocol bug must fault, not hang the GPU).
+//
+// k_bn_finalize_peer fuses that exchange between the second stage of the batch-norm statistics reduction and the
+// mean / rstd / moving-average finalisation: reduce partials -> exchange -> finalize in ONE launch.
+#include "common.cuh"
+
+#define SG_PEER_MAX_WORLD 16
+#define SG_PEER_SLOT_BYTES 16384
+
+struct PeerTable {
+  unsigned long long buf[SG_PEER_MAX_WORLD];     // peer buffer base addresses, as mapped in this process
+  int world, rank;
+  unsigned int seq;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int* peer_flags(unsigned long long base) {
+  return reinterpret_cast<unsigned int*>(base + 2ull * SG_PEER_SLOT_BYTES);
+}
+
+// steps (2) and (3); call with ALL threads of the block after the payload stores, returns with the peers' data visible
+__device__ __forceinline__ void peer_publish_and_wait(const PeerTable& pt) {
+  __threadfence_system();
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < pt.world && t != pt.rank) st_release_sys(peer_flags(pt.buf[t]) + pt.rank, pt.seq);
+  if (t < pt.world && t != pt.rank) {
+    const unsigned int* f = peer_flags(pt.buf[pt.rank]) + t;
+    unsigned int spins = 0;
+    while ((int)(ld_acquire_sys(f) - pt.seq) < 0) {
+      if (++spins > (1u << 26)) __trap();
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) k_peer_allreduce(T* __restrict__ data, int n, PeerTable pt) {
+  const size_t slot = (size_t)(pt.seq & 1u) * SG_PEER_SLOT_BYTES;
+  T* mine = reinterpret_cast<T*>(pt.buf[pt.rank] + slot);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = data[i];
+  peer_publish_and_wait(pt);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    T acc = 0;
+    for (int r = 0; r < pt.world; ++r) acc += __ldcv(reinterpret_cast<const T*>(pt.buf[r] + slot) + i);
+    data[i] = acc;
+  }
+}
+
+// second stage of the BN statistics (see bn.cu: partial[nblocks][2c]) + exchange + finalize, one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restrict__ partial, int nblocks, int c, double count_total,
+                                                            float eps, float momentum, float* __restrict__ sums_out,
+                                                            float* __restrict__ mean, float* __restrict__ rstd,
+                                                            float* __restrict__ mm, float* __restrict__ mv, PeerTable pt) {
+  __shared__ double red[1024];
+  const int c2 = 2 * c;
+  const size_t slot = (size_t)(pt.seq & 1u) * SG_PEER_SLOT_BYTES;
+  float* mine = reinterpret_cast<float*>(pt.buf[pt.rank] + slot);
+  // stage 2 of the statistics: 1024 threads = (c2p columns) x (slices of the per-block partials), double accumulation
+  int c2p = 32;
+  while (c2p < c2 && c2p < 1024) c2p <<= 1;
+  const int slices = 1024 / c2p;
+  for (int j0 = 0; j0 < c2; j0 += c2p) {
+    const int j = j0 + (threadIdx.x % c2p), sl = threadIdx.x / c2p;
+    double t = 0.0;
+    if (j < c2)
+      for (int b = sl; b < nblocks; b += slices) t += (double)partial[(long long)b * c2 + j];
+    __syncthreads();
+    red[threadIdx.x] = t;
+    __syncthreads();
+    if (sl == 0 && j < c2) {
+      for (int k = 1; k < slices; ++k) t += red[k * c2p + (threadIdx.x % c2p)];
+      mine[j] = (float)t;
+    }
+  }
+  if (pt.world > 1) peer_publish_and_wait(pt);
+  else __syncthreads();
+  for (int j = threadIdx.x; j < c; j += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    for (int r = 0; r < pt.world; ++r) {
+      const float* pr = reinterpret_cast<const float*>(pt.buf[r] + slot);
+      s += (double)__ldcv(pr + j);
+      ss += (double)__ldcv(pr + c + j);
+    }
+    if (sums_out) { sums_out[j] = (float)s; sums_out[c + j] = (float)ss; }
+    double m = s / count_total;
+    double var = ss / count_total - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[j] = (float)m;
+    rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+    if (mm) mm[j] = mm[j] * momentum + (float)m * (1.f - momentum);
+    if (mv) {
+      double unb = count_total > 1.0 ? var * (count_total / (count_total - 1.0)) : var;
+      mv[j] = mv[j] * momentum + (float)unb * (1.f - momentum);
+    }
+  }
+}
+
+static int make_table(PeerTable* pt, const unsigned long long* peer_bufs, int world, int rank, unsigned int seq, const char* who) {
+  SG_REQUIRE(peer_bufs && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "%s: bad peer table", who);
+  memset(pt, 0, sizeof(*pt));
+  for (int r = 0; r < world; ++r) {
+    SG_REQUIRE(peer_bufs[r] != 0 && (peer_bufs[r] & 15) == 0, "%s: peer buffer %d is NULL or misaligned", who, r);
+    pt->buf[r] = peer_bufs[r];
+  }
+  pt->world = world; pt->rank = rank; pt->seq = seq;
+  return SG_OK;
+}
+
+extern "C" {
+
+size_t sg_peer_buffer_bytes(void) { return 2 * (size_t)SG_PEER_SLOT_BYTES + SG_PEER_MAX_WORLD * sizeof(unsigned int) + 64; }
+size_t sg_peer_max_payload_bytes(void) { return SG_PEER_SLOT_BYTES; }
+
+int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsigned long long* peer_bufs, int world, int rank,
+                          unsigned int seq) {
+  SG_REQUIRE(ctx && data && n >= 0, "sg_peer_allreduce_sum: bad args");
+  SG_REQUIRE((size_t)n * (is_f64 ? 8 : 4) <= SG_PEER_SLOT_BYTES, "sg_peer_allreduce_sum: payload of %d elements exceeds the slot", n);
+  if (n == 0 || world <= 1) return SG_OK;
+  PeerTable pt;
+  int rc = make_table(&pt, peer_bufs, world, rank, seq, "sg_peer_allreduce_sum");
+  if (rc != SG_OK) return rc;
+  int threads = n >= 512 ? 512 : (n >= 256 ? 256 : 128);
+  if (threads < 32 * ((world + 31) / 32)) threads = 32 * ((world + 31) / 32);
+  if (is_f64) k_peer_allreduce<double><<<1, threads, 0, ctx->stream>>>((double*)data, n, pt);
+  else k_peer_allreduce<float><<<1, threads, 0, ctx->stream>>>((float*)data, n, pt);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* BN statistics, stage 2 + cross-replica exchange + finalize (replaces k_bn_stats_reduce, the NCCL all-reduce and
+ * k_bn_finalize).  `partial` / `nblocks` come from sg_bn_stats_partial.  count_total = rows summed over all replicas. */
+int sg_bn_finalize_peer(sg_ctx* ctx, const float* partial, int nblocks, int c, double count_total, float eps, float momentum,
+                        float* sums_out, float* mean, float* rstd, float* moving_mean, float* moving_var,
+                        const unsigned long long* peer_bufs, int world, int rank, unsigned int seq) {
+  SG_REQUIRE(ctx && partial && mean && rstd && nblocks >= 1 && c > 0, "sg_bn_finalize_peer: bad args");
+  SG_REQUIRE((size_t)c * 8 <= SG_PEER_SLOT_BYTES, "sg_bn_finalize_peer: c=%d exceeds the slot", c);
+  PeerTable pt;
+  int rc = make_table(&pt, peer_bufs, world, rank, seq, "sg_bn_finalize_peer");
+  if (rc != SG_OK) return rc;
+  k_bn_finalize_peer<<<1, 1024, 0, ctx->stream>>>(partial, nblocks, c, count_total, eps, momentum, sums_out, mean, rstd, moving_mean,
+                                                 moving_var, pt);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -32,6 +32,55 @@ def init_data_parallel(rt, backend: str = None) -> None:
     rt.world_size = dist.get_world_size()
     rt.rank = dist.get_rank()
     rt.process_group = None
+    if backend == "nccl" and os.environ.get("SGAN_NO_PEER", "0") != "1":
+        init_peer_exchange(rt)
+
+
+class PeerExchange:
+    """Symmetric-memory buffer + peer pointer table for the one-shot NVLink exchanges of libsgan (csrc/peer.cu)."""
+
+    def __init__(self, buf, handle, ptrs, world, rank):
+        import ctypes as C
+        self.buf, self.handle = buf, handle            # keep the allocation and the rendezvous handle alive
+        self.world, self.rank = world, rank
+        self.ptrs = (C.c_ulonglong * world)(*[int(p) for p in ptrs])
+        self.seq = 0
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+
+def init_peer_exchange(rt) -> bool:
+    """Allocate the small exchange buffer in symmetric memory (torch.distributed._symmetric_memory: plumbing only) and map
+    every peer's copy.  On any failure the runtime keeps using NCCL for the small exchanges (rt.peer stays None)."""
+    import sys
+    import torch.distributed as dist
+    from . import _abi
+    rt.peer = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        nbytes = int(_abi.load().sg_peer_buffer_bytes())
+        group = dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=rt.device)
+        hdl = symm_mem.rendezvous(buf, group.group_name)
+        buf.zero_()
+        torch.cuda.synchronize(rt.device)
+        dist.barrier()
+        ptrs = list(hdl.buffer_ptrs)
+        assert len(ptrs) == rt.world_size and all(int(p) != 0 for p in ptrs)
+        rt.peer = PeerExchange(buf, hdl, ptrs, rt.world_size, rt.rank)
+        return True
+    except Exception as ex:                         # noqa: BLE001 -- any failure means "use NCCL", never a wrong result
+        if rt.rank == 0:
+            print("scrabble-gan_b200: peer-memory exchange unavailable ({}); small all-reduces use NCCL".format(repr(ex)[:200]),
+                  file=sys.stderr)
+        rt.peer = None
+        return False
 
 
 def broadcast_parameters(rt, models) -> None:

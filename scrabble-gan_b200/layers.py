@@ -195,13 +195,18 @@ class BatchNormState:
 
 
 def batch_stats(rt: Runtime, x: torch.Tensor, bn: BatchNormState, update_moving: bool = True):
-    """Training-mode statistics over the GLOBAL batch: raw sums are all-reduced across replicas (sync-BN)."""
+    """Training-mode statistics over the GLOBAL batch (sync-BN).  With the NVLink peer-memory path up, the second stage
+    of the reduction, the cross-replica exchange and the finalisation are ONE launch (sg_bn_finalize_peer); otherwise the
+    raw sums are all-reduced with NCCL between sg_bn_stats and sg_bn_finalize."""
     c = x.shape[-1]
-    sums = ops.bn_stats(rt, x)
     count = x.numel() // c
+    mm = bn.moving_mean.data if update_moving else None
+    mv = bn.moving_var.data if update_moving else None
+    if rt.world_size > 1 and rt.peer is not None:
+        return ops.bn_stats_finalize_peer(rt, x, count * rt.world_size, c, mm, mv) + (count * rt.world_size,)
+    sums = ops.bn_stats(rt, x)
     if rt.world_size > 1:
         rt.allreduce_(sums)
         count *= rt.world_size
-    mean, rstd = ops.bn_finalize(rt, sums, count, c, bn.moving_mean.data if update_moving else None,
-                                 bn.moving_var.data if update_moving else None)
+    mean, rstd = ops.bn_finalize(rt, sums, count, c, mm, mv)
     return mean, rstd, count

@@ -281,6 +281,21 @@ def bn_stats(rt, x) -> torch.Tensor:
     return sums
 
 
+def bn_stats_finalize_peer(rt, x, count_total, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
+    """sync-BN statistics with the cross-replica exchange fused in (needs rt.peer): per-block partial sums, then ONE
+    launch doing stage-2 reduction + NVLink exchange + mean / rstd / moving averages."""
+    pe = rt.peer
+    rows = x.numel() // c
+    nbytes = rt.num_sms * 2 * c * 4
+    scratch = rt.scratch("bn_peer", nbytes)
+    nblocks = C.c_int(0)
+    call.sg_bn_stats_partial(rt.ctx, _p(x), rows, c, _p(scratch), nbytes, C.byref(nblocks))
+    mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
+    call.sg_bn_finalize_peer(rt.ctx, _p(scratch), nblocks.value, c, float(count_total), eps, momentum, _V(None), _p(mean), _p(rstd),
+                             _p(moving_mean), _p(moving_var), pe.ptrs, pe.world, pe.rank, pe.next_seq())
+    return mean, rstd
+
+
 def bn_finalize(rt, sums, count, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
     mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
     call.sg_bn_finalize(rt.ctx, _p(sums), float(count), c, eps, momentum, _p(mean), _p(rstd), _p(moving_mean), _p(moving_var))

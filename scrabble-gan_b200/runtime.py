@@ -43,6 +43,7 @@ class Runtime:
         self.world_size = 1
         self.rank = 0
         self.process_group = None
+        self.peer = None            # dp.PeerExchange when the NVLink peer-memory path is up
         self._scratch = {}
 
     # ---- precision mode -----------------------------------------------------------------------------
@@ -88,6 +89,24 @@ class Runtime:
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
         return t
+
+    def allreduce_small_(self, t: torch.Tensor) -> torch.Tensor:
+        """SUM all-reduce of a SMALL fp32 / fp64 vector (BN statistics, loss sums): one-shot exchange over NVLink peer
+        memory on the compute stream (csrc/peer.cu) when available, NCCL otherwise."""
+        if self.world_size <= 1:
+            return t
+        pe = self.peer
+        if pe is not None and t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and \
+                t.numel() * t.element_size() <= self._peer_max():
+            call.sg_peer_allreduce_sum(self.ctx, C.c_void_p(t.data_ptr()), t.numel(), int(t.dtype == torch.float64), pe.ptrs,
+                                       pe.world, pe.rank, pe.next_seq())
+            return t
+        return self.allreduce_(t)
+
+    def _peer_max(self) -> int:
+        if not hasattr(self, "_peer_max_bytes"):
+            self._peer_max_bytes = int(_abi.load().sg_peer_max_payload_bytes())
+        return self._peer_max_bytes
 
     def allreduce_async_(self, t: torch.Tensor):
         """Start a SUM all-reduce of `t` on NCCL's own stream (ordered after everything already enqueued on the compute

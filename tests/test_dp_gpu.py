@@ -105,3 +105,55 @@ def test_two_gpu_step_equals_single_gpu_big_batch(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "ok"))
+
+
+def _peer_worker(rank, world, port, tmp):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    runtime = importlib.import_module("scrabble-gan_b200.runtime")
+    dp = importlib.import_module("scrabble-gan_b200.dp")
+    ops = importlib.import_module("scrabble-gan_b200.ops")
+    rt = runtime.Runtime(device=rank, mode="fp32")
+    runtime.set_runtime(rt)
+    dp.init_data_parallel(rt)
+    import torch.distributed as dist
+    assert rt.peer is not None, "peer-memory exchange did not come up on a 2-GPU NVLink box"
+    g = torch.Generator().manual_seed(100 + rank)
+    for it, (n, dt) in enumerate([(1, torch.float32), (2048, torch.float32), (16, torch.float64), (4096, torch.float32), (130, torch.float32)] * 3):
+        x = torch.randn(n, generator=g, dtype=dt).to(rt.device)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        got = rt.allreduce_small_(x.clone())
+        torch.cuda.synchronize()
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6), (it, n, dt)
+        gathered = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gathered, got)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "replicas must hold bit-identical sums"
+    # fused sync-BN statistics == statistics of the concatenated batch
+    xs = [torch.randn(3, 8, 10, 64, generator=torch.Generator().manual_seed(7 + r)) * 2 + 0.5 for r in range(world)]
+    full = torch.cat(xs, 0).double()
+    mm, mv = torch.zeros(64, device=rt.device), torch.ones(64, device=rt.device)
+    mean, rstd = ops.bn_stats_finalize_peer(rt, xs[rank].to(rt.device).contiguous(), full.numel() // 64, 64, mm, mv)
+    torch.cuda.synchronize()
+    m_ref = full.mean((0, 1, 2))
+    v_ref = full.var((0, 1, 2), unbiased=False)
+    assert torch.allclose(mean.cpu().double(), m_ref, atol=1e-5)
+    assert torch.allclose(rstd.cpu().double(), torch.rsqrt(v_ref + 1e-3), rtol=1e-4)
+    cnt = full.numel() // 64
+    assert torch.allclose(mv.cpu().double(), 0.99 + 0.01 * v_ref * cnt / (cnt - 1), rtol=1e-5)
+    dist.barrier()
+    if rank == 0:
+        open(os.path.join(tmp, "ok_peer"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_peer_memory_small_allreduce_and_fused_sync_bn(tmp_path):
+    """csrc/peer.cu: one-shot NVLink peer-memory SUM all-reduce == NCCL, bit-identical on all replicas, and the fused
+    stage-2 + exchange + finalize sync-BN launch == statistics of the concatenated batch."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_peer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok_peer"))
