@@ -89,8 +89,7 @@ class ResNetBlockUp:
         n, hh, ww, _ = xshape
         dh_op = ops.cast(rt, dh, rt.op_dt)
         # main branch, back to front
-        self.conv.wgrad(rt, a2, dh_op)
-        ops.colsum_into(rt, dh_op, self.co, self.short.b.grad, accumulate=1)
+        self.conv.wgrad(rt, a2, dh_op, also_bias=self.short.b.grad)      # the shortcut bias sees the same upstream gradient
         da2 = self.conv.dgrad(rt, dh_op, (hh * self.stride[0], ww * self.stride[1]))
         du = self.cbn2.backward(rt, c2, da2, out_dt=rt.op_dt, dz_out=dz_out, dz_ld=dz_ld)
         self.up.wgrad(rt, a1, du)
@@ -137,12 +136,11 @@ class ResNetBlockDown:
         xr, xs, h1, (h, w) = cache
         dpre = ops.cast(rt, dout, rt.op_dt) if self.is_last else ops.avgpool2_bwd(rt, dout, rt.op_dt)
         if wgrad:
-            self.conv2.wgrad(rt, h1, dpre)
+            # the shortcut bias sees the same upstream gradient as conv2's bias: one column sum serves both
+            self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad)
             self.short.wgrad(rt, xs, dpre, bias_grad=False)
         dh1 = self.conv2.dgrad(rt, dpre, (h, w), mask=h1, out_dt=rt.op_dt)
         if wgrad:
-            # the shortcut bias sees the same upstream gradient as conv2's bias
-            ops.colsum_into(rt, dpre, self.co, self.short.b.grad, accumulate=1)
             self.conv1.wgrad(rt, xr, dh1)
         if not want_dx:
             return None

@@ -62,10 +62,13 @@ def init_peer_exchange(rt) -> bool:
         import torch.distributed._symmetric_memory as symm_mem
         nbytes = int(_abi.load().sg_peer_buffer_bytes())
         group = dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:                                   # required by older torch releases, a deprecated no-op in newer ones
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
         buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=rt.device)
         hdl = symm_mem.rendezvous(buf, group.group_name)
         buf.zero_()

@@ -80,12 +80,20 @@ class ConvLayer:
         ops.conv_run(rt, d, dy, self.w.data, self._pack(rt, "dgrad", d), None, mask, out)
         return out
 
-    def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True) -> None:
+    def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True, also_bias=None) -> None:
+        """Filter (+ bias) gradient.  `also_bias`: a second bias gradient [co] that sees the same upstream gradient (the
+        shortcut of a ResNet block): dy is column-summed ONCE and the sum is added to both."""
         n, h, w, _ = x.shape
         d = self._desc("fwd", n, h, w, dt_of(x), dt_of(dy))
         ops.conv_wgrad(rt, d, x, dy, self.w.grad)
         if bias_grad and self.b is not None:
-            ops.colsum_into(rt, dy, self.co, self.b.grad, accumulate=1)
+            if also_bias is None:
+                ops.colsum_into(rt, dy, self.co, self.b.grad, accumulate=1)
+            else:
+                s = rt.empty((self.co,), SG_F32)
+                ops.colsum_into(rt, dy, self.co, s, accumulate=0)
+                ops.axpby(rt, 1.0, s, 1.0, self.b.grad, out=self.b.grad)
+                ops.axpby(rt, 1.0, s, 1.0, also_bias, out=also_bias)
 
 
 class ConvTransposeLayer:
