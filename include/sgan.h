@@ -81,6 +81,11 @@ size_t sg_conv_packed_weight_elems(const sg_conv_desc* d);     /* c_out * ntaps 
 int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_master, void* w_packed);
 int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
                    const float* bias, const void* mask, void* out);
+/* the same launch reading the filter IN PLACE from a bf16 mirror of the master weights (identical indexing): no packing
+ * pass.  HWIO forward convs use the mirror as an N-major B operand, dgrads / transposed-conv phases as a K-major one. */
+int sg_conv_tc_direct_supported(const sg_conv_desc* d);
+int sg_conv_fwd_tc_direct(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_mirror_bf16,
+                          const float* bias, const void* mask, void* out);
 size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms);
 int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master,
                      void* workspace, size_t workspace_bytes);
@@ -236,6 +241,9 @@ int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b
 /* ---- optimizers (K19) -- main.py:25-35: Keras Adam / RMSprop --------------------------------------- */
 int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t,
             float beta1, float beta2, float eps);
+/* Adam that also refreshes the bf16 mirror of the weights in the same pass */
+int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n,
+                   float lr_t, float beta1, float beta2, float eps);
 int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps);
 
 /* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */

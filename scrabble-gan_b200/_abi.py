@@ -58,6 +58,8 @@ _PROTOS = {
     "sg_conv_packed_weight_elems": (_Z, [_DP]),
     "sg_conv_pack_weights": (_I, [_P, _DP, _P, _P]),
     "sg_conv_fwd_tc": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
+    "sg_conv_tc_direct_supported": (_I, [_DP]),
+    "sg_conv_fwd_tc_direct": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_wgrad_tc_workspace": (_Z, [_DP, _I]),
     "sg_conv_wgrad_tc": (_I, [_P, _DP, _P, _P, _P, _P, _Z]),
     "sg_act_prep": (_I, [_P, _P, _L, _P, _P, _I]),
@@ -107,6 +109,7 @@ _PROTOS = {
     "sg_loss_terms": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "sg_grad_balance": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "sg_adam": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
+    "sg_adam_mirror": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_rmsprop": (_I, [_P, _P, _P, _P, _L, _F, _F, _F]),
     "sg_spectral_norm": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
 }

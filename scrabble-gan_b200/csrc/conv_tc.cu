@@ -61,6 +61,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -147,6 +153,8 @@ struct alignas(64) TcFwdParams {
   CUtensorMap map_a[4];
   CUtensorMap map_b;
   int tap_view[SG_MAX_TAPS], tap_oy[SG_MAX_TAPS], tap_ox[SG_MAX_TAPS];
+  int tap_wt[SG_MAX_TAPS];      // direct-weight modes: index of tap t in the master filter (3rd TMA coordinate)
+  int b_mode;                   // 0 = packed K-major matrix (2-D map); 1 = master read in place, K-major; 2 = in place, N-major
   int ntaps, c_in, c_out, n, grid_h, grid_w;
   int out_h, out_w, out_sy, out_sx, out_py, out_px;
   int TW, TH, TN, tiles_x, tiles_y, tiles_n, tiles_col, BN;
@@ -219,7 +227,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
             tma_load_4d(a_base + s * p.a_stage_stride, ma, bar_full + 8 * s, c * KC, cx, cy, n0);
-            tma_load_2d(b_base + s * p.b_stage_stride, &p.map_b, bar_full + 8 * s, t * p.c_in + c * KC, col0);
+            const uint32_t bdst = b_base + s * p.b_stage_stride;
+            if (p.b_mode == 0) {
+              tma_load_2d(bdst, &p.map_b, bar_full + 8 * s, t * p.c_in + c * KC, col0);
+            } else if (p.b_mode == 1) {          // master [tap][c_out][c_in]: the same [BN rows][KC] K-major tile, read in place
+              tma_load_3d(bdst, &p.map_b, bar_full + 8 * s, c * KC, col0, p.tap_wt[t]);
+            } else {                             // master [tap][c_in][c_out]: N-major chunks of [KC rows][64 columns]
+              for (int j = 0; j < p.BN / 64; ++j)
+                tma_load_3d(bdst + j * (KC * 128), &p.map_b, bar_full + 8 * s, col0 + 64 * j, c * KC, p.tap_wt[t]);
+            }
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -227,7 +243,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(kTf32, false, false, 128, p.BN);
+    const bool b_mn = p.b_mode == 2;
+    const uint32_t idesc = make_idesc(kTf32, false, b_mn, 128, p.BN);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -239,10 +256,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         tc_fence_after();
         if (lane == 0) {
           uint64_t da = make_smem_desc(a_base + s * p.a_stage_stride, 16, 1024);
-          uint64_t db = make_smem_desc(b_base + s * p.b_stage_stride, 16, 1024);
+          // K-major B: 32 bytes of K per step inside the 128-byte swizzle row.  N-major B (weights read in place):
+          // LBO = distance between the 64-column chunks, a K step of 16 rows = 16 x 128 bytes.
+          uint64_t db = b_mn ? make_smem_desc(b_base + s * p.b_stage_stride, KC * 128, 1024)
+                             : make_smem_desc(b_base + s * p.b_stage_stride, 16, 1024);
+          const uint64_t bstep = b_mn ? (uint64_t)((16 * 128) >> 4) : 2ull;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)      // 4 x 32 bytes of K per 128-byte swizzle row
-            umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)      // 4 x 32 bytes of K per 128-byte swizzle row of A
+            umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + bstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);
           if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
         }
@@ -771,8 +792,35 @@ int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_mast
   return SG_OK;
 }
 
-int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
-                   const void* mask, void* out) {
+static int encode_3d(PFN_encodeTiled enc, CUtensorMap* m, const void* base, long long d0, long long d1, long long d2, long long s1,
+                     long long s2, int b0, int b1) {
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};          // bf16
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sg_set_error("cuTensorMapEncodeTiled(3d) failed: %d (dims %lld,%lld,%lld strides %lld,%lld box %d,%d)", (int)r, d0, d1, d2, s1, s2, b0, b1);
+    return SG_ERR_CUDA;
+  }
+  return SG_OK;
+}
+
+// 0 = not possible; 1 = master is K-major for this role (w_ci_stride == 1); 2 = N-major (w_co_stride == 1)
+static int direct_mode(const sg_conv_desc* d) {
+  if (!d || d->in_dt != SG_BF16) return 0;
+  if (d->c_in % 64 || d->c_out % 32) return 0;
+  const long long ts = (long long)d->c_in * d->c_out;
+  for (int t = 0; t < d->ntaps; ++t)
+    if (d->tap_w_off[t] < 0 || d->tap_w_off[t] % ts) return 0;
+  if (d->w_ci_stride == 1 && d->w_co_stride == d->c_in) return 1;
+  if (d->w_co_stride == 1 && d->w_ci_stride == d->c_out && d->c_out % 64 == 0) return 2;
+  return 0;
+}
+
+static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, int b_mode, const float* bias,
+                            const void* mask, void* out) {
   SG_REQUIRE(ctx && in && w_packed && out, "sg_conv_fwd_tc: NULL");
   int rc = tc_check(d, "sg_conv_fwd_tc");
   if (rc != SG_OK) return rc;
@@ -807,6 +855,7 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
     p.BN = 32;
     for (int i = 0; i < 4; ++i) {
       if (d->c_out % cand[i]) continue;
+      if (b_mode == 2 && cand[i] < 64) continue;
       long long tiles = m_tiles * (d->c_out / cand[i]);
       double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * rel[i];
       if (best < 0 || cost < best * 0.97) { best = cost; p.BN = cand[i]; }
@@ -843,7 +892,19 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
   }
   for (int v = 0; v < 4; ++v)
     if (!used[v]) p.map_a[v] = p.map_a[first_used];
-  rc = encode_2d(enc, &p.map_b, d->in_dt, w_packed, (long long)d->ntaps * d->c_in, d->c_out, KC, p.BN);
+  p.b_mode = b_mode;
+  if (b_mode == 0) {
+    rc = encode_2d(enc, &p.map_b, d->in_dt, w_packed, (long long)d->ntaps * d->c_in, d->c_out, KC, p.BN);
+  } else {
+    const long long ts = (long long)d->c_in * d->c_out;
+    long long tmax = 0;
+    for (int t = 0; t < d->ntaps; ++t) {
+      p.tap_wt[t] = (int)(d->tap_w_off[t] / ts);
+      if (p.tap_wt[t] > tmax) tmax = p.tap_wt[t];
+    }
+    if (b_mode == 1) rc = encode_3d(enc, &p.map_b, w_packed, d->c_in, d->c_out, tmax + 1, d->w_co_stride, ts, KC, p.BN);
+    else rc = encode_3d(enc, &p.map_b, w_packed, d->c_out, d->c_in, tmax + 1, d->w_ci_stride, ts, 64, KC);
+  }
   if (rc != SG_OK) return rc;
 
   long long total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
@@ -858,6 +919,22 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
+}
+
+int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
+                   const void* mask, void* out) {
+  return conv_fwd_tc_impl(ctx, d, in, w_packed, 0, bias, mask, out);
+}
+
+int sg_conv_tc_direct_supported(const sg_conv_desc* d) { return sg_conv_tc_supported(d) && direct_mode(d) != 0; }
+
+/* same launch reading the filter IN PLACE from a bf16 mirror of the master weights (same indexing as w_master): no
+ * packing pass.  Forward convs (HWIO) use it as an N-major B operand, dgrads / transposed convs as a K-major one. */
+int sg_conv_fwd_tc_direct(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_mirror_bf16, const float* bias,
+                          const void* mask, void* out) {
+  int mode = direct_mode(d);
+  SG_REQUIRE(mode != 0, "sg_conv_fwd_tc_direct: this descriptor cannot read the master filter in place");
+  return conv_fwd_tc_impl(ctx, d, in, w_mirror_bf16, mode, bias, mask, out);
 }
 
 size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms) {

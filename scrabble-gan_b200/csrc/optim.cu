@@ -7,8 +7,9 @@
 // HBM-bound: 4 reads + 3 writes per parameter, float4-vectorised.
 #include "common.cuh"
 
+// wb (optional): bf16 mirror of w, written in the same pass -- the tensor-core convs read their filters from it in place
 __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       long long n4, long long n, float lr_t, float b1, float b2, float eps) {
+                       long long n4, long long n, float lr_t, float b1, float b2, float eps, __nv_bfloat16* __restrict__ wb) {
   long long stride = (long long)gridDim.x * blockDim.x;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -19,12 +20,15 @@ __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float
     ww.x -= lr_t * mw.x / (sqrtf(vw.x) + eps); ww.y -= lr_t * mw.y / (sqrtf(vw.y) + eps);
     ww.z -= lr_t * mw.z / (sqrtf(vw.z) + eps); ww.w -= lr_t * mw.w / (sqrtf(vw.w) + eps);
     sg_st4(m + 4 * i, mw); sg_st4(v + 4 * i, vw); sg_st4(w + 4 * i, ww);
+    if (wb) sg_st4(wb + 4 * i, ww);
   }
   for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float gi = g[i];
     float mi = b1 * m[i] + c1 * gi, vi = b2 * v[i] + c2 * gi * gi;
     m[i] = mi; v[i] = vi;
-    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    float wi = w[i] - lr_t * mi / (sqrtf(vi) + eps);
+    w[i] = wi;
+    if (wb) wb[i] = __float2bfloat16_rn(wi);
   }
 }
 
@@ -91,15 +95,27 @@ __global__ void k_sn_scale(const float* __restrict__ w, long long n, const float
 
 extern "C" {
 
-int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-            float eps) {
+static int adam_impl(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* wb, long long n, float lr_t, float beta1,
+                     float beta2, float eps) {
   SG_REQUIRE(ctx && w && g && m && v && n >= 0, "sg_adam: bad args");
   if (n == 0) return SG_OK;
-  long long n4 = (((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 ? n / 4 : 0;
+  long long n4 = (((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)wb) & 15) == 0 ? n / 4 : 0;
   long long need = (n / 4 + 256) / 256, cap = (long long)ctx->num_sms * 8;
-  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps);
+  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps, (__nv_bfloat16*)wb);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
+}
+
+int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+            float eps) {
+  return adam_impl(ctx, w, g, m, v, nullptr, n, lr_t, beta1, beta2, eps);
+}
+
+/* Adam that also refreshes the bf16 mirror of the weights in the same pass (see sg_conv_fwd_tc_direct) */
+int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n, float lr_t,
+                   float beta1, float beta2, float eps) {
+  SG_REQUIRE(w_mirror_bf16 != nullptr, "sg_adam_mirror: NULL mirror");
+  return adam_impl(ctx, w, g, m, v, w_mirror_bf16, n, lr_t, beta1, beta2, eps);
 }
 
 int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps) {

@@ -66,7 +66,10 @@ class ConvLayer:
             ho, wo = self.out_hw(h, w)
             out = rt.empty((n, ho, wo, self.co), out_dt)
         b = (self.b.data if self.b is not None else None) if isinstance(bias, str) else bias
-        ops.conv_run(rt, d, x, self.w.data, self._pack(rt, "fwd", d), b, None, out)
+        if ops.direct_ok(rt, d):
+            ops.conv_run(rt, d, x, self.w.data, None, b, None, out, w_mirror=self.w.mirror(rt))
+        else:
+            ops.conv_run(rt, d, x, self.w.data, self._pack(rt, "fwd", d), b, None, out)
         return out
 
     def dgrad(self, rt: Runtime, dy: torch.Tensor, in_hw: Tuple[int, int], mask=None, out_dt: int = SG_F32, out=None,
@@ -77,7 +80,10 @@ class ConvLayer:
         d = self._desc("dgrad", n, h, w, dt_of(dy), odt, 0, int(accumulate), dt_of(mask) if mask is not None else SG_F32)
         if out is None:
             out = rt.empty((n, h, w, self.ci), out_dt)
-        ops.conv_run(rt, d, dy, self.w.data, self._pack(rt, "dgrad", d), None, mask, out)
+        if ops.direct_ok(rt, d):
+            ops.conv_run(rt, d, dy, self.w.data, None, None, mask, out, w_mirror=self.w.mirror(rt))
+        else:
+            ops.conv_run(rt, d, dy, self.w.data, self._pack(rt, "dgrad", d), None, mask, out)
         return out
 
     def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True, also_bias=None) -> None:
@@ -138,7 +144,10 @@ class ConvTransposeLayer:
                 d = ops.desc_convT_phase(n, h, w, self.ci, self.co, self.k, self.sy, self.sx, py, px, dt_of(x), SG_F32, 0,
                                          int(accumulate))
                 self._descs[key] = d
-            ops.conv_run(rt, d, x, self.w.data, self._pack(rt, ("ph", py, px), d), b, None, out)
+            if ops.direct_ok(rt, d):
+                ops.conv_run(rt, d, x, self.w.data, None, b, None, out, w_mirror=self.w.mirror(rt))
+            else:
+                ops.conv_run(rt, d, x, self.w.data, self._pack(rt, ("ph", py, px), d), b, None, out)
         return out
 
     def _dgrad_desc(self, n, h, w, in_dt, out_dt, accumulate, mask_dt=SG_F32):
@@ -156,7 +165,10 @@ class ConvTransposeLayer:
         d = self._dgrad_desc(n, h, w, dt_of(dout), odt, int(accumulate))
         if out is None:
             out = rt.empty((n, h, w, self.ci), out_dt)
-        ops.conv_run(rt, d, dout, self.w.data, self._pack(rt, "dg", d), None, None, out)
+        if ops.direct_ok(rt, d):
+            ops.conv_run(rt, d, dout, self.w.data, None, None, None, out, w_mirror=self.w.mirror(rt))
+        else:
+            ops.conv_run(rt, d, dout, self.w.data, self._pack(rt, "dg", d), None, None, out)
         return out
 
     def wgrad(self, rt: Runtime, x: torch.Tensor, dout: torch.Tensor, bias_grad: bool = True) -> None:

@@ -143,9 +143,17 @@ def pack_weights(rt: Runtime, d: ConvDesc, w_master: torch.Tensor, out: Optional
     return out
 
 
-def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out) -> None:
-    """Launch the conv described by d on the tensor-core path when possible, else the fp32 direct path."""
-    if w_packed is not None and tc_ok(rt, d):
+def direct_ok(rt: Runtime, d: ConvDesc) -> bool:
+    """True when the tensor-core launch can read the filter in place from the store's bf16 mirror (no packing pass)."""
+    return bool(rt.use_direct and rt.mode == "bf16" and _abi.load().sg_conv_tc_direct_supported(C.byref(d)))
+
+
+def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w_mirror=None) -> None:
+    """Launch the conv described by d on the tensor-core path when possible, else the fp32 direct path.  `w_mirror`:
+    bf16 mirror of w_master (same layout) for the pack-free tensor-core launch."""
+    if w_mirror is not None:
+        call.sg_conv_fwd_tc_direct(rt.ctx, C.byref(d), _p(x), _p(w_mirror), _p(bias), _p(mask), _p(out))
+    elif w_packed is not None and tc_ok(rt, d):
         call.sg_conv_fwd_tc(rt.ctx, C.byref(d), _p(x), _p(w_packed), _p(bias), _p(mask), _p(out))
     else:
         call.sg_conv_fwd_simt(rt.ctx, C.byref(d), _p(x), _p(w_master), _p(bias), _p(mask), _p(out))
@@ -449,8 +457,11 @@ def ctc(rt, logits, labels, want_grad=True):
     return loss, grad
 
 
-def adam_(rt, w, g, m, v, lr_t, beta1, beta2, eps):
-    call.sg_adam(rt.ctx, _p(w), _p(g), _p(m), _p(v), w.numel(), lr_t, beta1, beta2, eps)
+def adam_(rt, w, g, m, v, lr_t, beta1, beta2, eps, mirror=None):
+    if mirror is not None:
+        call.sg_adam_mirror(rt.ctx, _p(w), _p(g), _p(m), _p(v), _p(mirror), w.numel(), lr_t, beta1, beta2, eps)
+    else:
+        call.sg_adam(rt.ctx, _p(w), _p(g), _p(m), _p(v), w.numel(), lr_t, beta1, beta2, eps)
 
 
 def rmsprop_(rt, w, g, ms, lr, rho, eps):

@@ -50,8 +50,12 @@ class Adam:
         st = self._slots(store)
         tv = store.trainable_variables
         fused = len(pairs) == len(tv) and all(v is tv[i] and g.data_ptr() == v.grad.data_ptr() for i, (g, v) in enumerate(pairs))
+        mirror_fresh = False
         if fused:
-            ops.adam_(rt, store.w, store.g, st.slots[0], st.slots[1], lr_t, self.beta_1, self.beta_2, self.epsilon)
+            # keep the bf16 mirror (pack-free tensor-core convs) current in the same pass when it exists and is in sync
+            mirror = store.wb if (store.wb is not None and store.wb_version == store.version) else None
+            ops.adam_(rt, store.w, store.g, st.slots[0], st.slots[1], lr_t, self.beta_1, self.beta_2, self.epsilon, mirror)
+            mirror_fresh = mirror is not None
         else:
             for g, v in pairs:
                 assert v.store is store, "one optimizer serves one network"
@@ -60,6 +64,8 @@ class Adam:
                 gg = gg.to(device=rt.device, dtype=torch.float32).reshape(-1).contiguous()
                 ops.adam_(rt, store.w[sl], gg, st.slots[0][sl], st.slots[1][sl], lr_t, self.beta_1, self.beta_2, self.epsilon)
         store.version += 1
+        if mirror_fresh:
+            store.wb_version = store.version
 
     def state_dict(self):
         return {"iterations": self.iterations, "slots": {k: [s.clone() for s in v.slots] for k, v in self._state.items()}}

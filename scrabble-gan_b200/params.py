@@ -39,6 +39,11 @@ class Variable:
         assert self.trainable
         return self.store.g[self.offset:self.offset + self.numel].view(self.shape)
 
+    def mirror(self, rt) -> torch.Tensor:
+        """bf16 mirror of this variable (view into the store's mirror buffer, refreshed lazily)."""
+        assert self.trainable
+        return self.store.mirror(rt)[self.offset:self.offset + self.numel].view(self.shape)
+
     def numpy(self):
         return self.data.detach().cpu().numpy()
 
@@ -101,6 +106,8 @@ class ParamStore:
         self.g: Optional[torch.Tensor] = None      # gradients          (flat fp32)
         self.s: Optional[torch.Tensor] = None      # non-trainable state (BN moving statistics)
         self.version = 0                           # bumped whenever values change (packed-weight caches key on it)
+        self.wb: Optional[torch.Tensor] = None     # bf16 mirror of w (same offsets), kept current by the optimizer kernel
+        self.wb_version = -1
         self.n_trainable = 0
 
     def add(self, name: str, shape, init: Callable = init_zeros, trainable: bool = True) -> Variable:
@@ -130,6 +137,18 @@ class ParamStore:
             for v in self.vars:
                 v.data.copy_(v.init(v.shape, dev, gen))
         self.version += 1
+
+    def mirror(self, rt) -> torch.Tensor:
+        """The bf16 mirror of the flat weight buffer.  The fused Adam launch writes it together with the fp32 weights;
+        after any other change (initialisation, weight load, assign, per-variable updates) it is re-cast here."""
+        if self.wb is None:
+            self.wb = torch.empty_like(self.w, dtype=torch.bfloat16)
+        if self.wb_version != self.version:
+            from . import ops
+            from ._abi import SG_BF16
+            ops.call.sg_cast(rt.ctx, ops._p(self.w), ops._p(self.wb), SG_BF16, self.w.numel())
+            self.wb_version = self.version
+        return self.wb
 
     @property
     def trainable_variables(self) -> List[Variable]:

@@ -54,6 +54,8 @@ class Runtime:
         self.use_tc = mode in ("bf16", "tf32")
         self.op_dt = SG_BF16 if mode == "bf16" else SG_F32
         self.op_torch = torch.bfloat16 if mode == "bf16" else torch.float32
+        # bf16 mode: tensor-core convs read their filters in place from a bf16 mirror of the flat parameter buffer
+        self.use_direct = os.environ.get("SGAN_NO_DIRECT", "0") != "1"
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
     def empty(self, shape, dt: int = SG_F32) -> torch.Tensor:

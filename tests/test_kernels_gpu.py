@@ -163,6 +163,24 @@ def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
         dwg = ops.desc_conv_fwd(n, h, w, ci, co, k, k, padding, in_dt=dt, out_dt=dt)
         ops.conv_wgrad(rt, dwg, xd, dyd, dw)
         check(dw, wt.grad, 2e-3, "tc wgrad")
+
+        if mode == "bf16":
+            # pack-free launches: the filter is read in place from a bf16 mirror of the HWIO master (N-major B operand for
+            # the forward conv, K-major for the dgrad)
+            wm = wd.to(torch.bfloat16)
+            if ops.direct_ok(rt, d):
+                out4 = rt.empty(y.shape)
+                ops.conv_run(rt, d, xd, wd, None, dev(rt, b), None, out4, w_mirror=wm)
+                check(out4, y, 2e-3, "tc fwd (direct weights)")
+                out5 = rt.empty(y.shape, dt)
+                ops.conv_run(rt, d2, xd, wd, None, dev(rt, b), dev(rt, m, dt), out5, w_mirror=wm)
+                check(out5, torch.relu(y) * (m > 0), 1e-2, "tc fwd epilogue (direct weights)")
+            else:
+                assert co % 64 != 0, "HWIO forward convs with c_out % 64 == 0 must support the direct path"
+            assert ops.direct_ok(rt, dd)
+            dx2 = rt.empty(x.shape)
+            ops.conv_run(rt, dd, dyd, wd, None, None, None, dx2, w_mirror=wm)
+            check(dx2, x.grad, 2e-3, "tc dgrad (direct weights)")
     finally:
         rt.set_mode("fp32")
 
@@ -212,6 +230,19 @@ def test_conv_transpose(rt, case, mode):
         dwg = ops.desc_convT_dgrad(n, h, w, ci, co, k, sy, sx, in_dt=dt, out_dt=dt)
         ops.conv_wgrad(rt, dwg, dyd, xd, dw)
         check(dw, wt.grad, tol, "convT wgrad")
+
+        if mode == "bf16":       # pack-free launches on the (kh,kw,Cout,Cin) master: phases K-major, dgrad N-major
+            wm = wd.to(torch.bfloat16)
+            out2 = dev(rt, (b.view(1, 1, 1, co)).expand(n, h * sy, w * sx, co).clone())
+            for (py, px) in ops.convT_phases(k, sy, sx):
+                d = ops.desc_convT_phase(n, h, w, ci, co, k, sy, sx, py, px, in_dt=dt, accumulate=1)
+                assert ops.direct_ok(rt, d)
+                ops.conv_run(rt, d, xd, wd, None, None, None, out2, w_mirror=wm)
+            check(out2, y, tol, "convT fwd (direct weights)")
+            if ops.direct_ok(rt, dd):
+                dx2 = rt.empty(x.shape)
+                ops.conv_run(rt, dd, dyd, wd, None, None, None, dx2, w_mirror=wm)
+                check(dx2, x.grad, tol, "convT dgrad (direct weights)")
     finally:
         rt.set_mode("fp32")
 
