@@ -244,6 +244,11 @@ int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long
 /* Adam that also refreshes the bf16 mirror of the weights in the same pass */
 int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n,
                    float lr_t, float beta1, float beta2, float eps);
+/* device-resident step size (CUDA-graph replay of the update): sg_adam_prepare sets (t >= 0) or advances (t < 0) the
+ * device step counter and writes lr_t = lr sqrt(1-b2^t)/(1-b1^t); sg_adam_dev reads lr_t from lr_dev (mirror may be NULL) */
+int sg_adam_prepare(sg_ctx* ctx, int* step_dev, float* lr_dev, int t, float lr, float beta1, float beta2);
+int sg_adam_dev(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n,
+                const float* lr_dev, float beta1, float beta2, float eps);
 int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps);
 
 /* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */

@@ -110,6 +110,8 @@ _PROTOS = {
     "sg_grad_balance": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "sg_adam": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_adam_mirror": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
+    "sg_adam_prepare": (_I, [_P, _P, _P, _I, _F, _F, _F]),
+    "sg_adam_dev": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _F, _F, _F]),
     "sg_rmsprop": (_I, [_P, _P, _P, _P, _L, _F, _F, _F]),
     "sg_spectral_norm": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
 }

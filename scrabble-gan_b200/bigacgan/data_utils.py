@@ -56,6 +56,35 @@ def _loss_kind(loss_fn) -> int:
     return kind
 
 
+# ----------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the step
+# ----------------------------------------------------------------------------------------------------
+# A step is ~390 kernel launches issued from Python through ctypes.  Once a (models, shapes, mode) signature has been
+# seen GRAPH_WARMUP times, the device part of the step (everything between the input copies and the 16 statistics) is
+# captured ONCE into a CUDA graph -- torch is used only as the capture / allocator plumbing -- and later calls replay it:
+# inputs are copied into static device buffers, the Adam step sizes travel through pinned host scalars that captured
+# memcpy nodes re-read on every replay, and the result is the same `stats` tensor.  Set SGAN_CUDA_GRAPH=0 to disable.
+GRAPH_ENABLED = os.environ.get("SGAN_CUDA_GRAPH", "1") != "0"
+GRAPH_WARMUP = 2
+_graph_cache = {}
+
+
+class _GraphedStep:
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.static = None          # (x_real, y_real, y_fake, g_in) static device buffers
+        self.stats = None
+        self.versions = None
+        self.failed = False
+        self.launches = 0           # libsgan kernel nodes in the graph
+
+
+def _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, balance, update_g):
+    return (id(generator), id(discriminator), id(recognizer), tuple(id(o) for o in opts), b, l_r, l_f, rt.mode, kind, bool(balance),
+            bool(update_g), bool(recognizer.trainable), os.environ.get("SGAN_NO_FUSED_BATCH", "0"))
+
+
 def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discriminator, recognizer, style_promoter, composite_gan,
                generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer, my_imgs, batch_size,
                latent_dim, loss_fn, disc_iters, apply_gradient_balance, random_words, bucket_size, gen_path, *,
@@ -75,33 +104,138 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     if fake_labels is None:
         random_bucket_idx = random.randint(0, bucket_size - 1)
         fake_labels = np.array([random.choice(random_words[random_bucket_idx]) for _ in range(batch_size)], np.int32)
+    b, l_r = int(np.shape(labels)[0]), int(np.shape(labels)[1])
+    l_f = int(np.shape(fake_labels)[1])
+    update_g = (batch_idx + 1) % disc_iters == 0
+    opts = (generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer)
+    args = (discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g)
+
+    # ---- CUDA-graph path (G+D+R mode on one replica) ---------------------------------------------------------------
+    graphable = (GRAPH_ENABLED and not use_w and generator.style is None and rt.world_size == 1 and
+                 all(type(o).__name__ == "Adam" for o in opts[:3]))
+    if graphable:
+        key = _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, apply_gradient_balance, update_g)
+        gs = _graph_cache.get(key)
+        if gs is None:
+            gs = _graph_cache[key] = _GraphedStep()
+        gs.calls += 1
+        if gs.graph is None and not gs.failed and gs.calls > GRAPH_WARMUP:
+            _capture(rt, gs, args, b, l_r, l_f, latent_dim)
+        if gs.graph is not None:
+            stats = _replay(rt, gs, args, images, labels, fake_labels, noise)
+            return _finish(stats, return_device_stats, verbose, epoch_idx, batch_idx, batch_per_epoch)
+
     y_real = to_device_i32(rt, labels)
     y_fake = to_device_i32(rt, fake_labels)
-    b = y_real.shape[0]
-    l_r, l_f = y_real.shape[1], y_fake.shape[1]
-    # R's BatchNorm mode follows the Keras `trainable` flag at forward time
-    recognizer.bn_training = bool(recognizer.trainable)
-    # When the real and the fake words have the same length, D and R see both batches in ONE pass over a
-    # [fake ; real] batch of 2B images (they have no cross-sample coupling: no batch-stat BN), which doubles the
-    # GEMM M of every layer; G writes its tanh output straight into the first half, the H2D copy of the real
-    # images lands in the second half.
-    fused = (l_r == l_f) and not recognizer.bn_training and os.environ.get("SGAN_NO_FUSED_BATCH", "0") != "1"
-    if fused:
-        xcat = rt.empty((2 * b, 32, 16 * l_r, 1))
-        src = _as_tensor(images, np.float32)
-        xcat[b:].copy_(src.reshape(b, 32, 16 * l_r, 1), non_blocking=True)
-        x_real = xcat[b:]
-        ycat = torch.empty((2 * b, l_r), device=rt.device, dtype=torch.int32)
-        ycat[:b].copy_(y_fake)
-        ycat[b:].copy_(y_real)
-    else:
-        x_real = _nhwc(to_device_f32(rt, images))
+    x_real = _nhwc(to_device_f32(rt, images)).reshape(b, 32, 16 * l_r, 1)
+    style_imgs = None
     if generator.style is not None or use_w:
         style_imgs = _nhwc(to_device_f32(rt, my_imgs))
     if generator.style is not None:
         g_in = style_imgs
     else:
         g_in = to_device_f32(rt, noise) if noise is not None else torch.randn(batch_size, latent_dim, device=rt.device)
+    stats = _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs)
+    return _finish(stats, return_device_stats, verbose, epoch_idx, batch_idx, batch_per_epoch)
+
+
+def _finish(stats, return_device_stats, verbose, epoch_idx, batch_idx, batch_per_epoch):
+    if return_device_stats:
+        return stats
+    host = stats.cpu().tolist()          # the reference's 16 .numpy() calls: one D2H copy + sync here
+    if verbose:
+        print('>%d, %d/%d, d=%.3f, d_real=%.3f, d_fake=%.3f, g_trad=%.3f, r_loss_fake=%.3f, g_loss=%.3f, r=%.3f, s=%.3f' % (
+            epoch_idx + 1, batch_idx + 1, batch_per_epoch, host[6], host[7], host[8], host[3], host[0], host[9], host[1], host[14]))
+    return tuple(host)
+
+
+def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
+    """Capture the device part of the step for this signature.  Kernels do not run during capture; Python-side state the
+    body advances (optimizer iteration counters, store versions) is rolled back afterwards and advanced by _replay."""
+    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g = args
+    stores = [discriminator.store, recognizer.store, generator.store]
+    try:
+        for st in stores:
+            if rt.mode == "bf16" and rt.use_direct:
+                st.mirror(rt)                                   # fresh mirrors: no cast gets captured
+        static = (rt.empty((b, 32, 16 * l_r, 1)), torch.zeros((b, l_r), device=rt.device, dtype=torch.int32),
+                  torch.zeros((b, l_f), device=rt.device, dtype=torch.int32), rt.empty((b, latent_dim)))
+        for t in static:
+            t.zero_()
+        saved = [(o.iterations if o is not None else 0) for o in opts]
+        versions = [(st.version, st.wb_version) for st in stores]
+        torch.cuda.synchronize(rt.device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=rt.device)
+        n0 = rt.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            rt.use_current_stream()
+            stats = _step_device(rt, args, static[0], static[1], static[2], static[3], None)
+        rt.use_current_stream()
+        gs.launches = rt.launch_count() - n0
+        rt.replayed_launches -= gs.launches                     # captured, not executed
+        for o, it in zip(opts, saved):
+            if o is not None:
+                o.iterations = it
+        # the captured Adam launches keep the mirrors current: versions only matter for changes made OUTSIDE the graph
+        for st, (v, wbv) in zip(stores, versions):
+            st.version = v
+            st.wb_version = wbv
+        gs.graph, gs.static, gs.stats = graph, static, stats
+        gs.versions = [st.version for st in stores]
+    except Exception as ex:      # noqa: BLE001 -- capture is an optimisation: on any failure stay on the eager path
+        import sys
+        rt.use_current_stream()
+        gs.failed = True
+        gs.graph = None
+        print("scrabble-gan_b200: CUDA-graph capture of train_step failed ({}); staying eager".format(repr(ex)[:300]), file=sys.stderr)
+
+
+def _replay(rt, gs, args, images, labels, fake_labels, noise):
+    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g = args
+    stores = [discriminator.store, recognizer.store, generator.store]
+    for i, st in enumerate(stores):
+        if st.version != gs.versions[i]:                        # weights changed outside the graph (load / assign)
+            if rt.mode == "bf16" and rt.use_direct:
+                st.mirror(rt)
+            gs.versions[i] = st.version
+    x_s, yr_s, yf_s, z_s = gs.static
+    x_s.copy_(_as_tensor(images, np.float32).reshape(x_s.shape), non_blocking=True)
+    yr_s.copy_(_as_tensor(labels, np.int32), non_blocking=True)
+    yf_s.copy_(_as_tensor(fake_labels, np.int32), non_blocking=True)
+    if noise is not None:
+        z_s.copy_(_as_tensor(noise, np.float32), non_blocking=True)
+    else:
+        z_s.normal_()
+    used = [opts[1], opts[2]] + ([opts[0]] if update_g else [])
+    for o in used:
+        o.advance_for_replay()
+    gs.graph.replay()
+    rt.replayed_launches += gs.launches
+    return gs.stats
+
+
+def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
+    """The device part of the step: every argument is a device tensor; returns the 16 statistics as a device tensor."""
+    discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g = args
+    generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer = opts
+    use_w = style_promoter is not None
+    b = y_real.shape[0]
+    l_r, l_f = y_real.shape[1], y_fake.shape[1]
+    # R's BatchNorm mode follows the Keras `trainable` flag at forward time (SURVEY Q5)
+    recognizer.bn_training = bool(recognizer.trainable)
+    # When the real and the fake words have the same length, D and R see both batches in ONE pass over a
+    # [fake ; real] batch of 2B images (they have no cross-sample coupling: no batch-stat BN), which doubles the
+    # GEMM M of every layer; G writes its tanh output straight into the first half, the real images are copied into
+    # the second half.
+    fused = (l_r == l_f) and not recognizer.bn_training and os.environ.get("SGAN_NO_FUSED_BATCH", "0") != "1"
+    if fused:
+        xcat = rt.empty((2 * b, 32, 16 * l_r, 1))
+        xcat[b:].copy_(x_real, non_blocking=True)
+        x_real = xcat[b:]
+        ycat = torch.empty((2 * b, l_r), device=rt.device, dtype=torch.int32)
+        ycat[:b].copy_(y_fake)
+        ycat[b:].copy_(y_real)
     assert g_in.shape[0] == b == y_fake.shape[0], "real and fake batches must have the same size (net_loss.py:49)"
 
     nets = [discriminator, recognizer, generator] + ([style_promoter] if use_w else [])
@@ -167,7 +301,6 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
         pending.append(rt.allreduce_async_(style_promoter.store.g))
 
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
-    update_g = (batch_idx + 1) % disc_iters == 0
     if update_g:
         recognizer.trainable = False
         discriminator.trainable = False
@@ -197,13 +330,7 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     if update_g:
         _apply(generator_optimizer, generator)
 
-    if return_device_stats:
-        return stats
-    host = stats.cpu().tolist()          # the reference's 16 .numpy() calls: one D2H copy + sync here
-    if verbose:
-        print('>%d, %d/%d, d=%.3f, d_real=%.3f, d_fake=%.3f, g_trad=%.3f, r_loss_fake=%.3f, g_loss=%.3f, r=%.3f, s=%.3f' % (
-            epoch_idx + 1, batch_idx + 1, batch_per_epoch, host[6], host[7], host[8], host[3], host[0], host[9], host[1], host[14]))
-    return tuple(host)
+    return stats
 
 
 def generate_and_save_images(model, epoch, test_input, gen_path, char_vector):

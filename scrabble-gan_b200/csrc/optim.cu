@@ -9,7 +9,9 @@
 
 // wb (optional): bf16 mirror of w, written in the same pass -- the tensor-core convs read their filters from it in place
 __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       long long n4, long long n, float lr_t, float b1, float b2, float eps, __nv_bfloat16* __restrict__ wb) {
+                       long long n4, long long n, float lr_t, float b1, float b2, float eps, __nv_bfloat16* __restrict__ wb,
+                       const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;          // step size from device memory (CUDA-graph replays: see k_adam_prepare)
   long long stride = (long long)gridDim.x * blockDim.x;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -29,6 +31,17 @@ __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float
     float wi = w[i] - lr_t * mi / (sqrtf(vi) + eps);
     w[i] = wi;
     if (wb) wb[i] = __float2bfloat16_rn(wi);
+  }
+}
+
+// Device-side step counter and Keras step size  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t):  t_set >= 0 sets the counter (eager
+// calls pass the host iteration count), t_set < 0 increments it (captured launches: every graph replay advances by one).
+__global__ void k_adam_prepare(int* __restrict__ step, float* __restrict__ lr_dev, int t_set, float lr, float b1, float b2) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int t = t_set >= 0 ? t_set : *step + 1;
+    *step = t;
+    double c1 = 1.0 - pow((double)b1, (double)t), c2 = 1.0 - pow((double)b2, (double)t);
+    *lr_dev = (float)((double)lr * sqrt(c2) / c1);
   }
 }
 
@@ -96,12 +109,12 @@ __global__ void k_sn_scale(const float* __restrict__ w, long long n, const float
 extern "C" {
 
 static int adam_impl(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* wb, long long n, float lr_t, float beta1,
-                     float beta2, float eps) {
+                     float beta2, float eps, const float* lr_dev = nullptr) {
   SG_REQUIRE(ctx && w && g && m && v && n >= 0, "sg_adam: bad args");
   if (n == 0) return SG_OK;
   long long n4 = (((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)wb) & 15) == 0 ? n / 4 : 0;
   long long need = (n / 4 + 256) / 256, cap = (long long)ctx->num_sms * 8;
-  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps, (__nv_bfloat16*)wb);
+  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps, (__nv_bfloat16*)wb, lr_dev);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -116,6 +129,21 @@ int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, vo
                    float beta1, float beta2, float eps) {
   SG_REQUIRE(w_mirror_bf16 != nullptr, "sg_adam_mirror: NULL mirror");
   return adam_impl(ctx, w, g, m, v, w_mirror_bf16, n, lr_t, beta1, beta2, eps);
+}
+
+/* step size kept on the device so that the update can be replayed from a CUDA graph: sg_adam_prepare sets (t >= 0) or
+ * advances (t < 0) the device step counter and writes lr_t; sg_adam_dev is sg_adam[_mirror] reading lr_t from lr_dev */
+int sg_adam_prepare(sg_ctx* ctx, int* step_dev, float* lr_dev, int t, float lr, float beta1, float beta2) {
+  SG_REQUIRE(ctx && step_dev && lr_dev, "sg_adam_prepare: NULL");
+  k_adam_prepare<<<1, 32, 0, ctx->stream>>>(step_dev, lr_dev, t, lr, beta1, beta2);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_adam_dev(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n, const float* lr_dev,
+                float beta1, float beta2, float eps) {
+  SG_REQUIRE(lr_dev != nullptr, "sg_adam_dev: NULL lr_dev");
+  return adam_impl(ctx, w, g, m, v, w_mirror_bf16, n, 0.f, beta1, beta2, eps, lr_dev);
 }
 
 int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps) {

@@ -28,6 +28,12 @@ class Adam:
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
         self.iterations = 0
         self._state: Dict[int, _FlatState] = {}
+        self._dev = None            # (step counter int32[1], lr_t float32[1]) on the device: graph-replayable updates
+
+    def advance_for_replay(self) -> None:
+        """Host-side bookkeeping for one CUDA-graph replay of a captured apply_gradients (the device counter advances
+        itself inside the graph)."""
+        self.iterations += 1
 
     def _lr_t(self) -> float:
         t = self.iterations
@@ -54,7 +60,13 @@ class Adam:
         if fused:
             # keep the bf16 mirror (pack-free tensor-core convs) current in the same pass when it exists and is in sync
             mirror = store.wb if (store.wb is not None and store.wb_version == store.version) else None
-            ops.adam_(rt, store.w, store.g, st.slots[0], st.slots[1], lr_t, self.beta_1, self.beta_2, self.epsilon, mirror)
+            if self._dev is None:
+                self._dev = (torch.zeros(1, device=rt.device, dtype=torch.int32), torch.zeros(1, device=rt.device))
+            capturing = torch.cuda.is_current_stream_capturing()
+            ops.call.sg_adam_prepare(rt.ctx, ops._p(self._dev[0]), ops._p(self._dev[1]), -1 if capturing else self.iterations,
+                                     self.learning_rate, self.beta_1, self.beta_2)
+            ops.call.sg_adam_dev(rt.ctx, ops._p(store.w), ops._p(store.g), ops._p(st.slots[0]), ops._p(st.slots[1]), ops._p(mirror),
+                                 store.w.numel(), ops._p(self._dev[1]), self.beta_1, self.beta_2, self.epsilon)
             mirror_fresh = mirror is not None
         else:
             for g, v in pairs:

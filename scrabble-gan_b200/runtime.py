@@ -44,6 +44,7 @@ class Runtime:
         self.rank = 0
         self.process_group = None
         self.peer = None            # dp.PeerExchange when the NVLink peer-memory path is up
+        self.replayed_launches = 0  # kernels executed through CUDA-graph replays (they bypass the C ABI's launch counter)
         self._scratch = {}
 
     # ---- precision mode -----------------------------------------------------------------------------
@@ -79,7 +80,8 @@ class Runtime:
         call.sg_ctx_sync(self.ctx)
 
     def launch_count(self) -> int:
-        return int(_abi.load().sg_ctx_launch_count(self.ctx))
+        """libsgan kernels launched so far: direct launches through the C ABI plus the kernel nodes of replayed graphs."""
+        return int(_abi.load().sg_ctx_launch_count(self.ctx)) + self.replayed_launches
 
     def use_current_stream(self) -> None:
         self.stream = torch.cuda.current_stream(self.device)

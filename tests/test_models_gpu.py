@@ -282,3 +282,56 @@ def test_public_loss_functions(rt):
     egb, erb, _, ers, egs = O.apply_gradient_balancing(v[0] + 30, v[1])
     assert rel(gb, egb) <= 1e-4 and rel(rb, erb) <= 1e-4
     assert abs(float(rs) - float(ers)) <= 1e-4 * float(ers) and abs(float(gs) - float(egs)) <= 1e-4 * float(egs)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_train_step_cuda_graph_matches_eager(rt, mode):
+    """CUDA-graph replay of train_step (captured on the 3rd call of a signature) == the eager step: 6 steps from identical
+    initial weights, identical inputs; statistics and weights must agree up to atomic-add ordering noise."""
+    rt.set_mode(mode)
+    try:
+        b, l = 2, 2
+        rng = np.random.RandomState(5)
+        batches = [(rng.uniform(-1, 1, size=(b, 32, 16 * l, 1)).astype(np.float32), rng.randint(0, 52, size=(b, l)).astype(np.int32),
+                    rng.randint(0, 52, size=(b, l)).astype(np.int32), rng.standard_normal(size=(b, 128)).astype(np.float32))
+                   for _ in range(6)]
+
+        def run(graph):
+            old = du.GRAPH_ENABLED
+            du.GRAPH_ENABLED = graph
+            try:
+                G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=31)
+                D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt, seed=32)
+                R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt, seed=33)
+                for m in (G, D):
+                    for v in m.store.vars:
+                        if v.name.endswith(".sigma"):
+                            v.assign(np.array([0.1], np.float32))
+                gan = na.make_gan(G, D, R, None, vis_model=False)
+                g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+                outs = []
+                for i, (imgs, labels, fake, z) in enumerate(batches):
+                    outs.append(du.train_step(0, i, 6, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn,
+                                              disc_iters, agb, None, 10, "", fake_labels=fake, noise=z))
+                captured = any(gs.graph is not None for gs in du._graph_cache.values())
+                return np.array(outs), {n: m.store.w.detach().cpu().double() for n, m in (("G", G), ("D", D), ("R", R))}, \
+                    (g_opt.iterations, d_opt.iterations, r_opt.iterations), captured
+            finally:
+                du.GRAPH_ENABLED = old
+
+        du._graph_cache.clear()
+        stats_e, w_e, it_e, cap_e = run(False)
+        assert not cap_e
+        stats_g, w_g, it_g, cap_g = run(True)
+        assert cap_g, "the 3rd call of a signature must have captured a CUDA graph"
+        assert it_e == it_g == (6, 6, 6)
+        tol = 2e-2 if mode == "bf16" else 2e-3
+        assert np.all(np.isfinite(stats_g))
+        assert np.allclose(stats_g, stats_e, rtol=tol, atol=tol), np.abs(stats_g - stats_e).max()
+        for n in w_e:
+            # 6 Adam steps of size ~lr: a sign flip of a near-zero gradient moves a weight by 2 lr; compare the bulk
+            diff = (w_g[n] - w_e[n]).abs()
+            assert float((diff > 3 * 2e-4).double().mean()) <= 0.02, n
+    finally:
+        du._graph_cache.clear()
+        rt.set_mode("fp32")
