@@ -339,7 +339,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": "ScrabbleGAN G+D+R train step, hinge + gradient balancing, Adam x3, fixed %d-char words (32x%d), "
                                        "batch %d per GPU" % (L, 16 * L, B), "batch_per_gpu": B, "global_batch": B * world, "word_len": L,
-                           "parallelism": "dp%d" % world, "cuda_graph": bool(graph_default and world == 1),
+                           "parallelism": "dp%d" % world, "cuda_graph": bool(graph_default and (world == 1 or du.GRAPH_DP)),
                            "l2": "no explicit flush: the per-step working set (>1 GB of activations, 0.7 GB weights+optimizer state) "
                                  "exceeds the 126 MB L2 and input batches rotate"},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -149,21 +149,21 @@ int sg_bn_bwd_apply(sg_ctx* ctx, const float* dy, const void* act, int act_dt, c
 
 /* ---- small cross-replica exchanges over NVLink peer memory (data-parallel sync-BN / loss sums) -------------------
  * peer_bufs[r] = base address of rank r's exchange buffer (sg_peer_buffer_bytes() bytes of SYMMETRIC memory, zeroed
- * once before the first call) as mapped in THIS process; seq = 1, 2, 3, ... identical on every rank (all ranks issue the
- * same call sequence).  One launch: publish -> flag peers -> wait -> sum in rank order (bit-identical on all ranks).
+ * once before the first call) as mapped in THIS process.  All ranks must issue the same sequence of exchange calls; the
+ * call sequence number lives in the buffer itself (device resident), so the launches can be replayed from a CUDA graph.
+ * One launch: publish -> flag peers -> wait -> sum in rank order (bit-identical on all ranks).
  * Replaces a NCCL all-reduce of <= sg_peer_max_payload_bytes() bytes. */
 size_t sg_peer_buffer_bytes(void);
 size_t sg_peer_max_payload_bytes(void);
 int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsigned long long* peer_bufs, int world,
-                          int rank, unsigned int seq);
+                          int rank);
 /* sync-BN forward statistics in one launch after the per-block partial sums: stage-2 reduction + exchange + mean /
  * rstd / moving-average finalisation (FusedBatchNormV3 training statistics, resnet_ops.py:14-17) */
 int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void* scratch, size_t scratch_bytes,
                         int* nblocks_out);
 int sg_bn_finalize_peer(sg_ctx* ctx, const float* partial, int nblocks, int c, double count_total, float eps,
                         float momentum, float* sums_out, float* mean, float* rstd, float* moving_mean,
-                        float* moving_var, const unsigned long long* peer_bufs, int world, int rank,
-                        unsigned int seq);
+                        float* moving_var, const unsigned long long* peer_bufs, int world, int rank);
 
 /* ---- small dense GEMM (K14): C (+)= op(A) op(B) + bias;  row-major, fp32 -------------------------- */
 int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, const float* a, int lda,

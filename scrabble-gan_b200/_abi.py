@@ -88,9 +88,9 @@ _PROTOS = {
     "sg_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _I, _L, _I, _P, _P, _P, _L, _P, _D, _I, _I, _P, _I, _I]),
     "sg_peer_buffer_bytes": (_Z, []),
     "sg_peer_max_payload_bytes": (_Z, []),
-    "sg_peer_allreduce_sum": (_I, [_P, _P, _I, _I, C.POINTER(C.c_ulonglong), _I, _I, C.c_uint]),
+    "sg_peer_allreduce_sum": (_I, [_P, _P, _I, _I, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_bn_stats_partial": (_I, [_P, _P, _L, _I, _P, _Z, C.POINTER(_I)]),
-    "sg_bn_finalize_peer": (_I, [_P, _P, _I, _I, _D, _F, _F, _P, _P, _P, _P, _P, C.POINTER(C.c_ulonglong), _I, _I, C.c_uint]),
+    "sg_bn_finalize_peer": (_I, [_P, _P, _I, _I, _D, _F, _F, _P, _P, _P, _P, _P, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_gemm": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I]),
     "sg_filterbank_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
     "sg_filterbank_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I]),

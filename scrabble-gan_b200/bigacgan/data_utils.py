@@ -65,6 +65,7 @@ def _loss_kind(loss_fn) -> int:
 # inputs are copied into static device buffers, the Adam step sizes travel through pinned host scalars that captured
 # memcpy nodes re-read on every replay, and the result is the same `stats` tensor.  Set SGAN_CUDA_GRAPH=0 to disable.
 GRAPH_ENABLED = os.environ.get("SGAN_CUDA_GRAPH", "1") != "0"
+GRAPH_DP = os.environ.get("SGAN_CUDA_GRAPH_DP", "1") != "0"      # capture the data-parallel step too (NCCL + peer exchanges)
 GRAPH_WARMUP = 2
 _graph_cache = {}
 
@@ -111,7 +112,7 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     args = (discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g)
 
     # ---- CUDA-graph path (G+D+R mode on one replica) ---------------------------------------------------------------
-    graphable = (GRAPH_ENABLED and not use_w and generator.style is None and rt.world_size == 1 and
+    graphable = (GRAPH_ENABLED and not use_w and generator.style is None and (rt.world_size == 1 or GRAPH_DP) and
                  all(type(o).__name__ == "Adam" for o in opts[:3]))
     if graphable:
         key = _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, apply_gradient_balance, update_g)

@@ -7,6 +7,8 @@
 // process' address space, full NVLink 5 bandwidth to any peer through NVSwitch):
 //     [2 slots][SG_PEER_SLOT_BYTES]  payload, double buffered by the call sequence number
 //     [SG_PEER_MAX_WORLD] uint32     flags: flags[r] = last sequence number rank r has published to me
+//     uint32                         my call sequence counter (device resident, so that the exchange can sit inside a
+//                                    replayed CUDA graph: every launch reads it, uses counter + 1 and stores it back)
 // One launch: (1) write my payload into my slot, (2) system-scope release + store my sequence number into every
 // peer's flag word (a remote NVLink write), (3) spin until every peer's flag in MY buffer reached the sequence number,
 // (4) read all ranks' payloads (remote NVLink reads, .cv so a stale L1 line is never used) and sum them in RANK ORDER,
@@ -24,7 +26,7 @@
 struct PeerTable {
   unsigned long long buf[SG_PEER_MAX_WORLD];     // peer buffer base addresses, as mapped in this process
   int world, rank;
-  unsigned int seq;
+  unsigned int seq;                              // filled in on the device from the counter in my buffer
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -37,6 +39,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 }
 __device__ __forceinline__ unsigned int* peer_flags(unsigned long long base) {
   return reinterpret_cast<unsigned int*>(base + 2ull * SG_PEER_SLOT_BYTES);
+}
+
+__device__ __forceinline__ unsigned int* peer_counter(unsigned long long base) { return peer_flags(base) + SG_PEER_MAX_WORLD; }
+// every thread reads the same value: the counter is only written at the very end of the previous launch on this stream
+__device__ __forceinline__ unsigned int peer_next_seq(const PeerTable& pt) { return *peer_counter(pt.buf[pt.rank]) + 1u; }
+__device__ __forceinline__ void peer_commit_seq(const PeerTable& pt) {
+  __syncthreads();
+  if (threadIdx.x == 0) *peer_counter(pt.buf[pt.rank]) = pt.seq;
 }
 
 // steps (2) and (3); call with ALL threads of the block after the payload stores, returns with the peers' data visible
@@ -58,6 +68,7 @@ __device__ __forceinline__ void peer_publish_and_wait(const PeerTable& pt) {
 
 template <typename T>
 __global__ void __launch_bounds__(512) k_peer_allreduce(T* __restrict__ data, int n, PeerTable pt) {
+  pt.seq = peer_next_seq(pt);
   const size_t slot = (size_t)(pt.seq & 1u) * SG_PEER_SLOT_BYTES;
   T* mine = reinterpret_cast<T*>(pt.buf[pt.rank] + slot);
   for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = data[i];
@@ -67,6 +78,7 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(T* __restrict__ data, in
     for (int r = 0; r < pt.world; ++r) acc += __ldcv(reinterpret_cast<const T*>(pt.buf[r] + slot) + i);
     data[i] = acc;
   }
+  peer_commit_seq(pt);
 }
 
 // second stage of the BN statistics (see bn.cu: partial[nblocks][2c]) + exchange + finalize, one block of 1024 threads
@@ -75,6 +87,7 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restri
                                                             float* __restrict__ mean, float* __restrict__ rstd,
                                                             float* __restrict__ mm, float* __restrict__ mv, PeerTable pt) {
   __shared__ double red[1024];
+  pt.seq = peer_next_seq(pt);
   const int c2 = 2 * c;
   const size_t slot = (size_t)(pt.seq & 1u) * SG_PEER_SLOT_BYTES;
   float* mine = reinterpret_cast<float*>(pt.buf[pt.rank] + slot);
@@ -116,31 +129,31 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restri
       mv[j] = mv[j] * momentum + (float)unb * (1.f - momentum);
     }
   }
+  peer_commit_seq(pt);
 }
 
-static int make_table(PeerTable* pt, const unsigned long long* peer_bufs, int world, int rank, unsigned int seq, const char* who) {
+static int make_table(PeerTable* pt, const unsigned long long* peer_bufs, int world, int rank, const char* who) {
   SG_REQUIRE(peer_bufs && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "%s: bad peer table", who);
   memset(pt, 0, sizeof(*pt));
   for (int r = 0; r < world; ++r) {
     SG_REQUIRE(peer_bufs[r] != 0 && (peer_bufs[r] & 15) == 0, "%s: peer buffer %d is NULL or misaligned", who, r);
     pt->buf[r] = peer_bufs[r];
   }
-  pt->world = world; pt->rank = rank; pt->seq = seq;
+  pt->world = world; pt->rank = rank; pt->seq = 0;
   return SG_OK;
 }
 
 extern "C" {
 
-size_t sg_peer_buffer_bytes(void) { return 2 * (size_t)SG_PEER_SLOT_BYTES + SG_PEER_MAX_WORLD * sizeof(unsigned int) + 64; }
+size_t sg_peer_buffer_bytes(void) { return 2 * (size_t)SG_PEER_SLOT_BYTES + (SG_PEER_MAX_WORLD + 1) * sizeof(unsigned int) + 60; }
 size_t sg_peer_max_payload_bytes(void) { return SG_PEER_SLOT_BYTES; }
 
-int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsigned long long* peer_bufs, int world, int rank,
-                          unsigned int seq) {
+int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsigned long long* peer_bufs, int world, int rank) {
   SG_REQUIRE(ctx && data && n >= 0, "sg_peer_allreduce_sum: bad args");
   SG_REQUIRE((size_t)n * (is_f64 ? 8 : 4) <= SG_PEER_SLOT_BYTES, "sg_peer_allreduce_sum: payload of %d elements exceeds the slot", n);
   if (n == 0 || world <= 1) return SG_OK;
   PeerTable pt;
-  int rc = make_table(&pt, peer_bufs, world, rank, seq, "sg_peer_allreduce_sum");
+  int rc = make_table(&pt, peer_bufs, world, rank, "sg_peer_allreduce_sum");
   if (rc != SG_OK) return rc;
   int threads = n >= 512 ? 512 : (n >= 256 ? 256 : 128);
   if (threads < 32 * ((world + 31) / 32)) threads = 32 * ((world + 31) / 32);
@@ -154,11 +167,11 @@ int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsi
  * k_bn_finalize).  `partial` / `nblocks` come from sg_bn_stats_partial.  count_total = rows summed over all replicas. */
 int sg_bn_finalize_peer(sg_ctx* ctx, const float* partial, int nblocks, int c, double count_total, float eps, float momentum,
                         float* sums_out, float* mean, float* rstd, float* moving_mean, float* moving_var,
-                        const unsigned long long* peer_bufs, int world, int rank, unsigned int seq) {
+                        const unsigned long long* peer_bufs, int world, int rank) {
   SG_REQUIRE(ctx && partial && mean && rstd && nblocks >= 1 && c > 0, "sg_bn_finalize_peer: bad args");
   SG_REQUIRE((size_t)c * 8 <= SG_PEER_SLOT_BYTES, "sg_bn_finalize_peer: c=%d exceeds the slot", c);
   PeerTable pt;
-  int rc = make_table(&pt, peer_bufs, world, rank, seq, "sg_bn_finalize_peer");
+  int rc = make_table(&pt, peer_bufs, world, rank, "sg_bn_finalize_peer");
   if (rc != SG_OK) return rc;
   k_bn_finalize_peer<<<1, 1024, 0, ctx->stream>>>(partial, nblocks, c, count_total, eps, momentum, sums_out, mean, rstd, moving_mean,
                                                  moving_var, pt);

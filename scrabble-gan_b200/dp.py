@@ -44,11 +44,6 @@ class PeerExchange:
         self.buf, self.handle = buf, handle            # keep the allocation and the rendezvous handle alive
         self.world, self.rank = world, rank
         self.ptrs = (C.c_ulonglong * world)(*[int(p) for p in ptrs])
-        self.seq = 0
-
-    def next_seq(self) -> int:
-        self.seq += 1
-        return self.seq
 
 
 def init_peer_exchange(rt) -> bool:

@@ -300,7 +300,7 @@ def bn_stats_finalize_peer(rt, x, count_total, c, moving_mean=None, moving_var=N
     call.sg_bn_stats_partial(rt.ctx, _p(x), rows, c, _p(scratch), nbytes, C.byref(nblocks))
     mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
     call.sg_bn_finalize_peer(rt.ctx, _p(scratch), nblocks.value, c, float(count_total), eps, momentum, _V(None), _p(mean), _p(rstd),
-                             _p(moving_mean), _p(moving_var), pe.ptrs, pe.world, pe.rank, pe.next_seq())
+                             _p(moving_mean), _p(moving_var), pe.ptrs, pe.world, pe.rank)
     return mean, rstd
 
 

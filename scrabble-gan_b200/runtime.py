@@ -103,7 +103,7 @@ class Runtime:
         if pe is not None and t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and \
                 t.numel() * t.element_size() <= self._peer_max():
             call.sg_peer_allreduce_sum(self.ctx, C.c_void_p(t.data_ptr()), t.numel(), int(t.dtype == torch.float64), pe.ptrs,
-                                       pe.world, pe.rank, pe.next_seq())
+                                       pe.world, pe.rank)
             return t
         return self.allreduce_(t)
 
