@@ -355,9 +355,14 @@ def main():
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: captured CUDA graphs hold NCCL work, and destroying the process group under them can block for
+        # minutes.  Everything is printed and synchronised at this point, so leave through os._exit after a last barrier.
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
