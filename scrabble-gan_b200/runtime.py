@@ -119,6 +119,9 @@ class Runtime:
         if self.world_size <= 1:
             return None
         import torch.distributed as dist
+        if os.environ.get("SGAN_DP_SYNC_ALLREDUCE", "0") == "1":      # diagnostic: no overlap with the backward passes
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+            return None
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
 
 
