@@ -3,7 +3,7 @@
 # writes the details page (text) and the raw page (csv) to gpurun_out/ncu_<tag>.{txt,csv}; the report stays in /tmp.
 PATTERN="$1"; COUNT="${2:-20}"; TAG="${3:-sel}"
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profile-range"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profile-range --no-graph"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$PATTERN" -c "$COUNT" \
     -f -o /tmp/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1
