@@ -143,9 +143,14 @@ def pack_weights(rt: Runtime, d: ConvDesc, w_master: torch.Tensor, out: Optional
     return out
 
 
-def direct_ok(rt: Runtime, d: ConvDesc) -> bool:
-    """True when the tensor-core launch can read the filter in place from the store's bf16 mirror (no packing pass)."""
-    return bool(rt.use_direct and rt.mode == "bf16" and _abi.load().sg_conv_tc_direct_supported(C.byref(d)))
+def direct_ok(rt: Runtime, d: ConvDesc, force: bool = False) -> bool:
+    """True when the tensor-core launch should read the filter in place from the store's bf16 mirror (no packing pass).
+    By default only roles for which the master layout is already K-major (dgrads of Conv2D, phases of Conv2DTranspose):
+    reading an HWIO filter in place makes it an N-major UMMA operand, which measured ~20% slower on the big forward
+    convs than the packed K-major copy (profiles/), more than the packing pass costs.  SGAN_DIRECT_NMAJOR=1 enables it."""
+    if not (rt.use_direct and rt.mode == "bf16" and _abi.load().sg_conv_tc_direct_supported(C.byref(d))):
+        return False
+    return force or d.w_ci_stride == 1 or rt.direct_nmajor
 
 
 def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w_mirror=None) -> None:

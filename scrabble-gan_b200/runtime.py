@@ -57,6 +57,7 @@ class Runtime:
         self.op_torch = torch.bfloat16 if mode == "bf16" else torch.float32
         # bf16 mode: tensor-core convs read their filters in place from a bf16 mirror of the flat parameter buffer
         self.use_direct = os.environ.get("SGAN_NO_DIRECT", "0") != "1"
+        self.direct_nmajor = os.environ.get("SGAN_DIRECT_NMAJOR", "0") == "1"
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
     def empty(self, shape, dt: int = SG_F32) -> torch.Tensor:

@@ -168,7 +168,7 @@ def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
             # pack-free launches: the filter is read in place from a bf16 mirror of the HWIO master (N-major B operand for
             # the forward conv, K-major for the dgrad)
             wm = wd.to(torch.bfloat16)
-            if ops.direct_ok(rt, d):
+            if ops.direct_ok(rt, d, force=True):
                 out4 = rt.empty(y.shape)
                 ops.conv_run(rt, d, xd, wd, None, dev(rt, b), None, out4, w_mirror=wm)
                 check(out4, y, 2e-3, "tc fwd (direct weights)")
@@ -239,7 +239,7 @@ def test_conv_transpose(rt, case, mode):
                 assert ops.direct_ok(rt, d)
                 ops.conv_run(rt, d, xd, wd, None, None, None, out2, w_mirror=wm)
             check(out2, y, tol, "convT fwd (direct weights)")
-            if ops.direct_ok(rt, dd):
+            if ops.direct_ok(rt, dd, force=True):
                 dx2 = rt.empty(x.shape)
                 ops.conv_run(rt, dd, dyd, wd, None, None, None, dx2, w_mirror=wm)
                 check(dx2, x.grad, tol, "convT dgrad (direct weights)")
