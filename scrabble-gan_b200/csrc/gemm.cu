@@ -7,8 +7,10 @@
 
 #define GT_M 64
 #define GT_N 64
-#define GT_K 16
 
+// GT_K = 16: generic k loop.  GT_K = 64: the whole reduction (K <= 64: CBN gamma / beta Dense layers with K = 32 or the
+// batch as K) is staged in ONE round of loads -- a single global-memory latency instead of one per 16-wide k step.
+template <int GT_K>
 __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                const float* __restrict__ bias, int accumulate, int k_per_split) {
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int 
   const bool split = gridDim.z > 1;
   for (int k0 = kbeg; k0 < kend; k0 += GT_K) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GT_K / 4; ++i) {
       int idx = tid + i * 256;
       int mm, kk;
       if (ta) { mm = idx % GT_M; kk = idx / GT_M; } else { kk = idx % GT_K; mm = idx / GT_K; }
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int 
       As[kk][mm] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GT_K / 4; ++i) {
       int idx = tid + i * 256;
       int nn, kk;
       if (tb) { kk = idx % GT_K; nn = idx / GT_K; } else { nn = idx % GT_N; kk = idx / GT_N; }
@@ -95,7 +97,7 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
     int max_splits = k >= 8192 ? k / 512 : k / 64;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    k_per_split = ((k + splits - 1) / splits + GT_K - 1) / GT_K * GT_K;
+    k_per_split = ((k + splits - 1) / splits + 15) / 16 * 16;
     splits = (k + k_per_split - 1) / k_per_split;
   }
   if (splits > 1 && !accumulate) {
@@ -103,7 +105,10 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
     SG_CHECK_CUDA(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, ctx->stream));
   }
   grid.z = splits;
-  k_gemm<<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
+  if (splits == 1 && k <= 64)
+    k_gemm<64><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
+  else
+    k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
