@@ -286,52 +286,73 @@ def test_public_loss_functions(rt):
 
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
 def test_train_step_cuda_graph_matches_eager(rt, mode):
-    """CUDA-graph replay of train_step (captured on the 3rd call of a signature) == the eager step: 6 steps from identical
-    initial weights, identical inputs; statistics and weights must agree up to atomic-add ordering noise."""
+    """CUDA-graph replay of train_step (captured on the 3rd call of a signature) == the eager step.  Two eager warm-up
+    steps, then from the SAME weights / optimizer state: step 3 replayed from the graph vs step 3 run eagerly (a GAN
+    step at B=2 is chaotic over several steps in bf16 because atomic-add ordering flips Adam update signs, so the
+    comparison is made on one step).  Afterwards three more replays must stay finite and advance the optimizers."""
     rt.set_mode(mode)
+    old = du.GRAPH_ENABLED
     try:
+        du._graph_cache.clear()
+        du.GRAPH_ENABLED = True
         b, l = 2, 2
         rng = np.random.RandomState(5)
         batches = [(rng.uniform(-1, 1, size=(b, 32, 16 * l, 1)).astype(np.float32), rng.randint(0, 52, size=(b, l)).astype(np.int32),
                     rng.randint(0, 52, size=(b, l)).astype(np.int32), rng.standard_normal(size=(b, 128)).astype(np.float32))
                    for _ in range(6)]
+        G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=31)
+        D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt, seed=32)
+        R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt, seed=33)
+        for m in (G, D):
+            for v in m.store.vars:
+                if v.name.endswith(".sigma"):
+                    v.assign(np.array([0.1], np.float32))
+        gan = na.make_gan(G, D, R, None, vis_model=False)
+        g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+        nets, opts = (G, D, R), (g_opt, d_opt, r_opt)
 
-        def run(graph):
-            old = du.GRAPH_ENABLED
-            du.GRAPH_ENABLED = graph
-            try:
-                G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=31)
-                D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt, seed=32)
-                R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt, seed=33)
-                for m in (G, D):
-                    for v in m.store.vars:
-                        if v.name.endswith(".sigma"):
-                            v.assign(np.array([0.1], np.float32))
-                gan = na.make_gan(G, D, R, None, vis_model=False)
-                g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
-                outs = []
-                for i, (imgs, labels, fake, z) in enumerate(batches):
-                    outs.append(du.train_step(0, i, 6, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn,
-                                              disc_iters, agb, None, 10, "", fake_labels=fake, noise=z))
-                captured = any(gs.graph is not None for gs in du._graph_cache.values())
-                return np.array(outs), {n: m.store.w.detach().cpu().double() for n, m in (("G", G), ("D", D), ("R", R))}, \
-                    (g_opt.iterations, d_opt.iterations, r_opt.iterations), captured
-            finally:
-                du.GRAPH_ENABLED = old
+        def step(i):
+            imgs, labels, fake, z = batches[i]
+            return np.array(du.train_step(0, i, 6, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn,
+                                          disc_iters, agb, None, 10, "", fake_labels=fake, noise=z))
 
-        du._graph_cache.clear()
-        stats_e, w_e, it_e, cap_e = run(False)
-        assert not cap_e
-        stats_g, w_g, it_g, cap_g = run(True)
-        assert cap_g, "the 3rd call of a signature must have captured a CUDA graph"
-        assert it_e == it_g == (6, 6, 6)
+        def snapshot():
+            return ([(m.store.w.clone(), m.store.s.clone()) for m in nets],
+                    [(o.iterations, [[t.clone() for t in st.slots] for st in o._state.values()]) for o in opts])
+
+        def restore(snap):
+            for m, (w, s_) in zip(nets, snap[0]):
+                m.store.w.copy_(w)
+                m.store.s.copy_(s_)
+                m.store.version += 1                      # weights changed outside the optimizer: mirrors / packs are stale
+            for o, (it, slots) in zip(opts, snap[1]):
+                o.iterations = it
+                for st, saved in zip(o._state.values(), slots):
+                    for t, sv in zip(st.slots, saved):
+                        t.copy_(sv)
+
+        step(0); step(1)
+        snap = snapshot()
+        stats_g = step(2)                                  # 3rd call: capture + first replay
+        assert any(gs.graph is not None for gs in du._graph_cache.values()), "the 3rd call must have captured a CUDA graph"
+        w_g = [m.store.w.detach().cpu().double() for m in nets]
+        restore(snap)
+        du.GRAPH_ENABLED = False
+        stats_e = step(2)
+        w_e = [m.store.w.detach().cpu().double() for m in nets]
+        du.GRAPH_ENABLED = True
         tol = 2e-2 if mode == "bf16" else 2e-3
         assert np.all(np.isfinite(stats_g))
-        assert np.allclose(stats_g, stats_e, rtol=tol, atol=tol), np.abs(stats_g - stats_e).max()
-        for n in w_e:
-            # 6 Adam steps of size ~lr: a sign flip of a near-zero gradient moves a weight by 2 lr; compare the bulk
-            diff = (w_g[n] - w_e[n]).abs()
-            assert float((diff > 3 * 2e-4).double().mean()) <= 0.02, n
+        assert np.allclose(stats_g, stats_e, rtol=tol, atol=tol), (np.abs(stats_g - stats_e).max(), stats_g, stats_e)
+        for a, e in zip(w_g, w_e):
+            # one Adam step of size ~lr: a sign flip of a near-zero gradient moves a weight by 2 lr; compare the bulk
+            assert float(((a - e).abs() > 1.5 * 2e-4).double().mean()) <= 0.02
+        assert (g_opt.iterations, d_opt.iterations, r_opt.iterations) == (3, 3, 3)
+        for i in (3, 4, 5):                                # replays (after the eager restore bumped the store versions)
+            out = step(i)
+            assert np.all(np.isfinite(out))
+        assert (g_opt.iterations, d_opt.iterations, r_opt.iterations) == (6, 6, 6)
     finally:
+        du.GRAPH_ENABLED = old
         du._graph_cache.clear()
         rt.set_mode("fp32")
