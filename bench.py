@@ -59,6 +59,16 @@ def step_gflop_per_image(lr, lf):
     return (gc + dlf + rlf + dlr + rlr) + 2 * (dlr + dlf) + 2 * rlr + (dlf + rlf) + 2 * gc
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of the dominant kernel's largest launch, from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,6 +174,55 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[1] and configs[2]); single GPU, eager, CUDA events
+# ----------------------------------------------------------------------------------------------------
+def run_secondary(args):
+    import numpy as np
+    import torch
+    runtime = importlib.import_module("scrabble-gan_b200.runtime")
+    na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+    rt = runtime.Runtime(device=int(os.environ.get("LOCAL_RANK", "0")), mode=args.dtype)
+    runtime.set_runtime(rt)
+    rng = np.random.RandomState(1234)
+    in_dim = (32, 160, 1)
+    if args.workload == "inference":
+        G = na.make_generator(128, in_dim, (32, 8192), None, "B3", 52, vis_model=False, rt=rt)
+        lengths = rng.randint(1, 11, size=256)
+        buckets = [(l, int((lengths == l).sum())) for l in range(1, 11) if (lengths == l).any()]
+        data = [(torch.from_numpy(rng.standard_normal(size=(n, 128)).astype(np.float32)).to(rt.device),
+                 torch.from_numpy(rng.randint(0, 52, size=(n, l)).astype(np.int32)).to(rt.device)) for l, n in buckets]
+
+        def one():
+            return [G([z, y], training=False) for z, y in data]
+        images, name = 256, "generator-only inference (run_inference path, training=False), 256 words of 1-10 chars in %d length buckets" % len(buckets)
+    else:
+        R = na.make_recognizer(in_dim, None, 81, vis_model=False, rt=rt)
+        x = torch.from_numpy(rng.uniform(-1, 1, size=(256, 32, 160, 1)).astype(np.float32)).to(rt.device)
+        y = torch.from_numpy(rng.randint(0, 80, size=(256, 10)).astype(np.int32)).to(rt.device)
+
+        def one():
+            R.store.zero_grad()
+            loss, cache = R.forward(rt, x, y)
+            R.backward(rt, cache, None, wgrad=True, want_dx=False)
+            return loss
+        images, name = 256, "recognizer CRNN + CTC loss fwd/bwd, batch 256, 32x160 images, 81 classes"
+    for _ in range(max(args.warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = rt.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": "images/sec", "value": images / (ms * 1e-3), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": args.dtype, "data": "synthetic",
+                      "config": {"workload": name}, "gpu_launches": int(rt.launch_count() - n0)}), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
 def main():
@@ -178,6 +237,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample batch for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="keep train_step eager (no CUDA-graph replay)")
+    ap.add_argument("--workload", default="step", choices=["step", "inference", "recognizer"],
+                    help="step = BASELINE configs[3] (default, the driver's line); inference = configs[1] (generator-only, batch "
+                         "256, 1-10 char words); recognizer = configs[2] (CRNN + CTC fwd/bwd, batch 256, 32x160, 81 classes)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -185,6 +247,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload != "step":
+        run_secondary(args)
         return
 
     import numpy as np
@@ -316,6 +381,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_traffic()
         images = B * world * args.steps
         value = images / (ms_dev * 1e-3)
         e2e = images / (ms_e2e * 1e-3)
@@ -331,7 +397,8 @@ def main():
         peak = peaks["bf16_tflops_sustained"]
         roofline = {"bound": "tensor", "kernel": "k_conv_tc<bf16> (tcgen05 implicit-GEMM conv), largest launch: D.B3.conv2 fwd/dgrad "
                     "M=%d K=9216 N=1024" % (B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                    "frac": (achieved / peak) if achieved else None, "traffic": (traffic or {}).get("traffic_bytes"),
+                    "traffic_source": (traffic or {}).get("source"), "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                     "launches_timed": len(kern_ms), "avg_launch_ms": avg_ms,
                     "step": {"achieved": step_tflops, "frac": step_tflops / peak, "gflop_per_image": gf_img}}
         line = {"metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s", "n_gpus": world,

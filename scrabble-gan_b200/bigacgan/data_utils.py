@@ -284,22 +284,22 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     recognizer.trainable = True
     if fused:
         discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
-        pending.append(rt.allreduce_async_(discriminator.store.g))
+        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         dfc = discriminator.slice_cache(dcc, 0, b)
         recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
-        pending.append(rt.allreduce_async_(recognizer.store.g))
+        pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
         rfc = recognizer.slice_cache(rcc, 0, b)
     else:
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
-        pending.append(rt.allreduce_async_(discriminator.store.g))
+        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
-        pending.append(rt.allreduce_async_(recognizer.store.g))
+        pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
     if use_w:
         style_promoter.trainable = True
         style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
         style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
-        pending.append(rt.allreduce_async_(style_promoter.store.g))
+        pending.append((id(style_promoter), rt.allreduce_async_(style_promoter.store.g)))
 
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
     if update_g:
@@ -314,22 +314,24 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
                 dimg_w = style_promoter.backward(rt, sfc, up_s_fake_g, wgrad=False, want_dx=True)
                 ops.axpby(rt, 1.0, dimg, 1.0, dimg_w, out=dimg)
         generator.backward(rt, g_cache, dimg)
-        pending.append(rt.allreduce_async_(generator.store.g))
-    for work in pending:
-        if work is not None:
-            work.wait()
-
-    # ---- optimizer steps (same call shape as the reference) -------------------------------------------------------
+        pending.append((id(generator), rt.allreduce_async_(generator.store.g)))
+    # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced: the Adam
+    # launches of D and R overlap with the all-reduce of G's bucket, which is the last one to start
     def _apply(opt, model):
         tv = model.store.trainable_variables
         opt.apply_gradients(zip([v.grad for v in tv], tv))
 
-    _apply(discriminator_optimizer, discriminator)
-    _apply(recognizer_optimizer, recognizer)
+    work = dict(pending)
+    order = [(discriminator_optimizer, discriminator), (recognizer_optimizer, recognizer)]
     if use_w:
-        _apply(stylepromoter_optimizer, style_promoter)
+        order.append((stylepromoter_optimizer, style_promoter))
     if update_g:
-        _apply(generator_optimizer, generator)
+        order.append((generator_optimizer, generator))
+    for opt, model in order:
+        w = work.get(id(model))
+        if w is not None:
+            w.wait()
+        _apply(opt, model)
 
     return stats
 
