@@ -81,6 +81,12 @@ size_t sg_conv_packed_weight_elems(const sg_conv_desc* d);     /* c_out * ntaps 
 int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_master, void* w_packed);
 int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
                    const float* bias, const void* mask, void* out);
+/* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the shortcut of a ResNet block
+ * (resnet_ops.py:109-114) accumulated in TMEM as extra k-blocks of the main conv -- no second pass over the output.
+ * d2: 1x1, stride 1, same batch / pixel grid / c_out / operand dtype; both filters packed (sg_conv_pack_weights). */
+int sg_conv_fwd_tc_dual(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
+                        const sg_conv_desc* d2, const void* in2, const void* w_packed2, const float* bias,
+                        const void* mask, void* out);
 /* the same launch reading the filter IN PLACE from a bf16 mirror of the master weights (identical indexing): no packing
  * pass.  HWIO forward convs use the mirror as an N-major B operand, dgrads / transposed-conv phases as a K-major one. */
 int sg_conv_tc_direct_supported(const sg_conv_desc* d);

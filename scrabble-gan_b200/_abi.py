@@ -58,6 +58,7 @@ _PROTOS = {
     "sg_conv_packed_weight_elems": (_Z, [_DP]),
     "sg_conv_pack_weights": (_I, [_P, _DP, _P, _P]),
     "sg_conv_fwd_tc": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
+    "sg_conv_fwd_tc_dual": (_I, [_P, _DP, _P, _P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_tc_direct_supported": (_I, [_DP]),
     "sg_conv_fwd_tc_direct": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_wgrad_tc_workspace": (_Z, [_DP, _I]),

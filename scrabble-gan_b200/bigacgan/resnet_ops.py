@@ -121,8 +121,14 @@ class ResNetBlockDown:
         if xs is None:
             xs = x
         h1 = self.conv1.forward(rt, xr, relu=True, out_dt=rt.op_dt)
-        h2 = self.conv2.forward(rt, h1)
-        self.short.forward(rt, xs, out=h2, accumulate=True)
+        h2 = None
+        if not narrow and rt.use_tc and rt.fuse_shortcut:
+            # conv2 and the 1x1 shortcut in ONE launch: the shortcut's k-blocks land in the same TMEM accumulator
+            bsum = ops.axpby(rt, 1.0, self.conv2.b.data, 1.0, self.short.b.data)
+            h2 = self.conv2.forward_with_shortcut(rt, h1, self.short, xs, bsum)
+        if h2 is None:
+            h2 = self.conv2.forward(rt, h1)
+            self.short.forward(rt, xs, out=h2, accumulate=True)
         out = h2 if self.is_last else ops.avgpool2_fwd(rt, h2)
         return out, (xr, xs, h1, (h, w))
 

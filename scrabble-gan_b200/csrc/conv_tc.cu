@@ -152,6 +152,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 struct alignas(64) TcFwdParams {
   CUtensorMap map_a[4];
   CUtensorMap map_b;
+  CUtensorMap map_a2, map_b2;   // optional second (1x1) conv accumulated into the same tile: kc2 extra k-blocks (0 = none)
+  int kc2;
   int tap_view[SG_MAX_TAPS], tap_oy[SG_MAX_TAPS], tap_ox[SG_MAX_TAPS];
   int tap_wt[SG_MAX_TAPS];      // direct-weight modes: index of tap t in the master filter (3rd TMA coordinate)
   int b_mode;                   // 0 = packed K-major matrix (2-D map); 1 = master read in place, K-major; 2 = in place, N-major
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.map_a[v]);
     tma_prefetch_desc(&p.map_b);
+    if (p.kc2) { tma_prefetch_desc(&p.map_a2); tma_prefetch_desc(&p.map_b2); }
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
   tc_fence_before();
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = m_tiles * p.tiles_col;
-  const int nkb = p.ntaps * p.kc_per_tap;
+  const int nkb = p.ntaps * p.kc_per_tap + p.kc2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -238,6 +241,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             }
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
+        }
+        for (int c = 0; c < p.kc2; ++c) {          // second operand: the block's 1x1 shortcut on its own input tensor
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+          tma_load_4d(a_base + s * p.a_stage_stride, &p.map_a2, bar_full + 8 * s, c * KC, x0, y0, n0);
+          tma_load_2d(b_base + s * p.b_stage_stride, &p.map_b2, bar_full + 8 * s, c * KC, col0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -820,7 +830,8 @@ static int direct_mode(const sg_conv_desc* d) {
 }
 
 static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, int b_mode, const float* bias,
-                            const void* mask, void* out) {
+                            const void* mask, void* out, const sg_conv_desc* d2 = nullptr, const void* in2 = nullptr,
+                            const void* w_packed2 = nullptr) {
   SG_REQUIRE(ctx && in && w_packed && out, "sg_conv_fwd_tc: NULL");
   int rc = tc_check(d, "sg_conv_fwd_tc");
   if (rc != SG_OK) return rc;
@@ -892,6 +903,20 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   }
   for (int v = 0; v < 4; ++v)
     if (!used[v]) p.map_a[v] = p.map_a[first_used];
+  if (d2) {      // second operand: a 1x1, stride-1 conv on the same pixel grid and output channels, packed K-major weights
+    SG_REQUIRE(in2 && w_packed2 && b_mode == 0, "sg_conv_fwd_tc_dual: NULL second operand / needs packed weights");
+    SG_REQUIRE(d2->ntaps == 1 && d2->tap_dy[0] == 0 && d2->tap_dx[0] == 0 && d2->in_sy == 1 && d2->in_sx == 1,
+               "sg_conv_fwd_tc_dual: the second conv must be 1x1, stride 1");
+    SG_REQUIRE(d2->n == d->n && d2->grid_h == d->grid_h && d2->grid_w == d->grid_w && d2->c_out == d->c_out && d2->in_dt == d->in_dt &&
+                   d2->in_h == d->grid_h && d2->in_w == d->grid_w && d2->c_in % KC == 0,
+               "sg_conv_fwd_tc_dual: the second conv must share the batch, pixel grid, output channels and operand dtype");
+    SG_REQUIRE(((uintptr_t)in2 & 15) == 0 && ((uintptr_t)w_packed2 & 15) == 0, "sg_conv_fwd_tc_dual: pointers must be 16-byte aligned");
+    p.kc2 = d2->c_in / KC;
+    rc = encode_nhwc_view(enc, &p.map_a2, d2->in_dt, in2, d2->n, d2->in_h, d2->in_w, d2->c_in, 1, 1, 0, 0, KC, p.TW, p.TH, p.TN);
+    if (rc != SG_OK) return rc;
+    rc = encode_2d(enc, &p.map_b2, d2->in_dt, w_packed2, d2->c_in, d2->c_out, KC, p.BN);
+    if (rc != SG_OK) return rc;
+  }
   p.b_mode = b_mode;
   if (b_mode == 0) {
     rc = encode_2d(enc, &p.map_b, d->in_dt, w_packed, (long long)d->ntaps * d->c_in, d->c_out, KC, p.BN);
@@ -924,6 +949,14 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
 int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
                    const void* mask, void* out) {
   return conv_fwd_tc_impl(ctx, d, in, w_packed, 0, bias, mask, out);
+}
+
+/* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the ResNet block's shortcut (resnet_ops.py:109-114)
+ * accumulated in TMEM as extra k-blocks of the main conv instead of a second read-modify-write pass over the output */
+int sg_conv_fwd_tc_dual(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const sg_conv_desc* d2,
+                        const void* in2, const void* w_packed2, const float* bias, const void* mask, void* out) {
+  SG_REQUIRE(d2 != nullptr, "sg_conv_fwd_tc_dual: NULL second descriptor");
+  return conv_fwd_tc_impl(ctx, d, in, w_packed, 0, bias, mask, out, d2, in2, w_packed2);
 }
 
 int sg_conv_tc_direct_supported(const sg_conv_desc* d) { return sg_conv_tc_supported(d) && direct_mode(d) != 0; }

@@ -72,6 +72,19 @@ class ConvLayer:
             ops.conv_run(rt, d, x, self.w.data, self._pack(rt, "fwd", d), b, None, out)
         return out
 
+    def forward_with_shortcut(self, rt: Runtime, x: torch.Tensor, short: "ConvLayer", x2: torch.Tensor, bias, out_dt: int = SG_F32):
+        """self(x) + short(x2) + bias in ONE tensor-core launch (short is a 1x1 conv; its k-blocks are accumulated into the
+        same TMEM tile).  Returns None when the pair cannot take the tensor-core path (caller falls back)."""
+        n, h, w, _ = x.shape
+        d = self._desc("fwd", n, h, w, dt_of(x), out_dt, 0, 0)
+        d2 = short._desc("fwd", n, h, w, dt_of(x2), out_dt, 0, 0)
+        if short.kh != 1 or short.kw != 1 or dt_of(x) != dt_of(x2) or not (ops.tc_ok(rt, d) and ops.tc_ok(rt, d2)):
+            return None
+        ho, wo = self.out_hw(h, w)
+        out = rt.empty((n, ho, wo, self.co), out_dt)
+        ops.conv_run_dual(rt, d, x, self._pack(rt, "fwd", d), d2, x2, short._pack(rt, "fwd", d2), bias, None, out)
+        return out
+
     def dgrad(self, rt: Runtime, dy: torch.Tensor, in_hw: Tuple[int, int], mask=None, out_dt: int = SG_F32, out=None,
               accumulate: bool = False) -> torch.Tensor:
         n = dy.shape[0]

@@ -164,6 +164,11 @@ def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w
         call.sg_conv_fwd_simt(rt.ctx, C.byref(d), _p(x), _p(w_master), _p(bias), _p(mask), _p(out))
 
 
+def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_packed2, bias, mask, out) -> None:
+    """Main conv + 1x1 shortcut conv accumulated in ONE tensor-core launch (both filters packed)."""
+    call.sg_conv_fwd_tc_dual(rt.ctx, C.byref(d), _p(x), _p(w_packed), C.byref(d2), _p(x2), _p(w_packed2), _p(bias), _p(mask), _p(out))
+
+
 def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False) -> None:
     """dw_master += filter gradient of the conv described by d."""
     if not force_simt and tc_ok(rt, d) and d.in_dt == SG_BF16 and d.out_dt == SG_BF16:

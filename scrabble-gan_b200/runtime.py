@@ -58,6 +58,7 @@ class Runtime:
         # bf16 mode: tensor-core convs read their filters in place from a bf16 mirror of the flat parameter buffer
         self.use_direct = os.environ.get("SGAN_NO_DIRECT", "0") != "1"
         self.direct_nmajor = os.environ.get("SGAN_DIRECT_NMAJOR", "0") == "1"
+        self.fuse_shortcut = os.environ.get("SGAN_NO_FUSED_SHORTCUT", "0") != "1"
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
     def empty(self, shape, dt: int = SG_F32) -> torch.Tensor:

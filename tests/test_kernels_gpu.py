@@ -185,6 +185,32 @@ def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
         rt.set_mode("fp32")
 
 
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+@pytest.mark.parametrize("case", [(3, 8, 20, 128, 256, 64), (2, 4, 10, 256, 512, 512), (4, 16, 40, 64, 64, 64)])
+def test_conv_tc_with_fused_shortcut(rt, case, mode):
+    """conv3x3(h1) + conv1x1(xs) + bias in ONE tensor-core launch (ResNetBlockDown: resnet_ops.py:103-114)."""
+    n, h, w, ci, co, ci2 = case
+    rt.set_mode(mode)
+    try:
+        dt = rt.op_dt
+        g = torch.Generator().manual_seed(17)
+        x = quant(rnd(g, n, h, w, ci), mode)
+        x2 = quant(rnd(g, n, h, w, ci2), mode)
+        w1 = quant(rnd(g, 3, 3, ci, co) * (1.0 / (9 * ci) ** 0.5), mode)
+        w2 = quant(rnd(g, 1, 1, ci2, co) * (1.0 / ci2 ** 0.5), mode)
+        b = rnd(g, co)
+        y = O.conv2d(x, w1, None, "same") + O.conv2d(x2, w2, None, "same") + b
+        d = ops.desc_conv_fwd(n, h, w, ci, co, 3, 3, "same", in_dt=dt)
+        d2 = ops.desc_conv_fwd(n, h, w, ci2, co, 1, 1, "same", in_dt=dt)
+        w1d, w2d = dev(rt, w1), dev(rt, w2)
+        out = rt.empty(y.shape)
+        ops.conv_run_dual(rt, d, dev(rt, x, dt), ops.pack_weights(rt, d, w1d), d2, dev(rt, x2, dt), ops.pack_weights(rt, d2, w2d),
+                          dev(rt, b), None, out)
+        check(out, y, 2e-3, "conv + fused 1x1 shortcut")
+    finally:
+        rt.set_mode("fp32")
+
+
 CONVT_CASES = [
     # n, h, w, ci, co, k, sy, sx
     (2, 4, 8, 128, 64, 3, 2, 2),
