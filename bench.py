@@ -59,6 +59,11 @@ def step_gflop_per_image(lr, lf):
     return (gc + dlf + rlf + dlr + rlr) + 2 * (dlr + dlf) + 2 * rlr + (dlf + rlf) + 2 * gc
 
 
+def workload_name(batch, length):
+    return ("ScrabbleGAN G+D+R train step, hinge + gradient balancing, Adam x3, fixed %d-char words (32x%d), batch %d per GPU"
+            % (length, 16 * length, batch))
+
+
 def load_traffic():
     """DRAM bytes (read + write) of the dominant kernel's largest launch, from the committed `ncu --set full` capture."""
     p = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
@@ -164,8 +169,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ScrabbleGAN G+D+R train step, hinge + gradient balancing, fixed %d-char words (32x%d)"
-                                   % (args.length, 16 * args.length), "batch_per_gpu": args.batch, "word_len": args.length},
+            "config": {"workload": workload_name(args.batch, args.length), "batch_per_gpu": args.batch,
+                       "global_batch": args.batch * max(args.gpus, 1), "word_len": args.length,
+                       "parallelism": "host cores (rank 0 only)"},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                              "sample": "batch %d of the same 32x%d workload per step (torch-CPU restatement of the reference "
                                        "step; TensorFlow is not installable here)" % (sample_b, 16 * args.length)},
@@ -404,8 +410,7 @@ def main():
         line = {"metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "ScrabbleGAN G+D+R train step, hinge + gradient balancing, Adam x3, fixed %d-char words (32x%d), "
-                                       "batch %d per GPU" % (L, 16 * L, B), "batch_per_gpu": B, "global_batch": B * world, "word_len": L,
+                "config": {"workload": workload_name(B, L), "batch_per_gpu": B, "global_batch": B * world, "word_len": L,
                            "parallelism": "dp%d" % world, "cuda_graph": bool(graph_default and (world == 1 or du.GRAPH_DP)),
                            "l2": "no explicit flush: the per-step working set (>1 GB of activations, 0.7 GB weights+optimizer state) "
                                  "exceeds the 126 MB L2 and input batches rotate"},

@@ -299,10 +299,10 @@ def bn_stats(rt, x) -> torch.Tensor:
     return sums
 
 
-def bn_stats_finalize_peer(rt, x, count_total, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99):
+def bn_stats_finalize_peer(rt, x, count_total, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99, pe=None):
     """sync-BN statistics with the cross-replica exchange fused in (needs rt.peer): per-block partial sums, then ONE
     launch doing stage-2 reduction + NVLink exchange + mean / rstd / moving averages."""
-    pe = rt.peer
+    pe = rt.peer if pe is None else pe
     rows = x.numel() // c
     nbytes = rt.num_sms * 2 * c * 4
     scratch = rt.scratch("bn_peer", nbytes)
