@@ -105,10 +105,9 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
     SG_CHECK_CUDA(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, ctx->stream));
   }
   grid.z = splits;
-  if (splits == 1 && k <= 64)
-    k_gemm<64><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
-  else
-    k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
+  // (a one-shot GT_K = 64 instantiation for K <= 64 measured SLOWER than the 16-wide loop on the CBN Dense layers --
+  //  19 us vs 10 us per launch in profiles/r01_launches_step.csv -- so the generic loop is used for every shape)
+  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -237,9 +237,8 @@ def batch_stats(rt: Runtime, x: torch.Tensor, bn: BatchNormState, update_moving:
     mv = bn.moving_var.data if update_moving else None
     if rt.world_size > 1 and rt.peer is not None:
         return ops.bn_stats_finalize_peer(rt, x, count * rt.world_size, c, mm, mv) + (count * rt.world_size,)
-    if rt.world_size == 1:
-        # same fused launch with a one-rank table: stage-2 reduction + finalisation, no exchange
-        return ops.bn_stats_finalize_peer(rt, x, count, c, mm, mv, pe=rt.solo_exchange()) + (count,)
+    # (on a single replica the one-block fused launch is slower than the wide stage-2 + finalize pair: 260 vs 150 us per
+    #  step over G's 7 BN layers, profiles/r01_launches_step.csv -- it only pays when it replaces a NCCL call)
     sums = ops.bn_stats(rt, x)
     if rt.world_size > 1:
         rt.allreduce_(sums)
