@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: the gin-subset reader on the reference's own configuration text, the TF SAME /
+transposed-conv phase descriptors, the Keras Adam step size, the channel tables and the step's FLOP model."""
+import importlib
+import math
+
+import pytest
+
+gin = importlib.import_module("scrabble-gan_b200.gin_lite")
+
+# the bindings of /root/reference/src/scrabble_gan.gin (quoted here: the GPU box has no /root/reference)
+GIN_TEXT = """
+# Loss and Optimizer (AdamOptimizer for both G, D and R)
+setup_optimizer.g_lr = 2E-4
+setup_optimizer.d_lr = 2E-4
+setup_optimizer.r_lr = 2E-4
+setup_optimizer.w_lr = 2E-4
+setup_optimizer.beta_1 = 0.0
+setup_optimizer.beta_2 = 0.999
+setup_optimizer.loss_fn = @hinge                #@not_saturating       #@hinge
+setup_optimizer.disc_iters=1                    #2
+setup_optimizer.apply_gradient_balance=0        #1      #0
+setup_optimizer.rmsprop=0                       #0      #1
+shared_specs.latent_dim = 128
+shared_specs.embed_y = (32, 8192)
+shared_specs.kernel_reg = @spectral_norm
+shared_specs.g_bw_attention = 'B3'              #'B_skip'
+io.input_dim = (32, 160, 1)
+io.seq_len = None
+io.char_vec = 'abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ'
+"""
+
+
+def test_gin_subset_reader_parses_the_reference_config():
+    gin.clear_config()
+
+    def hinge(a, b, c, d):
+        return "hinge"
+
+    def spectral_norm(w, power_iteration=1):
+        return w
+    gin.external_configurable(hinge)
+    gin.external_configurable(spectral_norm)
+
+    @gin.configurable
+    def setup_optimizer(g_lr, d_lr, r_lr, w_lr, beta_1, beta_2, loss_fn, disc_iters, apply_gradient_balance, rmsprop):
+        return g_lr, beta_1, beta_2, loss_fn, disc_iters, apply_gradient_balance, rmsprop
+
+    @gin.configurable("shared_specs")
+    def get_shared_specs(latent_dim, embed_y, kernel_reg, g_bw_attention):
+        return latent_dim, embed_y, kernel_reg, g_bw_attention
+
+    gin.parse_config(GIN_TEXT)
+    g_lr, b1, b2, loss_fn, disc_iters, agb, rms = setup_optimizer()
+    assert (g_lr, b1, b2, disc_iters, agb, rms) == (2e-4, 0.0, 0.999, 1, 0, 0) and loss_fn is hinge
+    latent, embed_y, reg, attn = get_shared_specs()
+    assert latent == 128 and embed_y == (32, 8192) and reg is spectral_norm and attn == "B3"
+    assert gin.query_parameter("io.input_dim") == (32, 160, 1) and gin.query_parameter("io.seq_len") is None
+    assert len(gin.query_parameter("io.char_vec")) == 52
+    assert setup_optimizer(g_lr=1.0)[0] == 1.0            # explicit arguments win over bindings
+    with pytest.raises(ValueError):
+        gin.parse_config("not a binding")
+    gin.clear_config()
+
+
+def test_conv_descriptors_follow_tf_padding_rules():
+    ops = importlib.import_module("scrabble-gan_b200.ops")
+    d = ops.desc_conv_fwd(2, 8, 20, 64, 128, 3, 3, "same")
+    assert (d.out_h, d.out_w, d.ntaps) == (8, 20, 9) and (d.tap_dy[0], d.tap_dx[0]) == (-1, -1) and d.w_co_stride == 1
+    d = ops.desc_conv_fwd(2, 2, 19, 512, 512, 2, 2, "valid")
+    assert (d.out_h, d.out_w, d.ntaps) == (1, 18, 4) and (d.tap_dy[3], d.tap_dx[3]) == (1, 1)
+    # Conv2DTranspose 3x3 stride (2,2) SAME: out y = 2 i + kh, cropped -> phases with 1, 2, 2, 4 taps; (2,1): 3 and 6 taps
+    taps = sorted(ops.desc_convT_phase(1, 4, 4, 64, 64, 3, 2, 2, py, px).ntaps for (py, px) in ops.convT_phases(3, 2, 2))
+    assert taps == [1, 2, 2, 4]
+    taps = sorted(ops.desc_convT_phase(1, 4, 4, 64, 64, 3, 2, 1, py, px).ntaps for (py, px) in ops.convT_phases(3, 2, 1))
+    assert taps == [3, 6]
+    # the 1x1 stride-2 shortcut only reaches even output positions
+    assert ops.convT_phases(1, 2, 2) == [(0, 0)] and ops.convT_phases(1, 2, 1) == [(0, 0)]
+    dd = ops.desc_conv_dgrad(2, 8, 20, 64, 128, 3, 3, "same")
+    assert (dd.c_in, dd.c_out, dd.w_ci_stride, dd.w_co_stride) == (128, 64, 1, 128)
+
+
+def test_keras_adam_step_size_and_channel_tables():
+    optim = importlib.import_module("scrabble-gan_b200.optim")
+    na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+    a = optim.Adam(2e-4, 0.0, 0.999)
+    a.iterations = 1
+    assert math.isclose(a._lr_t(), 2e-4 * math.sqrt(1 - 0.999), rel_tol=1e-12)
+    a.iterations = 1000
+    assert math.isclose(a._lr_t(), 2e-4 * math.sqrt(1 - 0.999 ** 1000), rel_tol=1e-12)
+    a.advance_for_replay()
+    assert a.iterations == 1001
+    assert na.get_in_out_channels_gen(32) == ([512, 256, 128], [256, 128, 64])
+    assert na.get_in_out_channels_disc(1, 32) == ([1, 64, 512, 1024], [64, 512, 1024, 1024])
+    with pytest.raises(ValueError):
+        na.get_in_out_channels_gen(64)
+    g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, "hinge", 2, 1, 1)
+    assert type(r_opt).__name__ == "RMSprop" and type(g_opt).__name__ == "Adam" and (disc_iters, agb) == (2, 1)
+
+
+def test_bench_flop_model_matches_the_survey():
+    import bench
+    # Mode A step = 79.71 GF/img at L=5/5 and 160.32 at L=10/10
+    assert abs(bench.step_gflop_per_image(5, 5) - 79.714) < 0.01
+    assert abs(bench.step_gflop_per_image(10, 10) - 160.32) < 0.05
