@@ -143,7 +143,8 @@ class ResNetBlockDown:
         dpre = ops.cast(rt, dout, rt.op_dt) if self.is_last else ops.avgpool2_bwd(rt, dout, rt.op_dt)
         if wgrad:
             # the shortcut bias sees the same upstream gradient as conv2's bias: one column sum serves both
-            self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad)
+            # (sum over pixels of avgpool_bwd(dout) == sum over pooled pixels of dout: read the 4x smaller fp32 tensor)
+            self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad, bias_src=dout)
             self.short.wgrad(rt, xs, dpre, bias_grad=False)
         dh1 = self.conv2.dgrad(rt, dpre, (h, w), mask=h1, out_dt=rt.op_dt)
         if wgrad:

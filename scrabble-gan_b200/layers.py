@@ -99,18 +99,20 @@ class ConvLayer:
             ops.conv_run(rt, d, dy, self.w.data, self._pack(rt, "dgrad", d), None, mask, out)
         return out
 
-    def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True, also_bias=None) -> None:
+    def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True, also_bias=None, bias_src=None) -> None:
         """Filter (+ bias) gradient.  `also_bias`: a second bias gradient [co] that sees the same upstream gradient (the
-        shortcut of a ResNet block): dy is column-summed ONCE and the sum is added to both."""
+        shortcut of a ResNet block): dy is column-summed ONCE and the sum is added to both.  `bias_src`: a tensor with the
+        same column sums as dy that is cheaper to read (the un-pooled fp32 gradient: avg-pool backward preserves sums)."""
         n, h, w, _ = x.shape
         d = self._desc("fwd", n, h, w, dt_of(x), dt_of(dy))
         ops.conv_wgrad(rt, d, x, dy, self.w.grad)
         if bias_grad and self.b is not None:
+            src = dy if bias_src is None else bias_src
             if also_bias is None:
-                ops.colsum_into(rt, dy, self.co, self.b.grad, accumulate=1)
+                ops.colsum_into(rt, src, self.co, self.b.grad, accumulate=1)
             else:
                 s = rt.empty((self.co,), SG_F32)
-                ops.colsum_into(rt, dy, self.co, s, accumulate=0)
+                ops.colsum_into(rt, src, self.co, s, accumulate=0)
                 ops.axpby(rt, 1.0, s, 1.0, self.b.grad, out=self.b.grad)
                 ops.axpby(rt, 1.0, s, 1.0, also_bias, out=also_bias)
 
