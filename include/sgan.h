@@ -40,6 +40,9 @@ int sg_ctx_destroy(sg_ctx* ctx);
 int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
 int sg_ctx_sync(sg_ctx* ctx);
 long long sg_ctx_launch_count(sg_ctx* ctx);      /* kernels launched through this context so far */
+/* speed mode (bf16 runs): the fp32 1x1 projections of the non-local block take their products on bf16 warp-level tensor
+ * ops (fp32 accumulate) instead of exact FFMA; off by default */
+int sg_ctx_set_speed_mode(sg_ctx* ctx, int on);
 int sg_sizeof_conv_desc(void);                    /* sizeof(sg_conv_desc): layout guard for FFI mirrors */
 
 /* ---- convolution family (K1-K8) ------------------------------------------------------------------

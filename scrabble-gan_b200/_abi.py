@@ -51,6 +51,7 @@ _PROTOS = {
     "sg_ctx_set_stream": (_I, [_P, _P]),
     "sg_ctx_sync": (_I, [_P]),
     "sg_ctx_launch_count": (_L, [_P]),
+    "sg_ctx_set_speed_mode": (_I, [_P, _I]),
     "sg_sizeof_conv_desc": (_I, []),
     "sg_conv_fwd_simt": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_wgrad_simt": (_I, [_P, _DP, _P, _P, _P]),

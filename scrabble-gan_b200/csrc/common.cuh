@@ -15,6 +15,7 @@ struct sg_ctx {
   int num_sms;
   void* encode_tiled;        // PFN cuTensorMapEncodeTiled (resolved lazily)
   long long launches;        // number of kernels launched through this context
+  int speed_mode;            // 1: bf16 speed mode -- small fp32 GEMMs of the non-local block use bf16 warp-level tensor ops
 };
 
 void sg_set_error(const char* fmt, ...);

@@ -426,11 +426,14 @@ __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ w
 // forward conv with c_in == 1, c_out % 8 == 0 (<= 64 per pixel group), unit strides: 8 output channels per thread with
 // their ntaps x 8 weights in registers; the input patch comes through L1 (neighbouring threads share it); 16/32-byte
 // vector stores.  out = act(bias + sum_t x[p + tap_t] * w[t, :]) (+ out when accumulate).
-template <typename TOut>
+template <typename TOut, int CH>
 __global__ void __launch_bounds__(256, 4) k_conv_fwd_cin1(sg_conv_desc d, const float* __restrict__ in, const float* __restrict__ w,
                                                            const float* __restrict__ bias, TOut* __restrict__ out) {
+  // CH output channels per thread: the 3x3 input patch is loaded ONCE per (pixel, CH channels) and reused for CH/8 chunks
+  // of 8 channels (this kernel is instruction bound: with CH = 8 the nine patch loads and their bounds checks were
+  // repeated for every 8 channels)
   __shared__ __align__(16) float ws[10][256];          // 9 taps + bias row, c_out <= 256
-  const int groups = d.c_out / 8;                      // threads per pixel
+  const int groups = d.c_out / CH;                     // threads per pixel
   const int sub = threadIdx.x % groups;
   const int pix_per_block = 256 / groups;
   for (int i = threadIdx.x; i < 10 * d.c_out; i += 256) {
@@ -441,43 +444,52 @@ __global__ void __launch_bounds__(256, 4) k_conv_fwd_cin1(sg_conv_desc d, const 
     ws[t][co] = v;
   }
   __syncthreads();
-  float br[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) br[j] = ws[9][sub * 8 + j];
-  // one image row per block iteration (no per-pixel integer division)
-  const int nrows = d.n * d.grid_h;
+  // pixels are linearised over (image, y, x) with 32-bit index math (two divisions per ~400 instructions of work)
+  const int total = d.n * d.grid_h * d.grid_w;
   const int px_lane = threadIdx.x / groups;
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+  for (int p = blockIdx.x * pix_per_block + px_lane; p < total; p += gridDim.x * pix_per_block) {
+    const int x = p % d.grid_w, row = p / d.grid_w;
     const int ni = row / d.grid_h, y = row - ni * d.grid_h;
     const float* img = in + (long long)ni * d.in_h * d.in_w;
     TOut* orow = out + ((long long)ni * d.out_h + y) * d.out_w * d.c_out;
-    for (int x = px_lane; x < d.grid_w; x += pix_per_block) {
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = br[j];
+    {
+      float xv[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
+        xv[t] = 0.f;
         if (t < d.ntaps) {
           int iy = y + d.tap_dy[t], ix = x + d.tap_dx[t];
-          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
-            float xv = __ldg(img + iy * d.in_w + ix);
-            const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][sub * 8]), w1 = *reinterpret_cast<const float4*>(&ws[t][sub * 8 + 4]);
-            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
-          }
+          if (iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) xv[t] = __ldg(img + iy * d.in_w + ix);
         }
       }
-      if (d.relu) {
+      TOut* op = orow + x * d.c_out + sub * CH;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      for (int c8 = 0; c8 < CH; c8 += 8) {
+        const int cb = sub * CH + c8;
+        float acc[8];
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(&ws[9][cb]), b1 = *reinterpret_cast<const float4*>(&ws[9][cb + 4]);
+          acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < d.ntaps) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][cb]), w1 = *reinterpret_cast<const float4*>(&ws[t][cb + 4]);
+            acc[0] = fmaf(xv[t], w0.x, acc[0]); acc[1] = fmaf(xv[t], w0.y, acc[1]); acc[2] = fmaf(xv[t], w0.z, acc[2]); acc[3] = fmaf(xv[t], w0.w, acc[3]);
+            acc[4] = fmaf(xv[t], w1.x, acc[4]); acc[5] = fmaf(xv[t], w1.y, acc[5]); acc[6] = fmaf(xv[t], w1.z, acc[6]); acc[7] = fmaf(xv[t], w1.w, acc[7]);
+          }
+        }
+        if (d.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        if (d.accumulate) {
+          float4 a = sg_ld4(op + c8), b = sg_ld4(op + c8 + 4);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        sg_st4(op + c8, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        sg_st4(op + c8 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
       }
-      TOut* op = orow + x * d.c_out + sub * 8;
-      if (d.accumulate) {
-        float4 a = sg_ld4(op), b = sg_ld4(op + 4);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-      }
-      sg_st4(op, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      sg_st4(op + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
   }
 }
@@ -522,11 +534,18 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
     bool unit = d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0;
     int groups = d->c_out / 8;
     bool g_ok = d->c_out % 8 == 0 && groups >= 1 && groups <= 32 && 256 % groups == 0;
-    if (unit && d->c_in == 1 && g_ok && d->ntaps <= 9 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0) {
-      long long need = (long long)d->n * d->grid_h, cap = (long long)ctx->num_sms * 8;   // one image row per block iteration
+    if (unit && d->c_in == 1 && g_ok && d->ntaps <= 9 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0 && M < (1LL << 30)) {
+      const bool wide = d->c_out % 32 == 0 && 256 % (d->c_out / 32) == 0;
+      const int ppb = 256 / (wide ? d->c_out / 32 : groups);
+      long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 10;
       int grid = (int)(need < cap ? need : cap);
-      if (d->out_dt == SG_F32) k_conv_fwd_cin1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
-      else k_conv_fwd_cin1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+      if (wide) {
+        if (d->out_dt == SG_F32) k_conv_fwd_cin1<float, 32><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
+        else k_conv_fwd_cin1<__nv_bfloat16, 32><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+      } else {
+        if (d->out_dt == SG_F32) k_conv_fwd_cin1<float, 8><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
+        else k_conv_fwd_cin1<__nv_bfloat16, 8><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+      }
       SG_POST_LAUNCH(ctx);
       return SG_OK;
     }

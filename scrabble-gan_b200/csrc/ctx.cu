@@ -60,6 +60,12 @@ int sg_ctx_sync(sg_ctx* ctx) {
 
 long long sg_ctx_launch_count(sg_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+int sg_ctx_set_speed_mode(sg_ctx* ctx, int on) {
+  SG_REQUIRE(ctx != nullptr, "ctx is NULL");
+  ctx->speed_mode = on ? 1 : 0;
+  return SG_OK;
+}
+
 }  // extern "C"
 
 // layout guard for the ctypes mirror of sg_conv_desc

@@ -211,6 +211,164 @@ __global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bf16 speed mode: the same two operations on warp-level tensor ops (mma.sync m16n8k16, fp32 accumulate).
+// The FFMA kernels above are instruction bound (~2x the 64x48 FMAs per row in issue slots); here a warp owns 16 rows, loads
+// the fp32 operands straight from global memory in fragment order (every 32-byte sector is used exactly once, no staging
+// of the activations), converts to bf16 in registers, and the kernels become HBM bound.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nl_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void nl_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C[rows,N] (+)= alpha * A[rows,K] . W[K,N]; 8 warps x 16 rows per block iteration; W^T (bf16) resident in smem
+template <int K, int N, bool TRANS_W>
+__global__ void __launch_bounds__(256) k_nl_rowgemm_mma(long long rows, SegMat A, SegMat W, SegMat C, const float* __restrict__ alpha_p,
+                                                         int accumulate, const float* __restrict__ resid_scale_p,
+                                                         const float* __restrict__ resid_x, float* __restrict__ resid_out) {
+  constexpr int KP = K + 8;                                  // padded row (bf16): conflict-free 32-bit fragment reads
+  __shared__ __align__(16) __nv_bfloat16 Wt[N * KP];         // Wt[n][k] = Wlogical[k][n]
+  for (int i = threadIdx.x; i < K * N; i += 256) {
+    int k = i / N, n = i % N;
+    int s, off;
+    float v;
+    if (!TRANS_W) { seg_find(W, n, s, off); v = W.p[s][(long long)k * W.w[s] + off]; }
+    else { seg_find(W, k, s, off); v = W.p[s][(long long)n * W.w[s] + off]; }
+    Wt[n * KP + k] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const float alpha = alpha_p ? *alpha_p : 1.f;
+  const float rscale = resid_scale_p ? *resid_scale_p : 1.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (long long r0 = ((long long)blockIdx.x * 8 + warp) * 16; r0 < rows; r0 += (long long)gridDim.x * 128) {
+    const long long ra = r0 + g, rb = r0 + g + 8;
+    const long long ca = ra < rows ? ra : rows - 1, cb = rb < rows ? rb : rows - 1;
+    uint32_t a[K / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                          // k halves of 8 never straddle a segment (widths % 8 == 0)
+        int s, off;
+        seg_find(A, 16 * ks + 8 * h, s, off);
+        const float2 va = *reinterpret_cast<const float2*>(A.p[s] + ca * A.w[s] + off + 2 * t);
+        const float2 vb = *reinterpret_cast<const float2*>(A.p[s] + cb * A.w[s] + off + 2 * t);
+        a[ks][2 * h] = nl_pack(va.x, va.y);
+        a[ks][2 * h + 1] = nl_pack(vb.x, vb.y);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const __nv_bfloat16* wp = Wt + (8 * nt + g) * KP + 16 * ks + 2 * t;
+        nl_mma(acc, a[ks], *reinterpret_cast<const uint32_t*>(wp), *reinterpret_cast<const uint32_t*>(wp + 8));
+      }
+      int s, off;
+      seg_find(C, 8 * nt, s, off);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long row = h ? rb : ra;
+        if (row >= rows) continue;
+        float2 v = make_float2(alpha * acc[2 * h], alpha * acc[2 * h + 1]);
+        float* cp = C.p[s] + row * C.w[s] + off + 2 * t;
+        if (accumulate) {
+          float2 o = *reinterpret_cast<const float2*>(cp);
+          v.x += o.x; v.y += o.y;
+        }
+        *reinterpret_cast<float2*>(cp) = v;
+        if (resid_out) {
+          const float2 x = *reinterpret_cast<const float2*>(resid_x + row * N + 8 * nt + 2 * t);
+          *reinterpret_cast<float2*>(resid_out + row * N + 8 * nt + 2 * t) = make_float2(fmaf(rscale, v.x, x.x), fmaf(rscale, v.y, x.y));
+        }
+      }
+    }
+  }
+}
+
+// dW[KA,KB] += alpha * A^T . B over rows: a warp keeps the WHOLE dW tile in accumulator fragments ((KA/16) x (KB/8) mma
+// tiles) and walks 16-row chunks; A^T and B fragments are pairs of consecutive ROWS of one column, read straight from
+// global memory (8 lanes cover one 32-byte sector).  The 8 warps of a block are combined with shared-memory atomics,
+// then one global atomicAdd per element and block.
+template <int KA, int KB>
+__global__ void __launch_bounds__(256, 1) k_nl_wgrad_mma(long long rows, long long rows_per_block, SegMat A, SegMat B, SegMat DW,
+                                                          const float* __restrict__ alpha_p) {
+  constexpr int MT = KA / 16, NT = KB / 8;
+  __shared__ float red[KA * KB];
+  for (int i = threadIdx.x; i < KA * KB; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+  long long r_begin = (long long)blockIdx.x * rows_per_block, r_end = r_begin + rows_per_block;
+  if (r_end > rows) r_end = rows;
+  for (long long r0 = r_begin + warp * 16; r0 < r_end; r0 += 128) {
+    // the four row pairs of this chunk that this lane touches: rows 2t, 2t+1, 2t+8, 2t+9 (zero beyond r_end)
+    long long rr[4] = {r0 + 2 * t, r0 + 2 * t + 1, r0 + 2 * t + 8, r0 + 2 * t + 9};
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ok[i] = rr[i] < r_end; if (!ok[i]) rr[i] = r_end - 1; }
+    uint32_t af[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                          // column 16m + g + 8h of A
+        int s, off;
+        seg_find(A, 16 * m + 8 * h, s, off);
+        const float* base = A.p[s] + off + g;
+        const long long w = A.w[s];
+        float v0 = ok[0] ? base[rr[0] * w] : 0.f, v1 = ok[1] ? base[rr[1] * w] : 0.f;
+        float v2 = ok[2] ? base[rr[2] * w] : 0.f, v3 = ok[3] ? base[rr[3] * w] : 0.f;
+        af[m][h] = nl_pack(v0, v1);                          // a0 / a1: k = rows 2t, 2t+1
+        af[m][2 + h] = nl_pack(v2, v3);                      // a2 / a3: k = rows 2t+8, 2t+9
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      int s, off;
+      seg_find(B, 8 * n, s, off);
+      const float* base = B.p[s] + off + g;
+      const long long w = B.w[s];
+      float v0 = ok[0] ? base[rr[0] * w] : 0.f, v1 = ok[1] ? base[rr[1] * w] : 0.f;
+      float v2 = ok[2] ? base[rr[2] * w] : 0.f, v3 = ok[3] ? base[rr[3] * w] : 0.f;
+      const uint32_t b0 = nl_pack(v0, v1), b1 = nl_pack(v2, v3);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) nl_mma(acc[m][n], af[m], b0, b1);
+    }
+  }
+  // accumulator (m tile, n tile): c0,c1 = (row 16m + g, cols 8n + 2t, +1); c2,c3 = row + 8
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      atomicAdd(&red[(16 * m + g) * KB + 8 * n + 2 * t], acc[m][n][0]);
+      atomicAdd(&red[(16 * m + g) * KB + 8 * n + 2 * t + 1], acc[m][n][1]);
+      atomicAdd(&red[(16 * m + g + 8) * KB + 8 * n + 2 * t], acc[m][n][2]);
+      atomicAdd(&red[(16 * m + g + 8) * KB + 8 * n + 2 * t + 1], acc[m][n][3]);
+    }
+  __syncthreads();
+  const float alpha = alpha_p ? *alpha_p : 1.f;
+  for (int i = threadIdx.x; i < KA * KB; i += 256) {
+    int r = i / KB, c = i % KB, s, off;
+    seg_find(DW, c, s, off);
+    atomicAdd(DW.p[s] + (long long)r * DW.w[s] + off, alpha * red[i]);
+  }
+}
+
+template <int K, int N, bool TRANS_W>
+static int nl_rowgemm_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat W, SegMat C, const float* alpha, int accumulate,
+                             const float* resid_scale, const float* resid_x, float* resid_out);
+
 static SegMat seg1(const float* a, int w) {
   SegMat m;
   m.p[0] = const_cast<float*>(a); m.p[1] = m.p[2] = nullptr;
@@ -238,6 +396,14 @@ static void nl_wgrad_grid(sg_ctx* ctx, long long rows, int* grid, long long* rpb
 }
 template <int KA, int KB>
 static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegMat DW, const float* alpha) {
+  if (ctx->speed_mode) {
+    long long blocks = (long long)ctx->num_sms * 2;
+    long long rpb = ((rows + blocks - 1) / blocks + 127) / 128 * 128;
+    int grid_m = (int)((rows + rpb - 1) / rpb);
+    k_nl_wgrad_mma<KA, KB><<<grid_m, 256, 0, ctx->stream>>>(rows, rpb, A, B, DW, alpha);
+    SG_POST_LAUNCH(ctx);
+    return SG_OK;
+  }
   int grid;
   long long rpb;
   nl_wgrad_grid(ctx, rows, &grid, &rpb);
@@ -245,6 +411,21 @@ static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegM
   static_assert(NLW_SUB * 16 * (KA / 4) * (KB / 4) <= NLW_SUB * NLW_ROWS * (KA + KB), "reduction buffer does not fit");
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_nl_wgrad<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_nl_wgrad<KA, KB><<<grid, NLW_SUB * (KA / 4) * (KB / 4), smem, ctx->stream>>>(rows, rpb, A, B, DW, alpha);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+template <int K, int N, bool TRANS_W>
+static int nl_rowgemm_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat W, SegMat C, const float* alpha, int accumulate,
+                             const float* resid_scale, const float* resid_x, float* resid_out) {
+  if (ctx->speed_mode) {
+    long long need = (rows + 127) / 128, cap = (long long)ctx->num_sms * 8;
+    k_nl_rowgemm_mma<K, N, TRANS_W><<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(rows, A, W, C, alpha, accumulate, resid_scale,
+                                                                                            resid_x, resid_out);
+  } else {
+    k_nl_rowgemm<K, N, TRANS_W><<<nl_grid<K, N>(ctx, rows), 256, 0, ctx->stream>>>(rows, A, W, C, alpha, accumulate, resid_scale, resid_x,
+                                                                                  resid_out);
+  }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -261,11 +442,8 @@ int sg_nonlocal_proj_fwd(sg_ctx* ctx, const float* x, long long rows, const floa
   SG_REQUIRE(ctx && x && w_theta && w_phi && w_g && theta && phi_f && g_f, "sg_nonlocal_proj_fwd: NULL");
   SG_REQUIRE(NL_ALIGNED(x) && NL_ALIGNED(theta) && NL_ALIGNED(phi_f) && NL_ALIGNED(g_f), "sg_nonlocal_proj_fwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
-  k_nl_rowgemm<NL_C, 2 * NL_DK + NL_DV, false><<<nl_grid<NL_C, 2 * NL_DK + NL_DV>(ctx, rows), 256, 0, ctx->stream>>>(
-      rows, seg1(x, NL_C), seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV), seg3(theta, NL_DK, phi_f, NL_DK, g_f, NL_DV), nullptr, 0,
-      nullptr, nullptr, nullptr);
-  SG_POST_LAUNCH(ctx);
-  return SG_OK;
+  return nl_rowgemm_launch<NL_C, 2 * NL_DK + NL_DV, false>(ctx, rows, seg1(x, NL_C), seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV),
+                                                           seg3(theta, NL_DK, phi_f, NL_DK, g_f, NL_DV), nullptr, 0, nullptr, nullptr, nullptr);
 }
 
 int sg_nonlocal_out_fwd(sg_ctx* ctx, const float* o, long long rows, const float* w_o, const float* sigma, const float* x,
@@ -274,10 +452,7 @@ int sg_nonlocal_out_fwd(sg_ctx* ctx, const float* o, long long rows, const float
   SG_REQUIRE(NL_ALIGNED(o) && NL_ALIGNED(x) && NL_ALIGNED(og) && NL_ALIGNED(out), "sg_nonlocal_out_fwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
   // og = o . Wo (kept un-scaled for d sigma = <dout, og>);  out = sigma * og + x
-  k_nl_rowgemm<NL_DV, NL_C, false><<<nl_grid<NL_DV, NL_C>(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(o, NL_DV), seg1(w_o, NL_C), seg1(og, NL_C),
-                                                                                 nullptr, 0, sigma, x, out);
-  SG_POST_LAUNCH(ctx);
-  return SG_OK;
+  return nl_rowgemm_launch<NL_DV, NL_C, false>(ctx, rows, seg1(o, NL_DV), seg1(w_o, NL_C), seg1(og, NL_C), nullptr, 0, sigma, x, out);
 }
 
 int sg_nonlocal_out_bwd(sg_ctx* ctx, const float* dout, const float* o, long long rows, const float* w_o, const float* sigma,
@@ -286,9 +461,9 @@ int sg_nonlocal_out_bwd(sg_ctx* ctx, const float* dout, const float* o, long lon
   SG_REQUIRE(NL_ALIGNED(dout) && NL_ALIGNED(o) && NL_ALIGNED(d_o), "sg_nonlocal_out_bwd: 16-byte alignment");
   if (rows == 0) return SG_OK;
   // d_o = sigma * dout . Wo^T
-  k_nl_rowgemm<NL_C, NL_DV, true><<<nl_grid<NL_C, NL_DV>(ctx, rows), 256, 0, ctx->stream>>>(rows, seg1(dout, NL_C), seg1(w_o, NL_C), seg1(d_o, NL_DV),
-                                                                                sigma, 0, nullptr, nullptr, nullptr);
-  SG_POST_LAUNCH(ctx);
+  int rc = nl_rowgemm_launch<NL_C, NL_DV, true>(ctx, rows, seg1(dout, NL_C), seg1(w_o, NL_C), seg1(d_o, NL_DV), sigma, 0, nullptr, nullptr,
+                                                nullptr);
+  if (rc != SG_OK) return rc;
   if (dw_o)                    // dWo[32,64] += sigma * o^T . dout
     return nl_wgrad_launch<NL_DV, NL_C>(ctx, rows, seg1(o, NL_DV), seg1(dout, NL_C), seg1(dw_o, NL_C), sigma);
   return SG_OK;
@@ -305,9 +480,9 @@ int sg_nonlocal_proj_bwd(sg_ctx* ctx, const float* x, const float* dtheta, const
   if (rows == 0) return SG_OK;
   SegMat d = seg3(dtheta, NL_DK, dphi_f, NL_DK, dg_f, NL_DV);
   // dx += [dtheta | dphi | dg] . [Wtheta | Wphi | Wg]^T
-  k_nl_rowgemm<2 * NL_DK + NL_DV, NL_C, true><<<nl_grid<2 * NL_DK + NL_DV, NL_C>(ctx, rows), 256, 0, ctx->stream>>>(
-      rows, d, seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV), seg1(dx, NL_C), nullptr, 1, nullptr, nullptr, nullptr);
-  SG_POST_LAUNCH(ctx);
+  int rc = nl_rowgemm_launch<2 * NL_DK + NL_DV, NL_C, true>(ctx, rows, d, seg3(w_theta, NL_DK, w_phi, NL_DK, w_g, NL_DV), seg1(dx, NL_C), nullptr,
+                                                            1, nullptr, nullptr, nullptr);
+  if (rc != SG_OK) return rc;
   if (dw_theta)                // [dWtheta | dWphi | dWg] += x^T . [dtheta | dphi | dg]
     return nl_wgrad_launch<NL_C, 2 * NL_DK + NL_DV>(ctx, rows, seg1(x, NL_C), d, seg3(dw_theta, NL_DK, dw_phi, NL_DK, dw_g, NL_DV), nullptr);
   return SG_OK;

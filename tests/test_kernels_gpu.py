@@ -455,9 +455,19 @@ def test_filterbank(rt):
     check(dz0, z.grad[:, :32], 1e-5, "dz0")
 
 
-@pytest.mark.parametrize("p", [77, 128 * 3, 5000])
-def test_nonlocal_projections(rt, p):
-    """Fused 1x1 projections of the non-local block (arch_ops.py:38-67), forward and backward, vs plain matmuls."""
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("p", [77, 128 * 3, 5000, 20001])
+def test_nonlocal_projections(rt, p, mode):
+    """Fused 1x1 projections of the non-local block (arch_ops.py:38-67), forward and backward, vs plain matmuls: exact FFMA
+    kernels in fp32 mode (1e-5), bf16 warp-level tensor ops in the speed mode (1e-2 of the largest magnitude)."""
+    rt.set_mode(mode)
+    try:
+        _nonlocal_projections_case(rt, p, 1e-5 if mode == "fp32" else 1e-2)
+    finally:
+        rt.set_mode("fp32")
+
+
+def _nonlocal_projections_case(rt, p, tol):
     g = torch.Generator().manual_seed(21)
     x = rnd(g, p, 64).requires_grad_(True)
     wt, wp, wg = [(rnd(g, 64, k) * 0.2).requires_grad_(True) for k in (8, 8, 32)]
@@ -465,7 +475,7 @@ def test_nonlocal_projections(rt, p):
     sigma = torch.tensor([0.37], dtype=torch.float64, requires_grad=True)
     theta, phi, gg = x @ wt, x @ wp, x @ wg
     th_d, ph_d, g_d = ops.nonlocal_proj_fwd(rt, dev(rt, x), dev(rt, wt), dev(rt, wp), dev(rt, wg))
-    check(th_d, theta, 1e-5, "theta"); check(ph_d, phi, 1e-5, "phi"); check(g_d, gg, 1e-5, "g")
+    check(th_d, theta, tol, "theta"); check(ph_d, phi, tol, "phi"); check(g_d, gg, tol, "g")
     # projection backward
     dth, dph, dgg = rnd(g, p, 8), rnd(g, p, 8), rnd(g, p, 32)
     dx0 = rnd(g, p, 64)
@@ -473,23 +483,23 @@ def test_nonlocal_projections(rt, p):
     dx = dev(rt, dx0)
     gt, gp, gg_ = rt.zeros((64, 8)), rt.zeros((64, 8)), rt.zeros((64, 32))
     ops.nonlocal_proj_bwd(rt, dev(rt, x), dev(rt, dth), dev(rt, dph), dev(rt, dgg), dev(rt, wt), dev(rt, wp), dev(rt, wg), dx, gt, gp, gg_)
-    check(dx, dx0 + x.grad, 1e-5, "dx")
-    check(gt, wt.grad, 1e-5, "dw_theta"); check(gp, wp.grad, 1e-5, "dw_phi"); check(gg_, wg.grad, 1e-5, "dw_g")
+    check(dx, dx0 + x.grad, tol, "dx")
+    check(gt, wt.grad, tol, "dw_theta"); check(gp, wp.grad, tol, "dw_phi"); check(gg_, wg.grad, tol, "dw_g")
     dx2 = dev(rt, dx0)
     ops.nonlocal_proj_bwd(rt, dev(rt, x), dev(rt, dth), dev(rt, dph), dev(rt, dgg), dev(rt, wt), dev(rt, wp), dev(rt, wg), dx2)
-    check(dx2, dx0 + x.grad, 1e-5, "dx (no wgrad)")
+    check(dx2, dx0 + x.grad, tol, "dx (no wgrad)")
     # output projection
     o = rnd(g, p, 32).requires_grad_(True)
     xr = rnd(g, p, 64)
     og = o @ wo
     out = sigma * og + xr
     og_d, out_d = ops.nonlocal_out_fwd(rt, dev(rt, o), dev(rt, wo), dev(rt, sigma), dev(rt, xr))
-    check(og_d, og, 1e-5, "og"); check(out_d, out, 1e-5, "out")
+    check(og_d, og, tol, "og"); check(out_d, out, tol, "out")
     dout = rnd(g, p, 64)
     (out * dout).sum().backward()
     dwo = rt.zeros((32, 64))
     d_o = ops.nonlocal_out_bwd(rt, dev(rt, dout), dev(rt, o), dev(rt, wo), dev(rt, sigma), dwo)
-    check(d_o, o.grad, 1e-5, "d_o"); check(dwo, wo.grad, 1e-5, "dw_o")
+    check(d_o, o.grad, tol, "d_o"); check(dwo, wo.grad, tol, "dw_o")
 
 
 @pytest.mark.parametrize("n,h,w", [(2, 8, 12), (1, 32, 80), (3, 16, 40)])
