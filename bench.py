@@ -401,8 +401,9 @@ def main():
         else:
             avg_ms, achieved = None, None
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": "k_conv_tc<bf16> (tcgen05 implicit-GEMM conv), largest launch: D.B3.conv2 fwd/dgrad "
-                    "M=%d K=9216 N=1024" % (B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roofline = {"bound": "tensor", "kernel": "k_conv_tc<bf16> (tcgen05 implicit-GEMM conv), largest launch shape: D.B3.conv2 dgrad, "
+                    "M=%d (D-loss pass, fused [fake;real] batch) / %d (G-loss pass), K=9216, N=1024; timed in 2 eager steps"
+                    % (2 * B * 8 * 4 * L, B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": (traffic or {}).get("traffic_bytes"),
                     "traffic_source": (traffic or {}).get("source"), "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                     "launches_timed": len(kern_ms), "avg_launch_ms": avg_ms,
