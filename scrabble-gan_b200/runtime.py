@@ -110,14 +110,6 @@ class Runtime:
             return t
         return self.allreduce_(t)
 
-    def solo_exchange(self):
-        """One-rank exchange table (a plain local buffer): lets a single replica use the fused sync-BN launch."""
-        if getattr(self, "_solo", None) is None:
-            from .dp import PeerExchange
-            buf = torch.zeros(int(_abi.load().sg_peer_buffer_bytes()), device=self.device, dtype=torch.uint8)
-            self._solo = PeerExchange(buf, None, [buf.data_ptr()], 1, 0)
-        return self._solo
-
     def _peer_max(self) -> int:
         if not hasattr(self, "_peer_max_bytes"):
             self._peer_max_bytes = int(_abi.load().sg_peer_max_payload_bytes())
