@@ -280,15 +280,23 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     # Data parallel: each network's flat gradient bucket is SUM-all-reduced (not averaged: SURVEY Q7) as soon as its
     # filter gradients are complete, on NCCL's stream, overlapping with the backward passes that follow.
     pending = []
+    dimg_r_merged = None
     discriminator.trainable = True
     recognizer.trainable = True
     if fused:
         discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         dfc = discriminator.slice_cache(dcc, 0, b)
-        recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
+        if update_g and rt.merge_r_backward:
+            # ONE backward pass of R over the fused batch: filter gradients from the real half (R-loss, weight 1), image
+            # gradient of the fake half with the G-loss per-sample weights (different samples: nothing mixes)
+            recognizer.trainable = True
+            dimg_r_all = recognizer.backward(rt, rcc, up_r_fake_g, wgrad=True, want_dx=True, wgrad_rows=(b, 2 * b), up_rows=(0, b))
+            dimg_r_merged = dimg_r_all[:b]
+        else:
+            recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
+            rfc = recognizer.slice_cache(rcc, 0, b)
         pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
-        rfc = recognizer.slice_cache(rcc, 0, b)
     else:
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
@@ -306,7 +314,10 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         recognizer.trainable = False
         discriminator.trainable = False
         dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
-        dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
+        if dimg_r_merged is not None:
+            dimg_r = dimg_r_merged
+        else:
+            dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
         ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
         if use_w:
             style_promoter.trainable = False

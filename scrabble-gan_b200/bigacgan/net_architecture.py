@@ -238,14 +238,15 @@ class Recognizer(_Model):
         y = ops.bn_apply(rt, x, mean, rstd, bn.gamma.data, bn.beta.data, False, False, out_dt)
         return y, (mean, rstd, count, self.bn_training)
 
-    def _bn_backward(self, rt, bn: BatchNormState, bc, dy, x, wgrad, out_dt):
+    def _bn_backward(self, rt, bn: BatchNormState, bc, dy, x, wgrad, out_dt, rows=None):
         """dy = grad of the BN output (fp32); x = BN input = relu(conv) (fp32).  Returns grad w.r.t. the conv
-        pre-activation in the operand dtype (gated by x > 0)."""
+        pre-activation in the operand dtype (gated by x > 0).  `rows` = (a, b): samples whose parameter gradients count."""
         mean, rstd, count, training = bc
         s1, s2 = ops.bn_bwd_reduce(rt, dy, None, x, mean, rstd)
         if wgrad:
-            ops.colsum_into(rt, s2, bn.c, bn.gamma.grad, accumulate=1)
-            ops.colsum_into(rt, s1, bn.c, bn.beta.grad, accumulate=1)
+            a, b = rows if rows is not None else (0, s1.shape[0])
+            ops.colsum_into(rt, s2[a:b], bn.c, bn.gamma.grad, accumulate=1)
+            ops.colsum_into(rt, s1[a:b], bn.c, bn.beta.grad, accumulate=1)
         ab = None
         if training:
             ab = ops.bn_bwd_combine(rt, s1, s2, bn.gamma.data, False)
@@ -282,41 +283,50 @@ class Recognizer(_Model):
         return (sl(x), sl(a1), sl(p1), sl(a2), sl(p2), sl(a3), sl(a4), sl(p4), sl(a5), sl(b5), bc5, sl(a6), sl(b6), bc6, sl(p6),
                 sl(a7), sl(glogits) if glogits is not None else None)
 
-    def backward(self, rt, cache, up, wgrad: bool = True, want_dx: bool = False):
+    def backward(self, rt, cache, up, wgrad: bool = True, want_dx: bool = False, wgrad_rows=None, up_rows=None):
+        """up [n] (or None = 1): per-sample upstream weight of the CTC loss.  `up_rows` = (a, b) applies `up` to those samples
+        only (the others keep weight 1); `wgrad_rows` = (a, b) restricts the PARAMETER gradients to those samples -- together
+        they let ONE pass over the fused [fake ; real] batch serve the R-loss update (real half, filter gradients) and
+        the G-loss image gradient (fake half, per-sample weights): different samples, so the two never mix."""
         x, a1, p1, a2, p2, a3, a4, p4, a5, b5, bc5, a6, b6, bc6, p6, a7, glogits = cache
         T = rt.op_dt
         cv = self.convs
         n, _, t, c = a7.shape
+        wa, wb = wgrad_rows if wgrad_rows is not None else (0, n)
+        sl = lambda v: v[wa:wb]
         if up is not None:
-            ops.scale_rows_(rt, glogits, up)                          # chain the per-sample upstream weight (None = 1)
-        da7 = self.dense.backward(rt, a7, glogits, n * t, want_dx=True, wgrad=wgrad).view(a7.shape)
+            ua, ub = up_rows if up_rows is not None else (0, n)
+            ops.scale_rows_(rt, glogits[ua:ub], up)                   # chain the per-sample upstream weight (None = 1)
+        da7 = self.dense.backward(rt, a7, glogits, n * t, want_dx=True, wgrad=False).view(a7.shape)
+        if wgrad:
+            self.dense.backward(rt, sl(a7), sl(glogits), (wb - wa) * t, want_dx=False, wgrad=True)
         d7 = ops.mask_mul(rt, da7, a7, T)
         if wgrad:
-            cv[6].wgrad(rt, p6, d7)
+            cv[6].wgrad(rt, sl(p6), sl(d7))
         dp6 = cv[6].dgrad(rt, d7, (p6.shape[1], p6.shape[2]))
         db6 = ops.maxpool_bwd(rt, dp6, b6, 2, 1, False, SG_F32)
-        d6 = self._bn_backward(rt, self.bn6, bc6, db6, a6, wgrad, T)
+        d6 = self._bn_backward(rt, self.bn6, bc6, db6, a6, wgrad, T, (wa, wb))
         if wgrad:
-            cv[5].wgrad(rt, b5, d6)
+            cv[5].wgrad(rt, sl(b5), sl(d6))
         db5 = cv[5].dgrad(rt, d6, (b5.shape[1], b5.shape[2]))
-        d5 = self._bn_backward(rt, self.bn5, bc5, db5, a5, wgrad, T)
+        d5 = self._bn_backward(rt, self.bn5, bc5, db5, a5, wgrad, T, (wa, wb))
         if wgrad:
-            cv[4].wgrad(rt, p4, d5)
+            cv[4].wgrad(rt, sl(p4), sl(d5))
         dp4 = cv[4].dgrad(rt, d5, (p4.shape[1], p4.shape[2]))
         d4 = ops.maxpool_bwd(rt, dp4, a4, 2, 1, True, T)
         if wgrad:
-            cv[3].wgrad(rt, a3, d4)
+            cv[3].wgrad(rt, sl(a3), sl(d4))
         d3 = cv[3].dgrad(rt, d4, (a3.shape[1], a3.shape[2]), mask=a3, out_dt=T)
         if wgrad:
-            cv[2].wgrad(rt, p2, d3)
+            cv[2].wgrad(rt, sl(p2), sl(d3))
         dp2 = cv[2].dgrad(rt, d3, (p2.shape[1], p2.shape[2]))
         d2 = ops.maxpool_bwd(rt, dp2, a2, 2, 2, True, T)
         if wgrad:
-            cv[1].wgrad(rt, p1, d2)
+            cv[1].wgrad(rt, sl(p1), sl(d2))
         dp1 = cv[1].dgrad(rt, d2, (p1.shape[1], p1.shape[2]))
         d1 = ops.maxpool_bwd(rt, dp1, a1, 2, 2, True, T)
         if wgrad:
-            cv[0].wgrad(rt, x, d1)
+            cv[0].wgrad(rt, sl(x), sl(d1))
         if not want_dx:
             return None
         return cv[0].dgrad(rt, d1, (x.shape[1], x.shape[2]))

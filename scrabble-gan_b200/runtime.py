@@ -59,6 +59,7 @@ class Runtime:
         self.use_direct = os.environ.get("SGAN_NO_DIRECT", "0") != "1"
         self.direct_nmajor = os.environ.get("SGAN_DIRECT_NMAJOR", "0") == "1"
         self.fuse_shortcut = os.environ.get("SGAN_NO_FUSED_SHORTCUT", "0") != "1"
+        self.merge_r_backward = os.environ.get("SGAN_NO_MERGED_R_BWD", "0") != "1"
         call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
