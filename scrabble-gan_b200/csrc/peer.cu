@@ -14,7 +14,7 @@
 // (4) read all ranks' payloads (remote NVLink reads, .cv so a stale L1 line is never used) and sum them in RANK ORDER,
 // so every replica gets bit-identical results.  Double buffering is safe because a rank can only publish call s+1
 // after it finished reading in call s, and nobody overwrites slot (s & 1) before call s+2, which needs all flags of s+1.
-// A spin that never completes traps (a protocol bug must fault, not hang the GPU).
+// A spin that never completes (~1 minute) traps: a protocol bug must fault, not hang the GPU.
 //
 // k_bn_finalize_peer fuses that exchange between the second stage of the batch-norm statistics reduction and the
 // mean / rstd / moving-average finalisation: reduce partials -> exchange -> finalize in ONE launch.
@@ -57,10 +57,12 @@ __device__ __forceinline__ void peer_publish_and_wait(const PeerTable& pt) {
   if (t < pt.world && t != pt.rank) st_release_sys(peer_flags(pt.buf[t]) + pt.rank, pt.seq);
   if (t < pt.world && t != pt.rank) {
     const unsigned int* f = peer_flags(pt.buf[pt.rank]) + t;
+    // bounded spin: replicas can be skewed by seconds on their first steps (module loading, graph capture), so the
+    // bound is generous (~1 min); a peer that never arrives still faults instead of hanging the GPU forever
     unsigned int spins = 0;
     while ((int)(ld_acquire_sys(f) - pt.seq) < 0) {
-      if (++spins > (1u << 26)) __trap();
-      __nanosleep(20);
+      if (++spins > (1u << 28)) __trap();
+      __nanosleep(spins < 4096 ? 20 : 200);
     }
   }
   __syncthreads();
