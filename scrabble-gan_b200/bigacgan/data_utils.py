@@ -67,6 +67,7 @@ def _loss_kind(loss_fn) -> int:
 GRAPH_ENABLED = os.environ.get("SGAN_CUDA_GRAPH", "1") != "0"
 GRAPH_DP = os.environ.get("SGAN_CUDA_GRAPH_DP", "1") != "0"      # capture the data-parallel step too (NCCL + peer exchanges)
 GRAPH_WARMUP = 2
+GRAPH_MAX = int(os.environ.get("SGAN_CUDA_GRAPH_MAX", "8"))     # each captured signature keeps its own activation pool (GBs)
 _graph_cache = {}
 
 
@@ -120,7 +121,8 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
         if gs is None:
             gs = _graph_cache[key] = _GraphedStep()
         gs.calls += 1
-        if gs.graph is None and not gs.failed and gs.calls > GRAPH_WARMUP:
+        if gs.graph is None and not gs.failed and gs.calls > GRAPH_WARMUP and \
+                sum(1 for g_ in _graph_cache.values() if g_.graph is not None) < GRAPH_MAX:
             _capture(rt, gs, args, b, l_r, l_f, latent_dim)
         if gs.graph is not None:
             stats = _replay(rt, gs, args, images, labels, fake_labels, noise)
@@ -155,6 +157,19 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
     body advances (optimizer iteration counters, store versions) is rolled back afterwards and advanced by _replay."""
     discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g = args
     stores = [discriminator.store, recognizer.store, generator.store]
+    saved = [(o.iterations if o is not None else 0) for o in opts]
+    versions = None
+
+    def roll_back():
+        for o, it in zip(opts, saved):
+            if o is not None:
+                o.iterations = it
+        if versions is not None:
+            # the captured Adam launches keep the mirrors current: versions only matter for changes made OUTSIDE the graph
+            for st, (v, wbv) in zip(stores, versions):
+                st.version = v
+                st.wb_version = wbv
+
     try:
         for st in stores:
             if rt.mode == "bf16" and rt.use_direct:
@@ -163,7 +178,6 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
                   torch.zeros((b, l_f), device=rt.device, dtype=torch.int32), rt.empty((b, latent_dim)))
         for t in static:
             t.zero_()
-        saved = [(o.iterations if o is not None else 0) for o in opts]
         versions = [(st.version, st.wb_version) for st in stores]
         torch.cuda.synchronize(rt.device)
         graph = torch.cuda.CUDAGraph()
@@ -175,18 +189,13 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
         rt.use_current_stream()
         gs.launches = rt.launch_count() - n0
         rt.replayed_launches -= gs.launches                     # captured, not executed
-        for o, it in zip(opts, saved):
-            if o is not None:
-                o.iterations = it
-        # the captured Adam launches keep the mirrors current: versions only matter for changes made OUTSIDE the graph
-        for st, (v, wbv) in zip(stores, versions):
-            st.version = v
-            st.wb_version = wbv
+        roll_back()
         gs.graph, gs.static, gs.stats = graph, static, stats
         gs.versions = [st.version for st in stores]
     except Exception as ex:      # noqa: BLE001 -- capture is an optimisation: on any failure stay on the eager path
         import sys
         rt.use_current_stream()
+        roll_back()
         gs.failed = True
         gs.graph = None
         print("scrabble-gan_b200: CUDA-graph capture of train_step failed ({}); staying eager".format(repr(ex)[:300]), file=sys.stderr)
