@@ -155,3 +155,114 @@ def test_parameter_counts_match_the_reference_models():
     gp = O.make_generator_params(0, torch.float32)
     assert gp["filter_bank"].numel() == 13631488
     assert count(gp) - gp["filter_bank"].numel() == 2582530 + attn
+
+
+def test_non_local_block_matches_per_pixel_loops():
+    """NonLocalBlock (arch_ops.py:32-67) written out with explicit loops in numpy: 1x1 projections, 2x2 max-pool of phi / g,
+    softmax over the pooled keys WITHOUT 1/sqrt(d), projection back, sigma * o + x."""
+    g = torch.Generator().manual_seed(31)
+    n, h, w, c = 2, 4, 6, 16
+    x = torch.randn(n, h, w, c, generator=g, dtype=DT)
+    p = {"a.theta.w": torch.randn(1, 1, c, c // 8, generator=g, dtype=DT), "a.phi.w": torch.randn(1, 1, c, c // 8, generator=g, dtype=DT),
+         "a.g.w": torch.randn(1, 1, c, c // 2, generator=g, dtype=DT), "a.o.w": torch.randn(1, 1, c // 2, c, generator=g, dtype=DT),
+         "a.sigma": torch.tensor([0.3], dtype=DT)}
+    got = O.non_local_block(x, p, "a").numpy()
+    X = x.numpy()
+    Wt, Wp, Wg, Wo = (p[k][0, 0].numpy() for k in ("a.theta.w", "a.phi.w", "a.g.w", "a.o.w"))
+    exp = np.zeros_like(X)
+    for ni in range(n):
+        theta = X[ni] @ Wt                                     # (h, w, c/8)
+        phi_f, g_f = X[ni] @ Wp, X[ni] @ Wg
+        phi = phi_f.reshape(h // 2, 2, w // 2, 2, -1).max(axis=(1, 3)).reshape(-1, c // 8)
+        gg = g_f.reshape(h // 2, 2, w // 2, 2, -1).max(axis=(1, 3)).reshape(-1, c // 2)
+        for i in range(h):
+            for j in range(w):
+                s = phi @ theta[i, j]
+                a = np.exp(s - s.max())
+                a /= a.sum()
+                exp[ni, i, j] = 0.3 * ((a @ gg) @ Wo) + X[ni, i, j]
+    assert np.abs(got - exp).max() < 1e-12
+
+
+def test_conditional_batchnorm_and_resnet_up_block_semantics():
+    """CBN = batch-normalise (biased variance, eps 1e-3, no scale / centre) then * gamma(z) + beta(z) with bias-free Dense
+    layers and NO '1 + gamma' (resnet_ops.py:13-28); the up block adds a 1x1 stride-2 transposed-conv shortcut of the RAW
+    input whose kernel only reaches even positions while its bias is added everywhere (resnet_ops.py:57-73)."""
+    g = torch.Generator().manual_seed(32)
+    n, h, w, c, zdim = 3, 2, 3, 4, 5
+    x = torch.randn(n, h, w, c, generator=g, dtype=DT) * 2 + 1
+    z = torch.randn(n, zdim, generator=g, dtype=DT)
+    p = {"c.gamma.w": torch.randn(zdim, c, generator=g, dtype=DT), "c.beta.w": torch.randn(zdim, c, generator=g, dtype=DT),
+         "c.moving_mean": torch.zeros(c, dtype=DT), "c.moving_var": torch.ones(c, dtype=DT)}
+    stats = {}
+    got = O.conditional_batchnorm(x, z, p, "c", True, stats).numpy()
+    X = x.numpy()
+    mean, var = X.mean(axis=(0, 1, 2)), X.var(axis=(0, 1, 2))
+    gam, bet = z.numpy() @ p["c.gamma.w"].numpy(), z.numpy() @ p["c.beta.w"].numpy()
+    exp = (X - mean) / np.sqrt(var + 1e-3) * gam[:, None, None, :] + bet[:, None, None, :]
+    assert np.abs(got - exp).max() < 1e-12
+    cnt = n * h * w
+    assert np.allclose(stats["c.moving_var"].numpy(), 0.99 + 0.01 * var * cnt / (cnt - 1))
+    # shortcut of the up block
+    ws = torch.randn(1, 1, 6, c, generator=g, dtype=DT)
+    bs = torch.randn(6, generator=g, dtype=DT)
+    s = O.conv2d_transpose(x, ws, bs, (2, 2)).numpy()
+    val = X @ ws[0, 0].numpy().T
+    assert np.allclose(s[:, ::2, ::2], val + bs.numpy()) and np.allclose(s[:, 1::2, :], bs.numpy()) and np.allclose(s[:, :, 1::2], bs.numpy())
+    s21 = O.conv2d_transpose(x, ws, bs, (2, 1)).numpy()
+    assert s21.shape == (n, 2 * h, w, 6) and np.allclose(s21[:, ::2], val + bs.numpy()) and np.allclose(s21[:, 1::2], bs.numpy())
+
+
+def test_resnet_down_block_relu_on_raw_input_and_pool_commutes():
+    """ResNetBlockDown (resnet_ops.py:93-115): ReLU is applied to the block INPUT before conv1 (even to raw images, Q11), the
+    1x1 shortcut sees the un-rectified input, and avgpool(a) + avgpool(b) == avgpool(a + b) (what the CUDA path exploits)."""
+    g = torch.Generator().manual_seed(33)
+    n, h, w, ci, co = 2, 4, 4, 3, 5
+    x = torch.randn(n, h, w, ci, generator=g, dtype=DT)
+    p = {"b.conv1.w": torch.randn(3, 3, ci, co, generator=g, dtype=DT), "b.conv1.b": torch.randn(co, generator=g, dtype=DT),
+         "b.conv2.w": torch.randn(3, 3, co, co, generator=g, dtype=DT), "b.conv2.b": torch.randn(co, generator=g, dtype=DT),
+         "b.short.w": torch.randn(1, 1, ci, co, generator=g, dtype=DT), "b.short.b": torch.randn(co, generator=g, dtype=DT)}
+    got = O.resnet_block_down(x, p, "b", False)
+    main = O.conv2d(torch.relu(O.conv2d(torch.relu(x), p["b.conv1.w"], p["b.conv1.b"])), p["b.conv2.w"], p["b.conv2.b"])
+    short = O.conv2d(x, p["b.short.w"], p["b.short.b"])
+    summed = (main + short).numpy().reshape(n, h // 2, 2, w // 2, 2, co).mean(axis=(2, 4))
+    assert np.abs(got.numpy() - summed).max() < 1e-12
+    neg = -torch.rand(n, h, w, ci, generator=g, dtype=DT)             # an all-negative input only survives through the shortcut
+    only_short = O.resnet_block_down(neg, p, "b", True)
+    bias_path = O.conv2d(torch.relu(O.conv2d(torch.zeros_like(neg), p["b.conv1.w"], p["b.conv1.b"])), p["b.conv2.w"], p["b.conv2.b"])
+    assert np.abs((only_short - bias_path - O.conv2d(neg, p["b.short.w"], p["b.short.b"])).numpy()).max() < 1e-12
+
+
+def test_ctc_gradient_matches_finite_differences():
+    """d loss / d probs of K.ctc_batch_cost's restatement (eps + re-softmax inside) against central differences in fp64."""
+    g = torch.Generator().manual_seed(34)
+    t, c = 7, 5
+    probs = torch.softmax(torch.randn(1, t, c, generator=g, dtype=DT), -1).requires_grad_(True)
+    labels = torch.tensor([[1, 1, 3]])
+    il, ll = torch.tensor([[t]]), torch.tensor([[3]])
+    loss = O.ctc_batch_cost(labels, probs, il, ll).sum()
+    (grad,) = torch.autograd.grad(loss, probs)
+    base = probs.detach()
+    eps = 1e-6
+    for (ti, ci) in ((0, 1), (3, 4), (6, 3), (2, 0)):
+        pp, pm = base.clone(), base.clone()
+        pp[0, ti, ci] += eps
+        pm[0, ti, ci] -= eps
+        fd = (O.ctc_batch_cost(labels, pp, il, ll).sum() - O.ctc_batch_cost(labels, pm, il, ll).sum()) / (2 * eps)
+        assert abs(float(fd) - float(grad[0, ti, ci])) <= 1e-6 * max(1.0, abs(float(fd)))
+
+
+def test_losses_match_numpy_formulas():
+    """hinge / not_saturating (net_loss.py:4-54) against the literal numpy formulas, incl. the positional quirk of
+    not_saturating (3rd arg: style images -> label 1, 4th: training images -> label 0)."""
+    g = torch.Generator().manual_seed(35)
+    a, b_, c_, d_, e_ = (torch.randn(6, 1, generator=g, dtype=DT) for _ in range(5))
+    A, B, C, D_, E = (t.numpy() for t in (a, b_, c_, d_, e_))
+    out = [t.numpy() for t in O.hinge(a, b_, c_, d_)]
+    relu = lambda v: np.maximum(v, 0)
+    exp = [relu(1 - A) + relu(1 + B), relu(1 - A), relu(1 + B), -(B + D_), relu(1 - C) + relu(1 + D_), relu(1 - C), relu(1 + D_)]
+    assert all(np.abs(o - e).max() < 1e-12 for o, e in zip(out, exp))
+    sce = lambda x, z: np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+    out = [t.numpy() for t in O.not_saturating(a, b_, c_, d_, e_)]
+    exp = [sce(A, 1) + sce(B, 0), sce(A, 1), sce(B, 0), sce(B, 1) + sce(E, 1), sce(C, 1) + sce(D_, 0), sce(C, 1), sce(D_, 0)]
+    assert all(np.abs(o - e).max() < 1e-12 for o, e in zip(out, exp))
