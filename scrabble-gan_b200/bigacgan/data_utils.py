@@ -420,3 +420,33 @@ def train(dataset, generator, discriminator, recognizer, style_promoter, composi
             print('Time for epoch {} is {} sec'.format(epoch_idx + 1, time.time() - start))
             generator.save_weights(os.path.join(generator_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))
             recognizer.save_weights(os.path.join(recognizer_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic stand-ins for the reference's data loaders (the IAM dataset is not available here)
+# ----------------------------------------------------------------------------------------------------
+def synthetic_word_batches(input_dim, batch_size, char_vector, bucket_size, bucket_weights=None, seed: int = 0, pinned: bool = False):
+    """Python generator with the interface of the reference's load_prepare_data (data_utils.py:14-84): yields
+    (image_batch (B, h, (h/2)*len, c) float32 in [-1, 1], label_batch (B, len) int32), ONE random length bucket per batch
+    drawn from `bucket_weights` (uniform if None) -- the reference's own rule (:64).  Images are uniform noise: this feeds
+    benchmarks and the train() shell, it is not a dataset.  `pinned`: yield page-locked torch tensors (async H2D)."""
+    h, _, c = input_dim
+    rng = np.random.RandomState(seed)
+    p = None
+    if bucket_weights is not None:
+        p = np.asarray(bucket_weights, np.float64)
+        p = p / p.sum()
+    while True:
+        length = int(rng.choice(bucket_size, 1, p=p)[0]) + 1
+        images = rng.uniform(-1.0, 1.0, size=(batch_size, h, (h // 2) * length, c)).astype(np.float32)
+        labels = rng.randint(0, len(char_vector), size=(batch_size, length)).astype(np.int32)
+        if pinned:
+            yield torch.from_numpy(images).pin_memory(), torch.from_numpy(labels).pin_memory()
+        else:
+            yield images, labels
+
+
+def synthetic_random_words(bucket_size, char_vector, words_per_bucket: int = 256, seed: int = 0):
+    """Stand-in for load_random_word_list (data_utils.py:550-574): random_words[len-1] = list of encoded words of that length."""
+    rng = np.random.RandomState(seed)
+    return [[list(map(int, rng.randint(0, len(char_vector), size=length))) for _ in range(words_per_bucket)]
+            for length in range(1, bucket_size + 1)]

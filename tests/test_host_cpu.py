@@ -102,3 +102,22 @@ def test_bench_flop_model_matches_the_survey():
     # Mode A step = 79.71 GF/img at L=5/5 and 160.32 at L=10/10
     assert abs(bench.step_gflop_per_image(5, 5) - 79.714) < 0.01
     assert abs(bench.step_gflop_per_image(10, 10) - 160.32) < 0.05
+
+
+def test_synthetic_loaders_keep_the_reference_interfaces():
+    du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+    char_vec = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    gen = du.synthetic_word_batches((32, 160, 1), 4, char_vec, 10, seed=3)
+    seen = set()
+    for _ in range(40):
+        imgs, labels = next(gen)
+        length = labels.shape[1]
+        seen.add(length)
+        assert imgs.shape == (4, 32, 16 * length, 1) and imgs.dtype.name == "float32" and labels.dtype.name == "int32"
+        assert -1.0 <= imgs.min() and imgs.max() <= 1.0 and 0 <= labels.min() and labels.max() < 52
+    assert len(seen) > 3 and min(seen) >= 1 and max(seen) <= 10          # one bucket per batch, several buckets over time
+    only5 = du.synthetic_word_batches((32, 160, 1), 2, char_vec, 10, bucket_weights=[0, 0, 0, 0, 1, 0, 0, 0, 0, 0])
+    assert next(only5)[1].shape == (2, 5)
+    words = du.synthetic_random_words(10, char_vec, words_per_bucket=7)
+    assert len(words) == 10 and all(len(words[i]) == 7 and all(len(w) == i + 1 for w in words[i]) for i in range(10))
+    assert du.STAT_NAMES[:3] == ("r_loss_fake", "r_loss_real", "r_loss_balanced") and len(du.STAT_NAMES) == 16
