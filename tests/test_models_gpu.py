@@ -377,10 +377,10 @@ def test_train_shell_runs_on_synthetic_buckets(rt, tmp_path):
         du.train(dataset, G, D, R, None, gan, None, ckpt, g_opt, d_opt, r_opt, w_opt, None, seed_labels, 3, bs, 2, str(tmp_path / "model"),
                  128, out, loss_fn, disc_iters, agb, words, 3, char_vec)
         import os
-        lines = open(os.path.join(out, "batch_summary.txt")).read().strip().split("\\n")
+        lines = open(os.path.join(out, "batch_summary.txt")).read().strip().split("\n")
         assert lines[0].split(";")[:4] == ["disc_loss", "disc_loss_real", "disc_loss_fake", "r_loss_real"] and len(lines[0].split(";")) == 16
         assert len(lines) == 1 + 2 * 2 and all(len(l.split(";")) == 16 and all(np.isfinite(float(v)) for v in l.split(";")) for l in lines[1:])
-        assert len(open(os.path.join(out, "epoch_summary.txt")).read().strip().split("\\n")) == 1 + 2
+        assert len(open(os.path.join(out, "epoch_summary.txt")).read().strip().split("\n")) == 1 + 2
         assert os.path.exists(os.path.join(ckpt, "generator", "2", "cktp-2.npz")) and os.path.exists(os.path.join(ckpt, "recognizer", "1", "cktp-1.npz"))
         imgs = np.load(os.path.join(out, "image_at_epoch_0002.npy"))
         assert imgs.shape == (bs, 32, 48, 1) and imgs.min() >= 0.0 and imgs.max() <= 1.0
