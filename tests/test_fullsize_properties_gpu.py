@@ -1,0 +1,130 @@
+"""Size-independent properties checked at BASELINE.json's FULL sizes (where the fp64 oracle would take minutes):
+integer-valued operands make the bf16 tensor-core convolutions EXACT (products and fp32 partial sums are integers below 2^24),
+so linearity must hold bit for bit and spot checks against int64 arithmetic must match exactly; batch independence of D;
+softmax-gradient rows of the CTC gradient sum to zero; bit-exact filter-bank indexing at B=64, L=10."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ops = importlib.import_module("scrabble-gan_b200.ops")
+abi = importlib.import_module("scrabble-gan_b200._abi")
+na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+F32, BF16 = abi.SG_F32, abi.SG_BF16
+
+
+def _ints(rng, shape, lo, hi):
+    return torch.from_numpy(rng.randint(lo, hi + 1, size=shape).astype(np.float32))
+
+
+def test_largest_conv_is_exact_and_linear_on_integer_operands(rt):
+    """D.B3.conv2 on the fused [fake;real] batch: N=128, 8x20, 1024 -> 1024, 3x3 (M=20480, K=9216): forward, dgrad, wgrad."""
+    rt.set_mode("bf16")
+    try:
+        rng = np.random.RandomState(0)
+        n, h, w, c = 128, 8, 20, 1024
+        a, b = _ints(rng, (n, h, w, c), -2, 2), _ints(rng, (n, h, w, c), -2, 2)
+        wt = _ints(rng, (3, 3, c, c), -1, 1)
+        ad, bd, sd = (t.to(rt.device).to(torch.bfloat16) for t in (a, b, a + b))
+        wd = wt.to(rt.device)
+        d = ops.desc_conv_fwd(n, h, w, c, c, 3, 3, "same", BF16, F32)
+        wp = ops.pack_weights(rt, d, wd)
+        outs = []
+        for x in (ad, bd, sd):
+            o = rt.empty((n, h, w, c))
+            ops.conv_run(rt, d, x, wd, wp, None, None, o)
+            outs.append(o)
+        assert torch.equal(outs[0] + outs[1], outs[2]), "conv(a) + conv(b) != conv(a + b) on exactly representable operands"
+        # spot checks against int64 arithmetic (SAME padding: taps outside the image contribute 0)
+        A, W = a.to(torch.int64), wt.to(torch.int64)
+        got = outs[0].cpu()
+        for (ni, y, x_, co) in ((0, 0, 0, 0), (5, 3, 7, 100), (127, 7, 19, 1023), (64, 4, 0, 511), (17, 0, 19, 3)):
+            acc = 0
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    yy, xx = y + dy, x_ + dx
+                    if 0 <= yy < h and 0 <= xx < w:
+                        acc += int((A[ni, yy, xx] * W[dy + 1, dx + 1, :, co]).sum())
+            assert int(got[ni, y, x_, co]) == acc
+        # dgrad is the same kernel with the channel roles swapped: linear and exact as well
+        dd = ops.desc_conv_dgrad(n, h, w, c, c, 3, 3, "same", BF16, F32)
+        wpd = ops.pack_weights(rt, dd, wd)
+        gs = []
+        for x in (ad, bd, sd):
+            o = rt.empty((n, h, w, c))
+            ops.conv_run(rt, dd, x, wd, wpd, None, None, o)
+            gs.append(o)
+        assert torch.equal(gs[0] + gs[1], gs[2])
+        # filter gradient: dW[a,b,ci,co] = sum_pixels x[p + tap, ci] * dy[p, co]: exact integers (|sum| < 2^24)
+        dy = _ints(rng, (n, h, w, c), -1, 1)
+        dyd = dy.to(rt.device).to(torch.bfloat16)
+        dw = rt.zeros((3, 3, c, c))
+        dwg = ops.desc_conv_fwd(n, h, w, c, c, 3, 3, "same", BF16, BF16)
+        ops.conv_wgrad(rt, dwg, ad, dyd, dw)
+        dwc = dw.cpu()
+        DY = dy.to(torch.int64)
+        for (ta, tb, ci, co) in ((1, 1, 0, 0), (0, 0, 17, 900), (2, 2, 1023, 1023), (0, 2, 512, 1), (2, 1, 5, 640)):
+            dy_, dx_ = ta - 1, tb - 1
+            ys = slice(max(0, -dy_), h - max(0, dy_))          # output rows whose tap stays inside the image
+            xs = slice(max(0, -dx_), w - max(0, dx_))
+            xin = A[:, ys.start + dy_:ys.stop + dy_, xs.start + dx_:xs.stop + dx_, ci]
+            exp = int((xin * DY[:, ys, xs, co]).sum())
+            assert int(dwc[ta, tb, ci, co]) == exp
+    finally:
+        rt.set_mode("fp32")
+
+
+def test_discriminator_is_batch_independent_at_full_size(rt):
+    """D has no cross-sample coupling: logits of a 64-image batch == logits of its two halves (what the fused [fake;real]
+    pass and the data-parallel sharding rely on)."""
+    rt.set_mode("bf16")
+    try:
+        D = na.make_discriminator((32, 160, 1), None, "B1", vis_model=False, rt=rt, seed=7)
+        for v in D.store.vars:
+            if v.name.endswith(".sigma"):
+                v.assign(np.array([0.1], np.float32))
+        x = torch.from_numpy(np.random.RandomState(1).uniform(-1, 1, size=(64, 32, 80, 1)).astype(np.float32)).to(rt.device)
+        full, _ = D.forward(rt, x)
+        lo, _ = D.forward(rt, x[:32].contiguous())
+        hi, _ = D.forward(rt, x[32:].contiguous())
+        halves = torch.cat([lo.view(-1), hi.view(-1)])
+        scale = float(full.abs().max())
+        assert float((full.view(-1) - halves).abs().max()) <= 1e-5 * max(scale, 1.0)
+    finally:
+        rt.set_mode("fp32")
+
+
+def test_ctc_gradient_rows_sum_to_zero_at_config3_size(rt):
+    """BASELINE configs[2]: B=256, T=39, C=81, L=10.  d loss / d logits = (softmax - posterior): every frame's row sums to 0,
+    the loss is positive and finite, and shuffling the batch permutes the per-sample losses."""
+    rng = np.random.RandomState(2)
+    b, t, c, l = 256, 39, 81, 10
+    logits = torch.from_numpy((rng.standard_normal((b, t, c)) * 2).astype(np.float32)).to(rt.device)
+    labels = torch.from_numpy(rng.randint(0, c - 1, size=(b, l)).astype(np.int32)).to(rt.device)
+    loss, grad = ops.ctc(rt, logits, labels)
+    assert torch.isfinite(loss).all() and float(loss.min()) > 0
+    assert float(grad.sum(-1).abs().max()) <= 1e-4
+    perm = torch.from_numpy(rng.permutation(b)).to(rt.device)
+    loss_p, _ = ops.ctc(rt, logits[perm].contiguous(), labels[perm].contiguous())
+    assert torch.allclose(loss_p, loss[perm], rtol=1e-6, atol=1e-6)
+
+
+def test_filter_bank_indexing_is_bit_exact_at_full_size(rt):
+    """B=64, L=10, vocab 52: with a one-hot z the output must be single bank rows, unrounded, at
+    out[b, k%4, 4l + k//2048, (k%2048)//4] = bank[y[b,l], j, k]."""
+    rng = np.random.RandomState(3)
+    b, l, vocab, j = 64, 10, 52, 13
+    bank = torch.from_numpy(rng.standard_normal((vocab, 32, 8192)).astype(np.float32))
+    y = torch.from_numpy(rng.randint(0, vocab, size=(b, l)).astype(np.int32))
+    z = torch.zeros(b, 32)
+    z[:, j] = 1.0
+    out = ops.filterbank_fwd(rt, z.to(rt.device), 32, y.to(rt.device), bank.to(rt.device)).cpu()
+    rows = bank[y.long(), j]                                   # (b, l, 8192)
+    k = torch.arange(8192)
+    exp = torch.zeros(b, 4, 4 * l, 512)
+    for li in range(l):
+        exp[:, k % 4, 4 * li + k // 2048, (k % 2048) // 4] = rows[:, li]
+    assert torch.equal(out, exp)
