@@ -128,3 +128,61 @@ def test_filter_bank_indexing_is_bit_exact_at_full_size(rt):
     for li in range(l):
         exp[:, k % 4, 4 * li + k // 2048, (k % 2048) // 4] = rows[:, li]
     assert torch.equal(out, exp)
+
+
+def test_run_inference_path_accepts_a_15_character_word(rt):
+    """run_inference.py:27-35 encodes 'machinelearning' (15 characters > the training buckets) and calls the generator with
+    [noise, labels], training=False: the fully-convolutional G must take any length (32 x 240 image; the 7680 x 1920
+    attention map exceeds the tensor-op kernel's shared memory and takes the exact FFMA path in bf16 mode too)."""
+    char_vec = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    word = "machinelearning"
+    for mode in ("bf16", "fp32"):
+        rt.set_mode(mode)
+        try:
+            G = na.make_generator(128, (32, 160, 1), (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=5)
+            for v in G.store.vars:
+                if v.name.endswith(".sigma"):
+                    v.assign(np.array([0.2], np.float32))
+            labels = np.array([[char_vec.index(ch) for ch in word]] * 3, np.int32)
+            noise = np.random.RandomState(0).standard_normal((3, 128)).astype(np.float32)
+            img = G([noise, labels], training=False)
+            assert tuple(img.shape) == (3, 32, 16 * len(word), 1)
+            assert torch.isfinite(img).all() and float(img.min()) >= -1.0 and float(img.max()) <= 1.0
+            again = G([noise, labels], training=False)
+            assert torch.equal(img, again), "inference must be deterministic"
+            pred = ((img + 1) / 2.0).cpu().numpy()                 # run_inference.py:37
+            assert pred.min() >= 0.0 and pred.max() <= 1.0
+        finally:
+            rt.set_mode("fp32")
+
+
+def test_tf32_conv_is_exact_on_integer_operands(rt):
+    """Same exactness argument for the kind::tf32 path (fp32 storage): D.B2.conv2 shape, N=16, 16x40, 512 -> 512."""
+    rt.set_mode("tf32")
+    try:
+        rng = np.random.RandomState(4)
+        n, h, w, c = 16, 16, 40, 512
+        a, b = _ints(rng, (n, h, w, c), -3, 3), _ints(rng, (n, h, w, c), -3, 3)
+        wt = _ints(rng, (3, 3, c, c), -1, 1)
+        d = ops.desc_conv_fwd(n, h, w, c, c, 3, 3, "same", F32, F32)
+        assert ops.tc_ok(rt, d)
+        wd = wt.to(rt.device)
+        wp = ops.pack_weights(rt, d, wd)
+        outs = []
+        for x in (a, b, a + b):
+            o = rt.empty((n, h, w, c))
+            ops.conv_run(rt, d, x.to(rt.device), wd, wp, None, None, o)
+            outs.append(o)
+        assert torch.equal(outs[0] + outs[1], outs[2])
+        A, W = a.to(torch.int64), wt.to(torch.int64)
+        got = outs[0].cpu()
+        for (ni, y, x_, co) in ((0, 0, 0, 0), (15, 15, 39, 511), (7, 8, 20, 300)):
+            acc = 0
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    yy, xx = y + dy, x_ + dx
+                    if 0 <= yy < h and 0 <= xx < w:
+                        acc += int((A[ni, yy, xx] * W[dy + 1, dx + 1, :, co]).sum())
+            assert int(got[ni, y, x_, co]) == acc
+    finally:
+        rt.set_mode("fp32")
