@@ -186,3 +186,37 @@ def test_tf32_conv_is_exact_on_integer_operands(rt):
             assert int(got[ni, y, x_, co]) == acc
     finally:
         rt.set_mode("fp32")
+
+
+def test_fork_mode_step_at_the_gin_batch_size(rt):
+    """Mode B ("as-written fork": in-G style encoder on (32,160,1) style images + style promoter W) at the reference's own
+    configuration (scrabble_gan.gin: batch 16, hinge, words <= 10 characters): three steps run, every statistic is finite,
+    the optimizers of all four networks advance, and weights change."""
+    du = importlib.import_module("scrabble-gan_b200.bigacgan.data_utils")
+    nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+    optim = importlib.import_module("scrabble-gan_b200.optim")
+    rt.set_mode("bf16")
+    try:
+        in_dim = (32, 160, 1)
+        G = na.make_generator(128, in_dim, (32, 8192), None, "B3", 52, vis_model=False, style_encoder=True, rt=rt, seed=51)
+        D = na.make_discriminator(in_dim, None, "B1", vis_model=False, rt=rt, seed=52)
+        R = na.make_recognizer(in_dim, None, 53, vis_model=False, rt=rt, seed=53)
+        W = na.make_style_promoter(in_dim, None, "B1", vis_model=False, rt=rt, seed=54)
+        gan = na.make_gan(G, D, R, W, vis_model=False)
+        g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 0, 0)
+        rng = np.random.RandomState(6)
+        bs = 16
+        words = du.synthetic_random_words(10, "x" * 52, words_per_bucket=32, seed=1)
+        w0 = {n: m.store.w.clone() for n, m in (("G", G), ("D", D), ("R", R), ("W", W))}
+        for i, length in enumerate((5, 10, 3)):
+            imgs = rng.uniform(-1, 1, size=(bs, 32, 16 * length, 1)).astype(np.float32)
+            labels = rng.randint(0, 52, size=(bs, length)).astype(np.int32)
+            style = [rng.uniform(-1, 1, size=(32, 160)).astype(np.float32) for _ in range(bs)]       # list of B (32,160) images
+            out = du.train_step(0, i, 3, imgs, labels, D, R, W, gan, g_opt, d_opt, r_opt, w_opt, style, bs, 128, loss_fn, disc_iters,
+                                agb, words, 10, "")
+            assert len(out) == 16 and all(np.isfinite(v) for v in out), out
+        assert (g_opt.iterations, d_opt.iterations, r_opt.iterations, w_opt.iterations) == (3, 3, 3, 3)
+        for n, m in (("G", G), ("D", D), ("R", R), ("W", W)):
+            assert not torch.equal(m.store.w, w0[n]), n + " did not move"
+    finally:
+        rt.set_mode("fp32")
