@@ -16,13 +16,12 @@ from __future__ import annotations
 import os
 import random
 import time
-from typing import Optional
 
 import numpy as np
 import torch
 
 from .. import ops
-from .._abi import SG_F32, SG_LOSS_NSUMS, call
+from .._abi import SG_LOSS_NSUMS, call
 from ..ops import _p
 from ..runtime import Runtime, get_runtime
 from . import net_loss

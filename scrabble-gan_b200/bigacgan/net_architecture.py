@@ -23,7 +23,7 @@ import torch
 from .. import ops
 from .._abi import SG_F32, from_dlpack
 from ..layers import BatchNormState, ConvLayer, DenseLayer, batch_stats
-from ..params import ParamStore, init_glorot_uniform, init_orthogonal
+from ..params import ParamStore, init_glorot_uniform
 from ..runtime import Runtime, get_runtime
 from .arch_ops import NonLocalBlock, SpatialEmbedding
 from .resnet_ops import ResNetBlockDown, ResNetBlockUp

@@ -7,10 +7,6 @@ summed is fp32; tensors that are consumed only as convolution operands are writt
 dtype (bf16 in "bf16" mode) by the producing kernel's epilogue."""
 from __future__ import annotations
 
-from typing import Optional
-
-import torch
-
 from .. import ops
 from .._abi import SG_F32
 from ..layers import BatchNormState, ConvLayer, ConvTransposeLayer, DenseLayer, batch_stats

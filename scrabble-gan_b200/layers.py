@@ -10,8 +10,8 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import ops
-from ._abi import SG_BF16, SG_F32
-from .params import ParamStore, Variable, init_glorot_uniform, init_ones, init_orthogonal, init_zeros
+from ._abi import SG_F32
+from .params import ParamStore, Variable, init_ones, init_orthogonal, init_zeros
 from .runtime import Runtime, dt_of
 
 

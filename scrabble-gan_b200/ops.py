@@ -6,12 +6,12 @@ Nothing in this file computes on the host or with torch ops: every function is o
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 
 from . import _abi
-from ._abi import SG_BF16, SG_F32, ConvDesc, call, ptr
+from ._abi import SG_BF16, SG_F32, ConvDesc, call
 from .runtime import Runtime, dt_of
 
 _V = C.c_void_p

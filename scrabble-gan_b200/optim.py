@@ -15,7 +15,6 @@ import torch
 
 from . import ops
 from .params import ParamStore, Variable
-from .runtime import get_runtime
 
 
 class _FlatState:

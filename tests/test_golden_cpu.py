@@ -5,7 +5,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
