@@ -135,46 +135,64 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the torch-CPU restatement of the reference step
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(batch, length, steps, warmup, threads=None):
+def cpu_reference_step_time(batch, length, steps, warmup, threads=None, budget_s=None):
+    """Times the torch-CPU restatement of the reference step (oracle/sgan_oracle.py) on `threads` host threads.  With
+    `budget_s`, the sample batch is halved (from `batch`) until warmup + steps fit the budget, judged from one probe step at
+    batch 8.  Returns (seconds per step, threads, batch actually used)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sgan_oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     dt = torch.float32
-    g = torch.Generator().manual_seed(1234)
-    P = {"G": O.make_generator_params(1, dt), "D": O.make_discriminator_params(2, dt), "R": O.make_recognizer_params(3, dt)}
-    images = torch.rand(batch, 32, 16 * length, 1, generator=g) * 2 - 1
-    labels = torch.randint(0, 52, (batch, length), generator=g)
-    fake = torch.randint(0, 52, (batch, length), generator=g)
-    z = torch.randn(batch, 128, generator=g)
-    opt = {}
-    times = []
+    P0 = {"G": O.make_generator_params(1, dt), "D": O.make_discriminator_params(2, dt), "R": O.make_recognizer_params(3, dt)}
+
+    def data(b):
+        g = torch.Generator().manual_seed(1234)
+        return (torch.rand(b, 32, 16 * length, 1, generator=g) * 2 - 1, torch.randint(0, 52, (b, length), generator=g),
+                torch.randint(0, 52, (b, length), generator=g), torch.randn(b, 128, generator=g))
+
+    if budget_s is not None and batch > 8:
+        images, labels, fake, z = data(8)
+        O.train_step(P0, {}, images, labels, fake, z, loss_fn="hinge", apply_gradient_balance=True)       # page in / warm the allocator
+        t0 = time.perf_counter()
+        O.train_step(P0, {}, images, labels, fake, z, loss_fn="hinge", apply_gradient_balance=True)
+        per_img = (time.perf_counter() - t0) / 8
+        while batch > 8 and per_img * batch * (steps + warmup) > budget_s:
+            batch //= 2
+    images, labels, fake, z = data(batch)
+    P, opt, times = P0, {}, []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         _, P, opt = O.train_step(P, opt, images, labels, fake, z, loss_fn="hinge", apply_gradient_balance=True)
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
-    return sum(times) / len(times), threads
+    return sum(times) / len(times), threads, batch
 
 
 def run_reference_arm(args):
+    """The reference's own CPU path, timed on the box's host cores: rank 0 only.  The step runs at the arm's full per-GPU
+    batch when warmup + steps fit ~4 minutes (they do at the driver's 20 + 5 steps on 16 cores), else on the largest
+    power-of-two fraction of it that does; `same_config` / `cpu_baseline.sample` say which."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = args.ref_batch
-    t, threads = cpu_reference_step_time(sample_b, args.length, args.steps, max(args.warmup, 1))
+    warm = max(min(args.warmup, 2), 1)
+    want_b = args.ref_batch if args.ref_batch > 0 else args.batch
+    t, threads, sample_b = cpu_reference_step_time(want_b, args.length, args.steps, warm, budget_s=args.ref_budget_s)
     value = sample_b / t
+    same = sample_b == args.batch
     line = {"impl": "reference", "metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch, args.length), "batch_per_gpu": args.batch,
-                       "global_batch": args.batch * max(args.gpus, 1), "word_len": args.length,
-                       "parallelism": "host cores (rank 0 only)"},
+            "config": {"workload": workload_name(sample_b, args.length) + ("" if same else " [bounded CPU sample of the batch-%d workload]" % args.batch),
+                       "batch_per_gpu": sample_b, "global_batch": sample_b, "word_len": args.length,
+                       "parallelism": "host cores (rank 0 only; one CPU process whatever --gpus says)"},
+            "same_config": same,
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": "batch %d of the same 32x%d workload per step (torch-CPU restatement of the reference "
-                                       "step; TensorFlow is not installable here)" % (sample_b, 16 * args.length)},
+                             "sample": "batch %d per step of the 32x%d workload (torch-CPU fp32 restatement of the reference "
+                                       "step, oracle/sgan_oracle.py; TensorFlow is not installable here)" % (sample_b, 16 * args.length)},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -240,7 +258,9 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("SGAN_MODE", "bf16"), choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--length", type=int, default=5, help="word length (real and fake)")
-    ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample batch for the reference arm")
+    ap.add_argument("--ref-batch", type=int, default=0, help="CPU batch of the reference arm (0 = the arm's own --batch)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="the reference arm halves its batch until warmup+steps fit this")
+    ap.add_argument("--cpu-baseline-batch", type=int, default=16, help="bounded sample batch of the in-line cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="keep train_step eager (no CUDA-graph replay)")
     ap.add_argument("--workload", default="step", choices=["step", "inference", "recognizer"],
@@ -420,10 +440,10 @@ def main():
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                t, threads = cpu_reference_step_time(args.ref_batch, L, 1, 1)
-                line["cpu_baseline"] = {"value": args.ref_batch / t, "unit": "images/s", "cores": threads, "kind": "port",
-                                        "sample": "1 step at batch %d of the same 32x%d workload (torch-CPU restatement of the "
-                                                  "reference train step; TensorFlow is not installable here)" % (args.ref_batch, 16 * L)}
+                t, threads, cb = cpu_reference_step_time(args.cpu_baseline_batch, L, 2, 1)
+                line["cpu_baseline"] = {"value": cb / t, "unit": "images/s", "cores": threads, "kind": "port",
+                                        "sample": "2 steps at batch %d of the same 32x%d workload (torch-CPU restatement of the "
+                                                  "reference train step; TensorFlow is not installable here)" % (cb, 16 * L)}
             except Exception as ex:      # the baseline is a report, never a reason to lose the GPU numbers
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line), flush=True)

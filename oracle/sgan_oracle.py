@@ -31,6 +31,102 @@ import torch
 import torch.nn.functional as F
 
 Tensor = torch.Tensor
+
+# ----------------------------------------------------------------------------------------------------
+# OPERAND ROUNDING (test infrastructure for the reduced-precision modes of the CUDA path)
+# ----------------------------------------------------------------------------------------------------
+# With set_operand_rounding("bf16") the restatement rounds to bf16 at the points where the CUDA path STORES bf16
+# (scrabble-gan_b200 DESIGN.md section 3): the input activations, the filters and the upstream gradient of every
+# convolution that runs on the tensor cores, and the upstream gradient / bf16-stored activations of the Cin = 1 / Cout = 1
+# edge convolutions.  Accumulation stays in the oracle's dtype.  Because the ReLU / max-pool masks then come from the
+# same rounded operands as on the GPU, gradients can be compared at the bf16 tolerance of north_star (1e-2) instead of
+# at the mask-flip noise level of a comparison against exact arithmetic.  "tf32": the fp32-storage tensor-core mode --
+# the tensor-core convolutions read their fp32 operands as tf32 (low 13 mantissa bits dropped); `wgrad` says whether the
+# filter gradients run on tf32 tensor cores too (True) or in exact fp32.  None (default) = the exact restatement.
+_ROUND: Optional[str] = None
+_ROUND_WGRAD: bool = True
+
+
+def set_operand_rounding(mode: Optional[str], wgrad: bool = True) -> None:
+    global _ROUND, _ROUND_WGRAD
+    assert mode in (None, "bf16", "tf32"), mode
+    _ROUND, _ROUND_WGRAD = mode, bool(wgrad)
+
+
+def _q_tf32(t: Tensor) -> Tensor:
+    """fp32 -> tf32 as the tensor core reads it: the low 13 mantissa bits are dropped."""
+    f = t.to(torch.float32).contiguous()
+    return (f.view(torch.int32) & ~0x1FFF).view(torch.float32).to(t.dtype)
+
+
+def _q_bf16(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _q(t: Tensor) -> Tensor:
+    return _q_tf32(t) if _ROUND == "tf32" else _q_bf16(t)
+
+
+def _ste(t: Tensor, rounded: Tensor) -> Tensor:
+    """Value of `rounded`, gradient of `t` (rounding is transparent to the backward pass)."""
+    return t + (rounded - t).detach()
+
+
+class _RoundedBilinear(torch.autograd.Function):
+    """y = f(q(x), q(w));  dx, dw = vjp of f at (q(x), q(w)) with the upstream gradient rounded: exactly what a kernel
+    computes whose operands x, w and dy are stored in bf16 and whose accumulator is wide."""
+
+    @staticmethod
+    def forward(ctx, x, w, f, qx, qw, qdy, q_wgrad):
+        xq = _q(x) if qx else x
+        wq = _q(w) if qw else w
+        ctx.save_for_backward(x, xq, wq)
+        ctx.f, ctx.qdy, ctx.q_wgrad = f, qdy, q_wgrad
+        with torch.no_grad():
+            return f(xq, wq)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, xq, wq = ctx.saved_tensors
+        dyq = _q(dy) if ctx.qdy else dy
+        with torch.enable_grad():
+            if ctx.q_wgrad:
+                xr, wr = xq.detach().requires_grad_(True), wq.detach().requires_grad_(True)
+                dx, dw = torch.autograd.grad(ctx.f(xr, wr), (xr, wr), dyq)
+            else:      # input gradient from the rounded operands, filter gradient in exact arithmetic
+                wr = wq.detach().requires_grad_(True)
+                xr = xq.detach().requires_grad_(True)
+                dx, = torch.autograd.grad(ctx.f(xr, wq.detach()), (xr,), dyq)
+                dw, = torch.autograd.grad(ctx.f(x.detach(), wr), (wr,), dy)
+        return dx, dw, None, None, None, None, None
+
+
+def _rounding_flags(c_in: int, c_out: int):
+    """(round x, round w, round dy) of a convolution with these channel counts in the CUDA path's bf16 mode:
+    tensor-core eligible (c_in % 64 == 0 and c_out % 32 == 0): all three are bf16 operands; image-input edge layers
+    (c_in == 1): fp32 image and filter, bf16 upstream gradient; the 64 -> 1 output conv: bf16 activation, fp32 filter and
+    fp32 upstream gradient."""
+    if _ROUND == "tf32":       # fp32 storage everywhere: only the tensor-core layers (c_in % 32 == 0) see rounded operands
+        tc = c_in % 32 == 0 and c_out % 32 == 0
+        return tc, tc, tc
+    if c_in % 64 == 0 and c_out % 32 == 0:
+        return True, True, True
+    if c_out == 1:
+        return True, False, False
+    return False, False, True
+
+
+def _bilinear(f, x, w, c_in, c_out, flags=None):
+    if _ROUND is None:
+        return f(x, w)
+    if _ROUND == "tf32":
+        flags = None if flags is None else (False, False, False)      # the non-local block stays on exact FFMA kernels in tf32 mode
+    qx, qw, qdy = flags if flags is not None else _rounding_flags(c_in, c_out)
+    if not (qx or qw or qdy):
+        return f(x, w)
+    return _RoundedBilinear.apply(x, w, f, qx, qw, qdy, _ROUND_WGRAD)
+
+
 BN_EPS = 1e-3          # Keras BatchNormalization default epsilon
 BN_MOMENTUM = 0.99     # Keras BatchNormalization default momentum
 KERAS_EPS = 1e-7       # K.epsilon()
@@ -67,16 +163,20 @@ def _same_pad(n: int, k: int, s: int) -> Tuple[int, int]:
     return total // 2, total - total // 2
 
 
-def conv2d(x: Tensor, w: Tensor, b: Optional[Tensor] = None, padding: str = "same") -> Tensor:
-    """tf.keras.layers.Conv2D, stride 1.  x NHWC, w HWIO.  (resnet_ops.py:65,98,103,109; net_architecture.py:28-49)"""
+def conv2d(x: Tensor, w: Tensor, b: Optional[Tensor] = None, padding: str = "same", rounding=None) -> Tensor:
+    """tf.keras.layers.Conv2D, stride 1.  x NHWC, w HWIO.  (resnet_ops.py:65,98,103,109; net_architecture.py:28-49)
+    `rounding`: explicit (x, w, dy) operand-rounding flags for the rounded mode (default: by channel counts)."""
     kh, kw = w.shape[0], w.shape[1]
-    xt = x.permute(0, 3, 1, 2)
-    if padding == "same":
-        pt, pb = _same_pad(x.shape[1], kh, 1)
-        pl, pr = _same_pad(x.shape[2], kw, 1)
-        xt = F.pad(xt, (pl, pr, pt, pb))
-    y = F.conv2d(xt, w.permute(3, 2, 0, 1).contiguous(), b)
-    return y.permute(0, 2, 3, 1)
+
+    def f(x_, w_):
+        xt = x_.permute(0, 3, 1, 2)
+        if padding == "same":
+            pt, pb = _same_pad(x_.shape[1], kh, 1)
+            pl, pr = _same_pad(x_.shape[2], kw, 1)
+            xt = F.pad(xt, (pl, pr, pt, pb))
+        return F.conv2d(xt, w_.permute(3, 2, 0, 1).contiguous(), None).permute(0, 2, 3, 1)
+    y = _bilinear(f, x, w, w.shape[2], w.shape[3], rounding)
+    return y if b is None else y + b
 
 
 def conv2d_transpose(x: Tensor, w: Tensor, b: Optional[Tensor], strides: Tuple[int, int]) -> Tensor:
@@ -89,18 +189,20 @@ def conv2d_transpose(x: Tensor, w: Tensor, b: Optional[Tensor], strides: Tuple[i
     kh, kw = w.shape[0], w.shape[1]
     sh, sw = strides
     n_h, n_w = x.shape[1], x.shape[2]
-    full = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1).contiguous(), None, stride=(sh, sw), padding=0)
-    pb_h, _ = _same_pad(n_h * sh, kh, sh)
-    pb_w, _ = _same_pad(n_w * sw, kw, sw)
-    y = full[:, :, pb_h:pb_h + n_h * sh, pb_w:pb_w + n_w * sw]
-    # the full transposed conv can be shorter than pb + n*s when k < s (1x1 stride 2): pad with zeros at the end
-    ph = n_h * sh - y.shape[2]
-    pw = n_w * sw - y.shape[3]
-    if ph > 0 or pw > 0:
-        y = F.pad(y, (0, pw, 0, ph))
-    if b is not None:
-        y = y + b.view(1, -1, 1, 1)
-    return y.permute(0, 2, 3, 1)
+
+    def f(x_, w_):
+        full = F.conv_transpose2d(x_.permute(0, 3, 1, 2), w_.permute(3, 2, 0, 1).contiguous(), None, stride=(sh, sw), padding=0)
+        pb_h, _ = _same_pad(n_h * sh, kh, sh)
+        pb_w, _ = _same_pad(n_w * sw, kw, sw)
+        y_ = full[:, :, pb_h:pb_h + n_h * sh, pb_w:pb_w + n_w * sw]
+        # the full transposed conv can be shorter than pb + n*s when k < s (1x1 stride 2): pad with zeros at the end
+        ph = n_h * sh - y_.shape[2]
+        pw = n_w * sw - y_.shape[3]
+        if ph > 0 or pw > 0:
+            y_ = F.pad(y_, (0, pw, 0, ph))
+        return y_.permute(0, 2, 3, 1)
+    y = _bilinear(f, x, w, w.shape[3], w.shape[2])
+    return y if b is None else y + b
 
 
 def avg_pool_2x2_same(x: Tensor) -> Tensor:
@@ -188,12 +290,19 @@ def non_local_block(x, p, pre: str):
     """NonLocalBlock.call (arch_ops.py:32-67) with persistent theta/phi/g/o kernels (deviation D2, Q4).
     No 1/sqrt(d) scaling; softmax over the (max-pooled) key axis."""
     n, h, w, c = x.shape
-    theta = conv2d(x, p[pre + ".theta.w"]).reshape(n, h * w, c // 8)
-    phi = max_pool(conv2d(x, p[pre + ".phi.w"]), 2, 2).reshape(n, -1, c // 8)
-    attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
-    g = max_pool(conv2d(x, p[pre + ".g.w"]), 2, 2).reshape(n, -1, c // 2)
+    rb = (True, True, True)      # speed mode: the four 1x1 projections run on bf16 warp-level tensor ops, fwd and bwd
+    theta = conv2d(x, p[pre + ".theta.w"], rounding=rb).reshape(n, h * w, c // 8)
+    phi = max_pool(conv2d(x, p[pre + ".phi.w"], rounding=rb), 2, 2).reshape(n, -1, c // 8)
+    g = max_pool(conv2d(x, p[pre + ".g.w"], rounding=rb), 2, 2).reshape(n, -1, c // 2)
+    if _ROUND == "bf16":
+        # the speed-mode attention kernels: S = theta phi^T on tf32 operands, P g on bf16 operands (fp32 softmax between)
+        theta, phi = _ste(theta, _q_tf32(theta)), _ste(phi, _q_tf32(phi))
+        attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+        attn, g = _ste(attn, _q_bf16(attn)), _ste(g, _q_bf16(g))
+    else:
+        attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
     attn_g = (attn @ g).reshape(n, h, w, c // 2)
-    attn_g = conv2d(attn_g, p[pre + ".o.w"])
+    attn_g = conv2d(attn_g, p[pre + ".o.w"], rounding=rb)
     return p[pre + ".sigma"] * attn_g + x
 
 

@@ -79,6 +79,8 @@ class _GraphedStep:
         self.versions = None
         self.failed = False
         self.launches = 0           # libsgan kernel nodes in the graph
+        self.owners = None          # strong references to the models / optimizers the key's id()s stand for: an id can
+                                    # only be recycled after the object dies, and the graph's kernels point at its buffers
 
 
 def _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, balance, update_g):
@@ -173,6 +175,10 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
         for st in stores:
             if rt.mode == "bf16" and rt.use_direct:
                 st.mirror(rt)                                   # fresh mirrors: no cast gets captured
+        # optimizer state must exist BEFORE the capture: created inside it, the (m, v) slots would live in the graph's
+        # private pool and their zero-fill would become a graph node (re-zeroing them on every replay)
+        for o, st in ((opts[1], stores[0]), (opts[2], stores[1]), (opts[0], stores[2])):
+            o.ensure_state(st)
         static = (rt.empty((b, 32, 16 * l_r, 1)), torch.zeros((b, l_r), device=rt.device, dtype=torch.int32),
                   torch.zeros((b, l_f), device=rt.device, dtype=torch.int32), rt.empty((b, latent_dim)))
         for t in static:
@@ -191,6 +197,7 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
         roll_back()
         gs.graph, gs.static, gs.stats = graph, static, stats
         gs.versions = [st.version for st in stores]
+        gs.owners = (discriminator, recognizer, generator, opts)
     except Exception as ex:      # noqa: BLE001 -- capture is an optimisation: on any failure stay on the eager path
         import sys
         rt.use_current_stream()
@@ -216,11 +223,23 @@ def _replay(rt, gs, args, images, labels, fake_labels, noise):
         z_s.copy_(_as_tensor(noise, np.float32), non_blocking=True)
     else:
         z_s.normal_()
-    used = [opts[1], opts[2]] + ([opts[0]] if update_g else [])
-    for o in used:
-        o.advance_for_replay()
+    used = [(opts[1], stores[0]), (opts[2], stores[1])] + ([(opts[0], stores[2])] if update_g else [])
+    for o, _ in used:
+        o.advance_for_replay(rt)
     gs.graph.replay()
     rt.replayed_launches += gs.launches
+    # Python-side state the captured body would have advanced (the reference flips these flags at data_utils.py:449-466):
+    # the Keras `trainable` flags as _step_device leaves them, and one store version per captured optimizer launch -- the
+    # packed-filter caches of the layers key on it, so eager code after a replay re-packs from the CURRENT weights.  The
+    # captured Adam launch wrote the bf16 mirror in the same pass, so the mirror stays in sync with the new version.
+    discriminator.trainable = recognizer.trainable = not update_g
+    for i, st in enumerate(stores):
+        if any(s_ is st for _, s_ in used):
+            mirror_current = st.wb is not None and st.wb_version == st.version
+            st.version += 1
+            if mirror_current:
+                st.wb_version = st.version
+            gs.versions[i] = st.version
     return gs.stats
 
 

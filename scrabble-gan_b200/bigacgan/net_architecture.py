@@ -173,13 +173,13 @@ class Discriminator(_Model):
     """make_discriminator / make_style_promoter: 4x ResNetBlockDown (64,512,1024,1024), NonLocalBlock after the
     blocks named in `blocks_with_attention`, ReLU, global average pool, Dense(1024 -> 1, no bias)."""
 
-    def __init__(self, rt, input_dim, kernel_reg, blocks_with_attention, name="discriminator", seed=1):
+    def __init__(self, rt, input_dim, kernel_reg, blocks_with_attention, name="discriminator", seed=1, initialise=True):
         super().__init__(rt, name, seed)
         h, w, c = input_dim
         self.kernel_reg = kernel_reg
         self.trunk = _DownTrunk(self.store, "B", c, h, lambda nm: nm in blocks_with_attention)
         self.dense = DenseLayer(self.store, "dense", self.trunk.out_channels, 1)
-        self.store.finalize()
+        self.store.finalize(initialise)
 
     def forward(self, rt, x):
         feats, c = self.trunk.forward(rt, x)
@@ -213,7 +213,7 @@ class Recognizer(_Model):
     initialisers (glorot-uniform, zero bias).  BatchNorm runs in inference mode (`bn_training=False`) exactly as in
     the reference's train_step, where R.trainable is False during every forward pass."""
 
-    def __init__(self, rt, input_dim, sequence_length, output_classes, name="recognizer", seed=3):
+    def __init__(self, rt, input_dim, sequence_length, output_classes, name="recognizer", seed=3, initialise=True):
         super().__init__(rt, name, seed)
         h, w, c = input_dim
         assert h == 32, "the CRNN collapses exactly 32 rows to 1"
@@ -227,7 +227,7 @@ class Recognizer(_Model):
         self.bn6 = BatchNormState(self.store, "bn6", 512, affine=True)
         self.dense = DenseLayer(self.store, "dense", 512, output_classes, use_bias=True, init=init_glorot_uniform)
         self.bn_training = False
-        self.store.finalize()
+        self.store.finalize(initialise)
 
     def _bn_forward(self, rt, x, bn: BatchNormState, out_dt):
         if self.bn_training:
@@ -349,7 +349,7 @@ class Generator(_Model):
     style_encoder=True, [style images (B,32,160,1), y] as in this fork."""
 
     def __init__(self, rt, latent_dim, input_dim, embed_y, kernel_reg, blocks_with_attention, vocab_size,
-                 style_encoder: bool = False, name="generator", seed=2):
+                 style_encoder: bool = False, name="generator", seed=2, initialise=True):
         super().__init__(rt, name, seed)
         h, w, c = input_dim
         in_ch, out_ch = get_in_out_channels_gen(h)
@@ -372,7 +372,7 @@ class Generator(_Model):
         if style_encoder:
             self.style = _DownTrunk(self.store, "B_style", c, h, lambda nm: nm == "B_style1")
             self.style_dense = DenseLayer(self.store, "style_dense", self.style.out_channels, latent_dim)
-        self.store.finalize()
+        self.store.finalize(initialise)
 
     def forward(self, rt, z_or_imgs, y, training: bool = True, img_out=None):
         sc = None
@@ -468,31 +468,35 @@ class CompositeGAN(_Model):
 # ----------------------------------------------------------------------------------------------------
 # builders
 # ----------------------------------------------------------------------------------------------------
-def make_recognizer(input_dim, sequence_length, output_classes, vis_model=True, rt: Optional[Runtime] = None, seed: int = 3):
-    m = Recognizer(rt or get_runtime(), input_dim, sequence_length, output_classes, seed=seed)
+def make_recognizer(input_dim, sequence_length, output_classes, vis_model=True, rt: Optional[Runtime] = None, seed: int = 3,
+                    initialise: bool = True):
+    """`initialise=False` (keyword extension, all builders): skip the random initialisation when the caller loads weights."""
+    m = Recognizer(rt or get_runtime(), input_dim, sequence_length, output_classes, seed=seed, initialise=initialise)
     if vis_model:
         m.summary()
     return m
 
 
 def make_generator(latent_dim, input_dim, embed_y, kernel_reg, blocks_with_attention, vocab_size, vis_model=True,
-                   style_encoder: bool = False, rt: Optional[Runtime] = None, seed: int = 2):
+                   style_encoder: bool = False, rt: Optional[Runtime] = None, seed: int = 2, initialise: bool = True):
     m = Generator(rt or get_runtime(), latent_dim, input_dim, embed_y, kernel_reg, blocks_with_attention, vocab_size,
-                  style_encoder=style_encoder, seed=seed)
+                  style_encoder=style_encoder, seed=seed, initialise=initialise)
     if vis_model:
         m.summary()
     return m
 
 
-def make_discriminator(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 1):
-    m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "discriminator", seed)
+def make_discriminator(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 1,
+                       initialise: bool = True):
+    m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "discriminator", seed, initialise)
     if vis_model:
         m.summary()
     return m
 
 
-def make_style_promoter(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 4):
-    m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "style_promoter", seed)
+def make_style_promoter(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 4,
+                        initialise: bool = True):
+    m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "style_promoter", seed, initialise)
     if vis_model:
         m.summary()
     return m

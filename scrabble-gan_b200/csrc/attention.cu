@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_bwd_kv(const float* __restr
                                                              const float* __restrict__ g, const float* __restrict__ o,
                                                              const float* __restrict__ lse, const float* __restrict__ d_o,
                                                              int Q, int KV, int q_per_split, float* __restrict__ dphi,
-                                                             float* __restrict__ dg) {
+                                                             float* __restrict__ dg, unsigned int* __restrict__ sems) {
   __shared__ __align__(16) float qs[AT_QT * AT_DK];
   __shared__ __align__(16) float dos[AT_QT * AT_DV];
   __shared__ float ls[AT_QT], Ds[AT_QT];
@@ -223,11 +223,21 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_bwd_kv(const float* __restr
       dk[4] = fmaf(ds, b.x, dk[4]); dk[5] = fmaf(ds, b.y, dk[5]); dk[6] = fmaf(ds, b.z, dk[6]); dk[7] = fmaf(ds, b.w, dk[7]);
     }
   }
+  // the q-splits of a key block add in split order (ordered turns, common.cuh scheme A): bitwise repeatable
+  unsigned int* sem = sems + (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if (gridDim.z > 1) {
+    if (threadIdx.x == 0) sg_turn_wait(sem, blockIdx.z);
+    __syncthreads();
+  }
   if (valid) {
 #pragma unroll
     for (int j = 0; j < AT_DK; ++j) atomicAdd(dphi + krow * AT_DK + j, dk[j]);
 #pragma unroll
     for (int j = 0; j < AT_DV; ++j) atomicAdd(dg + krow * AT_DV + j, dv[j]);
+  }
+  if (gridDim.z > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) sg_turn_pass(sem, blockIdx.z, gridDim.z);
   }
 }
 
@@ -261,10 +271,11 @@ int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
   int max_splits = sg_div_up(q, 4 * AT_QT);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
+  if ((long long)kblocks * n > SG_DET_TICKETS) splits = 1;
   int qps = sg_div_up(sg_div_up(q, splits), AT_QT) * AT_QT;
   splits = sg_div_up(q, qps);
   dim3 g2(kblocks, n, splits);
-  k_attn_bwd_kv<<<g2, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, o, lse, d_o, q, kv, qps, dphi, dg);
+  k_attn_bwd_kv<<<g2, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, o, lse, d_o, q, kv, qps, dphi, dg, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

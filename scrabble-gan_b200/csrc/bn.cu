@@ -110,7 +110,8 @@ template <typename TA>
 __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restrict__ act, const float* __restrict__ x,
                                 long long hw, int c, int tc, int lanes, long long rows_per_block,
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                float* __restrict__ s1, float* __restrict__ s2) {
+                                float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ scratch,
+                                unsigned int* __restrict__ tickets) {
   extern __shared__ float sm[];     // [lanes][2*c]
   int ni = blockIdx.y;
   int q = threadIdx.x % tc, lane = threadIdx.x / tc;
@@ -137,11 +138,24 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restri
     sg_st4(row + c + 4 * q, b);
   }
   __syncthreads();
+  // deterministic combine over the gridDim.x row slabs of sample ni (common.cuh, scheme B); s1 / s2 are overwritten
+  float* slots = scratch + (long long)ni * gridDim.x * 2 * c;
   for (int j = threadIdx.x; j < 2 * c; j += blockDim.x) {
     float t = 0.f;
     for (int l = 0; l < lanes; ++l) t += sm[(long long)l * 2 * c + j];
-    if (j < c) atomicAdd(s1 + (long long)ni * c + j, t);
-    else atomicAdd(s2 + (long long)ni * c + (j - c), t);
+    if (gridDim.x == 1) {
+      if (j < c) s1[(long long)ni * c + j] = t;
+      else s2[(long long)ni * c + (j - c)] = t;
+    } else {
+      slots[(long long)blockIdx.x * 2 * c + j] = t;
+    }
+  }
+  if (gridDim.x == 1) return;
+  if (!sg_det_arrive_last(tickets + ni, gridDim.x)) return;
+  for (int j = threadIdx.x; j < 2 * c; j += blockDim.x) {
+    float t = sg_det_sum(slots, gridDim.x, 2 * c, j);
+    if (j < c) s1[(long long)ni * c + j] = t;
+    else s2[(long long)ni * c + (j - c)] = t;
   }
 }
 
@@ -297,13 +311,18 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
                      int c, const float* mean, const float* rstd, float* s1, float* s2) {
   SG_REQUIRE(ctx && dy && x && mean && rstd && s1 && s2, "sg_bn_bwd_reduce: NULL");
   SG_REQUIRE(c % 4 == 0 && c >= 4 && c <= 1024, "sg_bn_bwd_reduce: c=%d must be a multiple of 4 in [4,1024]", c);
-  SG_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)n * c, ctx->stream));
-  SG_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)n * c, ctx->stream));
-  if ((long long)n * hw == 0) return SG_OK;
+  if ((long long)n * hw == 0) {
+    SG_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)n * c, ctx->stream));
+    SG_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)n * c, ctx->stream));
+    return SG_OK;
+  }
+  SG_REQUIRE(n <= SG_DET_TICKETS, "sg_bn_bwd_reduce: batch %d too large", n);
   BnLayout l = bn_layout(c);
   long long blocks = ((long long)ctx->num_sms * 4 + n - 1) / n;
   long long min_rows = 4LL * l.lanes;
   if (blocks > (hw + min_rows - 1) / min_rows) blocks = (hw + min_rows - 1) / min_rows;
+  long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / ((long long)n * 2 * c);      // per-block partial slots
+  if (blocks > fit) blocks = fit;
   if (blocks < 1) blocks = 1;
   long long rpb = (hw + blocks - 1) / blocks;
   blocks = (hw + rpb - 1) / rpb;
@@ -311,9 +330,11 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
   dim3 grid((unsigned)blocks, (unsigned)n);
   if (act) {
     SG_DISPATCH_DT(act_dt, TA,
-                   k_bn_bwd_reduce<TA><<<grid, 256, smem, ctx->stream>>>(dy, (const TA*)act, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2));
+                   k_bn_bwd_reduce<TA><<<grid, 256, smem, ctx->stream>>>(dy, (const TA*)act, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2,
+                                                                         ctx->det_scratch, ctx->det_tickets));
   } else {
-    k_bn_bwd_reduce<float><<<grid, 256, smem, ctx->stream>>>(dy, nullptr, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2);
+    k_bn_bwd_reduce<float><<<grid, 256, smem, ctx->stream>>>(dy, nullptr, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2, ctx->det_scratch,
+                                                             ctx->det_tickets);
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;

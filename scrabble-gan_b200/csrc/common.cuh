@@ -16,7 +16,12 @@ struct sg_ctx {
   void* encode_tiled;        // PFN cuTensorMapEncodeTiled (resolved lazily)
   long long launches;        // number of kernels launched through this context
   int speed_mode;            // 1: bf16 speed mode -- small fp32 GEMMs of the non-local block use bf16 warp-level tensor ops
+  // fixed workspace of the deterministic cross-block reductions (allocated once by sg_ctx_create, see sg_det_* below):
+  float* det_scratch;        // SG_DET_SCRATCH_BYTES of per-block partial sums
+  unsigned int* det_tickets; // SG_DET_TICKETS arrival counters / turn semaphores, all zero between launches
 };
+#define SG_DET_SCRATCH_BYTES (16u << 20)
+#define SG_DET_TICKETS 16384
 
 void sg_set_error(const char* fmt, ...);
 
@@ -102,6 +107,54 @@ __device__ __forceinline__ float sg_block_sum(float v, float* smem32) {
   }
   __syncthreads();
   return smem32[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Deterministic cross-block reductions.  Floating-point atomics make a sum depend on the arrival order of the blocks;
+// the two schemes below fix the order, so that gradients are bitwise repeatable from run to run.
+//   (B) partials + last block: every block of a group stores its partial vector in its own scratch slot, takes a ticket,
+//       and the block that arrives LAST sums the slots in block-index order (whichever block that is, the order of the
+//       additions is the same).  Used where the output is small and many blocks contribute (bias / BN sums, dot, ...).
+//   (A) ordered turns: split s of an output tile waits until splits 0..s-1 have added their partial tiles (a semaphore per
+//       tile), then adds its own.  A waiting block only ever waits on blocks with a LOWER linear block index (dispatched
+//       before it; in the persistent tensor-core kernel: on units processed earlier), so the wait always ends.  Used for
+//       the filter-gradient kernels (large output tiles, few splits).
+// Tickets / semaphores are left at zero by the last arrival, so launches on one stream can share them.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sg_det_arrive_last(unsigned int* ticket, unsigned int nblk) {
+  __shared__ unsigned int s_last;
+  __threadfence();                    // this block's partials are visible device-wide before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == nblk - 1) ? 1u : 0u;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  const bool last = s_last != 0u;
+  if (last) __threadfence();
+  return last;
+}
+// sum over the nblk slots (slot stride `n` floats) of element j, in slot order; L2 loads (the slots were written by other SMs)
+__device__ __forceinline__ float sg_det_sum(const float* slots, unsigned int nblk, long long n, long long j) {
+  float t = 0.f;
+  for (unsigned int b = 0; b < nblk; ++b) t += __ldcg(slots + (long long)b * n + j);
+  return t;
+}
+__device__ __forceinline__ void sg_turn_wait(unsigned int* sem, unsigned int turn) {
+  if (turn == 0) return;
+  unsigned int v, spins = 0;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sem) : "memory");
+    if (v == turn) break;
+    if (++spins > (1u << 26)) __trap();      // a protocol bug must fault, never hang the GPU
+    __nanosleep(64);
+  } while (true);
+}
+__device__ __forceinline__ void sg_turn_pass(unsigned int* sem, unsigned int turn, unsigned int nturns) {
+  unsigned int next = (turn + 1 == nturns) ? 0u : turn + 1;      // the last turn leaves the semaphore at zero
+  __threadfence();
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sem), "r"(next) : "memory");
 }
 
 #define SG_DISPATCH_DT(dt, T, ...)                              \

@@ -127,11 +127,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(sg_conv_desc d, const voi
 
 // ---------------------------------------------------------------------------------------------------
 // filter gradient.  M' = ntaps*c_in (flattened k index), N = c_out, reduction over output positions,
-// split across gridDim.z with atomicAdd into dw (dw is accumulated into: caller zeroes it).
+// split across gridDim.z; the splits of a tile add into dw in split order (ordered turns, common.cuh scheme A), so the
+// result is bitwise repeatable (dw is accumulated into: caller zeroes it).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const void* __restrict__ in,
                                                           const void* __restrict__ dy, float* __restrict__ dw,
-                                                          long long pos_per_split) {
+                                                          long long pos_per_split, unsigned int* __restrict__ sems) {
   __shared__ float As[CS_TK][CS_TM + 4];   // [pos][kflat]
   __shared__ float Bs[CS_TK][64 + 4];      // [pos][co]
   const int tid = threadIdx.x;
@@ -207,6 +208,11 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const v
     }
     __syncthreads();
   }
+  unsigned int* sem = sems + (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if (gridDim.z > 1) {
+    if (tid == 0) sg_turn_wait(sem, blockIdx.z);
+    __syncthreads();
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int kf = kf0 + ty * 4 + i;
@@ -218,6 +224,10 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const v
       if (gn >= d.c_out) continue;
       atomicAdd(dw + d.tap_w_off[t] + (long long)ci * d.w_ci_stride + (long long)gn * d.w_co_stride, acc[i][j]);
     }
+  }
+  if (gridDim.z > 1) {
+    __syncthreads();
+    if (tid == 0) sg_turn_pass(sem, blockIdx.z, gridDim.z);
   }
 }
 
@@ -241,7 +251,8 @@ __device__ __forceinline__ Pix decode_pix(long long p, int gh, int gw) {
 //   !NARROW_IN (c_out == 1): dW[t][ci] += sum_p in[p + tap_t, ci] * dy[p]     thread <-> ci
 template <bool NARROW_IN>
 __global__ void __launch_bounds__(256) k_wgrad_narrow(sg_conv_desc d, const void* __restrict__ in, const void* __restrict__ dy,
-                                                       float* __restrict__ dw, long long pos_per_block) {
+                                                       float* __restrict__ dw, long long pos_per_block, float* __restrict__ scratch,
+                                                       unsigned int* __restrict__ ticket) {
   extern __shared__ float red[];                       // [lanes][ntaps][wide]
   const int wide = NARROW_IN ? d.c_out : d.c_in;
   const int lanes = 256 / wide;
@@ -274,12 +285,19 @@ __global__ void __launch_bounds__(256) k_wgrad_narrow(sg_conv_desc d, const void
       if (t < d.ntaps) red[((long long)lane * d.ntaps + t) * wide + ch] = acc[t];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d.ntaps * wide; i += 256) {
+  // deterministic combine (common.cuh, scheme B): per-block partial filters, summed in block order by the last block
+  const int nout = d.ntaps * wide;
+  for (int i = threadIdx.x; i < nout; i += 256) {
     int t = i / wide, c = i % wide;
     float sum = 0.f;
     for (int l = 0; l < lanes; ++l) sum += red[((long long)l * d.ntaps + t) * wide + c];
+    scratch[(long long)blockIdx.x * nout + i] = sum;
+  }
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  for (int i = threadIdx.x; i < nout; i += 256) {
+    int t = i / wide, c = i % wide;
     long long off = d.tap_w_off[t] + (NARROW_IN ? (long long)c * d.w_co_stride : (long long)c * d.w_ci_stride);
-    atomicAdd(dw + off, sum);
+    dw[off] += sg_det_sum(scratch, gridDim.x, nout, i);
   }
 }
 
@@ -365,7 +383,7 @@ template <typename TW>
 __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ wide, const void* __restrict__ narrow, int narrow_dt,
                                                          int n, int H, int W, int nH, int nW, int ntaps, sg_conv_desc d,
                                                          int sign, float* __restrict__ dw, long long chunks_per_block,
-                                                         int narrow_in) {
+                                                         int narrow_in, float* __restrict__ scratch, unsigned int* __restrict__ ticket) {
   __shared__ float Bs[WN_PIX][64];
   __shared__ __align__(16) float As[9][WN_PIX];
   const int tid = threadIdx.x;
@@ -413,13 +431,17 @@ __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ w
       }
     }
   }
+  // deterministic combine (common.cuh, scheme B): slot = [9 taps][64 channels] per block
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     int t = 3 * tg + j;
-    if (t < ntaps) {
-      long long off = d.tap_w_off[t] + (narrow_in ? (long long)c * d.w_co_stride : (long long)c * d.w_ci_stride);
-      atomicAdd(dw + off, acc[j]);
-    }
+    if (t < 9) scratch[(long long)blockIdx.x * 576 + t * 64 + c] = (t < ntaps) ? acc[j] : 0.f;
+  }
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  for (int i = tid; i < ntaps * 64; i += 192) {
+    int t = i >> 6, cc = i & 63;
+    long long off = d.tap_w_off[t] + (narrow_in ? (long long)cc * d.w_co_stride : (long long)cc * d.w_ci_stride);
+    dw[off] += sg_det_sum(scratch, gridDim.x, 576, i);
   }
 }
 
@@ -589,11 +611,12 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
         blocks = (nchunks + cpb - 1) / cpb;
         if (wide_dt == SG_F32)
           k_wgrad_narrow64<float><<<(int)blocks, 192, 0, ctx->stream>>>((const float*)wide, nar, nar_dt, d->n, H, W, nH, nW, d->ntaps, *d,
-                                                                       narrow_in ? 1 : -1, dw_master, cpb, narrow_in ? 1 : 0);
+                                                                       narrow_in ? 1 : -1, dw_master, cpb, narrow_in ? 1 : 0,
+                                                                       ctx->det_scratch, ctx->det_tickets);
         else
           k_wgrad_narrow64<__nv_bfloat16><<<(int)blocks, 192, 0, ctx->stream>>>((const __nv_bfloat16*)wide, nar, nar_dt, d->n, H, W, nH,
                                                                                nW, d->ntaps, *d, narrow_in ? 1 : -1, dw_master, cpb,
-                                                                               narrow_in ? 1 : 0);
+                                                                               narrow_in ? 1 : 0, ctx->det_scratch, ctx->det_tickets);
         SG_POST_LAUNCH(ctx);
         return SG_OK;
       }
@@ -607,8 +630,8 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
       long long ppb = (P + blocks - 1) / blocks;
       blocks = (P + ppb - 1) / ppb;
       size_t smem = sizeof(float) * (size_t)lanes * d->ntaps * wide;
-      if (narrow_in) k_wgrad_narrow<true><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb);
-      else k_wgrad_narrow<false><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb);
+      if (narrow_in) k_wgrad_narrow<true><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
+      else k_wgrad_narrow<false><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
       SG_POST_LAUNCH(ctx);
       return SG_OK;
     }
@@ -620,10 +643,11 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
+  if (tiles > SG_DET_TICKETS) splits = 1;      // no turn semaphores for that many tiles: one block per tile
   long long pps = ((P + splits - 1) / splits + CS_TK - 1) / CS_TK * CS_TK;
   splits = (P + pps - 1) / pps;
   dim3 grid(gx, gy, (unsigned)splits);
-  k_conv_wgrad_simt<<<grid, 256, 0, ctx->stream>>>(*d, in, dy, dw_master, pps);
+  k_conv_wgrad_simt<<<grid, 256, 0, ctx->stream>>>(*d, in, dy, dw_master, pps, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -427,6 +427,7 @@ struct alignas(64) TcWgradParams {
   int a_chunks, b_chunks, stages;
   uint32_t chunk_bytes, stage_stride;
   float* dw;
+  unsigned int* sems;           // one turn semaphore per (tap, co tile, ci tile): the pixel splits of a tile add in split order
 };
 
 template <typename TIn>
@@ -540,8 +541,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     const int row = quarter * 32 + lane;           // accumulator row = output channel inside the co tile
     int as = 0;
     uint32_t aph = 0;
+    const int base_units = p.ntaps * p.co_tiles * p.ci_tiles;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int r = u % (p.ntaps * p.co_tiles * p.ci_tiles);
+      const int tile = u % base_units, sp = u / base_units;
+      int r = tile;
       int cit = r % p.ci_tiles; r /= p.ci_tiles;
       int cot = r % p.co_tiles;
       int t = r / p.co_tiles;
@@ -550,6 +553,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       float* wbase = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
+      // Deterministic split combine (common.cuh, scheme A): the pixel splits of one filter tile add their partial tiles in
+      // split order.  Unit (tile, sp) only waits on unit (tile, sp - 1), which has a lower unit index: it was taken earlier
+      // by its CTA (static round-robin, every CTA walks its units in increasing order), so the wait always ends.
+      if (p.splits > 1) {
+        if (threadIdx.x == 64) sg_turn_wait(p.sems + tile, (unsigned int)sp);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
       for (int ch = 0; ch < p.BN / 32; ++ch) {
         uint32_t v[32];
@@ -562,6 +572,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
             if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, __uint_as_float(v[j]));
           }
         }
+      }
+      if (p.splits > 1) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) sg_turn_pass(p.sems + tile, (unsigned int)sp, (unsigned int)p.splits);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * as);
@@ -972,7 +986,7 @@ int sg_conv_fwd_tc_direct(sg_ctx* ctx, const sg_conv_desc* d, const void* in, co
 
 size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms) {
   (void)d; (void)num_sms;
-  return 0;      // split partials are combined with red.global.add.f32 straight into dw: no workspace
+  return 0;      // split partials are added straight into dw in split order (turn semaphores in the context): no workspace
 }
 
 int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, void* workspace,
@@ -1000,6 +1014,7 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   p.ntaps = d->ntaps; p.c_in = d->c_in; p.c_out = d->c_out;
   p.w_ci_stride = d->w_ci_stride; p.w_co_stride = d->w_co_stride;
   p.dw = dw_master;
+  p.sems = ctx->det_tickets;
   p.BN = d->c_in % 256 == 0 ? 256 : (d->c_in % 128 == 0 ? 128 : (d->c_in % 64 == 0 ? 64 : 32));
   p.ci_tiles = d->c_in / p.BN;
   p.co_tiles = sg_div_up(d->c_out, 128);
@@ -1028,6 +1043,7 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   // count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43 waves)
   int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
   if (max_splits > 32) max_splits = 32;
+  if (base_units > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
   int splits = 1;
   double best_eff = -1.0;
   for (int sp = 1; sp <= max_splits; ++sp) {

@@ -105,14 +105,16 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
   // gradient, frame by frame (block-cooperative: occupancy scatter, then a block reduction for the softmax chain)
   __shared__ float red[32];
   for (int t = 0; t < T; ++t) {
-    for (int k = tid; k < C; k += blockDim.x) occ[k] = 0.f;
-    __syncthreads();
-    for (int s = tid; s < S; s += blockDim.x) {
-      float ab = alpha[t * S + s] + beta[t * S + s];
-      if (ab != NEG_INF) {
-        int k = ext[s];
-        atomicAdd(&occ[k], expf(ab - 2.f * logq[t * C + k] - logp));   // alpha*beta/q^2/P  (beta includes one q)
+    // occupancy of class k = sum over the extended-label positions s that carry k, in position order (no atomics: the
+    // blank and repeated letters occur at several positions, and a fixed order keeps the gradient bitwise repeatable)
+    for (int k = tid; k < C; k += blockDim.x) {
+      float o = 0.f;
+      for (int s = 0; s < S; ++s) {
+        if (ext[s] != k) continue;
+        float ab = alpha[t * S + s] + beta[t * S + s];
+        if (ab != NEG_INF) o += expf(ab - 2.f * logq[t * C + k] - logp);   // alpha*beta/q^2/P  (beta includes one q)
       }
+      occ[k] = o;
     }
     __syncthreads();
     // g_u[k] = q - q*occ' where occ' = sum alpha*beta/(q^2 P) ... so occupancy/P expressed relative to q:

@@ -37,12 +37,27 @@ int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->encode_tiled = nullptr;
   c->launches = 0;
+  // the ONE device allocation libsgan makes: the fixed workspace of the deterministic reductions (common.cuh)
+  cudaError_t e1 = cudaMalloc((void**)&c->det_scratch, SG_DET_SCRATCH_BYTES);
+  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void**)&c->det_tickets, SG_DET_TICKETS * sizeof(unsigned int)) : e1;
+  cudaError_t e3 = e2 == cudaSuccess ? cudaMemset(c->det_tickets, 0, SG_DET_TICKETS * sizeof(unsigned int)) : e2;
+  if (e3 != cudaSuccess) {
+    sg_set_error("sg_ctx_create: workspace allocation failed: %s", cudaGetErrorString(e3));
+    if (c->det_scratch) cudaFree(c->det_scratch);
+    if (c->det_tickets) cudaFree(c->det_tickets);
+    free(c);
+    return SG_ERR_CUDA;
+  }
   *out = c;
   return SG_OK;
 }
 
 int sg_ctx_destroy(sg_ctx* ctx) {
-  if (ctx) free(ctx);
+  if (ctx) {
+    if (ctx->det_scratch) cudaFree(ctx->det_scratch);
+    if (ctx->det_tickets) cudaFree(ctx->det_tickets);
+    free(ctx);
+  }
   return SG_OK;
 }
 

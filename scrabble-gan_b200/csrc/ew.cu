@@ -97,13 +97,20 @@ __global__ void k_scale_rows(float* __restrict__ x, const float* __restrict__ w,
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= w[i / cols];
 }
 
-__global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, float* partial) {
+// deterministic: per-block partials, summed in block order by the block that arrives last (common.cuh, scheme B)
+__global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, float* out, int accumulate,
+                      float* __restrict__ scratch, unsigned int* ticket) {
   __shared__ float sm[32];
   float acc = 0.f;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += a[i] * b[i];
   float t = sg_block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(partial, t);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = t;
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  float part = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) part += __ldcg(scratch + i);
+  float tot = sg_block_sum(part, sm);
+  if (threadIdx.x == 0) *out = (accumulate ? *out : 0.f) + tot;
 }
 
 // column sums of a [rows, cols] matrix (bias gradients): a block owns a slab of rows; its 256 threads are arranged as
@@ -111,7 +118,8 @@ __global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, 
 // row lanes are combined through shared memory and the block adds its partial sums with one atomicAdd per column.
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
-                                                    float* __restrict__ out) {
+                                                    float* __restrict__ out, int accumulate, float* __restrict__ scratch,
+                                                    unsigned int* ticket) {
   __shared__ float4 sm[NT];
   const int cgs = cols >> 2;                          // column groups of 4
   const int cg_per_pass = cgs < NT ? cgs : NT;
@@ -145,24 +153,35 @@ __global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long 
         float4 o = sm[j * cg_per_pass + cgi];
         acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
       }
-      float* op = out + (long long)cg * 4;
-      atomicAdd(op, acc.x); atomicAdd(op + 1, acc.y); atomicAdd(op + 2, acc.z); atomicAdd(op + 3, acc.w);
+      if (gridDim.x == 1) {
+        float* op = out + (long long)cg * 4;
+        float4 prev = accumulate ? sg_ld4(op) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sg_st4(op, make_float4(prev.x + acc.x, prev.y + acc.y, prev.z + acc.z, prev.w + acc.w));
+      } else {
+        sg_st4(scratch + (long long)blockIdx.x * cols + (long long)cg * 4, acc);
+      }
     }
   }
+  if (gridDim.x == 1) return;
+  // deterministic combine (common.cuh, scheme B): the last block to arrive sums the per-block partials in block order
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  for (int c = threadIdx.x; c < cols; c += NT) out[c] = (accumulate ? out[c] : 0.f) + sg_det_sum(scratch, gridDim.x, cols, c);
 }
 
 // generic fallback (cols not a multiple of 4): thread t handles columns t, t+blockDim...
 template <typename T>
 __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
-                         float* __restrict__ out) {
+                         float* __restrict__ out, int accumulate, float* __restrict__ scratch, unsigned int* ticket) {
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     float acc = 0.f;
     for (long long r = r0; r < r1; ++r) acc += sg_ld(x + r * cols + c);
-    atomicAdd(out + c, acc);
+    scratch[(long long)blockIdx.x * cols + c] = acc;
   }
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) out[c] = (accumulate ? out[c] : 0.f) + sg_det_sum(scratch, gridDim.x, cols, c);
 }
 
 template <typename TO>
@@ -429,21 +448,28 @@ int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long col
 
 int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out, int accumulate) {
   SG_REQUIRE(ctx && a && b && out && n >= 0, "sg_dot: bad args");
-  if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ctx->stream));
-  if (n == 0) return SG_OK;
-  k_dot<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(a, b, n, out);
+  if (n == 0) {
+    if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ctx->stream));
+    return SG_OK;
+  }
+  int dot_blocks = ew_grid(ctx, n, 256);
+  if (dot_blocks > 1024) dot_blocks = 1024;
+  k_dot<<<dot_blocks, 256, 0, ctx->stream>>>(a, b, n, out, accumulate, ctx->det_scratch, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
 
 int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, float* out, int accumulate) {
   SG_REQUIRE(ctx && x && out && rows >= 0 && cols > 0, "sg_colsum: bad args");
-  if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ctx->stream));
-  if (rows == 0) return SG_OK;
+  if (rows == 0) {
+    if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ctx->stream));
+    return SG_OK;
+  }
   SG_REQUIRE(dt == SG_F32 || dt == SG_BF16, "sg_colsum: bad dtype %d", dt);
   if (cols % 4 == 0 && ((uintptr_t)x & 15) == 0) {
-    // same-address float atomics serialise in L2 (~45 ns each, measured): bound blocks * cols, i.e. the atomics per
-    // output address, and use 1024-thread blocks so that few blocks still keep enough loads in flight
+    // per-block partial sums are combined in block order by the last block (deterministic; round 1 used float atomics,
+    // which also serialised at ~45 ns per same-address add): bound blocks * cols = the floats that block re-reads, and use
+    // 1024-thread blocks so that few blocks still keep enough loads in flight
     constexpr int NT = 1024;
     int cgs = cols / 4, cg_per_pass = cgs < NT ? cgs : NT, lanes_r = NT / cg_per_pass;
     long long blocks = (long long)ctx->num_sms * 2;
@@ -455,17 +481,25 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
     if (rpb < min_rpb) rpb = min_rpb;
     rpb = (rpb + lanes_r - 1) / lanes_r * lanes_r;
     blocks = (rows + rpb - 1) / rpb;
-    if (dt == SG_F32) k_colsum_v4<float, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const float*)x, rows, cols, rpb, out);
-    else k_colsum_v4<__nv_bfloat16, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const __nv_bfloat16*)x, rows, cols, rpb, out);
+    if (dt == SG_F32)
+      k_colsum_v4<float, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const float*)x, rows, cols, rpb, out, accumulate, ctx->det_scratch,
+                                                                  ctx->det_tickets);
+    else
+      k_colsum_v4<__nv_bfloat16, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const __nv_bfloat16*)x, rows, cols, rpb, out, accumulate,
+                                                                          ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
     return SG_OK;
   }
   long long blocks = (long long)ctx->num_sms * 4;
   if (blocks > rows) blocks = rows;
+  long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / cols;
+  if (blocks > fit) blocks = fit;
+  SG_REQUIRE(blocks >= 1, "sg_colsum: cols=%d too wide", cols);
   long long rpb = (rows + blocks - 1) / blocks;
   blocks = (rows + rpb - 1) / rpb;
   int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
-  SG_DISPATCH_DT(dt, T, k_colsum<T><<<(int)blocks, threads, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out));
+  SG_DISPATCH_DT(dt, T, k_colsum<T><<<(int)blocks, threads, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out, accumulate,
+                                                                              ctx->det_scratch, ctx->det_tickets));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

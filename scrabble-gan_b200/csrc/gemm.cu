@@ -13,7 +13,7 @@
 template <int GT_K>
 __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                               const float* __restrict__ bias, int accumulate, int k_per_split) {
+                                               const float* __restrict__ bias, int accumulate, int k_per_split, unsigned int* __restrict__ sems) {
   __shared__ float As[GT_K][GT_M + 4];
   __shared__ float Bs[GT_K][GT_N + 4];
   const int tid = threadIdx.x;
@@ -64,6 +64,12 @@ __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int 
     }
     __syncthreads();
   }
+  // split-K: the splits of a tile add into C in split order (ordered turns, common.cuh scheme A): bitwise repeatable
+  unsigned int* sem = sems + (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if (split) {
+    if (threadIdx.x == 0) sg_turn_wait(sem, blockIdx.z);
+    __syncthreads();
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int gm = m0 + ty * 4 + i;
@@ -79,6 +85,10 @@ __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int 
       if (accumulate) v += *p;
       *p = v;
     }
+  }
+  if (split) {
+    __syncthreads();
+    if (threadIdx.x == 0) sg_turn_pass(sem, blockIdx.z, gridDim.z);
   }
 }
 
@@ -107,7 +117,7 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
   grid.z = splits;
   // (a one-shot GT_K = 64 instantiation for K <= 64 measured SLOWER than the 16-wide loop on the CBN Dense layers --
   //  19 us vs 10 us per launch in profiles/r01_launches_step.csv -- so the generic loop is used for every shape)
-  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split);
+  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

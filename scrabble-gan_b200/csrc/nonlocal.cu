@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) k_nl_rowgemm(long long rows, SegMat A, Se
 #define NLW_SUB 4
 template <int KA, int KB>
 __global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long long rows, long long rows_per_block, SegMat A, SegMat B,
-                                                                             SegMat DW, const float* __restrict__ alpha_p) {
+                                                                             SegMat DW, const float* __restrict__ alpha_p,
+                                                                             float* __restrict__ scratch, unsigned int* __restrict__ ticket) {
   constexpr int TA = KA / 4, TB = KB / 4, NT = TA * TB;
   extern __shared__ __align__(16) float nlw_smem[];
   const int sub = threadIdx.x / NT, tid = threadIdx.x % NT;
@@ -193,21 +194,25 @@ __global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[((size_t)sub * 16 + i * 4 + j) * NT + tid] = acc[i][j];
   __syncthreads();
+  // deterministic combine across blocks (common.cuh, scheme B): the block's [KA][KB] partial goes to its scratch slot
   if (sub == 0) {
-    const float alpha = alpha_p ? *alpha_p : 1.f;
-    int s, off;
-    seg_find(DW, 4 * tj, s, off);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float* dp = DW.p[s] + (long long)(4 * ti + i) * DW.w[s] + off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = acc[i][j];
 #pragma unroll
         for (int u = 1; u < NLW_SUB; ++u) v += red[((size_t)u * 16 + i * 4 + j) * NT + tid];
-        atomicAdd(dp + j, alpha * v);
+        scratch[(long long)blockIdx.x * (KA * KB) + (4 * ti + i) * KB + 4 * tj + j] = v;
       }
     }
+  }
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
+  const float alpha = alpha_p ? *alpha_p : 1.f;
+  for (int i = threadIdx.x; i < KA * KB; i += blockDim.x) {
+    int r = i / KB, c = i % KB, s, off;
+    seg_find(DW, c, s, off);
+    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sg_det_sum(scratch, gridDim.x, KA * KB, i);
   }
 }
 
@@ -299,7 +304,8 @@ __global__ void __launch_bounds__(256) k_nl_rowgemm_mma(long long rows, SegMat A
 // then one global atomicAdd per element and block.
 template <int KA, int KB>
 __global__ void __launch_bounds__(256, 1) k_nl_wgrad_mma(long long rows, long long rows_per_block, SegMat A, SegMat B, SegMat DW,
-                                                          const float* __restrict__ alpha_p) {
+                                                          const float* __restrict__ alpha_p, float* __restrict__ scratch,
+                                                          unsigned int* __restrict__ ticket) {
   constexpr int MT = KA / 16, NT = KB / 8;
   __shared__ float red[KA * KB];
   for (int i = threadIdx.x; i < KA * KB; i += 256) red[i] = 0.f;
@@ -346,22 +352,30 @@ __global__ void __launch_bounds__(256, 1) k_nl_wgrad_mma(long long rows, long lo
       for (int m = 0; m < MT; ++m) nl_mma(acc[m][n], af[m], b0, b1);
     }
   }
-  // accumulator (m tile, n tile): c0,c1 = (row 16m + g, cols 8n + 2t, +1); c2,c3 = row + 8
+  // accumulator (m tile, n tile): c0,c1 = (row 16m + g, cols 8n + 2t, +1); c2,c3 = row + 8.  The 8 warps add their
+  // fragments into the block tile one warp after the other (fixed order: bitwise repeatable), then the blocks are combined
+  // in block order by the last block to arrive (common.cuh, scheme B)
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      atomicAdd(&red[(16 * m + g) * KB + 8 * n + 2 * t], acc[m][n][0]);
-      atomicAdd(&red[(16 * m + g) * KB + 8 * n + 2 * t + 1], acc[m][n][1]);
-      atomicAdd(&red[(16 * m + g + 8) * KB + 8 * n + 2 * t], acc[m][n][2]);
-      atomicAdd(&red[(16 * m + g + 8) * KB + 8 * n + 2 * t + 1], acc[m][n][3]);
+        for (int n = 0; n < NT; ++n) {
+          red[(16 * m + g) * KB + 8 * n + 2 * t] += acc[m][n][0];
+          red[(16 * m + g) * KB + 8 * n + 2 * t + 1] += acc[m][n][1];
+          red[(16 * m + g + 8) * KB + 8 * n + 2 * t] += acc[m][n][2];
+          red[(16 * m + g + 8) * KB + 8 * n + 2 * t + 1] += acc[m][n][3];
+        }
     }
-  __syncthreads();
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < KA * KB; i += 256) scratch[(long long)blockIdx.x * (KA * KB) + i] = red[i];
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
   const float alpha = alpha_p ? *alpha_p : 1.f;
   for (int i = threadIdx.x; i < KA * KB; i += 256) {
     int r = i / KB, c = i % KB, s, off;
     seg_find(DW, c, s, off);
-    atomicAdd(DW.p[s] + (long long)r * DW.w[s] + off, alpha * red[i]);
+    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sg_det_sum(scratch, gridDim.x, KA * KB, i);
   }
 }
 
@@ -400,7 +414,7 @@ static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegM
     long long blocks = (long long)ctx->num_sms * 2;
     long long rpb = ((rows + blocks - 1) / blocks + 127) / 128 * 128;
     int grid_m = (int)((rows + rpb - 1) / rpb);
-    k_nl_wgrad_mma<KA, KB><<<grid_m, 256, 0, ctx->stream>>>(rows, rpb, A, B, DW, alpha);
+    k_nl_wgrad_mma<KA, KB><<<grid_m, 256, 0, ctx->stream>>>(rows, rpb, A, B, DW, alpha, ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
     return SG_OK;
   }
@@ -410,7 +424,8 @@ static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegM
   size_t smem = sizeof(float) * (size_t)NLW_SUB * NLW_ROWS * (KA + KB);
   static_assert(NLW_SUB * 16 * (KA / 4) * (KB / 4) <= NLW_SUB * NLW_ROWS * (KA + KB), "reduction buffer does not fit");
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_nl_wgrad<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_nl_wgrad<KA, KB><<<grid, NLW_SUB * (KA / 4) * (KB / 4), smem, ctx->stream>>>(rows, rpb, A, B, DW, alpha);
+  k_nl_wgrad<KA, KB><<<grid, NLW_SUB * (KA / 4) * (KB / 4), smem, ctx->stream>>>(rows, rpb, A, B, DW, alpha, ctx->det_scratch,
+                                                                                  ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -68,16 +68,21 @@ __global__ void k_sn_rowdot(const float* __restrict__ w, int rows, int cols, con
   acc = sg_warp_sum(acc);
   if (lane == 0) v[r] = acc * (u_scale ? *u_scale : 1.f);
 }
-// t[c] += sum_{r in slab} v[r] * v_scale * W[r,c]
+// t[c] = sum_r v[r] * v_scale * W[r,c]: row slabs (blockIdx.y) are combined in slab order by the last block of each column
+// block to arrive (common.cuh, scheme B: deterministic)
 __global__ void k_sn_coldot(const float* __restrict__ w, int rows, int cols, const float* __restrict__ v,
-                            const float* __restrict__ v_scale, int rows_per_block, float* __restrict__ t) {
+                            const float* __restrict__ v_scale, int rows_per_block, float* __restrict__ t,
+                            float* __restrict__ scratch, unsigned int* __restrict__ tickets) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
   int r0 = blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r) acc += v[r] * w[(long long)r * cols + c];
-  atomicAdd(t + c, acc * (*v_scale));
+  if (c < cols)
+    for (int r = r0; r < r1; ++r) acc += v[r] * w[(long long)r * cols + c];
+  float* slots = scratch + (long long)blockIdx.x * gridDim.y * blockDim.x;
+  slots[(long long)blockIdx.y * blockDim.x + threadIdx.x] = acc * (*v_scale);
+  if (!sg_det_arrive_last(tickets + blockIdx.x, gridDim.y)) return;
+  if (c < cols) t[c] = sg_det_sum(slots, gridDim.y, blockDim.x, threadIdx.x);
 }
 // out[0] = rsqrt(max(sum x^2, 1e-12))   (tf.nn.l2_normalize scale), out[1] = sum x^2
 __global__ void k_sn_invnorm(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -169,13 +174,18 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
     SG_POST_LAUNCH(ctx);
     k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(v, rows, sc);
     SG_POST_LAUNCH(ctx);
-    SG_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, ctx->stream));
     int slabs = sg_div_up(rows, 64);
     if (slabs > 4 * ctx->num_sms) slabs = 4 * ctx->num_sms;
+    SG_REQUIRE(sg_div_up(cols, 128) <= SG_DET_TICKETS, "sg_spectral_norm: too many columns");
+    {
+      long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / ((long long)sg_div_up(cols, 128) * 128);
+      if (slabs > fit) slabs = (int)fit;
+      if (slabs < 1) slabs = 1;
+    }
     int rpb = sg_div_up(rows, slabs);
     slabs = sg_div_up(rows, rpb);
     dim3 grid(sg_div_up(cols, 128), slabs);
-    k_sn_coldot<<<grid, 128, 0, ctx->stream>>>(w, rows, cols, v, sc, rpb, t);
+    k_sn_coldot<<<grid, 128, 0, ctx->stream>>>(w, rows, cols, v, sc, rpb, t, ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
     k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2);
     SG_POST_LAUNCH(ctx);

@@ -29,11 +29,23 @@ def init_data_parallel(rt, backend: str = None) -> None:
         if backend == "nccl":
             kw["device_id"] = rt.device
         dist.init_process_group(backend=backend, **kw)
+    else:
+        backend = str(dist.get_backend())           # a process group made by the caller: ask it what it is
     rt.world_size = dist.get_world_size()
     rt.rank = dist.get_rank()
     rt.process_group = None
-    if backend == "nccl" and os.environ.get("SGAN_NO_PEER", "0") != "1":
-        init_peer_exchange(rt)
+    rt.peer = None
+    if "nccl" in backend:
+        # every rank must take the SAME path (a rank on NCCL while its peers spin on peer flags would hang both): the
+        # opt-out and the outcome of the set-up are agreed on with a MIN all-reduce
+        want = 0 if os.environ.get("SGAN_NO_PEER", "0") == "1" else 1
+        flag = torch.tensor([want], device=rt.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item()) == 1 and init_peer_exchange(rt)
+        flag = torch.tensor([1 if ok else 0], device=rt.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            rt.peer = None
 
 
 class PeerExchange:

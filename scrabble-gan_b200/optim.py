@@ -28,11 +28,18 @@ class Adam:
         self.iterations = 0
         self._state: Dict[int, _FlatState] = {}
         self._dev = None            # (step counter int32[1], lr_t float32[1]) on the device: graph-replayable updates
+        self._dev_step = None       # host shadow of the device step counter (None = unknown)
 
-    def advance_for_replay(self) -> None:
-        """Host-side bookkeeping for one CUDA-graph replay of a captured apply_gradients (the device counter advances
-        itself inside the graph)."""
+    def advance_for_replay(self, rt=None) -> None:
+        """Host-side bookkeeping for one CUDA-graph replay of a captured apply_gradients.  The captured sg_adam_prepare
+        increments the DEVICE counter; if the host count was changed outside the graph since the last update (restored
+        optimizer state, load_state_dict, a roll-back) the device counter is first re-seeded with an explicit launch so
+        that the replayed bias-corrected step size uses t = iterations + 1."""
+        if self._dev is not None and self._dev_step != self.iterations and rt is not None:
+            ops.call.sg_adam_prepare(rt.ctx, ops._p(self._dev[0]), ops._p(self._dev[1]), self.iterations, self.learning_rate,
+                                     self.beta_1, self.beta_2)
         self.iterations += 1
+        self._dev_step = self.iterations
 
     def _lr_t(self) -> float:
         t = self.iterations
@@ -43,6 +50,13 @@ class Adam:
         if st is None:
             st = self._state[id(store)] = _FlatState(store, 2)
         return st
+
+    def ensure_state(self, store: ParamStore) -> None:
+        """Allocate the (m, v) slots and the device-side step counter for `store` (idempotent)."""
+        self._slots(store)
+        if self._dev is None:
+            rt = store.rt
+            self._dev = (torch.zeros(1, device=rt.device, dtype=torch.int32), torch.zeros(1, device=rt.device))
 
     def apply_gradients(self, grads_and_vars: Iterable[Tuple[torch.Tensor, Variable]]) -> None:
         pairs = list(grads_and_vars)
@@ -64,6 +78,8 @@ class Adam:
             capturing = torch.cuda.is_current_stream_capturing()
             ops.call.sg_adam_prepare(rt.ctx, ops._p(self._dev[0]), ops._p(self._dev[1]), -1 if capturing else self.iterations,
                                      self.learning_rate, self.beta_1, self.beta_2)
+            if not capturing:
+                self._dev_step = self.iterations
             ops.call.sg_adam_dev(rt.ctx, ops._p(store.w), ops._p(store.g), ops._p(st.slots[0]), ops._p(st.slots[1]), ops._p(mirror),
                                  store.w.numel(), ops._p(self._dev[1]), self.beta_1, self.beta_2, self.epsilon)
             mirror_fresh = mirror is not None
@@ -80,6 +96,18 @@ class Adam:
 
     def state_dict(self):
         return {"iterations": self.iterations, "slots": {k: [s.clone() for s in v.slots] for k, v in self._state.items()}}
+
+    def load_state_dict(self, sd) -> None:
+        """Restore `iterations` and the (m, v) slots saved by state_dict(); the device step counter is re-seeded on the next
+        update (eager: explicit t; replayed: advance_for_replay notices the mismatch)."""
+        self.iterations = int(sd["iterations"])
+        for k, slots in sd.get("slots", {}).items():
+            st = self._state.get(k)
+            if st is None:
+                continue
+            for t, src in zip(st.slots, slots):
+                t.copy_(src)
+        self._dev_step = None
 
 
 class RMSprop:

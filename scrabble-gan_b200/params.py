@@ -56,7 +56,8 @@ class Variable:
         return "Variable({}, shape={}, trainable={})".format(self.name, self.shape, self.trainable)
 
 
-# ---- initialisers (construction time only; torch is used as a host-side RNG / QR, not on the hot path) -------
+# ---- initialisers (construction time only: they run on the HOST -- torch CPU as RNG / LAPACK QR -- and the result is
+# copied into the flat buffer, so model construction launches no GPU kernels besides the copies) -------
 def init_orthogonal(shape, device, gen):
     """tf.initializers.orthogonal(gain=1): QR of a normal matrix of shape (prod(shape[:-1]), shape[-1])."""
     rows = 1
@@ -133,9 +134,14 @@ class ParamStore:
         self.s = torch.zeros(max(off_s, 1), device=dev, dtype=torch.float32)
         self.n_trainable = sum(v.numel for v in self.vars if v.trainable)
         if initialise:
-            gen = torch.Generator(device=dev).manual_seed(self.seed)
+            gen = torch.Generator().manual_seed(self.seed)
             for v in self.vars:
-                v.data.copy_(v.init(v.shape, dev, gen))
+                v.data.copy_(v.init(v.shape, "cpu", gen))
+        else:
+            # weights will be loaded by the caller (load_state_dict / load_weights): only the non-zero constants
+            for v in self.vars:
+                if v.init is init_ones:
+                    v.data.fill_(1.0)
         self.version += 1
 
     def mirror(self, rt) -> torch.Tensor:

@@ -46,7 +46,8 @@ def l2_profile(a, b):
 
 def check_dict(got, exp, tol, what, skip=(), floor=None):
     """Gradient parity of one network: (i) relative L2 error of the WHOLE gradient (all tensors concatenated) <= tol,
-    and (ii) relative L2 error of every single tensor <= 50*tol (a wrong layer shows up as O(1)).
+    and (ii) relative L2 error of every single tensor <= 10*tol, a tensor's error being taken relative to
+    max(its own norm, 1e-3 x the norm of the whole gradient).
 
     Why not max-abs per tensor at tol: ReLU/max-pool masks are discontinuous, so an activation that is ~0 in fp64 can
     take the other sign in fp32 (or, far more often, in bf16/tf32) and move O(1/N) of a tensor's gradient; bias
@@ -54,6 +55,7 @@ def check_dict(got, exp, tol, what, skip=(), floor=None):
     torch oracle itself deviates from the fp64 one by 1e-3 on G's out.b).  tools/diag_parity.py prints the details."""
     num = den = 0.0
     worst = ("", 0.0)
+    rows = []
     for k, e in exp.items():
         if k in skip or k.endswith(O.NON_TRAINABLE_SUFFIXES):
             continue
@@ -70,7 +72,9 @@ def check_dict(got, exp, tol, what, skip=(), floor=None):
         d2, e2 = float(((g - e) ** 2).sum()), float((e ** 2).sum())
         num += d2
         den += e2
-        r = (d2 / max(e2, 1e-30)) ** 0.5
+        rows.append((k, d2, e2))
+    for k, d2, e2 in rows:
+        r = (d2 / max(e2, 1e-6 * den, 1e-30)) ** 0.5
         if r > worst[1]:
             worst = (k, r)
     total = (num / max(den, 1e-30)) ** 0.5
@@ -79,9 +83,9 @@ def check_dict(got, exp, tol, what, skip=(), floor=None):
         # problem; being within 3x of what plain fp32 arithmetic achieves is the most an fp32 kernel can promise
         f_total, f_per = floor
         tol = max(tol, 3 * f_total)
-        bound = max(50 * tol, 3 * f_per.get(worst[0], 0.0))
+        bound = max(10 * tol, 3 * f_per.get(worst[0], 0.0))
     else:
-        bound = 50 * tol
+        bound = 10 * tol
     assert total <= tol, "{}: whole-gradient rel L2 err {:.3e} > {:.1e} (worst tensor {} {:.3e})".format(what, total, tol, *worst)
     assert worst[1] <= bound, "{}: tensor {} rel L2 err {:.3e} > {:.1e}".format(what, worst[0], worst[1], bound)
     return total, worst
@@ -171,8 +175,18 @@ def test_generator_fwd_bwd_and_inference(rt):
 
 
 def _train_step_case(rt, mode, use_w, loss_name, balance, tol_out, tol_grad, b=3, l_r=2, l_f=3, style_encoder=False, seed=5,
-                     calibrate=False):
+                     calibrate=False, rounding=None):
+    """`rounding`: operand-rounding mode of the oracle ("bf16" / "tf32", sgan_oracle.set_operand_rounding) so that the
+    reduced-precision modes are compared against an oracle that rounds where the CUDA path rounds."""
     rt.set_mode(mode)
+    O.set_operand_rounding(rounding, wgrad=(rounding == "bf16" or bool(getattr(rt, "tf32_wgrad_tc", False))))
+    try:
+        return _train_step_case_impl(rt, mode, use_w, loss_name, balance, tol_out, tol_grad, b, l_r, l_f, style_encoder, seed, calibrate)
+    finally:
+        O.set_operand_rounding(None)
+
+
+def _train_step_case_impl(rt, mode, use_w, loss_name, balance, tol_out, tol_grad, b, l_r, l_f, style_encoder, seed, calibrate):
     dt = torch.float64
     g = torch.Generator().manual_seed(seed)
     P = {"G": O.make_generator_params(21, dt, sigma=0.2, bias_scale=0.05, style_encoder_too=style_encoder),
@@ -255,16 +269,16 @@ def test_train_step_fp32_fork_mode_style_encoder(rt):
 
 
 def test_train_step_tf32(rt):
-    # tf32 operands (10-bit mantissa): ~4e-4 of the ReLU masks flip w.r.t. fp64 => ~2e-2 gradient noise (sqrt law)
-    _train_step_case(rt, "tf32", False, "hinge", True, 5e-3, 5e-2)
+    # unfused path (l_r != l_f), tf32 operands, against the oracle that truncates the same operands to tf32: north_star's
+    # fp32-class tolerance (the fused path and the BASELINE sizes are in tests/test_parity_benchpath_gpu.py)
+    _train_step_case(rt, "tf32", False, "hinge", True, 1e-3, 1e-3, rounding="tf32")
     rt.set_mode("fp32")
 
 
 def test_train_step_bf16(rt):
-    # bf16 operands (8-bit mantissa): outputs / losses within 1e-2; ~3e-3 of the ReLU masks flip w.r.t. fp64 at
-    # batch 3, which alone gives ~6e-2 relative gradient noise (DESIGN.md "precision"); the operand-rounding-exact
-    # comparison is test_bf16_matches_quantised_oracle
-    _train_step_case(rt, "bf16", False, "hinge", True, 1e-2, 2e-1)
+    # unfused path (l_r != l_f), bf16 operands, against the oracle that rounds the same operands to bf16: north_star's
+    # 1e-2 for outputs, losses and the whole gradient of every network, 1e-1 per tensor
+    _train_step_case(rt, "bf16", False, "hinge", True, 1e-2, 1e-2, rounding="bf16")
     rt.set_mode("fp32")
 
 
@@ -390,5 +404,55 @@ def test_train_shell_runs_on_synthetic_buckets(rt, tmp_path):
         G2.load_weights(os.path.join(ckpt, "generator", "2", "cktp-2"))
         assert torch.equal(G2.store.w, G.store.w)
     finally:
+        du._graph_cache.clear()
+        rt.set_mode("fp32")
+
+
+def test_eager_after_graph_replay_uses_current_weights(rt):
+    """After CUDA-graph replays (whose captured Adam launches change the weights), eager code must see the CURRENT weights:
+    the packed-filter caches key on store.version, which every replay advances.  G inference and a D forward of the
+    replayed models must equal those of fresh models loaded with the same state.  Also: with disc_iters = 2 the Keras
+    `trainable` flags after a replayed step equal those the eager step leaves (reference data_utils.py:449-466)."""
+    rt.set_mode("bf16")
+    old = du.GRAPH_ENABLED
+    try:
+        du._graph_cache.clear()
+        du.GRAPH_ENABLED = True
+        b, l = 2, 2
+        rng = np.random.RandomState(9)
+        G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=51)
+        D = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt, seed=52)
+        R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt, seed=53)
+        gan = na.make_gan(G, D, R, None, vis_model=False)
+        g_opt, d_opt, r_opt, w_opt, loss_fn, _, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+        z_inf = rng.standard_normal(size=(b, 128)).astype(np.float32)
+        y_inf = rng.randint(0, 52, size=(b, l)).astype(np.int32)
+        G([z_inf, y_inf], training=False)                       # fills the eager packed-filter caches with the INITIAL weights
+        x_d = rng.uniform(-1, 1, size=(b, 32, 16 * l, 1)).astype(np.float32)
+        D([x_d])
+        flags = []
+        for i in range(8):                                       # disc_iters = 2: G is updated on odd batch indices only
+            imgs = rng.uniform(-1, 1, size=(b, 32, 16 * l, 1)).astype(np.float32)
+            labels = rng.randint(0, 52, size=(b, l)).astype(np.int32)
+            fake = rng.randint(0, 52, size=(b, l)).astype(np.int32)
+            z = rng.standard_normal(size=(b, 128)).astype(np.float32)
+            du.train_step(0, i, 8, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn, 2, agb, None, 10, "",
+                          fake_labels=fake, noise=z)
+            flags.append((D.trainable, R.trainable))
+        assert sum(1 for gs in du._graph_cache.values() if gs.graph is not None) >= 1, "some signature must have been captured"
+        assert rt.replayed_launches > 0
+        # a step that skips the G update leaves D, R trainable (True); one that updates G leaves them frozen (False)
+        assert flags == [(True, True), (False, False)] * 4, flags
+        assert (g_opt.iterations, d_opt.iterations, r_opt.iterations) == (4, 8, 8)
+        got_img = G([z_inf, y_inf], training=False)
+        got_d = D([x_d])
+        G2 = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, initialise=False)
+        D2 = na.make_discriminator(IN_DIM, None, "B1", vis_model=False, rt=rt, initialise=False)
+        G2.load_state_dict(G.state_dict())
+        D2.load_state_dict(D.state_dict())
+        assert torch.equal(got_img, G2([z_inf, y_inf], training=False)), "G inference after replays used stale packed filters"
+        assert torch.equal(got_d, D2([x_d])), "D forward after replays used stale packed filters"
+    finally:
+        du.GRAPH_ENABLED = old
         du._graph_cache.clear()
         rt.set_mode("fp32")

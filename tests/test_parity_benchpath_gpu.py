@@ -1,0 +1,245 @@
+"""Parity of the path bench.py times -- bf16 operands, fused [fake ; real] D/R batch, ONE merged backward pass of R,
+CUDA-graph replay -- and parity at BASELINE.json's sizes (configs 1/4: B = 64, L = 5; config 3: R + CTC at B = 256, 81 outputs;
+config 2: generator inference buckets at L = 1 and L = 10), against the CPU oracle.
+
+The reduced-precision modes are compared with the oracle run in its operand-rounding mode
+(sgan_oracle.set_operand_rounding): the oracle rounds to bf16 (or truncates to tf32) at exactly the points where the CUDA
+path stores / reads that precision and accumulates wide, so ReLU and max-pool masks come from the same operands on both
+sides and the comparison can be held to north_star's tolerances: whole-gradient relative L2 <= 1e-2 in bf16, 1e-3 in
+fp32 / tf32, with a per-tensor bound of 5x that (tests/_parity.py: grad_profile)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import sgan_oracle as O
+from _parity import (assert_grads, assert_stats, build_models, du, make_inputs, make_params, rel_elementwise, rel_max, run_step)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (1e-3, 5e-3), "tf32": (1e-3, 5e-3), "bf16": (1e-2, 5e-2)}       # (whole-gradient, per tensor)
+TOL_OUT = {"fp32": 1e-3, "tf32": 1e-3, "bf16": 1e-2}
+
+
+def _oracle_step(P, images, labels, fake_labels, z, mode, tf32_wgrad=False, **kw):
+    O.set_operand_rounding({"fp32": None, "tf32": "tf32", "bf16": "bf16"}[mode], wgrad=(mode == "bf16" or tf32_wgrad))
+    try:
+        return O.train_step(P, {}, images, labels, fake_labels, z, return_grads=True, **kw)
+    finally:
+        O.set_operand_rounding(None)
+
+
+def _tf32_wgrad_on_tc(rt):
+    return bool(getattr(rt, "tf32_wgrad_tc", False))
+
+
+# ----------------------------------------------------------------------------------------------------
+# the benchmarked path at a size the fp64 oracle finishes in seconds
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph-replay"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_fused_path_matches_rounded_oracle(rt, mode, graph):
+    """`test_bf16_matches_quantised_oracle`: l_r == l_f (fused 2B batch), merge_r_backward on, eager and replayed from a
+    CUDA graph; gradients of all three networks against the fp64 oracle with operand rounding."""
+    rt.set_mode(mode)
+    old = (du.GRAPH_ENABLED, du.GRAPH_WARMUP)
+    try:
+        du._graph_cache.clear()
+        du.GRAPH_ENABLED, du.GRAPH_WARMUP = graph, 0
+        assert rt.merge_r_backward
+        dt = torch.float64
+        b, l = 4, 3
+        P = make_params(40, dt)
+        images, labels, fake_labels, z = make_inputs(41, b, l, l, dt)
+        stats, newp, _, grads, extra = _oracle_step(P, images, labels, fake_labels, z, mode, _tf32_wgrad_on_tc(rt))
+        if graph:
+            # every kernel of the step is launched once eagerly first (on throw-away models): CUDA loads a kernel's module
+            # at its first launch, which must not happen inside a stream capture
+            du.GRAPH_ENABLED = False
+            run_step(rt, *build_models(rt, P)[:3], None, images, labels, fake_labels, z)
+            du.GRAPH_ENABLED = True
+        G, D, R, _ = build_models(rt, P)
+        n_replayed = rt.replayed_launches
+        got, _ = run_step(rt, G, D, R, None, images, labels, fake_labels, z)
+        if graph:
+            assert any(gs.graph is not None for gs in du._graph_cache.values()), "the step must have been captured"
+            assert rt.replayed_launches > n_replayed, "the step must have been REPLAYED from the graph"
+        else:
+            assert rt.replayed_launches == n_replayed
+        assert_stats(got, stats, TOL_OUT[mode], "{} fused step".format(mode))
+        tw, tt = TOL[mode]
+        for n, m in (("D", D), ("R", R), ("G", G)):
+            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, "graph" if graph else "eager"))
+    finally:
+        du.GRAPH_ENABLED, du.GRAPH_WARMUP = old
+        du._graph_cache.clear()
+        rt.set_mode("fp32")
+
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE configs 1 / 4: B = 64, L = 5, Mode A (G + D + R), hinge + gradient balancing
+# ----------------------------------------------------------------------------------------------------
+class _FullCase:
+    B, L = 64, 5
+
+    def __init__(self):
+        dt = torch.float32
+        self.P = make_params(60, dt, sigma=0.1, bias_scale=0.02)
+        self.inputs = make_inputs(61, self.B, self.L, self.L, dt)
+        self._oracle = {}
+
+    def oracle(self, mode, tf32_wgrad=False):
+        key = (mode, tf32_wgrad)
+        if key not in self._oracle:
+            stats, newp, _, grads, extra = _oracle_step(self.P, *self.inputs, mode, tf32_wgrad)
+            self._oracle[key] = (stats, grads, extra)
+        return self._oracle[key]
+
+
+@pytest.fixture(scope="module")
+def full_case():
+    torch.set_num_threads(max(torch.get_num_threads(), 1))
+    return _FullCase()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_train_step_at_baseline_size(rt, full_case, mode):
+    """One full step at B = 64, L = 5 (BASELINE configs[0] / configs[3]) against the fp32 oracle: forward images, D logits,
+    R losses (elementwise relative), the 16 statistics and the whole gradient of every network."""
+    rt.set_mode(mode)
+    old = du.GRAPH_ENABLED
+    try:
+        du._graph_cache.clear()
+        du.GRAPH_ENABLED = False
+        fc = full_case
+        images, labels, fake_labels, z = fc.inputs
+        stats, grads, extra = fc.oracle(mode, _tf32_wgrad_on_tc(rt))
+        G, D, R, _ = build_models(rt, fc.P)
+        tol = TOL_OUT[mode]
+
+        # forward outputs (no parameter update, G's moving statistics restored afterwards)
+        s_saved = G.store.s.clone()
+        zd, yf = z.to(rt.device), fake_labels.to(rt.device, torch.int32)
+        img, _ = G.forward(rt, zd, yf, training=True)
+        G.store.s.copy_(s_saved)
+        assert rel_max(img, extra["gen_images"]) <= tol, "generated images: {:.3e}".format(rel_max(img, extra["gen_images"]))
+        xr = images.to(rt.device)
+        d_real, _ = D.forward(rt, xr)
+        assert rel_elementwise(d_real, extra["d_real"]) <= 5 * tol, "D(real) logits: {:.3e}".format(rel_elementwise(d_real, extra["d_real"]))
+        d_fake, _ = D.forward(rt, extra["gen_images"].to(rt.device))
+        assert rel_elementwise(d_fake, extra["d_fake"]) <= 5 * tol, "D(fake) logits: {:.3e}".format(rel_elementwise(d_fake, extra["d_fake"]))
+        r_real, _ = R.forward(rt, xr, labels.to(rt.device, torch.int32), want_grad=False)
+        ctc_tol = 1e-4 if mode == "fp32" else tol
+        assert rel_elementwise(r_real, extra["r_real"], 1.0) <= ctc_tol, "R(real) CTC losses: {:.3e}".format(rel_elementwise(r_real, extra["r_real"], 1.0))
+
+        got, _ = run_step(rt, G, D, R, None, images, labels, fake_labels, z)
+        assert_stats(got, stats, tol, "{} B=64 L=5 step".format(mode))
+        tw, tt = TOL[mode]
+        for n, m in (("D", D), ("R", R), ("G", G)):
+            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients at B=64, L=5".format(mode, n))
+    finally:
+        du.GRAPH_ENABLED = old
+        du._graph_cache.clear()
+        rt.set_mode("fp32")
+
+
+def test_bf16_step_vs_exact_oracle_statistics(rt, full_case):
+    """The bf16 step against the EXACT fp32 oracle at B = 64, L = 5: the 16 statistics within north_star's 1e-2 (no operand
+    rounding on the oracle's side), and the whole-gradient distance reported (it is mask-flip noise, bounded loosely)."""
+    rt.set_mode("bf16")
+    old = du.GRAPH_ENABLED
+    try:
+        du._graph_cache.clear()
+        du.GRAPH_ENABLED = False
+        fc = full_case
+        stats, grads, extra = fc.oracle("fp32")
+        G, D, R, _ = build_models(rt, fc.P)
+        got, _ = run_step(rt, G, D, R, None, *fc.inputs)
+        # the two balanced losses multiply by std(g_loss) / std(r_fake), a ratio of spreads of nearly equal numbers: they
+        # amplify the 1e-2-class error of D's logits and are held to 5e-2 here (tight against the rounded oracle above)
+        hard = ("r_loss_balanced", "g_loss_balanced", "g_loss_final", "g_loss_std", "r_loss_fake_std")
+        bad = []
+        for k in O.STAT_NAMES:
+            err = abs(got[k] - stats[k]) / max(abs(stats[k]), 1e-2)
+            if not np.isfinite(got[k]) or err > (5e-2 if k in hard else 1e-2):
+                bad.append("{}: got {!r} expected {!r} (rel {:.2e})".format(k, got[k], stats[k], err))
+        assert not bad, "bf16 step vs the exact oracle:\n  " + "\n  ".join(bad)
+        for n, m in (("D", D), ("R", R), ("G", G)):
+            assert_grads(m.store.grad_dict(), grads[n], 1e-1, 1.0, "bf16 {} gradients vs the exact fp32 oracle".format(n))
+    finally:
+        du.GRAPH_ENABLED = old
+        du._graph_cache.clear()
+        rt.set_mode("fp32")
+
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE config 3: recogniser CRNN + CTC, B = 256, 32x160, 80-class alphabet (81 outputs)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_recognizer_ctc_at_config3_size(rt, mode):
+    rt.set_mode(mode)
+    try:
+        dt = torch.float32
+        b, l, classes = 256, 10, 81
+        P = O.make_recognizer_params(70, dt, output_classes=classes, bias_scale=0.02)
+        g = torch.Generator().manual_seed(71)
+        x = torch.rand(b, 32, 16 * l, 1, generator=g) * 2 - 1
+        y = torch.randint(0, classes - 1, (b, l), generator=g)
+        leaf = {k: v.clone().requires_grad_(not k.endswith(O.NON_TRAINABLE_SUFFIXES)) for k, v in P.items()}
+        O.set_operand_rounding({"fp32": None, "tf32": "tf32", "bf16": "bf16"}[mode], wgrad=(mode == "bf16" or _tf32_wgrad_on_tc(rt)))
+        try:
+            loss = O.recognizer(x, y, torch.full((b, 1), 4 * l - 1), torch.full((b, 1), l), leaf)
+            loss.sum().backward()
+        finally:
+            O.set_operand_rounding(None)
+        R = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture").make_recognizer((32, 160, 1), None, classes, vis_model=False,
+                                                                                                    rt=rt, initialise=False)
+        R.load_state_dict(P)
+        R.store.zero_grad()
+        got, cache = R.forward(rt, x.to(rt.device), y.to(rt.device, torch.int32))
+        R.backward(rt, cache, None, wgrad=True, want_dx=False)
+        tol = 1e-4 if mode == "fp32" else TOL_OUT[mode]        # north_star: CTC loss within 1e-4 relative in fp32
+        err = rel_elementwise(got, loss.detach().view(-1), 1.0)
+        assert err <= tol, "CTC losses at B=256, T=39, C=81: elementwise rel err {:.3e} > {:.0e}".format(err, tol)
+        tw, tt = TOL[mode]
+        assert_grads(R.store.grad_dict(), {k: v.grad for k, v in leaf.items() if v.grad is not None}, tw, tt,
+                     "{} R gradients at config-3 size".format(mode))
+    finally:
+        rt.set_mode("fp32")
+
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE config 2: generator-only inference (run_inference path): length buckets of a 256-word batch
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_generator_inference_at_config2_buckets(rt, mode):
+    """256 words with lengths ~ U{1..10} fall into buckets of ~26 words: the L = 1 and the L = 10 bucket, training=False
+    (moving statistics), against the oracle."""
+    rt.set_mode(mode)
+    try:
+        dt = torch.float32
+        P = O.make_generator_params(80, dt, sigma=0.1, bias_scale=0.02)
+        g = torch.Generator().manual_seed(81)
+        for k in list(P):       # non-trivial moving statistics, as after training
+            if k.endswith(".moving_mean"):
+                P[k] = torch.randn(P[k].shape, generator=g) * 0.1
+            if k.endswith(".moving_var"):
+                P[k] = torch.rand(P[k].shape, generator=g) + 0.5
+        G = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture").make_generator(128, (32, 160, 1), (32, 8192), None, "B3", 52,
+                                                                                                   vis_model=False, rt=rt, initialise=False)
+        G.load_state_dict(P)
+        for l, n in ((1, 27), (10, 26)):
+            z = torch.randn(n, 128, generator=g)
+            y = torch.randint(0, 52, (n, l), generator=g)
+            O.set_operand_rounding({"fp32": None, "tf32": "tf32", "bf16": "bf16"}[mode])
+            try:
+                exp = O.generator_core(z, y, P, "B3", False)
+            finally:
+                O.set_operand_rounding(None)
+            got = G([z.numpy(), y.numpy()], training=False)
+            assert tuple(got.shape) == (n, 32, 16 * l, 1)
+            err = rel_max(got, exp)
+            assert err <= TOL_OUT[mode], "G inference, bucket L={}: {:.3e} > {:.0e}".format(l, err, TOL_OUT[mode])
+    finally:
+        rt.set_mode("fp32")
