@@ -65,9 +65,13 @@ def _loss_kind(loss_fn) -> int:
 # memcpy nodes re-read on every replay, and the result is the same `stats` tensor.  Set SGAN_CUDA_GRAPH=0 to disable.
 GRAPH_ENABLED = os.environ.get("SGAN_CUDA_GRAPH", "1") != "0"
 GRAPH_DP = os.environ.get("SGAN_CUDA_GRAPH_DP", "1") != "0"      # capture the data-parallel step too (NCCL + peer exchanges)
-GRAPH_WARMUP = 2
-GRAPH_MAX = int(os.environ.get("SGAN_CUDA_GRAPH_MAX", "8"))     # each captured signature keeps its own activation pool (GBs)
+GRAPH_WARMUP = int(os.environ.get("SGAN_CUDA_GRAPH_WARMUP", "2"))   # eager calls of a signature before it is captured
+# One graph per (models, B, L_real, L_fake, mode, ...) signature -- up to 100 (L_real, L_fake) pairs in training on words of
+# 1..10 characters.  All graphs allocate from ONE shared memory pool (they replay one after the other on one stream, so the
+# activations of one graph may reuse the memory of another): the footprint is the largest signature's, not the sum.
+GRAPH_MAX = int(os.environ.get("SGAN_CUDA_GRAPH_MAX", "256"))
 _graph_cache = {}
+_graph_pool = [None]
 
 
 class _GraphedStep:
@@ -188,7 +192,9 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=rt.device)
         n0 = rt.launch_count()
-        with torch.cuda.graph(graph, stream=side):
+        if _graph_pool[0] is None:
+            _graph_pool[0] = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(graph, pool=_graph_pool[0], stream=side):
             rt.use_current_stream()
             stats = _step_device(rt, args, static[0], static[1], static[2], static[3], None)
         rt.use_current_stream()

@@ -151,12 +151,11 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restri
     }
   }
   if (gridDim.x == 1) return;
-  if (!sg_det_arrive_last(tickets + ni, gridDim.x)) return;
-  for (int j = threadIdx.x; j < 2 * c; j += blockDim.x) {
-    float t = sg_det_sum(slots, gridDim.x, 2 * c, j);
+  if (!sg_det_arrive_last(tickets + ni, gridDim.x)) return;      // gridDim.x <= 32: one level
+  sg_det_block_reduce(slots, gridDim.x, 2 * c, [&](int j, float t) {
     if (j < c) s1[(long long)ni * c + j] = t;
     else s2[(long long)ni * c + (j - c)] = t;
-  }
+  });
 }
 
 // block = 32 channels x 8 sample slices, slices combined through shared memory
@@ -323,6 +322,7 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
   if (blocks > (hw + min_rows - 1) / min_rows) blocks = (hw + min_rows - 1) / min_rows;
   long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / ((long long)n * 2 * c);      // per-block partial slots
   if (blocks > fit) blocks = fit;
+  if (blocks > 32) blocks = 32;
   if (blocks < 1) blocks = 1;
   long long rpb = (hw + blocks - 1) / blocks;
   blocks = (hw + rpb - 1) / rpb;

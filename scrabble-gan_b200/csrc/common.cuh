@@ -135,11 +135,72 @@ __device__ __forceinline__ bool sg_det_arrive_last(unsigned int* ticket, unsigne
   if (last) __threadfence();
   return last;
 }
-// sum over the nblk slots (slot stride `n` floats) of element j, in slot order; L2 loads (the slots were written by other SMs)
-__device__ __forceinline__ float sg_det_sum(const float* slots, unsigned int nblk, long long n, long long j) {
-  float t = 0.f;
-  for (unsigned int b = 0; b < nblk; ++b) t += __ldcg(slots + (long long)b * n + j);
-  return t;
+// sum over slots [b0, b1) (slot stride `n` floats) of element j, in a FIXED association (four interleaved chains, so that
+// the L2 loads -- the slots were written by other SMs -- overlap instead of forming one long dependent chain)
+__device__ __forceinline__ float sg_det_range_sum(const float* slots, unsigned int b0, unsigned int b1, long long n, long long j) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  unsigned int b = b0;
+  for (; b + 3 < b1; b += 4) {
+    a0 += __ldcg(slots + (long long)b * n + j);
+    a1 += __ldcg(slots + (long long)(b + 1) * n + j);
+    a2 += __ldcg(slots + (long long)(b + 2) * n + j);
+    a3 += __ldcg(slots + (long long)(b + 3) * n + j);
+  }
+  for (; b < b1; ++b) a0 += __ldcg(slots + (long long)b * n + j);
+  return (a0 + a1) + (a2 + a3);
+}
+// Block-cooperative ordered sum of `nblk` slots of `n` floats (1-D blocks of <= 1024 threads; ALL threads must call).  When
+// the block has more threads than elements, the slots are cut into up to 32 contiguous ranges summed by different threads and
+// combined in range order through shared memory.  emit(j, total) runs once per element.  The result depends only on
+// (nblk, n, blockDim), never on timing.
+template <class Emit>
+__device__ __forceinline__ void sg_det_block_reduce(const float* slots, unsigned int nblk, int n, Emit emit) {
+  __shared__ float part_sm[1024];
+  const int nt = blockDim.x, tid = threadIdx.x;
+  for (int j0 = 0; j0 < n; j0 += nt) {
+    const int cols = n - j0 < nt ? n - j0 : nt;
+    int P = nt / cols;
+    if (P > 32) P = 32;
+    if (P > (int)nblk) P = (int)nblk;
+    const int jl = tid % cols, part = tid / cols;
+    if (part < P) {
+      const unsigned int chunk = (nblk + P - 1) / P;
+      unsigned int b0 = part * chunk, b1 = b0 + chunk;
+      if (b1 > nblk) b1 = nblk;
+      part_sm[part * cols + jl] = b0 < b1 ? sg_det_range_sum(slots, b0, b1, n, j0 + jl) : 0.f;
+    }
+    __syncthreads();
+    if (part == 0) {
+      float t = 0.f;
+      for (int q = 0; q < P; ++q) t += part_sm[q * cols + jl];
+      emit(j0 + jl, t);
+    }
+    __syncthreads();
+  }
+}
+// Scheme (B) in full: block `bi` of `nblk` has stored its partial vector in slots[bi * n ...].  Up to 32 blocks: the last
+// arrival sums all slots.  More: two levels -- the last arrival of each group of 16 consecutive blocks sums its group into
+// slots2[group * n ...], and the last group to finish sums the groups -- so no thread ever walks more than ~40 slots.
+// tickets: 1 + ceil(nblk / 16) counters (zero between launches); slots2: ceil(nblk / 16) * n floats.
+#define SG_DET_GROUP 16
+template <class Emit>
+__device__ __forceinline__ void sg_det_finish(const float* slots, float* slots2, unsigned int* tickets, unsigned int nblk, unsigned int bi, int n,
+                                              Emit emit) {
+  if (nblk <= 32) {
+    if (sg_det_arrive_last(tickets, nblk)) sg_det_block_reduce(slots, nblk, n, emit);
+    return;
+  }
+  const unsigned int ngroups = (nblk + SG_DET_GROUP - 1) / SG_DET_GROUP, grp = bi / SG_DET_GROUP;
+  const unsigned int gsize = (grp + 1) * SG_DET_GROUP <= nblk ? SG_DET_GROUP : nblk - grp * SG_DET_GROUP;
+  if (!sg_det_arrive_last(tickets + 1 + grp, gsize)) return;
+  float* mine = slots2 + (long long)grp * n;
+  sg_det_block_reduce(slots + (long long)grp * SG_DET_GROUP * n, gsize, n, [&](int j, float t) { mine[j] = t; });
+  if (!sg_det_arrive_last(tickets, ngroups)) return;
+  sg_det_block_reduce(slots2, ngroups, n, emit);
+}
+// floats of scratch one such reduction needs
+static inline long long sg_det_floats(long long nblk, long long n) {
+  return nblk * n + (nblk > 32 ? (nblk + SG_DET_GROUP - 1) / SG_DET_GROUP * n : 0);
 }
 __device__ __forceinline__ void sg_turn_wait(unsigned int* sem, unsigned int turn) {
   if (turn == 0) return;

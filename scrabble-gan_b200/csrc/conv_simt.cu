@@ -293,12 +293,11 @@ __global__ void __launch_bounds__(256) k_wgrad_narrow(sg_conv_desc d, const void
     for (int l = 0; l < lanes; ++l) sum += red[((long long)l * d.ntaps + t) * wide + c];
     scratch[(long long)blockIdx.x * nout + i] = sum;
   }
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
-  for (int i = threadIdx.x; i < nout; i += 256) {
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * nout, ticket, gridDim.x, blockIdx.x, nout, [&](int i, float sum) {
     int t = i / wide, c = i % wide;
     long long off = d.tap_w_off[t] + (NARROW_IN ? (long long)c * d.w_co_stride : (long long)c * d.w_ci_stride);
-    dw[off] += sg_det_sum(scratch, gridDim.x, nout, i);
-  }
+    dw[off] += sum;
+  });
 }
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -437,12 +436,12 @@ __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ w
     int t = 3 * tg + j;
     if (t < 9) scratch[(long long)blockIdx.x * 576 + t * 64 + c] = (t < ntaps) ? acc[j] : 0.f;
   }
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
-  for (int i = tid; i < ntaps * 64; i += 192) {
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * 576, ticket, gridDim.x, blockIdx.x, 576, [&](int i, float sum) {
     int t = i >> 6, cc = i & 63;
+    if (t >= ntaps) return;
     long long off = d.tap_w_off[t] + (narrow_in ? (long long)cc * d.w_co_stride : (long long)cc * d.w_ci_stride);
-    dw[off] += sg_det_sum(scratch, gridDim.x, 576, i);
-  }
+    dw[off] += sum;
+  });
 }
 
 // forward conv with c_in == 1, c_out % 8 == 0 (<= 64 per pixel group), unit strides: 8 output channels per thread with

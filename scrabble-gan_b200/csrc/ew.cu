@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long 
   }
   if (gridDim.x == 1) return;
   // deterministic combine (common.cuh, scheme B): the last block to arrive sums the per-block partials in block order
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
-  for (int c = threadIdx.x; c < cols; c += NT) out[c] = (accumulate ? out[c] : 0.f) + sg_det_sum(scratch, gridDim.x, cols, c);
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * cols, ticket, gridDim.x, blockIdx.x, cols,
+                [&](int c, float t) { out[c] = (accumulate ? out[c] : 0.f) + t; });
 }
 
 // generic fallback (cols not a multiple of 4): thread t handles columns t, t+blockDim...
@@ -180,8 +180,8 @@ __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long
     for (long long r = r0; r < r1; ++r) acc += sg_ld(x + r * cols + c);
     scratch[(long long)blockIdx.x * cols + c] = acc;
   }
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) out[c] = (accumulate ? out[c] : 0.f) + sg_det_sum(scratch, gridDim.x, cols, c);
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * cols, ticket, gridDim.x, blockIdx.x, cols,
+                [&](int c, float t) { out[c] = (accumulate ? out[c] : 0.f) + t; });
 }
 
 template <typename TO>
@@ -492,7 +492,7 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
   }
   long long blocks = (long long)ctx->num_sms * 4;
   if (blocks > rows) blocks = rows;
-  long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / cols;
+  long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / cols / 2;
   if (blocks > fit) blocks = fit;
   SG_REQUIRE(blocks >= 1, "sg_colsum: cols=%d too wide", cols);
   long long rpb = (rows + blocks - 1) / blocks;

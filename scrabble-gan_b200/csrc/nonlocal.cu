@@ -207,13 +207,12 @@ __global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long
       }
     }
   }
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
   const float alpha = alpha_p ? *alpha_p : 1.f;
-  for (int i = threadIdx.x; i < KA * KB; i += blockDim.x) {
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * (KA * KB), ticket, gridDim.x, blockIdx.x, KA * KB, [&](int i, float sum) {
     int r = i / KB, c = i % KB, s, off;
     seg_find(DW, c, s, off);
-    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sg_det_sum(scratch, gridDim.x, KA * KB, i);
-  }
+    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sum;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -370,13 +369,12 @@ __global__ void __launch_bounds__(256, 1) k_nl_wgrad_mma(long long rows, long lo
     __syncthreads();
   }
   for (int i = threadIdx.x; i < KA * KB; i += 256) scratch[(long long)blockIdx.x * (KA * KB) + i] = red[i];
-  if (!sg_det_arrive_last(ticket, gridDim.x)) return;
   const float alpha = alpha_p ? *alpha_p : 1.f;
-  for (int i = threadIdx.x; i < KA * KB; i += 256) {
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * (KA * KB), ticket, gridDim.x, blockIdx.x, KA * KB, [&](int i, float sum) {
     int r = i / KB, c = i % KB, s, off;
     seg_find(DW, c, s, off);
-    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sg_det_sum(scratch, gridDim.x, KA * KB, i);
-  }
+    DW.p[s][(long long)r * DW.w[s] + off] += alpha * sum;
+  });
 }
 
 template <int K, int N, bool TRANS_W>

@@ -81,8 +81,11 @@ __global__ void k_sn_coldot(const float* __restrict__ w, int rows, int cols, con
     for (int r = r0; r < r1; ++r) acc += v[r] * w[(long long)r * cols + c];
   float* slots = scratch + (long long)blockIdx.x * gridDim.y * blockDim.x;
   slots[(long long)blockIdx.y * blockDim.x + threadIdx.x] = acc * (*v_scale);
-  if (!sg_det_arrive_last(tickets + blockIdx.x, gridDim.y)) return;
-  if (c < cols) t[c] = sg_det_sum(slots, gridDim.y, blockDim.x, threadIdx.x);
+  if (!sg_det_arrive_last(tickets + blockIdx.x, gridDim.y)) return;      // gridDim.y <= 32: one level
+  sg_det_block_reduce(slots, gridDim.y, blockDim.x, [&](int j, float sum) {
+    int cc = blockIdx.x * blockDim.x + j;
+    if (cc < cols) t[cc] = sum;
+  });
 }
 // out[0] = rsqrt(max(sum x^2, 1e-12))   (tf.nn.l2_normalize scale), out[1] = sum x^2
 __global__ void k_sn_invnorm(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -175,7 +178,7 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
     k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(v, rows, sc);
     SG_POST_LAUNCH(ctx);
     int slabs = sg_div_up(rows, 64);
-    if (slabs > 4 * ctx->num_sms) slabs = 4 * ctx->num_sms;
+    if (slabs > 32) slabs = 32;
     SG_REQUIRE(sg_div_up(cols, 128) <= SG_DET_TICKETS, "sg_spectral_norm: too many columns");
     {
       long long fit = (long long)(SG_DET_SCRATCH_BYTES / sizeof(float)) / ((long long)sg_div_up(cols, 128) * 128);

@@ -60,13 +60,12 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
             run_step(rt, *build_models(rt, P)[:3], None, images, labels, fake_labels, z)
             du.GRAPH_ENABLED = True
         G, D, R, _ = build_models(rt, P)
-        n_replayed = rt.replayed_launches
         got, _ = run_step(rt, G, D, R, None, images, labels, fake_labels, z)
-        if graph:
-            assert any(gs.graph is not None for gs in du._graph_cache.values()), "the step must have been captured"
-            assert rt.replayed_launches > n_replayed, "the step must have been REPLAYED from the graph"
+        captured = [gs for gs in du._graph_cache.values() if gs.graph is not None]
+        if graph:       # GRAPH_WARMUP = 0: the first call of the signature captures the step and replays it
+            assert len(captured) == 1 and captured[0].calls == 1 and captured[0].launches > 100, "the step must have been captured and replayed"
         else:
-            assert rt.replayed_launches == n_replayed
+            assert not captured
         assert_stats(got, stats, TOL_OUT[mode], "{} fused step".format(mode))
         tw, tt = TOL[mode]
         for n, m in (("D", D), ("R", R), ("G", G)):
