@@ -41,7 +41,7 @@ Tensor = torch.Tensor
 # edge convolutions.  Accumulation stays in the oracle's dtype.  Because the ReLU / max-pool masks then come from the
 # same rounded operands as on the GPU, gradients can be compared at the bf16 tolerance of north_star (1e-2) instead of
 # at the mask-flip noise level of a comparison against exact arithmetic.  "tf32": the fp32-storage tensor-core mode --
-# the tensor-core convolutions read their fp32 operands as tf32 (low 13 mantissa bits dropped); `wgrad` says whether the
+# the tensor-core convolutions read their fp32 operands as tf32 (rounded to nearest even by the TMA load); `wgrad` says whether the
 # filter gradients run on tf32 tensor cores too (True) or in exact fp32.  None (default) = the exact restatement.
 _ROUND: Optional[str] = None
 _ROUND_WGRAD: bool = True
@@ -54,9 +54,12 @@ def set_operand_rounding(mode: Optional[str], wgrad: bool = True) -> None:
 
 
 def _q_tf32(t: Tensor) -> Tensor:
-    """fp32 -> tf32 as the tensor core reads it: the low 13 mantissa bits are dropped."""
+    """fp32 -> tf32 (10-bit mantissa), round to nearest even: what the TMA unit does when it loads an fp32 tensor through a
+    TFLOAT32 tensor map (measured on B200 with tools/diag_rounding.py: 1.5e-6 against this model, 7e-4 against truncation)."""
     f = t.to(torch.float32).contiguous()
-    return (f.view(torch.int32) & ~0x1FFF).view(torch.float32).to(t.dtype)
+    i = f.view(torch.int32)
+    i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return i.view(torch.float32).to(t.dtype)
 
 
 def _q_bf16(t: Tensor) -> Tensor:
@@ -385,19 +388,26 @@ def generator(inputs, y, p, attention_blocks="B3", training=True, new_stats=None
     return generator_core(z, y, p, attention_blocks, training, new_stats)
 
 
+def _stored(t: Tensor) -> Tensor:
+    """bf16 rounding mode: an activation the CUDA path STORES in bf16 before a max-pool.  Rounding creates ties inside the
+    pooling windows (~1% of them), and the gradient goes to the first maximum of the ROUNDED values, so the rounding has to
+    happen before the pooling here too (for every other consumer rounding at the convolution's input is equivalent)."""
+    return _ste(t, _q_bf16(t)) if _ROUND == "bf16" else t
+
+
 def recognizer_probs(x, p):
     """CRNN trunk of make_recognizer (net_architecture.py:28-55); BN in inference mode (Q5).  -> (B, T, C) softmax."""
-    net = torch.relu(conv2d(x, p["conv1.w"], p["conv1.b"]))
+    net = _stored(torch.relu(conv2d(x, p["conv1.w"], p["conv1.b"])))
     net = max_pool(net, 2, 2)
-    net = torch.relu(conv2d(net, p["conv2.w"], p["conv2.b"]))
+    net = _stored(torch.relu(conv2d(net, p["conv2.w"], p["conv2.b"])))
     net = max_pool(net, 2, 2)
     net = torch.relu(conv2d(net, p["conv3.w"], p["conv3.b"]))
-    net = torch.relu(conv2d(net, p["conv4.w"], p["conv4.b"]))
+    net = _stored(torch.relu(conv2d(net, p["conv4.w"], p["conv4.b"])))
     net = max_pool(net, 2, 1)
     net = torch.relu(conv2d(net, p["conv5.w"], p["conv5.b"]))
     net = batchnorm_infer(net, p["bn5.moving_mean"], p["bn5.moving_var"]) * p["bn5.gamma"] + p["bn5.beta"]
     net = torch.relu(conv2d(net, p["conv6.w"], p["conv6.b"]))
-    net = batchnorm_infer(net, p["bn6.moving_mean"], p["bn6.moving_var"]) * p["bn6.gamma"] + p["bn6.beta"]
+    net = _stored(batchnorm_infer(net, p["bn6.moving_mean"], p["bn6.moving_var"]) * p["bn6.gamma"] + p["bn6.beta"])
     net = max_pool(net, 2, 1)
     net = torch.relu(conv2d(net, p["conv7.w"], p["conv7.b"], padding="valid"))
     net = net.squeeze(1)                                    # (B, T, 512)

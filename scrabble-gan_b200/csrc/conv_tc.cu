@@ -119,13 +119,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout for MN-major tf32)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 @4, a/b format @7/@10 (BF16=1, TF32=2),
@@ -427,7 +428,11 @@ struct alignas(64) TcWgradParams {
   int a_chunks, b_chunks, stages;
   uint32_t chunk_bytes, stage_stride;
   float* dw;
-  unsigned int* sems;           // one turn semaphore per (tap, co tile, ci tile): the pixel splits of a tile add in split order
+  unsigned int* sems;           // one semaphore / ticket per (tap, co tile, ci tile)
+  float* partial;               // det_mode 2: per-(tile, split) partial tiles [128][BN] fp32
+  int det_mode;                 // how the pixel splits of a filter tile are combined (always in split order: bitwise repeatable)
+                                //   0: one split, added straight into dw   1: ordered turns (<= 4 splits)
+                                //   2: partial tiles in scratch, summed by the last split to arrive (many splits)
 };
 
 template <typename TIn>
@@ -438,6 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -520,9 +526,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
         if (lane == 0) {
           uint32_t a_addr = smem_base + s * p.stage_stride;
           uint32_t b_addr = a_addr + p.a_chunks * p.chunk_bytes;
-          // MN-major, 128B swizzle: LBO = distance between 128-byte channel chunks, SBO = 8 pixel rows = 1024 B
-          uint64_t da = make_smem_desc(a_addr, p.chunk_bytes, 1024);
-          uint64_t db = make_smem_desc(b_addr, p.chunk_bytes, 1024);
+          // MN-major, 128B swizzle: LBO = distance between 128-byte channel chunks, SBO = distance between swizzle atoms
+          // along the pixel (K) axis: 8 pixel rows = 1024 B with 16-byte atoms (bf16); tf32 MN-major operands must use the
+          // 32-byte-atom variant of the 128B swizzle (TMA: SWIZZLE_128B_ATOM_32B), whose pattern repeats every 4 rows = 512 B
+          uint64_t da = make_smem_desc(a_addr, p.chunk_bytes, kTf32 ? 512 : 1024, kTf32 ? 1 : 2);
+          uint64_t db = make_smem_desc(b_addr, p.chunk_bytes, kTf32 ? 512 : 1024, kTf32 ? 1 : 2);
           const int ksteps = PR / UK;
           const uint32_t kadv = (UK * 128) >> 4;
           for (int k = 0; k < ksteps; ++k)
@@ -553,32 +561,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       float* wbase = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
-      // Deterministic split combine (common.cuh, scheme A): the pixel splits of one filter tile add their partial tiles in
-      // split order.  Unit (tile, sp) only waits on unit (tile, sp - 1), which has a lower unit index: it was taken earlier
-      // by its CTA (static round-robin, every CTA walks its units in increasing order), so the wait always ends.
-      if (p.splits > 1) {
-        if (threadIdx.x == 64) sg_turn_wait(p.sems + tile, (unsigned int)sp);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
-      for (int ch = 0; ch < p.BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        if (valid) {
-          int ci0 = cit * p.BN + ch * 32;
+      if (p.det_mode == 2) {
+        // Many pixel splits: every split stores its partial tile in its own scratch slot (one 128-byte line per lane and
+        // chunk), takes a ticket, and the split that arrives LAST adds the slots in split order into dw -- the order of
+        // the additions never depends on timing (common.cuh, scheme B).
+        float* slot = p.partial + ((long long)tile * p.splits + sp) * (128 * p.BN) + (long long)row * p.BN;
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int ci = ci0 + j;
-            if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            __stcg(reinterpret_cast<float4*>(slot + ch * 32 + j),
+                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * as);                    // the accumulator is free again: the next unit's MMAs may start
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          unsigned int tk = atomicAdd(p.sems + tile, 1u);
+          s_last = (tk == (unsigned int)p.splits - 1) ? 1u : 0u;
+          if (s_last) { p.sems[tile] = 0u; __threadfence(); }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last && valid) {
+          const float* base = p.partial + (long long)tile * p.splits * (128 * p.BN) + (long long)row * p.BN;
+          for (int ch = 0; ch < p.BN / 32; ++ch) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll 2
+            for (int s2 = 0; s2 < p.splits; ++s2) {
+              const float4* src = reinterpret_cast<const float4*>(base + (long long)s2 * (128 * p.BN) + ch * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 q = __ldcg(src + j);
+                acc[4 * j] += q.x; acc[4 * j + 1] += q.y; acc[4 * j + 2] += q.z; acc[4 * j + 3] += q.w;
+              }
+            }
+            int ci0 = cit * p.BN + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int ci = ci0 + j;
+              if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, acc[j]);
+            }
           }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // s_last is rewritten by the next unit
+      } else {
+        // Ordered turns (common.cuh, scheme A): the few pixel splits of one filter tile add their partial tiles in split
+        // order.  Unit (tile, sp) only waits on unit (tile, sp - 1), which has a lower unit index: it was taken earlier by
+        // its CTA (static round-robin, every CTA walks its units in increasing order), so the wait always ends.
+        if (p.det_mode == 1) {
+          if (threadIdx.x == 64) sg_turn_wait(p.sems + tile, (unsigned int)sp);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          if (valid) {
+            int ci0 = cit * p.BN + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int ci = ci0 + j;
+              if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, __uint_as_float(v[j]));
+            }
+          }
+        }
+        if (p.det_mode == 1) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) sg_turn_pass(p.sems + tile, (unsigned int)sp, (unsigned int)p.splits);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * as);
       }
-      if (p.splits > 1) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) sg_turn_pass(p.sems + tile, (unsigned int)sp, (unsigned int)p.splits);
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * as);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -675,7 +732,8 @@ static inline int posmod(int a, int b) { return a - floordiv(a, b) * b; }
 
 // 4-D NHWC view (optionally a stride-phase view): dims {c, wv, hv, n}
 static int encode_nhwc_view(PFN_encodeTiled enc, CUtensorMap* m, int dt, const void* base, int n, int h, int w, int c, int sy,
-                            int sx, int py, int px, int box_c, int box_w, int box_h, int box_n) {
+                            int sx, int py, int px, int box_c, int box_w, int box_h, int box_n,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   size_t e = dt == SG_F32 ? 4 : 2;
   int hv = (h - py + sy - 1) / sy, wv = (w - px + sx - 1) / sx;
   if (hv < 1) hv = 1;
@@ -686,7 +744,7 @@ static int encode_nhwc_view(PFN_encodeTiled enc, CUtensorMap* m, int dt, const v
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const char* addr = (const char*)base + ((size_t)py * w + px) * c * e;
   CUresult r = enc(m, dt == SG_F32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)addr, gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     sg_set_error("cuTensorMapEncodeTiled(4d) failed: %d (dims %d,%d,%d,%d box %d,%d,%d,%d)", (int)r, c, wv, hv, n, box_c, box_w,
@@ -996,11 +1054,9 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   int rc = tc_check(d, "sg_conv_wgrad_tc");
   if (rc != SG_OK) return rc;
   SG_REQUIRE(d->out_dt == d->in_dt, "sg_conv_wgrad_tc: dy must have the operand dtype (in_dt)");
-  if (d->in_dt != SG_BF16) {
-    // MN-major tf32 operands need the 128B-swizzle/32B-atom shared-memory layout, which is not built yet
-    sg_set_error("sg_conv_wgrad_tc: only bf16 operands are supported (tf32 filter gradients use sg_conv_wgrad_simt)");
-    return SG_ERR_UNSUPPORTED;
-  }
+  // fp32 operands are read as tf32: both operands are MN-major, which for 4-byte types exists only in the 32-byte-atom
+  // flavour of the 128B swizzle (TMA SWIZZLE_128B_ATOM_32B + UMMA layout type SWIZZLE_128B_BASE32B)
+  const CUtensorMapSwizzle swz = d->in_dt == SG_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   SG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)dy & 15) == 0, "sg_conv_wgrad_tc: pointers must be 16-byte aligned");
   PFN_encodeTiled enc;
   rc = get_encode(ctx, &enc);
@@ -1059,6 +1115,14 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   }
   p.ptiles_per_split = sg_div_up(ptiles, splits);
   p.splits = sg_div_up(ptiles, p.ptiles_per_split);
+  p.partial = ctx->det_scratch;
+  p.det_mode = p.splits == 1 ? 0 : (p.splits <= 4 ? 1 : 2);
+  if (p.det_mode == 2 && (long long)base_units * p.splits * 128 * p.BN * (long long)sizeof(float) > (long long)SG_DET_SCRATCH_BYTES) {
+    // the partial tiles would not fit the context's scratch: fall back to 4 ordered splits
+    p.ptiles_per_split = sg_div_up(ptiles, 4);
+    p.splits = sg_div_up(ptiles, p.ptiles_per_split);
+    p.det_mode = p.splits == 1 ? 0 : 1;
+  }
 
   bool used[4] = {false, false, false, false};
   for (int t = 0; t < d->ntaps; ++t) {
@@ -1075,13 +1139,13 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
     if (!used[v]) continue;
     if (first_used < 0) first_used = v;
     rc = encode_nhwc_view(enc, &p.map_in[v], d->in_dt, in, d->n, d->in_h, d->in_w, d->c_in, d->in_sy, d->in_sx, v / 2, v % 2, KC,
-                          p.TW, p.TH, p.TN);
+                          p.TW, p.TH, p.TN, swz);
     if (rc != SG_OK) return rc;
   }
   for (int v = 0; v < 4; ++v)
     if (!used[v]) p.map_in[v] = p.map_in[first_used];
   rc = encode_nhwc_view(enc, &p.map_dy, d->in_dt, dy, d->n, d->out_h, d->out_w, d->c_out, d->out_sy, d->out_sx, d->out_py,
-                        d->out_px, KC, p.TW, p.TH, p.TN);
+                        d->out_px, KC, p.TW, p.TH, p.TN, swz);
   if (rc != SG_OK) return rc;
 
   long long units = base_units * p.splits;

@@ -13,7 +13,7 @@
 template <int GT_K>
 __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                               const float* __restrict__ bias, int accumulate, int k_per_split, unsigned int* __restrict__ sems) {
+                                               const float* __restrict__ bias, int accumulate, int k_per_split, float* __restrict__ scratch, unsigned int* __restrict__ tickets) {
   __shared__ float As[GT_K][GT_M + 4];
   __shared__ float Bs[GT_K][GT_N + 4];
   const int tid = threadIdx.x;
@@ -64,32 +64,43 @@ __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int 
     }
     __syncthreads();
   }
-  // split-K: the splits of a tile add into C in split order (ordered turns, common.cuh scheme A): bitwise repeatable
-  unsigned int* sem = sems + (long long)blockIdx.y * gridDim.x + blockIdx.x;
-  if (split) {
-    if (threadIdx.x == 0) sg_turn_wait(sem, blockIdx.z);
-    __syncthreads();
-  }
+  if (!split) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
+    for (int i = 0; i < 4; ++i) {
+      int gm = m0 + ty * 4 + i;
+      if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (bias && blockIdx.z == 0) v += bias[gn];
-      float* p = C + (long long)gm * ldc + gn;
-      if (split) { atomicAdd(p, v); continue; }
-      if (accumulate) v += *p;
-      *p = v;
+      for (int j = 0; j < 4; ++j) {
+        int gn = n0 + tx * 4 + j;
+        if (gn >= N) continue;
+        float v = acc[i][j];
+        if (bias) v += bias[gn];
+        float* p = C + (long long)gm * ldc + gn;
+        if (accumulate) v += *p;
+        *p = v;
+      }
     }
+    return;
   }
-  if (split) {
-    __syncthreads();
-    if (threadIdx.x == 0) sg_turn_pass(sem, blockIdx.z, gridDim.z);
-  }
+  // split-K, deterministic (common.cuh scheme B): every split stores its 64 x 64 partial tile in its own scratch slot; the
+  // last split of the tile to arrive adds the slots in split order and writes C (+ bias, + previous C when accumulating)
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const unsigned int nsp = gridDim.z, tk_per_tile = 1 + (nsp + SG_DET_GROUP - 1) / SG_DET_GROUP;
+  const long long fl_per_tile = (long long)GT_M * GT_N * (nsp + (nsp > 32 ? (nsp + SG_DET_GROUP - 1) / SG_DET_GROUP : 0));
+  float* slots = scratch + (long long)tile * fl_per_tile;
+  float* mine = slots + (long long)blockIdx.z * (GT_M * GT_N);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(mine + (ty * 4 + i) * GT_N + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  sg_det_finish(slots, slots + (long long)nsp * (GT_M * GT_N), tickets + (long long)tile * tk_per_tile, nsp, blockIdx.z, GT_M * GT_N,
+                [&](int idx, float t) {
+                  int gm = m0 + idx / GT_N, gn = n0 + idx % GT_N;
+                  if (gm >= M || gn >= N) return;
+                  float* p = C + (long long)gm * ldc + gn;
+                  float v = t + (bias ? bias[gn] : 0.f);
+                  if (accumulate) v += *p;
+                  *p = v;
+                });
 }
 
 extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, const float* a, int lda,
@@ -110,14 +121,18 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
     k_per_split = ((k + splits - 1) / splits + 15) / 16 * 16;
     splits = (k + k_per_split - 1) / k_per_split;
   }
-  if (splits > 1 && !accumulate) {
-    SG_REQUIRE(ldc == n, "sg_gemm: split-K without accumulate needs a contiguous C");
-    SG_CHECK_CUDA(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, ctx->stream));
+  if (splits > 1) {      // scratch / ticket budget of the deterministic split combine
+    long long fl = (long long)tiles * GT_M * GT_N * (splits + (splits + SG_DET_GROUP - 1) / SG_DET_GROUP);
+    long long tk = (long long)tiles * (1 + (splits + SG_DET_GROUP - 1) / SG_DET_GROUP);
+    if (fl * (long long)sizeof(float) > (long long)SG_DET_SCRATCH_BYTES || tk > SG_DET_TICKETS) {
+      splits = 1;
+      k_per_split = k > 0 ? k : 1;
+    }
   }
   grid.z = splits;
   // (a one-shot GT_K = 64 instantiation for K <= 64 measured SLOWER than the 16-wide loop on the CBN Dense layers --
   //  19 us vs 10 us per launch in profiles/r01_launches_step.csv -- so the generic loop is used for every shape)
-  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split, ctx->det_tickets);
+  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split, ctx->det_scratch, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

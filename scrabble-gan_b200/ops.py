@@ -170,10 +170,16 @@ def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_pac
 
 
 def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False) -> None:
-    """dw_master += filter gradient of the conv described by d."""
-    if not force_simt and tc_ok(rt, d) and d.in_dt == SG_BF16 and d.out_dt == SG_BF16:
+    """dw_master += filter gradient of the conv described by d: on the tensor cores whenever the layer is eligible and both
+    operands have the mode's operand dtype (bf16, or fp32 read as tf32 in "tf32" mode); the FFMA kernel serves the edge
+    layers (Cin = 1 / Cout = 1) and the exact "fp32" mode -- by rule, not as a silent fallback."""
+    tc_dt = SG_BF16 if rt.mode == "bf16" else (SG_F32 if (rt.mode == "tf32" and rt.tf32_wgrad_tc) else None)
+    if not force_simt and tc_dt is not None and d.in_dt == tc_dt and d.out_dt == tc_dt and tc_ok(rt, d):
         call.sg_conv_wgrad_tc(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _V(None), 0)
     else:
+        if rt.use_tc and tc_ok(rt, d) and not force_simt and d.in_dt != d.out_dt:
+            raise _abi.SganError("conv_wgrad: tensor-core layer with mixed operand dtypes (in {}, dy {}): the producer must write the "
+                                 "operand dtype".format(d.in_dt, d.out_dt))
         call.sg_conv_wgrad_simt(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master))
 
 

@@ -60,6 +60,8 @@ class Runtime:
         self.direct_nmajor = os.environ.get("SGAN_DIRECT_NMAJOR", "0") == "1"
         self.fuse_shortcut = os.environ.get("SGAN_NO_FUSED_SHORTCUT", "0") != "1"
         self.merge_r_backward = os.environ.get("SGAN_NO_MERGED_R_BWD", "0") != "1"
+        # "tf32" mode: filter gradients on the tensor cores too (fp32 operands read as tf32, MN-major 32-byte-atom swizzle)
+        self.tf32_wgrad_tc = os.environ.get("SGAN_TF32_WGRAD_SIMT", "0") != "1"
         call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------

@@ -143,9 +143,84 @@ def g_isolation(rt, mode, sigma):
     table("G grads", G.store.grad_dict(), {k: v.grad for k, v in leaf.items() if v.requires_grad})
 
 
+def g_stages(rt, mode, sigma=0.0):
+    """stage-by-stage forward of G against the (rounded) oracle"""
+    rt.set_mode(mode)
+    layers = importlib.import_module("scrabble-gan_b200.layers")
+    dt = torch.float64
+    P = make_params(40, dt, sigma=sigma)["G"]
+    g = torch.Generator().manual_seed(7)
+    b, l = 4, 3
+    z = torch.randn(b, 128, generator=g, dtype=dt)
+    y = torch.randint(0, 52, (b, l), generator=g)
+    O.set_operand_rounding(mode if mode != "fp32" else None)
+    try:
+        zs = torch.split(z, 32, dim=1)
+        exp = {}
+        net = O.filter_bank(zs[0], y, P["filter_bank"])
+        exp["bank"] = net
+        for i in range(3):
+            name = "B%d" % (i + 1)
+            net = O.resnet_block_up(net, zs[i + 1], P, name, i == 2, True, {})
+            exp[name] = net
+            if name == "B3":
+                net = O.non_local_block(net, P, name + ".attn")
+                exp["attn"] = net
+        xh, _, _ = O.batchnorm_train(net, P["bn.moving_mean"], P["bn.moving_var"])
+        act = torch.relu(xh * P["bn.gamma"] + P["bn.beta"])
+        exp["act"] = act
+        exp["pre"] = O.conv2d(act, P["out.w"], P["out.b"])
+    finally:
+        O.set_operand_rounding(None)
+    G, _, _, _ = build_models(rt, make_params(40, dt, sigma=sigma))
+    zd, yd = z.float().to(rt.device), y.to(rt.device, torch.int32)
+    print("G stages mode={} sigma={}".format(mode, sigma))
+    net, _ = G.embed.forward(rt, zd, 128, yd)
+    print("  bank : {:.3e}".format(rel_max(net, exp["bank"])))
+    for i, blk in enumerate(G.blocks):
+        net, _ = blk.forward(rt, net, zd[:, 32 * (i + 1):], 128, True)
+        print("  B{}   : {:.3e}".format(i + 1, rel_max(net, exp["B%d" % (i + 1)])))
+        if i in G.attn:
+            net, _ = G.attn[i].forward(rt, net)
+            print("  attn : {:.3e}".format(rel_max(net, exp["attn"])))
+    mean, rstd, count = layers.batch_stats(rt, net, G.bn, update_moving=False)
+    act = ops.bn_apply(rt, net, mean, rstd, G.bn.gamma.data, G.bn.beta.data, False, True, rt.op_dt)
+    print("  act  : {:.3e}".format(rel_max(act.float(), exp["act"])))
+    pre = G.out.forward(rt, act)
+    print("  pre  : {:.3e}  (max |pre| {:.3f})".format(rel_max(pre, exp["pre"]), float(exp["pre"].abs().max())))
+    # block 1 in detail
+    blk = G.blocks[0]
+    x0, _ = G.embed.forward(rt, zd, 128, yd)
+    O.set_operand_rounding(mode if mode != "fp32" else None)
+    try:
+        e_a1 = torch.relu(O.conditional_batchnorm(exp["bank"], zs[1], P, "B1.cbn1", True, {}))
+        e_u = O.conv2d_transpose(e_a1, P["B1.up.w"], P["B1.up.b"], (2, 2))
+        e_a2 = torch.relu(O.conditional_batchnorm(e_u, zs[1], P, "B1.cbn2", True, {}))
+        e_h = O.conv2d(e_a2, P["B1.conv.w"], P["B1.conv.b"])
+        e_s = O.conv2d_transpose(exp["bank"], P["B1.short.w"], P["B1.short.b"], (2, 2))
+    finally:
+        O.set_operand_rounding(None)
+    zi = zd[:, 32:]
+    a1, _ = blk.cbn1.forward(rt, x0, zi, 128, True, True, rt.op_dt)
+    print("  B1.a1: {:.3e}".format(rel_max(a1.float(), e_a1)))
+    u = blk.up.forward(rt, a1)
+    print("  B1.u : {:.3e}".format(rel_max(u, e_u)))
+    a2, _ = blk.cbn2.forward(rt, u, zi, 128, True, True, rt.op_dt)
+    print("  B1.a2: {:.3e}".format(rel_max(a2.float(), e_a2)))
+    h = blk.conv.forward(rt, a2)
+    print("  B1.h : {:.3e}".format(rel_max(h, e_h)))
+    xs = ops.cast(rt, x0, rt.op_dt)
+    sh = blk.short.forward(rt, xs, out=torch.zeros_like(h), accumulate=True)
+    print("  B1.sh: {:.3e}".format(rel_max(sh, e_s)))
+
+
 def main():
     rt = runtime.Runtime(device=0, mode="fp32")
     runtime.set_runtime(rt)
+    if len(sys.argv) > 1 and sys.argv[1] == "g":
+        for mode in ("fp32", "bf16", "tf32"):
+            g_stages(rt, mode)
+        return
     tf32_mode_probe(rt)
     for mode in ("bf16", "tf32"):
         for sigma in (0.0, 0.2):
