@@ -246,6 +246,185 @@ def run_secondary(args):
                       "config": {"workload": name}, "gpu_launches": int(rt.launch_count() - n0)}), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# secondary legs of the one driver-visible line (C4 at L = 10 and with per-step random lengths, the
+# fp32-class tf32 mode, C2 generator inference, C3 recogniser + CTC, C5 at 128 per GPU) and the data-parallel check
+# ----------------------------------------------------------------------------------------------------
+def _timed(torch, fn, steps, barrier):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_legs(args, rt, mods, nets, opts, barrier, world, rank):
+    import numpy as np
+    import torch
+    du, dp, na = mods["du"], mods["dp"], mods["na"]
+    G, D, R, gan = nets
+    g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = opts
+    B = args.batch
+    rng = np.random.RandomState(4321 + rank)
+    out = {}
+
+    def data(b, lr, lf):
+        return tuple(t.to(rt.device) for t in (
+            torch.from_numpy(rng.uniform(-1, 1, size=(b, 32, 16 * lr, 1)).astype(np.float32)),
+            torch.from_numpy(rng.randint(0, 52, size=(b, lr)).astype(np.int32)),
+            torch.from_numpy(rng.randint(0, 52, size=(b, lf)).astype(np.int32)),
+            torch.from_numpy(rng.standard_normal(size=(b, 128)).astype(np.float32))))
+
+    def step_on(bufs, i, b):
+        imgs, labels, fake, z = bufs
+        return du.train_step(0, i, 1, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn, disc_iters, agb,
+                             None, 10, "", fake_labels=fake, noise=z, return_device_stats=True)
+
+    def leg_fixed(name, b, length, steps, note):
+        bufs = data(b, length, length)
+        for i in range(4):
+            step_on(bufs, i, b)
+        ms = _timed(torch, lambda i: step_on(bufs, i, b), steps, barrier)
+        gf = step_gflop_per_image(length, length)
+        out[name] = {"workload": note, "ms_per_step": ms, "images_per_s": b * world / (ms * 1e-3), "steps": steps, "dtype": rt.mode,
+                     "algorithmic_tflops_per_gpu": gf * 1e-3 * b / (ms * 1e-3)}
+
+    if world == 1:
+        leg_fixed("c4_fixed_L10", B, 10, 10, "full G+D+R step, batch %d, fixed 10-char words (32x160)" % B)
+        # per-step (L_real, L_fake) ~ U{1..10} from the shared-seed schedule every rank agrees on.  Every
+        # signature gets its own CUDA graph out of one shared memory pool; the warm-up below visits each pair of the timed
+        # schedule until it is captured (one eager call + the capturing call), as the first epoch of a training run does.
+        steps = 60
+        sched = [dp.length_schedule(s, seed=1234) for s in range(steps)]
+        pairs = sorted(set(sched))
+        bufs = {pr: data(B, pr[0], pr[1]) for pr in pairs}
+        old_warm = du.GRAPH_WARMUP
+        du.GRAPH_WARMUP = 1
+        t0 = time.perf_counter()
+        for pr in pairs:
+            for i in range(3):
+                step_on(bufs[pr], i, B)
+        torch.cuda.synchronize()
+        warm_s = time.perf_counter() - t0
+        r0 = rt.replayed_launches
+        n0 = rt.launch_count()
+        ms = _timed(torch, lambda i: step_on(bufs[sched[i]], i, B), steps, barrier)
+        replayed = rt.replayed_launches - r0
+        total = rt.launch_count() - n0
+        du.GRAPH_WARMUP = old_warm
+        gf = sum(step_gflop_per_image(a, b_) for a, b_ in sched) / steps
+        out["c4_random_L"] = {"workload": "full G+D+R step, batch %d, per-step (L_real, L_fake) ~ U{1..10} (dp.length_schedule, seed 1234)" % B,
+                              "ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "steps": steps, "dtype": rt.mode,
+                              "distinct_length_pairs": len(pairs), "fused_pairs": sum(1 for a, b_ in pairs if a == b_),
+                              "launches_replayed_from_graphs_frac": replayed / max(total, 1), "warmup_s_all_pairs": warm_s,
+                              "mean_gflop_per_image": gf, "algorithmic_tflops_per_gpu": gf * 1e-3 * B / (ms * 1e-3)}
+        # fp32-class mode: fp32 storage, tf32 tensor-core operands for forward, dgrad AND wgrad
+        mode0 = rt.mode
+        rt.set_mode("tf32")
+        try:
+            leg_fixed("c4_tf32_L5", B, args.length, 10, "full G+D+R step, batch %d, fixed %d-char words, tf32 operands / fp32 storage" % (B, args.length))
+        finally:
+            rt.set_mode(mode0)
+        # C2: generator-only inference, 256 words of 1-10 characters in length buckets (run_inference path, training=False)
+        lengths = rng.randint(1, 11, size=256)
+        buckets = [(l, int((lengths == l).sum())) for l in range(1, 11) if (lengths == l).any()]
+        inf = [(torch.from_numpy(rng.standard_normal(size=(n, 128)).astype(np.float32)).to(rt.device),
+                torch.from_numpy(rng.randint(0, 52, size=(n, l)).astype(np.int32)).to(rt.device)) for l, n in buckets]
+        for _ in range(3):
+            [G([z, y], training=False) for z, y in inf]
+        ms = _timed(torch, lambda i: [G([z, y], training=False) for z, y in inf], 10, barrier)
+        out["c2_inference"] = {"workload": "generator-only inference (training=False), 256 words of 1-10 chars in %d length buckets" % len(buckets),
+                               "ms_per_batch": ms, "images_per_s": 256 / (ms * 1e-3), "dtype": rt.mode}
+        # C3: recogniser CRNN + CTC forward + backward, batch 256, 32x160, 80-class alphabet (81 outputs)
+        R81 = na.make_recognizer((32, 160, 1), None, 81, vis_model=False, rt=rt, seed=9)
+        x = torch.from_numpy(rng.uniform(-1, 1, size=(256, 32, 160, 1)).astype(np.float32)).to(rt.device)
+        y = torch.from_numpy(rng.randint(0, 80, size=(256, 10)).astype(np.int32)).to(rt.device)
+
+        def r_step(i):
+            R81.store.zero_grad()
+            loss, cache = R81.forward(rt, x, y)
+            R81.backward(rt, cache, None, wgrad=True, want_dx=False)
+        for i in range(3):
+            r_step(i)
+        ms = _timed(torch, r_step, 10, barrier)
+        out["c3_recognizer_ctc"] = {"workload": "recognizer CRNN + CTC fwd/bwd, batch 256, 32x160 images, 81 outputs", "ms_per_batch": ms,
+                                    "images_per_s": 256 / (ms * 1e-3), "dtype": rt.mode,
+                                    "algorithmic_tflops": 3 * 1.978 * 1e-3 * 256 / (ms * 1e-3)}
+    else:
+        # C5: bf16, 128 per GPU (global 1024 at 8 GPUs), sync-BN + gradient all-reduce
+        leg_fixed("c5_b128_per_gpu", 128, args.length, 10,
+                  "bf16 full step, 128 per GPU x %d GPUs = global batch %d, sync-BN + NCCL gradient all-reduce" % (world, 128 * world))
+    return out
+
+
+def dp_check(args, rt, mods, nets, world, rank):
+    """Driver-visible data-parallel correctness (tests/test_dp_gpu.py cannot run on the 1-GPU test box):
+    (i) after the timed steps every replica holds bit-identical weights; (ii) one fp32 step on tiny shapes: N replicas on
+    their shards == ONE replica on the concatenated batch (gradients, relative L2 per network)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    du, na, nl, optim, runtime = mods["du"], mods["na"], mods["nl"], mods["optim"], mods["runtime"]
+    res = {}
+    sums = []
+    for m in nets[:3]:
+        w = m.store.w
+        sums += [int(w.view(torch.int32).to(torch.int64).sum().item()), int(m.store.s.view(torch.int32).to(torch.int64).sum().item())]
+    t = torch.tensor(sums, device=rt.device, dtype=torch.int64)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    res["weights_bit_identical_across_replicas"] = bool(all(torch.equal(allt[0], a) for a in allt))
+
+    graph0, mode0 = du.GRAPH_ENABLED, rt.mode
+    du.GRAPH_ENABLED = False
+    rt.set_mode("fp32")
+    try:
+        b, l, in_dim = 2, 2, (32, 160, 1)
+
+        def shard(r):
+            g = np.random.RandomState(777 + r)
+            return (g.uniform(-1, 1, size=(b, 32, 16 * l, 1)).astype(np.float32), g.randint(0, 52, size=(b, l)).astype(np.int32),
+                    g.randint(0, 52, size=(b, l)).astype(np.int32), g.standard_normal(size=(b, 128)).astype(np.float32))
+
+        def run(rt_, data, bsz):
+            G = na.make_generator(128, in_dim, (32, 8192), None, "B3", 52, vis_model=False, rt=rt_, seed=12)
+            D = na.make_discriminator(in_dim, None, "B1", vis_model=False, rt=rt_, seed=11)
+            R = na.make_recognizer(in_dim, None, 53, vis_model=False, rt=rt_, seed=13)
+            for m in (G, D):
+                for v in m.store.vars:
+                    if v.name.endswith(".sigma"):
+                        v.assign(np.array([0.1], np.float32))
+            gan = na.make_gan(G, D, R, None, vis_model=False)
+            g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+            imgs, labels, fake, z = data
+            stats = du.train_step(0, 0, 1, imgs, labels, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, bsz, 128, loss_fn, disc_iters,
+                                  agb, None, 10, "", fake_labels=fake, noise=z)
+            return stats, [m.store.g.clone() for m in (G, D, R)]
+
+        stats_dp, g_dp = run(rt, shard(rank), b)
+        rt1 = runtime.Runtime(device=rt.device_index, mode="fp32")          # a single-replica runtime on the same GPU
+        parts = [shard(r) for r in range(world)]
+        big = tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(4))
+        stats_1, g_1 = run(rt1, big, b * world)
+        errs = {}
+        for name, a, e in zip("GDR", g_dp, g_1):
+            errs[name] = float(((a.double() - e.double()).norm() / e.double().norm().clamp_min(1e-30)).item())
+        worst = torch.tensor([max(errs.values()), max(abs(x - y) / max(abs(y), 1e-2) for x, y in zip(stats_dp, stats_1))], device=rt.device,
+                             dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        res["bigbatch_step_fp32"] = {"shapes": "batch %d per replica, %d-char words" % (b, l), "grad_rel_l2_rank0": errs,
+                                     "grad_rel_l2_max_over_ranks": float(worst[0]), "stats_rel_max_over_ranks": float(worst[1]),
+                                     "ok": bool(worst[0] <= 1e-3 and worst[1] <= 1e-3)}
+    finally:
+        du.GRAPH_ENABLED = graph0
+        rt.set_mode(mode0)
+        runtime.set_runtime(rt)
+    return res
+
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
@@ -266,6 +445,7 @@ def main():
     ap.add_argument("--workload", default="step", choices=["step", "inference", "recognizer"],
                     help="step = BASELINE configs[3] (default, the driver's line); inference = configs[1] (generator-only, batch "
                          "256, 1-10 char words); recognizer = configs[2] (CRNN + CTC fwd/bwd, batch 256, 32x160, 81 classes)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary legs (L=10, random lengths, tf32, C2, C3, C5) and dp_check")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -399,6 +579,18 @@ def main():
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
 
+    secondary, dpc = None, None
+    if not args.no_secondary and not args.profile_range:
+        mods = {"du": du, "dp": dp, "na": na, "nl": nl, "optim": optim, "runtime": runtime}
+        ops.conv_run = orig_conv_run
+        try:
+            if world > 1:
+                dpc = dp_check(args, rt, mods, (G, D, R, gan), world, rank)
+            secondary = secondary_legs(args, rt, mods, (G, D, R, gan), (g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb), barrier, world, rank)
+        except Exception as ex:          # a secondary leg never costs the headline line
+            import traceback
+            secondary = {"error": repr(ex)[:300], "trace": traceback.format_exc()[-600:]}
+
     tt = torch.tensor([ms_dev, t_e2e * 1e3], device=rt.device, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
@@ -438,6 +630,10 @@ def main():
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline}
+        if secondary is not None:
+            line["secondary"] = secondary
+        if dpc is not None:
+            line["dp_check"] = dpc
         if world == 1 and not args.no_cpu_baseline:
             try:
                 t, threads, cb = cpu_reference_step_time(args.cpu_baseline_batch, L, 2, 1)

@@ -135,19 +135,19 @@ __device__ __forceinline__ bool sg_det_arrive_last(unsigned int* ticket, unsigne
   if (last) __threadfence();
   return last;
 }
-// sum over slots [b0, b1) (slot stride `n` floats) of element j, in a FIXED association (four interleaved chains, so that
+// sum over slots [b0, b1) (slot stride `n` floats) of element j, in a FIXED association (eight interleaved chains, so that
 // the L2 loads -- the slots were written by other SMs -- overlap instead of forming one long dependent chain)
 __device__ __forceinline__ float sg_det_range_sum(const float* slots, unsigned int b0, unsigned int b1, long long n, long long j) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
   unsigned int b = b0;
-  for (; b + 3 < b1; b += 4) {
-    a0 += __ldcg(slots + (long long)b * n + j);
-    a1 += __ldcg(slots + (long long)(b + 1) * n + j);
-    a2 += __ldcg(slots + (long long)(b + 2) * n + j);
-    a3 += __ldcg(slots + (long long)(b + 3) * n + j);
+  for (; b + 7 < b1; b += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += __ldcg(slots + (long long)(b + k) * n + j);
   }
-  for (; b < b1; ++b) a0 += __ldcg(slots + (long long)b * n + j);
-  return (a0 + a1) + (a2 + a3);
+  for (; b < b1; ++b) a[0] += __ldcg(slots + (long long)b * n + j);
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 // Block-cooperative ordered sum of `nblk` slots of `n` floats (1-D blocks of <= 1024 threads; ALL threads must call).  When
 // the block has more threads than elements, the slots are cut into up to 32 contiguous ranges summed by different threads and

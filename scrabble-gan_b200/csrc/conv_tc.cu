@@ -432,7 +432,7 @@ struct alignas(64) TcWgradParams {
   float* partial;               // det_mode 2: per-(tile, split) partial tiles [128][BN] fp32
   int det_mode;                 // how the pixel splits of a filter tile are combined (always in split order: bitwise repeatable)
                                 //   0: one split, added straight into dw   1: ordered turns (<= 4 splits)
-                                //   2: partial tiles in scratch, summed by the last split to arrive (many splits)
+                                //   2: partial tiles in scratch, grid barrier, summation shared by all CTAs (many splits)
 };
 
 template <typename TIn>
@@ -443,7 +443,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -564,8 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
       if (p.det_mode == 2) {
         // Many pixel splits: every split stores its partial tile in its own scratch slot (one 128-byte line per lane and
-        // chunk), takes a ticket, and the split that arrives LAST adds the slots in split order into dw -- the order of
-        // the additions never depends on timing (common.cuh, scheme B).
+        // chunk); after the unit loop the whole grid meets at a barrier and ALL CTAs share the ordered summation (below).
         float* slot = p.partial + ((long long)tile * p.splits + sp) * (128 * p.BN) + (long long)row * p.BN;
         for (int ch = 0; ch < p.BN / 32; ++ch) {
           uint32_t v[32];
@@ -576,39 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
         }
         tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * as);                    // the accumulator is free again: the next unit's MMAs may start
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          __threadfence();
-          unsigned int tk = atomicAdd(p.sems + tile, 1u);
-          s_last = (tk == (unsigned int)p.splits - 1) ? 1u : 0u;
-          if (s_last) { p.sems[tile] = 0u; __threadfence(); }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (s_last && valid) {
-          const float* base = p.partial + (long long)tile * p.splits * (128 * p.BN) + (long long)row * p.BN;
-          for (int ch = 0; ch < p.BN / 32; ++ch) {
-            float acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll 2
-            for (int s2 = 0; s2 < p.splits; ++s2) {
-              const float4* src = reinterpret_cast<const float4*>(base + (long long)s2 * (128 * p.BN) + ch * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 q = __ldcg(src + j);
-                acc[4 * j] += q.x; acc[4 * j + 1] += q.y; acc[4 * j + 2] += q.z; acc[4 * j + 3] += q.w;
-              }
-            }
-            int ci0 = cit * p.BN + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              int ci = ci0 + j;
-              if (ci < p.c_in) atomicAdd(wbase + (long long)ci * p.w_ci_stride, acc[j]);
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // s_last is rewritten by the next unit
+        mbar_arrive(bar_tempty + 8 * as);
       } else {
         // Ordered turns (common.cuh, scheme A): the few pixel splits of one filter tile add their partial tiles in split
         // order.  Unit (tile, sp) only waits on unit (tile, sp - 1), which has a lower unit index: it was taken earlier by
@@ -638,6 +604,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
+    }
+    if (p.det_mode == 2) {
+      // Grid-wide phase 2 (all CTAs are co-resident: the grid never exceeds the SM count and a CTA owns its SM): once every
+      // CTA has stored its partial tiles, the epilogue threads of the WHOLE grid add the splits of every filter-tile element
+      // in split order -- a fixed order of additions, shared by ~19 000 threads instead of one chain per tile.
+      unsigned int* gbar = p.sems + base_units;              // [0]: arrivals before phase 2, [1]: departures after it
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        __threadfence();
+        atomicAdd(gbar, 1u);
+        unsigned int v, spins = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar) : "memory");
+          if (v >= gridDim.x) break;
+          if (++spins > (1u << 28)) __trap();
+          __nanosleep(64);
+        } while (true);
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int q4 = p.BN / 4;                               // float4 groups per accumulator row
+      const long long items = (long long)base_units * 128 * q4;
+      const long long tile_fl = (long long)128 * p.BN;
+      for (long long it = (long long)blockIdx.x * 128 + (threadIdx.x - 64); it < items; it += (long long)gridDim.x * 128) {
+        const int jj = (int)(it % q4);
+        const long long rr = it / q4;
+        const int r_ = (int)(rr % 128), tile = (int)(rr / 128);
+        int q = tile;
+        const int cit = q % p.ci_tiles; q /= p.ci_tiles;
+        const int cot = q % p.co_tiles;
+        const int t = q / p.co_tiles;
+        const int co = cot * 128 + r_, ci = cit * p.BN + 4 * jj;
+        if (co >= p.c_out || ci >= p.c_in) continue;
+        const float* src = p.partial + (long long)tile * p.splits * tile_fl + (long long)r_ * p.BN + 4 * jj;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+          float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)s2 * tile_fl));
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        float* wp = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride + (long long)ci * p.w_ci_stride;
+        wp[0] += a.x;                                        // exclusive owner of these four elements: plain read-modify-write
+        if (ci + 1 < p.c_in) wp[p.w_ci_stride] += a.y;
+        if (ci + 2 < p.c_in) wp[2 * p.w_ci_stride] += a.z;
+        if (ci + 3 < p.c_in) wp[3 * p.w_ci_stride] += a.w;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {                               // the last CTA to leave clears the barrier words for the next launch
+        unsigned int left = atomicAdd(gbar + 1, 1u);
+        if (left == gridDim.x - 1) { gbar[0] = 0u; gbar[1] = 0u; }
+      }
     }
   }
 
@@ -1099,7 +1116,7 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   // count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43 waves)
   int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
   if (max_splits > 32) max_splits = 32;
-  if (base_units > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
+  if (base_units + 2 > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
   int splits = 1;
   double best_eff = -1.0;
   for (int sp = 1; sp <= max_splits; ++sp) {
@@ -1151,12 +1168,24 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   long long units = base_units * p.splits;
   int grid = (int)(units < ctx->num_sms ? units : ctx->num_sms);
   size_t smem = (size_t)stages * p.stage_stride + 1024;
+  // det_mode 2 ends in a grid-wide barrier: launched cooperatively, so the runtime guarantees (or refuses) co-residency
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.det_mode == 2 ? 1 : 0;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad_tc<float><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+    SG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_wgrad_tc<float>, p));
   } else {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad_tc<__nv_bfloat16><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+    SG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_wgrad_tc<__nv_bfloat16>, p));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import sgan_oracle as O
-from _parity import (assert_grads, assert_stats, build_models, du, make_inputs, make_params, rel_elementwise, rel_max, run_step)
+from _parity import (Soft, assert_grads, assert_stats, build_models, du, make_inputs, make_params, rel_elementwise, rel_max, run_step)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,22 @@ def _tf32_wgrad_on_tc(rt):
 # ----------------------------------------------------------------------------------------------------
 # the benchmarked path at a size the fp64 oracle finishes in seconds
 # ----------------------------------------------------------------------------------------------------
+_FUSED_ORACLE = {}
+
+
+def _fused_case(mode, tf32_wgrad):
+    """B = 16, L = 3 (fp64 oracle with operand rounding: ~20 s once per mode)."""
+    key = (mode, tf32_wgrad)
+    if key not in _FUSED_ORACLE:
+        dt = torch.float64
+        b, l = 16, 3
+        P = make_params(40, dt)
+        inputs = make_inputs(41, b, l, l, dt)
+        stats, newp, _, grads, extra = _oracle_step(P, *inputs, mode, tf32_wgrad)
+        _FUSED_ORACLE[key] = (P, inputs, stats, grads)
+    return _FUSED_ORACLE[key]
+
+
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph-replay"])
 @pytest.mark.parametrize("mode", ["bf16", "tf32"])
 def test_fused_path_matches_rounded_oracle(rt, mode, graph):
@@ -44,15 +60,12 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
     CUDA graph; gradients of all three networks against the fp64 oracle with operand rounding."""
     rt.set_mode(mode)
     old = (du.GRAPH_ENABLED, du.GRAPH_WARMUP)
+    soft = Soft()
     try:
         du._graph_cache.clear()
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = graph, 0
         assert rt.merge_r_backward
-        dt = torch.float64
-        b, l = 4, 3
-        P = make_params(40, dt)
-        images, labels, fake_labels, z = make_inputs(41, b, l, l, dt)
-        stats, newp, _, grads, extra = _oracle_step(P, images, labels, fake_labels, z, mode, _tf32_wgrad_on_tc(rt))
+        P, (images, labels, fake_labels, z), stats, grads = _fused_case(mode, _tf32_wgrad_on_tc(rt))
         if graph:
             # every kernel of the step is launched once eagerly first (on throw-away models): CUDA loads a kernel's module
             # at its first launch, which must not happen inside a stream capture
@@ -66,10 +79,11 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
             assert len(captured) == 1 and captured[0].calls == 1 and captured[0].launches > 100, "the step must have been captured and replayed"
         else:
             assert not captured
-        assert_stats(got, stats, TOL_OUT[mode], "{} fused step".format(mode))
+        assert_stats(got, stats, TOL_OUT[mode], "{} fused step".format(mode), soft=soft)
         tw, tt = TOL[mode]
         for n, m in (("D", D), ("R", R), ("G", G)):
-            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, "graph" if graph else "eager"))
+            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, "graph" if graph else "eager"), soft=soft)
+        soft.done()
     finally:
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = old
         du._graph_cache.clear()
@@ -104,10 +118,12 @@ def full_case():
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_train_step_at_baseline_size(rt, full_case, mode):
-    """One full step at B = 64, L = 5 (BASELINE configs[0] / configs[3]) against the fp32 oracle: forward images, D logits,
-    R losses (elementwise relative), the 16 statistics and the whole gradient of every network."""
+    """One full step at B = 64, L = 5 (BASELINE configs[0] / configs[3]) against the fp32 oracle (operand rounding in the
+    reduced-precision modes): forward images and D logits (relative to the tensor's scale: logits are sums with heavy
+    cancellation), R's CTC losses (elementwise relative), the 16 statistics and the whole gradient of every network."""
     rt.set_mode(mode)
     old = du.GRAPH_ENABLED
+    soft = Soft()
     try:
         du._graph_cache.clear()
         du.GRAPH_ENABLED = False
@@ -122,21 +138,26 @@ def test_train_step_at_baseline_size(rt, full_case, mode):
         zd, yf = z.to(rt.device), fake_labels.to(rt.device, torch.int32)
         img, _ = G.forward(rt, zd, yf, training=True)
         G.store.s.copy_(s_saved)
-        assert rel_max(img, extra["gen_images"]) <= tol, "generated images: {:.3e}".format(rel_max(img, extra["gen_images"]))
+        e = rel_max(img, extra["gen_images"])
+        soft.check(e <= tol, "generated images: rel max err {:.3e} (bound {:.0e})".format(e, tol))
         xr = images.to(rt.device)
         d_real, _ = D.forward(rt, xr)
-        assert rel_elementwise(d_real, extra["d_real"]) <= 5 * tol, "D(real) logits: {:.3e}".format(rel_elementwise(d_real, extra["d_real"]))
+        e = rel_max(d_real, extra["d_real"])
+        soft.check(e <= tol, "D(real) logits: rel max err {:.3e} (bound {:.0e})".format(e, tol))
         d_fake, _ = D.forward(rt, extra["gen_images"].to(rt.device))
-        assert rel_elementwise(d_fake, extra["d_fake"]) <= 5 * tol, "D(fake) logits: {:.3e}".format(rel_elementwise(d_fake, extra["d_fake"]))
+        e = rel_max(d_fake, extra["d_fake"])
+        soft.check(e <= tol, "D(fake) logits: rel max err {:.3e} (bound {:.0e})".format(e, tol))
         r_real, _ = R.forward(rt, xr, labels.to(rt.device, torch.int32), want_grad=False)
         ctc_tol = 1e-4 if mode == "fp32" else tol
-        assert rel_elementwise(r_real, extra["r_real"], 1.0) <= ctc_tol, "R(real) CTC losses: {:.3e}".format(rel_elementwise(r_real, extra["r_real"], 1.0))
+        e = rel_elementwise(r_real, extra["r_real"], 1.0)
+        soft.check(e <= ctc_tol, "R(real) CTC losses: elementwise rel err {:.3e} (bound {:.0e})".format(e, ctc_tol))
 
         got, _ = run_step(rt, G, D, R, None, images, labels, fake_labels, z)
-        assert_stats(got, stats, tol, "{} B=64 L=5 step".format(mode))
+        assert_stats(got, stats, tol, "{} B=64 L=5 step".format(mode), soft=soft)
         tw, tt = TOL[mode]
         for n, m in (("D", D), ("R", R), ("G", G)):
-            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients at B=64, L=5".format(mode, n))
+            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients at B=64, L=5".format(mode, n), soft=soft)
+        soft.done()
     finally:
         du.GRAPH_ENABLED = old
         du._graph_cache.clear()
