@@ -247,6 +247,15 @@ int sg_loss_terms(sg_ctx* ctx, int kind, const float* d_real, const float* d_fak
 int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b, float alpha,
                     float* g_balanced, float* r_balanced, float* stds);
 
+/* Paper-faithful gradient balancing (arXiv 2003.10557 section 3.4; BASELINE north_star "std(grad_D)/std(grad_R)"): both
+ * gradients are w.r.t. the generated image; out = grad_d + alpha * (std(grad_d) / std(grad_r)) * grad_r with population
+ * std over all n elements.  sums is double[8] ({sum d, sum d^2, sum r, sum r^2, n, 0, 0, 0}): all-reduce it across
+ * replicas between the two calls.  `stats` (may be NULL) is the step's 16-tuple, patched with the balanced losses, alpha and
+ * the two stds.  The reference fork balances LOSS values instead (data_utils.py:476-490): that is sg_loss_finish. */
+int sg_image_grad_balance_sums(sg_ctx* ctx, const float* grad_d, const float* grad_r, long long n, double* sums);
+int sg_image_grad_balance_apply(sg_ctx* ctx, const float* grad_d, const float* grad_r, long long n, float alpha,
+                                const double* sums, float* out, float* stats);
+
 /* ---- optimizers (K19) -- main.py:25-35: Keras Adam / RMSprop --------------------------------------- */
 int sg_adam(sg_ctx* ctx, float* w, const float* g, float* m, float* v, long long n, float lr_t,
             float beta1, float beta2, float eps);
@@ -263,6 +272,13 @@ int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, fl
 /* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */
 int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
                      float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
+
+/* backward of the weight re-parameterisation W_sn = W / sigma (u, v constants), in place on g = dL/dW_sn:
+ * g <- (g - <g, W_sn> v u^T) / sigma.  fwd_scratch is the scratch sg_spectral_norm filled for this weight (it holds the
+ * un-normalised v and its inverse norm), u_hat its u_out, dot_scratch one float.  Paper-faithful option `apply_sn`:
+ * in the reference spectral_norm is a kernel_regularizer nobody reads (arch_ops.py:99-126). */
+int sg_spectral_norm_bwd(sg_ctx* ctx, float* g, const float* w_sn, int rows, int cols, const float* u_hat,
+                         const float* sigma, const float* fwd_scratch, float* dot_scratch);
 
 #ifdef __cplusplus
 }

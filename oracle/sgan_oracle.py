@@ -726,6 +726,13 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
     if return_grads:
         extra = dict(gen_images=gen_images.detach(), d_fake=d_fake.detach(), d_real=d_real.detach(),
                      r_fake=r_fake.detach(), r_real=r_real.detach())
+        # per-sample upstream weights of the G-loss pass, d(sum g_final)/d(d_fake_i) and /d(r_fake_i), and the image
+        # gradient: with gradient balancing these weights contain (R / sd_r)(g_i - mean g)/(N sd_g) -- O(1e3) at random
+        # init, where all logits are nearly equal -- so G's gradient is an ill-conditioned function of the logits; tests
+        # that want to check the backward OPERATOR feed these weights to the CUDA path (tests/test_parity_benchpath_gpu.py)
+        ups = torch.autograd.grad(g_final.sum(), [d_fake, r_fake], retain_graph=True)
+        extra["up_d_fake_g"], extra["up_r_fake_g"] = ups[0].detach().reshape(-1), ups[1].detach().reshape(-1)
+        extra["dimg"] = torch.autograd.grad(g_final.sum(), gen_images, retain_graph=True)[0].detach()
         out = out + (grads, extra)
     return out
 

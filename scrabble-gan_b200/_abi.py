@@ -110,6 +110,9 @@ _PROTOS = {
     "sg_loss_finish": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sg_loss_terms": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "sg_grad_balance": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
+    "sg_image_grad_balance_sums": (_I, [_P, _P, _P, _L, _P]),
+    "sg_image_grad_balance_apply": (_I, [_P, _P, _P, _L, _F, _P, _P, _P]),
+    "sg_spectral_norm_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "sg_adam": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_adam_mirror": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_adam_prepare": (_I, [_P, _P, _P, _I, _F, _F, _F]),

@@ -21,6 +21,7 @@
 // Filter-gradient kernel: D[128 c_out, BN c_in] += dy_tile^T[128, P] * in_tile[P, BN] with BOTH operands
 // MN-major (pixels are the reduction dim and the slow smem dim), split over pixel ranges with fp32 red.add.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
         // Ordered turns (common.cuh, scheme A): the few pixel splits of one filter tile add their partial tiles in split
         // order.  Unit (tile, sp) only waits on unit (tile, sp - 1), which has a lower unit index: it was taken earlier by
         // its CTA (static round-robin, every CTA walks its units in increasing order), so the wait always ends.
-        if (p.det_mode == 1) {
+        if (p.det_mode == 1) {              // (det_mode 3, diagnostics only: unordered atomics as in round 1)
           if (threadIdx.x == 64) sg_turn_wait(p.sems + tile, (unsigned int)sp);
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -645,10 +646,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
           a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         float* wp = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride + (long long)ci * p.w_ci_stride;
-        wp[0] += a.x;                                        // exclusive owner of these four elements: plain read-modify-write
-        if (ci + 1 < p.c_in) wp[p.w_ci_stride] += a.y;
-        if (ci + 2 < p.c_in) wp[2 * p.w_ci_stride] += a.z;
-        if (ci + 3 < p.c_in) wp[3 * p.w_ci_stride] += a.w;
+        atomicAdd(wp, a.x);                                  // exclusive owner of these four elements: RED = fire and forget
+        if (ci + 1 < p.c_in) atomicAdd(wp + p.w_ci_stride, a.y);
+        if (ci + 2 < p.c_in) atomicAdd(wp + 2 * p.w_ci_stride, a.z);
+        if (ci + 3 < p.c_in) atomicAdd(wp + 3 * p.w_ci_stride, a.w);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {                               // the last CTA to leave clears the barrier words for the next launch
@@ -1134,6 +1135,14 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   p.splits = sg_div_up(ptiles, p.ptiles_per_split);
   p.partial = ctx->det_scratch;
   p.det_mode = p.splits == 1 ? 0 : (p.splits <= 4 ? 1 : 2);
+  {
+    const char* ov = getenv("SGAN_WGRAD_DET");          // A/B diagnostics: "legacy" = unordered atomics, "turns" = ordered turns only
+    if (ov && p.splits > 1) {
+      if (!strcmp(ov, "legacy")) p.det_mode = 3;
+      else if (!strcmp(ov, "turns")) p.det_mode = 1;
+      else if (!strcmp(ov, "scratch")) p.det_mode = 2;
+    }
+  }
   if (p.det_mode == 2 && (long long)base_units * p.splits * 128 * p.BN * (long long)sizeof(float) > (long long)SG_DET_SCRATCH_BYTES) {
     // the partial tiles would not fit the context's scratch: fall back to 4 ordered splits
     p.ptiles_per_split = sg_div_up(ptiles, 4);

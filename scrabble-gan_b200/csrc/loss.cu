@@ -235,3 +235,80 @@ int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Paper-faithful gradient balancing (ScrabbleGAN, arXiv 2003.10557, section 3.4; north_star "std(grad_D)/std(grad_R)"):
+//     grad_R <- alpha * (std(grad_D) / std(grad_R)) * grad_R,   both gradients taken w.r.t. the generated IMAGE,
+//     std = population std over every element of the (global) batch of image gradients.
+// The reference fork balances LOSS values instead (data_utils.py:476-490); this is the opt-in alternative.
+// sums[0..4] = {sum gd, sum gd^2, sum gr, sum gr^2, n} in double: all-reduce them across replicas between the two calls.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_imgbal_sums(const float* __restrict__ gd, const float* __restrict__ gr, long long n,
+                                                      double* __restrict__ sums, double* __restrict__ scratch, unsigned int* ticket) {
+  __shared__ double sm[32];
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double d = gd[i], r = gr[i];
+    a[0] += d; a[1] += d * d; a[2] += r; a[3] += r * r;
+  }
+  for (int j = 0; j < 4; ++j) {
+    double t = block_sum_d(a[j], sm);
+    if (threadIdx.x == 0) scratch[(long long)blockIdx.x * 4 + j] = t;
+  }
+  if (!sg_det_arrive_last(ticket, gridDim.x)) return;        // per-block partials, added in block order by the last block
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(scratch + (long long)b * 4 + threadIdx.x);
+    sums[threadIdx.x] = t;
+  }
+  if (threadIdx.x == 0) {
+    sums[4] = (double)n;
+    for (int j = 5; j < 8; ++j) sums[j] = 0.0;
+  }
+}
+
+// out = gd + alpha (sd_d / sd_r) gr;  stats (the step's 16-tuple) is patched: r_loss_balanced = ratio * r_loss_fake,
+// g_loss_balanced = g_loss_final = g_loss + r_loss_balanced, alpha, r_loss_fake_std := sd_r, g_loss_std := sd_d
+__global__ void k_imgbal_apply(const float* __restrict__ gd, const float* __restrict__ gr, long long n, float alpha,
+                               const double* __restrict__ sums, float* __restrict__ out, float* __restrict__ stats) {
+  const double N = sums[4];
+  const double md = sums[0] / N, mr = sums[2] / N;
+  double vd = sums[1] / N - md * md, vr = sums[3] / N - mr * mr;
+  const double sd_d = sqrt(vd > 0 ? vd : 0), sd_r = sqrt(vr > 0 ? vr : 0);
+  const float ratio = (float)((double)alpha * sd_d / sd_r);          // no zero guard, as in the loss-level original
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = gd[i] + ratio * gr[i];
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
+    float r_bal = ratio * stats[0];
+    stats[2] = r_bal;
+    stats[5] = stats[3] + r_bal;
+    stats[9] = stats[3] + r_bal;
+    stats[10] = alpha;
+    stats[11] = (float)sd_r;
+    stats[12] = (float)sd_d;
+  }
+}
+
+extern "C" {
+
+int sg_image_grad_balance_sums(sg_ctx* ctx, const float* grad_d, const float* grad_r, long long n, double* sums) {
+  SG_REQUIRE(ctx && grad_d && grad_r && sums && n > 0, "sg_image_grad_balance_sums: bad args");
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8), cap = (long long)ctx->num_sms * 2;
+  if (blocks > cap) blocks = cap;
+  k_imgbal_sums<<<(int)blocks, 256, 0, ctx->stream>>>(grad_d, grad_r, n, sums, reinterpret_cast<double*>(ctx->det_scratch), ctx->det_tickets);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_image_grad_balance_apply(sg_ctx* ctx, const float* grad_d, const float* grad_r, long long n, float alpha, const double* sums,
+                                float* out, float* stats) {
+  SG_REQUIRE(ctx && grad_d && grad_r && sums && out && n > 0, "sg_image_grad_balance_apply: bad args");
+  long long blocks = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  k_imgbal_apply<<<(int)blocks, 256, 0, ctx->stream>>>(grad_d, grad_r, n, alpha, sums, out, stats);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -213,3 +213,35 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Spectral-norm weight re-parameterisation, backward (paper-faithful option `apply_sn`):
+//     W_sn = W / sigma,  sigma = v^T W u  with the power-iteration vectors u, v treated as constants
+//     dL/dW = ( G - <G, W_sn> v u^T ) / sigma,   G = dL/dW_sn   (in place on g)
+// v_raw / inv_v are what sg_spectral_norm leaves in its scratch (v_hat = v_raw * inv_v), u_hat its u_out.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_sn_bwd(float* __restrict__ g, const float* __restrict__ dot, const float* __restrict__ v_raw,
+                         const float* __restrict__ inv_v, const float* __restrict__ u_hat, const float* __restrict__ sigma, int rows,
+                         int cols) {
+  const float d = *dot, iv = *inv_v, is = 1.f / *sigma;
+  const long long n = (long long)rows * cols, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int r = (int)(i / cols), c = (int)(i % cols);
+    g[i] = (g[i] - d * (v_raw[r] * iv) * u_hat[c]) * is;
+  }
+}
+
+extern "C" int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out, int accumulate);
+
+extern "C" int sg_spectral_norm_bwd(sg_ctx* ctx, float* g, const float* w_sn, int rows, int cols, const float* u_hat,
+                                    const float* sigma, const float* fwd_scratch, float* dot_scratch) {
+  SG_REQUIRE(ctx && g && w_sn && u_hat && sigma && fwd_scratch && dot_scratch && rows > 0 && cols > 0, "sg_spectral_norm_bwd: bad args");
+  int rc = sg_dot(ctx, g, w_sn, (long long)rows * cols, dot_scratch, 0);
+  if (rc != SG_OK) return rc;
+  long long n = (long long)rows * cols;
+  long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  k_sn_bwd<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(g, dot_scratch, fwd_scratch, fwd_scratch + rows + cols, u_hat, sigma, rows,
+                                                                      cols);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}

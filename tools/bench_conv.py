@@ -34,6 +34,9 @@ LAYERS = [
     ("R.conv6", 4, 20, 512, 512, 3),
     ("G.B1.conv", 8, 40, 256, 256, 3),
     ("G.B3.conv", 32, 80, 64, 64, 3),
+    ("R.conv3", 8, 40, 128, 256, 3),
+    ("R.conv5", 4, 40, 256, 512, 3),
+    ("G.B2.conv", 16, 80, 128, 128, 3),
 ]
 
 
