@@ -482,6 +482,25 @@ def spectral_norm(w: Tensor, u: Tensor, power_iteration: int = 1) -> Tensor:
     return (w2 / sigma).reshape(shape)
 
 
+def spectral_norm_reparam(w: Tensor, u: Tensor, power_iteration: int = 1):
+    """Spectral-norm weight re-parameterisation as a training-time op (SN-GAN / compare_gan semantics, which is what the
+    reference's `kernel_reg` was meant to be): W / sigma with sigma = v^T W u from `power_iteration` steps started at the
+    given u; u and v are CONSTANTS in the backward pass.  (arch_ops.py:99-126 computes the same W / sigma but is installed
+    as a kernel_regularizer whose value is never read: SURVEY Q2.)"""
+    shape = w.shape
+    w2 = w.reshape(-1, shape[-1])
+
+    def l2n(v):
+        return v * torch.rsqrt(torch.clamp((v * v).sum(), min=1e-12))
+    with torch.no_grad():
+        u_hat, v_hat = u.reshape(1, -1), None
+        for _ in range(power_iteration):
+            v_hat = l2n(u_hat @ w2.t())
+            u_hat = l2n(v_hat @ w2)
+    sigma = (v_hat @ w2) @ u_hat.t()
+    return (w2 / sigma).reshape(shape)
+
+
 # ----------------------------------------------------------------------------------------------------
 # optimizers (Keras semantics)                                                       main.py:25-35
 # ----------------------------------------------------------------------------------------------------
@@ -627,12 +646,19 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
                fake_labels: Tensor, z_or_style: Tensor, *, loss_fn: str = "hinge", apply_gradient_balance: bool = True,
                use_style_encoder: bool = False, use_style_promoter: bool = False, update_g: bool = True,
                lr: float = 2e-4, beta1: float = 0.0, beta2: float = 0.999, g_attn="B3", d_attn="B1",
-               return_grads: bool = False, style_images: Optional[Tensor] = None):
+               return_grads: bool = False, style_images: Optional[Tensor] = None, balance_mode: str = "reference",
+               sn_u: Optional[Dict[str, Dict[str, Tensor]]] = None):
     """One G + D + R (+ W) step following data_utils.py:385-473.
 
     params = {"G": {...}, "D": {...}, "R": {...}, ["W": {...}]}; tensors are updated functionally (new dicts
     are returned).  `z_or_style` is z (B,128) in G+D+R mode (Mode A) or the style-image batch (B,32,160,1)
     in fork mode (Mode B, use_style_encoder=True).  Returns (stats dict, new params, new opt_state[, grads]).
+
+    Paper-faithful options (NOT what the reference executes):
+      balance_mode="paper": gradient-level balancing of arXiv 2003.10557 section 3.4 -- the image gradient of the R term is
+          rescaled by alpha * std(grad_I L_D) / std(grad_I L_R) (population std over all elements) before it enters G;
+      sn_u={"G": {name: u}, "D": {...}}: spectral-norm weight re-parameterisation W / sigma(W) with the given
+          power-iteration vectors u (one step, u and v held constant in the backward pass) for the listed kernels.
     """
     leaf = {}
     for net, d in params.items():
@@ -642,6 +668,12 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
             if not k.endswith(NON_TRAINABLE_SUFFIXES):
                 t.requires_grad_(True)
             leaf[net][k] = t
+    raw_leaf = leaf
+    if sn_u:
+        leaf = {net: dict(d) for net, d in leaf.items()}
+        for net, us in sn_u.items():
+            for k, u in us.items():
+                leaf[net][k] = spectral_norm_reparam(raw_leaf[net][k], u)
     G, D, R = leaf["G"], leaf["D"], leaf["R"]
     Wn = leaf.get("W") if use_style_promoter else None
     b = images.shape[0]
@@ -682,6 +714,18 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
     g_bal, r_bal, alpha, r_std, g_std = apply_gradient_balancing(r_fake, g_loss, 1.0)     # :421
     g_added = g_loss + r_fake
     g_final = g_bal if apply_gradient_balance else g_added
+    paper = apply_gradient_balance and balance_mode == "paper"
+    if paper:
+        # the image gradients of the two terms, balanced at gradient level; G then receives gd + ratio * gr
+        gd = torch.autograd.grad(g_loss.sum(), gen_images, retain_graph=True)[0]
+        gr = torch.autograd.grad(r_fake.sum(), gen_images, retain_graph=True)[0]
+        sd_d, sd_r = gd.std(unbiased=False), gr.std(unbiased=False)
+        ratio = float(alpha) * sd_d / sd_r
+        paper_dimg = (gd + ratio * gr).detach()
+        r_bal = ratio.detach() * r_fake
+        g_bal = g_loss + r_bal
+        g_final = g_bal
+        r_std, g_std = sd_r.detach(), sd_d.detach()
 
     stats = dict(r_loss_fake=r_fake.mean(), r_loss_real=r_real.mean(), r_loss_balanced=r_bal.mean(),
                  g_loss=g_loss.mean(), g_loss_added=g_added.mean(), g_loss_balanced=g_bal.mean(),
@@ -692,17 +736,20 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
 
     grads: Dict[str, Dict[str, Tensor]] = {}
 
-    def grad_of(target, net):
-        names = [k for k in trainable_names(leaf[net])]
-        gs = torch.autograd.grad(target.sum(), [leaf[net][k] for k in names], retain_graph=True, allow_unused=True)
-        return {k: (g if g is not None else torch.zeros_like(leaf[net][k])) for k, g in zip(names, gs)}
+    def grad_of(target, net, grad_outputs=None):
+        names = [k for k in trainable_names(raw_leaf[net])]
+        if grad_outputs is None:
+            gs = torch.autograd.grad(target.sum(), [raw_leaf[net][k] for k in names], retain_graph=True, allow_unused=True)
+        else:
+            gs = torch.autograd.grad(target, [raw_leaf[net][k] for k in names], grad_outputs, retain_graph=True, allow_unused=True)
+        return {k: (g if g is not None else torch.zeros_like(raw_leaf[net][k])) for k, g in zip(names, gs)}
 
     grads["D"] = grad_of(d_loss, "D")                                          # :449-451  (Q7: sum)
     grads["R"] = grad_of(r_real, "R")                                          # :453-455
     if Wn is not None:
         grads["W"] = grad_of(s_loss, "W")                                      # :457-459
     if update_g:
-        grads["G"] = grad_of(g_final, "G")                                     # :462-468
+        grads["G"] = grad_of(gen_images, "G", paper_dimg) if paper else grad_of(g_final, "G")      # :462-468
 
     new_params = {net: {k: v.detach().clone() for k, v in d.items()} for net, d in params.items()}
     new_opt = {}
@@ -730,9 +777,12 @@ def train_step(params: Dict[str, Dict[str, Tensor]], opt_state: Dict[str, Dict],
         # gradient: with gradient balancing these weights contain (R / sd_r)(g_i - mean g)/(N sd_g) -- O(1e3) at random
         # init, where all logits are nearly equal -- so G's gradient is an ill-conditioned function of the logits; tests
         # that want to check the backward OPERATOR feed these weights to the CUDA path (tests/test_parity_benchpath_gpu.py)
-        ups = torch.autograd.grad(g_final.sum(), [d_fake, r_fake], retain_graph=True)
-        extra["up_d_fake_g"], extra["up_r_fake_g"] = ups[0].detach().reshape(-1), ups[1].detach().reshape(-1)
-        extra["dimg"] = torch.autograd.grad(g_final.sum(), gen_images, retain_graph=True)[0].detach()
+        if paper:
+            extra["dimg"] = paper_dimg
+        else:
+            ups = torch.autograd.grad(g_final.sum(), [d_fake, r_fake], retain_graph=True)
+            extra["up_d_fake_g"], extra["up_r_fake_g"] = ups[0].detach().reshape(-1), ups[1].detach().reshape(-1)
+            extra["dimg"] = torch.autograd.grad(g_final.sum(), gen_images, retain_graph=True)[0].detach()
         out = out + (grads, extra)
     return out
 

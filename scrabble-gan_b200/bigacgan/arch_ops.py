@@ -29,13 +29,13 @@ class NonLocalBlock:
 
     def forward(self, rt: Runtime, x):
         n, h, w, c = x.shape
-        theta, phi_f, g_f = ops.nonlocal_proj_fwd(rt, x, self.theta.data, self.phi.data, self.g.data)
+        theta, phi_f, g_f = ops.nonlocal_proj_fwd(rt, x, self.theta.eff, self.phi.eff, self.g.eff)
         phi_f, g_f = phi_f.view(n, h, w, self.dk), g_f.view(n, h, w, self.dv)
         phi = ops.maxpool_fwd(rt, phi_f, 2, 2)
         g = ops.maxpool_fwd(rt, g_f, 2, 2)
         q, kv = h * w, (h // 2) * (w // 2)
         o, lse = ops.attn_fwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv))
-        og, out = ops.nonlocal_out_fwd(rt, o, self.o.data, self.sigma.data, x)
+        og, out = ops.nonlocal_out_fwd(rt, o, self.o.eff, self.sigma.data, x)
         # every cached tensor keeps the image index as its first dimension so that sub-batches can be sliced
         return out.view(n, h, w, c), (x, theta.view(n, q, self.dk), phi_f, phi, g_f, g, o, lse, og.view(n, h, w, c))
 
@@ -50,13 +50,13 @@ class NonLocalBlock:
         q, kv = h * w, (h // 2) * (w // 2)
         if wgrad:
             ops.dot_into(rt, dout, og, self.sigma.grad, accumulate=1)
-        d_o = ops.nonlocal_out_bwd(rt, dout, o, self.o.data, self.sigma.data, self.o.grad if wgrad else None)
+        d_o = ops.nonlocal_out_bwd(rt, dout, o, self.o.eff, self.sigma.data, self.o.grad if wgrad else None)
         dtheta, dphi, dg = ops.attn_bwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv),
                                         o.view(n, q, self.dv), lse, d_o.view(n, q, self.dv))
         dphi_f = ops.maxpool_bwd(rt, dphi.view(n, h // 2, w // 2, self.dk), phi_f, 2, 2, False, SG_F32)
         dg_f = ops.maxpool_bwd(rt, dg.view(n, h // 2, w // 2, self.dv), g_f, 2, 2, False, SG_F32)
         gr = (self.theta.grad, self.phi.grad, self.g.grad) if wgrad else (None, None, None)
-        return ops.nonlocal_proj_bwd(rt, x, dtheta, dphi_f, dg_f, self.theta.data, self.phi.data, self.g.data, dout, *gr)
+        return ops.nonlocal_proj_bwd(rt, x, dtheta, dphi_f, dg_f, self.theta.eff, self.phi.eff, self.g.eff, dout, *gr)
 
 
 class SpatialEmbedding:

@@ -63,6 +63,9 @@ def _loss_kind(loss_fn) -> int:
 # captured ONCE into a CUDA graph -- torch is used only as the capture / allocator plumbing -- and later calls replay it:
 # inputs are copied into static device buffers, the Adam step sizes travel through pinned host scalars that captured
 # memcpy nodes re-read on every replay, and the result is the same `stats` tensor.  Set SGAN_CUDA_GRAPH=0 to disable.
+# "reference" = this fork's loss-level balancing (data_utils.py:476-490, the default and the parity target); "paper" = the
+# gradient-level balancing of the ScrabbleGAN paper / BASELINE north_star, std(grad_D)/std(grad_R) on the image gradients
+BALANCE_MODE = os.environ.get("SGAN_BALANCE_MODE", "reference")
 GRAPH_ENABLED = os.environ.get("SGAN_CUDA_GRAPH", "1") != "0"
 GRAPH_DP = os.environ.get("SGAN_CUDA_GRAPH_DP", "1") != "0"      # capture the data-parallel step too (NCCL + peer exchanges)
 GRAPH_WARMUP = int(os.environ.get("SGAN_CUDA_GRAPH_WARMUP", "2"))   # eager calls of a signature before it is captured
@@ -87,22 +90,28 @@ class _GraphedStep:
                                     # only be recycled after the object dies, and the graph's kernels point at its buffers
 
 
-def _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, balance, update_g):
+def _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, balance, update_g, balance_mode="reference"):
     return (id(generator), id(discriminator), id(recognizer), tuple(id(o) for o in opts), b, l_r, l_f, rt.mode, kind, bool(balance),
-            bool(update_g), bool(recognizer.trainable), os.environ.get("SGAN_NO_FUSED_BATCH", "0"))
+            bool(update_g), bool(recognizer.trainable), os.environ.get("SGAN_NO_FUSED_BATCH", "0"), balance_mode,
+            tuple(bool(getattr(m, "apply_sn", False)) for m in (generator, discriminator)))
 
 
 def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discriminator, recognizer, style_promoter, composite_gan,
                generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer, my_imgs, batch_size,
                latent_dim, loss_fn, disc_iters, apply_gradient_balance, random_words, bucket_size, gen_path, *,
-               fake_labels=None, noise=None, verbose: bool = False, return_device_stats: bool = False):
+               fake_labels=None, noise=None, verbose: bool = False, return_device_stats: bool = False, balance_mode: str = None):
     """One G + D + R (+ W) training step.  Positional signature = the reference's (data_utils.py:358-360); returns the
     same 16-tuple of Python floats in the same order (:470-473).
 
     images (B,32,16*L_r[,1]) and labels (B,L_r) may be host numpy arrays (copied H2D here), torch tensors or DLPack
     producers.  `style_promoter` may be None (G+D+R mode).  Keyword extensions: `fake_labels` (B,L_f) int and `noise`
-    (B,latent_dim) make the step deterministic (the reference samples both internally)."""
+    (B,latent_dim) make the step deterministic (the reference samples both internally); `balance_mode`
+    "reference" (default: loss-level balancing, data_utils.py:476-490) or "paper" (gradient-level balancing on the image
+    gradients, std(grad_D)/std(grad_R): arXiv 2003.10557 section 3.4)."""
     generator = composite_gan.generator
+    balance_mode = balance_mode or BALANCE_MODE
+    if balance_mode not in ("reference", "paper"):
+        raise ValueError("balance_mode must be 'reference' or 'paper'")
     rt: Runtime = generator.rt
     use_w = style_promoter is not None
     kind = _loss_kind(loss_fn)
@@ -115,13 +124,13 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     l_f = int(np.shape(fake_labels)[1])
     update_g = (batch_idx + 1) % disc_iters == 0
     opts = (generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer)
-    args = (discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g)
+    args = (discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g, balance_mode)
 
     # ---- CUDA-graph path (G+D+R mode on one replica) ---------------------------------------------------------------
     graphable = (GRAPH_ENABLED and not use_w and generator.style is None and (rt.world_size == 1 or GRAPH_DP) and
                  all(type(o).__name__ == "Adam" for o in opts[:3]))
     if graphable:
-        key = _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, apply_gradient_balance, update_g)
+        key = _graph_key(rt, generator, discriminator, recognizer, opts, b, l_r, l_f, kind, apply_gradient_balance, update_g, balance_mode)
         gs = _graph_cache.get(key)
         if gs is None:
             gs = _graph_cache[key] = _GraphedStep()
@@ -160,7 +169,7 @@ def _finish(stats, return_device_stats, verbose, epoch_idx, batch_idx, batch_per
 def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
     """Capture the device part of the step for this signature.  Kernels do not run during capture; Python-side state the
     body advances (optimizer iteration counters, store versions) is rolled back afterwards and advanced by _replay."""
-    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g = args
+    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g, balance_mode = args
     stores = [discriminator.store, recognizer.store, generator.store]
     saved = [(o.iterations if o is not None else 0) for o in opts]
     versions = None
@@ -214,7 +223,7 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
 
 
 def _replay(rt, gs, args, images, labels, fake_labels, noise):
-    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g = args
+    discriminator, recognizer, style_promoter, generator, opts, kind, balance, update_g, balance_mode = args
     stores = [discriminator.store, recognizer.store, generator.store]
     for i, st in enumerate(stores):
         if st.version != gs.versions[i]:                        # weights changed outside the graph (load / assign)
@@ -251,8 +260,9 @@ def _replay(rt, gs, args, images, labels, fake_labels, noise):
 
 def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     """The device part of the step: every argument is a device tensor; returns the 16 statistics as a device tensor."""
-    discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g = args
+    discriminator, recognizer, style_promoter, generator, opts, kind, apply_gradient_balance, update_g, balance_mode = args
     generator_optimizer, discriminator_optimizer, recognizer_optimizer, stylepromoter_optimizer = opts
+    paper = bool(apply_gradient_balance) and balance_mode == "paper"
     use_w = style_promoter is not None
     b = y_real.shape[0]
     l_r, l_f = y_real.shape[1], y_fake.shape[1]
@@ -275,6 +285,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     nets = [discriminator, recognizer, generator] + ([style_promoter] if use_w else [])
     for m in nets:
         m.store.zero_grad()
+        m.sn_forward(rt, update_u=True)             # apply_sn: refresh W / sigma(W) (one power-iteration step, persistent u)
 
     # ---- forward passes (data_utils.py:398-415) -------------------------------------------------------------------
     if fused:
@@ -305,7 +316,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     stats = rt.empty((16,))
     # rows 0,1 = (up_d_fake_d, up_d_real): adjacent and in [fake ; real] order for the fused D backward
     up_d_fake_d, up_d_real, up_s_real, up_s_fake_w, _up_s5, up_d_fake_g, up_s_fake_g, up_r_fake_g = ups
-    call.sg_loss_finish(rt.ctx, kind, int(use_w), int(bool(apply_gradient_balance)), 1.0, _p(d_real), _p(d_fake), _p(s_real),
+    call.sg_loss_finish(rt.ctx, kind, int(use_w), int(bool(apply_gradient_balance) and not paper), 1.0, _p(d_real), _p(d_fake), _p(s_real),
                         _p(s_fake), _p(s_slot5), _p(r_fake), b, _p(sums), _p(up_d_real), _p(up_d_fake_d), _p(up_s_real),
                         _p(up_s_fake_w), _p(_up_s5), _p(up_d_fake_g), _p(up_s_fake_g), _p(up_r_fake_g), _p(stats))
 
@@ -318,6 +329,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     recognizer.trainable = True
     if fused:
         discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
+        discriminator.sn_backward(rt)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         dfc = discriminator.slice_cache(dcc, 0, b)
         if update_g and rt.merge_r_backward:
@@ -333,6 +345,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     else:
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
+        discriminator.sn_backward(rt)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
         pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
@@ -340,6 +353,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         style_promoter.trainable = True
         style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
         style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
+        style_promoter.sn_backward(rt)
         pending.append((id(style_promoter), rt.allreduce_async_(style_promoter.store.g)))
 
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
@@ -351,13 +365,23 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             dimg_r = dimg_r_merged
         else:
             dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
-        ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
         if use_w:
             style_promoter.trainable = False
             if kind == net_loss.hinge.sg_kind:
                 dimg_w = style_promoter.backward(rt, sfc, up_s_fake_g, wgrad=False, want_dx=True)
                 ops.axpby(rt, 1.0, dimg, 1.0, dimg_w, out=dimg)
+        if paper:
+            # gradient-level balancing (paper): grad_R <- alpha * std(grad_D) / std(grad_R) * grad_R on the image gradients,
+            # population std over the GLOBAL batch (the five sums are all-reduced across replicas); the step's statistics
+            # are patched with the balanced losses, alpha and the two stds
+            bal = torch.empty(8, device=rt.device, dtype=torch.float64)
+            call.sg_image_grad_balance_sums(rt.ctx, _p(dimg), _p(dimg_r), dimg.numel(), _p(bal))
+            rt.allreduce_small_(bal)
+            call.sg_image_grad_balance_apply(rt.ctx, _p(dimg), _p(dimg_r), dimg.numel(), 1.0, _p(bal), _p(dimg), _p(stats))
+        else:
+            ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
         generator.backward(rt, g_cache, dimg)
+        generator.sn_backward(rt)
         pending.append((id(generator), rt.allreduce_async_(generator.store.g)))
     # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced: the Adam
     # launches of D and R overlap with the all-reduce of G's bucket, which is the last one to start

@@ -89,6 +89,25 @@ class _Model:
         self.name = name
         self.store = ParamStore(rt, name, seed)
         self.trainable = True
+        self.apply_sn = False
+
+    def enable_spectral_norm(self, seed: int = 0):
+        """Paper-faithful option `apply_sn`: W / sigma(W) as a weight re-parameterisation with a
+        persistent power-iteration vector u for every kernel the reference tags with kernel_regularizer=spectral_norm
+        (resnet_ops.py:18-24,57-71,98-111; arch_ops.py:40-65; net_architecture.py:254,286,345): all conv / transposed conv /
+        dense kernels of this model, i.e. every trainable variable named *.w except the filter bank.  In the reference the
+        regulariser's value is never read, so the default (off) is the reference-faithful behaviour."""
+        names = [v.name for v in self.store.vars if v.trainable and v.name.endswith(".w") and len(v.shape) >= 2]
+        self.apply_sn = True
+        return self.store.enable_spectral_norm(names, seed)
+
+    def sn_forward(self, rt, update_u: bool) -> None:
+        if self.apply_sn:
+            self.store.sn.forward(rt, update_u)
+
+    def sn_backward(self, rt) -> None:
+        if self.apply_sn:
+            self.store.sn.backward(rt)
 
     @property
     def trainable_variables(self):
@@ -200,6 +219,7 @@ class Discriminator(_Model):
     def __call__(self, inputs, training=True):
         x = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
         x = _nhwc(to_device_f32(self.rt, x))
+        self.sn_forward(self.rt, update_u=False)
         logits, _ = self.forward(self.rt, x)
         return logits
 
@@ -437,6 +457,7 @@ class Generator(_Model):
             a = _nhwc(to_device_f32(self.rt, a))
         else:
             a = to_device_f32(self.rt, a)
+        self.sn_forward(self.rt, update_u=False)
         img, _ = self.forward(self.rt, a, y, training)
         return img
 
@@ -478,25 +499,32 @@ def make_recognizer(input_dim, sequence_length, output_classes, vis_model=True, 
 
 
 def make_generator(latent_dim, input_dim, embed_y, kernel_reg, blocks_with_attention, vocab_size, vis_model=True,
-                   style_encoder: bool = False, rt: Optional[Runtime] = None, seed: int = 2, initialise: bool = True):
+                   style_encoder: bool = False, rt: Optional[Runtime] = None, seed: int = 2, initialise: bool = True,
+                   apply_sn: bool = False):
     m = Generator(rt or get_runtime(), latent_dim, input_dim, embed_y, kernel_reg, blocks_with_attention, vocab_size,
                   style_encoder=style_encoder, seed=seed, initialise=initialise)
+    if apply_sn:
+        m.enable_spectral_norm(seed)
     if vis_model:
         m.summary()
     return m
 
 
 def make_discriminator(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 1,
-                       initialise: bool = True):
+                       initialise: bool = True, apply_sn: bool = False):
     m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "discriminator", seed, initialise)
+    if apply_sn:
+        m.enable_spectral_norm(seed)
     if vis_model:
         m.summary()
     return m
 
 
 def make_style_promoter(input_dim, kernel_reg, blocks_with_attention, vis_model=True, rt: Optional[Runtime] = None, seed: int = 4,
-                        initialise: bool = True):
+                        initialise: bool = True, apply_sn: bool = False):
     m = Discriminator(rt or get_runtime(), input_dim, kernel_reg, blocks_with_attention, "style_promoter", seed, initialise)
+    if apply_sn:
+        m.enable_spectral_norm(seed)
     if vis_model:
         m.summary()
     return m

@@ -51,8 +51,8 @@ class ConditionalBatchNorm:
         self.gamma.backward(rt, z, s2, n, ldx=z_stride, want_dx=False)
         self.beta.backward(rt, z, s1, n, ldx=z_stride, want_dx=False)
         if dz_out is not None:
-            ops.gemm(rt, s2, self.gamma.w.data, n, self.gamma.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
-            ops.gemm(rt, s1, self.beta.w.data, n, self.beta.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
+            ops.gemm(rt, s2, self.gamma.w.eff, n, self.gamma.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
+            ops.gemm(rt, s1, self.beta.w.eff, n, self.beta.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
         return dx
 
 

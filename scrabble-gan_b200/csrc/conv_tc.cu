@@ -565,13 +565,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       if (p.det_mode == 2) {
         // Many pixel splits: every split stores its partial tile in its own scratch slot (one 128-byte line per lane and
         // chunk); after the unit loop the whole grid meets at a barrier and ALL CTAs share the ordered summation (below).
-        float* slot = p.partial + ((long long)tile * p.splits + sp) * (128 * p.BN) + (long long)row * p.BN;
+        // slot layout [BN / 4 column groups][128 rows] of float4: one store instruction of a warp (fixed column group, 32
+        // consecutive rows) writes 512 contiguous bytes
+        float4* slot = reinterpret_cast<float4*>(p.partial + ((long long)tile * p.splits + sp) * (128 * p.BN)) + row;
         for (int ch = 0; ch < p.BN / 32; ++ch) {
           uint32_t v[32];
           tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            __stcg(reinterpret_cast<float4*>(slot + ch * 32 + j),
+            __stcg(slot + (long long)(ch * 8 + j / 4) * 128,
                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
         }
         tc_fence_before();
@@ -625,24 +627,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
         __threadfence();
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int q4 = p.BN / 4;                               // float4 groups per accumulator row
-      const long long items = (long long)base_units * 128 * q4;
-      const long long tile_fl = (long long)128 * p.BN;
+      const int q4 = p.BN / 4;                               // float4 column groups per accumulator row
+      const long long items = (long long)base_units * q4 * 128;
+      const long long tile_v4 = (long long)32 * p.BN;        // float4 per partial tile
       for (long long it = (long long)blockIdx.x * 128 + (threadIdx.x - 64); it < items; it += (long long)gridDim.x * 128) {
-        const int jj = (int)(it % q4);
-        const long long rr = it / q4;
-        const int r_ = (int)(rr % 128), tile = (int)(rr / 128);
+        const int r_ = (int)(it % 128);                      // row fastest: a warp reads / writes 32 consecutive rows
+        const long long rr = it / 128;
+        const int jj = (int)(rr % q4), tile = (int)(rr / q4);
         int q = tile;
         const int cit = q % p.ci_tiles; q /= p.ci_tiles;
         const int cot = q % p.co_tiles;
         const int t = q / p.co_tiles;
         const int co = cot * 128 + r_, ci = cit * p.BN + 4 * jj;
         if (co >= p.c_out || ci >= p.c_in) continue;
-        const float* src = p.partial + (long long)tile * p.splits * tile_fl + (long long)r_ * p.BN + 4 * jj;
+        const float4* src = reinterpret_cast<const float4*>(p.partial) + (long long)tile * p.splits * tile_v4 + (long long)jj * 128 + r_;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int s2 = 0; s2 < p.splits; ++s2) {
-          float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)s2 * tile_fl));
+          float4 v = __ldcg(src + (long long)s2 * tile_v4);
           a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         float* wp = p.dw + p.tap_w_off[t] + (long long)co * p.w_co_stride + (long long)ci * p.w_ci_stride;

@@ -52,7 +52,7 @@ class ConvLayer:
         ent = self._packed.get(key)
         if ent is None or ent[0] != self.store.version:
             buf = ent[1] if ent is not None else None
-            buf = ops.pack_weights(rt, d, self.w.data, buf)
+            buf = ops.pack_weights(rt, d, self.w.eff, buf)
             self._packed[key] = (self.store.version, buf)
             return buf
         return ent[1]
@@ -67,9 +67,9 @@ class ConvLayer:
             out = rt.empty((n, ho, wo, self.co), out_dt)
         b = (self.b.data if self.b is not None else None) if isinstance(bias, str) else bias
         if ops.direct_ok(rt, d):
-            ops.conv_run(rt, d, x, self.w.data, None, b, None, out, w_mirror=self.w.mirror(rt))
+            ops.conv_run(rt, d, x, self.w.eff, None, b, None, out, w_mirror=self.w.mirror(rt))
         else:
-            ops.conv_run(rt, d, x, self.w.data, self._pack(rt, "fwd", d), b, None, out)
+            ops.conv_run(rt, d, x, self.w.eff, self._pack(rt, "fwd", d), b, None, out)
         return out
 
     def forward_with_shortcut(self, rt: Runtime, x: torch.Tensor, short: "ConvLayer", x2: torch.Tensor, bias, out_dt: int = SG_F32):
@@ -94,9 +94,9 @@ class ConvLayer:
         if out is None:
             out = rt.empty((n, h, w, self.ci), out_dt)
         if ops.direct_ok(rt, d):
-            ops.conv_run(rt, d, dy, self.w.data, None, None, mask, out, w_mirror=self.w.mirror(rt))
+            ops.conv_run(rt, d, dy, self.w.eff, None, None, mask, out, w_mirror=self.w.mirror(rt))
         else:
-            ops.conv_run(rt, d, dy, self.w.data, self._pack(rt, "dgrad", d), None, mask, out)
+            ops.conv_run(rt, d, dy, self.w.eff, self._pack(rt, "dgrad", d), None, mask, out)
         return out
 
     def wgrad(self, rt: Runtime, x: torch.Tensor, dy: torch.Tensor, bias_grad: bool = True, also_bias=None, bias_src=None) -> None:
@@ -138,7 +138,7 @@ class ConvTransposeLayer:
         key = (key, d.in_dt)
         ent = self._packed.get(key)
         if ent is None or ent[0] != self.store.version:
-            buf = ops.pack_weights(rt, d, self.w.data, ent[1] if ent is not None else None)
+            buf = ops.pack_weights(rt, d, self.w.eff, ent[1] if ent is not None else None)
             self._packed[key] = (self.store.version, buf)
             return buf
         return ent[1]
@@ -160,9 +160,9 @@ class ConvTransposeLayer:
                                          int(accumulate))
                 self._descs[key] = d
             if ops.direct_ok(rt, d):
-                ops.conv_run(rt, d, x, self.w.data, None, b, None, out, w_mirror=self.w.mirror(rt))
+                ops.conv_run(rt, d, x, self.w.eff, None, b, None, out, w_mirror=self.w.mirror(rt))
             else:
-                ops.conv_run(rt, d, x, self.w.data, self._pack(rt, ("ph", py, px), d), b, None, out)
+                ops.conv_run(rt, d, x, self.w.eff, self._pack(rt, ("ph", py, px), d), b, None, out)
         return out
 
     def _dgrad_desc(self, n, h, w, in_dt, out_dt, accumulate, mask_dt=SG_F32):
@@ -181,9 +181,9 @@ class ConvTransposeLayer:
         if out is None:
             out = rt.empty((n, h, w, self.ci), out_dt)
         if ops.direct_ok(rt, d):
-            ops.conv_run(rt, d, dout, self.w.data, None, None, None, out, w_mirror=self.w.mirror(rt))
+            ops.conv_run(rt, d, dout, self.w.eff, None, None, None, out, w_mirror=self.w.mirror(rt))
         else:
-            ops.conv_run(rt, d, dout, self.w.data, self._pack(rt, "dg", d), None, None, out)
+            ops.conv_run(rt, d, dout, self.w.eff, self._pack(rt, "dg", d), None, None, out)
         return out
 
     def wgrad(self, rt: Runtime, x: torch.Tensor, dout: torch.Tensor, bias_grad: bool = True) -> None:
@@ -204,7 +204,7 @@ class DenseLayer:
         self.b: Optional[Variable] = store.add(name + ".b", (cout,), init_zeros) if use_bias else None
 
     def forward(self, rt, x, rows: int, ldx: Optional[int] = None) -> torch.Tensor:
-        return ops.gemm(rt, x, self.w.data, rows, self.cout, self.cin, lda=ldx,
+        return ops.gemm(rt, x, self.w.eff, rows, self.cout, self.cin, lda=ldx,
                         bias=self.b.data if self.b is not None else None)
 
     def backward(self, rt, x, dy, rows: int, ldx: Optional[int] = None, want_dx: bool = True, wgrad: bool = True):
@@ -214,7 +214,7 @@ class DenseLayer:
             if self.b is not None:
                 ops.colsum_into(rt, dy, self.cout, self.b.grad, accumulate=1)
         if want_dx:
-            return ops.gemm(rt, dy, self.w.data, rows, self.cin, self.cout, trans_b=True)
+            return ops.gemm(rt, dy, self.w.eff, rows, self.cin, self.cout, trans_b=True)
         return None
 
 

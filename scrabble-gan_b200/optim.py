@@ -72,7 +72,7 @@ class Adam:
         mirror_fresh = False
         if fused:
             # keep the bf16 mirror (pack-free tensor-core convs) current in the same pass when it exists and is in sync
-            mirror = store.wb if (store.wb is not None and store.wb_version == store.version) else None
+            mirror = store.wb if (store.wb is not None and store.wb_version == store.version and store.w_eff is None) else None
             if self._dev is None:
                 self._dev = (torch.zeros(1, device=rt.device, dtype=torch.int32), torch.zeros(1, device=rt.device))
             capturing = torch.cuda.is_current_stream_capturing()

@@ -39,6 +39,15 @@ class Variable:
         assert self.trainable
         return self.store.g[self.offset:self.offset + self.numel].view(self.shape)
 
+    @property
+    def eff(self) -> torch.Tensor:
+        """The values the COMPUTE path uses: the variable itself, or -- with the spectral-norm re-parameterisation switched
+        on (ParamStore.enable_spectral_norm) -- its normalised copy W / sigma in the store's effective-weight buffer."""
+        buf = self.store.w_eff
+        if buf is None or not self.trainable:
+            return self.data
+        return buf[self.offset:self.offset + self.numel].view(self.shape)
+
     def mirror(self, rt) -> torch.Tensor:
         """bf16 mirror of this variable (view into the store's mirror buffer, refreshed lazily)."""
         assert self.trainable
@@ -110,6 +119,8 @@ class ParamStore:
         self.wb: Optional[torch.Tensor] = None     # bf16 mirror of w (same offsets), kept current by the optimizer kernel
         self.wb_version = -1
         self.n_trainable = 0
+        self.w_eff: Optional[torch.Tensor] = None  # effective weights (spectral-norm re-parameterisation on): same layout as w
+        self.sn: Optional["SpectralNormState"] = None
 
     def add(self, name: str, shape, init: Callable = init_zeros, trainable: bool = True) -> Variable:
         assert self.w is None, "store already finalised"
@@ -152,9 +163,20 @@ class ParamStore:
         if self.wb_version != self.version:
             from . import ops
             from ._abi import SG_BF16
-            ops.call.sg_cast(rt.ctx, ops._p(self.w), ops._p(self.wb), SG_BF16, self.w.numel())
+            src = self.w if self.w_eff is None else self.w_eff
+            ops.call.sg_cast(rt.ctx, ops._p(src), ops._p(self.wb), SG_BF16, self.w.numel())
             self.wb_version = self.version
         return self.wb
+
+    def enable_spectral_norm(self, names, seed: int = 0) -> "SpectralNormState":
+        """Switch on the spectral-norm weight re-parameterisation for the listed kernels (paper-faithful option; in the
+        reference spectral_norm is a kernel_regularizer nobody reads -- SURVEY Q2).  The compute path then reads
+        W / sigma(W) from `w_eff`; one power-iteration step per training forward with a PERSISTENT u."""
+        assert self.w is not None, "finalize the store first"
+        self.w_eff = self.w.clone()
+        self.sn = SpectralNormState(self, [self.by_name[n] for n in names], seed)
+        self.version += 1
+        return self.sn
 
     @property
     def trainable_variables(self) -> List[Variable]:
@@ -176,3 +198,50 @@ class ParamStore:
 
     def grad_dict(self) -> Dict[str, torch.Tensor]:
         return {v.name: v.grad.detach().clone() for v in self.vars if v.trainable}
+
+
+class SpectralNormState:
+    """W_sn = W / sigma, sigma = v^T W u after one power-iteration step from the persistent u (arch_ops.py:99-126 computes the
+    same quantity from a fresh random u; SN-GAN / compare_gan keep u).  forward() refreshes the effective weights of the
+    store, backward() maps the gradients w.r.t. W_sn (accumulated in the store's gradient bucket by the ordinary backward
+    passes) to gradients w.r.t. W, with u and v treated as constants:  dW = (G - <G, W_sn> v u^T) / sigma."""
+
+    def __init__(self, store: ParamStore, variables, seed: int):
+        self.store = store
+        dev = store.w.device
+        gen = torch.Generator().manual_seed(seed + 7919)
+        self.entries = []
+        for v in variables:
+            cols = v.shape[-1]
+            rows = v.numel // cols
+            u = torch.randn(cols, generator=gen, dtype=torch.float32).to(dev)
+            self.entries.append({"var": v, "rows": rows, "cols": cols, "u": u, "u_new": torch.empty_like(u),
+                                 "sigma": torch.ones(1, device=dev), "scratch": torch.empty(rows + cols + 4, device=dev),
+                                 "dot": torch.empty(1, device=dev)})
+
+    def u_dict(self):
+        return {e["var"].name: e["u"].detach().clone() for e in self.entries}
+
+    def load_u(self, us) -> None:
+        for e in self.entries:
+            if e["var"].name in us:
+                e["u"].copy_(torch.as_tensor(us[e["var"].name]).to(device=e["u"].device, dtype=torch.float32).reshape(-1))
+
+    def forward(self, rt, update_u: bool = True) -> None:
+        from . import ops
+        st = self.store
+        st.w_eff.copy_(st.w)                          # biases, BN / CBN parameters, ... are used as they are
+        for e in self.entries:
+            v = e["var"]
+            ops.call.sg_spectral_norm(rt.ctx, ops._p(v.data), e["rows"], e["cols"], ops._p(e["u"]), 1, ops._p(v.eff), ops._p(e["u_new"]),
+                                      ops._p(e["sigma"]), ops._p(e["scratch"]))
+            if update_u:
+                e["u"].copy_(e["u_new"])
+        st.version += 1                               # packed filters / the bf16 mirror derive from w_eff
+
+    def backward(self, rt) -> None:
+        from . import ops
+        for e in self.entries:
+            v = e["var"]
+            ops.call.sg_spectral_norm_bwd(rt.ctx, ops._p(v.grad), ops._p(v.eff), e["rows"], e["cols"], ops._p(e["u_new"]), ops._p(e["sigma"]),
+                                          ops._p(e["scratch"]), ops._p(e["dot"]))

@@ -1,0 +1,120 @@
+"""The paper-faithful options of SURVEY.md section 8f (rank 4) -- NOT what the reference executes, hence off by default:
+  * balance_mode="paper": gradient-level balancing std(grad_D)/std(grad_R) on the image gradients (arXiv 2003.10557 s. 3.4,
+    BASELINE north_star's wording) instead of the fork's loss-level balancing (data_utils.py:476-490);
+  * apply_sn=True: spectral norm as a weight re-parameterisation with a persistent u (arch_ops.py:99-126 is installed as a
+    kernel_regularizer whose value nobody reads: SURVEY Q2 / Q3).
+Both against the fp64 oracle's statement of the same option, in exact-fp32 mode."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import sgan_oracle as O
+from _parity import Soft, assert_grads, assert_stats, build_models, du, make_inputs, make_params, na, nl, optim, rel_max
+
+pytestmark = pytest.mark.gpu
+ops = importlib.import_module("scrabble-gan_b200.ops")
+
+
+def _step(rt, G, D, R, inputs, **kw):
+    images, labels, fake_labels, z = inputs
+    gan = na.make_gan(G, D, R, None, vis_model=False)
+    g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+    out = du.train_step(0, 0, 1, images.float().numpy(), labels.numpy(), D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, images.shape[0], 128,
+                        loss_fn, disc_iters, agb, None, 10, "", fake_labels=fake_labels.numpy(), noise=z.float().numpy(), **kw)
+    return dict(zip(du.STAT_NAMES, out))
+
+
+@pytest.mark.parametrize("l_r,l_f", [(2, 2), (2, 3)])
+def test_paper_gradient_balancing(rt, l_r, l_f):
+    rt.set_mode("fp32")
+    old = du.GRAPH_ENABLED
+    soft = Soft()
+    try:
+        du.GRAPH_ENABLED = False
+        dt = torch.float64
+        P = make_params(90, dt)
+        inputs = make_inputs(91, 3, l_r, l_f, dt)
+        stats, _, _, grads, extra = O.train_step(P, {}, *inputs, return_grads=True, balance_mode="paper")
+        G, D, R, _ = build_models(rt, P)
+        got = _step(rt, G, D, R, inputs, balance_mode="paper")
+        assert_stats(got, stats, 1e-3, "paper-mode step", soft=soft)
+        assert abs(got["r_loss_balanced"] - got["r_loss_fake"] * got["alpha"] * got["g_loss_std"] / got["r_loss_fake_std"]) <= 1e-3 * abs(got["r_loss_balanced"])
+        for n, m in (("D", D), ("R", R), ("G", G)):
+            assert_grads(m.store.grad_dict(), grads[n], 1e-3, 1e-2, "paper-mode {} gradients".format(n), soft=soft)
+        # and it is a different algorithm from the fork's loss-level balancing
+        ref_stats = O.train_step(P, {}, *inputs)[0]
+        assert abs(ref_stats["g_loss_final"] - stats["g_loss_final"]) > 1e-2 * abs(ref_stats["g_loss_final"])
+        soft.done()
+    finally:
+        du.GRAPH_ENABLED = old
+        rt.set_mode("fp32")
+
+
+def test_spectral_norm_backward_operator(rt):
+    """sg_spectral_norm + sg_spectral_norm_bwd == autograd through W / sigma with u, v held constant."""
+    g = torch.Generator().manual_seed(3)
+    for shape in ((3, 3, 16, 24), (32, 64), (1024, 1)):
+        w = torch.randn(*shape, generator=g, dtype=torch.float64)
+        u = torch.randn(shape[-1], generator=g, dtype=torch.float64)
+        gout = torch.randn(*shape, generator=g, dtype=torch.float64)
+        wl = w.clone().requires_grad_(True)
+        wsn = O.spectral_norm_reparam(wl, u)
+        (wsn * gout).sum().backward()
+        wd = w.float().to(rt.device)
+        w_sn, u_hat, sigma = ops.spectral_norm(rt, wd, u.float().to(rt.device), 1)
+        assert rel_max(w_sn, wsn) <= 1e-4
+        # the operator's scratch is internal to ops.spectral_norm: redo the forward through the raw ABI to keep it
+        cols = shape[-1]
+        rows = w.numel() // cols
+        scratch, w_out, u_out, sg = rt.empty((rows + cols + 4,)), rt.empty(shape), rt.empty((cols,)), rt.empty((1,))
+        ops.call.sg_spectral_norm(rt.ctx, ops._p(wd), rows, cols, ops._p(u.float().to(rt.device)), 1, ops._p(w_out), ops._p(u_out), ops._p(sg), ops._p(scratch))
+        gd = gout.float().to(rt.device).contiguous()
+        ops.call.sg_spectral_norm_bwd(rt.ctx, ops._p(gd), ops._p(w_out), rows, cols, ops._p(u_out), ops._p(sg), ops._p(scratch), ops._p(rt.empty((1,))))
+        assert rel_max(gd, wl.grad) <= 1e-4, shape
+
+
+def test_apply_sn_train_step(rt):
+    rt.set_mode("fp32")
+    old = du.GRAPH_ENABLED
+    soft = Soft()
+    try:
+        du.GRAPH_ENABLED = False
+        dt = torch.float64
+        P = make_params(95, dt)
+        g = torch.Generator().manual_seed(96)
+        for n in ("G", "D"):             # make sigma(W) != 1 so that the normalisation matters
+            for k in P[n]:
+                if k.endswith(".w") and P[n][k].dim() >= 2:
+                    P[n][k] = P[n][k] * (0.5 + torch.rand(1, generator=g, dtype=dt))
+        inputs = make_inputs(97, 3, 2, 2, dt)
+        G, D, R, _ = build_models(rt, P)
+        G.enable_spectral_norm(1)
+        D.enable_spectral_norm(2)
+        sn_u = {"G": {k: v.double().cpu() for k, v in G.store.sn.u_dict().items()}, "D": {k: v.double().cpu() for k, v in D.store.sn.u_dict().items()}}
+        assert set(sn_u["D"]) == {k for k in P["D"] if k.endswith(".w") and P["D"][k].dim() >= 2}
+        assert "filter_bank" not in sn_u["G"] and "B1.cbn1.gamma.w" in sn_u["G"] and "B3.attn.theta.w" in sn_u["G"]
+        stats, newp, _, grads, extra = O.train_step(P, {}, *inputs, return_grads=True, sn_u=sn_u)
+        plain = O.train_step(P, {}, *inputs)[0]
+        assert abs(plain["d_loss_fake"] - stats["d_loss_fake"]) > 1e-4, "the test weights must make the normalisation visible"
+        got = _step(rt, G, D, R, inputs)
+        assert_stats(got, stats, 1e-3, "apply_sn step", soft=soft)
+        for n, m in (("D", D), ("R", R), ("G", G)):
+            assert_grads(m.store.grad_dict(), grads[n], 1e-3, 1e-2, "apply_sn {} gradients".format(n), soft=soft)
+        # persistent u: after the step u is the power-iterated u_hat of the weights the step STARTED from
+        w0 = P["D"]["B3.conv2.w"].reshape(-1, 1024)
+        u0 = sn_u["D"]["B3.conv2.w"].reshape(1, -1)
+        v = u0 @ w0.t()
+        v = v / v.norm()
+        u1 = v @ w0
+        u1 = u1 / u1.norm()
+        soft.check(rel_max(D.store.sn.u_dict()["B3.conv2.w"], u1.reshape(-1)) <= 1e-4, "persistent u after one step")
+        # inference applies W / sigma with the current u and does not move u
+        u_before = D.store.sn.u_dict()["B3.conv2.w"].clone()
+        D([inputs[0].float().numpy()])
+        soft.check(torch.equal(u_before, D.store.sn.u_dict()["B3.conv2.w"]), "inference leaves u untouched")
+        soft.done()
+    finally:
+        du.GRAPH_ENABLED = old
+        rt.set_mode("fp32")
