@@ -1136,7 +1136,9 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   p.ptiles_per_split = sg_div_up(ptiles, splits);
   p.splits = sg_div_up(ptiles, p.ptiles_per_split);
   p.partial = ctx->det_scratch;
-  p.det_mode = p.splits == 1 ? 0 : (p.splits <= 4 ? 1 : 2);
+  // measured per layer (tools/bench_conv.py, SGAN_WGRAD_DET=turns|scratch): ordered turns cost ~one epilogue per split on the
+  // critical path, which only long main loops hide; the scratch + grid-barrier combine costs ~5-15 us flat
+  p.det_mode = p.splits == 1 ? 0 : ((p.splits <= 4 && p.ptiles_per_split >= 64) ? 1 : 2);
   {
     const char* ov = getenv("SGAN_WGRAD_DET");          // A/B diagnostics: "legacy" = unordered atomics, "turns" = ordered turns only
     if (ov && p.splits > 1) {

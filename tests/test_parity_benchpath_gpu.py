@@ -28,28 +28,49 @@ TOL_OUT = {"fp32": 1e-3, "tf32": 2e-3, "bf16": 1e-2}
 #   * the image gradient through the frozen D is a sum with ~100x cancellation: the fp32 CUDA path, whose D gradients agree
 #     with the fp32 oracle to 2e-5, has an image gradient 2e-3 off and G gradients 4e-4 off (measured, B = 64).
 # So it is checked in three well-posed parts: (i) the 16 statistics (alpha, the two stds, the balanced losses), which pin the
-# scalar map, at TOL_OUT; (ii) G's backward OPERATOR: G.backward fed with the oracle's image gradient, at TOL; (iii) the
-# composed gradient against a CONDITIONING-CALIBRATED bound: kappa = (error of G's gradient) / (error of D's and R's
-# gradients) between two runs of the ORACLE itself that differ only in accumulation precision (fp32 vs fp64), and the CUDA
-# path must satisfy err_G <= 2 * kappa * max(err_D, err_R, floor) -- a wrong G backward would exceed it by orders of magnitude.
-# fp32 mode, where the logits agree to 1e-6, is held to the plain 1e-3.
+# scalar map, at TOL_OUT; (ii) G's backward OPERATOR: G.backward fed with the oracle's image gradient, at TOL_G_OP; (iii) the
+# composed gradient by a SCALING criterion: conditioning amplifies whatever arithmetic noise there is by a fixed factor, so
+# the ratio err_G / max(err_D, err_R) must be the same in every precision mode.  It is measured on the exact-fp32 CUDA path
+# (where the gradient itself is held to 1e-3 absolutely) and the reduced-precision modes must stay within 2.5x of it
+# (measured at B = 64: 18.8 in fp32, 13.4 in tf32, 16.8 in bf16 -- over three orders of magnitude of arithmetic noise).  A
+# wrong G backward does not scale with the arithmetic precision and breaks the ratio by orders of magnitude.
+# (With the paper's gradient-level balancing the same G gradient agrees to 1e-6 in fp32: tests/test_paper_options_gpu.py.)
+# G's own backward contains the batch-norm backward (dy - mean(dy) - x_hat mean(dy x_hat)), a 3.5-7.5x amplifier in every mode
+# (fp32 1.6e-4 vs 2.1e-5 on D): its operator bound in the reduced-precision modes is 5x the whole-gradient tolerance.
+TOL_G_OP = {"fp32": (1e-3, 5e-3), "tf32": (5e-3, 4e-2), "bf16": (1e-2, 5e-2)}
+_FP32_RATIO = {}
 
 
-def _kappa(grads_lo, grads_hi):
-    """Noise amplification of G's gradient relative to D's / R's, from two oracle runs of different accumulation precision."""
+def _fp32_ratio(rt, key, P, inputs, grads_fp32_oracle):
+    """err_G / max(err_D, err_R) of the exact-fp32 CUDA path on this case (against the un-rounded oracle): the conditioning
+    amplification every other mode is compared with.  grads_fp32_oracle() returns the oracle's gradients without rounding."""
     from _parity import grad_profile
-    e = {n: grad_profile(grads_lo[n], grads_hi[n])[0] for n in ("D", "R", "G")}
-    return e["G"] / max(e["D"], e["R"], 1e-12), e
+    if key not in _FP32_RATIO:
+        mode0, graph0 = rt.mode, du.GRAPH_ENABLED
+        rt.set_mode("fp32")
+        du.GRAPH_ENABLED = False
+        try:
+            G, D, R, _ = build_models(rt, P)
+            run_step(rt, G, D, R, None, *inputs)
+            g = grads_fp32_oracle()
+            e = {n: grad_profile(m.store.grad_dict(), g[n])[0] for n, m in (("D", D), ("R", R), ("G", G))}
+        finally:
+            rt.set_mode(mode0)
+            du.GRAPH_ENABLED = graph0
+        _FP32_RATIO[key] = (e["G"] / max(e["D"], e["R"], 1e-12), e)
+    return _FP32_RATIO[key]
 
 
-def _check_g(soft, mode, errs, err_g, kappa, what):
+def _check_g(soft, mode, errs, err_g, ref, what):
     tw = TOL[mode][0]
     if mode == "fp32":
         soft.check(err_g <= tw, "{}: G gradients of the whole step: rel L2 {:.3e} (bound {:.0e})".format(what, err_g, tw))
         return
-    bound = 2.0 * kappa * max(errs["D"], errs["R"], 0.1 * tw)
-    soft.check(err_g <= max(bound, tw), "{}: G gradients of the whole step: rel L2 {:.3e}; conditioning-calibrated bound 2 * kappa * max(err_D, err_R) "
-               "= 2 * {:.1f} * {:.2e} = {:.3e}".format(what, err_g, kappa, max(errs["D"], errs["R"]), bound))
+    ratio0, e0 = ref
+    ratio = err_g / max(errs["D"], errs["R"], 1e-12)
+    soft.check(err_g <= tw or ratio <= 2.5 * ratio0,
+               "{}: G gradients of the whole step: rel L2 {:.3e} = {:.1f} x max(err_D, err_R); the exact-fp32 CUDA path has {:.1f} x "
+               "(D {:.1e} R {:.1e} G {:.1e}); bound 2.5 x that ratio".format(what, err_g, ratio, ratio0, e0["D"], e0["R"], e0["G"]))
 
 
 def _g_backward_with_oracle_image_gradient(rt, soft, P, inputs, extra, g_exp, tw, tt, what):
@@ -92,10 +113,7 @@ def _fused_case(mode, tf32_wgrad):
         P = make_params(40, dt)
         inputs = make_inputs(41, b, l, l, dt)
         stats, newp, _, grads, extra = _oracle_step(P, *inputs, mode, tf32_wgrad)
-        P32 = {n: {k: v.float() for k, v in d.items()} for n, d in P.items()}
-        in32 = tuple(t.float() if t.is_floating_point() else t for t in inputs)
-        grads32 = _oracle_step(P32, *in32, mode, tf32_wgrad)[3]
-        _FUSED_ORACLE[key] = (P, inputs, stats, grads, extra, _kappa(grads32, grads)[0])
+        _FUSED_ORACLE[key] = (P, inputs, stats, grads, extra)
     return _FUSED_ORACLE[key]
 
 
@@ -111,7 +129,7 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
         du._graph_cache.clear()
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = graph, 0
         assert rt.merge_r_backward
-        P, (images, labels, fake_labels, z), stats, grads, extra, kappa = _fused_case(mode, _tf32_wgrad_on_tc(rt))
+        P, (images, labels, fake_labels, z), stats, grads, extra = _fused_case(mode, _tf32_wgrad_on_tc(rt))
         if graph:
             # every kernel of the step is launched once eagerly first (on throw-away models): CUDA loads a kernel's module
             # at its first launch, which must not happen inside a stream capture
@@ -134,9 +152,12 @@ def test_fused_path_matches_rounded_oracle(rt, mode, graph):
         for n, m in (("D", D), ("R", R)):
             errs[n] = assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients ({})".format(mode, n, how), soft=soft)[0]
         from _parity import grad_profile
-        _check_g(soft, mode, errs, grad_profile(G.store.grad_dict(), grads["G"])[0], kappa, "{} B=16 ({})".format(mode, how))
+        err_g = grad_profile(G.store.grad_dict(), grads["G"])[0]
+        ref = _fp32_ratio(rt, "fused", P, (images, labels, fake_labels, z), lambda: _oracle_step(P, images, labels, fake_labels, z, "fp32")[3])
+        _check_g(soft, mode, errs, err_g, ref, "{} B=16 ({})".format(mode, how))
         if not graph:
-            _g_backward_with_oracle_image_gradient(rt, soft, P, (images, labels, fake_labels, z), extra, grads["G"], tw, tt, "{} B=16".format(mode))
+            _g_backward_with_oracle_image_gradient(rt, soft, P, (images, labels, fake_labels, z), extra, grads["G"], *TOL_G_OP[mode],
+                                                   "{} B=16".format(mode))
         soft.done()
     finally:
         du.GRAPH_ENABLED, du.GRAPH_WARMUP = old
@@ -155,7 +176,6 @@ class _FullCase:
         self.P = make_params(60, dt, sigma=0.1, bias_scale=0.02)
         self.inputs = make_inputs(61, self.B, self.L, self.L, dt)
         self._oracle = {}
-        self._kappa = None
 
     def oracle(self, mode, tf32_wgrad=False):
         key = (mode, tf32_wgrad)
@@ -163,15 +183,6 @@ class _FullCase:
             stats, newp, _, grads, extra = _oracle_step(self.P, *self.inputs, mode, tf32_wgrad)
             self._oracle[key] = (stats, grads, extra)
         return self._oracle[key]
-
-    def kappa(self):
-        """G-gradient noise amplification at this size: exact oracle in fp32 against exact oracle in fp64."""
-        if self._kappa is None:
-            P64 = {n: {k: v.double() for k, v in d.items()} for n, d in self.P.items()}
-            in64 = tuple(t.double() if t.is_floating_point() else t for t in self.inputs)
-            g64 = _oracle_step(P64, *in64, "fp32")[3]
-            self._kappa = _kappa(self.oracle("fp32")[1], g64)
-        return self._kappa
 
 
 @pytest.fixture(scope="module")
@@ -223,11 +234,14 @@ def test_train_step_at_baseline_size(rt, full_case, mode):
         for n, m in (("D", D), ("R", R)):
             errs[n] = assert_grads(m.store.grad_dict(), grads[n], tw, tt, "{} {} gradients at B=64, L=5".format(mode, n), soft=soft)[0]
         from _parity import grad_profile
-        kappa, ke = fc.kappa() if mode != "fp32" else (1.0, {})
-        if ke:
-            print("oracle fp32 vs fp64 at B=64, L=5: rel L2 D {:.2e} R {:.2e} G {:.2e} -> kappa {:.1f}".format(ke["D"], ke["R"], ke["G"], kappa))
-        _check_g(soft, mode, errs, grad_profile(G.store.grad_dict(), grads["G"])[0], kappa, "{} B=64 L=5".format(mode))
-        _g_backward_with_oracle_image_gradient(rt, soft, fc.P, fc.inputs, extra, grads["G"], tw, tt, "{} B=64 L=5".format(mode))
+        err_g = grad_profile(G.store.grad_dict(), grads["G"])[0]
+        ref = None
+        if mode == "fp32":
+            _FP32_RATIO["full"] = (err_g / max(errs["D"], errs["R"], 1e-12), dict(errs, G=err_g))
+        else:
+            ref = _fp32_ratio(rt, "full", fc.P, fc.inputs, lambda: fc.oracle("fp32")[1])
+        _check_g(soft, mode, errs, err_g, ref, "{} B=64 L=5".format(mode))
+        _g_backward_with_oracle_image_gradient(rt, soft, fc.P, fc.inputs, extra, grads["G"], *TOL_G_OP[mode], "{} B=64 L=5".format(mode))
         soft.done()
     finally:
         du.GRAPH_ENABLED = old
