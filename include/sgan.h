@@ -273,6 +273,10 @@ int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, fl
 int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
                      float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
 
+/* ---- host utility: CRC32C (Castagnoli) of a HOST buffer, chained through `crc` (start with 0).  TensorFlow checkpoints --
+ * what the reference's save_weights writes (data_utils.py:346-348) -- protect tensors and index blocks with it. */
+unsigned int sg_crc32c(const void* host_data, size_t n, unsigned int crc);
+
 /* backward of the weight re-parameterisation W_sn = W / sigma (u, v constants), in place on g = dL/dW_sn:
  * g <- (g - <g, W_sn> v u^T) / sigma.  fwd_scratch is the scratch sg_spectral_norm filled for this weight (it holds the
  * un-normalised v and its inverse norm), u_hat its u_out, dot_scratch one float.  Paper-faithful option `apply_sn`:

@@ -124,14 +124,42 @@ class _Model:
         print('Model "{}": {:,} trainable parameters in {} variables'.format(self.name, self.store.n_trainable,
                                                                            len(self.store.trainable_variables)))
 
-    def save_weights(self, prefix: str) -> None:
-        """Per-epoch checkpoint (reference data_utils.py:346-348): an .npz of every variable in TF layouts."""
+    def save_weights(self, prefix: str, save_format: Optional[str] = None) -> None:
+        """Per-epoch checkpoint (reference data_utils.py:346-348: `model.save_weights(prefix)`).  Default: what Keras writes
+        for such a prefix -- a TensorFlow checkpoint `<prefix>.index` + `<prefix>.data-00000-of-00001` whose keys are the
+        reference model's `layer_with_weights-N/...` names (bigacgan/keras_names.py), so the file can be loaded by the
+        reference; variables the reference does not track (the NonLocalBlock projections) are stored under
+        `_sgan/<name>`.  save_format="npz" (or a prefix ending in .npz): one .npz of every variable by libsgan name."""
         d = os.path.dirname(prefix)
         if d:
             os.makedirs(d, exist_ok=True)
-        np.savez(prefix + ".npz", **{k: v.cpu().numpy() for k, v in self.store.state_dict().items()})
+        if save_format == "npz" or prefix.endswith(".npz"):
+            path = prefix if prefix.endswith(".npz") else prefix + ".npz"
+            np.savez(path, **{k: v.cpu().numpy() for k, v in self.store.state_dict().items()})
+            return
+        from .. import tf_checkpoint
+        from . import keras_names
+        keys = keras_names.keys_for(self)
+        tensors = {}
+        for name, t in self.store.state_dict().items():
+            a = t.detach().cpu().numpy().astype(np.float32)
+            if name in keys:
+                tensors[keys[name]] = a.reshape(()) if name.endswith(".sigma") else a
+            else:
+                tensors["_sgan/" + name] = a
+        tf_checkpoint.write_checkpoint(prefix, tensors)
 
-    def load_weights(self, prefix: str) -> None:
+    def load_weights(self, prefix: str, key_map=None) -> None:
+        """Load a checkpoint written by `save_weights` -- or by the REFERENCE's `model.save_weights(prefix)` (TensorFlow
+        checkpoint with Keras names; every tensor is shape-checked, `key_map` overrides derived names) -- or an .npz."""
+        if os.path.exists(prefix + ".index"):
+            from .. import tf_checkpoint
+            from . import keras_names
+            keras_names.load_keras_checkpoint(self, prefix, key_map=key_map)
+            extra = {k[len("_sgan/"):]: v for k, v in tf_checkpoint.read_checkpoint(prefix).items() if k.startswith("_sgan/")}
+            if extra:
+                self.store.load_state_dict(extra, strict=False)
+            return
         path = prefix if prefix.endswith(".npz") else prefix + ".npz"
         with np.load(path) as f:
             self.store.load_state_dict({k: f[k] for k in f.files})

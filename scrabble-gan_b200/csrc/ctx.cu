@@ -85,3 +85,38 @@ int sg_ctx_set_speed_mode(sg_ctx* ctx, int on) {
 
 // layout guard for the ctypes mirror of sg_conv_desc
 extern "C" int sg_sizeof_conv_desc(void) { return (int)sizeof(sg_conv_desc); }
+
+// ---------------------------------------------------------------------------------------------------
+// CRC32C (Castagnoli), slicing-by-8, host side: TensorFlow checkpoints protect every tensor and every index block with it
+// (tf_checkpoint.py reads / writes the reference's save_weights files: data_utils.py:346-348)
+// ---------------------------------------------------------------------------------------------------
+static uint32_t g_crc_tab[8][256];
+static bool g_crc_init = false;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0u);
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFF];
+  g_crc_init = true;
+}
+
+extern "C" unsigned int sg_crc32c(const void* data, size_t n, unsigned int crc) {
+  if (!g_crc_init) crc_init();
+  const unsigned char* p = (const unsigned char*)data;
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n && ((uintptr_t)p & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8); --n; }
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    uint32_t lo = (uint32_t)v ^ c, hi = (uint32_t)(v >> 32);
+    c = g_crc_tab[7][lo & 0xFF] ^ g_crc_tab[6][(lo >> 8) & 0xFF] ^ g_crc_tab[5][(lo >> 16) & 0xFF] ^ g_crc_tab[4][lo >> 24] ^
+        g_crc_tab[3][hi & 0xFF] ^ g_crc_tab[2][(hi >> 8) & 0xFF] ^ g_crc_tab[1][(hi >> 16) & 0xFF] ^ g_crc_tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}

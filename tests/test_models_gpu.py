@@ -403,7 +403,12 @@ def test_train_shell_runs_on_synthetic_buckets(rt, tmp_path):
         assert lines[0].split(";")[:4] == ["disc_loss", "disc_loss_real", "disc_loss_fake", "r_loss_real"] and len(lines[0].split(";")) == 16
         assert len(lines) == 1 + 2 * 2 and all(len(l.split(";")) == 16 and all(np.isfinite(float(v)) for v in l.split(";")) for l in lines[1:])
         assert len(open(os.path.join(out, "epoch_summary.txt")).read().strip().split("\n")) == 1 + 2
-        assert os.path.exists(os.path.join(ckpt, "generator", "2", "cktp-2.npz")) and os.path.exists(os.path.join(ckpt, "recognizer", "1", "cktp-1.npz"))
+        # per-epoch save_weights in the reference's own format: TensorFlow checkpoints with Keras variable names
+        assert os.path.exists(os.path.join(ckpt, "generator", "2", "cktp-2.index")) and os.path.exists(os.path.join(ckpt, "recognizer", "1", "cktp-1.data-00000-of-00001"))
+        tfc = importlib.import_module("scrabble-gan_b200.tf_checkpoint")
+        saved = tfc.read_checkpoint(os.path.join(ckpt, "recognizer", "2", "cktp-2"), verify_crc=True)
+        assert saved["layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"].shape == (3, 3, 1, 64)
+        assert saved["layer_with_weights-9/bias/.ATTRIBUTES/VARIABLE_VALUE"].shape == (53,)
         imgs = np.load(os.path.join(out, "image_at_epoch_0002.npy"))
         assert imgs.shape == (bs, 32, 48, 1) and imgs.min() >= 0.0 and imgs.max() <= 1.0
         assert (g_opt.iterations, d_opt.iterations, r_opt.iterations) == (4, 4, 4)
@@ -464,3 +469,46 @@ def test_eager_after_graph_replay_uses_current_weights(rt):
         du.GRAPH_ENABLED = old
         du._graph_cache.clear()
         rt.set_mode("fp32")
+
+
+def test_load_reference_style_checkpoint(rt, tmp_path):
+    """A TensorFlow checkpoint laid out as the reference's `generator.save_weights` / `recognizer.save_weights` write it
+    (data_utils.py:346-348: Keras `layer_with_weights-N/<attr>/.ATTRIBUTES/VARIABLE_VALUE` keys, TF layouts) loads into the
+    libsgan models through `load_weights`: outputs equal the oracle's on those weights.  (The file is produced here with
+    scrabble-gan_b200/tf_checkpoint.py from the oracle's parameters: no TensorFlow in this image -- unpinned.)"""
+    rt.set_mode("fp32")
+    tfc = importlib.import_module("scrabble-gan_b200.tf_checkpoint")
+    kn = importlib.import_module("scrabble-gan_b200.bigacgan.keras_names")
+    g = torch.Generator().manual_seed(3)
+    PG = O.make_generator_params(61, torch.float32, sigma=0.2, bias_scale=0.1)
+    PR = O.make_recognizer_params(62, torch.float32, bias_scale=0.1)
+    for k in list(PG):
+        if k.endswith(".moving_mean"):
+            PG[k] = torch.randn(PG[k].shape, generator=g) * 0.1
+        if k.endswith(".moving_var"):
+            PG[k] = torch.rand(PG[k].shape, generator=g) + 0.5
+    for P, keys, name in ((PG, kn.generator_keys("B3", style_encoder=False), "g"), (PR, kn.recognizer_keys(), "r")):
+        tensors = {key: (P[ours].numpy().reshape(()) if ours.endswith(".sigma") else P[ours].numpy()) for ours, key in keys.items()}
+        tfc.write_checkpoint(str(tmp_path / name / "cktp-3"), tensors)
+    G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=5)
+    R = na.make_recognizer(IN_DIM, None, 53, vis_model=False, rt=rt, seed=6)
+    G.load_weights(str(tmp_path / "g" / "cktp-3"))
+    R.load_weights(str(tmp_path / "r" / "cktp-3"))
+    # the attention projections are not part of a reference checkpoint (SURVEY Q4): give the oracle the model's own
+    sd = G.state_dict()
+    for k in ("B3.attn.theta.w", "B3.attn.phi.w", "B3.attn.g.w", "B3.attn.o.w"):
+        PG[k] = sd[k].cpu()
+    z = torch.randn(3, 128, generator=g)
+    y = torch.randint(0, 52, (3, 4), generator=g)
+    assert rel(G([z.numpy(), y.numpy()], training=False), O.generator_core(z, y, PG, "B3", False)) <= 1e-3
+    x = torch.rand(3, 32, 64, 1, generator=g) * 2 - 1
+    exp = O.recognizer(x, y, torch.full((3, 1), 15), torch.full((3, 1), 4), PR)
+    assert rel(R([x.numpy(), y.numpy()]), exp) <= 1e-4
+    # a checkpoint of the wrong model is refused with the key table, not loaded silently
+    with pytest.raises(ValueError):
+        R.load_weights(str(tmp_path / "g" / "cktp-3"))
+    # and our own save_weights round-trips everything, attention projections included
+    G.save_weights(str(tmp_path / "ours" / "cktp-1"))
+    G2 = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=99)
+    G2.load_weights(str(tmp_path / "ours" / "cktp-1"))
+    assert torch.equal(G2.store.w, G.store.w) and torch.equal(G2.store.s, G.store.s)
