@@ -273,6 +273,12 @@ int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, fl
 int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
                      float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
 
+/* ---- counter-based random numbers (K21; replaces tf.random.normal of data_utils.py:385) -- Philox4x32-10.  out[n] ~ U[-1,1)
+ * (normal = 0) or N(0,1) (normal = 1, Box-Muller) at stream position offset + *offset_dev (offset_dev may be NULL); a given
+ * offset_dev is advanced by ceil(n / 4) afterwards, so CUDA-graph replays continue the stream. */
+int sg_random(sg_ctx* ctx, float* out, long long n, unsigned long long seed, unsigned long long offset,
+              unsigned long long* offset_dev, int normal);
+
 /* ---- host utility: CRC32C (Castagnoli) of a HOST buffer, chained through `crc` (start with 0).  TensorFlow checkpoints --
  * what the reference's save_weights writes (data_utils.py:346-348) -- protect tensors and index blocks with it. */
 unsigned int sg_crc32c(const void* host_data, size_t n, unsigned int crc);

@@ -54,6 +54,7 @@ _PROTOS = {
     "sg_ctx_set_speed_mode": (_I, [_P, _I]),
     "sg_sizeof_conv_desc": (_I, []),
     "sg_crc32c": (C.c_uint, [_P, _Z, C.c_uint]),
+    "sg_random": (_I, [_P, _P, _L, C.c_ulonglong, C.c_ulonglong, _P, _I]),
     "sg_conv_fwd_simt": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_wgrad_simt": (_I, [_P, _DP, _P, _P, _P]),
     "sg_conv_tc_supported": (_I, [_DP]),

@@ -151,7 +151,8 @@ def train_step(epoch_idx, batch_idx, batch_per_epoch, images, labels, discrimina
     if generator.style is not None:
         g_in = style_imgs
     else:
-        g_in = to_device_f32(rt, noise) if noise is not None else torch.randn(batch_size, latent_dim, device=rt.device)
+        # noise = tf.random.normal([batch_size, latent_dim]) (data_utils.py:385): libsgan's Philox kernel, no torch op
+        g_in = to_device_f32(rt, noise) if noise is not None else ops.random_(rt, rt.empty((batch_size, latent_dim)))
     stats = _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs)
     return _finish(stats, return_device_stats, verbose, epoch_idx, batch_idx, batch_per_epoch)
 
@@ -237,7 +238,7 @@ def _replay(rt, gs, args, images, labels, fake_labels, noise):
     if noise is not None:
         z_s.copy_(_as_tensor(noise, np.float32), non_blocking=True)
     else:
-        z_s.normal_()
+        ops.random_(rt, z_s)
     used = [(opts[1], stores[0]), (opts[2], stores[1])] + ([(opts[0], stores[2])] if update_g else [])
     for o, _ in used:
         o.advance_for_replay(rt)
@@ -440,6 +441,9 @@ def train(dataset, generator, discriminator, recognizer, style_promoter, composi
     os.makedirs(recognizer_save_dir, exist_ok=True)
     os.makedirs(gen_path, exist_ok=True)
     batch_per_epoch = int(buffer_size / batch_size) + 1
+    rt_ = generator.rt
+    if os.environ.get("SGAN_NO_PREFETCH", "0") != "1" and not isinstance(dataset, DevicePrefetcher):
+        dataset = DevicePrefetcher(dataset, rt_)           # H2D of batch i+1 overlaps step i
     header = "disc_loss;disc_loss_real;disc_loss_fake;r_loss_real;r_loss_fake;r_loss_balanced;g_loss;g_lossT;g_lossS;" \
              "g_loss_final;alpha;r_loss_fake_std;g_loss_std;s_loss;s_loss_real;s_loss_fake\n"
     order = ("d_loss", "d_loss_real", "d_loss_fake", "r_loss_real", "r_loss_fake", "r_loss_balanced", "g_loss", "g_loss_added",
@@ -468,6 +472,105 @@ def train(dataset, generator, discriminator, recognizer, style_promoter, composi
             print('Time for epoch {} is {} sec'.format(epoch_idx + 1, time.time() - start))
             generator.save_weights(os.path.join(generator_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))
             recognizer.save_weights(os.path.join(recognizer_save_dir, str(epoch_idx + 1), 'cktp-' + str(epoch_idx + 1)))
+
+# ----------------------------------------------------------------------------------------------------
+# input pipeline: length-bucketed batches staged through pinned memory, H2D copy overlapped with the running step
+# ----------------------------------------------------------------------------------------------------
+class DevicePrefetcher:
+    """Wraps a generator with the interface of the reference's `load_prepare_data` (data_utils.py:14-84: an endless Python
+    generator of (image_batch (B,32,16*len,1) float32, label_batch (B,len) int32), ONE length bucket per batch).  A worker
+    thread pulls batch i+1, stages it in page-locked host memory (a small rotating pool per bucket shape) and copies it to
+    the GPU on its own CUDA stream while step i runs; `next()` makes the compute stream wait on the copy's event and hands
+    out DEVICE tensors, so train_step's own H2D copy disappears from the step.  (torch streams / events are plumbing.)"""
+
+    def __init__(self, dataset, rt: Runtime, depth: int = 2):
+        import queue
+        import threading
+        self.rt, self.depth = rt, max(int(depth), 1)
+        self._src = iter(dataset)
+        self._q = queue.Queue(maxsize=self.depth)
+        self._stream = torch.cuda.Stream(device=rt.device)
+        self._pool = {}
+        self._live = None
+        self._stop = False
+        self._thread = threading.Thread(target=self._work, daemon=True)
+        self._thread.start()
+
+    def _pinned(self, shape, dtype, slot):
+        key = (tuple(shape), dtype, slot)
+        t = self._pool.get(key)
+        if t is None:
+            t = self._pool[key] = torch.empty(shape, dtype=dtype).pin_memory()
+        return t
+
+    def _work(self):
+        torch.cuda.set_device(self.rt.device)
+        slot = 0
+        try:
+            for images, labels in self._src:
+                if self._stop:
+                    return
+                img = _as_tensor(images, np.float32)
+                lab = _as_tensor(labels, np.int32)
+                if img.is_cuda:
+                    self._q.put((img, lab.to(self.rt.device), None))
+                    continue
+                # a pinned staging buffer may only be reused once its previous copy has been consumed: depth + 2 slots
+                ph = self._pinned(img.shape, torch.float32, slot)
+                pl = self._pinned(lab.shape, torch.int32, slot)
+                slot = (slot + 1) % (self.depth + 2)
+                ph.copy_(img)
+                pl.copy_(lab)
+                with torch.cuda.stream(self._stream):
+                    d_img = ph.to(self.rt.device, non_blocking=True)
+                    d_lab = pl.to(self.rt.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._stream)
+                self._q.put((d_img, d_lab, ev))
+        except Exception as ex:      # noqa: BLE001 -- surfaced to the consumer
+            self._q.put(ex)
+        self._q.put(StopIteration())
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self._q.get()
+        if isinstance(item, StopIteration):
+            raise StopIteration
+        if isinstance(item, Exception):
+            raise item
+        d_img, d_lab, ev = item
+        if ev is not None:
+            torch.cuda.current_stream(self.rt.device).wait_event(ev)
+            # the tensors were allocated on the copy stream: tell the caching allocator the compute stream uses them too
+            d_img.record_stream(torch.cuda.current_stream(self.rt.device))
+            d_lab.record_stream(torch.cuda.current_stream(self.rt.device))
+        self._live = (d_img, d_lab)
+        return d_img, d_lab
+
+    def close(self):
+        self._stop = True
+
+
+def synthetic_word_batches_device(rt: Runtime, input_dim, batch_size, char_vector, bucket_size, bucket_weights=None, seed: int = 0):
+    """Device-side synthetic loader with the interface of `load_prepare_data`: the bucket (word length) is drawn on the host
+    from `bucket_weights` -- one bucket per batch, the reference's rule (data_utils.py:64) -- and the images / labels are
+    generated directly in HBM by libsgan's Philox kernel (no host buffer, no H2D copy)."""
+    h, _, c = input_dim
+    rng = np.random.RandomState(seed)
+    p = None
+    if bucket_weights is not None:
+        p = np.asarray(bucket_weights, np.float64)
+        p = p / p.sum()
+    n_chars = len(char_vector)
+    while True:
+        length = int(rng.choice(bucket_size, 1, p=p)[0]) + 1
+        images = ops.random_(rt, rt.empty((batch_size, h, (h // 2) * length, c)), normal=False)
+        u = ops.random_(rt, rt.empty((batch_size, length)), normal=False)
+        labels = ((u + 1.0) * (0.5 * n_chars)).to(torch.int32).clamp_(0, n_chars - 1)      # (label synthesis only: not on the step)
+        yield images, labels
+
 
 # ----------------------------------------------------------------------------------------------------
 # synthetic stand-ins for the reference's data loaders (the IAM dataset is not available here)

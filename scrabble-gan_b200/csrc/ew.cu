@@ -379,6 +379,56 @@ __global__ void k_gap_relu_bwd(const float* __restrict__ dfeat, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------------
+// counter-based random numbers (K21): Philox4x32-10 keyed by `seed`, one 128-bit counter value per group of four outputs;
+// uniform in [-1, 1) or standard normal (Box-Muller).  Replaces tf.random.normal of data_utils.py:385 (the latent z) without
+// a torch op on the step; the stream position lives in DEVICE memory so that a CUDA-graph replay draws fresh numbers.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+__global__ void k_philox(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                         const unsigned long long* __restrict__ offset_dev, int normal) {
+  const unsigned long long base = offset + (offset_dev ? *offset_dev : 0ull);
+  const long long groups = (n + 3) / 4, stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const unsigned long long ctr = base + (unsigned long long)g;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    float v[4];
+    if (normal) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;      // (0, 1]
+        const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;           // [0, 1)
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        v[2 * h] = rad * cs;
+        v[2 * h + 1] = rad * sn;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (float)r[j] * 4.656612873077393e-10f - 1.0f;  // [-1, 1)
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * g + j < n) out[4 * g + j] = v[j];
+  }
+}
+__global__ void k_philox_advance(unsigned long long* offset_dev, unsigned long long by) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *offset_dev += by;
+}
+
 extern "C" {
 
 int sg_act_prep(sg_ctx* ctx, const float* x, long long n, void* relu_out, void* copy_out, int out_dt) {
@@ -582,6 +632,24 @@ int sg_gap_relu_bwd(sg_ctx* ctx, const float* dfeat, const float* x, int n, long
   if (total == 0) return SG_OK;
   k_gap_relu_bwd<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(dfeat, x, hw, c, total, dx);
   SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+
+/* out[n] ~ U[-1, 1) (normal = 0) or N(0, 1) (normal = 1) from the Philox stream (seed, offset + *offset_dev); when offset_dev
+ * is given it is advanced by ceil(n / 4) afterwards (a second, one-thread launch), so a replayed CUDA graph continues the
+ * stream instead of repeating it. */
+int sg_random(sg_ctx* ctx, float* out, long long n, unsigned long long seed, unsigned long long offset,
+              unsigned long long* offset_dev, int normal) {
+  SG_REQUIRE(ctx && out && n >= 0, "sg_random: bad args");
+  if (n == 0) return SG_OK;
+  long long groups = (n + 3) / 4;
+  k_philox<<<ew_grid(ctx, groups, 256), 256, 0, ctx->stream>>>(out, n, seed, offset, offset_dev, normal);
+  SG_POST_LAUNCH(ctx);
+  if (offset_dev) {
+    k_philox_advance<<<1, 32, 0, ctx->stream>>>(offset_dev, (unsigned long long)groups);
+    SG_POST_LAUNCH(ctx);
+  }
   return SG_OK;
 }
 

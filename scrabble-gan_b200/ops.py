@@ -473,6 +473,14 @@ def ctc(rt, logits, labels, want_grad=True):
     return loss, grad
 
 
+def random_(rt, out, normal: bool = True, seed: Optional[int] = None):
+    """Fill `out` (fp32) with N(0,1) (or U[-1,1)) numbers from the runtime's Philox stream; the stream position lives on the
+    device (rt.rng_state), so the launch can be captured in a CUDA graph and still draw fresh numbers on every replay."""
+    st = rt.rng_state()
+    call.sg_random(rt.ctx, _p(out), out.numel(), rt.rng_seed if seed is None else int(seed), 0, _p(st), int(normal))
+    return out
+
+
 def adam_(rt, w, g, m, v, lr_t, beta1, beta2, eps, mirror=None):
     if mirror is not None:
         call.sg_adam_mirror(rt.ctx, _p(w), _p(g), _p(m), _p(v), _p(mirror), w.numel(), lr_t, beta1, beta2, eps)

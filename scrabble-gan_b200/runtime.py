@@ -46,6 +46,8 @@ class Runtime:
         self.peer = None            # dp.PeerExchange when the NVLink peer-memory path is up
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (they bypass the C ABI's launch counter)
         self._scratch = {}
+        self.rng_seed = int(os.environ.get("SGAN_SEED", "1234")) + 7919 * int(os.environ.get("RANK", "0"))
+        self._rng_state = None      # device-resident Philox stream position (uint64[1])
 
     # ---- precision mode -----------------------------------------------------------------------------
     def set_mode(self, mode: str) -> None:
@@ -80,6 +82,15 @@ class Runtime:
             t = torch.empty(max(nbytes, 1), device=self.device, dtype=torch.uint8)
             self._scratch[key] = t
         return t
+
+    def rng_state(self) -> torch.Tensor:
+        if self._rng_state is None:
+            self._rng_state = torch.zeros(1, device=self.device, dtype=torch.int64)
+        return self._rng_state
+
+    def manual_seed(self, seed: int) -> None:
+        self.rng_seed = int(seed)
+        self.rng_state().zero_()
 
     # ---- misc ---------------------------------------------------------------------------------------
     def sync(self) -> None:
