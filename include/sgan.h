@@ -222,6 +222,12 @@ int sg_nonlocal_proj_bwd(sg_ctx* ctx, const float* x, const float* dtheta, const
  * loss[b] = -log p(labels_b | x_b); grad_logits = d loss / d (Dense pre-activations), blank = c-1 */
 int sg_ctc(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, float* loss,
            float* grad_logits);
+/* ragged batch -- K.ctc_batch_cost's own interface (net_architecture.py:57-72 passes per-sample input_length / label_length):
+ * input_len[b] <= t_max frames and label_len[b] <= l_max labels per sample (device int32); logits / labels / grad keep the
+ * rectangular [b, t_max, c] / [b, l_max] layout; frames beyond a sample's length get a zero gradient; a sample without any
+ * valid alignment gets loss = +inf and a zero gradient. */
+int sg_ctc_ragged(sg_ctx* ctx, const float* logits, const int* labels, int b, int t_max, int c, int l_max,
+                  const int* input_len, const int* label_len, float* loss, float* grad_logits);
 
 /* ---- GAN losses + gradient balancing (K16, K17) -- net_loss.py:4-54; data_utils.py:418-442,476-490 --
  * sums is double[SG_LOSS_NSUMS]; all-reduce it across replicas between the two calls. */

@@ -301,8 +301,11 @@ class Recognizer(_Model):
             rt.allreduce_small_(ab)
         return ops.bn_bwd_apply(rt, dy, None, x, mean, rstd, bn.gamma.data, False, ab, count, training, True, out_dt)
 
-    def forward(self, rt, x, labels, want_grad: bool = True):
-        """x (n,32,W,1) fp32, labels (n,L) int32 -> CTC loss (n,) plus a cache for backward."""
+    def forward(self, rt, x, labels, want_grad: bool = True, input_length=None, label_length=None):
+        """x (n,32,W,1) fp32, labels (n,L) int32 -> CTC loss (n,) plus a cache for backward.  input_length / label_length
+        (n,) int32: a RAGGED batch exactly as the reference model takes one (its inputs are [images, labels, input_length,
+        label_length], net_architecture.py:66-75): words of different lengths padded to a common width, every sample's CTC
+        recursion over its own 4*len-1 frames and len labels."""
         T = rt.op_dt
         cv = self.convs
         a1 = cv[0].forward(rt, x, relu=True, out_dt=T)
@@ -320,7 +323,7 @@ class Recognizer(_Model):
         a7 = cv[6].forward(rt, p6, relu=True, out_dt=SG_F32)           # (n, 1, W/4-1, 512)
         n, _, t, c = a7.shape
         logits = self.dense.forward(rt, a7, n * t).view(n, t, self.output_classes)
-        loss, glogits = ops.ctc(rt, logits, labels, want_grad)
+        loss, glogits = ops.ctc(rt, logits, labels, want_grad, input_length, label_length)
         cache = (x, a1, p1, a2, p2, a3, a4, p4, a5, b5, bc5, a6, b6, bc6, p6, a7, glogits)
         return loss, cache
 
@@ -380,10 +383,14 @@ class Recognizer(_Model):
         return cv[0].dgrad(rt, d1, (x.shape[1], x.shape[2]))
 
     def __call__(self, inputs, training=True):
-        imgs, labels = inputs[0], inputs[1]          # input_length / label_length are implied: T = W/4 - 1, L = labels.shape[1]
+        imgs, labels = inputs[0], inputs[1]
         x = _nhwc(to_device_f32(self.rt, imgs))
         y = to_device_i32(self.rt, labels)
-        loss, _ = self.forward(self.rt, x, y, want_grad=False)
+        # [images, labels, input_length, label_length] as in the reference; with two inputs the lengths are implied
+        # (T = W/4 - 1, L = labels.shape[1])
+        il = to_device_i32(self.rt, inputs[2]).reshape(-1) if len(inputs) > 2 and inputs[2] is not None else None
+        ll = to_device_i32(self.rt, inputs[3]).reshape(-1) if len(inputs) > 3 and inputs[3] is not None else None
+        loss, _ = self.forward(self.rt, x, y, want_grad=False, input_length=il, label_length=ll)
         return loss.view(-1, 1)
 
 

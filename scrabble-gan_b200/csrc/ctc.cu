@@ -25,23 +25,30 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 }
 
 // dynamic smem: logq[T*C] | alpha[T*S] | beta[T*S] | occ[C] | ext[S] (int)
-__global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ labels, int T, int C, int L,
-                      float* __restrict__ loss, float* __restrict__ grad) {
+// Ragged batches (K.ctc_batch_cost's own interface: per-sample input_length / label_length, net_architecture.py:57-72):
+// input_len / label_len, when given, hold every sample's frame count T_b <= Tmax and label count L_b <= Lmax; logits / labels
+// / grad keep the rectangular [b, Tmax, C] / [b, Lmax] layout, frames t >= T_b get a zero gradient.
+__global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ labels, int Tmax, int C, int Lmax,
+                      const int* __restrict__ input_len, const int* __restrict__ label_len, float* __restrict__ loss,
+                      float* __restrict__ grad) {
   extern __shared__ float sm[];
-  const int S = 2 * L + 1;
+  const int b = blockIdx.x;
+  int T = input_len ? input_len[b] : Tmax, L = label_len ? label_len[b] : Lmax;
+  T = T < 1 ? 1 : (T > Tmax ? Tmax : T);
+  L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
+  const int S = 2 * L + 1, Smax = 2 * Lmax + 1;
   float* logq = sm;
-  float* alpha = logq + T * C;
-  float* beta = alpha + T * S;
-  float* occ = beta + T * S;
+  float* alpha = logq + Tmax * C;
+  float* beta = alpha + Tmax * Smax;
+  float* occ = beta + Tmax * Smax;
   int* ext = reinterpret_cast<int*>(occ + C);
   __shared__ float s_logp;
 
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int blank = C - 1;
-  const float* z = logits + (long long)b * T * C;
+  const float* z = logits + (long long)b * Tmax * C;
 
-  for (int s = tid; s < S; s += blockDim.x) ext[s] = (s & 1) ? labels[b * L + (s >> 1)] : blank;
+  for (int s = tid; s < S; s += blockDim.x) ext[s] = (s & 1) ? labels[b * Lmax + (s >> 1)] : blank;
 
   // per-frame effective log-probabilities: one warp per frame
   const float log_norm = logf(1.f + (float)C * CTC_EPS);
@@ -100,7 +107,12 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
   __syncthreads();
   if (!grad) return;
   const float logp = s_logp;
-  float* gz = grad + (long long)b * T * C;
+  float* gz = grad + (long long)b * Tmax * C;
+  for (int i = T * C + tid; i < Tmax * C; i += blockDim.x) gz[i] = 0.f;      // frames beyond this sample's length
+  if (logp == NEG_INF) {                                                    // no valid alignment (T_b too short): loss = +inf
+    for (int i = tid; i < T * C; i += blockDim.x) gz[i] = 0.f;
+    return;
+  }
 
   // gradient, frame by frame (block-cooperative: occupancy scatter, then a block reduction for the softmax chain)
   __shared__ float red[32];
@@ -140,17 +152,29 @@ __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ 
   }
 }
 
-extern "C" int sg_ctc(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, float* loss,
-                      float* grad_logits) {
-  SG_REQUIRE(ctx && logits && labels && loss, "sg_ctc: NULL");
-  SG_REQUIRE(b >= 0 && t > 0 && c > 1 && l >= 0, "sg_ctc: bad sizes");
-  SG_REQUIRE(t >= l, "sg_ctc: %d frames cannot emit %d labels", t, l);
+static int ctc_launch(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, const int* input_len,
+                      const int* label_len, float* loss, float* grad_logits, const char* who) {
+  SG_REQUIRE(ctx && logits && labels && loss, "%s: NULL", who);
+  SG_REQUIRE(b >= 0 && t > 0 && c > 1 && l >= 0, "%s: bad sizes", who);
+  SG_REQUIRE(input_len || label_len || t >= l, "%s: %d frames cannot emit %d labels", who, t, l);
   if (b == 0) return SG_OK;
   int S = 2 * l + 1;
   size_t smem = sizeof(float) * ((size_t)t * c + 2 * (size_t)t * S + c) + sizeof(int) * S;
-  SG_REQUIRE(smem <= 200 * 1024, "sg_ctc: T*C too large for shared memory (%zu bytes)", smem);
+  SG_REQUIRE(smem <= 200 * 1024, "%s: T*C too large for shared memory (%zu bytes)", who, smem);
   if (smem > 48 * 1024) SG_CHECK_CUDA(cudaFuncSetAttribute(k_ctc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ctc<<<b, 128, smem, ctx->stream>>>(logits, labels, t, c, l, loss, grad_logits);
+  k_ctc<<<b, 128, smem, ctx->stream>>>(logits, labels, t, c, l, input_len, label_len, loss, grad_logits);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
+}
+
+extern "C" int sg_ctc(sg_ctx* ctx, const float* logits, const int* labels, int b, int t, int c, int l, float* loss,
+                      float* grad_logits) {
+  return ctc_launch(ctx, logits, labels, b, t, c, l, nullptr, nullptr, loss, grad_logits, "sg_ctc");
+}
+
+/* ragged batch: per-sample frame counts input_len[b] <= t_max and label counts label_len[b] <= l_max (device int32) */
+extern "C" int sg_ctc_ragged(sg_ctx* ctx, const float* logits, const int* labels, int b, int t_max, int c, int l_max,
+                             const int* input_len, const int* label_len, float* loss, float* grad_logits) {
+  SG_REQUIRE(input_len && label_len, "sg_ctc_ragged: NULL length arrays");
+  return ctc_launch(ctx, logits, labels, b, t_max, c, l_max, input_len, label_len, loss, grad_logits, "sg_ctc_ragged");
 }

@@ -464,12 +464,18 @@ def nonlocal_proj_bwd(rt, x, dtheta, dphi_f, dg_f, w_theta, w_phi, w_g, dx, dw_t
     return dx
 
 
-def ctc(rt, logits, labels, want_grad=True):
+def ctc(rt, logits, labels, want_grad=True, input_length=None, label_length=None):
+    """K.ctc_batch_cost: per-sample (B,) int32 device tensors input_length / label_length make the batch ragged."""
     b, t, c = logits.shape
     l = labels.shape[1]
     loss = rt.empty((b,), SG_F32)
     grad = rt.empty(logits.shape, SG_F32) if want_grad else None
-    call.sg_ctc(rt.ctx, _p(logits), _p(labels), b, t, c, l, _p(loss), _p(grad))
+    if input_length is None and label_length is None:
+        call.sg_ctc(rt.ctx, _p(logits), _p(labels), b, t, c, l, _p(loss), _p(grad))
+    else:
+        il = input_length if input_length is not None else torch.full((b,), t, device=rt.device, dtype=torch.int32)
+        ll = label_length if label_length is not None else torch.full((b,), l, device=rt.device, dtype=torch.int32)
+        call.sg_ctc_ragged(rt.ctx, _p(logits), _p(labels), b, t, c, l, _p(il), _p(ll), _p(loss), _p(grad))
     return loss, grad
 
 
