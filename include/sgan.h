@@ -98,6 +98,12 @@ int sg_conv_fwd_tc_direct(sg_ctx* ctx, const sg_conv_desc* d, const void* in, co
 size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms);
 int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master,
                      void* workspace, size_t workspace_bytes);
+/* the same launch also producing the layer's BIAS gradient (BiasAddGrad of resnet_ops.py:65,98,103 / net_architecture.py:28-49):
+ * db[c_out] (and db2 when not NULL: the bias of the block's shortcut conv, which sees the same upstream gradient) += column
+ * sums of dy, computed on the tensor cores as dy^T . 1 by extra units that reuse the dy tiles.  Plain Conv2D filter
+ * gradients only (the pixel grid must cover dy exactly once). */
+int sg_conv_wgrad_tc_bias(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master,
+                          float* db, float* db2);
 
 /* ---- element-wise glue --------------------------------------------------------------------------- */
 /* relu_out = relu(x), copy_out = x, both cast to out_dt (either may be NULL).  resnet_ops.py:97,101 */

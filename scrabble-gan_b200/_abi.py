@@ -66,6 +66,7 @@ _PROTOS = {
     "sg_conv_fwd_tc_direct": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_wgrad_tc_workspace": (_Z, [_DP, _I]),
     "sg_conv_wgrad_tc": (_I, [_P, _DP, _P, _P, _P, _P, _Z]),
+    "sg_conv_wgrad_tc_bias": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_act_prep": (_I, [_P, _P, _L, _P, _P, _I]),
     "sg_mask_mul": (_I, [_P, _P, _P, _I, _P, _I, _L, _I]),
     "sg_axpby": (_I, [_P, _F, _P, _F, _P, _P, _L]),

@@ -430,6 +430,9 @@ struct alignas(64) TcWgradParams {
   uint32_t chunk_bytes, stage_stride;
   float* dw;
   unsigned int* sems;           // one semaphore / ticket per (tap, co tile, ci tile)
+  float* db;                    // optional bias gradient [c_out] += column sums of dy (extra "bias units", see the kernel); db2: a second
+  float* db2;                   //   bias that sees the same upstream gradient (the block's shortcut conv)
+  float* bias_partial;          // [co_tiles][splits][128] partial column sums when splits > 1
   float* partial;               // det_mode 2: per-(tile, split) partial tiles [128][BN] fp32
   int det_mode;                 // how the pixel splits of a filter tile are combined (always in split order: bitwise repeatable)
                                 //   0: one split, added straight into dw   1: ordered turns (<= 4 splits)
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -468,6 +472,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     tma_prefetch_desc(&p.map_dy);
     for (int v = 0; v < 4; ++v) tma_prefetch_desc(&p.map_in[v]);
   }
+  if (p.db) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * p.stage_stride);
+    const uint32_t one = kTf32 ? 0x3F800000u : 0x3F803F80u;
+    for (int i = threadIdx.x; i < p.TW * p.TH * p.TN * 32; i += TC_THREADS) ones[i] = one;
+    fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core's async proxy
+  }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -475,8 +485,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   const uint32_t tmem_base = tmem_slot;
 
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int units = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+  const int units_w = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+  // Bias units (p.db != NULL): the bias gradient of the layer is the column sum of dy, i.e. dy^T . 1 -- one more
+  // accumulation of the SAME A tiles against a constant all-ones B tile of 16 columns.  They are appended to the unit list
+  // as (co tile, pixel split) units that load only A and issue N = 16 MMAs: the separate column-sum launch over dy goes away.
+  const int units = units_w + (p.db ? p.co_tiles * p.splits : 0);
   const int PR = p.TW * p.TH * p.TN;
+  const uint32_t ones_addr = smem_base + p.stages * p.stage_stride;      // PR x 128 bytes of 1.0 (layout-agnostic: all equal)
 
   // unit -> (ci tile fastest, co tile, tap, pixel split slowest): the CTAs of one wave work on the SAME pixel range with
   // different (tap, co, ci) tiles, so every dy / input tile is fetched from HBM once and shared through L2
@@ -486,35 +501,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       uint32_t ph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int base_units = p.ntaps * p.co_tiles * p.ci_tiles;
-        int sp = u / base_units, r = u % base_units;
-        int cit = r % p.ci_tiles; r /= p.ci_tiles;
-        int cot = r % p.co_tiles;
-        int t = r / p.co_tiles;
+        const bool bias_u = u >= units_w;
+        int sp, cit = 0, cot, t = 0;
+        if (bias_u) {
+          cot = (u - units_w) % p.co_tiles;
+          sp = (u - units_w) / p.co_tiles;
+        } else {
+          int r = u % base_units;
+          sp = u / base_units;
+          cit = r % p.ci_tiles; r /= p.ci_tiles;
+          cot = r % p.co_tiles;
+          t = r / p.co_tiles;
+        }
         int pt0 = sp * p.ptiles_per_split, pt1 = pt0 + p.ptiles_per_split;
         if (pt1 > ptiles) pt1 = ptiles;
         const CUtensorMap* mi = &p.map_in[p.tap_view[t]];
+        const int nb = bias_u ? 0 : p.b_chunks;
         for (int pt = pt0; pt < pt1; ++pt) {
           int tx = pt % p.tiles_x, q = pt / p.tiles_x;
           int ty = q % p.tiles_y, tn = q / p.tiles_y;
           int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, (p.a_chunks + p.b_chunks) * p.chunk_bytes);
+          mbar_expect_tx(bar_full + 8 * s, (p.a_chunks + nb) * p.chunk_bytes);
           uint32_t dst = smem_base + s * p.stage_stride;
           for (int j = 0; j < p.a_chunks; ++j)
             tma_load_4d(dst + j * p.chunk_bytes, &p.map_dy, bar_full + 8 * s, cot * 128 + j * KC, x0, y0, n0);
           dst += p.a_chunks * p.chunk_bytes;
-          for (int j = 0; j < p.b_chunks; ++j)
+          for (int j = 0; j < nb; ++j)
             tma_load_4d(dst + j * p.chunk_bytes, mi, bar_full + 8 * s, cit * p.BN + j * KC, x0 + p.tap_ox[t], y0 + p.tap_oy[t], n0);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(kTf32, true, true, 128, p.BN);
+    const uint32_t idesc_w = make_idesc(kTf32, true, true, 128, p.BN), idesc_b = make_idesc(kTf32, true, true, 128, 16);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int sp = u / (p.ntaps * p.co_tiles * p.ci_tiles);
+      const bool bias_u = u >= units_w;
+      const uint32_t idesc = bias_u ? idesc_b : idesc_w;
+      int sp = bias_u ? (u - units_w) / p.co_tiles : u / (p.ntaps * p.co_tiles * p.ci_tiles);
       int pt0 = sp * p.ptiles_per_split, pt1 = pt0 + p.ptiles_per_split;
       if (pt1 > ptiles) pt1 = ptiles;
       mbar_wait(bar_tempty + 8 * as, aph ^ 1);
@@ -530,7 +556,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
           // along the pixel (K) axis: 8 pixel rows = 1024 B with 16-byte atoms (bf16); tf32 MN-major operands must use the
           // 32-byte-atom variant of the 128B swizzle (TMA: SWIZZLE_128B_ATOM_32B), whose pattern repeats every 4 rows = 512 B
           uint64_t da = make_smem_desc(a_addr, p.chunk_bytes, kTf32 ? 512 : 1024, kTf32 ? 1 : 2);
-          uint64_t db = make_smem_desc(b_addr, p.chunk_bytes, kTf32 ? 512 : 1024, kTf32 ? 1 : 2);
+          uint64_t db = make_smem_desc(bias_u ? ones_addr : b_addr, p.chunk_bytes, kTf32 ? 512 : 1024, kTf32 ? 1 : 2);
           const int ksteps = PR / UK;
           const uint32_t kadv = (UK * 128) >> 4;
           for (int k = 0; k < ksteps; ++k)
@@ -551,6 +577,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     uint32_t aph = 0;
     const int base_units = p.ntaps * p.co_tiles * p.ci_tiles;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      if (u >= units_w) {
+        // ---- bias unit: column 0 of the 16-column accumulator = sum over this split's pixels of dy[:, co] ----
+        const int cot_b = (u - units_w) % p.co_tiles, sp_b = (u - units_w) / p.co_tiles;
+        const int co_b = cot_b * 128 + row;
+        mbar_wait(bar_tfull + 8 * as, aph);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u, v);
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * as);
+        const float part = __uint_as_float(v[0]);
+        if (p.splits == 1) {
+          if (co_b < p.c_out) {
+            atomicAdd(p.db + co_b, part);
+            if (p.db2) atomicAdd(p.db2 + co_b, part);
+          }
+        } else {
+          // partial sums of the splits in scratch, added in split order by the split that arrives last (common.cuh scheme B)
+          float* slots = p.bias_partial + (long long)cot_b * p.splits * 128;
+          __stcg(slots + sp_b * 128 + row, part);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            __threadfence();
+            unsigned int tk = atomicAdd(p.sems + base_units + 2 + cot_b, 1u);
+            s_last = (tk == (unsigned int)p.splits - 1) ? 1u : 0u;
+            if (s_last) { p.sems[base_units + 2 + cot_b] = 0u; __threadfence(); }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (s_last && co_b < p.c_out) {
+            float tot = 0.f;
+            for (int s2 = 0; s2 < p.splits; ++s2) tot += __ldcg(slots + s2 * 128 + row);
+            atomicAdd(p.db + co_b, tot);
+            if (p.db2) atomicAdd(p.db2 + co_b, tot);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+        continue;
+      }
       const int tile = u % base_units, sp = u / base_units;
       int r = tile;
       int cit = r % p.ci_tiles; r /= p.ci_tiles;
@@ -1067,9 +1133,24 @@ size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms) {
   return 0;      // split partials are added straight into dw in split order (turn semaphores in the context): no workspace
 }
 
+static int conv_wgrad_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, float* db, float* db2);
+
 int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, void* workspace,
                      size_t workspace_bytes) {
   (void)workspace; (void)workspace_bytes;
+  return conv_wgrad_tc_impl(ctx, d, in, dy, dw_master, nullptr, nullptr);
+}
+
+/* filter gradient + bias gradient in ONE launch: db[c_out] (and db2, the bias of a shortcut conv that sees the same upstream
+ * gradient; may be NULL) += column sums of dy, computed by the tensor cores as dy^T . 1 */
+int sg_conv_wgrad_tc_bias(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, float* db, float* db2) {
+  SG_REQUIRE(db != nullptr, "sg_conv_wgrad_tc_bias: NULL bias gradient");
+  SG_REQUIRE(d && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0 && d->grid_h == d->out_h && d->grid_w == d->out_w,
+             "sg_conv_wgrad_tc_bias: the pixel grid must cover dy exactly once (plain Conv2D filter gradients only)");
+  return conv_wgrad_tc_impl(ctx, d, in, dy, dw_master, db, db2);
+}
+
+static int conv_wgrad_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, float* db, float* db2) {
   SG_REQUIRE(ctx && in && dy && dw_master, "sg_conv_wgrad_tc: NULL");
   int rc = tc_check(d, "sg_conv_wgrad_tc");
   if (rc != SG_OK) return rc;
@@ -1090,6 +1171,9 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   p.ntaps = d->ntaps; p.c_in = d->c_in; p.c_out = d->c_out;
   p.w_ci_stride = d->w_ci_stride; p.w_co_stride = d->w_co_stride;
   p.dw = dw_master;
+  p.db = db;
+  p.db2 = db2;
+  p.bias_partial = ctx->det_scratch + (SG_DET_SCRATCH_BYTES - (1u << 20)) / sizeof(float);      // last MB of the scratch
   p.sems = ctx->det_tickets;
   p.BN = d->c_in % 256 == 0 ? 256 : (d->c_in % 128 == 0 ? 128 : (d->c_in % 64 == 0 ? 64 : 32));
   p.ci_tiles = d->c_in / p.BN;
@@ -1108,7 +1192,8 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   p.chunk_bytes = (uint32_t)PR * 128u;
   p.stage_stride = (uint32_t)(p.a_chunks + p.b_chunks) * p.chunk_bytes;
   p.stage_stride = (p.stage_stride + 1023u) & ~1023u;
-  int stages = (int)((220u * 1024u) / p.stage_stride);
+  const uint32_t ones_bytes = db ? (uint32_t)PR * 128u : 0u;             // constant all-ones B tile of the bias units
+  int stages = (int)((220u * 1024u - ones_bytes) / p.stage_stride);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SG_REQUIRE(stages >= 2, "sg_conv_wgrad_tc: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -1119,7 +1204,7 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   // count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43 waves)
   int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
   if (max_splits > 32) max_splits = 32;
-  if (base_units + 2 > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
+  if (base_units + 2 + p.co_tiles > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
   int splits = 1;
   double best_eff = -1.0;
   for (int sp = 1; sp <= max_splits; ++sp) {
@@ -1147,7 +1232,7 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
       else if (!strcmp(ov, "scratch")) p.det_mode = 2;
     }
   }
-  if (p.det_mode == 2 && (long long)base_units * p.splits * 128 * p.BN * (long long)sizeof(float) > (long long)SG_DET_SCRATCH_BYTES) {
+  if (p.det_mode == 2 && (long long)base_units * p.splits * 128 * p.BN * (long long)sizeof(float) > (long long)SG_DET_SCRATCH_BYTES - (1 << 20)) {
     // the partial tiles would not fit the context's scratch: fall back to 4 ordered splits
     p.ptiles_per_split = sg_div_up(ptiles, 4);
     p.splits = sg_div_up(ptiles, p.ptiles_per_split);
@@ -1178,9 +1263,9 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
                         d->out_px, KC, p.TW, p.TH, p.TN, swz);
   if (rc != SG_OK) return rc;
 
-  long long units = base_units * p.splits;
+  long long units = base_units * p.splits + (db ? (long long)p.co_tiles * p.splits : 0);
   int grid = (int)(units < ctx->num_sms ? units : ctx->num_sms);
-  size_t smem = (size_t)stages * p.stage_stride + 1024;
+  size_t smem = (size_t)stages * p.stage_stride + 1024 + ones_bytes;
   // det_mode 2 ends in a grid-wide barrier: launched cooperatively, so the runtime guarantees (or refuses) co-residency
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -105,8 +105,10 @@ class ConvLayer:
         same column sums as dy that is cheaper to read (the un-pooled fp32 gradient: avg-pool backward preserves sums)."""
         n, h, w, _ = x.shape
         d = self._desc("fwd", n, h, w, dt_of(x), dt_of(dy))
-        ops.conv_wgrad(rt, d, x, dy, self.w.grad)
-        if bias_grad and self.b is not None:
+        want_b = bias_grad and self.b is not None
+        if ops.conv_wgrad(rt, d, x, dy, self.w.grad, db=self.b.grad if want_b else None, db2=also_bias if want_b else None):
+            return                                        # bias gradient(s) came out of the same tensor-core launch
+        if want_b:
             src = dy if bias_src is None else bias_src
             if also_bias is None:
                 ops.colsum_into(rt, src, self.co, self.b.grad, accumulate=1)

@@ -169,18 +169,24 @@ def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_pac
     call.sg_conv_fwd_tc_dual(rt.ctx, C.byref(d), _p(x), _p(w_packed), C.byref(d2), _p(x2), _p(w_packed2), _p(bias), _p(mask), _p(out))
 
 
-def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False) -> None:
+def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False, db=None, db2=None) -> bool:
     """dw_master += filter gradient of the conv described by d: on the tensor cores whenever the layer is eligible and both
     operands have the mode's operand dtype (bf16, or fp32 read as tf32 in "tf32" mode); the FFMA kernel serves the edge
-    layers (Cin = 1 / Cout = 1) and the exact "fp32" mode -- by rule, not as a silent fallback."""
+    layers (Cin = 1 / Cout = 1) and the exact "fp32" mode -- by rule, not as a silent fallback.
+    db (and db2): bias gradient(s) to accumulate the column sums of dy into IN THE SAME LAUNCH; returns True when that was
+    done (tensor-core path of a plain Conv2D), False when the caller still has to sum dy itself."""
     tc_dt = SG_BF16 if rt.mode == "bf16" else (SG_F32 if (rt.mode == "tf32" and rt.tf32_wgrad_tc) else None)
     if not force_simt and tc_dt is not None and d.in_dt == tc_dt and d.out_dt == tc_dt and tc_ok(rt, d):
+        if db is not None and rt.fuse_bias_grad and d.out_sy == 1 and d.out_sx == 1 and d.grid_h == d.out_h and d.grid_w == d.out_w:
+            call.sg_conv_wgrad_tc_bias(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _p(db), _p(db2))
+            return True
         call.sg_conv_wgrad_tc(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _V(None), 0)
     else:
         if rt.use_tc and tc_ok(rt, d) and not force_simt and d.in_dt != d.out_dt:
             raise _abi.SganError("conv_wgrad: tensor-core layer with mixed operand dtypes (in {}, dy {}): the producer must write the "
                                  "operand dtype".format(d.in_dt, d.out_dt))
         call.sg_conv_wgrad_simt(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master))
+    return False
 
 
 # ----------------------------------------------------------------------------------------------------

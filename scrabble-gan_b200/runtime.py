@@ -64,6 +64,8 @@ class Runtime:
         self.merge_r_backward = os.environ.get("SGAN_NO_MERGED_R_BWD", "0") != "1"
         # "tf32" mode: filter gradients on the tensor cores too (fp32 operands read as tf32, MN-major 32-byte-atom swizzle)
         self.tf32_wgrad_tc = os.environ.get("SGAN_TF32_WGRAD_SIMT", "0") != "1"
+        # bias gradients of tensor-core convs come out of the filter-gradient launch (dy^T . 1 on the tensor cores)
+        self.fuse_bias_grad = os.environ.get("SGAN_NO_FUSED_BIAS_GRAD", "0") != "1"
         call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
