@@ -39,6 +39,8 @@ int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out);
 int sg_ctx_destroy(sg_ctx* ctx);
 int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
 int sg_ctx_sync(sg_ctx* ctx);
+/* zero `bytes` of device memory on the context's stream (cudaMemsetAsync: no kernel launch) */
+int sg_zero(sg_ctx* ctx, void* ptr, size_t bytes);
 long long sg_ctx_launch_count(sg_ctx* ctx);      /* kernels launched through this context so far */
 /* speed mode (bf16 runs): the fp32 1x1 projections of the non-local block take their products on bf16 warp-level tensor
  * ops (fp32 accumulate) instead of exact FFMA; off by default */
@@ -82,6 +84,11 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
 int sg_conv_tc_supported(const sg_conv_desc* d);
 size_t sg_conv_packed_weight_elems(const sg_conv_desc* d);     /* c_out * ntaps * c_in */
 int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_master, void* w_packed);
+/* several packing jobs (<= 32: e.g. all forward filters of a network after an optimizer step) in ONE launch; descs / w_master /
+ * w_packed are HOST arrays of length njobs; sg_conv_pack_multi_supported says whether a filter qualifies. */
+int sg_conv_pack_multi_supported(const sg_conv_desc* d, const float* w_master);
+int sg_conv_pack_weights_multi(sg_ctx* ctx, int njobs, const sg_conv_desc* const* descs, const float* const* w_master,
+                               void* const* w_packed);
 int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
                    const float* bias, const void* mask, void* out);
 /* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the shortcut of a ResNet block
@@ -104,6 +111,9 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
  * gradients only (the pixel grid must cover dy exactly once). */
 int sg_conv_wgrad_tc_bias(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master,
                           float* db, float* db2);
+/* 1 when those extra units fit into the idle CTA slots of the launch's last wave (the bias gradient is then free), 0 when
+ * they would open another wave (a separate column sum is faster: use sg_colsum). */
+int sg_conv_wgrad_tc_bias_fits(sg_ctx* ctx, const sg_conv_desc* d);
 
 /* ---- element-wise glue --------------------------------------------------------------------------- */
 /* relu_out = relu(x), copy_out = x, both cast to out_dt (either may be NULL).  resnet_ops.py:97,101 */
@@ -284,6 +294,15 @@ int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, fl
 /* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */
 int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
                      float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
+
+/* ---- grouped conditional-batch-norm Dense layers (resnet_ops.py:18-26: gamma / beta = Dense(32 -> C, no bias)(z_block)) -----
+ * ONE launch for all segments i < nseg (<= 16): out[n, sum c] = concat_i( z[:, z_off[i] : z_off[i] + 32] @ W_i ), W_i the (32, c[i])
+ * kernel at w_base + w_off[i]; and one launch for all their filter gradients dW_i += z_slice^T @ upstream[i] ((n, c[i]) each).
+ * c / z_off / w_off / upstream are HOST arrays of length nseg. */
+int sg_cbn_dense_fwd(sg_ctx* ctx, const float* z, int z_stride, int n, int nseg, const int* c, const int* z_off,
+                     const long long* w_off, const float* w_base, float* out);
+int sg_cbn_dense_wgrad(sg_ctx* ctx, const float* z, int z_stride, int n, int nseg, const int* c, const int* z_off,
+                       const long long* w_off, const float* const* upstream, float* dw_base);
 
 /* ---- counter-based random numbers (K21; replaces tf.random.normal of data_utils.py:385) -- Philox4x32-10.  out[n] ~ U[-1,1)
  * (normal = 0) or N(0,1) (normal = 1, Box-Muller) at stream position offset + *offset_dev (offset_dev may be NULL); a given

@@ -51,6 +51,7 @@ _PROTOS = {
     "sg_ctx_set_stream": (_I, [_P, _P]),
     "sg_ctx_sync": (_I, [_P]),
     "sg_ctx_launch_count": (_L, [_P]),
+    "sg_zero": (_I, [_P, _P, _Z]),
     "sg_ctx_set_speed_mode": (_I, [_P, _I]),
     "sg_sizeof_conv_desc": (_I, []),
     "sg_crc32c": (C.c_uint, [_P, _Z, C.c_uint]),
@@ -60,6 +61,8 @@ _PROTOS = {
     "sg_conv_tc_supported": (_I, [_DP]),
     "sg_conv_packed_weight_elems": (_Z, [_DP]),
     "sg_conv_pack_weights": (_I, [_P, _DP, _P, _P]),
+    "sg_conv_pack_multi_supported": (_I, [_DP, _P]),
+    "sg_conv_pack_weights_multi": (_I, [_P, _I, C.POINTER(_DP), C.POINTER(_P), C.POINTER(_P)]),
     "sg_conv_fwd_tc": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_fwd_tc_dual": (_I, [_P, _DP, _P, _P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_tc_direct_supported": (_I, [_DP]),
@@ -67,6 +70,7 @@ _PROTOS = {
     "sg_conv_wgrad_tc_workspace": (_Z, [_DP, _I]),
     "sg_conv_wgrad_tc": (_I, [_P, _DP, _P, _P, _P, _P, _Z]),
     "sg_conv_wgrad_tc_bias": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
+    "sg_conv_wgrad_tc_bias_fits": (_I, [_P, _DP]),
     "sg_act_prep": (_I, [_P, _P, _L, _P, _P, _I]),
     "sg_mask_mul": (_I, [_P, _P, _P, _I, _P, _I, _L, _I]),
     "sg_axpby": (_I, [_P, _F, _P, _F, _P, _P, _L]),
@@ -97,6 +101,8 @@ _PROTOS = {
     "sg_bn_stats_partial": (_I, [_P, _P, _L, _I, _P, _Z, C.POINTER(_I)]),
     "sg_bn_finalize_peer": (_I, [_P, _P, _I, _I, _D, _F, _F, _P, _P, _P, _P, _P, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_gemm": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I]),
+    "sg_cbn_dense_fwd": (_I, [_P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _P, _P]),
+    "sg_cbn_dense_wgrad": (_I, [_P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), C.POINTER(_P), _P]),
     "sg_filterbank_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
     "sg_filterbank_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I]),
     "sg_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),

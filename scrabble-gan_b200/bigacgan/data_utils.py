@@ -187,6 +187,10 @@ def _capture(rt, gs, args, b, l_r, l_f, latent_dim):
 
     try:
         for st in stores:
+            # every packed filter must be stale at capture time, so that the packing launches become part of the graph: a
+            # forward pass since the last weight change (e.g. inference between two steps) would have left fresh entries,
+            # the capture would skip the packs and every replay would then read filters from before its own Adam steps
+            st.version += 1
             if rt.mode == "bf16" and rt.use_direct:
                 st.mirror(rt)                                   # fresh mirrors: no cast gets captured
         # optimizer state must exist BEFORE the capture: created inside it, the (m, v) slots would live in the graph's
@@ -287,6 +291,8 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     for m in nets:
         m.store.zero_grad()
         m.sn_forward(rt, update_u=True)             # apply_sn: refresh W / sigma(W) (one power-iteration step, persistent u)
+        if rt.use_tc and rt.batch_packs:
+            m.prepack(rt)                           # all forward filters of the network that the last Adam step made stale: one launch
 
     # ---- forward passes (data_utils.py:398-415) -------------------------------------------------------------------
     if fused:

@@ -101,6 +101,37 @@ class _Model:
         self.apply_sn = True
         return self.store.enable_spectral_norm(names, seed)
 
+    def conv_layers(self):
+        """Every ConvLayer / ConvTransposeLayer of the model (found by walking its attributes once)."""
+        if getattr(self, "_conv_cache", None) is None:
+            from ..layers import ConvLayer, ConvTransposeLayer
+            found, seen = [], set()
+
+            def walk(o, depth=0):
+                if id(o) in seen or depth > 6:
+                    return
+                seen.add(id(o))
+                if isinstance(o, (ConvLayer, ConvTransposeLayer)):
+                    found.append(o)
+                    return
+                if isinstance(o, (list, tuple)):
+                    for x in o:
+                        walk(x, depth + 1)
+                elif isinstance(o, dict):
+                    for x in o.values():
+                        walk(x, depth + 1)
+                elif hasattr(o, "__dict__") and type(o).__module__.startswith("scrabble-gan_b200") and not isinstance(o, (ParamStore, Runtime)):
+                    for x in vars(o).values():
+                        walk(x, depth + 1)
+            walk(self)
+            self._conv_cache = found
+        return self._conv_cache
+
+    def prepack(self, rt) -> int:
+        """After an optimizer step: re-pack all stale tensor-core filters of this model in one launch (layers.prepack)."""
+        from ..layers import prepack
+        return prepack(rt, self.conv_layers())
+
     def sn_forward(self, rt, update_u: bool) -> None:
         if self.apply_sn:
             self.store.sn.forward(rt, update_u)
@@ -439,10 +470,23 @@ class Generator(_Model):
             z = z_or_imgs
         zs = self.latent_dim
         net, ec = self.embed.forward(rt, z, zs, y)
+        # all 12 CBN gamma / beta Dense layers (resnet_ops.py:18-26) in ONE launch: [n, sum of 2 C] with per-layer column blocks
+        gb = None
+        if rt.group_cbn_dense:
+            segs = self._cbn_segments()
+            gb_all = ops.cbn_dense_fwd(rt, z, zs, z.shape[0], [s[:3] for s in segs], self._cbn_wbase())
+            gb, col = [], 0
+            for c_, _, _, _ in segs:
+                gb.append(gb_all[:, col:])
+                col += c_
+            gb_stride = gb_all.shape[1]
         caches = []
         for i, blk in enumerate(self.blocks):
             zi = z[:, self.zchunk * (i + 1):]
-            net, c = blk.forward(rt, net, zi, zs, training)
+            kw = {}
+            if gb is not None:
+                kw = {"gb1": (gb[4 * i], gb[4 * i + 1], gb_stride), "gb2": (gb[4 * i + 2], gb[4 * i + 3], gb_stride)}
+            net, c = blk.forward(rt, net, zi, zs, training, **kw)
             ca = None
             if i in self.attn:
                 net, ca = self.attn[i].forward(rt, net)
@@ -474,16 +518,39 @@ class Generator(_Model):
             rt.allreduce_small_(ab)
         d = ops.bn_bwd_apply(rt, dact, act, net, mean, rstd, self.bn.gamma.data, False, ab, count, training, False, SG_F32)
         dz = rt.zeros((n, self.latent_dim)) if want_dz else None
+        defer = [] if rt.group_cbn_dense else None
         for i in reversed(range(self.num_blocks)):
             c, ca = caches[i]
             if ca is not None:
                 d = self.attn[i].backward(rt, ca, d, True)
-            d = self.blocks[i].backward(rt, c, d, dz[:, self.zchunk * (i + 1):] if want_dz else None, self.latent_dim)
+            d = self.blocks[i].backward(rt, c, d, dz[:, self.zchunk * (i + 1):] if want_dz else None, self.latent_dim, defer=defer)
+        if defer:
+            # the 12 Dense filter gradients dW = z_block^T @ (d gamma | d beta) in ONE launch
+            by_layer = {id(cbn): (s1, s2) for cbn, s1, s2 in defer}
+            segs, ups = [], []
+            for (c_, zoff, woff, (cbn, which)) in self._cbn_segments(grad=True):
+                s1, s2 = by_layer[id(cbn)]
+                segs.append((c_, zoff, woff))
+                ups.append(s2 if which == "gamma" else s1)
+            ops.cbn_dense_wgrad(rt, z, self.latent_dim, n, segs, ups, self.store.g)
         self.embed.backward(rt, ec, d, dz, self.latent_dim)
         if want_dz:
             feats, tc = sc
             dfeats = self.style_dense.backward(rt, feats, dz, n, want_dx=True, wgrad=True)
             self.style.backward(rt, tc, dfeats, True, False)
+
+    def _cbn_segments(self, grad: bool = False):
+        """(C, column offset of the block's z slice, offset of the Dense kernel in the flat store, (layer, which)) for the
+        12 gamma / beta Dense layers, in the order B1.cbn1.gamma, B1.cbn1.beta, B1.cbn2.gamma, ..."""
+        out = []
+        for i, blk in enumerate(self.blocks):
+            for cbn in (blk.cbn1, blk.cbn2):
+                for which, dense in (("gamma", cbn.gamma), ("beta", cbn.beta)):
+                    out.append((cbn.c, self.zchunk * (i + 1), dense.w.offset, (cbn, which)))
+        return out
+
+    def _cbn_wbase(self):
+        return self.store.w if self.store.w_eff is None else self.store.w_eff
 
     def __call__(self, inputs, training=True):
         a, y = inputs[0], inputs[1]

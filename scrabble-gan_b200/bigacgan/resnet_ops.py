@@ -24,32 +24,43 @@ class ConditionalBatchNorm:
         self.beta = DenseLayer(store, name + ".beta", zdim, c)
         self.bn = BatchNormState(store, name, c, affine=False)
 
-    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool, relu: bool, out_dt: int):
+    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool, relu: bool, out_dt: int, gb=None):
+        """gb = (gamma, beta, row stride): views into the grouped Dense output of the whole generator (one launch for all
+        CBN layers, ops.cbn_dense_fwd); without it the two Dense layers are launched here."""
         n = x.shape[0]
         if training:
             mean, rstd, count = batch_stats(rt, x, self.bn)
         else:
             mean, rstd = ops.bn_infer_prepare(rt, self.bn.moving_mean.data, self.bn.moving_var.data)
             count = 1
-        g = self.gamma.forward(rt, z, n, ldx=z_stride)
-        b = self.beta.forward(rt, z, n, ldx=z_stride)
-        y = ops.bn_apply(rt, x, mean, rstd, g, b, True, relu, out_dt)
-        return y, (x, y if relu else None, z, z_stride, mean, rstd, g, count, training)
+        if gb is None:
+            g = self.gamma.forward(rt, z, n, ldx=z_stride)
+            b = self.beta.forward(rt, z, n, ldx=z_stride)
+            gs = None
+        else:
+            g, b, gs = gb
+        y = ops.bn_apply(rt, x, mean, rstd, g, b, True, relu, out_dt, gb_stride=gs)
+        return y, (x, y if relu else None, z, z_stride, mean, rstd, g, count, training, gs)
 
     def backward(self, rt: Runtime, cache, dy, out_dt: int = SG_F32, out=None, accumulate: bool = False, dz_out=None,
-                 dz_ld: int = 0):
-        """dy: gradient w.r.t. the (post-ReLU) output.  Accumulates the Dense weight gradients and, when dz_out is
-        given, adds d/dz into dz_out (row stride dz_ld).  Returns dx."""
-        x, act, z, z_stride, mean, rstd, g, count, training = cache
+                 dz_ld: int = 0, defer=None):
+        """dy: gradient w.r.t. the (post-ReLU) output.  Accumulates the Dense weight gradients -- or, with `defer` (a list),
+        only records (layer, d beta, d gamma) so that the caller computes all of them in one grouped launch -- and, when
+        dz_out is given, adds d/dz into dz_out (row stride dz_ld).  Returns dx."""
+        x, act, z, z_stride, mean, rstd, g, count, training, gs = cache
         n = x.shape[0]
         s1, s2 = ops.bn_bwd_reduce(rt, dy, act, x, mean, rstd)          # s1 = d beta [n,c], s2 = d gamma [n,c]
         ab = None
         if training:
-            ab = ops.bn_bwd_combine(rt, s1, s2, g, True)
+            ab = ops.bn_bwd_combine(rt, s1, s2, g, True, gb_stride=gs)
             rt.allreduce_small_(ab)                                           # sync-BN backward statistics
-        dx = ops.bn_bwd_apply(rt, dy, act, x, mean, rstd, g, True, ab, count, training, False, out_dt, out, int(accumulate))
-        self.gamma.backward(rt, z, s2, n, ldx=z_stride, want_dx=False)
-        self.beta.backward(rt, z, s1, n, ldx=z_stride, want_dx=False)
+        dx = ops.bn_bwd_apply(rt, dy, act, x, mean, rstd, g, True, ab, count, training, False, out_dt, out, int(accumulate),
+                              gb_stride=gs)
+        if defer is not None:
+            defer.append((self, s1, s2))
+        else:
+            self.gamma.backward(rt, z, s2, n, ldx=z_stride, want_dx=False)
+            self.beta.backward(rt, z, s1, n, ldx=z_stride, want_dx=False)
         if dz_out is not None:
             ops.gemm(rt, s2, self.gamma.w.eff, n, self.gamma.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
             ops.gemm(rt, s1, self.beta.w.eff, n, self.beta.cin, self.c, trans_b=True, out=dz_out, ldc=dz_ld, accumulate=1)
@@ -70,27 +81,27 @@ class ResNetBlockUp:
         self.conv = ConvLayer(store, name + ".conv", 3, 3, co, co)
         self.short = ConvTransposeLayer(store, name + ".short", 1, ci, co, self.stride)
 
-    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool):
-        a1, c1 = self.cbn1.forward(rt, x, z, z_stride, training, True, rt.op_dt)
+    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool, gb1=None, gb2=None):
+        a1, c1 = self.cbn1.forward(rt, x, z, z_stride, training, True, rt.op_dt, gb=gb1)
         u = self.up.forward(rt, a1)
-        a2, c2 = self.cbn2.forward(rt, u, z, z_stride, training, True, rt.op_dt)
+        a2, c2 = self.cbn2.forward(rt, u, z, z_stride, training, True, rt.op_dt, gb=gb2)
         bsum = ops.axpby(rt, 1.0, self.conv.b.data, 1.0, self.short.b.data)      # conv bias + shortcut bias (everywhere)
         h = self.conv.forward(rt, a2, bias=bsum)
         xs = ops.cast(rt, x, rt.op_dt)
         self.short.forward(rt, xs, out=h, accumulate=True, bias=None)
         return h, (c1, c2, a1, a2, xs, x.shape)
 
-    def backward(self, rt: Runtime, cache, dh, dz_out=None, dz_ld: int = 0):
+    def backward(self, rt: Runtime, cache, dh, dz_out=None, dz_ld: int = 0, defer=None):
         c1, c2, a1, a2, xs, xshape = cache
         n, hh, ww, _ = xshape
         dh_op = ops.cast(rt, dh, rt.op_dt)
         # main branch, back to front
         self.conv.wgrad(rt, a2, dh_op, also_bias=self.short.b.grad)      # the shortcut bias sees the same upstream gradient
         da2 = self.conv.dgrad(rt, dh_op, (hh * self.stride[0], ww * self.stride[1]))
-        du = self.cbn2.backward(rt, c2, da2, out_dt=rt.op_dt, dz_out=dz_out, dz_ld=dz_ld)
+        du = self.cbn2.backward(rt, c2, da2, out_dt=rt.op_dt, dz_out=dz_out, dz_ld=dz_ld, defer=defer)
         self.up.wgrad(rt, a1, du)
         da1 = self.up.dgrad(rt, du)
-        dx = self.cbn1.backward(rt, c1, da1, out_dt=SG_F32, dz_out=dz_out, dz_ld=dz_ld)
+        dx = self.cbn1.backward(rt, c1, da1, out_dt=SG_F32, dz_out=dz_out, dz_ld=dz_ld, defer=defer)
         # shortcut branch
         self.short.wgrad(rt, xs, dh_op, bias_grad=False)
         self.short.dgrad(rt, dh_op, out=dx, accumulate=True)

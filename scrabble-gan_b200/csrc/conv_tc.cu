@@ -794,6 +794,71 @@ __global__ void __launch_bounds__(256) k_pack_weights_t(sg_conv_desc d, const fl
   }
 }
 
+// Several packing jobs in ONE launch (the forward filters of a whole network after an optimizer step): block b belongs to
+// the job whose tile range contains it.  kind 0: transposing pack of an HWIO filter (k_pack_weights_t's 32 x 32 tiles);
+// kind 1: 8-wide vector copy of a filter whose master layout already has the descriptor's c_in fastest.
+#define PACK_MAX_JOBS 32
+struct PackJob {
+  const float* src;
+  void* dst;
+  long long tap_stride, w_ci_stride, w_co_stride;
+  int c_in, c_out, ntaps, kind, tile0, tiles_ci, tiles_co, dt;
+};
+struct PackJobs {
+  int njobs, total_tiles;
+  PackJob job[PACK_MAX_JOBS];
+};
+template <typename TO>
+__device__ __forceinline__ void pack_tile_t(const PackJob& j, int tile, float (*smt)[33]) {
+  const int tci = tile % j.tiles_ci, r = tile / j.tiles_ci;
+  const int tco = r % j.tiles_co, t = r / j.tiles_co;
+  const int ci0 = tci * 32, co0 = tco * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = j.src + (long long)t * j.tap_stride;
+  TO* out = reinterpret_cast<TO*>(j.dst);
+#pragma unroll
+  for (int q = 0; q < 32; q += 8) {
+    int ci = ci0 + ty + q, co = co0 + tx;
+    smt[ty + q][tx] = (ci < j.c_in && co < j.c_out) ? src[(long long)ci * j.w_ci_stride + co] : 0.f;
+  }
+  __syncthreads();
+  const long long ktot = (long long)j.ntaps * j.c_in;
+#pragma unroll
+  for (int q = 0; q < 32; q += 8) {
+    int co = co0 + ty + q, ci = ci0 + tx;
+    if (ci < j.c_in && co < j.c_out) sg_st(out + (long long)co * ktot + (long long)t * j.c_in + ci, smt[tx][ty + q]);
+  }
+}
+template <typename TO>
+__device__ __forceinline__ void pack_tile_v8(const PackJob& j, int tile) {
+  const int c8 = j.c_in / 8;
+  const long long total8 = (long long)j.c_out * j.ntaps * c8;
+  const long long i = (long long)tile * 256 + threadIdx.x;
+  if (i >= total8) return;
+  const int g = (int)(i % c8);
+  const long long r = i / c8;
+  const int t = (int)(r % j.ntaps), co = (int)(r / j.ntaps);
+  const float* src = j.src + (long long)t * j.tap_stride + (long long)co * j.w_co_stride + 8 * g;
+  float4 a = sg_ld4(src), b = sg_ld4(src + 4);
+  TO* dst = reinterpret_cast<TO*>(j.dst) + i * 8;
+  sg_st4(dst, a);
+  sg_st4(dst + 4, b);
+}
+__global__ void __launch_bounds__(256) k_pack_weights_multi(const __grid_constant__ PackJobs jobs) {
+  __shared__ float smt[32][33];
+  int ji = 0;
+  while (ji + 1 < jobs.njobs && (int)blockIdx.x >= jobs.job[ji + 1].tile0) ++ji;
+  const PackJob& j = jobs.job[ji];
+  const int tile = blockIdx.x - j.tile0;
+  if (j.kind == 0) {
+    if (j.dt == SG_F32) pack_tile_t<float>(j, tile, smt);
+    else pack_tile_t<__nv_bfloat16>(j, tile, smt);
+  } else {
+    if (j.dt == SG_F32) pack_tile_v8<float>(j, tile);
+    else pack_tile_v8<__nv_bfloat16>(j, tile);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -909,6 +974,28 @@ static void choose_box(int gw, int gh, int n, int max_rows, int mult, int* TW, i
   *TW = bw; *TH = bh; *TN = bn;
 }
 
+// pixel splits of the filter gradient: static round-robin over #SMs persistent CTAs costs ceil(units / #SMs) unit-times, so
+// pick the split count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43)
+static int wgrad_choose_splits(int ptiles, long long base_units, int co_tiles, int num_sms) {
+  int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
+  if (max_splits > 32) max_splits = 32;
+  if (base_units + 2 + co_tiles > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
+  int splits = 1;
+  double best_eff = -1.0;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    int pps = sg_div_up(ptiles, sp);
+    int eff_sp = sg_div_up(ptiles, pps);
+    if (eff_sp != sp) continue;
+    long long units_sp = base_units * sp;
+    long long waves = (units_sp + num_sms - 1) / num_sms;
+    // work per CTA in k-blocks: waves * pps (plus one epilogue per unit, ~ 4 k-blocks worth)
+    double cost = (double)waves * (pps + 4.0);
+    double eff = 1.0 / cost;
+    if (eff > best_eff * 1.02) { best_eff = eff; splits = sp; }
+  }
+  return splits;
+}
+
 static int tc_check(const sg_conv_desc* d, const char* who) {
   SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   int kc = d->in_dt == SG_F32 ? 32 : 64;
@@ -956,6 +1043,50 @@ int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_mast
     int grid = (int)(need < cap ? need : cap);
     SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
   }
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* 1 when sg_conv_pack_weights_multi can take this filter (regular taps t * c_in * c_out; one of the two vectorisable layouts) */
+int sg_conv_pack_multi_supported(const sg_conv_desc* d, const float* w_master) {
+  if (!d) return 0;
+  const long long ts = (long long)d->c_in * d->c_out;
+  for (int t = 0; t < d->ntaps; ++t)
+    if (d->tap_w_off[t] != (long long)t * ts) return 0;
+  if (d->w_co_stride == 1 && d->w_ci_stride != 1 && d->c_out >= 32) return 1;
+  if (d->w_ci_stride == 1 && d->c_in % 8 == 0 && d->w_co_stride % 4 == 0 && ((uintptr_t)w_master & 15) == 0 && ts % 4 == 0) return 1;
+  return 0;
+}
+
+/* njobs (<= 32) packing jobs in one launch: descs / w_master / w_packed are HOST arrays of length njobs */
+int sg_conv_pack_weights_multi(sg_ctx* ctx, int njobs, const sg_conv_desc* const* descs, const float* const* w_master, void* const* w_packed) {
+  SG_REQUIRE(ctx && descs && w_master && w_packed && njobs >= 1 && njobs <= PACK_MAX_JOBS, "sg_conv_pack_weights_multi: bad args");
+  static_assert(sizeof(PackJobs) < 4000, "kernel parameter block too large");
+  PackJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.njobs = njobs;
+  int tile = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const sg_conv_desc* d = descs[i];
+    SG_REQUIRE(d && w_master[i] && w_packed[i] && sg_conv_pack_multi_supported(d, w_master[i]), "sg_conv_pack_weights_multi: job %d not supported", i);
+    PackJob& j = jobs.job[i];
+    j.src = w_master[i]; j.dst = w_packed[i];
+    j.tap_stride = (long long)d->c_in * d->c_out; j.w_ci_stride = d->w_ci_stride; j.w_co_stride = d->w_co_stride;
+    j.c_in = d->c_in; j.c_out = d->c_out; j.ntaps = d->ntaps; j.dt = d->in_dt;
+    j.tile0 = tile;
+    if (d->w_co_stride == 1 && d->w_ci_stride != 1 && d->c_out >= 32) {
+      j.kind = 0;
+      j.tiles_ci = sg_div_up(d->c_in, 32); j.tiles_co = sg_div_up(d->c_out, 32);
+      tile += j.tiles_ci * j.tiles_co * d->ntaps;
+    } else {
+      j.kind = 1;
+      long long total8 = (long long)d->c_out * d->ntaps * (d->c_in / 8);
+      tile += (int)((total8 + 255) / 256);
+    }
+  }
+  jobs.total_tiles = tile;
+  if (tile == 0) return SG_OK;
+  k_pack_weights_multi<<<tile, 256, 0, ctx->stream>>>(jobs);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -1141,6 +1272,29 @@ int sg_conv_wgrad_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const v
   return conv_wgrad_tc_impl(ctx, d, in, dy, dw_master, nullptr, nullptr);
 }
 
+/* 1 when the bias units of sg_conv_wgrad_tc_bias fit into the idle CTA slots of the filter-gradient launch's last wave (then the
+ * bias gradient is free); 0 when they would open an extra wave -- measured slower than a separate column-sum launch, because a
+ * bias unit streams only the dy tiles (16 KB per stage in flight: latency bound) and lasts about as long as a full unit. */
+int sg_conv_wgrad_tc_bias_fits(sg_ctx* ctx, const sg_conv_desc* d) {
+  if (!ctx || !d || !sg_conv_tc_supported(d)) return 0;
+  const int es = d->in_dt == SG_F32 ? 4 : 2;
+  const int KC = 128 / es, UK = 32 / es;
+  const int BN = d->c_in % 256 == 0 ? 256 : (d->c_in % 128 == 0 ? 128 : (d->c_in % 64 == 0 ? 64 : 32));
+  const int ci_tiles = d->c_in / BN, co_tiles = sg_div_up(d->c_out, 128);
+  int max_rows = (48 * 1024) / (128 * (128 / KC + BN / KC));
+  if (max_rows > 128) max_rows = 128;
+  max_rows = max_rows / UK * UK;
+  int TW, TH, TN;
+  choose_box(d->grid_w, d->grid_h, d->n, max_rows, UK, &TW, &TH, &TN);
+  const int ptiles = sg_div_up(d->grid_w, TW) * sg_div_up(d->grid_h, TH) * sg_div_up(d->n, TN);
+  const long long base_units = (long long)d->ntaps * co_tiles * ci_tiles;
+  const int splits = wgrad_choose_splits(ptiles, base_units, co_tiles, ctx->num_sms);
+  const long long units = base_units * splits, bias_units = (long long)co_tiles * splits;
+  if (units < ctx->num_sms) return units + bias_units <= ctx->num_sms;
+  const long long idle = (ctx->num_sms - units % ctx->num_sms) % ctx->num_sms;
+  return bias_units <= idle;
+}
+
 /* filter gradient + bias gradient in ONE launch: db[c_out] (and db2, the bias of a shortcut conv that sees the same upstream
  * gradient; may be NULL) += column sums of dy, computed by the tensor cores as dy^T . 1 */
 int sg_conv_wgrad_tc_bias(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* dy, float* dw_master, float* db, float* db2) {
@@ -1202,22 +1356,7 @@ static int conv_wgrad_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in
   long long base_units = (long long)d->ntaps * p.co_tiles * p.ci_tiles;
   // pixel splits: static round-robin over #SMs persistent CTAs costs ceil(units / #SMs) unit-times, so pick the split
   // count whose last wave is fullest (e.g. 72 base units: 4 splits = 288 units = 1.95 waves, not 5 splits = 2.43 waves)
-  int max_splits = sg_div_up(ptiles, 8);           // at least 8 k-blocks per unit
-  if (max_splits > 32) max_splits = 32;
-  if (base_units + 2 + p.co_tiles > SG_DET_TICKETS) max_splits = 1;  // no turn semaphores for that many filter tiles
-  int splits = 1;
-  double best_eff = -1.0;
-  for (int sp = 1; sp <= max_splits; ++sp) {
-    int pps = sg_div_up(ptiles, sp);
-    int eff_sp = sg_div_up(ptiles, pps);
-    if (eff_sp != sp) continue;
-    long long units_sp = base_units * sp;
-    long long waves = (units_sp + ctx->num_sms - 1) / ctx->num_sms;
-    // work per CTA in k-blocks: waves * pps (plus one epilogue per unit, ~ 4 k-blocks worth)
-    double cost = (double)waves * (pps + 4.0);
-    double eff = 1.0 / cost;
-    if (eff > best_eff * 1.02) { best_eff = eff; splits = sp; }
-  }
+  int splits = wgrad_choose_splits(ptiles, base_units, p.co_tiles, ctx->num_sms);
   p.ptiles_per_split = sg_div_up(ptiles, splits);
   p.splits = sg_div_up(ptiles, p.ptiles_per_split);
   p.partial = ctx->det_scratch;

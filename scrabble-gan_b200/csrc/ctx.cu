@@ -75,6 +75,13 @@ int sg_ctx_sync(sg_ctx* ctx) {
 
 long long sg_ctx_launch_count(sg_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+/* zero `bytes` of device memory on the context's stream (a memset node, no kernel): gradient buckets at the start of a step */
+int sg_zero(sg_ctx* ctx, void* ptr, size_t bytes) {
+  SG_REQUIRE(ctx != nullptr && (ptr != nullptr || bytes == 0), "sg_zero: bad args");
+  if (bytes) SG_CHECK_CUDA(cudaMemsetAsync(ptr, 0, bytes, ctx->stream));
+  return SG_OK;
+}
+
 int sg_ctx_set_speed_mode(sg_ctx* ctx, int on) {
   SG_REQUIRE(ctx != nullptr, "ctx is NULL");
   ctx->speed_mode = on ? 1 : 0;

@@ -136,3 +136,96 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Grouped conditional-batch-norm Dense layers (resnet_ops.py:18-26): the generator has 6 CBN layers x (gamma, beta), each a
+// bias-free Dense(32 -> C) of the block's 32-wide slice of z.  One launch computes all twelve (forward) and one launch all
+// twelve filter gradients (backward) instead of 12 + 12 tiny GEMM launches.
+// ---------------------------------------------------------------------------------------------------
+#define CBN_MAX_SEG 16
+struct CbnSegs {
+  int nseg, total;
+  int col0[CBN_MAX_SEG], c[CBN_MAX_SEG], z_off[CBN_MAX_SEG];
+  long long w_off[CBN_MAX_SEG];
+  const float* s[CBN_MAX_SEG];          // backward: upstream [n, c] of the segment
+};
+
+// out[r, col] = sum_k z[r, z_off(seg) + k] * W_seg[k, col - col0(seg)],  k < 32
+__global__ void __launch_bounds__(256) k_cbn_dense_fwd(const float* __restrict__ z, int z_stride, int n, CbnSegs t,
+                                                       const float* __restrict__ w, float* __restrict__ out) {
+  const long long total = (long long)n * t.total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % t.total), r = (int)(i / t.total);
+    int sg = 0;
+    while (sg + 1 < t.nseg && col >= t.col0[sg + 1]) ++sg;
+    const int cl = col - t.col0[sg], c = t.c[sg];
+    const float* zz = z + (long long)r * z_stride + t.z_off[sg];
+    const float* ww = w + t.w_off[sg] + cl;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc = fmaf(zz[k], ww[(long long)k * c], acc);
+    out[i] = acc;
+  }
+}
+// dW_seg[k, cl] += sum_r z[r, z_off + k] * s_seg[r, cl]     (one thread per output: no atomics, fixed order over r)
+__global__ void __launch_bounds__(256) k_cbn_dense_wgrad(const float* __restrict__ z, int z_stride, int n, CbnSegs t,
+                                                         float* __restrict__ dw) {
+  const long long total = 32LL * t.total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % t.total), k = (int)(i / t.total);
+    int sg = 0;
+    while (sg + 1 < t.nseg && col >= t.col0[sg + 1]) ++sg;
+    const int cl = col - t.col0[sg], c = t.c[sg];
+    const float* ss = t.s[sg] + cl;
+    const float* zz = z + t.z_off[sg] + k;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < n; ++r) acc = fmaf(zz[(long long)r * z_stride], ss[(long long)r * c], acc);
+    dw[t.w_off[sg] + (long long)k * c + cl] += acc;
+  }
+}
+
+static int cbn_fill(CbnSegs* t, int nseg, const int* c, const int* z_off, const long long* w_off, const char* who) {
+  SG_REQUIRE(nseg >= 1 && nseg <= CBN_MAX_SEG && c && z_off && w_off, "%s: bad segment table", who);
+  t->nseg = nseg;
+  int col = 0;
+  for (int i = 0; i < nseg; ++i) {
+    SG_REQUIRE(c[i] > 0 && z_off[i] >= 0 && w_off[i] >= 0, "%s: bad segment %d", who, i);
+    t->col0[i] = col; t->c[i] = c[i]; t->z_off[i] = z_off[i]; t->w_off[i] = w_off[i]; t->s[i] = nullptr;
+    col += c[i];
+  }
+  t->total = col;
+  return SG_OK;
+}
+
+/* out[n, sum c] = for every segment i: z[:, z_off[i] : z_off[i] + 32] @ W_i, W_i = w_base + w_off[i] of shape (32, c[i]) */
+extern "C" int sg_cbn_dense_fwd(sg_ctx* ctx, const float* z, int z_stride, int n, int nseg, const int* c, const int* z_off,
+                                const long long* w_off, const float* w_base, float* out) {
+  SG_REQUIRE(ctx && z && w_base && out && n >= 0, "sg_cbn_dense_fwd: bad args");
+  CbnSegs t;
+  int rc = cbn_fill(&t, nseg, c, z_off, w_off, "sg_cbn_dense_fwd");
+  if (rc != SG_OK) return rc;
+  if (n == 0) return SG_OK;
+  long long need = ((long long)n * t.total + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  k_cbn_dense_fwd<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(z, z_stride, n, t, w_base, out);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* dW_i (at dw_base + w_off[i], shape (32, c[i])) += z[:, z_off[i] : +32]^T @ s_i, s_i = upstream[i] of shape (n, c[i]) */
+extern "C" int sg_cbn_dense_wgrad(sg_ctx* ctx, const float* z, int z_stride, int n, int nseg, const int* c, const int* z_off,
+                                  const long long* w_off, const float* const* upstream, float* dw_base) {
+  SG_REQUIRE(ctx && z && upstream && dw_base && n >= 0, "sg_cbn_dense_wgrad: bad args");
+  CbnSegs t;
+  int rc = cbn_fill(&t, nseg, c, z_off, w_off, "sg_cbn_dense_wgrad");
+  if (rc != SG_OK) return rc;
+  for (int i = 0; i < nseg; ++i) {
+    SG_REQUIRE(upstream[i] != nullptr, "sg_cbn_dense_wgrad: NULL upstream %d", i);
+    t.s[i] = upstream[i];
+  }
+  if (n == 0) return SG_OK;
+  long long need = (32LL * t.total + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  k_cbn_dense_wgrad<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(z, z_stride, n, t, dw_base);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}

@@ -53,7 +53,7 @@ class ConvLayer:
         if ent is None or ent[0] != self.store.version:
             buf = ent[1] if ent is not None else None
             buf = ops.pack_weights(rt, d, self.w.eff, buf)
-            self._packed[key] = (self.store.version, buf)
+            self._packed[key] = (self.store.version, buf, d)      # the descriptor lets layers.prepack() redo this in a batch
             return buf
         return ent[1]
 
@@ -119,6 +119,35 @@ class ConvLayer:
                 ops.axpby(rt, 1.0, s, 1.0, also_bias, out=also_bias)
 
 
+def prepack(rt: Runtime, convs) -> int:
+    """Re-pack, in ONE launch per 32 filters, every packed tensor-core filter of the given layers whose weights changed since
+    it was packed (i.e. after an optimizer step): the per-layer lazy packing in ConvLayer._pack then finds fresh entries.
+    Only filters that have been used before are known (their descriptor is cached with the packed buffer)."""
+    import ctypes as C
+    from . import _abi
+    lib = _abi.load()
+    jobs = []
+    for lay in convs:
+        ver = lay.store.version
+        for key, ent in lay._packed.items():
+            if ent[0] == ver or len(ent) < 3:
+                continue
+            d, buf = ent[2], ent[1]
+            src = lay.w.eff
+            if lib.sg_conv_pack_multi_supported(C.byref(d), C.c_void_p(src.data_ptr())):
+                jobs.append((lay, key, d, src, buf))
+    for i in range(0, len(jobs), 32):
+        chunk = jobs[i:i + 32]
+        k = len(chunk)
+        descs = (C.POINTER(_abi.ConvDesc) * k)(*[C.pointer(j[2]) for j in chunk])
+        srcs = (C.c_void_p * k)(*[j[3].data_ptr() for j in chunk])
+        dsts = (C.c_void_p * k)(*[j[4].data_ptr() for j in chunk])
+        _abi.call.sg_conv_pack_weights_multi(rt.ctx, k, descs, srcs, dsts)
+        for lay, key, d, src, buf in chunk:
+            lay._packed[key] = (lay.store.version, buf, d)
+    return len(jobs)
+
+
 class ConvTransposeLayer:
     """tf.keras.layers.Conv2DTranspose(filters, (k,k), strides=(sy,sx), padding='same') -- kernel (kh,kw,Cout,Cin).
     Forward is phase-decomposed (no zero-stuffed MACs): one launch per output phase, each a small stride-1 conv
@@ -141,7 +170,7 @@ class ConvTransposeLayer:
         ent = self._packed.get(key)
         if ent is None or ent[0] != self.store.version:
             buf = ops.pack_weights(rt, d, self.w.eff, ent[1] if ent is not None else None)
-            self._packed[key] = (self.store.version, buf)
+            self._packed[key] = (self.store.version, buf, d)
             return buf
         return ent[1]
 

@@ -169,15 +169,17 @@ def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_pac
     call.sg_conv_fwd_tc_dual(rt.ctx, C.byref(d), _p(x), _p(w_packed), C.byref(d2), _p(x2), _p(w_packed2), _p(bias), _p(mask), _p(out))
 
 
-def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False, db=None, db2=None) -> bool:
+def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False, db=None, db2=None, force_bias: bool = False) -> bool:
     """dw_master += filter gradient of the conv described by d: on the tensor cores whenever the layer is eligible and both
     operands have the mode's operand dtype (bf16, or fp32 read as tf32 in "tf32" mode); the FFMA kernel serves the edge
     layers (Cin = 1 / Cout = 1) and the exact "fp32" mode -- by rule, not as a silent fallback.
     db (and db2): bias gradient(s) to accumulate the column sums of dy into IN THE SAME LAUNCH; returns True when that was
-    done (tensor-core path of a plain Conv2D), False when the caller still has to sum dy itself."""
+    done (tensor-core path of a plain Conv2D whose extra bias units fit into the idle slots of the launch's last wave --
+    sg_conv_wgrad_tc_bias_fits; force_bias skips that test), False when the caller still has to sum dy itself."""
     tc_dt = SG_BF16 if rt.mode == "bf16" else (SG_F32 if (rt.mode == "tf32" and rt.tf32_wgrad_tc) else None)
     if not force_simt and tc_dt is not None and d.in_dt == tc_dt and d.out_dt == tc_dt and tc_ok(rt, d):
-        if db is not None and rt.fuse_bias_grad and d.out_sy == 1 and d.out_sx == 1 and d.grid_h == d.out_h and d.grid_w == d.out_w:
+        if db is not None and rt.fuse_bias_grad and d.out_sy == 1 and d.out_sx == 1 and d.grid_h == d.out_h and d.grid_w == d.out_w and \
+                (force_bias or _abi.load().sg_conv_wgrad_tc_bias_fits(rt.ctx, C.byref(d))):
             call.sg_conv_wgrad_tc_bias(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _p(db), _p(db2))
             return True
         call.sg_conv_wgrad_tc(rt.ctx, C.byref(d), _p(x), _p(dy), _p(dw_master), _V(None), 0)
@@ -339,12 +341,13 @@ def bn_infer_prepare(rt, moving_mean, moving_var, eps=1e-3):
     return mean, rstd
 
 
-def bn_apply(rt, x, mean, rstd, gamma, beta, per_sample: bool, relu: bool, out_dt):
+def bn_apply(rt, x, mean, rstd, gamma, beta, per_sample: bool, relu: bool, out_dt, gb_stride=None):
+    """gb_stride: row stride of per-sample gamma / beta (default c; the grouped CBN Dense output has a wider row)."""
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
     out = rt.empty(x.shape, out_dt)
-    call.sg_bn_apply(rt.ctx, _p(x), n, hw, c, _p(mean), _p(rstd), _p(gamma), _p(beta), c if per_sample else 0, int(relu),
-                     _p(out), out_dt)
+    stride = (c if gb_stride is None else gb_stride) if per_sample else 0
+    call.sg_bn_apply(rt.ctx, _p(x), n, hw, c, _p(mean), _p(rstd), _p(gamma), _p(beta), stride, int(relu), _p(out), out_dt)
     return out
 
 
@@ -357,23 +360,47 @@ def bn_bwd_reduce(rt, dy, act, x, mean, rstd):
     return s1, s2
 
 
-def bn_bwd_combine(rt, s1, s2, gamma, per_sample: bool):
+def bn_bwd_combine(rt, s1, s2, gamma, per_sample: bool, gb_stride=None):
     n, c = s1.shape
     ab = rt.empty((2 * c,), SG_F32)
-    call.sg_bn_bwd_combine(rt.ctx, _p(s1), _p(s2), _p(gamma), c if per_sample else 0, n, c, _p(ab))
+    stride = (c if gb_stride is None else gb_stride) if per_sample else 0
+    call.sg_bn_bwd_combine(rt.ctx, _p(s1), _p(s2), _p(gamma), stride, n, c, _p(ab))
     return ab
 
 
 def bn_bwd_apply(rt, dy, act, x, mean, rstd, gamma, per_sample, ab, count, use_batch_terms, mask_by_x, out_dt, out=None,
-                 accumulate=0):
+                 accumulate=0, gb_stride=None):
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
     if out is None:
         out = rt.empty(x.shape, out_dt)
+    stride = (c if gb_stride is None else gb_stride) if per_sample else 0
     call.sg_bn_bwd_apply(rt.ctx, _p(dy), _p(act), dt_of(act) if act is not None else SG_F32, _p(x), n, hw, c, _p(mean), _p(rstd),
-                         _p(gamma), c if per_sample else 0, _p(ab), float(count), int(use_batch_terms), int(mask_by_x), _p(out),
+                         _p(gamma), stride, _p(ab), float(count), int(use_batch_terms), int(mask_by_x), _p(out),
                          dt_of(out), accumulate)
     return out
+
+
+def cbn_dense_fwd(rt, z, z_stride, n, segs, w_base):
+    """segs: [(c, z_off, w_off)]: all CBN gamma / beta Dense layers of the generator in ONE launch -> [n, sum c]."""
+    k = len(segs)
+    total = sum(s[0] for s in segs)
+    out = rt.empty((n, total), SG_F32)
+    ci = (C.c_int * k)(*[s[0] for s in segs])
+    zi = (C.c_int * k)(*[s[1] for s in segs])
+    wi = (C.c_longlong * k)(*[s[2] for s in segs])
+    call.sg_cbn_dense_fwd(rt.ctx, _p(z), z_stride, n, k, ci, zi, wi, _p(w_base), _p(out))
+    return out
+
+
+def cbn_dense_wgrad(rt, z, z_stride, n, segs, upstream, dw_base):
+    """dW of every segment in ONE launch; upstream[i]: [n, c_i] contiguous."""
+    k = len(segs)
+    ci = (C.c_int * k)(*[s[0] for s in segs])
+    zi = (C.c_int * k)(*[s[1] for s in segs])
+    wi = (C.c_longlong * k)(*[s[2] for s in segs])
+    up = (C.c_void_p * k)(*[u.data_ptr() for u in upstream])
+    call.sg_cbn_dense_wgrad(rt.ctx, _p(z), z_stride, n, k, ci, zi, wi, up, _p(dw_base))
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -183,7 +183,8 @@ class ParamStore:
         return [v for v in self.vars if v.trainable]
 
     def zero_grad(self) -> None:
-        self.g.zero_()
+        from . import ops
+        ops.call.sg_zero(self.rt.ctx, ops._p(self.g), self.g.numel() * 4)       # a memset node, not a (torch) fill kernel
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {v.name: v.data.detach().clone() for v in self.vars}

@@ -66,6 +66,10 @@ class Runtime:
         self.tf32_wgrad_tc = os.environ.get("SGAN_TF32_WGRAD_SIMT", "0") != "1"
         # bias gradients of tensor-core convs come out of the filter-gradient launch (dy^T . 1 on the tensor cores)
         self.fuse_bias_grad = os.environ.get("SGAN_NO_FUSED_BIAS_GRAD", "0") != "1"
+        # the generator's 12 conditional-batch-norm Dense layers (and their filter gradients) as one grouped launch each
+        self.group_cbn_dense = os.environ.get("SGAN_NO_GROUPED_CBN", "0") != "1"
+        # one packing launch per network and step instead of one per layer
+        self.batch_packs = os.environ.get("SGAN_NO_BATCHED_PACKS", "0") != "1"
         call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------

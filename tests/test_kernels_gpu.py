@@ -165,7 +165,7 @@ def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
         check(dw, wt.grad, 2e-3, "tc wgrad")
         # filter gradient + bias gradient(s) in one launch (dy^T . 1 on the tensor cores), accumulating into both biases
         dw2, db, db2 = rt.zeros(wt.shape), rt.zeros((co,)), torch.ones(co, device=rt.device)
-        assert ops.conv_wgrad(rt, dwg, xd, dyd, dw2, db=db, db2=db2), "a plain Conv2D on the tensor-core path must fuse its bias gradient"
+        assert ops.conv_wgrad(rt, dwg, xd, dyd, dw2, db=db, db2=db2, force_bias=True), "a plain Conv2D on the tensor-core path can fuse its bias gradient"
         assert torch.equal(dw2, dw), "the bias units must not change the filter gradient"
         exp_db = dy.sum(dim=(0, 1, 2))
         check(db, exp_db, 2e-3, "tc wgrad fused bias gradient")
