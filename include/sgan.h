@@ -289,11 +289,28 @@ int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, vo
 int sg_adam_prepare(sg_ctx* ctx, int* step_dev, float* lr_dev, int t, float lr, float beta1, float beta2);
 int sg_adam_dev(sg_ctx* ctx, float* w, const float* g, float* m, float* v, void* w_mirror_bf16, long long n,
                 const float* lr_dev, float beta1, float beta2, float eps);
+/* the train step's optimizer launch (one per network): sg_adam_dev that (i) with beta1 == 0 -- the reference's setting
+ * (scrabble_gan.gin:8), where Keras' m_t equals g_t -- neither reads nor writes the first-moment slot (it is then not
+ * maintained), and (ii) with clear_grad overwrites the consumed gradient with zeros, so the next step needs no memset. */
+int sg_adam_fused(sg_ctx* ctx, float* w, float* g, float* m, float* v, void* w_mirror_bf16, long long n, const float* lr_dev,
+                  float beta1, float beta2, float eps, int clear_grad);
 int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, float lr, float rho, float eps);
 
 /* ---- spectral norm (K18) -- arch_ops.py:99-126; one power iteration from an explicit u ------------- */
 int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const float* u, int power_iteration,
                      float* w_out, float* u_out, float* sigma_out, float* scratch /* rows+cols+4 floats */);
+
+/* ---- ragged-width batches (words of different lengths in ONE launch, per-word SAME-padding semantics) --------
+ * sg_label_lengths: lens[b] = leading labels >= 0 of a (b, l) label matrix padded with -1;  sg_mask_width: zero an NHWC tensor
+ * right of every word's own width cols_per_char * lens[n] (applied to the inputs of every convolution of the generator, so that
+ * a short word sees the zero padding it would see on its own);  sg_attn_fwd[_tc]_masked: the non-local block with the keys
+ * beyond a word's width removed from the softmax (key j lies in column j % kv_w; kv_cols[n] columns are valid). */
+int sg_label_lengths(sg_ctx* ctx, const int* labels, int b, int l, int* lens);
+int sg_mask_width(sg_ctx* ctx, void* x, int dt, int n, int h, int w, int c, const int* lens, int cols_per_char);
+int sg_attn_fwd_masked(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv, int dk, int dv,
+                       int kv_w, const int* kv_cols, float* o, float* lse);
+int sg_attn_fwd_tc_masked(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv, int dk, int dv,
+                          int kv_w, const int* kv_cols, float* o, float* lse);
 
 /* ---- grouped conditional-batch-norm Dense layers (resnet_ops.py:18-26: gamma / beta = Dense(32 -> C, no bias)(z_block)) -----
  * ONE launch for all segments i < nseg (<= 16): out[n, sum c] = concat_i( z[:, z_off[i] : z_off[i] + 32] @ W_i ), W_i the (32, c[i])

@@ -101,6 +101,10 @@ _PROTOS = {
     "sg_bn_stats_partial": (_I, [_P, _P, _L, _I, _P, _Z, C.POINTER(_I)]),
     "sg_bn_finalize_peer": (_I, [_P, _P, _I, _I, _D, _F, _F, _P, _P, _P, _P, _P, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_gemm": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I]),
+    "sg_label_lengths": (_I, [_P, _P, _I, _I, _P]),
+    "sg_mask_width": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I]),
+    "sg_attn_fwd_masked": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "sg_attn_fwd_tc_masked": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "sg_cbn_dense_fwd": (_I, [_P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _P, _P]),
     "sg_cbn_dense_wgrad": (_I, [_P, _P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), C.POINTER(_P), _P]),
     "sg_filterbank_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
@@ -127,6 +131,7 @@ _PROTOS = {
     "sg_adam_mirror": (_I, [_P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F]),
     "sg_adam_prepare": (_I, [_P, _P, _P, _I, _F, _F, _F]),
     "sg_adam_dev": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _F, _F, _F]),
+    "sg_adam_fused": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _I]),
     "sg_rmsprop": (_I, [_P, _P, _P, _P, _L, _F, _F, _F]),
     "sg_spectral_norm": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
 }

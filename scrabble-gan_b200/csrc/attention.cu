@@ -16,12 +16,15 @@
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AT_THREADS) k_attn_fwd(const float* __restrict__ theta, const float* __restrict__ phi,
                                                           const float* __restrict__ g, int Q, int KV,
-                                                          float* __restrict__ o, float* __restrict__ lse) {
+                                                          float* __restrict__ o, float* __restrict__ lse, int kv_w,
+                                                          const int* __restrict__ kv_cols) {
+  // ragged batches: kv_cols[n] (may be NULL) = number of valid key COLUMNS of image n; key j sits in column j % kv_w
   __shared__ __align__(16) float ks[128 * AT_DK];
   __shared__ __align__(16) float vs[128 * AT_DV];
   const int n = blockIdx.y;
   const int qi = blockIdx.x * AT_THREADS + threadIdx.x;
   const bool valid = qi < Q;
+  const int vcn = kv_cols ? kv_cols[n] : kv_w;
   float qv[AT_DK];
   {
     const float* tp = theta + ((long long)n * Q + (valid ? qi : 0)) * AT_DK;
@@ -50,6 +53,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_fwd(const float* __restrict
         if (i < cc) {
           float4 a = reinterpret_cast<const float4*>(ks)[(c0 + i) * 2], b = reinterpret_cast<const float4*>(ks)[(c0 + i) * 2 + 1];
           float d = qv[0] * a.x + qv[1] * a.y + qv[2] * a.z + qv[3] * a.w + qv[4] * b.x + qv[5] * b.y + qv[6] * b.z + qv[7] * b.w;
+          if (kv_cols && (k0 + c0 + i) % kv_w >= vcn) d = -INFINITY;      // key beyond this word's width
           s[i] = d;
           cmax = fmaxf(cmax, d);
         } else {
@@ -250,7 +254,20 @@ int sg_attn_fwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
   SG_REQUIRE(q > 0 && kv > 0 && n >= 0, "sg_attn_fwd: bad sizes");
   if (n == 0) return SG_OK;
   dim3 grid(sg_div_up(q, AT_THREADS), n);
-  k_attn_fwd<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, q, kv, o, lse);
+  k_attn_fwd<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, q, kv, o, lse, kv, nullptr);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* ragged batch (inference): key j of image n lies in column j % kv_w of the key map; columns >= kv_cols[n] are outside the word */
+int sg_attn_fwd_masked(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv, int dk,
+                       int dv, int kv_w, const int* kv_cols, float* o, float* lse) {
+  SG_REQUIRE(ctx && theta && phi && g && o && lse && kv_cols, "sg_attn_fwd_masked: NULL");
+  SG_REQUIRE(dk == AT_DK && dv == AT_DV, "sg_attn_fwd_masked: only dk=8, dv=32 is built (got %d,%d)", dk, dv);
+  SG_REQUIRE(q > 0 && kv > 0 && n >= 0 && kv_w > 0 && kv % kv_w == 0, "sg_attn_fwd_masked: bad sizes");
+  if (n == 0) return SG_OK;
+  dim3 grid(sg_div_up(q, AT_THREADS), n);
+  k_attn_fwd<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, q, kv, o, lse, kv_w, kv_cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

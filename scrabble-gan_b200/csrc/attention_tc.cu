@@ -79,11 +79,14 @@ __global__ void __launch_bounds__(256) k_attn_rowdot(const float* __restrict__ d
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATC_THREADS) k_attn_fwd_tc(const float* __restrict__ theta, const float* __restrict__ phi,
                                                               const float* __restrict__ gv, int Q, int KV, int KVp,
-                                                              float* __restrict__ o, float* __restrict__ lse) {
+                                                              float* __restrict__ o, float* __restrict__ lse, int kv_w,
+                                                              const int* __restrict__ kv_cols) {
+  // ragged batches: kv_cols[n] (may be NULL) = valid key COLUMNS of image n; key j sits in column j % kv_w
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt = reinterpret_cast<uint32_t*>(smem);                         // [8][KVp]  tf32
   __nv_bfloat16* Vt = reinterpret_cast<__nv_bfloat16*>(Kt + ATC_DK * KVp);  // [32][KVp] bf16
   const int n = blockIdx.y;
+  const int vcn = kv_cols ? kv_cols[n] : kv_w;
   const int KVr = (KV + 15) & ~15;
   const float* phin = phi + (long long)n * KV * ATC_DK;
   const float* gn = gv + (long long)n * KV * ATC_DV;
@@ -128,9 +131,10 @@ __global__ void __launch_bounds__(ATC_THREADS) k_attn_fwd_tc(const float* __rest
         const int key0 = kc + 8 * j;
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         mma_tf32_16x8x8(s[j], qa, Kt[t * KVp + key0 + g], Kt[(t + 4) * KVp + key0 + g]);
-        if (key0 + 8 > KV) {
-          if (key0 + 2 * t >= KV) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-          if (key0 + 2 * t + 1 >= KV) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        if (key0 + 8 > KV || kv_cols) {
+          const int ka = key0 + 2 * t, kb = ka + 1;
+          if (ka >= KV || (kv_cols && ka % kv_w >= vcn)) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (kb >= KV || (kv_cols && kb % kv_w >= vcn)) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
         }
         cma = fmaxf(cma, fmaxf(s[j][0], s[j][1]));
         cmb = fmaxf(cmb, fmaxf(s[j][2], s[j][3]));
@@ -409,7 +413,21 @@ int sg_attn_fwd_tc(sg_ctx* ctx, const float* theta, const float* phi, const floa
   size_t smem = (size_t)ATC_DK * kvp * 4 + (size_t)ATC_DV * kvp * 2;
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(sg_div_up(q, ATC_ROWS), n);
-  k_attn_fwd_tc<<<grid, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, q, kv, kvp, o, lse);
+  k_attn_fwd_tc<<<grid, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, q, kv, kvp, o, lse, kv, nullptr);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+int sg_attn_fwd_tc_masked(sg_ctx* ctx, const float* theta, const float* phi, const float* g, int n, int q, int kv, int dk, int dv,
+                          int kv_w, const int* kv_cols, float* o, float* lse) {
+  SG_REQUIRE(ctx && theta && phi && g && o && lse && kv_cols, "sg_attn_fwd_tc_masked: NULL");
+  SG_REQUIRE(sg_attn_tc_supported(q, kv, dk, dv) && kv_w > 0 && kv % kv_w == 0, "sg_attn_fwd_tc_masked: unsupported sizes q=%d kv=%d kv_w=%d", q, kv, kv_w);
+  if (n == 0) return SG_OK;
+  int kvp = atc_pad(kv);
+  size_t smem = (size_t)ATC_DK * kvp * 4 + (size_t)ATC_DV * kvp * 2;
+  SG_CHECK_CUDA(cudaFuncSetAttribute(k_attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(sg_div_up(q, ATC_ROWS), n);
+  k_attn_fwd_tc<<<grid, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, q, kv, kvp, o, lse, kv_w, kv_cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -429,6 +429,26 @@ __global__ void k_philox_advance(unsigned long long* offset_dev, unsigned long l
   if (blockIdx.x == 0 && threadIdx.x == 0) *offset_dev += by;
 }
 
+
+// ragged batches (several word lengths in one launch): zero everything right of a word's own width
+template <typename T>
+__global__ void k_mask_width(T* __restrict__ x, long long total4, int h, int w, int c4, const int* __restrict__ lens, int cols_per_char) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long pix = i / c4;
+    const int col = (int)(pix % w);
+    const int ni = (int)(pix / ((long long)w * h));
+    if (col >= lens[ni] * cols_per_char) sg_st4(x + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+__global__ void k_label_lengths(const int* __restrict__ labels, int b, int l, int* __restrict__ lens) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  int n = 0;
+  while (n < l && labels[(long long)i * l + n] >= 0) ++n;
+  lens[i] = n;
+}
+
 extern "C" {
 
 int sg_act_prep(sg_ctx* ctx, const float* x, long long n, void* relu_out, void* copy_out, int out_dt) {
@@ -650,6 +670,26 @@ int sg_random(sg_ctx* ctx, float* out, long long n, unsigned long long seed, uns
     k_philox_advance<<<1, 32, 0, ctx->stream>>>(offset_dev, (unsigned long long)groups);
     SG_POST_LAUNCH(ctx);
   }
+  return SG_OK;
+}
+
+
+/* ragged batches: x[n, :, col, :] = 0 for col >= cols_per_char * lens[n]  (x is NHWC [n,h,w,c], c % 4 == 0) */
+int sg_mask_width(sg_ctx* ctx, void* x, int dt, int n, int h, int w, int c, const int* lens, int cols_per_char) {
+  SG_REQUIRE(ctx && x && lens && n >= 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0 && cols_per_char > 0, "sg_mask_width: bad args");
+  long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return SG_OK;
+  SG_DISPATCH_DT(dt, T, k_mask_width<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((T*)x, total, h, w, c / 4, lens, cols_per_char));
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* lens[b] = number of leading labels >= 0 of row b (padded label matrices of ragged batches use -1) */
+int sg_label_lengths(sg_ctx* ctx, const int* labels, int b, int l, int* lens) {
+  SG_REQUIRE(ctx && labels && lens && b >= 0 && l > 0, "sg_label_lengths: bad args");
+  if (b == 0) return SG_OK;
+  k_label_lengths<<<sg_div_up(b, 256), 256, 0, ctx->stream>>>(labels, b, l, lens);
+  SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
 

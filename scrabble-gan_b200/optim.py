@@ -80,8 +80,10 @@ class Adam:
                                      self.learning_rate, self.beta_1, self.beta_2)
             if not capturing:
                 self._dev_step = self.iterations
-            ops.call.sg_adam_dev(rt.ctx, ops._p(store.w), ops._p(store.g), ops._p(st.slots[0]), ops._p(st.slots[1]), ops._p(mirror),
-                                 store.w.numel(), ops._p(self._dev[1]), self.beta_1, self.beta_2, self.epsilon)
+            # one launch per network: the update and the bf16 mirror; with beta_1 == 0 the m slot is not touched.  The gradient
+            # is left in place (clear_grad = 0): callers and the parity tests read it after the step
+            ops.call.sg_adam_fused(rt.ctx, ops._p(store.w), ops._p(store.g), ops._p(st.slots[0]), ops._p(st.slots[1]), ops._p(mirror),
+                                   store.w.numel(), ops._p(self._dev[1]), self.beta_1, self.beta_2, self.epsilon, 0)
             mirror_fresh = mirror is not None
         else:
             for g, v in pairs:

@@ -652,6 +652,18 @@ def test_adam_rmsprop(rt):
         check(wd, w1, 1e-6, "adam w")
         check(md, m1, 1e-6, "adam m")
         check(vd, v1, 1e-6, "adam v")
+        # the train step's launch: same update with the step size read from device memory and a bf16 mirror written in the
+        # same pass; with beta1 == 0 (m_t = g_t) the first-moment slot is left alone; clear_grad zeroes the consumed gradient
+        for clear in (0, 1):
+            wd, md, vd, gd = dev(rt, w), dev(rt, m), dev(rt, v), dev(rt, gr)
+            mirror = torch.empty(n, device=rt.device, dtype=torch.bfloat16)
+            lr_dev = torch.tensor([lr_t], device=rt.device, dtype=torch.float32)
+            ops.call.sg_adam_fused(rt.ctx, ops._p(wd), ops._p(gd), ops._p(md), ops._p(vd), ops._p(mirror), n, ops._p(lr_dev), b1, b2, 1e-7, clear)
+            check(wd, w1, 1e-6, "fused adam w")
+            check(vd, v1, 1e-6, "fused adam v")
+            check(md, m if b1 == 0.0 else m1, 1e-6, "fused adam m")
+            assert torch.equal(mirror, wd.to(torch.bfloat16))
+            assert torch.equal(gd, torch.zeros_like(gd) if clear else dev(rt, gr))
     w1, ms1 = O.rmsprop_update(w, gr, v, 2e-4)
     wd, msd = dev(rt, w), dev(rt, v)
     ops.rmsprop_(rt, wd, dev(rt, gr), msd, 2e-4, 0.9, 1e-7)
