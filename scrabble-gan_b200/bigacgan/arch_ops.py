@@ -27,14 +27,15 @@ class NonLocalBlock:
         self.o = store.add(name + ".o.w", (1, 1, self.dv, c), init_orthogonal)
         self.sigma = store.add(name + ".sigma", (1,), init_zeros)
 
-    def forward(self, rt: Runtime, x):
+    def forward(self, rt: Runtime, x, kv_cols=None):
+        """kv_cols (int32 [n], ragged batches): image n attends to the first kv_cols[n] columns of the pooled key map only."""
         n, h, w, c = x.shape
         theta, phi_f, g_f = ops.nonlocal_proj_fwd(rt, x, self.theta.eff, self.phi.eff, self.g.eff)
         phi_f, g_f = phi_f.view(n, h, w, self.dk), g_f.view(n, h, w, self.dv)
         phi = ops.maxpool_fwd(rt, phi_f, 2, 2)
         g = ops.maxpool_fwd(rt, g_f, 2, 2)
         q, kv = h * w, (h // 2) * (w // 2)
-        o, lse = ops.attn_fwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv))
+        o, lse = ops.attn_fwd(rt, theta.view(n, q, self.dk), phi.view(n, kv, self.dk), g.view(n, kv, self.dv), kv_w=w // 2, kv_cols=kv_cols)
         og, out = ops.nonlocal_out_fwd(rt, o, self.o.eff, self.sigma.data, x)
         # every cached tensor keeps the image index as its first dimension so that sub-batches can be sliced
         return out.view(n, h, w, c), (x, theta.view(n, q, self.dk), phi_f, phi, g_f, g, o, lse, og.view(n, h, w, c))

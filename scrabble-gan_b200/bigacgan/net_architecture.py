@@ -460,8 +460,17 @@ class Generator(_Model):
             self.style_dense = DenseLayer(self.store, "style_dense", self.style.out_channels, latent_dim)
         self.store.finalize(initialise)
 
-    def forward(self, rt, z_or_imgs, y, training: bool = True, img_out=None):
+    def forward(self, rt, z_or_imgs, y, training: bool = True, img_out=None, ragged: bool = False):
+        """ragged=True (inference only): y is a label matrix padded with -1 on the right; every word is
+        generated exactly as it would be alone at its own width 16 * len -- the inputs of all 3x3 convolutions are zeroed
+        right of the word (its SAME padding), the non-local block leaves the keys beyond the word out of the softmax -- and
+        the image is zero right of the word."""
         sc = None
+        lens = None
+        if ragged:
+            if training:
+                raise ValueError("ragged generator batches are an inference feature: batch-statistics BN couples the words of a batch")
+            lens = ops.label_lengths(rt, y)
         if self.style is not None:
             feats, tc = self.style.forward(rt, z_or_imgs)
             z = self.style_dense.forward(rt, feats, feats.shape[0])
@@ -486,10 +495,15 @@ class Generator(_Model):
             kw = {}
             if gb is not None:
                 kw = {"gb1": (gb[4 * i], gb[4 * i + 1], gb_stride), "gb2": (gb[4 * i + 2], gb[4 * i + 3], gb_stride)}
+            if lens is not None:
+                kw["ragged"] = (lens, net.shape[2] // y.shape[1])
             net, c = blk.forward(rt, net, zi, zs, training, **kw)
             ca = None
             if i in self.attn:
-                net, ca = self.attn[i].forward(rt, net)
+                kv_cols = None
+                if lens is not None:
+                    kv_cols = lens * (net.shape[2] // y.shape[1] // 2)          # widths are even: no pooling window straddles a word's edge
+                net, ca = self.attn[i].forward(rt, net, kv_cols=kv_cols)
             caches.append((c, ca))
         if training:
             mean, rstd, count = batch_stats(rt, net, self.bn)
@@ -497,8 +511,13 @@ class Generator(_Model):
             mean, rstd = ops.bn_infer_prepare(rt, self.bn.moving_mean.data, self.bn.moving_var.data)
             count = 1
         act = ops.bn_apply(rt, net, mean, rstd, self.bn.gamma.data, self.bn.beta.data, False, True, rt.op_dt)
+        if lens is not None:
+            ops.mask_width_(rt, act, lens, act.shape[2] // y.shape[1])
         pre = self.out.forward(rt, act)
         img = ops.tanh_fwd(rt, pre, img_out)
+        if lens is not None:
+            ops.mask_width_(rt, img.view(img.shape[0], img.shape[1], img.shape[2] // 4, 4) if img.shape[3] == 1 else img, lens,
+                            (img.shape[2] // 4 if img.shape[3] == 1 else img.shape[2]) // y.shape[1])
         return img, (sc, z, ec, caches, net, mean, rstd, count, act, training, img)
 
     def backward(self, rt, cache, dimg):
@@ -552,15 +571,20 @@ class Generator(_Model):
     def _cbn_wbase(self):
         return self.store.w if self.store.w_eff is None else self.store.w_eff
 
-    def __call__(self, inputs, training=True):
+    def __call__(self, inputs, training=True, ragged=None):
+        """inputs = [z, y] (or [style images, y]).  A HOST label matrix that contains -1 padding is run as a ragged batch
+        (see forward); for labels already on the device say ragged=True (no device read-back to find out)."""
         a, y = inputs[0], inputs[1]
+        if ragged is None:
+            host = isinstance(y, (np.ndarray, list, tuple)) or (isinstance(y, torch.Tensor) and not y.is_cuda)
+            ragged = host and bool((np.asarray(y) < 0).any())
         y = to_device_i32(self.rt, y)
         if self.style is not None:
             a = _nhwc(to_device_f32(self.rt, a))
         else:
             a = to_device_f32(self.rt, a)
         self.sn_forward(self.rt, update_u=False)
-        img, _ = self.forward(self.rt, a, y, training)
+        img, _ = self.forward(self.rt, a, y, training, ragged=bool(ragged))
         return img
 
 

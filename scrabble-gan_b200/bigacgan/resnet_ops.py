@@ -81,10 +81,16 @@ class ResNetBlockUp:
         self.conv = ConvLayer(store, name + ".conv", 3, 3, co, co)
         self.short = ConvTransposeLayer(store, name + ".short", 1, ci, co, self.stride)
 
-    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool, gb1=None, gb2=None):
+    def forward(self, rt: Runtime, x, z, z_stride: int, training: bool, gb1=None, gb2=None, ragged=None):
+        """ragged = (lens, columns per character of x): the inputs of both 3x3 convolutions are zeroed right of every word's
+        own width, so a short word of a padded batch sees the zero padding it would see alone (inference only)."""
         a1, c1 = self.cbn1.forward(rt, x, z, z_stride, training, True, rt.op_dt, gb=gb1)
+        if ragged is not None:
+            ops.mask_width_(rt, a1, ragged[0], ragged[1])
         u = self.up.forward(rt, a1)
         a2, c2 = self.cbn2.forward(rt, u, z, z_stride, training, True, rt.op_dt, gb=gb2)
+        if ragged is not None:
+            ops.mask_width_(rt, a2, ragged[0], ragged[1] * self.stride[1])
         bsum = ops.axpby(rt, 1.0, self.conv.b.data, 1.0, self.short.b.data)      # conv bias + shortcut bias (everywhere)
         h = self.conv.forward(rt, a2, bias=bsum)
         xs = ops.cast(rt, x, rt.op_dt)

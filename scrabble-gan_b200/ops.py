@@ -442,10 +442,30 @@ def _attn_tc(rt, q, kv, dk, dv, tc) -> bool:
     return bool(tc and _abi.load().sg_attn_tc_supported(q, kv, dk, dv))
 
 
-def attn_fwd(rt, theta, phi, g, tc=None):
+def label_lengths(rt, labels):
+    """lens[b] = number of leading labels >= 0 (ragged batches pad the label matrix with -1)."""
+    b, l = labels.shape
+    lens = torch.empty((b,), device=rt.device, dtype=torch.int32)
+    call.sg_label_lengths(rt.ctx, _p(labels), b, l, _p(lens))
+    return lens
+
+
+def mask_width_(rt, x, lens, cols_per_char: int):
+    """In place: zero the NHWC tensor x right of column cols_per_char * lens[n] of every image n."""
+    n, h, w, c = x.shape
+    call.sg_mask_width(rt.ctx, _p(x), dt_of(x), n, h, w, c, _p(lens), cols_per_char)
+    return x
+
+
+def attn_fwd(rt, theta, phi, g, tc=None, kv_w: int = 0, kv_cols=None):
+    """kv_cols (int32 [n]) with kv_w = key columns per row: keys in columns >= kv_cols[n] are left out of image n's softmax."""
     n, q, dk = theta.shape
     kv, dv = g.shape[1], g.shape[2]
     o, lse = rt.empty((n, q, dv), SG_F32), rt.empty((n, q), SG_F32)
+    if kv_cols is not None:
+        fn = call.sg_attn_fwd_tc_masked if _attn_tc(rt, q, kv, dk, dv, tc) else call.sg_attn_fwd_masked
+        fn(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, kv_w, _p(kv_cols), _p(o), _p(lse))
+        return o, lse
     if _attn_tc(rt, q, kv, dk, dv, tc):
         call.sg_attn_fwd_tc(rt.ctx, _p(theta), _p(phi), _p(g), n, q, kv, dk, dv, _p(o), _p(lse))
     else:

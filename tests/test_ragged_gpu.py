@@ -68,3 +68,49 @@ def test_recognizer_on_ragged_batch(rt):
     got, cache = R.forward(rt, x.float().to(rt.device), labels.to(rt.device, torch.int32), True, il, ll)
     R.backward(rt, cache, None, wgrad=True, want_dx=False)
     assert_grads(R.store.grad_dict(), {k: v.grad for k, v in leaf.items() if v.grad is not None}, 1e-3, 1e-2, "R gradients on a ragged batch")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_generator_on_ragged_batch(rt, mode):
+    """Words of different lengths in ONE generator launch (labels padded with -1) == each word generated alone at its own
+    width: the reference's inference loop (run_inference.py:35-50 calls the generator once per word) as one padded batch.
+    Also against the fp64 oracle for the words alone."""
+    rt.set_mode(mode)
+    try:
+        b, l_max = 7, 6
+        g = torch.Generator().manual_seed(21)
+        lens = torch.tensor([6, 1, 3, 2, 6, 4, 5])
+        labels = torch.randint(0, 52, (b, l_max), generator=g)
+        for i in range(b):
+            labels[i, lens[i]:] = -1
+        z = torch.randn(b, 128, generator=g, dtype=torch.float64)
+        P = O.make_generator_params(40, torch.float64, sigma=0.2, bias_scale=0.05)
+        for k in P:                                             # inference BN: moving statistics that matter
+            if k.endswith("moving_mean"):
+                P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.1
+            if k.endswith("moving_var"):
+                P[k] = 0.5 + torch.rand(P[k].shape, generator=g, dtype=torch.float64)
+        G = na.make_generator(128, IN_DIM, (32, 8192), None, "B3", 52, vis_model=False, rt=rt, initialise=False)
+        G.load_state_dict(P)
+        out = G([z.float().numpy(), labels.numpy()], training=False)          # -1 in a host label matrix: ragged
+        assert tuple(out.shape) == (b, 32, 16 * l_max, 1)
+        n0 = rt.launch_count()
+        out_dev = G([z.float().to(rt.device), labels.to(rt.device, torch.int32)], training=False, ragged=True)
+        launches = rt.launch_count() - n0
+        assert torch.equal(out, out_dev)
+        tol = 1e-4 if mode == "fp32" else 3e-2
+        alone_launches = 0
+        for i in range(b):
+            li = int(lens[i])
+            n0 = rt.launch_count()
+            alone = G([z[i:i + 1].float().numpy(), labels[i:i + 1, :li].numpy()], training=False)
+            alone_launches += rt.launch_count() - n0
+            err = float((out[i, :, :16 * li] - alone[0]).abs().max())
+            assert err <= tol, "word {} (length {}): ragged batch vs alone differ by {:.3e}".format(i, li, err)
+            assert float(out[i, :, 16 * li:].abs().max() if li < l_max else 0.0) == 0.0, "the image right of the word must be zero"
+            if mode == "fp32":
+                exp = O.generator(z[i:i + 1], labels[i:i + 1, :li], P, training=False)
+                assert rel_max(out[i, :, :16 * li], exp[0]) <= 1e-3
+        assert launches < alone_launches / 3, (launches, alone_launches)
+    finally:
+        rt.set_mode("fp32")
