@@ -45,6 +45,10 @@ long long sg_ctx_launch_count(sg_ctx* ctx);      /* kernels launched through thi
 /* speed mode (bf16 runs): the fp32 1x1 projections of the non-local block take their products on bf16 warp-level tensor
  * ops (fp32 accumulate) instead of exact FFMA; off by default */
 int sg_ctx_set_speed_mode(sg_ctx* ctx, int on);
+/* tensor-core convolutions: when the last wave of output tiles of a launch would leave most SMs idle, the k-range of each of its
+ * tiles is split over several CTAs, which exchange fp32 partial accumulators through the context's workspace and add them in a
+ * fixed order (results stay bit-reproducible run to run).  On by default (SGAN_NO_SPLIT_TAIL=1 at context creation disables). */
+int sg_ctx_set_conv_split_tail(sg_ctx* ctx, int on);
 int sg_sizeof_conv_desc(void);                    /* sizeof(sg_conv_desc): layout guard for FFI mirrors */
 
 /* ---- convolution family (K1-K8) ------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct sg_ctx {
   // fixed workspace of the deterministic cross-block reductions (allocated once by sg_ctx_create, see sg_det_* below):
   float* det_scratch;        // SG_DET_SCRATCH_BYTES of per-block partial sums
   unsigned int* det_tickets; // SG_DET_TICKETS arrival counters / turn semaphores, all zero between launches
+  int conv_split_tail;       // k_conv_tc: split the k-range of the tiles of a partial last wave (SGAN_NO_SPLIT_TAIL=1 disables)
 };
 #define SG_DET_SCRATCH_BYTES (48u << 20)
 #define SG_DET_TICKETS 16384

@@ -168,7 +168,27 @@ struct alignas(64) TcFwdParams {
   const float* bias;
   const void* mask;
   void* out;
+  // split tail (wave quantisation): tiles [0, t_full) are whole units; each later tile is `split` units, one contiguous k-block
+  // range each, on `split` consecutive CTAs.  Every unit parks the accumulator chunks it does not own in `part`, the units of a
+  // tile meet at `cnt`, and each finishes its own share of the tile's 32-column chunks: own accumulators + the peers' partials
+  // added in unit order (deterministic), then the usual epilogue.
+  int t_full, split, total_units;
+  float* part;                  // [tail unit][BN/32 chunks][8][128 rows] float4
+  unsigned int* cnt;            // [tail tile][2]: arrivals, departures; zero between launches
 };
+
+// unit v of the launch -> (tile, k-block range); si = index of the unit inside its tile (0 for whole tiles)
+struct TcUnit { int tile, kb0, kb1, si; };
+__device__ __forceinline__ TcUnit tc_unit(const TcFwdParams& p, int v, int nkb) {
+  TcUnit u;
+  if (v < p.t_full) { u.tile = v; u.kb0 = 0; u.kb1 = nkb; u.si = 0; return u; }
+  const int w = v - p.t_full;
+  u.tile = p.t_full + w / p.split;
+  u.si = w % p.split;
+  u.kb0 = (int)((long long)nkb * u.si / p.split);
+  u.kb1 = (int)((long long)nkb * (u.si + 1) / p.split);
+  return u;
+}
 
 template <typename TIn>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcFwdParams p) {
@@ -210,8 +230,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int total_tiles = m_tiles * p.tiles_col;
   const int nkb = p.ntaps * p.kc_per_tap + p.kc2;
 
   if (warp == 0) {
@@ -219,19 +237,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nkb1 = p.ntaps * p.kc_per_tap;
+      for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
+        const TcUnit u = tc_unit(p, v, nkb);
+        const int tile = u.tile;
         int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
         int tx = mt % p.tiles_x;
         int r = mt / p.tiles_x;
         int ty = r % p.tiles_y, tn = r / p.tiles_y;
         int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, col0 = col_t * p.BN;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const CUtensorMap* ma = &p.map_a[p.tap_view[t]];
-          int cx = x0 + p.tap_ox[t], cy = y0 + p.tap_oy[t];
-          for (int c = 0; c < p.kc_per_tap; ++c) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
-            tma_load_4d(a_base + s * p.a_stage_stride, ma, bar_full + 8 * s, c * KC, cx, cy, n0);
+        int t = u.kb0 / p.kc_per_tap, c = u.kb0 % p.kc_per_tap;      // (tap, channel chunk) of k-block kb < nkb1
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+          if (kb < nkb1) {
+            const CUtensorMap* ma = &p.map_a[p.tap_view[t]];
+            tma_load_4d(a_base + s * p.a_stage_stride, ma, bar_full + 8 * s, c * KC, x0 + p.tap_ox[t], y0 + p.tap_oy[t], n0);
             const uint32_t bdst = b_base + s * p.b_stage_stride;
             if (p.b_mode == 0) {
               tma_load_2d(bdst, &p.map_b, bar_full + 8 * s, t * p.c_in + c * KC, col0);
@@ -241,14 +262,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
               for (int j = 0; j < p.BN / 64; ++j)
                 tma_load_3d(bdst + j * (KC * 128), &p.map_b, bar_full + 8 * s, col0 + 64 * j, c * KC, p.tap_wt[t]);
             }
-            if (++s == p.stages) { s = 0; ph ^= 1; }
+            if (++c == p.kc_per_tap) { c = 0; ++t; }
+          } else {                               // second operand: the block's 1x1 shortcut on its own input tensor
+            const int c2 = kb - nkb1;
+            tma_load_4d(a_base + s * p.a_stage_stride, &p.map_a2, bar_full + 8 * s, c2 * KC, x0, y0, n0);
+            tma_load_2d(b_base + s * p.b_stage_stride, &p.map_b2, bar_full + 8 * s, c2 * KC, col0);
           }
-        }
-        for (int c = 0; c < p.kc2; ++c) {          // second operand: the block's 1x1 shortcut on its own input tensor
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
-          tma_load_4d(a_base + s * p.a_stage_stride, &p.map_a2, bar_full + 8 * s, c * KC, x0, y0, n0);
-          tma_load_2d(b_base + s * p.b_stage_stride, &p.map_b2, bar_full + 8 * s, c * KC, col0);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -259,11 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const uint32_t idesc = make_idesc(kTf32, false, b_mn, 128, p.BN);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
+      const TcUnit u = tc_unit(p, v, nkb);
       mbar_wait(bar_tempty + 8 * as, aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -275,9 +295,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           const uint64_t bstep = b_mn ? (uint64_t)((16 * 128) >> 4) : 2ull;
 #pragma unroll
           for (int k = 0; k < 4; ++k)      // 4 x 32 bytes of K per 128-byte swizzle row of A
-            umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + bstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma<kTf32>(d_tmem, da + (uint64_t)(2 * k), db + bstep * k, idesc, (kb != u.kb0 || k != 0) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);
-          if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+          if (kb == u.kb1 - 1) umma_commit(bar_tfull + 8 * as);
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -299,7 +319,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const int tr0 = lane >> 2, c0 = (lane & 3) * 8;      // transposed ownership: rows tr0 + 8 i, channels c0 .. c0 + 7
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int nchunks = p.BN / 32;
+    for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
+      const TcUnit u = tc_unit(p, v, nkb);
+      const int tile = u.tile;
       int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
       int tx = mt % p.tiles_x;
       int r = mt / p.tiles_x;
@@ -318,7 +341,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
-      for (int ch = 0; ch < p.BN / 32; ++ch) {
+      int ch_lo = 0, ch_hi = nchunks;
+      const float4* peers = nullptr;                        // partials of the tile's units, unit 0 first
+      if (v >= p.t_full) {
+        // a split tile: park the chunks the peers will finish, meet them, then finish chunks [ch_lo, ch_hi) of the tile
+        ch_lo = nchunks * u.si / p.split;
+        ch_hi = nchunks * (u.si + 1) / p.split;
+        const int tail_tile = tile - p.t_full;
+        const long long unit_f4 = (long long)nchunks * 8 * 128;
+        peers = reinterpret_cast<const float4*>(p.part) + (long long)tail_tile * p.split * unit_f4;
+        float4* mine = reinterpret_cast<float4*>(p.part) + ((long long)tail_tile * p.split + u.si) * unit_f4;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          if (ch >= ch_lo && ch < ch_hi) continue;
+          uint32_t pv[32];
+          tmem_ld32(taddr + ch * 32, pv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(mine + ((long long)ch * 8 + j) * 128 + row,
+                   make_float4(__uint_as_float(pv[4 * j]), __uint_as_float(pv[4 * j + 1]), __uint_as_float(pv[4 * j + 2]), __uint_as_float(pv[4 * j + 3])));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        unsigned int* cn = p.cnt + 2 * tail_tile;
+        if (threadIdx.x == 64) {
+          atomicAdd(cn, 1u);
+          while (*reinterpret_cast<volatile unsigned int*>(cn) < (unsigned int)p.split) __nanosleep(64);
+          __threadfence();
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      for (int ch = ch_lo; ch < ch_hi; ++ch) {
         // issue every global read of this chunk (ReLU mask, accumulate operand) up front: all of them are in flight while
         // the accumulators come out of TMEM and go through the transpose
         float mk[4][8], prev[4][8];
@@ -354,6 +406,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (peers) {
+            // sum over the tile's units in unit order, this unit's own accumulators at its own position
+            float acc[32];
+            const long long unit_f4 = (long long)nchunks * 8 * 128;
+            for (int sp = 0; sp < p.split; ++sp) {
+              float t[32];
+              if (sp == u.si) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = f[j];
+              } else {
+                const float4* q = peers + sp * unit_f4 + (long long)ch * 8 * 128 + row;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float4 a = __ldcg(q + j * 128);
+                  t[4 * j] = a.x; t[4 * j + 1] = a.y; t[4 * j + 2] = a.z; t[4 * j + 3] = a.w;
+                }
+              }
+              if (sp == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = t[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += t[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = acc[j];
+          }
           if (p.bias) {
             const float* bp = p.bias + col_t * p.BN + ch * 32;
 #pragma unroll
@@ -403,6 +483,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       mbar_arrive(bar_tempty + 8 * as);
       as ^= 1;
       if (as == 0) aph ^= 1;
+      if (peers) {
+        // the last unit to leave the tile re-arms its counters for the next launch (every peer has read the partials it needs)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          unsigned int* cn = p.cnt + 2 * (tile - p.t_full);
+          if (atomicAdd(cn + 1, 1u) == (unsigned int)p.split - 1u) { cn[0] = 0u; cn[1] = 0u; __threadfence(); }
+        }
+      }
     }
   }
 
@@ -1118,6 +1206,29 @@ static int direct_mode(const sg_conv_desc* d) {
   return 0;
 }
 
+// Cost (in tile-times of the given N tile) of `tiles` output tiles on `sms` persistent CTAs, and the tail split that achieves it:
+// whole waves run unsplit; the tiles of the last, partial wave are cut into `split` k-ranges each (<= 8, >= 4 k-blocks per range,
+// partials within the workspace).  A split wave costs ceil(rem * split / sms) / split tile-times plus the exchange: the rendezvous
+// and one tile of fp32 partials written and read through L2, ~10 us measured (tools/trace_step.py), against ~0.45 us per k-block of
+// a 128 x 256 tile -- i.e. ~22 k-blocks' worth, which is why short-k launches (R's deep layers, the G phases) stay unsplit.
+static double tc_split_plan(long long tiles, int sms, int nkb, int bn, int enabled, int* split_out) {
+  const long long full = tiles / sms, rem = tiles % sms;
+  *split_out = 1;
+  if (rem == 0) return (double)full;
+  double best = (double)full + 1.0;
+  if (!enabled) return best;
+  const double exchange = 22.0 * (256.0 / (double)bn) / (double)nkb;
+  for (int s = 2; s <= 8; ++s) {
+    if (nkb / s < 4) break;
+    if ((long long)rem * s * 128 * bn * 4 > (long long)SG_DET_SCRATCH_BYTES) break;
+    if (2 * rem > SG_DET_TICKETS) break;
+    const long long waves = (rem * s + sms - 1) / sms;
+    const double cost = (double)full + (double)waves / s + exchange;
+    if (cost < best * 0.97) { best = cost; *split_out = s; }
+  }
+  return best;
+}
+
 static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, int b_mode, const float* bias,
                             const void* mask, void* out, const sg_conv_desc* d2 = nullptr, const void* in2 = nullptr,
                             const void* w_packed2 = nullptr) {
@@ -1143,11 +1254,14 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   p.bias = bias; p.mask = mask; p.out = out;
   choose_box(d->grid_w, d->grid_h, d->n, 128, 1, &p.TW, &p.TH, &p.TN);
   p.tiles_x = sg_div_up(d->grid_w, p.TW); p.tiles_y = sg_div_up(d->grid_h, p.TH); p.tiles_n = sg_div_up(d->n, p.TN);
+  const int nkb_total = d->ntaps * (d->c_in / KC) + (d2 ? d2->c_in / KC : 0);
+  int best_split = 1;
   {
-    // N tile: the widest tile has the best operand reuse, but with a static persistent schedule a launch costs
-    // ceil(tiles / #SMs) tile-times, so narrower tiles win when the wide ones leave the last wave mostly empty
-    // (e.g. D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs).  Relative tile times from tools/bench_conv.py on B200: the main loop is operand-load bound, so a 128-column
-    // tile costs ~0.85 of a 256-column one (D.B4.conv1: 127 us with 256 columns vs 164 us with 128).
+    // N tile and tail split.  With a static persistent schedule a launch costs ceil(tiles / #SMs) tile-times, so a launch whose
+    // last wave is mostly empty (D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs = 2 waves for 1.16 waves of work)
+    // runs at half speed.  Two remedies, costed together: a narrower N tile (relative tile times from tools/bench_conv.py on
+    // B200: the main loop is operand-load bound, a 128-column tile costs ~0.85 of a 256-column one), and splitting the k-range of
+    // the tiles of the last, partial wave over `split` CTAs each (tc_split_plan).
     const int cand[4] = {256, 128, 64, 32};
     const double rel[4] = {1.0, 0.85, 0.75, 0.7};
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
@@ -1157,8 +1271,9 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
       if (d->c_out % cand[i]) continue;
       if (b_mode == 2 && cand[i] < 64) continue;
       long long tiles = m_tiles * (d->c_out / cand[i]);
-      double cost = (double)((tiles + ctx->num_sms - 1) / ctx->num_sms) * rel[i];
-      if (best < 0 || cost < best * 0.97) { best = cost; p.BN = cand[i]; }
+      int split = 1;
+      double cost = tc_split_plan(tiles, ctx->num_sms, nkb_total, cand[i], ctx->conv_split_tail, &split) * rel[i];
+      if (best < 0 || cost < best * 0.97) { best = cost; p.BN = cand[i]; best_split = split; }
     }
   }
   p.tiles_col = d->c_out / p.BN;
@@ -1222,7 +1337,12 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   if (rc != SG_OK) return rc;
 
   long long total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
-  int grid = (int)(total_tiles < ctx->num_sms ? total_tiles : ctx->num_sms);
+  p.split = best_split;
+  p.t_full = (int)(best_split > 1 ? total_tiles / ctx->num_sms * ctx->num_sms : total_tiles);
+  p.total_units = (int)(p.t_full + (total_tiles - p.t_full) * p.split);
+  p.part = ctx->det_scratch;
+  p.cnt = ctx->det_tickets;
+  int grid = p.total_units < ctx->num_sms ? p.total_units : ctx->num_sms;
   size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024 + TC_EPI_STAGING;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

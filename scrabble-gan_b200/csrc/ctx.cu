@@ -37,6 +37,10 @@ int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->encode_tiled = nullptr;
   c->launches = 0;
+  {
+    const char* e = getenv("SGAN_NO_SPLIT_TAIL");
+    c->conv_split_tail = !(e && e[0] == '1');
+  }
   // the ONE device allocation libsgan makes: the fixed workspace of the deterministic reductions (common.cuh)
   cudaError_t e1 = cudaMalloc((void**)&c->det_scratch, SG_DET_SCRATCH_BYTES);
   cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void**)&c->det_tickets, SG_DET_TICKETS * sizeof(unsigned int)) : e1;
@@ -85,6 +89,12 @@ int sg_zero(sg_ctx* ctx, void* ptr, size_t bytes) {
 int sg_ctx_set_speed_mode(sg_ctx* ctx, int on) {
   SG_REQUIRE(ctx != nullptr, "ctx is NULL");
   ctx->speed_mode = on ? 1 : 0;
+  return SG_OK;
+}
+
+int sg_ctx_set_conv_split_tail(sg_ctx* ctx, int on) {
+  SG_REQUIRE(ctx != nullptr, "ctx is NULL");
+  ctx->conv_split_tail = on ? 1 : 0;
   return SG_OK;
 }
 

@@ -153,9 +153,43 @@ def direct_ok(rt: Runtime, d: ConvDesc, force: bool = False) -> bool:
     return force or d.w_ci_stride == 1 or rt.direct_nmajor
 
 
+class _Traced:
+    """Diagnostics (tools/trace_step.py): with rt.trace a list, every convolution launch is bracketed by CUDA events and
+    recorded as (role, desc summary, start event, end event).  rt.trace is None in normal operation (one attribute test)."""
+
+    def __init__(self, rt, role, d, d2=None):
+        self.rt, self.role, self.d, self.d2 = rt, role, d, d2
+
+    def __enter__(self):
+        if self.rt.trace is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.rt.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.rt.trace is not None:
+            self.e1.record(torch.cuda.current_stream(self.rt.device))
+            d = self.d
+            k = d.ntaps * d.c_in + (self.d2.ntaps * self.d2.c_in if self.d2 is not None else 0)
+            self.rt.trace.append((self.role, dict(n=d.n, in_hw=(d.in_h, d.in_w), grid_hw=(d.grid_h, d.grid_w), ci=d.c_in, co=d.c_out, taps=d.ntaps,
+                                                  m=d.n * d.grid_h * d.grid_w, k=k, stride=(d.out_sy, d.out_sx), in_stride=(d.in_sy, d.in_sx),
+                                                  relu=d.relu, acc=d.accumulate), self.e0, self.e1))
+        return False
+
+
 def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w_mirror=None) -> None:
     """Launch the conv described by d on the tensor-core path when possible, else the fp32 direct path.  `w_mirror`:
     bf16 mirror of w_master (same layout) for the pack-free tensor-core launch."""
+    if rt.trace is not None:
+        role = "tc_direct" if w_mirror is not None else ("tc" if (w_packed is not None and tc_ok(rt, d)) else "simt")
+        with _Traced(rt, role, d):
+            _conv_run(rt, d, x, w_master, w_packed, bias, mask, out, w_mirror)
+        return
+    _conv_run(rt, d, x, w_master, w_packed, bias, mask, out, w_mirror)
+
+
+def _conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w_mirror=None) -> None:
     if w_mirror is not None:
         call.sg_conv_fwd_tc_direct(rt.ctx, C.byref(d), _p(x), _p(w_mirror), _p(bias), _p(mask), _p(out))
     elif w_packed is not None and tc_ok(rt, d):
@@ -166,10 +200,18 @@ def conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, w
 
 def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_packed2, bias, mask, out) -> None:
     """Main conv + 1x1 shortcut conv accumulated in ONE tensor-core launch (both filters packed)."""
-    call.sg_conv_fwd_tc_dual(rt.ctx, C.byref(d), _p(x), _p(w_packed), C.byref(d2), _p(x2), _p(w_packed2), _p(bias), _p(mask), _p(out))
+    with _Traced(rt, "tc_dual", d, d2):
+        call.sg_conv_fwd_tc_dual(rt.ctx, C.byref(d), _p(x), _p(w_packed), C.byref(d2), _p(x2), _p(w_packed2), _p(bias), _p(mask), _p(out))
 
 
 def conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False, db=None, db2=None, force_bias: bool = False) -> bool:
+    if rt.trace is not None:
+        with _Traced(rt, "wgrad", d):
+            return _conv_wgrad(rt, d, x, dy, dw_master, force_simt, db, db2, force_bias)
+    return _conv_wgrad(rt, d, x, dy, dw_master, force_simt, db, db2, force_bias)
+
+
+def _conv_wgrad(rt: Runtime, d: ConvDesc, x, dy, dw_master, force_simt: bool = False, db=None, db2=None, force_bias: bool = False) -> bool:
     """dw_master += filter gradient of the conv described by d: on the tensor cores whenever the layer is eligible and both
     operands have the mode's operand dtype (bf16, or fp32 read as tf32 in "tf32" mode); the FFMA kernel serves the edge
     layers (Cin = 1 / Cout = 1) and the exact "fp32" mode -- by rule, not as a silent fallback.

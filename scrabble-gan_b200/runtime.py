@@ -68,6 +68,7 @@ class Runtime:
         self.fuse_bias_grad = os.environ.get("SGAN_NO_FUSED_BIAS_GRAD", "0") != "1"
         # the generator's 12 conditional-batch-norm Dense layers (and their filter gradients) as one grouped launch each
         self.group_cbn_dense = os.environ.get("SGAN_NO_GROUPED_CBN", "0") != "1"
+        self.trace = None                       # diagnostics: a list makes ops.conv_* record (role, shape, events) per launch
         # one packing launch per network and step instead of one per layer
         self.batch_packs = os.environ.get("SGAN_NO_BATCHED_PACKS", "0") != "1"
         call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))

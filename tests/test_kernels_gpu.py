@@ -192,6 +192,50 @@ def test_conv_tc_fwd_dgrad_wgrad(rt, case, mode):
         rt.set_mode("fp32")
 
 
+@pytest.mark.parametrize("case", [(128, 4, 10, 1024, 1024, 3), (64, 4, 10, 1024, 1024, 3), (64, 8, 20, 1024, 512, 3), (2, 4, 10, 1024, 1024, 3),
+                                  (128, 4, 10, 1024, 1024, 1)])
+def test_conv_tc_split_tail(rt, case):
+    """Wave quantisation: the tiles of a partial last wave are split along k over several CTAs (sg_ctx_set_conv_split_tail).
+    Same result as the unsplit launch up to the fp32 summation order, bit-identical run to run, and the rendezvous counters are
+    re-armed (the launch can be repeated)."""
+    n, h, w, ci, co, k = case
+    rt.set_mode("bf16")
+    try:
+        g = torch.Generator().manual_seed(11)
+        x = dev(rt, rnd(g, n, h, w, ci), BF16)
+        wt = dev(rt, rnd(g, k, k, ci, co) * (1.0 / (k * k * ci) ** 0.5))
+        b = dev(rt, rnd(g, co))
+        m = dev(rt, rnd(g, n, h, w, co), BF16)
+        outs = {}
+        for split in (0, 1):
+            ops.call.sg_ctx_set_conv_split_tail(rt.ctx, split)
+            res = []
+            for rep in range(3):
+                d = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", in_dt=BF16)
+                wp = ops.pack_weights(rt, d, wt)
+                out = rt.empty((n, h, w, co))
+                ops.conv_run(rt, d, x, wt, wp, b, None, out)
+                d2 = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", in_dt=BF16, out_dt=BF16, relu=1, mask_dt=BF16)
+                out2 = rt.empty((n, h, w, co), BF16)
+                ops.conv_run(rt, d2, x, wt, wp, b, m, out2)
+                dd = ops.desc_conv_dgrad(n, h, w, co, ci, k, k, "same", in_dt=BF16) if ci == co else None
+                out3 = None
+                if dd is not None:
+                    out3 = rt.empty((n, h, w, ci))
+                    ops.conv_run(rt, dd, x, wt, None, None, None, out3, w_mirror=wt.to(torch.bfloat16))
+                res.append((out, out2, out3))
+            for r in res[1:]:
+                for a, b_ in zip(res[0], r):
+                    assert a is None or torch.equal(a, b_), "split-tail launches must be bit-reproducible"
+            outs[split] = res[0]
+        for a, b_ in zip(outs[0], outs[1]):
+            if a is not None:
+                assert rel_err(b_, a) <= (2e-5 if a.dtype == torch.float32 else 1e-2), "split and unsplit launches differ"
+    finally:
+        ops.call.sg_ctx_set_conv_split_tail(rt.ctx, 1)
+        rt.set_mode("fp32")
+
+
 @pytest.mark.parametrize("mode", ["bf16", "tf32"])
 @pytest.mark.parametrize("case", [(3, 8, 20, 128, 256, 64), (2, 4, 10, 256, 512, 512), (4, 16, 40, 64, 64, 64)])
 def test_conv_tc_with_fused_shortcut(rt, case, mode):
