@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_fwd(const float* __restrict
                                                           const float* __restrict__ g, int Q, int KV,
                                                           float* __restrict__ o, float* __restrict__ lse, int kv_w,
                                                           const int* __restrict__ kv_cols) {
+  sg_pdl_prologue();
   // ragged batches: kv_cols[n] (may be NULL) = number of valid key COLUMNS of image n; key j sits in column j % kv_w
   __shared__ __align__(16) float ks[128 * AT_DK];
   __shared__ __align__(16) float vs[128 * AT_DV];
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_bwd_q(const float* __restri
                                                             const float* __restrict__ g, const float* __restrict__ o,
                                                             const float* __restrict__ lse, const float* __restrict__ d_o,
                                                             int Q, int KV, float* __restrict__ dtheta) {
+  sg_pdl_prologue();
   __shared__ __align__(16) float ks[128 * AT_DK];
   __shared__ __align__(16) float vs[128 * AT_DV];
   const int n = blockIdx.y;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_bwd_kv(const float* __restr
                                                              const float* __restrict__ lse, const float* __restrict__ d_o,
                                                              int Q, int KV, int q_per_split, float* __restrict__ dphi,
                                                              float* __restrict__ dg, unsigned int* __restrict__ sems) {
+  sg_pdl_prologue();
   __shared__ __align__(16) float qs[AT_QT * AT_DK];
   __shared__ __align__(16) float dos[AT_QT * AT_DV];
   __shared__ float ls[AT_QT], Ds[AT_QT];
@@ -254,7 +257,7 @@ int sg_attn_fwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
   SG_REQUIRE(q > 0 && kv > 0 && n >= 0, "sg_attn_fwd: bad sizes");
   if (n == 0) return SG_OK;
   dim3 grid(sg_div_up(q, AT_THREADS), n);
-  k_attn_fwd<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, q, kv, o, lse, kv, nullptr);
+  sg_launch(ctx, k_attn_fwd, grid, AT_THREADS, 0, theta, phi, g, q, kv, o, lse, kv, nullptr);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -267,7 +270,7 @@ int sg_attn_fwd_masked(sg_ctx* ctx, const float* theta, const float* phi, const 
   SG_REQUIRE(q > 0 && kv > 0 && n >= 0 && kv_w > 0 && kv % kv_w == 0, "sg_attn_fwd_masked: bad sizes");
   if (n == 0) return SG_OK;
   dim3 grid(sg_div_up(q, AT_THREADS), n);
-  k_attn_fwd<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, q, kv, o, lse, kv_w, kv_cols);
+  sg_launch(ctx, k_attn_fwd, grid, AT_THREADS, 0, theta, phi, g, q, kv, o, lse, kv_w, kv_cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -279,7 +282,7 @@ int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
   SG_REQUIRE(q > 0 && kv > 0 && n >= 0, "sg_attn_bwd: bad sizes");
   if (n == 0) return SG_OK;
   dim3 grid(sg_div_up(q, AT_THREADS), n);
-  k_attn_bwd_q<<<grid, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, o, lse, d_o, q, kv, dtheta);
+  sg_launch(ctx, k_attn_bwd_q, grid, AT_THREADS, 0, theta, phi, g, o, lse, d_o, q, kv, dtheta);
   SG_POST_LAUNCH(ctx);
   SG_CHECK_CUDA(cudaMemsetAsync(dphi, 0, sizeof(float) * (size_t)n * kv * AT_DK, ctx->stream));
   SG_CHECK_CUDA(cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)n * kv * AT_DV, ctx->stream));
@@ -292,7 +295,7 @@ int sg_attn_bwd(sg_ctx* ctx, const float* theta, const float* phi, const float* 
   int qps = sg_div_up(sg_div_up(q, splits), AT_QT) * AT_QT;
   splits = sg_div_up(q, qps);
   dim3 g2(kblocks, n, splits);
-  k_attn_bwd_kv<<<g2, AT_THREADS, 0, ctx->stream>>>(theta, phi, g, o, lse, d_o, q, kv, qps, dphi, dg, ctx->det_tickets);
+  sg_launch(ctx, k_attn_bwd_kv, g2, AT_THREADS, 0, theta, phi, g, o, lse, d_o, q, kv, qps, dphi, dg, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -60,6 +60,7 @@ static inline int atc_pad(int n) { return (n + 63) / 64 * 64 + 8; }
 // D[row] = sum_j dO[row,j] * O[row,j]   (32 columns); 8 threads per row
 __global__ void __launch_bounds__(256) k_attn_rowdot(const float* __restrict__ d_o, const float* __restrict__ o, long long rows,
                                                       float* __restrict__ D) {
+  sg_pdl_prologue();
   long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   long long row = i >> 3;
   int sub = (int)(i & 7);
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(ATC_THREADS) k_attn_fwd_tc(const float* __rest
                                                               const float* __restrict__ gv, int Q, int KV, int KVp,
                                                               float* __restrict__ o, float* __restrict__ lse, int kv_w,
                                                               const int* __restrict__ kv_cols) {
+  sg_pdl_prologue();
   // ragged batches: kv_cols[n] (may be NULL) = valid key COLUMNS of image n; key j sits in column j % kv_w
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt = reinterpret_cast<uint32_t*>(smem);                         // [8][KVp]  tf32
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(ATC_THREADS) k_attn_bwd_q_tc(const float* __re
                                                                 const float* __restrict__ gv, const float* __restrict__ lse,
                                                                 const float* __restrict__ d_o, const float* __restrict__ Dv, int Q,
                                                                 int KV, int KVp, float* __restrict__ dtheta) {
+  sg_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt = reinterpret_cast<uint32_t*>(smem);                               // [8][KVp] tf32
   __nv_bfloat16* Ktb = reinterpret_cast<__nv_bfloat16*>(Kt + ATC_DK * KVp);       // [8][KVp] bf16
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(ATC_THREADS) k_attn_bwd_kv_tc(const float* __r
                                                                  const float* __restrict__ gv, const float* __restrict__ lse,
                                                                  const float* __restrict__ d_o, const float* __restrict__ Dv, int Q,
                                                                  int KV, float* __restrict__ dphi, float* __restrict__ dg) {
+  sg_pdl_prologue();
   __shared__ uint32_t Qt[ATC_DK * ATC_QP];
   __shared__ __align__(16) __nv_bfloat16 Qtb[ATC_DK * ATC_QP];
   __shared__ __align__(16) __nv_bfloat16 dOs[ATC_QC * ATC_VROW];
@@ -413,7 +417,7 @@ int sg_attn_fwd_tc(sg_ctx* ctx, const float* theta, const float* phi, const floa
   size_t smem = (size_t)ATC_DK * kvp * 4 + (size_t)ATC_DV * kvp * 2;
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(sg_div_up(q, ATC_ROWS), n);
-  k_attn_fwd_tc<<<grid, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, q, kv, kvp, o, lse, kv, nullptr);
+  sg_launch(ctx, k_attn_fwd_tc, grid, ATC_THREADS, smem, theta, phi, g, q, kv, kvp, o, lse, kv, nullptr);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -427,7 +431,7 @@ int sg_attn_fwd_tc_masked(sg_ctx* ctx, const float* theta, const float* phi, con
   size_t smem = (size_t)ATC_DK * kvp * 4 + (size_t)ATC_DV * kvp * 2;
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(sg_div_up(q, ATC_ROWS), n);
-  k_attn_fwd_tc<<<grid, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, q, kv, kvp, o, lse, kv_w, kv_cols);
+  sg_launch(ctx, k_attn_fwd_tc, grid, ATC_THREADS, smem, theta, phi, g, q, kv, kvp, o, lse, kv_w, kv_cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -439,16 +443,16 @@ int sg_attn_bwd_tc(sg_ctx* ctx, const float* theta, const float* phi, const floa
   SG_REQUIRE(sg_attn_tc_supported(q, kv, dk, dv), "sg_attn_bwd_tc: unsupported sizes q=%d kv=%d dk=%d dv=%d", q, kv, dk, dv);
   if (n == 0) return SG_OK;
   long long rows = (long long)n * q;
-  k_attn_rowdot<<<sg_div_up(rows * 8, 256), 256, 0, ctx->stream>>>(d_o, o, rows, scratch);
+  sg_launch(ctx, k_attn_rowdot, sg_div_up(rows * 8, 256), 256, 0, d_o, o, rows, scratch);
   SG_POST_LAUNCH(ctx);
   int kvp = atc_pad(kv), kvr = (kv + 15) & ~15;
   size_t smem = (size_t)ATC_DK * kvp * 4 + (size_t)ATC_DK * kvp * 2 + (size_t)kvr * ATC_VROW * 2;
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_attn_bwd_q_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 gq(sg_div_up(q, ATC_ROWS), n);
-  k_attn_bwd_q_tc<<<gq, ATC_THREADS, smem, ctx->stream>>>(theta, phi, g, lse, d_o, scratch, q, kv, kvp, dtheta);
+  sg_launch(ctx, k_attn_bwd_q_tc, gq, ATC_THREADS, smem, theta, phi, g, lse, d_o, scratch, q, kv, kvp, dtheta);
   SG_POST_LAUNCH(ctx);
   dim3 gk(sg_div_up(kv, ATC_ROWS), n);
-  k_attn_bwd_kv_tc<<<gk, ATC_THREADS, 0, ctx->stream>>>(theta, phi, g, lse, d_o, scratch, q, kv, dphi, dg);
+  sg_launch(ctx, k_attn_bwd_kv_tc, gk, ATC_THREADS, 0, theta, phi, g, lse, d_o, scratch, q, kv, dphi, dg);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

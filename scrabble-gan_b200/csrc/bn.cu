@@ -19,6 +19,7 @@ static inline BnLayout bn_layout(int c) {
 
 __global__ void k_bn_stats(const float* __restrict__ x, long long rows, int c, int tc, int lanes,
                            long long rows_per_block, float* __restrict__ partial) {
+  sg_pdl_prologue();
   extern __shared__ float sm[];     // [lanes][2*c]
   int q = threadIdx.x % tc, lane = threadIdx.x / tc;
   long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -47,6 +48,7 @@ __global__ void k_bn_stats(const float* __restrict__ x, long long rows, int c, i
 // slices combined through shared memory -- the serial chain per thread is nblocks/16 loads instead of nblocks.
 __global__ void __launch_bounds__(512) k_bn_stats_reduce(const float* __restrict__ partial, int nblocks, int c2,
                                                           float* __restrict__ sums) {
+  sg_pdl_prologue();
   __shared__ double sm[16][33];
   const int jx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + jx;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(512) k_bn_stats_reduce(const float* __restrict
 __global__ void k_bn_finalize(const float* __restrict__ sums, double count, int c, float eps, float momentum,
                               float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ mm,
                               float* __restrict__ mv) {
+  sg_pdl_prologue();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= c) return;
   double m = (double)sums[j] / count;
@@ -81,6 +84,7 @@ __global__ void k_bn_finalize(const float* __restrict__ sums, double count, int 
 
 __global__ void k_bn_infer_prepare(const float* __restrict__ mm, const float* __restrict__ mv, int c, float eps,
                                    float* __restrict__ mean, float* __restrict__ rstd) {
+  sg_pdl_prologue();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= c) return;
   mean[j] = mm[j];
@@ -92,6 +96,7 @@ __global__ void k_bn_apply(const float* __restrict__ x, long long total4, long l
                            const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, long long gb_stride,
                            int relu, TO* __restrict__ out) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     int q = (int)(i % c4);
@@ -112,6 +117,7 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restri
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                 float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ scratch,
                                 unsigned int* __restrict__ tickets) {
+  sg_pdl_prologue();
   extern __shared__ float sm[];     // [lanes][2*c]
   int ni = blockIdx.y;
   int q = threadIdx.x % tc, lane = threadIdx.x / tc;
@@ -162,6 +168,7 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const TA* __restri
 __global__ void __launch_bounds__(256) k_bn_bwd_combine(const float* __restrict__ s1, const float* __restrict__ s2,
                                                          const float* __restrict__ gamma, long long gb_stride, int n, int c,
                                                          float* __restrict__ ab) {
+  sg_pdl_prologue();
   __shared__ float sa[8][33], sb[8][33];
   const int jx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + jx;
@@ -189,6 +196,7 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ dy, const TA* __restric
                                const float* __restrict__ rstd, const float* __restrict__ gamma, long long gb_stride,
                                const float* __restrict__ ab, float inv_count, int use_batch, int mask_by_x,
                                TO* __restrict__ dx, int accumulate) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   int c = 4 * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
@@ -250,9 +258,9 @@ int sg_bn_stats(sg_ctx* ctx, const float* x, long long rows, int c, float* sums,
   long long rpb = (rows + blocks - 1) / blocks;
   blocks = (rows + rpb - 1) / rpb;
   size_t smem = (size_t)l.lanes * 2 * c * sizeof(float);
-  k_bn_stats<<<(int)blocks, 256, smem, ctx->stream>>>(x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
+  sg_launch(ctx, k_bn_stats, (int)blocks, 256, smem, x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
   SG_POST_LAUNCH(ctx);
-  k_bn_stats_reduce<<<sg_div_up(2 * c, 32), 512, 0, ctx->stream>>>((const float*)scratch, (int)blocks, 2 * c, sums);
+  sg_launch(ctx, k_bn_stats_reduce, sg_div_up(2 * c, 32), 512, 0, (const float*)scratch, (int)blocks, 2 * c, sums);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -271,7 +279,7 @@ int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void
   blocks = (rows + rpb - 1) / rpb;
   SG_REQUIRE(scratch_bytes >= (size_t)blocks * 2 * c * sizeof(float), "sg_bn_stats_partial: scratch too small");
   size_t smem = (size_t)l.lanes * 2 * c * sizeof(float);
-  k_bn_stats<<<(int)blocks, 256, smem, ctx->stream>>>(x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
+  sg_launch(ctx, k_bn_stats, (int)blocks, 256, smem, x, rows, c, l.tc, l.lanes, rpb, (float*)scratch);
   SG_POST_LAUNCH(ctx);
   *nblocks_out = (int)blocks;
   return SG_OK;
@@ -280,7 +288,7 @@ int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void
 int sg_bn_finalize(sg_ctx* ctx, const float* sums, double count, int c, float eps, float momentum, float* mean,
                    float* rstd, float* moving_mean, float* moving_var) {
   SG_REQUIRE(ctx && sums && mean && rstd && count > 0 && c > 0, "sg_bn_finalize: bad args");
-  k_bn_finalize<<<sg_div_up(c, 128), 128, 0, ctx->stream>>>(sums, count, c, eps, momentum, mean, rstd, moving_mean, moving_var);
+  sg_launch(ctx, k_bn_finalize, sg_div_up(c, 128), 128, 0, sums, count, c, eps, momentum, mean, rstd, moving_mean, moving_var);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -288,7 +296,7 @@ int sg_bn_finalize(sg_ctx* ctx, const float* sums, double count, int c, float ep
 int sg_bn_infer_prepare(sg_ctx* ctx, const float* moving_mean, const float* moving_var, int c, float eps, float* mean,
                         float* rstd) {
   SG_REQUIRE(ctx && moving_mean && moving_var && mean && rstd && c > 0, "sg_bn_infer_prepare: bad args");
-  k_bn_infer_prepare<<<sg_div_up(c, 128), 128, 0, ctx->stream>>>(moving_mean, moving_var, c, eps, mean, rstd);
+  sg_launch(ctx, k_bn_infer_prepare, sg_div_up(c, 128), 128, 0, moving_mean, moving_var, c, eps, mean, rstd);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -300,7 +308,7 @@ int sg_bn_apply(sg_ctx* ctx, const float* x, int n, long long hw, int c, const f
   long long total4 = (long long)n * hw * (c / 4);
   if (total4 == 0) return SG_OK;
   SG_DISPATCH_DT(out_dt, TO,
-                 k_bn_apply<TO><<<bn_grid(ctx, total4), 256, 0, ctx->stream>>>(x, total4, hw, c / 4, mean, rstd, gamma, beta,
+                 sg_launch(ctx, k_bn_apply<TO>, bn_grid(ctx, total4), 256, 0, x, total4, hw, c / 4, mean, rstd, gamma, beta,
                                                                                gb_stride, relu, (TO*)out));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -330,10 +338,10 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
   dim3 grid((unsigned)blocks, (unsigned)n);
   if (act) {
     SG_DISPATCH_DT(act_dt, TA,
-                   k_bn_bwd_reduce<TA><<<grid, 256, smem, ctx->stream>>>(dy, (const TA*)act, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2,
+                   sg_launch(ctx, k_bn_bwd_reduce<TA>, grid, 256, smem, dy, (const TA*)act, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2,
                                                                          ctx->det_scratch, ctx->det_tickets));
   } else {
-    k_bn_bwd_reduce<float><<<grid, 256, smem, ctx->stream>>>(dy, nullptr, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2, ctx->det_scratch,
+    sg_launch(ctx, k_bn_bwd_reduce<float>, grid, 256, smem, dy, nullptr, x, hw, c, l.tc, l.lanes, rpb, mean, rstd, s1, s2, ctx->det_scratch,
                                                              ctx->det_tickets);
   }
   SG_POST_LAUNCH(ctx);
@@ -343,7 +351,7 @@ int sg_bn_bwd_reduce(sg_ctx* ctx, const float* dy, const void* act, int act_dt, 
 int sg_bn_bwd_combine(sg_ctx* ctx, const float* s1, const float* s2, const float* gamma, long long gb_stride, int n,
                       int c, float* ab) {
   SG_REQUIRE(ctx && s1 && s2 && ab && c > 0, "sg_bn_bwd_combine: bad args");
-  k_bn_bwd_combine<<<sg_div_up(c, 32), 256, 0, ctx->stream>>>(s1, s2, gamma, gb_stride, n, c, ab);
+  sg_launch(ctx, k_bn_bwd_combine, sg_div_up(c, 32), 256, 0, s1, s2, gamma, gb_stride, n, c, ab);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -363,11 +371,11 @@ int sg_bn_bwd_apply(sg_ctx* ctx, const float* dy, const void* act, int act_dt, c
   if (act) {
     SG_DISPATCH_DT(act_dt, TA,
                    SG_DISPATCH_DT(dx_dt, TO,
-                                  k_bn_bwd_apply<TA, TO><<<grid, 256, 0, ctx->stream>>>(dy, (const TA*)act, x, total4, hw, c / 4, mean, rstd, gamma,
+                                  sg_launch(ctx, k_bn_bwd_apply<TA, TO>, grid, 256, 0, dy, (const TA*)act, x, total4, hw, c / 4, mean, rstd, gamma,
                                                                                         gb_stride, ab, inv, use_batch_terms, mask_by_x, (TO*)dx, accumulate)));
   } else {
     SG_DISPATCH_DT(dx_dt, TO,
-                   k_bn_bwd_apply<float, TO><<<grid, 256, 0, ctx->stream>>>(dy, nullptr, x, total4, hw, c / 4, mean, rstd, gamma, gb_stride,
+                   sg_launch(ctx, k_bn_bwd_apply<float, TO>, grid, 256, 0, dy, nullptr, x, total4, hw, c / 4, mean, rstd, gamma, gb_stride,
                                                                             ab, inv, use_batch_terms, mask_by_x, (TO*)dx, accumulate));
   }
   SG_POST_LAUNCH(ctx);

@@ -26,6 +26,7 @@ template <int TN, int RN>
 __global__ void __launch_bounds__(256) k_conv_fwd_simt(sg_conv_desc d, const void* __restrict__ in,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         const void* __restrict__ mask, void* __restrict__ out) {
+  sg_pdl_prologue();
   __shared__ float As[CS_TK][CS_TM + 4];
   __shared__ float Bs[CS_TK][TN + 4];
   constexpr int TX = TN / RN;                  // threads along N (16)
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(sg_conv_desc d, const voi
 __global__ void __launch_bounds__(256) k_conv_wgrad_simt(sg_conv_desc d, const void* __restrict__ in,
                                                           const void* __restrict__ dy, float* __restrict__ dw,
                                                           long long pos_per_split, unsigned int* __restrict__ sems) {
+  sg_pdl_prologue();
   __shared__ float As[CS_TK][CS_TM + 4];   // [pos][kflat]
   __shared__ float Bs[CS_TK][64 + 4];      // [pos][co]
   const int tid = threadIdx.x;
@@ -253,6 +255,7 @@ template <bool NARROW_IN>
 __global__ void __launch_bounds__(256) k_wgrad_narrow(sg_conv_desc d, const void* __restrict__ in, const void* __restrict__ dy,
                                                        float* __restrict__ dw, long long pos_per_block, float* __restrict__ scratch,
                                                        unsigned int* __restrict__ ticket) {
+  sg_pdl_prologue();
   extern __shared__ float red[];                       // [lanes][ntaps][wide]
   const int wide = NARROW_IN ? d.c_out : d.c_in;
   const int lanes = 256 / wide;
@@ -315,6 +318,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(256, 4) k_conv_fwd_cout1(sg_conv_desc d, const TIn* __restrict__ in, const float* __restrict__ w,
                                                             const float* __restrict__ bias, const void* __restrict__ mask,
                                                             void* __restrict__ out) {
+  sg_pdl_prologue();
   // the ntaps x c_in filter lives in shared memory (2 broadcast LDS.128 per tap) instead of 72 registers per thread:
   // 4 blocks per SM instead of 2, which is what hides the load latency of this streaming kernel
   __shared__ __align__(16) float ws[9][256];
@@ -383,6 +387,7 @@ __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ w
                                                          int n, int H, int W, int nH, int nW, int ntaps, sg_conv_desc d,
                                                          int sign, float* __restrict__ dw, long long chunks_per_block,
                                                          int narrow_in, float* __restrict__ scratch, unsigned int* __restrict__ ticket) {
+  sg_pdl_prologue();
   __shared__ float Bs[WN_PIX][64];
   __shared__ __align__(16) float As[9][WN_PIX];
   const int tid = threadIdx.x;
@@ -450,6 +455,7 @@ __global__ void __launch_bounds__(192) k_wgrad_narrow64(const TW* __restrict__ w
 template <typename TOut, int CH>
 __global__ void __launch_bounds__(256, 4) k_conv_fwd_cin1(sg_conv_desc d, const float* __restrict__ in, const float* __restrict__ w,
                                                            const float* __restrict__ bias, TOut* __restrict__ out) {
+  sg_pdl_prologue();
   // CH output channels per thread: the 3x3 input patch is loaded ONCE per (pixel, CH channels) and reused for CH/8 chunks
   // of 8 channels (this kernel is instruction bound: with CH = 8 the nine patch loads and their bounds checks were
   // repeated for every 8 channels)
@@ -544,9 +550,9 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
       long long need = (long long)d->n * d->grid_h, cap = (long long)ctx->num_sms * 8;   // one image row per block iteration
       int grid = (int)(need < cap ? need : cap);
       if (d->in_dt == SG_F32)
-        k_conv_fwd_cout1<float><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, mask, out);
+        sg_launch(ctx, k_conv_fwd_cout1<float>, grid, 256, 0, *d, (const float*)in, w_master, bias, mask, out);
       else
-        k_conv_fwd_cout1<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(*d, (const __nv_bfloat16*)in, w_master, bias, mask, out);
+        sg_launch(ctx, k_conv_fwd_cout1<__nv_bfloat16>, grid, 256, 0, *d, (const __nv_bfloat16*)in, w_master, bias, mask, out);
       SG_POST_LAUNCH(ctx);
       return SG_OK;
     }
@@ -561,11 +567,11 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
       long long need = (M + ppb - 1) / ppb, cap = (long long)ctx->num_sms * 10;
       int grid = (int)(need < cap ? need : cap);
       if (wide) {
-        if (d->out_dt == SG_F32) k_conv_fwd_cin1<float, 32><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
-        else k_conv_fwd_cin1<__nv_bfloat16, 32><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+        if (d->out_dt == SG_F32) sg_launch(ctx, k_conv_fwd_cin1<float, 32>, grid, 256, 0, *d, (const float*)in, w_master, bias, (float*)out);
+        else sg_launch(ctx, k_conv_fwd_cin1<__nv_bfloat16, 32>, grid, 256, 0, *d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
       } else {
-        if (d->out_dt == SG_F32) k_conv_fwd_cin1<float, 8><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (float*)out);
-        else k_conv_fwd_cin1<__nv_bfloat16, 8><<<grid, 256, 0, ctx->stream>>>(*d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+        if (d->out_dt == SG_F32) sg_launch(ctx, k_conv_fwd_cin1<float, 8>, grid, 256, 0, *d, (const float*)in, w_master, bias, (float*)out);
+        else sg_launch(ctx, k_conv_fwd_cin1<__nv_bfloat16, 8>, grid, 256, 0, *d, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
       }
       SG_POST_LAUNCH(ctx);
       return SG_OK;
@@ -573,10 +579,10 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
   }
   if (d->c_out > 16) {
     dim3 grid(sg_div_up(M, CS_TM), sg_div_up(d->c_out, 64));
-    k_conv_fwd_simt<64, 4><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
+    sg_launch(ctx, k_conv_fwd_simt<64, 4>, grid, 256, 0, *d, in, w_master, bias, mask, out);
   } else {
     dim3 grid(sg_div_up(M, CS_TM), 1);
-    k_conv_fwd_simt<16, 1><<<grid, 256, 0, ctx->stream>>>(*d, in, w_master, bias, mask, out);
+    sg_launch(ctx, k_conv_fwd_simt<16, 1>, grid, 256, 0, *d, in, w_master, bias, mask, out);
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -609,11 +615,11 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
         long long cpb = (nchunks + blocks - 1) / blocks;
         blocks = (nchunks + cpb - 1) / cpb;
         if (wide_dt == SG_F32)
-          k_wgrad_narrow64<float><<<(int)blocks, 192, 0, ctx->stream>>>((const float*)wide, nar, nar_dt, d->n, H, W, nH, nW, d->ntaps, *d,
+          sg_launch(ctx, k_wgrad_narrow64<float>, (int)blocks, 192, 0, (const float*)wide, nar, nar_dt, d->n, H, W, nH, nW, d->ntaps, *d,
                                                                        narrow_in ? 1 : -1, dw_master, cpb, narrow_in ? 1 : 0,
                                                                        ctx->det_scratch, ctx->det_tickets);
         else
-          k_wgrad_narrow64<__nv_bfloat16><<<(int)blocks, 192, 0, ctx->stream>>>((const __nv_bfloat16*)wide, nar, nar_dt, d->n, H, W, nH,
+          sg_launch(ctx, k_wgrad_narrow64<__nv_bfloat16>, (int)blocks, 192, 0, (const __nv_bfloat16*)wide, nar, nar_dt, d->n, H, W, nH,
                                                                                nW, d->ntaps, *d, narrow_in ? 1 : -1, dw_master, cpb,
                                                                                narrow_in ? 1 : 0, ctx->det_scratch, ctx->det_tickets);
         SG_POST_LAUNCH(ctx);
@@ -629,8 +635,8 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
       long long ppb = (P + blocks - 1) / blocks;
       blocks = (P + ppb - 1) / ppb;
       size_t smem = sizeof(float) * (size_t)lanes * d->ntaps * wide;
-      if (narrow_in) k_wgrad_narrow<true><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
-      else k_wgrad_narrow<false><<<(int)blocks, 256, smem, ctx->stream>>>(*d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
+      if (narrow_in) sg_launch(ctx, k_wgrad_narrow<true>, (int)blocks, 256, smem, *d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
+      else sg_launch(ctx, k_wgrad_narrow<false>, (int)blocks, 256, smem, *d, in, dy, dw_master, ppb, ctx->det_scratch, ctx->det_tickets);
       SG_POST_LAUNCH(ctx);
       return SG_OK;
     }
@@ -646,7 +652,7 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
   long long pps = ((P + splits - 1) / splits + CS_TK - 1) / CS_TK * CS_TK;
   splits = (P + pps - 1) / pps;
   dim3 grid(gx, gy, (unsigned)splits);
-  k_conv_wgrad_simt<<<grid, 256, 0, ctx->stream>>>(*d, in, dy, dw_master, pps, ctx->det_tickets);
+  sg_launch(ctx, k_conv_wgrad_simt, grid, 256, 0, *d, in, dy, dw_master, pps, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  sg_pdl_prologue();        // barriers, descriptors and TMEM are set up while the preceding kernel drains; global memory from here on
   const uint32_t tmem_base = tmem_slot;
 
   const int nkb = p.ntaps * p.kc_per_tap + p.kc2;
@@ -570,6 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  sg_pdl_prologue();        // barriers, descriptors and TMEM are set up while the preceding kernel drains; global memory from here on
   const uint32_t tmem_base = tmem_slot;
 
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -828,6 +830,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 template <typename TO>
 __global__ void k_pack_weights(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  sg_pdl_prologue();
   const long long ktot = (long long)d.ntaps * d.c_in;
   const long long total = ktot * d.c_out;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -843,6 +846,7 @@ __global__ void k_pack_weights(sg_conv_desc d, const float* __restrict__ w, TO* 
 // two float4 loads -> one 16/32-byte store
 template <typename TO>
 __global__ void __launch_bounds__(256) k_pack_weights_v8(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  sg_pdl_prologue();
   const int c8 = d.c_in / 8;
   const long long total8 = (long long)d.c_out * d.ntaps * c8;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -864,6 +868,7 @@ __global__ void __launch_bounds__(256) k_pack_weights_v8(sg_conv_desc d, const f
 // coalesced.  grid = (ci tiles, co tiles, taps), block = 32 x 8.
 template <typename TO>
 __global__ void __launch_bounds__(256) k_pack_weights_t(sg_conv_desc d, const float* __restrict__ w, TO* __restrict__ out) {
+  sg_pdl_prologue();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -933,6 +938,7 @@ __device__ __forceinline__ void pack_tile_v8(const PackJob& j, int tile) {
   sg_st4(dst + 4, b);
 }
 __global__ void __launch_bounds__(256) k_pack_weights_multi(const __grid_constant__ PackJobs jobs) {
+  sg_pdl_prologue();
   __shared__ float smt[32][33];
   int ji = 0;
   while (ji + 1 < jobs.njobs && (int)blockIdx.x >= jobs.job[ji + 1].tile0) ++ji;
@@ -1115,21 +1121,21 @@ int sg_conv_pack_weights(sg_ctx* ctx, const sg_conv_desc* d, const float* w_mast
   if (total == 0) return SG_OK;
   if (d->w_co_stride == 1 && d->w_ci_stride != 1 && d->c_out >= 32) {
     dim3 grid(sg_div_up(d->c_in, 32), sg_div_up(d->c_out, 32), d->ntaps), block(32, 8);
-    SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights_t<TO><<<grid, block, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+    SG_DISPATCH_DT(d->in_dt, TO, sg_launch(ctx, k_pack_weights_t<TO>, grid, block, 0, *d, w_master, (TO*)w_packed));
   } else if (d->w_ci_stride == 1 && d->c_in % 8 == 0 && d->w_co_stride % 4 == 0 && ((uintptr_t)w_master & 15) == 0) {
     bool taps_ok = true;
     for (int t = 0; t < d->ntaps; ++t) taps_ok = taps_ok && (d->tap_w_off[t] % 4 == 0);
     long long need = (total / 8 + 255) / 256, cap = (long long)ctx->num_sms * 8;
     int grid = (int)(need < cap ? need : cap);
     if (taps_ok) {
-      SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights_v8<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+      SG_DISPATCH_DT(d->in_dt, TO, sg_launch(ctx, k_pack_weights_v8<TO>, grid, 256, 0, *d, w_master, (TO*)w_packed));
     } else {
-      SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+      SG_DISPATCH_DT(d->in_dt, TO, sg_launch(ctx, k_pack_weights<TO>, grid, 256, 0, *d, w_master, (TO*)w_packed));
     }
   } else {
     long long need = (total + 255) / 256, cap = (long long)ctx->num_sms * 8;
     int grid = (int)(need < cap ? need : cap);
-    SG_DISPATCH_DT(d->in_dt, TO, k_pack_weights<TO><<<grid, 256, 0, ctx->stream>>>(*d, w_master, (TO*)w_packed));
+    SG_DISPATCH_DT(d->in_dt, TO, sg_launch(ctx, k_pack_weights<TO>, grid, 256, 0, *d, w_master, (TO*)w_packed));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -1174,7 +1180,7 @@ int sg_conv_pack_weights_multi(sg_ctx* ctx, int njobs, const sg_conv_desc* const
   }
   jobs.total_tiles = tile;
   if (tile == 0) return SG_OK;
-  k_pack_weights_multi<<<tile, 256, 0, ctx->stream>>>(jobs);
+  sg_launch(ctx, k_pack_weights_multi, tile, 256, 0, jobs);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -1346,10 +1352,10 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024 + TC_EPI_STAGING;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<float><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+    sg_launch(ctx, k_conv_tc<float>, grid, TC_THREADS, smem, p);
   } else {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<__nv_bfloat16><<<grid, TC_THREADS, smem, ctx->stream>>>(p);
+    sg_launch(ctx, k_conv_tc<__nv_bfloat16>, grid, TC_THREADS, smem, p);
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -1526,23 +1532,12 @@ static int conv_wgrad_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in
   int grid = (int)(units < ctx->num_sms ? units : ctx->num_sms);
   size_t smem = (size_t)stages * p.stage_stride + 1024 + ones_bytes;
   // det_mode 2 ends in a grid-wide barrier: launched cooperatively, so the runtime guarantees (or refuses) co-residency
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = p.det_mode == 2 ? 1 : 0;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_wgrad_tc<float>, p));
+    SG_CHECK_CUDA(sg_launch_ex(ctx, p.det_mode == 2, k_wgrad_tc<float>, grid, TC_THREADS, smem, p));
   } else {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_wgrad_tc<__nv_bfloat16>, p));
+    SG_CHECK_CUDA(sg_launch_ex(ctx, p.det_mode == 2, k_wgrad_tc<__nv_bfloat16>, grid, TC_THREADS, smem, p));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;

@@ -31,6 +31,7 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 __global__ void k_ctc(const float* __restrict__ logits, const int* __restrict__ labels, int Tmax, int C, int Lmax,
                       const int* __restrict__ input_len, const int* __restrict__ label_len, float* __restrict__ loss,
                       float* __restrict__ grad) {
+  sg_pdl_prologue();
   extern __shared__ float sm[];
   const int b = blockIdx.x;
   int T = input_len ? input_len[b] : Tmax, L = label_len ? label_len[b] : Lmax;
@@ -162,7 +163,7 @@ static int ctc_launch(sg_ctx* ctx, const float* logits, const int* labels, int b
   size_t smem = sizeof(float) * ((size_t)t * c + 2 * (size_t)t * S + c) + sizeof(int) * S;
   SG_REQUIRE(smem <= 200 * 1024, "%s: T*C too large for shared memory (%zu bytes)", who, smem);
   if (smem > 48 * 1024) SG_CHECK_CUDA(cudaFuncSetAttribute(k_ctc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ctc<<<b, 128, smem, ctx->stream>>>(logits, labels, t, c, l, input_len, label_len, loss, grad_logits);
+  sg_launch(ctx, k_ctc, b, 128, smem, logits, labels, t, c, l, input_len, label_len, loss, grad_logits);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

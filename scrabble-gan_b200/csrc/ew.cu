@@ -13,6 +13,7 @@ static inline int ew_grid(sg_ctx* ctx, long long work_items, int threads) {
 template <typename TO>
 __global__ void k_act_prep(const float* __restrict__ x, long long n4, long long n, TO* __restrict__ relu_out,
                            TO* __restrict__ copy_out) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = sg_ld4(x + 4 * i);
@@ -30,6 +31,7 @@ __global__ void k_act_prep(const float* __restrict__ x, long long n4, long long 
 template <typename TA, typename TO>
 __global__ void k_mask_mul(const float* __restrict__ dy, const TA* __restrict__ act, TO* __restrict__ out,
                            long long n4, long long n, int accumulate) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 d = sg_ld4(dy + 4 * i);
@@ -50,6 +52,7 @@ __global__ void k_mask_mul(const float* __restrict__ dy, const TA* __restrict__ 
 
 __global__ void k_axpby(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
                         float* __restrict__ out, long long n4, long long n) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = sg_ld4(x + 4 * i);
@@ -69,6 +72,7 @@ __global__ void k_axpby(float a, const float* __restrict__ x, float b, const flo
 
 __global__ void k_scale_add(const float* __restrict__ sigma, const float* __restrict__ a,
                             const float* __restrict__ x, float* __restrict__ out, long long n4, long long n) {
+  sg_pdl_prologue();
   const float s = *sigma;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -80,11 +84,13 @@ __global__ void k_scale_add(const float* __restrict__ sigma, const float* __rest
 }
 
 __global__ void k_tanh_fwd(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = tanhf(x[i]);
 }
 __global__ void k_tanh_bwd(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
                            long long n) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float t = y[i];
@@ -92,6 +98,7 @@ __global__ void k_tanh_bwd(const float* __restrict__ dy, const float* __restrict
   }
 }
 __global__ void k_scale_rows(float* __restrict__ x, const float* __restrict__ w, int rows, long long cols) {
+  sg_pdl_prologue();
   long long n = (long long)rows * cols;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= w[i / cols];
@@ -100,6 +107,7 @@ __global__ void k_scale_rows(float* __restrict__ x, const float* __restrict__ w,
 // deterministic: per-block partials, summed in block order by the block that arrives last (common.cuh, scheme B)
 __global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, float* out, int accumulate,
                       float* __restrict__ scratch, unsigned int* ticket) {
+  sg_pdl_prologue();
   __shared__ float sm[32];
   float acc = 0.f;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -120,6 +128,7 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
                                                     float* __restrict__ out, int accumulate, float* __restrict__ scratch,
                                                     unsigned int* ticket) {
+  sg_pdl_prologue();
   __shared__ float4 sm[NT];
   const int cgs = cols >> 2;                          // column groups of 4
   const int cg_per_pass = cgs < NT ? cgs : NT;
@@ -172,6 +181,7 @@ __global__ void __launch_bounds__(NT) k_colsum_v4(const T* __restrict__ x, long 
 template <typename T>
 __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long long rows_per_block,
                          float* __restrict__ out, int accumulate, float* __restrict__ scratch, unsigned int* ticket) {
+  sg_pdl_prologue();
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
@@ -186,6 +196,7 @@ __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, long
 
 template <typename TO>
 __global__ void k_cast(const float* __restrict__ x, TO* __restrict__ out, long long n) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) sg_st(out + i, x[i]);
 }
@@ -194,6 +205,7 @@ __global__ void k_cast(const float* __restrict__ x, TO* __restrict__ out, long l
 // pooling (NHWC, c % 4 == 0)
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_avgpool2_fwd(const float* __restrict__ x, int n, int h, int w, int c4, float* __restrict__ out) {
+  sg_pdl_prologue();
   int ho = h / 2, wo = w / 2;
   long long total = (long long)n * ho * wo * c4;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -216,6 +228,7 @@ __global__ void k_avgpool2_fwd(const float* __restrict__ x, int n, int h, int w,
 // math: one division chain per 4 stores instead of per store)
 template <typename TO>
 __global__ void k_avgpool2_bwd(const float* __restrict__ dout, int n, int h, int w, int c4, TO* __restrict__ dx) {
+  sg_pdl_prologue();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * c4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -238,6 +251,7 @@ __global__ void k_avgpool2_bwd(const float* __restrict__ dout, int n, int h, int
 template <typename T>
 __global__ void k_maxpool_fwd(const T* __restrict__ x, int n, int h, int w, int c, int ph, int pw,
                               T* __restrict__ out) {
+  sg_pdl_prologue();
   int ho = h / ph, wo = w / pw;
   long long total = (long long)n * ho * wo * c;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -259,6 +273,7 @@ __global__ void k_maxpool_fwd(const T* __restrict__ x, int n, int h, int w, int 
 // 4 channels per thread (c % 4 == 0): 8/16-byte loads and stores
 template <typename T>
 __global__ void k_maxpool_fwd_v4(const T* __restrict__ x, int n, int h, int w, int c4, int ph, int pw, T* __restrict__ out) {
+  sg_pdl_prologue();
   int ho = h / ph, wo = w / pw;
   long long total = (long long)n * ho * wo * c4;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -282,6 +297,7 @@ __global__ void k_maxpool_fwd_v4(const T* __restrict__ x, int n, int h, int w, i
 template <typename TX, typename TO>
 __global__ void k_maxpool_bwd_v4(const float* __restrict__ dout, const TX* __restrict__ x, int n, int h, int w, int c4,
                                  int ph, int pw, int relu_mask, TO* __restrict__ dx) {
+  sg_pdl_prologue();
   int ho = h / ph, wo = w / pw;
   long long total = (long long)n * ho * wo * c4;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -322,6 +338,7 @@ __global__ void k_maxpool_bwd_v4(const float* __restrict__ dout, const TX* __res
 template <typename TX, typename TO>
 __global__ void k_maxpool_bwd(const float* __restrict__ dout, const TX* __restrict__ x, int n, int h, int w, int c,
                               int ph, int pw, int relu_mask, TO* __restrict__ dx) {
+  sg_pdl_prologue();
   int ho = h / ph, wo = w / pw;
   long long total = (long long)n * ho * wo * c;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -349,6 +366,7 @@ __global__ void k_maxpool_bwd(const float* __restrict__ dout, const TX* __restri
 
 // global average pool of relu(x): one block per (image, 128-channel slab); threads split (pixel-slices x channels)
 __global__ void k_gap_relu_fwd(const float* __restrict__ x, long long hw, int c, float* __restrict__ out) {
+  sg_pdl_prologue();
   __shared__ float sm[8][128];
   int ni = blockIdx.y;
   int c0 = blockIdx.x * 128;
@@ -369,6 +387,7 @@ __global__ void k_gap_relu_fwd(const float* __restrict__ x, long long hw, int c,
 
 __global__ void k_gap_relu_bwd(const float* __restrict__ dfeat, const float* __restrict__ x, long long hw, int c,
                                long long total, float* __restrict__ dx) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   float inv = 1.f / (float)hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -398,6 +417,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 __global__ void k_philox(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
                          const unsigned long long* __restrict__ offset_dev, int normal) {
+  sg_pdl_prologue();
   const unsigned long long base = offset + (offset_dev ? *offset_dev : 0ull);
   const long long groups = (n + 3) / 4, stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
@@ -426,6 +446,7 @@ __global__ void k_philox(float* __restrict__ out, long long n, unsigned long lon
   }
 }
 __global__ void k_philox_advance(unsigned long long* offset_dev, unsigned long long by) {
+  sg_pdl_prologue();
   if (blockIdx.x == 0 && threadIdx.x == 0) *offset_dev += by;
 }
 
@@ -433,6 +454,7 @@ __global__ void k_philox_advance(unsigned long long* offset_dev, unsigned long l
 // ragged batches (several word lengths in one launch): zero everything right of a word's own width
 template <typename T>
 __global__ void k_mask_width(T* __restrict__ x, long long total4, int h, int w, int c4, const int* __restrict__ lens, int cols_per_char) {
+  sg_pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     const long long pix = i / c4;
@@ -442,6 +464,7 @@ __global__ void k_mask_width(T* __restrict__ x, long long total4, int h, int w, 
   }
 }
 __global__ void k_label_lengths(const int* __restrict__ labels, int b, int l, int* __restrict__ lens) {
+  sg_pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   int n = 0;
@@ -456,7 +479,7 @@ int sg_act_prep(sg_ctx* ctx, const float* x, long long n, void* relu_out, void* 
   if (n == 0) return SG_OK;
   long long n4 = (((uintptr_t)x | (uintptr_t)relu_out | (uintptr_t)copy_out) & 15) == 0 ? n / 4 : 0;
   SG_DISPATCH_DT(out_dt, TO,
-                 k_act_prep<TO><<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(x, n4, n, (TO*)relu_out, (TO*)copy_out));
+                 sg_launch(ctx, k_act_prep<TO>, ew_grid(ctx, n / 4 + 1, 256), 256, 0, x, n4, n, (TO*)relu_out, (TO*)copy_out));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -469,7 +492,7 @@ int sg_mask_mul(sg_ctx* ctx, const float* dy, const void* act, int act_dt, void*
   int grid = ew_grid(ctx, n / 4 + 1, 256);
   SG_DISPATCH_DT(act_dt, TA,
                  SG_DISPATCH_DT(out_dt, TO,
-                                k_mask_mul<TA, TO><<<grid, 256, 0, ctx->stream>>>(dy, (const TA*)act, (TO*)out, n4, n, accumulate)));
+                                sg_launch(ctx, k_mask_mul<TA, TO>, grid, 256, 0, dy, (const TA*)act, (TO*)out, n4, n, accumulate)));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -478,7 +501,7 @@ int sg_axpby(sg_ctx* ctx, float a, const float* x, float b, const float* y, floa
   SG_REQUIRE(ctx && x && out && n >= 0, "sg_axpby: bad args");
   if (n == 0) return SG_OK;
   long long n4 = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out) & 15) == 0 ? n / 4 : 0;
-  k_axpby<<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(a, x, b, y, out, n4, n);
+  sg_launch(ctx, k_axpby, ew_grid(ctx, n / 4 + 1, 256), 256, 0, a, x, b, y, out, n4, n);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -487,7 +510,7 @@ int sg_scale_add(sg_ctx* ctx, const float* sigma, const float* a, const float* x
   SG_REQUIRE(ctx && sigma && a && out && n >= 0, "sg_scale_add: bad args");
   if (n == 0) return SG_OK;
   long long n4 = (((uintptr_t)a | (uintptr_t)x | (uintptr_t)out) & 15) == 0 ? n / 4 : 0;
-  k_scale_add<<<ew_grid(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(sigma, a, x, out, n4, n);
+  sg_launch(ctx, k_scale_add, ew_grid(ctx, n / 4 + 1, 256), 256, 0, sigma, a, x, out, n4, n);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -495,7 +518,7 @@ int sg_scale_add(sg_ctx* ctx, const float* sigma, const float* a, const float* x
 int sg_tanh_fwd(sg_ctx* ctx, const float* x, float* y, long long n) {
   SG_REQUIRE(ctx && x && y && n >= 0, "sg_tanh_fwd: bad args");
   if (n == 0) return SG_OK;
-  k_tanh_fwd<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(x, y, n);
+  sg_launch(ctx, k_tanh_fwd, ew_grid(ctx, n, 256), 256, 0, x, y, n);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -503,7 +526,7 @@ int sg_tanh_fwd(sg_ctx* ctx, const float* x, float* y, long long n) {
 int sg_tanh_bwd(sg_ctx* ctx, const float* dy, const float* y, float* dx, long long n) {
   SG_REQUIRE(ctx && dy && y && dx && n >= 0, "sg_tanh_bwd: bad args");
   if (n == 0) return SG_OK;
-  k_tanh_bwd<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(dy, y, dx, n);
+  sg_launch(ctx, k_tanh_bwd, ew_grid(ctx, n, 256), 256, 0, dy, y, dx, n);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -511,7 +534,7 @@ int sg_tanh_bwd(sg_ctx* ctx, const float* dy, const float* y, float* dx, long lo
 int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long cols) {
   SG_REQUIRE(ctx && x && w && rows >= 0 && cols >= 0, "sg_scale_rows: bad args");
   if ((long long)rows * cols == 0) return SG_OK;
-  k_scale_rows<<<ew_grid(ctx, (long long)rows * cols, 256), 256, 0, ctx->stream>>>(x, w, rows, cols);
+  sg_launch(ctx, k_scale_rows, ew_grid(ctx, (long long)rows * cols, 256), 256, 0, x, w, rows, cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -524,7 +547,7 @@ int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out,
   }
   int dot_blocks = ew_grid(ctx, n, 256);
   if (dot_blocks > 1024) dot_blocks = 1024;
-  k_dot<<<dot_blocks, 256, 0, ctx->stream>>>(a, b, n, out, accumulate, ctx->det_scratch, ctx->det_tickets);
+  sg_launch(ctx, k_dot, dot_blocks, 256, 0, a, b, n, out, accumulate, ctx->det_scratch, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -552,10 +575,10 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
     rpb = (rpb + lanes_r - 1) / lanes_r * lanes_r;
     blocks = (rows + rpb - 1) / rpb;
     if (dt == SG_F32)
-      k_colsum_v4<float, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const float*)x, rows, cols, rpb, out, accumulate, ctx->det_scratch,
+      sg_launch(ctx, k_colsum_v4<float, NT>, (int)blocks, NT, 0, (const float*)x, rows, cols, rpb, out, accumulate, ctx->det_scratch,
                                                                   ctx->det_tickets);
     else
-      k_colsum_v4<__nv_bfloat16, NT><<<(int)blocks, NT, 0, ctx->stream>>>((const __nv_bfloat16*)x, rows, cols, rpb, out, accumulate,
+      sg_launch(ctx, k_colsum_v4<__nv_bfloat16, NT>, (int)blocks, NT, 0, (const __nv_bfloat16*)x, rows, cols, rpb, out, accumulate,
                                                                           ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
     return SG_OK;
@@ -568,7 +591,7 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
   long long rpb = (rows + blocks - 1) / blocks;
   blocks = (rows + rpb - 1) / rpb;
   int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
-  SG_DISPATCH_DT(dt, T, k_colsum<T><<<(int)blocks, threads, 0, ctx->stream>>>((const T*)x, rows, cols, rpb, out, accumulate,
+  SG_DISPATCH_DT(dt, T, sg_launch(ctx, k_colsum<T>, (int)blocks, threads, 0, (const T*)x, rows, cols, rpb, out, accumulate,
                                                                               ctx->det_scratch, ctx->det_tickets));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -577,7 +600,7 @@ int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, floa
 int sg_cast(sg_ctx* ctx, const float* x, void* out, int out_dt, long long n) {
   SG_REQUIRE(ctx && x && out && n >= 0, "sg_cast: bad args");
   if (n == 0) return SG_OK;
-  SG_DISPATCH_DT(out_dt, TO, k_cast<TO><<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(x, (TO*)out, n));
+  SG_DISPATCH_DT(out_dt, TO, sg_launch(ctx, k_cast<TO>, ew_grid(ctx, n, 256), 256, 0, x, (TO*)out, n));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -587,7 +610,7 @@ int sg_avgpool2_fwd(sg_ctx* ctx, const float* x, int n, int h, int w, int c, flo
   SG_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "sg_avgpool2_fwd: needs even h,w and c%%4==0 (h=%d w=%d c=%d)", h, w, c);
   long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
   if (total == 0) return SG_OK;
-  k_avgpool2_fwd<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(x, n, h, w, c / 4, out);
+  sg_launch(ctx, k_avgpool2_fwd, ew_grid(ctx, total, 256), 256, 0, x, n, h, w, c / 4, out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -597,7 +620,7 @@ int sg_avgpool2_bwd(sg_ctx* ctx, const float* dout, int n, int h, int w, int c, 
   SG_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "sg_avgpool2_bwd: needs even h,w and c%%4==0");
   long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return SG_OK;
-  SG_DISPATCH_DT(dx_dt, TO, k_avgpool2_bwd<TO><<<ew_grid(ctx, total / 4, 256), 256, 0, ctx->stream>>>(dout, n, h, w, c / 4, (TO*)dx));
+  SG_DISPATCH_DT(dx_dt, TO, sg_launch(ctx, k_avgpool2_bwd<TO>, ew_grid(ctx, total / 4, 256), 256, 0, dout, n, h, w, c / 4, (TO*)dx));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -608,9 +631,9 @@ int sg_maxpool_fwd(sg_ctx* ctx, const void* x, int dt, int n, int h, int w, int 
   long long total = (long long)n * (h / ph) * (w / pw) * c;
   if (total == 0) return SG_OK;
   if (c % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
-    SG_DISPATCH_DT(dt, T, k_maxpool_fwd_v4<T><<<ew_grid(ctx, total / 4, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c / 4, ph, pw, (T*)out));
+    SG_DISPATCH_DT(dt, T, sg_launch(ctx, k_maxpool_fwd_v4<T>, ew_grid(ctx, total / 4, 256), 256, 0, (const T*)x, n, h, w, c / 4, ph, pw, (T*)out));
   } else {
-    SG_DISPATCH_DT(dt, T, k_maxpool_fwd<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((const T*)x, n, h, w, c, ph, pw, (T*)out));
+    SG_DISPATCH_DT(dt, T, sg_launch(ctx, k_maxpool_fwd<T>, ew_grid(ctx, total, 256), 256, 0, (const T*)x, n, h, w, c, ph, pw, (T*)out));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -626,12 +649,12 @@ int sg_maxpool_bwd(sg_ctx* ctx, const float* dout, const void* x, int x_dt, int 
     int grid = ew_grid(ctx, total / 4, 256);
     SG_DISPATCH_DT(x_dt, TX,
                    SG_DISPATCH_DT(dx_dt, TO,
-                                  k_maxpool_bwd_v4<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c / 4, ph, pw, relu_mask, (TO*)dx)));
+                                  sg_launch(ctx, k_maxpool_bwd_v4<TX, TO>, grid, 256, 0, dout, (const TX*)x, n, h, w, c / 4, ph, pw, relu_mask, (TO*)dx)));
   } else {
     int grid = ew_grid(ctx, total, 256);
     SG_DISPATCH_DT(x_dt, TX,
                    SG_DISPATCH_DT(dx_dt, TO,
-                                  k_maxpool_bwd<TX, TO><<<grid, 256, 0, ctx->stream>>>(dout, (const TX*)x, n, h, w, c, ph, pw, relu_mask, (TO*)dx)));
+                                  sg_launch(ctx, k_maxpool_bwd<TX, TO>, grid, 256, 0, dout, (const TX*)x, n, h, w, c, ph, pw, relu_mask, (TO*)dx)));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -641,7 +664,7 @@ int sg_gap_relu_fwd(sg_ctx* ctx, const float* x, int n, long long hw, int c, flo
   SG_REQUIRE(ctx && x && out && n >= 0 && hw > 0 && c > 0, "sg_gap_relu_fwd: bad args");
   if (n == 0) return SG_OK;
   dim3 grid(sg_div_up(c, 128), n);
-  k_gap_relu_fwd<<<grid, 1024, 0, ctx->stream>>>(x, hw, c, out);
+  sg_launch(ctx, k_gap_relu_fwd, grid, 1024, 0, x, hw, c, out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -650,7 +673,7 @@ int sg_gap_relu_bwd(sg_ctx* ctx, const float* dfeat, const float* x, int n, long
   SG_REQUIRE(ctx && dfeat && x && dx && n >= 0 && hw > 0 && c > 0, "sg_gap_relu_bwd: bad args");
   long long total = (long long)n * hw * c;
   if (total == 0) return SG_OK;
-  k_gap_relu_bwd<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(dfeat, x, hw, c, total, dx);
+  sg_launch(ctx, k_gap_relu_bwd, ew_grid(ctx, total, 256), 256, 0, dfeat, x, hw, c, total, dx);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -664,10 +687,10 @@ int sg_random(sg_ctx* ctx, float* out, long long n, unsigned long long seed, uns
   SG_REQUIRE(ctx && out && n >= 0, "sg_random: bad args");
   if (n == 0) return SG_OK;
   long long groups = (n + 3) / 4;
-  k_philox<<<ew_grid(ctx, groups, 256), 256, 0, ctx->stream>>>(out, n, seed, offset, offset_dev, normal);
+  sg_launch(ctx, k_philox, ew_grid(ctx, groups, 256), 256, 0, out, n, seed, offset, offset_dev, normal);
   SG_POST_LAUNCH(ctx);
   if (offset_dev) {
-    k_philox_advance<<<1, 32, 0, ctx->stream>>>(offset_dev, (unsigned long long)groups);
+    sg_launch(ctx, k_philox_advance, 1, 32, 0, offset_dev, (unsigned long long)groups);
     SG_POST_LAUNCH(ctx);
   }
   return SG_OK;
@@ -679,7 +702,7 @@ int sg_mask_width(sg_ctx* ctx, void* x, int dt, int n, int h, int w, int c, cons
   SG_REQUIRE(ctx && x && lens && n >= 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0 && cols_per_char > 0, "sg_mask_width: bad args");
   long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return SG_OK;
-  SG_DISPATCH_DT(dt, T, k_mask_width<T><<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>((T*)x, total, h, w, c / 4, lens, cols_per_char));
+  SG_DISPATCH_DT(dt, T, sg_launch(ctx, k_mask_width<T>, ew_grid(ctx, total, 256), 256, 0, (T*)x, total, h, w, c / 4, lens, cols_per_char));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -688,7 +711,7 @@ int sg_mask_width(sg_ctx* ctx, void* x, int dt, int n, int h, int w, int c, cons
 int sg_label_lengths(sg_ctx* ctx, const int* labels, int b, int l, int* lens) {
   SG_REQUIRE(ctx && labels && lens && b >= 0 && l > 0, "sg_label_lengths: bad args");
   if (b == 0) return SG_OK;
-  k_label_lengths<<<sg_div_up(b, 256), 256, 0, ctx->stream>>>(labels, b, l, lens);
+  sg_launch(ctx, k_label_lengths, sg_div_up(b, 256), 256, 0, labels, b, l, lens);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

@@ -17,6 +17,7 @@ __device__ __forceinline__ long long fb_out_index(int b, int l, int L, int k) {
 __global__ void __launch_bounds__(256) k_fb_fwd(const float* __restrict__ z, int z_stride, const int* __restrict__ y,
                                                  int L, int vocab, const float* __restrict__ bank,
                                                  float* __restrict__ out) {
+  sg_pdl_prologue();
   __shared__ float zs[FB_J];
   int p = blockIdx.y, b = p / L, l = p % L;
   int v = y[p];
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) k_fb_fwd(const float* __restrict__ z, int
 __global__ void __launch_bounds__(128) k_fb_bwd_bank(const float* __restrict__ dout, const float* __restrict__ z,
                                                       int z_stride, const int* __restrict__ y, int B, int L,
                                                       float* __restrict__ dbank) {
+  sg_pdl_prologue();
   __shared__ float zs[FB_J];
   int v = blockIdx.y;
   int k = blockIdx.x * 128 + threadIdx.x;
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(128) k_fb_bwd_bank(const float* __restrict__ d
 __global__ void __launch_bounds__(256) k_fb_bwd_z(const float* __restrict__ dout, const int* __restrict__ y, int L,
                                                    int vocab, const float* __restrict__ bank, float* __restrict__ dz0,
                                                    int dz_stride) {
+  sg_pdl_prologue();
   __shared__ float sm[32];
   int j = blockIdx.x, b = blockIdx.y;
   float acc = 0.f;
@@ -84,7 +87,7 @@ int sg_filterbank_fwd(sg_ctx* ctx, const float* z, int z_stride, const int* y, i
   SG_REQUIRE(b >= 0 && l >= 0 && vocab > 0 && z_stride >= FB_J, "sg_filterbank_fwd: bad sizes");
   if (b * l == 0) return SG_OK;
   dim3 grid(FB_K / 256, b * l);
-  k_fb_fwd<<<grid, 256, 0, ctx->stream>>>(z, z_stride, y, l, vocab, bank, out);
+  sg_launch(ctx, k_fb_fwd, grid, 256, 0, z, z_stride, y, l, vocab, bank, out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -94,11 +97,11 @@ int sg_filterbank_bwd(sg_ctx* ctx, const float* dout, const float* z, int z_stri
   SG_REQUIRE(ctx && dout && z && y && bank && dbank, "sg_filterbank_bwd: NULL");
   SG_REQUIRE(b >= 0 && l >= 0 && vocab > 0 && z_stride >= FB_J, "sg_filterbank_bwd: bad sizes");
   dim3 grid(FB_K / 128, vocab);
-  k_fb_bwd_bank<<<grid, 128, 0, ctx->stream>>>(dout, z, z_stride, y, b, l, dbank);
+  sg_launch(ctx, k_fb_bwd_bank, grid, 128, 0, dout, z, z_stride, y, b, l, dbank);
   SG_POST_LAUNCH(ctx);
   if (dz0 && b * l > 0) {
     dim3 g2(FB_J, b);
-    k_fb_bwd_z<<<g2, 256, 0, ctx->stream>>>(dout, y, l, vocab, bank, dz0, dz_stride);
+    sg_launch(ctx, k_fb_bwd_z, g2, 256, 0, dout, y, l, vocab, bank, dz0, dz_stride);
     SG_POST_LAUNCH(ctx);
   }
   return SG_OK;

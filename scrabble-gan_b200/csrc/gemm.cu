@@ -14,6 +14,7 @@ template <int GT_K>
 __global__ void __launch_bounds__(256) k_gemm(int ta, int tb, int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                const float* __restrict__ bias, int accumulate, int k_per_split, float* __restrict__ scratch, unsigned int* __restrict__ tickets) {
+  sg_pdl_prologue();
   __shared__ float As[GT_K][GT_M + 4];
   __shared__ float Bs[GT_K][GT_N + 4];
   const int tid = threadIdx.x;
@@ -132,7 +133,7 @@ extern "C" int sg_gemm(sg_ctx* ctx, int trans_a, int trans_b, int m, int n, int 
   grid.z = splits;
   // (a one-shot GT_K = 64 instantiation for K <= 64 measured SLOWER than the 16-wide loop on the CBN Dense layers --
   //  19 us vs 10 us per launch in profiles/r01_launches_step.csv -- so the generic loop is used for every shape)
-  k_gemm<16><<<grid, 256, 0, ctx->stream>>>(trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split, ctx->det_scratch, ctx->det_tickets);
+  sg_launch(ctx, k_gemm<16>, grid, 256, 0, trans_a, trans_b, m, n, k, a, lda, b, ldb, c, ldc, bias, accumulate, k_per_split, ctx->det_scratch, ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -153,6 +154,7 @@ struct CbnSegs {
 // out[r, col] = sum_k z[r, z_off(seg) + k] * W_seg[k, col - col0(seg)],  k < 32
 __global__ void __launch_bounds__(256) k_cbn_dense_fwd(const float* __restrict__ z, int z_stride, int n, CbnSegs t,
                                                        const float* __restrict__ w, float* __restrict__ out) {
+  sg_pdl_prologue();
   const long long total = (long long)n * t.total;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % t.total), r = (int)(i / t.total);
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) k_cbn_dense_fwd(const float* __restrict__
 // dW_seg[k, cl] += sum_r z[r, z_off + k] * s_seg[r, cl]     (one thread per output: no atomics, fixed order over r)
 __global__ void __launch_bounds__(256) k_cbn_dense_wgrad(const float* __restrict__ z, int z_stride, int n, CbnSegs t,
                                                          float* __restrict__ dw) {
+  sg_pdl_prologue();
   const long long total = 32LL * t.total;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % t.total), k = (int)(i / t.total);
@@ -207,7 +210,7 @@ extern "C" int sg_cbn_dense_fwd(sg_ctx* ctx, const float* z, int z_stride, int n
   if (rc != SG_OK) return rc;
   if (n == 0) return SG_OK;
   long long need = ((long long)n * t.total + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  k_cbn_dense_fwd<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(z, z_stride, n, t, w_base, out);
+  sg_launch(ctx, k_cbn_dense_fwd, (int)(need < cap ? need : cap), 256, 0, z, z_stride, n, t, w_base, out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -225,7 +228,7 @@ extern "C" int sg_cbn_dense_wgrad(sg_ctx* ctx, const float* z, int z_stride, int
   }
   if (n == 0) return SG_OK;
   long long need = (32LL * t.total + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  k_cbn_dense_wgrad<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(z, z_stride, n, t, dw_base);
+  sg_launch(ctx, k_cbn_dense_wgrad, (int)(need < cap ? need : cap), 256, 0, z, z_stride, n, t, dw_base);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

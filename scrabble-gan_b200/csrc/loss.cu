@@ -34,6 +34,7 @@ __device__ double block_sum_d(double v, double* sm) {
 __global__ void k_loss_sums(int kind, int use_w, const float* d_real, const float* d_fake, const float* s_real,
                             const float* s_fake, const float* s5, const float* r_fake, const float* r_real, int b,
                             double* sums) {
+  sg_pdl_prologue();
   __shared__ double sm[32];
   double acc[SUM_N];
   for (int j = 0; j < SUM_N; ++j) acc[j] = 0.0;
@@ -72,6 +73,7 @@ __global__ void k_loss_finish(int kind, int use_w, int balance, float alpha, con
                               const double* sums, float* up_d_real, float* up_d_fake_d, float* up_s_real,
                               float* up_s_fake_w, float* up_s_slot5, float* up_d_fake_g, float* up_s_fake_g,
                               float* up_r_fake_g, float* stats) {
+  sg_pdl_prologue();
   const double N = sums[SUM_N];
   const double mean_g = sums[SUM_G] / N, mean_r = sums[SUM_R] / N;
   double var_g = sums[SUM_G2] / N - mean_g * mean_g, var_r = sums[SUM_R2] / N - mean_r * mean_r;
@@ -148,7 +150,7 @@ int sg_loss_sums(sg_ctx* ctx, int kind, int use_w, const float* d_real, const fl
   SG_REQUIRE(ctx && d_real && d_fake && r_fake && r_real && sums && b > 0, "sg_loss_sums: bad args");
   SG_REQUIRE(!use_w || (s_real && s_fake), "sg_loss_sums: use_w needs s_real and s_fake");
   SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_sums: bad loss kind %d", kind);
-  k_loss_sums<<<1, 256, 0, ctx->stream>>>(kind, use_w, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, r_real, b, sums);
+  sg_launch(ctx, k_loss_sums, 1, 256, 0, kind, use_w, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, r_real, b, sums);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -161,7 +163,7 @@ int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, c
              "sg_loss_finish: bad args");
   SG_REQUIRE(!use_w || (s_real && s_fake && up_s_real && up_s_fake_w), "sg_loss_finish: use_w needs the s_* buffers");
   SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_finish: bad loss kind %d", kind);
-  k_loss_finish<<<1, 256, 0, ctx->stream>>>(kind, use_w, balance, alpha, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, b,
+  sg_launch(ctx, k_loss_finish, 1, 256, 0, kind, use_w, balance, alpha, d_real, d_fake, s_real, s_fake, s_slot5, r_fake, b,
                                             sums, up_d_real, up_d_fake_d, up_s_real, up_s_fake_w, up_s_slot5, up_d_fake_g,
                                             up_s_fake_g, up_r_fake_g, stats);
   SG_POST_LAUNCH(ctx);
@@ -177,6 +179,7 @@ int sg_loss_finish(sg_ctx* ctx, int kind, int use_w, int balance, float alpha, c
 // terms[7][b]: d_loss, d_loss_real, d_loss_fake, g_loss, s_loss, s_loss_1, s_loss_2   (net_loss.py return order)
 __global__ void k_loss_terms(int kind, const float* d_real, const float* d_fake, const float* s_a, const float* s_b,
                              const float* s_c, int b, float* terms) {
+  sg_pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
     float dr = d_real[i], df = d_fake[i], sa = s_a[i], sb = s_b[i], sc = s_c ? s_c[i] : 0.f;
     float dlr, dlf, g, s1, s2;
@@ -196,6 +199,7 @@ __global__ void k_loss_terms(int kind, const float* d_real, const float* d_fake,
 
 // g_bal = g + alpha (sd_g / sd_r) r ; r_bal = alpha (sd_g / sd_r) r ; stds = {sd_r, sd_g}   (single CTA)
 __global__ void k_grad_balance(const float* r, const float* g, int b, float alpha, float* g_bal, float* r_bal, float* stds) {
+  sg_pdl_prologue();
   __shared__ double sm[32];
   double sr = 0, sr2 = 0, sg = 0, sg2 = 0;
   for (int i = threadIdx.x; i < b; i += blockDim.x) {
@@ -221,7 +225,7 @@ int sg_loss_terms(sg_ctx* ctx, int kind, const float* d_real, const float* d_fak
                   const float* s_c, int b, float* terms) {
   SG_REQUIRE(ctx && d_real && d_fake && s_a && s_b && terms && b > 0, "sg_loss_terms: bad args");
   SG_REQUIRE(kind == SG_LOSS_HINGE || kind == SG_LOSS_NOT_SATURATING, "sg_loss_terms: bad loss kind %d", kind);
-  k_loss_terms<<<sg_div_up(b, 256), 256, 0, ctx->stream>>>(kind, d_real, d_fake, s_a, s_b, s_c, b, terms);
+  sg_launch(ctx, k_loss_terms, sg_div_up(b, 256), 256, 0, kind, d_real, d_fake, s_a, s_b, s_c, b, terms);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -229,7 +233,7 @@ int sg_loss_terms(sg_ctx* ctx, int kind, const float* d_real, const float* d_fak
 int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b, float alpha, float* g_balanced,
                     float* r_balanced, float* stds) {
   SG_REQUIRE(ctx && r_fake && g_loss && g_balanced && r_balanced && stds && b > 0, "sg_grad_balance: bad args");
-  k_grad_balance<<<1, 256, 0, ctx->stream>>>(r_fake, g_loss, b, alpha, g_balanced, r_balanced, stds);
+  sg_launch(ctx, k_grad_balance, 1, 256, 0, r_fake, g_loss, b, alpha, g_balanced, r_balanced, stds);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -245,6 +249,7 @@ int sg_grad_balance(sg_ctx* ctx, const float* r_fake, const float* g_loss, int b
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_imgbal_sums(const float* __restrict__ gd, const float* __restrict__ gr, long long n,
                                                       double* __restrict__ sums, double* __restrict__ scratch, unsigned int* ticket) {
+  sg_pdl_prologue();
   __shared__ double sm[32];
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -272,6 +277,7 @@ __global__ void __launch_bounds__(256) k_imgbal_sums(const float* __restrict__ g
 // g_loss_balanced = g_loss_final = g_loss + r_loss_balanced, alpha, r_loss_fake_std := sd_r, g_loss_std := sd_d
 __global__ void k_imgbal_apply(const float* __restrict__ gd, const float* __restrict__ gr, long long n, float alpha,
                                const double* __restrict__ sums, float* __restrict__ out, float* __restrict__ stats) {
+  sg_pdl_prologue();
   const double N = sums[4];
   const double md = sums[0] / N, mr = sums[2] / N;
   double vd = sums[1] / N - md * md, vr = sums[3] / N - mr * mr;
@@ -296,7 +302,7 @@ int sg_image_grad_balance_sums(sg_ctx* ctx, const float* grad_d, const float* gr
   SG_REQUIRE(ctx && grad_d && grad_r && sums && n > 0, "sg_image_grad_balance_sums: bad args");
   long long blocks = (n + 256 * 8 - 1) / (256 * 8), cap = (long long)ctx->num_sms * 2;
   if (blocks > cap) blocks = cap;
-  k_imgbal_sums<<<(int)blocks, 256, 0, ctx->stream>>>(grad_d, grad_r, n, sums, reinterpret_cast<double*>(ctx->det_scratch), ctx->det_tickets);
+  sg_launch(ctx, k_imgbal_sums, (int)blocks, 256, 0, grad_d, grad_r, n, sums, reinterpret_cast<double*>(ctx->det_scratch), ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -306,7 +312,7 @@ int sg_image_grad_balance_apply(sg_ctx* ctx, const float* grad_d, const float* g
   SG_REQUIRE(ctx && grad_d && grad_r && sums && out && n > 0, "sg_image_grad_balance_apply: bad args");
   long long blocks = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
   if (blocks > cap) blocks = cap;
-  k_imgbal_apply<<<(int)blocks, 256, 0, ctx->stream>>>(grad_d, grad_r, n, alpha, sums, out, stats);
+  sg_launch(ctx, k_imgbal_apply, (int)blocks, 256, 0, grad_d, grad_r, n, alpha, sums, out, stats);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

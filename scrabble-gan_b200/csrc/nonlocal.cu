@@ -39,6 +39,7 @@ template <int K, int N, bool TRANS_W>
 __global__ void __launch_bounds__(256) k_nl_rowgemm(long long rows, SegMat A, SegMat W, SegMat C, const float* __restrict__ alpha_p,
                                                      int accumulate, const float* __restrict__ resid_scale_p,
                                                      const float* __restrict__ resid_x, float* __restrict__ resid_out) {
+  sg_pdl_prologue();
   using T = NlTile<K, N>;
   __shared__ __align__(16) float As[K][T::TRP];     // transposed: As[k][row]
   __shared__ __align__(16) float Ws[K][N];
@@ -132,6 +133,7 @@ template <int KA, int KB>
 __global__ void __launch_bounds__(NLW_SUB * (KA / 4) * (KB / 4)) k_nl_wgrad(long long rows, long long rows_per_block, SegMat A, SegMat B,
                                                                              SegMat DW, const float* __restrict__ alpha_p,
                                                                              float* __restrict__ scratch, unsigned int* __restrict__ ticket) {
+  sg_pdl_prologue();
   constexpr int TA = KA / 4, TB = KB / 4, NT = TA * TB;
   extern __shared__ __align__(16) float nlw_smem[];
   const int sub = threadIdx.x / NT, tid = threadIdx.x % NT;
@@ -237,6 +239,7 @@ template <int K, int N, bool TRANS_W>
 __global__ void __launch_bounds__(256) k_nl_rowgemm_mma(long long rows, SegMat A, SegMat W, SegMat C, const float* __restrict__ alpha_p,
                                                          int accumulate, const float* __restrict__ resid_scale_p,
                                                          const float* __restrict__ resid_x, float* __restrict__ resid_out) {
+  sg_pdl_prologue();
   constexpr int KP = K + 8;                                  // padded row (bf16): conflict-free 32-bit fragment reads
   __shared__ __align__(16) __nv_bfloat16 Wt[N * KP];         // Wt[n][k] = Wlogical[k][n]
   for (int i = threadIdx.x; i < K * N; i += 256) {
@@ -305,6 +308,7 @@ template <int KA, int KB>
 __global__ void __launch_bounds__(256, 1) k_nl_wgrad_mma(long long rows, long long rows_per_block, SegMat A, SegMat B, SegMat DW,
                                                           const float* __restrict__ alpha_p, float* __restrict__ scratch,
                                                           unsigned int* __restrict__ ticket) {
+  sg_pdl_prologue();
   constexpr int MT = KA / 16, NT = KB / 8;
   __shared__ float red[KA * KB];
   for (int i = threadIdx.x; i < KA * KB; i += 256) red[i] = 0.f;
@@ -412,7 +416,7 @@ static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegM
     long long blocks = (long long)ctx->num_sms * 2;
     long long rpb = ((rows + blocks - 1) / blocks + 127) / 128 * 128;
     int grid_m = (int)((rows + rpb - 1) / rpb);
-    k_nl_wgrad_mma<KA, KB><<<grid_m, 256, 0, ctx->stream>>>(rows, rpb, A, B, DW, alpha, ctx->det_scratch, ctx->det_tickets);
+    sg_launch(ctx, k_nl_wgrad_mma<KA, KB>, grid_m, 256, 0, rows, rpb, A, B, DW, alpha, ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
     return SG_OK;
   }
@@ -422,7 +426,7 @@ static int nl_wgrad_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat B, SegM
   size_t smem = sizeof(float) * (size_t)NLW_SUB * NLW_ROWS * (KA + KB);
   static_assert(NLW_SUB * 16 * (KA / 4) * (KB / 4) <= NLW_SUB * NLW_ROWS * (KA + KB), "reduction buffer does not fit");
   SG_CHECK_CUDA(cudaFuncSetAttribute(k_nl_wgrad<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_nl_wgrad<KA, KB><<<grid, NLW_SUB * (KA / 4) * (KB / 4), smem, ctx->stream>>>(rows, rpb, A, B, DW, alpha, ctx->det_scratch,
+  sg_launch(ctx, k_nl_wgrad<KA, KB>, grid, NLW_SUB * (KA / 4) * (KB / 4), smem, rows, rpb, A, B, DW, alpha, ctx->det_scratch,
                                                                                   ctx->det_tickets);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -433,10 +437,10 @@ static int nl_rowgemm_launch(sg_ctx* ctx, long long rows, SegMat A, SegMat W, Se
                              const float* resid_scale, const float* resid_x, float* resid_out) {
   if (ctx->speed_mode) {
     long long need = (rows + 127) / 128, cap = (long long)ctx->num_sms * 8;
-    k_nl_rowgemm_mma<K, N, TRANS_W><<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(rows, A, W, C, alpha, accumulate, resid_scale,
+    sg_launch(ctx, k_nl_rowgemm_mma<K, N, TRANS_W>, (int)(need < cap ? need : cap), 256, 0, rows, A, W, C, alpha, accumulate, resid_scale,
                                                                                             resid_x, resid_out);
   } else {
-    k_nl_rowgemm<K, N, TRANS_W><<<nl_grid<K, N>(ctx, rows), 256, 0, ctx->stream>>>(rows, A, W, C, alpha, accumulate, resid_scale, resid_x,
+    sg_launch(ctx, k_nl_rowgemm<K, N, TRANS_W>, nl_grid<K, N>(ctx, rows), 256, 0, rows, A, W, C, alpha, accumulate, resid_scale, resid_x,
                                                                                   resid_out);
   }
   SG_POST_LAUNCH(ctx);

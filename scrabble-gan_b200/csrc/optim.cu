@@ -11,6 +11,7 @@
 __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                        long long n4, long long n, float lr_t, float b1, float b2, float eps, __nv_bfloat16* __restrict__ wb,
                        const float* __restrict__ lr_dev) {
+  sg_pdl_prologue();
   if (lr_dev) lr_t = *lr_dev;          // step size from device memory (CUDA-graph replays: see k_adam_prepare)
   long long stride = (long long)gridDim.x * blockDim.x;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
@@ -41,6 +42,7 @@ __global__ void k_adam(float* __restrict__ w, const float* __restrict__ g, float
 template <bool kNoM, bool kClear>
 __global__ void k_adam_fused(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n4,
                              long long n, float b1, float b2, float eps, __nv_bfloat16* __restrict__ wb, const float* __restrict__ lr_dev) {
+  sg_pdl_prologue();
   const float lr_t = *lr_dev;
   long long stride = (long long)gridDim.x * blockDim.x;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
@@ -74,6 +76,7 @@ __global__ void k_adam_fused(float* __restrict__ w, float* __restrict__ g, float
 // Device-side step counter and Keras step size  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t):  t_set >= 0 sets the counter (eager
 // calls pass the host iteration count), t_set < 0 increments it (captured launches: every graph replay advances by one).
 __global__ void k_adam_prepare(int* __restrict__ step, float* __restrict__ lr_dev, int t_set, float lr, float b1, float b2) {
+  sg_pdl_prologue();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int t = t_set >= 0 ? t_set : *step + 1;
     *step = t;
@@ -84,6 +87,7 @@ __global__ void k_adam_prepare(int* __restrict__ step, float* __restrict__ lr_de
 
 __global__ void k_rmsprop(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ ms, long long n,
                           float lr, float rho, float eps) {
+  sg_pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float gi = g[i];
@@ -97,6 +101,7 @@ __global__ void k_rmsprop(float* __restrict__ w, const float* __restrict__ g, fl
 // v_raw[r] = sum_c u[c] W[r,c]  (one warp per row)
 __global__ void k_sn_rowdot(const float* __restrict__ w, int rows, int cols, const float* __restrict__ u,
                             const float* __restrict__ u_scale, float* __restrict__ v) {
+  sg_pdl_prologue();
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   int lane = threadIdx.x & 31;
@@ -110,6 +115,7 @@ __global__ void k_sn_rowdot(const float* __restrict__ w, int rows, int cols, con
 __global__ void k_sn_coldot(const float* __restrict__ w, int rows, int cols, const float* __restrict__ v,
                             const float* __restrict__ v_scale, int rows_per_block, float* __restrict__ t,
                             float* __restrict__ scratch, unsigned int* __restrict__ tickets) {
+  sg_pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   int r0 = blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
@@ -126,6 +132,7 @@ __global__ void k_sn_coldot(const float* __restrict__ w, int rows, int cols, con
 }
 // out[0] = rsqrt(max(sum x^2, 1e-12))   (tf.nn.l2_normalize scale), out[1] = sum x^2
 __global__ void k_sn_invnorm(const float* __restrict__ x, int n, float* __restrict__ out) {
+  sg_pdl_prologue();
   __shared__ float sm[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += x[i] * x[i];
@@ -135,6 +142,7 @@ __global__ void k_sn_invnorm(const float* __restrict__ x, int n, float* __restri
 // sigma = (v W) . u_hat = sum_c t[c] * (t[c]*inv_t) ; u_out = t*inv_t
 __global__ void k_sn_sigma(const float* __restrict__ t, int cols, const float* __restrict__ inv_t, float* __restrict__ u_out,
                            float* __restrict__ sigma) {
+  sg_pdl_prologue();
   __shared__ float sm[32];
   float s = *inv_t, acc = 0.f;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) {
@@ -146,6 +154,7 @@ __global__ void k_sn_sigma(const float* __restrict__ t, int cols, const float* _
   if (threadIdx.x == 0) *sigma = r;
 }
 __global__ void k_sn_scale(const float* __restrict__ w, long long n, const float* __restrict__ sigma, float* __restrict__ out) {
+  sg_pdl_prologue();
   float inv = 1.f / *sigma;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = w[i] * inv;
@@ -159,7 +168,7 @@ static int adam_impl(sg_ctx* ctx, float* w, const float* g, float* m, float* v, 
   if (n == 0) return SG_OK;
   long long n4 = (((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)wb) & 15) == 0 ? n / 4 : 0;
   long long need = (n / 4 + 256) / 256, cap = (long long)ctx->num_sms * 8;
-  k_adam<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, m, v, n4, n, lr_t, beta1, beta2, eps, (__nv_bfloat16*)wb, lr_dev);
+  sg_launch(ctx, k_adam, (int)(need < cap ? need : cap), 256, 0, w, g, m, v, n4, n, lr_t, beta1, beta2, eps, (__nv_bfloat16*)wb, lr_dev);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -180,7 +189,7 @@ int sg_adam_mirror(sg_ctx* ctx, float* w, const float* g, float* m, float* v, vo
  * advances (t < 0) the device step counter and writes lr_t; sg_adam_dev is sg_adam[_mirror] reading lr_t from lr_dev */
 int sg_adam_prepare(sg_ctx* ctx, int* step_dev, float* lr_dev, int t, float lr, float beta1, float beta2) {
   SG_REQUIRE(ctx && step_dev && lr_dev, "sg_adam_prepare: NULL");
-  k_adam_prepare<<<1, 32, 0, ctx->stream>>>(step_dev, lr_dev, t, lr, beta1, beta2);
+  sg_launch(ctx, k_adam_prepare, 1, 32, 0, step_dev, lr_dev, t, lr, beta1, beta2);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -202,11 +211,11 @@ int sg_adam_fused(sg_ctx* ctx, float* w, float* g, float* m, float* v, void* w_m
   int grid = (int)(need < cap ? need : cap);
   __nv_bfloat16* wb = (__nv_bfloat16*)w_mirror_bf16;
   if (beta1 == 0.f) {
-    if (clear_grad) k_adam_fused<true, true><<<grid, 256, 0, ctx->stream>>>(w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
-    else k_adam_fused<true, false><<<grid, 256, 0, ctx->stream>>>(w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
+    if (clear_grad) sg_launch(ctx, k_adam_fused<true, true>, grid, 256, 0, w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
+    else sg_launch(ctx, k_adam_fused<true, false>, grid, 256, 0, w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
   } else {
-    if (clear_grad) k_adam_fused<false, true><<<grid, 256, 0, ctx->stream>>>(w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
-    else k_adam_fused<false, false><<<grid, 256, 0, ctx->stream>>>(w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
+    if (clear_grad) sg_launch(ctx, k_adam_fused<false, true>, grid, 256, 0, w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
+    else sg_launch(ctx, k_adam_fused<false, false>, grid, 256, 0, w, g, m, v, n4, n, beta1, beta2, eps, wb, lr_dev);
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;
@@ -216,7 +225,7 @@ int sg_rmsprop(sg_ctx* ctx, float* w, const float* g, float* ms, long long n, fl
   SG_REQUIRE(ctx && w && g && ms && n >= 0, "sg_rmsprop: bad args");
   if (n == 0) return SG_OK;
   long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  k_rmsprop<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, g, ms, n, lr, rho, eps);
+  sg_launch(ctx, k_rmsprop, (int)(need < cap ? need : cap), 256, 0, w, g, ms, n, lr, rho, eps);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -231,9 +240,9 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
   const float* u_cur = u;
   const float* u_scale = nullptr;
   for (int it = 0; it < power_iteration; ++it) {
-    k_sn_rowdot<<<sg_div_up(rows, 8), 256, 0, ctx->stream>>>(w, rows, cols, u_cur, u_scale, v);
+    sg_launch(ctx, k_sn_rowdot, sg_div_up(rows, 8), 256, 0, w, rows, cols, u_cur, u_scale, v);
     SG_POST_LAUNCH(ctx);
-    k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(v, rows, sc);
+    sg_launch(ctx, k_sn_invnorm, 1, 1024, 0, v, rows, sc);
     SG_POST_LAUNCH(ctx);
     int slabs = sg_div_up(rows, 64);
     if (slabs > 32) slabs = 32;
@@ -246,26 +255,26 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
     int rpb = sg_div_up(rows, slabs);
     slabs = sg_div_up(rows, rpb);
     dim3 grid(sg_div_up(cols, 128), slabs);
-    k_sn_coldot<<<grid, 128, 0, ctx->stream>>>(w, rows, cols, v, sc, rpb, t, ctx->det_scratch, ctx->det_tickets);
+    sg_launch(ctx, k_sn_coldot, grid, 128, 0, w, rows, cols, v, sc, rpb, t, ctx->det_scratch, ctx->det_tickets);
     SG_POST_LAUNCH(ctx);
-    k_sn_invnorm<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2);
+    sg_launch(ctx, k_sn_invnorm, 1, 1024, 0, t, cols, sc + 2);
     SG_POST_LAUNCH(ctx);
     u_cur = t;            // next iteration uses u_hat = t * inv_t
     u_scale = sc + 2;
     if (it + 1 < power_iteration) {
       // materialise u_hat so that t can be reused
       SG_REQUIRE(u_out != nullptr, "sg_spectral_norm: power_iteration > 1 needs u_out as a staging buffer");
-      k_sn_sigma<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2, u_out, sigma_out);
+      sg_launch(ctx, k_sn_sigma, 1, 1024, 0, t, cols, sc + 2, u_out, sigma_out);
       SG_POST_LAUNCH(ctx);
       u_cur = u_out;
       u_scale = nullptr;
     }
   }
-  k_sn_sigma<<<1, 1024, 0, ctx->stream>>>(t, cols, sc + 2, u_out, sigma_out);
+  sg_launch(ctx, k_sn_sigma, 1, 1024, 0, t, cols, sc + 2, u_out, sigma_out);
   SG_POST_LAUNCH(ctx);
   long long n = (long long)rows * cols;
   long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  k_sn_scale<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(w, n, sigma_out, w_out);
+  sg_launch(ctx, k_sn_scale, (int)(need < cap ? need : cap), 256, 0, w, n, sigma_out, w_out);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -281,6 +290,7 @@ int sg_spectral_norm(sg_ctx* ctx, const float* w, int rows, int cols, const floa
 __global__ void k_sn_bwd(float* __restrict__ g, const float* __restrict__ dot, const float* __restrict__ v_raw,
                          const float* __restrict__ inv_v, const float* __restrict__ u_hat, const float* __restrict__ sigma, int rows,
                          int cols) {
+  sg_pdl_prologue();
   const float d = *dot, iv = *inv_v, is = 1.f / *sigma;
   const long long n = (long long)rows * cols, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -298,7 +308,7 @@ extern "C" int sg_spectral_norm_bwd(sg_ctx* ctx, float* g, const float* w_sn, in
   if (rc != SG_OK) return rc;
   long long n = (long long)rows * cols;
   long long need = (n + 255) / 256, cap = (long long)ctx->num_sms * 8;
-  k_sn_bwd<<<(int)(need < cap ? need : cap), 256, 0, ctx->stream>>>(g, dot_scratch, fwd_scratch, fwd_scratch + rows + cols, u_hat, sigma, rows,
+  sg_launch(ctx, k_sn_bwd, (int)(need < cap ? need : cap), 256, 0, g, dot_scratch, fwd_scratch, fwd_scratch + rows + cols, u_hat, sigma, rows,
                                                                       cols);
   SG_POST_LAUNCH(ctx);
   return SG_OK;

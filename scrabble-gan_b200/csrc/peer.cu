@@ -70,6 +70,7 @@ __device__ __forceinline__ void peer_publish_and_wait(const PeerTable& pt) {
 
 template <typename T>
 __global__ void __launch_bounds__(512) k_peer_allreduce(T* __restrict__ data, int n, PeerTable pt) {
+  sg_pdl_prologue();
   pt.seq = peer_next_seq(pt);
   const size_t slot = (size_t)(pt.seq & 1u) * SG_PEER_SLOT_BYTES;
   T* mine = reinterpret_cast<T*>(pt.buf[pt.rank] + slot);
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restri
                                                             float eps, float momentum, float* __restrict__ sums_out,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
                                                             float* __restrict__ mm, float* __restrict__ mv, PeerTable pt) {
+  sg_pdl_prologue();
   __shared__ double red[1024];
   pt.seq = peer_next_seq(pt);
   const int c2 = 2 * c;
@@ -159,8 +161,8 @@ int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsi
   if (rc != SG_OK) return rc;
   int threads = n >= 512 ? 512 : (n >= 256 ? 256 : 128);
   if (threads < 32 * ((world + 31) / 32)) threads = 32 * ((world + 31) / 32);
-  if (is_f64) k_peer_allreduce<double><<<1, threads, 0, ctx->stream>>>((double*)data, n, pt);
-  else k_peer_allreduce<float><<<1, threads, 0, ctx->stream>>>((float*)data, n, pt);
+  if (is_f64) sg_launch(ctx, k_peer_allreduce<double>, 1, threads, 0, (double*)data, n, pt);
+  else sg_launch(ctx, k_peer_allreduce<float>, 1, threads, 0, (float*)data, n, pt);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }
@@ -175,7 +177,7 @@ int sg_bn_finalize_peer(sg_ctx* ctx, const float* partial, int nblocks, int c, d
   PeerTable pt;
   int rc = make_table(&pt, peer_bufs, world, rank, "sg_bn_finalize_peer");
   if (rc != SG_OK) return rc;
-  k_bn_finalize_peer<<<1, 1024, 0, ctx->stream>>>(partial, nblocks, c, count_total, eps, momentum, sums_out, mean, rstd, moving_mean,
+  sg_launch(ctx, k_bn_finalize_peer, 1, 1024, 0, partial, nblocks, c, count_total, eps, momentum, sums_out, mean, rstd, moving_mean,
                                                  moving_var, pt);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
