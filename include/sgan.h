@@ -98,6 +98,12 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
 /* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the shortcut of a ResNet block
  * (resnet_ops.py:109-114) accumulated in TMEM as extra k-blocks of the main conv -- no second pass over the output.
  * d2: 1x1, stride 1, same batch / pixel grid / c_out / operand dtype; both filters packed (sg_conv_pack_weights). */
+/* sg_conv_fwd_tc plus a rank-1 term in the epilogue: out[p, c] = conv(in)[p, c] + bias[c] + r1_x[p] * r1_w[c] (before ReLU /
+ * mask).  This is the 1x1 shortcut conv of a residual block whose input has ONE channel (D.B1 on the raw image,
+ * resnet_ops.py:107-110): an outer product, folded into the main conv instead of a launch that re-reads and re-writes the
+ * whole output.  r1_x: fp32 [n, out_h, out_w]; r1_w: fp32 [c_out]; unit output stride only. */
+int sg_conv_fwd_tc_rank1(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
+                         const void* mask, void* out, const float* r1_x, const float* r1_w);
 int sg_conv_fwd_tc_dual(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
                         const sg_conv_desc* d2, const void* in2, const void* w_packed2, const float* bias,
                         const void* mask, void* out);

@@ -139,6 +139,10 @@ class ResNetBlockDown:
             # conv2 and the 1x1 shortcut in ONE launch: the shortcut's k-blocks land in the same TMEM accumulator
             bsum = ops.axpby(rt, 1.0, self.conv2.b.data, 1.0, self.short.b.data)
             h2 = self.conv2.forward_with_shortcut(rt, h1, self.short, xs, bsum)
+        if h2 is None and narrow and rt.use_tc and rt.fuse_shortcut and self.ci == 1:
+            # one-channel input (the image): the 1x1 shortcut is an outer product, added in conv2's epilogue
+            bsum = ops.axpby(rt, 1.0, self.conv2.b.data, 1.0, self.short.b.data)
+            h2 = self.conv2.forward_with_rank1_shortcut(rt, h1, self.short, xs, bsum)
         if h2 is None:
             h2 = self.conv2.forward(rt, h1)
             self.short.forward(rt, xs, out=h2, accumulate=True)

@@ -521,6 +521,210 @@ __global__ void __launch_bounds__(256, 4) k_conv_fwd_cin1(sg_conv_desc d, const 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Edge layers, third generation (C = 64 on the wide side, 3x3 "same" or 1x1, unit strides): 4 consecutive pixels x 8
+// channels per thread.  ncu on the second-generation kernels (profiles/r02_edge_kernels_ncu.md) showed the L1/LSU path at
+// 60-80 % -- k_conv_fwd_cout1 re-read each input pixel once per tap with two 8-byte loads, k_conv_fwd_cin1<.,32> wrote its
+// 64 bf16 channels with 8-byte stores at a 64-byte lane stride (16 wavefronts per store) -- while DRAM sat at 5-10 %.  Here
+// a thread keeps a 3 x 6 pixel patch in registers for its 4 outputs (each input pixel is loaded 1.5 times, not 9), every
+// global access is a 16-byte vector per lane, and the 8 threads of a pixel quad cover the 64 channels of a pixel
+// contiguously (full 128-byte lines).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8f(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __bfloat1622float2(h[j]);
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8f(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); r.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); r.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); r.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); r.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+// taps of a 3x3 "same" / 1x1 conv as a dense 3 x 3 table: slot (dy + 1) * 3 + (dx + 1) -> tap index or -1
+struct EdgeTaps { int slot[9]; };
+
+// c_out == 1, c_in == 64: out[p] = act(b + sum_{t, c} in[p + tap_t, c] * w[t, c])
+template <typename TIn>
+__global__ void __launch_bounds__(256, 3) k_conv_fwd_cout1_q4(sg_conv_desc d, EdgeTaps tp, const TIn* __restrict__ in, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, const void* __restrict__ mask,
+                                                               void* __restrict__ out) {
+  sg_pdl_prologue();
+  __shared__ __align__(16) float ws[9][64];               // dense 3 x 3 slots (zero where the conv has no tap)
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) {
+    int sl = i / 64, ci = i - sl * 64;
+    int t = tp.slot[sl];
+    ws[sl][ci] = t >= 0 ? w[d.tap_w_off[t] + (long long)ci * d.w_ci_stride] : 0.f;
+  }
+  __syncthreads();
+  const float b0 = bias ? bias[0] : 0.f;
+  const int oct = threadIdx.x & 7;                         // channel octet of this thread
+  const int quads_x = d.grid_w >> 2;
+  const long long nquads = (long long)d.n * d.grid_h * quads_x;
+  for (long long q = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); q < nquads; q += (long long)gridDim.x * 32) {
+    const int xq = (int)(q % quads_x);
+    const long long row = q / quads_x;
+    const int y = (int)(row % d.grid_h);
+    const long long ni = row / d.grid_h;
+    const int x0 = xq * 4;
+    const TIn* img = in + ni * d.in_h * d.in_w * 64 + oct * 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = y + r - 1;
+      if (iy < 0 || iy >= d.in_h) continue;
+      if (r != 1 && tp.slot[3 * r] < 0 && tp.slot[3 * r + 1] < 0 && tp.slot[3 * r + 2] < 0) continue;
+      float v[6][8];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int ix = x0 + j - 1;
+        if (ix >= 0 && ix < d.in_w) ld8f(img + ((long long)iy * d.in_w + ix) * 64, v[j]);
+        else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[j][c] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[3 * r + dx][oct * 8]), w1 = *reinterpret_cast<const float4*>(&ws[3 * r + dx][oct * 8 + 4]);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float (&u)[8] = v[px + dx];
+          float a = acc[px];
+          a = fmaf(u[0], w0.x, a); a = fmaf(u[1], w0.y, a); a = fmaf(u[2], w0.z, a); a = fmaf(u[3], w0.w, a);
+          a = fmaf(u[4], w1.x, a); a = fmaf(u[5], w1.y, a); a = fmaf(u[6], w1.z, a); a = fmaf(u[7], w1.w, a);
+          acc[px] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      acc[px] += __shfl_xor_sync(0xffffffffu, acc[px], 1);
+      acc[px] += __shfl_xor_sync(0xffffffffu, acc[px], 2);
+      acc[px] += __shfl_xor_sync(0xffffffffu, acc[px], 4);
+    }
+    if (oct < 4) {                                         // thread `oct` of the quad finishes pixel x0 + oct
+      float vv = (oct == 0 ? acc[0] : oct == 1 ? acc[1] : oct == 2 ? acc[2] : acc[3]) + b0;
+      const long long idx = (ni * d.out_h + y) * d.out_w + x0 + oct;
+      if (d.relu) vv = fmaxf(vv, 0.f);
+      if (mask) vv = ld_any(mask, idx, d.mask_dt) > 0.f ? vv : 0.f;
+      if (d.accumulate) vv += ld_any(out, idx, d.out_dt);
+      st_any(out, idx, d.out_dt, vv);
+    }
+  }
+}
+
+// c_in == 1 (fp32 input), c_out == 64: out[p, :] = act(b + sum_t in[p + tap_t] * w[t, :]) (+ out when accumulate)
+template <typename TOut>
+__global__ void __launch_bounds__(256, 3) k_conv_fwd_cin1_q4(sg_conv_desc d, EdgeTaps tp, const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, TOut* __restrict__ out) {
+  sg_pdl_prologue();
+  __shared__ __align__(16) float ws[10][64];              // dense 3 x 3 slots + bias row
+  for (int i = threadIdx.x; i < 10 * 64; i += 256) {
+    int sl = i / 64, co = i - sl * 64;
+    float v = 0.f;
+    if (sl < 9) {
+      int t = tp.slot[sl];
+      if (t >= 0) v = w[d.tap_w_off[t] + (long long)co * d.w_co_stride];
+    } else if (bias) v = bias[co];
+    ws[sl][co] = v;
+  }
+  __syncthreads();
+  const int oct = threadIdx.x & 7;
+  const int quads_x = d.grid_w >> 2;
+  const long long nquads = (long long)d.n * d.grid_h * quads_x;
+  for (long long q = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); q < nquads; q += (long long)gridDim.x * 32) {
+    const int xq = (int)(q % quads_x);
+    const long long row = q / quads_x;
+    const int y = (int)(row % d.grid_h);
+    const long long ni = row / d.grid_h;
+    const int x0 = xq * 4;
+    const float* img = in + ni * d.in_h * d.in_w;
+    float acc[4][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&ws[9][oct * 8]), b1 = *reinterpret_cast<const float4*>(&ws[9][oct * 8 + 4]);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        acc[px][0] = b0.x; acc[px][1] = b0.y; acc[px][2] = b0.z; acc[px][3] = b0.w;
+        acc[px][4] = b1.x; acc[px][5] = b1.y; acc[px][6] = b1.z; acc[px][7] = b1.w;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = y + r - 1;
+      if (iy < 0 || iy >= d.in_h) continue;
+      if (r != 1 && tp.slot[3 * r] < 0 && tp.slot[3 * r + 1] < 0 && tp.slot[3 * r + 2] < 0) continue;
+      float xv[6];
+      {
+        // x0 is a multiple of 4 and the row starts 16-byte aligned: one float4 for the 4 centre pixels + the two neighbours
+        const float* rp = img + (long long)iy * d.in_w + x0;
+        float4 c4 = __ldg(reinterpret_cast<const float4*>(rp));
+        xv[1] = c4.x; xv[2] = c4.y; xv[3] = c4.z; xv[4] = c4.w;
+        xv[0] = x0 > 0 ? __ldg(rp - 1) : 0.f;
+        xv[5] = x0 + 4 < d.in_w ? __ldg(rp + 4) : 0.f;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[3 * r + dx][oct * 8]), w1 = *reinterpret_cast<const float4*>(&ws[3 * r + dx][oct * 8 + 4]);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float xs = xv[px + dx];
+          acc[px][0] = fmaf(xs, w0.x, acc[px][0]); acc[px][1] = fmaf(xs, w0.y, acc[px][1]); acc[px][2] = fmaf(xs, w0.z, acc[px][2]);
+          acc[px][3] = fmaf(xs, w0.w, acc[px][3]); acc[px][4] = fmaf(xs, w1.x, acc[px][4]); acc[px][5] = fmaf(xs, w1.y, acc[px][5]);
+          acc[px][6] = fmaf(xs, w1.z, acc[px][6]); acc[px][7] = fmaf(xs, w1.w, acc[px][7]);
+        }
+      }
+    }
+    TOut* op = out + ((ni * d.out_h + y) * d.out_w + x0) * 64 + oct * 8;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (d.relu) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[px][c] = fmaxf(acc[px][c], 0.f);
+      }
+      if (d.accumulate) {
+        float pv[8];
+        ld8f(op + px * 64, pv);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[px][c] += pv[c];
+      }
+      st8f(op + px * 64, acc[px]);
+    }
+  }
+}
+
+// true (and the slot table filled) when the conv is a unit-stride 3x3-"same"-like or 1x1 stencil on equal input / output grids
+static bool edge_taps(const sg_conv_desc* d, EdgeTaps* tp) {
+  if (!(d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0)) return false;
+  if (d->in_h != d->grid_h || d->in_w != d->grid_w || d->out_h != d->grid_h || d->out_w != d->grid_w || d->grid_w % 4 != 0) return false;
+  for (int i = 0; i < 9; ++i) tp->slot[i] = -1;
+  for (int t = 0; t < d->ntaps; ++t) {
+    int dy = d->tap_dy[t], dx = d->tap_dx[t];
+    if (dy < -1 || dy > 1 || dx < -1 || dx > 1) return false;
+    int sl = (dy + 1) * 3 + dx + 1;
+    if (tp->slot[sl] >= 0) return false;
+    tp->slot[sl] = t;
+  }
+  return true;
+}
+
 static int check_desc(const sg_conv_desc* d, const char* who) {
   SG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   SG_REQUIRE(d->n >= 0 && d->in_h > 0 && d->in_w > 0 && d->c_in > 0 && d->out_h > 0 && d->out_w > 0 && d->c_out > 0,
@@ -543,6 +747,26 @@ int sg_conv_fwd_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const f
   if (rc != SG_OK) return rc;
   long long M = (long long)d->n * d->grid_h * d->grid_w;
   if (M == 0) return SG_OK;
+  {
+    EdgeTaps tp;
+    const bool q4 = ctx->edge_q4 && M < (1LL << 40) && edge_taps(d, &tp);
+    if (q4 && d->c_out == 1 && d->c_in == 64 && ((uintptr_t)in & 15) == 0) {
+      long long need = (M / 4 + 31) / 32, cap = (long long)ctx->num_sms * 12;
+      int grid = (int)(need < cap ? need : cap);
+      if (d->in_dt == SG_F32) sg_launch(ctx, k_conv_fwd_cout1_q4<float>, grid, 256, 0, *d, tp, (const float*)in, w_master, bias, mask, out);
+      else sg_launch(ctx, k_conv_fwd_cout1_q4<__nv_bfloat16>, grid, 256, 0, *d, tp, (const __nv_bfloat16*)in, w_master, bias, mask, out);
+      SG_POST_LAUNCH(ctx);
+      return SG_OK;
+    }
+    if (q4 && d->c_in == 1 && d->c_out == 64 && d->in_dt == SG_F32 && !mask && ((uintptr_t)out & 15) == 0 && ((uintptr_t)in & 15) == 0) {
+      long long need = (M / 4 + 31) / 32, cap = (long long)ctx->num_sms * 12;
+      int grid = (int)(need < cap ? need : cap);
+      if (d->out_dt == SG_F32) sg_launch(ctx, k_conv_fwd_cin1_q4<float>, grid, 256, 0, *d, tp, (const float*)in, w_master, bias, (float*)out);
+      else sg_launch(ctx, k_conv_fwd_cin1_q4<__nv_bfloat16>, grid, 256, 0, *d, tp, (const float*)in, w_master, bias, (__nv_bfloat16*)out);
+      SG_POST_LAUNCH(ctx);
+      return SG_OK;
+    }
+  }
   {
     int tpp = d->c_in / 8;
     bool pow2 = tpp >= 1 && tpp <= 32 && (tpp & (tpp - 1)) == 0;

@@ -168,6 +168,10 @@ struct alignas(64) TcFwdParams {
   const float* bias;
   const void* mask;
   void* out;
+  // optional rank-1 term of the epilogue: out[p, c] += r1_x[p] * r1_w[c] -- the 1x1 shortcut conv of a block whose input has ONE
+  // channel (D.B1.short on the raw image, resnet_ops.py:107-110), which is an outer product, not a GEMM
+  const float* r1_x;            // [n, out_h, out_w] fp32, indexed like the output pixels
+  const float* r1_w;            // [c_out] fp32
   // split tail (wave quantisation): tiles [0, t_full) are whole units; each later tile is `split` units, one contiguous k-block
   // range each, on `split` consecutive CTAs.  Every unit parks the accumulator chunks it does not own in `part`, the units of a
   // tile meet at `cnt`, and each finishes its own share of the tile's 32-column chunks: own accumulators + the peers' partials
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       long long rbase[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) rbase[i] = __shfl_sync(0xffffffffu, base, tr0 + 8 * i);
+      const float r1 = (p.r1_x && valid) ? __ldg(p.r1_x + (base - col_t * p.BN) / p.c_out) : 0.f;
       mbar_wait(bar_tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
@@ -441,6 +446,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             for (int j = 0; j < 32; j += 4) {
               float4 b = __ldg(reinterpret_cast<const float4*>(bp + j));
               f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.r1_x) {
+            const float* wp = p.r1_w + col_t * p.BN + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + j));
+              f[j] = fmaf(r1, w4.x, f[j]); f[j + 1] = fmaf(r1, w4.y, f[j + 1]); f[j + 2] = fmaf(r1, w4.z, f[j + 2]); f[j + 3] = fmaf(r1, w4.w, f[j + 3]);
             }
           }
           if (p.relu) {
@@ -1237,7 +1250,7 @@ static double tc_split_plan(long long tiles, int sms, int nkb, int bn, int enabl
 
 static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, int b_mode, const float* bias,
                             const void* mask, void* out, const sg_conv_desc* d2 = nullptr, const void* in2 = nullptr,
-                            const void* w_packed2 = nullptr) {
+                            const void* w_packed2 = nullptr, const float* r1_x = nullptr, const float* r1_w = nullptr) {
   SG_REQUIRE(ctx && in && w_packed && out, "sg_conv_fwd_tc: NULL");
   int rc = tc_check(d, "sg_conv_fwd_tc");
   if (rc != SG_OK) return rc;
@@ -1258,6 +1271,11 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   p.out_h = d->out_h; p.out_w = d->out_w; p.out_sy = d->out_sy; p.out_sx = d->out_sx; p.out_py = d->out_py; p.out_px = d->out_px;
   p.relu = d->relu; p.accumulate = d->accumulate; p.out_dt = d->out_dt; p.mask_dt = d->mask_dt;
   p.bias = bias; p.mask = mask; p.out = out;
+  if (r1_x) {
+    SG_REQUIRE(r1_w && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0 && ((uintptr_t)r1_w & 15) == 0,
+               "sg_conv_fwd_tc_rank1: needs a unit-stride output and a 16-byte aligned weight vector");
+    p.r1_x = r1_x; p.r1_w = r1_w;
+  }
   choose_box(d->grid_w, d->grid_h, d->n, 128, 1, &p.TW, &p.TH, &p.TN);
   p.tiles_x = sg_div_up(d->grid_w, p.TW); p.tiles_y = sg_div_up(d->grid_h, p.TH); p.tiles_n = sg_div_up(d->n, p.TN);
   const int nkb_total = d->ntaps * (d->c_in / KC) + (d2 ? d2->c_in / KC : 0);
@@ -1368,6 +1386,12 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
 
 /* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the ResNet block's shortcut (resnet_ops.py:109-114)
  * accumulated in TMEM as extra k-blocks of the main conv instead of a second read-modify-write pass over the output */
+int sg_conv_fwd_tc_rank1(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
+                         const void* mask, void* out, const float* r1_x, const float* r1_w) {
+  SG_REQUIRE(r1_x && r1_w, "sg_conv_fwd_tc_rank1: NULL rank-1 operands");
+  return conv_fwd_tc_impl(ctx, d, in, w_packed, 0, bias, mask, out, nullptr, nullptr, nullptr, r1_x, r1_w);
+}
+
 int sg_conv_fwd_tc_dual(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const sg_conv_desc* d2,
                         const void* in2, const void* w_packed2, const float* bias, const void* mask, void* out) {
   SG_REQUIRE(d2 != nullptr, "sg_conv_fwd_tc_dual: NULL second descriptor");

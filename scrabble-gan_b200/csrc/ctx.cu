@@ -40,6 +40,8 @@ int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out) {
   {
     const char* e = getenv("SGAN_NO_SPLIT_TAIL");
     c->conv_split_tail = !(e && e[0] == '1');
+    e = getenv("SGAN_NO_EDGE_Q4");
+    c->edge_q4 = !(e && e[0] == '1');
     e = getenv("SGAN_PDL");
     c->pdl = e && e[0] == '1';
   }

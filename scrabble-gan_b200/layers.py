@@ -85,6 +85,18 @@ class ConvLayer:
         ops.conv_run_dual(rt, d, x, self._pack(rt, "fwd", d), d2, x2, short._pack(rt, "fwd", d2), bias, None, out)
         return out
 
+    def forward_with_rank1_shortcut(self, rt: Runtime, x: torch.Tensor, short: "ConvLayer", x2: torch.Tensor, bias, out_dt: int = SG_F32):
+        """self(x) + short(x2) + bias in ONE tensor-core launch when short is a 1x1 conv of a ONE-channel fp32 tensor (the
+        raw image): that conv is the outer product x2[p] * w[c], added in the epilogue.  None when not applicable."""
+        n, h, w, _ = x.shape
+        d = self._desc("fwd", n, h, w, dt_of(x), out_dt, 0, 0)
+        if short.kh != 1 or short.kw != 1 or short.ci != 1 or short.co != self.co or dt_of(x2) != SG_F32 or not ops.tc_ok(rt, d) or \
+                self.out_hw(h, w) != (h, w):
+            return None
+        out = rt.empty((n, h, w, self.co), out_dt)
+        ops.conv_run_rank1(rt, d, x, self._pack(rt, "fwd", d), bias, None, out, x2, short.w.eff.view(-1))
+        return out
+
     def dgrad(self, rt: Runtime, dy: torch.Tensor, in_hw: Tuple[int, int], mask=None, out_dt: int = SG_F32, out=None,
               accumulate: bool = False) -> torch.Tensor:
         n = dy.shape[0]

@@ -198,6 +198,12 @@ def _conv_run(rt: Runtime, d: ConvDesc, x, w_master, w_packed, bias, mask, out, 
         call.sg_conv_fwd_simt(rt.ctx, C.byref(d), _p(x), _p(w_master), _p(bias), _p(mask), _p(out))
 
 
+def conv_run_rank1(rt: Runtime, d: ConvDesc, x, w_packed, bias, mask, out, r1_x, r1_w) -> None:
+    """Tensor-core conv with the rank-1 epilogue term out[p, c] += r1_x[p] * r1_w[c] (a 1x1 conv of a one-channel tensor)."""
+    with _Traced(rt, "tc_rank1", d):
+        call.sg_conv_fwd_tc_rank1(rt.ctx, C.byref(d), _p(x), _p(w_packed), _p(bias), _p(mask), _p(out), _p(r1_x), _p(r1_w))
+
+
 def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_packed2, bias, mask, out) -> None:
     """Main conv + 1x1 shortcut conv accumulated in ONE tensor-core launch (both filters packed)."""
     with _Traced(rt, "tc_dual", d, d2):

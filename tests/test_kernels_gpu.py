@@ -64,6 +64,9 @@ CONV_CASES_SIMT = [
     (3, 5, 7, 1, 64, 3, "same"),       # pixel count not a multiple of the 64-pixel chunk
     (3, 5, 7, 64, 1, 3, "same"),
     (2, 4, 9, 1, 32, 3, "same"),       # Cin = 1, 4 channel groups
+    (2, 8, 16, 64, 1, 3, "same"),      # Cout = 1, 4 pixels x 8 channels per thread (width % 4 == 0)
+    (3, 4, 4, 64, 1, 1, "same"),       # ... single tap, one quad per row
+    (3, 4, 4, 1, 64, 3, "same"),
 ]
 
 
