@@ -710,6 +710,89 @@ __global__ void __launch_bounds__(256, 3) k_conv_fwd_cin1_q4(sg_conv_desc d, Edg
   }
 }
 
+// Filter gradient of the same edge layers (see k_wgrad_narrow64 for the algebra): dW[t][c] += sum_p wide[p, c] * narrow[p + s * tap_t].
+// 4 pixels x 8 channels per thread with all 9 x 8 partial filter entries in registers: per quad 4 vector loads of the wide
+// tensor, a 3 x 6 patch of the narrow one and 288 FMA, no shared-memory staging and no barriers inside the pixel loop; the
+// block then folds its 32 quad lanes (shuffles, one shared-memory pass) into ONE [9][64] partial for the ordered combine.
+// tp.slot holds the tap of the patch position (s * dy + 1) * 3 + (s * dx + 1).
+template <typename TW>
+__global__ void __launch_bounds__(256, 2) k_wgrad_edge_q4(const TW* __restrict__ wide, const void* __restrict__ narrow, int narrow_dt, int n, int H,
+                                                           int W, EdgeTaps tp, sg_conv_desc d, float* __restrict__ dw, int narrow_in,
+                                                           float* __restrict__ scratch, unsigned int* __restrict__ ticket) {
+  sg_pdl_prologue();
+  __shared__ float red[8][576];
+  const int oct = threadIdx.x & 7;
+  const int quads_x = W >> 2;
+  const long long nquads = (long long)n * H * quads_x;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+  bool row_used[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) row_used[r] = tp.slot[3 * r] >= 0 || tp.slot[3 * r + 1] >= 0 || tp.slot[3 * r + 2] >= 0;
+  for (long long q = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); q < nquads; q += (long long)gridDim.x * 32) {
+    const int xq = (int)(q % quads_x);
+    const long long row = q / quads_x;
+    const int y = (int)(row % H);
+    const long long ni = row / H;
+    const int x0 = xq * 4;
+    float wv[4][8];
+    {
+      const TW* wp = wide + ((ni * H + y) * W + x0) * 64 + oct * 8;
+#pragma unroll
+      for (int px = 0; px < 4; ++px) ld8f(wp + px * 64, wv[px]);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = y + r - 1;
+      if (!row_used[r] || iy < 0 || iy >= H) continue;
+      float xv[6];
+      const long long rb = (ni * H + iy) * W + x0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int ix = x0 + j - 1;
+        xv[j] = (ix >= 0 && ix < W) ? ld_any(narrow, rb + j - 1, narrow_dt) : 0.f;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float xs = xv[px + dx];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[3 * r + dx][c] = fmaf(xs, wv[px][c], acc[3 * r + dx][c]);
+        }
+      }
+    }
+  }
+  // fold the 4 quads of the warp (lanes with equal oct), then the 8 warps through shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v = acc[t][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) red[warp][t * 64 + oct * 8 + c] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 576; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][i];
+    scratch[(long long)blockIdx.x * 576 + i] = sum;
+  }
+  sg_det_finish(scratch, scratch + (long long)gridDim.x * 576, ticket, gridDim.x, blockIdx.x, 576, [&](int i, float sum) {
+    const int sl = i >> 6, cc = i & 63;
+    const int t = tp.slot[sl];
+    if (t < 0) return;
+    long long off = d.tap_w_off[t] + (narrow_in ? (long long)cc * d.w_co_stride : (long long)cc * d.w_ci_stride);
+    dw[off] += sum;
+  });
+}
+
 // true (and the slot table filled) when the conv is a unit-stride 3x3-"same"-like or 1x1 stencil on equal input / output grids
 static bool edge_taps(const sg_conv_desc* d, EdgeTaps* tp) {
   if (!(d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_py == 0 && d->out_px == 0)) return false;
@@ -833,6 +916,21 @@ int sg_conv_wgrad_simt(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const
       if ((!narrow_in || (d->grid_h == d->out_h && d->grid_w == d->out_w)) && (narrow_in || (d->grid_h == d->out_h && d->grid_w == d->out_w)) &&
           ((uintptr_t)wide & 15) == 0) {
         long long Pw = (long long)d->n * H * W;
+        EdgeTaps tp0, tp;
+        if (ctx->edge_q4 && nH == H && nW == W && edge_taps(d, &tp0) && ((uintptr_t)nar & 15) == 0) {
+          // patch position of tap t in the narrow tensor: +tap for c_in == 1 (narrow = input), -tap for c_out == 1 (narrow = dy)
+          for (int i = 0; i < 9; ++i) tp.slot[i] = narrow_in ? tp0.slot[i] : tp0.slot[8 - i];
+          long long need = (Pw / 4 + 31) / 32, cap = (long long)ctx->num_sms * 2;
+          int grid = (int)(need < cap ? need : cap);
+          if (wide_dt == SG_F32)
+            sg_launch(ctx, k_wgrad_edge_q4<float>, grid, 256, 0, (const float*)wide, nar, nar_dt, d->n, H, W, tp, *d, dw_master, narrow_in ? 1 : 0,
+                      ctx->det_scratch, ctx->det_tickets);
+          else
+            sg_launch(ctx, k_wgrad_edge_q4<__nv_bfloat16>, grid, 256, 0, (const __nv_bfloat16*)wide, nar, nar_dt, d->n, H, W, tp, *d, dw_master,
+                      narrow_in ? 1 : 0, ctx->det_scratch, ctx->det_tickets);
+          SG_POST_LAUNCH(ctx);
+          return SG_OK;
+        }
         long long nchunks = (Pw + WN_PIX - 1) / WN_PIX;
         long long blocks = (long long)ctx->num_sms * 4;
         if (blocks > nchunks) blocks = nchunks;
