@@ -295,18 +295,26 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             m.prepack(rt)                           # all forward filters of the network that the last Adam step made stale: one launch
 
     # ---- forward passes (data_utils.py:398-415) -------------------------------------------------------------------
+    # D and R read the same images and share nothing else: R's passes go to the side stream (rt.branch) and run next to D's --
+    # R's layers are small (most of its launches fill a fraction of the SMs), so they largely disappear inside D's time
     if fused:
         gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True, img_out=xcat[:b])
+        br = rt.branch()
+        with br:
+            r_cat, rcc = recognizer.forward(rt, xcat, ycat)
         d_cat, dcc = discriminator.forward(rt, xcat)
-        r_cat, rcc = recognizer.forward(rt, xcat, ycat)
+        br.join()
         d_fake, d_real = d_cat.view(-1)[:b], d_cat.view(-1)[b:]
         r_fake, r_real = r_cat[:b], r_cat[b:]
     else:
         gen_images, g_cache = generator.forward(rt, g_in, y_fake, training=True)
+        br = rt.branch()
+        with br:
+            r_fake, rfc = recognizer.forward(rt, gen_images, y_fake)
+            r_real, rrc = recognizer.forward(rt, x_real, y_real)
         d_fake, dfc = discriminator.forward(rt, gen_images)
-        r_fake, rfc = recognizer.forward(rt, gen_images, y_fake)
         d_real, drc = discriminator.forward(rt, x_real)
-        r_real, rrc = recognizer.forward(rt, x_real, y_real)
+        br.join()
     s_fake = s_real = s_slot5 = None
     if use_w:
         s_fake, sfc = style_promoter.forward(rt, gen_images)
@@ -334,28 +342,31 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     dimg_r_merged = None
     discriminator.trainable = True
     recognizer.trainable = True
+    br = rt.branch()                     # R's backward (side stream) next to D's two backward passes (main stream)
     if fused:
+        with br:
+            if update_g and rt.merge_r_backward:
+                # ONE backward pass of R over the fused batch: filter gradients from the real half (R-loss, weight 1), image
+                # gradient of the fake half with the G-loss per-sample weights (different samples: nothing mixes)
+                recognizer.trainable = True
+                dimg_r_all = recognizer.backward(rt, rcc, up_r_fake_g, wgrad=True, want_dx=True, wgrad_rows=(b, 2 * b), up_rows=(0, b))
+                dimg_r_merged = dimg_r_all[:b]
+            else:
+                recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
+                rfc = recognizer.slice_cache(rcc, 0, b)
+            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
         discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
         dfc = discriminator.slice_cache(dcc, 0, b)
-        if update_g and rt.merge_r_backward:
-            # ONE backward pass of R over the fused batch: filter gradients from the real half (R-loss, weight 1), image
-            # gradient of the fake half with the G-loss per-sample weights (different samples: nothing mixes)
-            recognizer.trainable = True
-            dimg_r_all = recognizer.backward(rt, rcc, up_r_fake_g, wgrad=True, want_dx=True, wgrad_rows=(b, 2 * b), up_rows=(0, b))
-            dimg_r_merged = dimg_r_all[:b]
-        else:
-            recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
-            rfc = recognizer.slice_cache(rcc, 0, b)
-        pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
     else:
+        with br:
+            recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
+            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
-        recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
-        pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
     if use_w:
         style_promoter.trainable = True
         style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
@@ -367,11 +378,13 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     if update_g:
         recognizer.trainable = False
         discriminator.trainable = False
-        dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
-        if dimg_r_merged is not None:
-            dimg_r = dimg_r_merged
+        if dimg_r_merged is None:
+            with br:
+                dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
         else:
-            dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
+            dimg_r = dimg_r_merged
+        dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
+        br.join()
         if use_w:
             style_promoter.trainable = False
             if kind == net_loss.hinge.sg_kind:
@@ -390,6 +403,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         generator.backward(rt, g_cache, dimg)
         generator.sn_backward(rt)
         pending.append((id(generator), rt.allreduce_async_(generator.store.g)))
+    br.join()
     # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced: the Adam
     # launches of D and R overlap with the all-reduce of G's bucket, which is the last one to start
     def _apply(opt, model):

@@ -1368,12 +1368,15 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   p.cnt = ctx->det_tickets;
   int grid = p.total_units < ctx->num_sms ? p.total_units : ctx->num_sms;
   size_t smem = (size_t)stages * (p.a_stage_stride + p.b_stage_stride) + 1024 + TC_EPI_STAGING;
+  // split tiles rendezvous inside the kernel: launched cooperatively, so that all CTAs are co-resident even when a kernel of
+  // another stream (rt.branch) holds part of the SMs
+  const bool coop = p.split > 1;
   if (d->in_dt == SG_F32) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sg_launch(ctx, k_conv_tc<float>, grid, TC_THREADS, smem, p);
+    SG_CHECK_CUDA(sg_launch_ex(ctx, coop, k_conv_tc<float>, grid, TC_THREADS, smem, p));
   } else {
     SG_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sg_launch(ctx, k_conv_tc<__nv_bfloat16>, grid, TC_THREADS, smem, p);
+    SG_CHECK_CUDA(sg_launch_ex(ctx, coop, k_conv_tc<__nv_bfloat16>, grid, TC_THREADS, smem, p));
   }
   SG_POST_LAUNCH(ctx);
   return SG_OK;

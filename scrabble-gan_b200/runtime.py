@@ -37,6 +37,12 @@ class Runtime:
         handle = C.c_void_p()
         call.sg_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(handle))
         self.ctx = handle
+        self._main_ctx = handle
+        # second stream + context for work that is independent of the main stream's (the recogniser's passes next to the
+        # discriminator's inside a train step): created on first use by branch()
+        self.side_stream = None
+        self._side_ctx = None
+        self.concurrent_branches = os.environ.get("SGAN_NO_BRANCHES", "0") != "1"
         self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
         self.set_mode(mode)
         # data-parallel state (see dp.py)
@@ -71,7 +77,9 @@ class Runtime:
         self.trace = None                       # diagnostics: a list makes ops.conv_* record (role, shape, events) per launch
         # one packing launch per network and step instead of one per layer
         self.batch_packs = os.environ.get("SGAN_NO_BATCHED_PACKS", "0") != "1"
-        call.sg_ctx_set_speed_mode(self.ctx, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
+        for c in (self._main_ctx, self._side_ctx):
+            if c is not None:
+                call.sg_ctx_set_speed_mode(c, int(mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
 
     # ---- memory helpers (torch = allocator only) ------------------------------------------------------
     def empty(self, shape, dt: int = SG_F32) -> torch.Tensor:
@@ -105,11 +113,27 @@ class Runtime:
 
     def launch_count(self) -> int:
         """libsgan kernels launched so far: direct launches through the C ABI plus the kernel nodes of replayed graphs."""
-        return int(_abi.load().sg_ctx_launch_count(self.ctx)) + self.replayed_launches
+        n = int(_abi.load().sg_ctx_launch_count(self._main_ctx))
+        if self._side_ctx is not None:
+            n += int(_abi.load().sg_ctx_launch_count(self._side_ctx))
+        return n + self.replayed_launches
 
     def use_current_stream(self) -> None:
         self.stream = torch.cuda.current_stream(self.device)
-        call.sg_ctx_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream))
+        call.sg_ctx_set_stream(self._main_ctx, C.c_void_p(self.stream.cuda_stream))
+
+    def branch(self) -> "Branch":
+        """Fork a branch of independent work onto the side stream:
+
+            br = rt.branch()          # the side stream waits for everything enqueued on the main stream so far
+            with br: ...              # launches (and allocations) inside go to the side stream / side context
+            ...                       # main-stream work enqueued here runs concurrently with the branch
+            br.join()                 # the main stream waits for the branch
+
+        The side context owns its own workspace (deterministic-reduction scratch, tickets), so kernels of the two streams
+        never share one.  With concurrent_branches off the branch degenerates to the main stream (same results)."""
+        return Branch(self)
+
 
     # ---- data parallel (sum all-reduce of small statistic vectors and of gradient buckets) -------------
     def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
@@ -147,6 +171,40 @@ class Runtime:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
             return None
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+
+
+class Branch:
+    def __init__(self, rt: Runtime):
+        self.rt = rt
+        self.active = rt.concurrent_branches
+        self._ctxmgr = None
+        if not self.active:
+            return
+        if rt.side_stream is None:
+            rt.side_stream = torch.cuda.Stream(device=rt.device)
+            handle = C.c_void_p()
+            call.sg_ctx_create(rt.device_index, C.c_void_p(rt.side_stream.cuda_stream), C.byref(handle))
+            rt._side_ctx = handle
+            call.sg_ctx_set_speed_mode(handle, int(rt.mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
+        self.main = torch.cuda.current_stream(rt.device)
+        rt.side_stream.wait_stream(self.main)
+
+    def __enter__(self):
+        if self.active:
+            self.rt.ctx = self.rt._side_ctx
+            self._ctxmgr = torch.cuda.stream(self.rt.side_stream)
+            self._ctxmgr.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._ctxmgr.__exit__(*exc)
+            self.rt.ctx = self.rt._main_ctx
+        return False
+
+    def join(self) -> None:
+        if self.active:
+            torch.cuda.current_stream(self.rt.device).wait_stream(self.rt.side_stream)
 
 
 _default: Optional[Runtime] = None
