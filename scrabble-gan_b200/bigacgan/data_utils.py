@@ -374,6 +374,11 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         style_promoter.sn_backward(rt)
         pending.append((id(style_promoter), rt.allreduce_async_(style_promoter.store.g)))
 
+    # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced -------------
+    others = [(discriminator_optimizer, discriminator), (recognizer_optimizer, recognizer)]
+    if use_w:
+        others.append((stylepromoter_optimizer, style_promoter))
+
     # ---- G gradient through the frozen D, R (, W) (data_utils.py:462-468) -----------------------------------------
     if update_g:
         recognizer.trainable = False
@@ -400,29 +405,32 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             call.sg_image_grad_balance_apply(rt.ctx, _p(dimg), _p(dimg_r), dimg.numel(), 1.0, _p(bal), _p(dimg), _p(stats))
         else:
             ops.axpby(rt, 1.0, dimg, 1.0, dimg_r, out=dimg)
+        # D, R (, W) are done with their weights: their optimizer launches (memory-bound) go to the side stream and run
+        # under G's backward pass (compute- and latency-bound) instead of after it
+        bo = rt.branch()
+        with bo:
+            _apply_all(rt, pending, others)
         generator.backward(rt, g_cache, dimg)
         generator.sn_backward(rt)
         pending.append((id(generator), rt.allreduce_async_(generator.store.g)))
-    br.join()
-    # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced: the Adam
-    # launches of D and R overlap with the all-reduce of G's bucket, which is the last one to start
-    def _apply(opt, model):
-        tv = model.store.trainable_variables
-        opt.apply_gradients(zip([v.grad for v in tv], tv))
+        bo.join()
+        _apply_all(rt, pending, [(generator_optimizer, generator)])
+    else:
+        br.join()
+        _apply_all(rt, pending, others)
+    return stats
 
+
+def _apply_all(rt, pending, order):
+    """optimizer.apply_gradients(zip(grads, trainable_variables)) per network (data_utils.py:452-468), each after the
+    all-reduce of ITS gradient bucket (data parallel) has been ordered before the current stream."""
     work = dict(pending)
-    order = [(discriminator_optimizer, discriminator), (recognizer_optimizer, recognizer)]
-    if use_w:
-        order.append((stylepromoter_optimizer, style_promoter))
-    if update_g:
-        order.append((generator_optimizer, generator))
     for opt, model in order:
         w = work.get(id(model))
         if w is not None:
             w.wait()
-        _apply(opt, model)
-
-    return stats
+        tv = model.store.trainable_variables
+        opt.apply_gradients(zip([v.grad for v in tv], tv))
 
 
 def generate_and_save_images(model, epoch, test_input, gen_path, char_vector):
