@@ -470,7 +470,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     rt = runtime.Runtime(device=local_rank, mode=args.dtype)
     runtime.set_runtime(rt)
-    dp.init_data_parallel(rt)
+    if os.environ.get("SGAN_BENCH_INDEPENDENT", "0") != "1":      # diagnostics: N replicas side by side with no exchange at all
+        dp.init_data_parallel(rt)
     world, rank = rt.world_size, rt.rank
     assert world == max(args.gpus, 1) or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 

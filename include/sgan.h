@@ -140,6 +140,11 @@ int sg_tanh_bwd(sg_ctx* ctx, const float* dy, const float* y, float* dx, long lo
 /* x[r, :] *= w[r] */
 int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long cols);
 /* out[0] (+)= sum a*b */
+/* x[i, :] *= up[i] * mult for the samples i < n of a batch-first tensor [n, per_sample] (fp32 / bf16; per_sample % 8 == 0).
+ * Samples with factor 1 are skipped, samples with factor 0 are zero-filled without being read.  Used by the merged
+ * discriminator backward: the fake half of the batch is back-propagated ONCE with a constant upstream weight; the filter
+ * gradients of the D loss then need the per-sample weights of that loss (hinge: 0 or 1). */
+int sg_scale_samples(sg_ctx* ctx, void* x, int dt, int n, long long per_sample, const float* up, float mult);
 int sg_dot(sg_ctx* ctx, const float* a, const float* b, long long n, float* out, int accumulate);
 /* out[c] (+)= sum_r x[r,c]   (bias gradients) */
 int sg_colsum(sg_ctx* ctx, const void* x, int dt, long long rows, int cols, float* out, int accumulate);
@@ -192,6 +197,19 @@ size_t sg_peer_buffer_bytes(void);
 size_t sg_peer_max_payload_bytes(void);
 int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsigned long long* peer_bufs, int world,
                           int rank);
+/* Gradient buckets (data parallel, SURVEY 8e exchange point 3): SUM all-reduce of a large fp32 vector that every replica keeps in
+ * peer-mapped (symmetric) memory, moved by the COPY ENGINES over NVLink -- the SMs stay with the step's compute kernels, which
+ * an SM-based collective running beside 148-CTA persistent kernels cannot offer (measured: overlapping NCCL's all-reduce with
+ * the backward pass gained nothing).  Reduce-scatter + all-gather, pull side: barrier; memcpy MY shard of every peer's bucket
+ * into staging; add in rank order (k_bucket_reduce: bit-identical on every replica); barrier; memcpy every peer's reduced shard;
+ * barrier.  All on ctx's stream: enqueue it on a stream of its own and it overlaps with whatever the compute stream runs.
+ *   g_ptrs[r]   = replica r's bucket as mapped in this process (g_ptrs[rank] == g)
+ *   flag_bufs   = a sg_peer_buffer_bytes() exchange buffer per replica, used by no other stream (barrier flags)
+ *   staging     = (world - 1) * sg_peer_bucket_shard(n, world) floats of local scratch */
+long long sg_peer_bucket_shard(long long n, int world);
+int sg_peer_barrier(sg_ctx* ctx, const unsigned long long* peer_bufs, int world, int rank);
+int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging, const unsigned long long* g_ptrs,
+                             const unsigned long long* flag_bufs, int world, int rank);
 /* sync-BN forward statistics in one launch after the per-block partial sums: stage-2 reduction + exchange + mean /
  * rstd / moving-average finalisation (FusedBatchNormV3 training statistics, resnet_ops.py:14-17) */
 int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void* scratch, size_t scratch_bytes,

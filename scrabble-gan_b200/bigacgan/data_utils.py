@@ -339,7 +339,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     # Data parallel: each network's flat gradient bucket is SUM-all-reduced (not averaged: SURVEY Q7) as soon as its
     # filter gradients are complete, on NCCL's stream, overlapping with the backward passes that follow.
     pending = []
-    dimg_r_merged = None
+    dimg_r_merged = dimg_d_merged = None
     discriminator.trainable = True
     recognizer.trainable = True
     br = rt.branch()                     # R's backward (side stream) next to D's two backward passes (main stream)
@@ -354,25 +354,29 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             else:
                 recognizer.backward(rt, recognizer.slice_cache(rcc, b, 2 * b), None, wgrad=True, want_dx=False)
                 rfc = recognizer.slice_cache(rcc, 0, b)
-            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
-        discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
+            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g, store=recognizer.store)))
+        if update_g and rt.merge_d_backward:
+            # ONE backward pass of D over the fused batch for both losses (Discriminator.backward_merged)
+            dimg_d_merged = discriminator.backward_merged(rt, dcc, ups[0:2].view(-1), b, up_d_fake_g, 1.0)
+        else:
+            discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
-        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
+        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g, store=discriminator.store)))
         dfc = discriminator.slice_cache(dcc, 0, b)
     else:
         with br:
             recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
-            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g)))
+            pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g, store=recognizer.store)))
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
-        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g)))
+        pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g, store=discriminator.store)))
     if use_w:
         style_promoter.trainable = True
         style_promoter.backward(rt, src_c, up_s_real, wgrad=True, want_dx=False)
         style_promoter.backward(rt, sfc, up_s_fake_w, wgrad=True, want_dx=False)
         style_promoter.sn_backward(rt)
-        pending.append((id(style_promoter), rt.allreduce_async_(style_promoter.store.g)))
+        pending.append((id(style_promoter), rt.allreduce_async_(style_promoter.store.g, store=style_promoter.store)))
 
     # ---- optimizer steps (same call shape as the reference), each as soon as ITS bucket has been reduced -------------
     others = [(discriminator_optimizer, discriminator), (recognizer_optimizer, recognizer)]
@@ -388,7 +392,10 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
                 dimg_r = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
         else:
             dimg_r = dimg_r_merged
-        dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
+        if dimg_d_merged is not None:
+            dimg = dimg_d_merged
+        else:
+            dimg = discriminator.backward(rt, dfc, up_d_fake_g, wgrad=False, want_dx=True)
         br.join()
         if use_w:
             style_promoter.trainable = False
@@ -412,7 +419,8 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             _apply_all(rt, pending, others)
         generator.backward(rt, g_cache, dimg)
         generator.sn_backward(rt)
-        pending.append((id(generator), rt.allreduce_async_(generator.store.g)))
+        if not rt.diag_skip_g_bucket:
+            pending.append((id(generator), rt.allreduce_async_(generator.store.g, store=generator.store)))
         bo.join()
         _apply_all(rt, pending, [(generator_optimizer, generator)])
     else:

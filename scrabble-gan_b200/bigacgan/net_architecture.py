@@ -236,14 +236,25 @@ class _DownTrunk:
             out.append((ResNetBlockDown.slice_cache(c, a, b), NonLocalBlock.slice_cache(ca, a, b) if ca is not None else None))
         return (out, net[a:b])
 
-    def backward(self, rt: Runtime, cache, dfeats, wgrad: bool, want_dx: bool):
+    def backward(self, rt: Runtime, cache, dfeats, wgrad: bool, want_dx: bool, fake=None):
+        """fake = (b, up, mult): merged backward (see ResNetBlockDown.backward); returns the image gradient of rows [0, b)."""
         caches, net = cache
         d = ops.gap_relu_bwd(rt, dfeats, net)
         for i in reversed(range(len(self.blocks))):
             c, ca = caches[i]
             if ca is not None:
-                d = self.attn[i].backward(rt, ca, d, wgrad)
-            d = self.blocks[i].backward(rt, c, d, wgrad, want_dx or i > 0)
+                if fake is None:
+                    d = self.attn[i].backward(rt, ca, d, wgrad)
+                else:
+                    # the non-local block interleaves its filter gradients with its input-gradient chain: rows [0, b) go
+                    # through it twice -- with the constant weight (input gradient only), then, rescaled, with the whole
+                    # batch for the filter gradients (whose input gradient is kept for the other rows only)
+                    b, up, mult = fake
+                    d_fake = self.attn[i].backward(rt, NonLocalBlock.slice_cache(ca, 0, b), d[:b].clone(), False)
+                    ops.scale_samples_(rt, d[:b], up, mult)
+                    d = self.attn[i].backward(rt, ca, d, wgrad)
+                    d[:b].copy_(d_fake)
+            d = self.blocks[i].backward(rt, c, d, wgrad, want_dx or i > 0, fake=fake)
         return d
 
 
@@ -274,6 +285,23 @@ class Discriminator(_Model):
         n = feats.shape[0]
         dfeats = self.dense.backward(rt, feats, up, n, want_dx=True, wgrad=wgrad)
         return self.trunk.backward(rt, c, dfeats, wgrad, want_dx)
+
+    def backward_merged(self, rt, cache, up_all, b: int, up_fake_g, mult: float):
+        """ONE backward pass over a [fake ; real] batch that serves both the D loss and the G loss (data_utils.py:449-468
+        differentiates them separately; frozen weights make the second tape the same linear map).  Back-propagation is linear
+        in a sample's upstream weight, so rows [0, b) -- the fake images -- travel with the constant weight 1 / mult; the
+        filter gradients of the D loss see them rescaled by up_all[i] * mult (hinge: exactly 0 or 1), and the image gradient
+        of the G loss is the returned d/d(fake image) rescaled by up_fake_g[i] * mult.  up_all [2b] = d(D loss)/d(logit) for
+        [fake ; real].  Accumulates D's parameter gradients; returns d(G loss)/d(fake images) [b, H, W, 1]."""
+        feats, c = cache
+        n = feats.shape[0]
+        self.dense.backward(rt, feats, up_all, n, want_dx=False, wgrad=True)
+        up_chain = up_all.clone()
+        up_chain[:b].fill_(1.0 / mult)
+        dfeats = self.dense.backward(rt, feats, up_chain, n, want_dx=True, wgrad=False)
+        dimg = self.trunk.backward(rt, c, dfeats, True, True, fake=(b, up_all, mult))
+        ops.scale_samples_(rt, dimg, up_fake_g, mult)
+        return dimg
 
     def __call__(self, inputs, training=True):
         x = inputs[0] if isinstance(inputs, (list, tuple)) else inputs

@@ -155,19 +155,42 @@ class ResNetBlockDown:
         xr, xs, h1, hw = cache
         return (xr[a:b], xs[a:b], h1[a:b], hw)
 
-    def backward(self, rt: Runtime, cache, dout, wgrad: bool = True, want_dx: bool = True):
+    def backward(self, rt: Runtime, cache, dout, wgrad: bool = True, want_dx: bool = True, fake=None):
+        """fake = (b, up, mult) -- the merged discriminator backward (Discriminator.backward_merged): rows [0, b) of the batch
+        carry a CONSTANT upstream weight through the input-gradient chain; the filter gradients need the per-sample weights
+        up[i] * mult of the D loss instead, so the block first computes its input gradients from the unscaled tensors, then
+        rescales rows [0, b) of the tensors the filter gradients read, in place.  With `fake`, dx is returned for rows [0, b)
+        only (the image gradient of the real half is never needed)."""
         xr, xs, h1, (h, w) = cache
         dpre = ops.cast(rt, dout, rt.op_dt) if self.is_last else ops.avgpool2_bwd(rt, dout, rt.op_dt)
+        if fake is None:
+            if wgrad:
+                # the shortcut bias sees the same upstream gradient as conv2's bias: one column sum serves both
+                # (sum over pixels of avgpool_bwd(dout) == sum over pooled pixels of dout: read the 4x smaller fp32 tensor)
+                self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad, bias_src=dout)
+                self.short.wgrad(rt, xs, dpre, bias_grad=False)
+            dh1 = self.conv2.dgrad(rt, dpre, (h, w), mask=h1, out_dt=rt.op_dt)
+            if wgrad:
+                self.conv1.wgrad(rt, xr, dh1)
+            if not want_dx:
+                return None
+            dx = self.conv1.dgrad(rt, dh1, (h, w), mask=xr)
+            self.short.dgrad(rt, dpre, (h, w), out=dx, accumulate=True)
+            return dx
+        b, up, mult = fake
+        dh1 = self.conv2.dgrad(rt, dpre, (h, w), mask=h1, out_dt=rt.op_dt)
+        dx = None
+        if want_dx:
+            rows = slice(0, b) if self.ci < 32 else slice(None)          # first block: only the fake half's image gradient
+            dx = self.conv1.dgrad(rt, dh1[rows], (h, w), mask=xr[rows])
+            self.short.dgrad(rt, dpre[rows], (h, w), out=dx, accumulate=True)
         if wgrad:
-            # the shortcut bias sees the same upstream gradient as conv2's bias: one column sum serves both
-            # (sum over pixels of avgpool_bwd(dout) == sum over pooled pixels of dout: read the 4x smaller fp32 tensor)
+            seen = set()
+            for t in (dpre, dh1, dout):
+                if t.data_ptr() not in seen:                 # last block in fp32 mode: dpre IS dout (no cast, no pooling)
+                    seen.add(t.data_ptr())
+                    ops.scale_samples_(rt, t[:b], up, mult)
             self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad, bias_src=dout)
             self.short.wgrad(rt, xs, dpre, bias_grad=False)
-        dh1 = self.conv2.dgrad(rt, dpre, (h, w), mask=h1, out_dt=rt.op_dt)
-        if wgrad:
             self.conv1.wgrad(rt, xr, dh1)
-        if not want_dx:
-            return None
-        dx = self.conv1.dgrad(rt, dh1, (h, w), mask=xr)
-        self.short.dgrad(rt, dpre, (h, w), out=dx, accumulate=True)
         return dx

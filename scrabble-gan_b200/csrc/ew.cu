@@ -104,6 +104,27 @@ __global__ void k_scale_rows(float* __restrict__ x, const float* __restrict__ w,
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= w[i / cols];
 }
 
+// x[i, :] *= up[i] * mult for the samples i of a batch-first tensor (8 elements per thread; per_sample % 8 == 0).  Samples whose
+// factor is exactly 1 are left alone and samples whose factor is 0 are only written: with the hinge loss the factors of the
+// merged discriminator backward (net_architecture.py: Discriminator.backward_merged) are exactly those two values.
+// grid: (blocks per sample, samples)
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_samples(T* __restrict__ x, long long per_sample8, const float* __restrict__ up, float mult) {
+  sg_pdl_prologue();
+  const float f = up[blockIdx.y] * mult;
+  if (f == 1.0f) return;
+  T* xs = x + (long long)blockIdx.y * per_sample8 * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample8; i += stride) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (f != 0.0f) {
+      a = sg_ld4(xs + 8 * i); b = sg_ld4(xs + 8 * i + 4);
+      a.x *= f; a.y *= f; a.z *= f; a.w *= f; b.x *= f; b.y *= f; b.z *= f; b.w *= f;
+    }
+    sg_st4(xs + 8 * i, a); sg_st4(xs + 8 * i + 4, b);
+  }
+}
+
 // deterministic: per-block partials, summed in block order by the block that arrives last (common.cuh, scheme B)
 __global__ void k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, float* out, int accumulate,
                       float* __restrict__ scratch, unsigned int* ticket) {
@@ -535,6 +556,19 @@ int sg_scale_rows(sg_ctx* ctx, float* x, const float* w, int rows, long long col
   SG_REQUIRE(ctx && x && w && rows >= 0 && cols >= 0, "sg_scale_rows: bad args");
   if ((long long)rows * cols == 0) return SG_OK;
   sg_launch(ctx, k_scale_rows, ew_grid(ctx, (long long)rows * cols, 256), 256, 0, x, w, rows, cols);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+/* x[i, :] *= up[i] * mult, i < n; x is [n, per_sample] (fp32 or bf16, per_sample % 8 == 0) */
+int sg_scale_samples(sg_ctx* ctx, void* x, int dt, int n, long long per_sample, const float* up, float mult) {
+  SG_REQUIRE(ctx && x && up && n >= 0 && per_sample >= 0 && per_sample % 8 == 0 && ((uintptr_t)x & 15) == 0, "sg_scale_samples: bad args");
+  if (n == 0 || per_sample == 0) return SG_OK;
+  SG_REQUIRE(n <= 65535, "sg_scale_samples: at most 65535 samples");
+  long long need = (per_sample / 8 + 255) / 256;
+  long long cap = (long long)ctx->num_sms * 8 / n + 1;
+  dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)n);
+  SG_DISPATCH_DT(dt, T, sg_launch(ctx, k_scale_samples<T>, grid, 256, 0, (T*)x, per_sample / 8, up, mult));
   SG_POST_LAUNCH(ctx);
   return SG_OK;
 }

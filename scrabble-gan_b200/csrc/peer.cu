@@ -136,6 +136,37 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restri
   peer_commit_seq(pt);
 }
 
+// barrier only: publish my next sequence number to every peer, wait for theirs
+__global__ void __launch_bounds__(32) k_peer_barrier(PeerTable pt) {
+  sg_pdl_prologue();
+  pt.seq = peer_next_seq(pt);
+  peer_publish_and_wait(pt);
+  peer_commit_seq(pt);
+}
+
+// my shard of the gradient bucket: g[i] = sum over ranks, in RANK order, of that rank's copy (mine in place, the peers' from the
+// staging slots the copy engines filled): the same additions in the same order whichever rank owns the shard
+__global__ void __launch_bounds__(256) k_bucket_reduce(float* __restrict__ g, const float* __restrict__ staging, long long len,
+                                                        long long slot_stride, int world, int rank) {
+  sg_pdl_prologue();
+  const long long n4 = len / 4, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int slot = 0;
+    for (int r = 0; r < world; ++r) {
+      float4 v = (r == rank) ? sg_ld4(g + 4 * i) : sg_ld4(staging + (long long)(slot++) * slot_stride + 4 * i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    sg_st4(g + 4 * i, acc);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    float acc = 0.f;
+    int slot = 0;
+    for (int r = 0; r < world; ++r) acc += (r == rank) ? g[i] : staging[(long long)(slot++) * slot_stride + i];
+    g[i] = acc;
+  }
+}
+
 static int make_table(PeerTable* pt, const unsigned long long* peer_bufs, int world, int rank, const char* who) {
   SG_REQUIRE(peer_bufs && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "%s: bad peer table", who);
   memset(pt, 0, sizeof(*pt));
@@ -165,6 +196,63 @@ int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsi
   else sg_launch(ctx, k_peer_allreduce<float>, 1, threads, 0, (float*)data, n, pt);
   SG_POST_LAUNCH(ctx);
   return SG_OK;
+}
+
+int sg_peer_barrier(sg_ctx* ctx, const unsigned long long* peer_bufs, int world, int rank) {
+  SG_REQUIRE(ctx != nullptr, "sg_peer_barrier: ctx is NULL");
+  if (world <= 1) return SG_OK;
+  PeerTable pt;
+  int rc = make_table(&pt, peer_bufs, world, rank, "sg_peer_barrier");
+  if (rc != SG_OK) return rc;
+  sg_launch(ctx, k_peer_barrier, 1, 32, 0, pt);
+  SG_POST_LAUNCH(ctx);
+  return SG_OK;
+}
+
+long long sg_peer_bucket_shard(long long n, int world) {
+  long long s = (n + world - 1) / world;
+  return (s + 3) / 4 * 4;                 // 16-byte aligned shard starts
+}
+
+int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging, const unsigned long long* g_ptrs,
+                             const unsigned long long* flag_bufs, int world, int rank) {
+  SG_REQUIRE(ctx && g && n >= 0 && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "sg_peer_bucket_allreduce: bad args");
+  if (world == 1 || n == 0) return SG_OK;
+  SG_REQUIRE(staging && g_ptrs && flag_bufs && (float*)(uintptr_t)g_ptrs[rank] == g && ((uintptr_t)g & 15) == 0 && ((uintptr_t)staging & 15) == 0,
+             "sg_peer_bucket_allreduce: needs a staging buffer, the peer table of the bucket (g_ptrs[rank] == g) and 16-byte alignment");
+  const long long shard = sg_peer_bucket_shard(n, world);
+  auto lo = [&](int r) { long long a = (long long)r * shard; return a < n ? a : n; };
+  auto len = [&](int r) { return lo(r + 1) - lo(r); };
+  // (1) every replica's bucket is complete (stream order on each rank + barrier)
+  int rc = sg_peer_barrier(ctx, flag_bufs, world, rank);
+  if (rc != SG_OK) return rc;
+  // (2) reduce-scatter, pull side: the copy engines fetch MY shard of every peer's bucket over NVLink (no SM involved)
+  const long long mylen = len(rank);
+  int slot = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    if (mylen > 0)
+      SG_CHECK_CUDA(cudaMemcpyAsync(staging + (long long)slot * shard, (const float*)(uintptr_t)g_ptrs[r] + lo(rank), (size_t)mylen * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    ++slot;
+  }
+  if (mylen > 0) {
+    long long need = (mylen / 4 + 255) / 256;
+    int grid = (int)(need < 64 ? (need < 1 ? 1 : need) : 64);       // a small grid: this runs under the step's compute kernels
+    sg_launch(ctx, k_bucket_reduce, grid, 256, 0, g + lo(rank), staging, mylen, shard, world, rank);
+    SG_POST_LAUNCH(ctx);
+  }
+  // (3) every shard is reduced on its owner
+  rc = sg_peer_barrier(ctx, flag_bufs, world, rank);
+  if (rc != SG_OK) return rc;
+  // (4) all-gather, pull side
+  for (int r = 0; r < world; ++r) {
+    if (r == rank || len(r) <= 0) continue;
+    SG_CHECK_CUDA(cudaMemcpyAsync(g + lo(r), (const float*)(uintptr_t)g_ptrs[r] + lo(r), (size_t)len(r) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  }
+  // (5) nobody touches its bucket again before every peer has read its shard
+  return sg_peer_barrier(ctx, flag_bufs, world, rank);
 }
 
 /* BN statistics, stage 2 + cross-replica exchange + finalize (replaces k_bn_stats_reduce, the NCCL all-reduce and

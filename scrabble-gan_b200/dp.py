@@ -35,6 +35,7 @@ def init_data_parallel(rt, backend: str = None) -> None:
     rt.rank = dist.get_rank()
     rt.process_group = None
     rt.peer = None
+    rt.peer_comm = None
     if "nccl" in backend:
         # every rank must take the SAME path (a rank on NCCL while its peers spin on peer flags would hang both): the
         # opt-out and the outcome of the set-up are agreed on with a MIN all-reduce
@@ -45,7 +46,7 @@ def init_data_parallel(rt, backend: str = None) -> None:
         flag = torch.tensor([1 if ok else 0], device=rt.device, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) != 1:
-            rt.peer = None
+            rt.peer = rt.peer_comm = None
 
 
 class PeerExchange:
@@ -76,21 +77,88 @@ def init_peer_exchange(rt) -> bool:
                 symm_mem.enable_symm_mem_for_group(group.group_name)
             except Exception:
                 pass
-        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=rt.device)
-        hdl = symm_mem.rendezvous(buf, group.group_name)
-        buf.zero_()
-        torch.cuda.synchronize(rt.device)
-        dist.barrier()
-        ptrs = list(hdl.buffer_ptrs)
-        assert len(ptrs) == rt.world_size and all(int(p) != 0 for p in ptrs)
-        rt.peer = PeerExchange(buf, hdl, ptrs, rt.world_size, rt.rank)
+        made = []
+        for _ in range(2):       # [0]: the compute stream's small exchanges; [1]: barrier flags of the communication stream
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=rt.device)
+            hdl = symm_mem.rendezvous(buf, group.group_name)
+            buf.zero_()
+            torch.cuda.synchronize(rt.device)
+            dist.barrier()
+            ptrs = list(hdl.buffer_ptrs)
+            assert len(ptrs) == rt.world_size and all(int(p) != 0 for p in ptrs)
+            made.append(PeerExchange(buf, hdl, ptrs, rt.world_size, rt.rank))
+        rt.peer, rt.peer_comm = made
         return True
     except Exception as ex:                         # noqa: BLE001 -- any failure means "use NCCL", never a wrong result
         if rt.rank == 0:
             print("scrabble-gan_b200: peer-memory exchange unavailable ({}); small all-reduces use NCCL".format(repr(ex)[:200]),
                   file=sys.stderr)
-        rt.peer = None
+        rt.peer = rt.peer_comm = None
         return False
+
+
+def _symm_alloc(rt, numel, dtype):
+    """(tensor, rendezvous handle, peer pointers) of a symmetric-memory allocation: a COLLECTIVE call (every rank, same order)."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    group = dist.group.WORLD
+    buf = symm_mem.empty(numel, dtype=dtype, device=rt.device)
+    hdl = symm_mem.rendezvous(buf, group.group_name)
+    ptrs = list(hdl.buffer_ptrs)
+    assert len(ptrs) == rt.world_size and all(int(p) != 0 for p in ptrs) and int(ptrs[rt.rank]) == buf.data_ptr()
+    return buf, hdl, ptrs
+
+
+class BucketExchange:
+    """A network's flat gradient bucket in symmetric memory + what libsgan's copy-engine all-reduce needs to reduce it
+    (sg_peer_bucket_allreduce): the peer pointer table of the bucket and a local staging buffer."""
+
+    def __init__(self, rt, store):
+        import ctypes as C
+        from . import _abi
+        n = store.g.numel()
+        g_sym, self.handle, ptrs = _symm_alloc(rt, n, torch.float32)
+        g_sym.copy_(store.g)
+        store.g = g_sym                                  # Variable.grad views are taken from store.g at access time
+        self.ptrs = (C.c_ulonglong * rt.world_size)(*[int(p) for p in ptrs])
+        shard = int(_abi.load().sg_peer_bucket_shard(n, rt.world_size))
+        self.staging = torch.empty(max(1, (rt.world_size - 1) * shard), device=rt.device, dtype=torch.float32)
+        self.n = n
+        self.g_ptr = g_sym.data_ptr()
+
+
+class _StreamWork:
+    """Handle of work enqueued on another stream: wait() orders the CURRENT stream after it."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def wait(self):
+        torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+
+
+def bucket_allreduce_async(rt, store):
+    """SUM all-reduce of store.g over the replicas by the copy engines, on the runtime's communication stream, ordered after
+    everything enqueued on the current stream; returns a handle whose wait() orders the current stream after the reduction.
+    First call per store: moves the bucket into symmetric memory (collective; must happen before any CUDA-graph capture --
+    it does: the first steps run eagerly).  None when the peer-memory path is not up (caller falls back to NCCL)."""
+    import ctypes as C
+    from . import _abi
+    if rt.peer is None or rt.peer_comm is None or os.environ.get("SGAN_NO_CE_ALLREDUCE", "0") == "1":
+        return None
+    ex = getattr(store, "bucket_exchange", None)
+    if ex is None or ex.g_ptr != store.g.data_ptr():     # first use (or the bucket was re-allocated): a collective set-up
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        torch.cuda.synchronize(rt.device)
+        ex = store.bucket_exchange = BucketExchange(rt, store)
+        torch.cuda.synchronize(rt.device)
+    comm, ctx = rt.comm_stream_ctx()
+    comm.wait_stream(torch.cuda.current_stream(rt.device))
+    with torch.cuda.stream(comm):
+        _abi.call.sg_peer_bucket_allreduce(ctx, C.c_void_p(store.g.data_ptr()), ex.n, C.c_void_p(ex.staging.data_ptr()), ex.ptrs,
+                                           rt.peer_comm.ptrs, rt.world_size, rt.rank)
+    return _StreamWork(comm)
 
 
 def broadcast_parameters(rt, models) -> None:

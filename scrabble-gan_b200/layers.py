@@ -280,6 +280,10 @@ def batch_stats(rt: Runtime, x: torch.Tensor, bn: BatchNormState, update_moving:
     count = x.numel() // c
     mm = bn.moving_mean.data if update_moving else None
     mv = bn.moving_var.data if update_moving else None
+    if rt.diag_local_small:                     # timing diagnostics only (WRONG statistics on > 1 replica): no exchange
+        sums = ops.bn_stats(rt, x)
+        mean, rstd = ops.bn_finalize(rt, sums, count, c, mm, mv)
+        return mean, rstd, count
     if rt.world_size > 1 and rt.peer is not None:
         return ops.bn_stats_finalize_peer(rt, x, count * rt.world_size, c, mm, mv) + (count * rt.world_size,)
     # (on a single replica the one-block fused launch is slower than the wide stage-2 + finalize pair: 260 vs 150 us per

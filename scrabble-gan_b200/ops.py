@@ -297,6 +297,13 @@ def scale_rows_(rt, x, w):
     return x
 
 
+def scale_samples_(rt, x, up, mult: float):
+    """In place: x[i] *= up[i] * mult for the samples i of the batch-first tensor x (fp32 or bf16)."""
+    n = x.shape[0]
+    call.sg_scale_samples(rt.ctx, _p(x), dt_of(x), n, x.numel() // max(n, 1), _p(up), float(mult))
+    return x
+
+
 def dot_into(rt, a, b, out, accumulate=1):
     call.sg_dot(rt.ctx, _p(a), _p(b), a.numel(), _p(out), accumulate)
 

@@ -49,7 +49,12 @@ class Runtime:
         self.world_size = 1
         self.rank = 0
         self.process_group = None
+        # timing diagnostics of the data-parallel step (they make its results WRONG): skip the small exchanges / G's bucket
+        self.diag_local_small = os.environ.get("SGAN_DIAG_LOCAL_SMALL", "0") == "1"
+        self.diag_skip_g_bucket = os.environ.get("SGAN_DIAG_SKIP_G_BUCKET", "0") == "1"
         self.peer = None            # dp.PeerExchange when the NVLink peer-memory path is up
+        self.peer_comm = None       # a second one: barrier flags of the communication stream (bucket all-reduce)
+        self._comm = None           # (stream, context) of the communication stream
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (they bypass the C ABI's launch counter)
         self._scratch = {}
         self.rng_seed = int(os.environ.get("SGAN_SEED", "1234")) + 7919 * int(os.environ.get("RANK", "0"))
@@ -68,6 +73,8 @@ class Runtime:
         self.direct_nmajor = os.environ.get("SGAN_DIRECT_NMAJOR", "0") == "1"
         self.fuse_shortcut = os.environ.get("SGAN_NO_FUSED_SHORTCUT", "0") != "1"
         self.merge_r_backward = os.environ.get("SGAN_NO_MERGED_R_BWD", "0") != "1"
+        # D's two backward passes of a step (D loss: filter gradients; G loss: image gradient through the frozen D) as one
+        self.merge_d_backward = os.environ.get("SGAN_NO_MERGED_D_BWD", "0") != "1"
         # "tf32" mode: filter gradients on the tensor cores too (fp32 operands read as tf32, MN-major 32-byte-atom swizzle)
         self.tf32_wgrad_tc = os.environ.get("SGAN_TF32_WGRAD_SIMT", "0") != "1"
         # bias gradients of tensor-core convs come out of the filter-gradient launch (dy^T . 1 on the tensor cores)
@@ -116,11 +123,22 @@ class Runtime:
         n = int(_abi.load().sg_ctx_launch_count(self._main_ctx))
         if self._side_ctx is not None:
             n += int(_abi.load().sg_ctx_launch_count(self._side_ctx))
+        if self._comm is not None:
+            n += int(_abi.load().sg_ctx_launch_count(self._comm[1]))
         return n + self.replayed_launches
 
     def use_current_stream(self) -> None:
         self.stream = torch.cuda.current_stream(self.device)
         call.sg_ctx_set_stream(self._main_ctx, C.c_void_p(self.stream.cuda_stream))
+
+    def comm_stream_ctx(self):
+        """The communication stream and its libsgan context (created on first use): gradient-bucket all-reduces run there."""
+        if self._comm is None:
+            st = torch.cuda.Stream(device=self.device)
+            handle = C.c_void_p()
+            call.sg_ctx_create(self.device_index, C.c_void_p(st.cuda_stream), C.byref(handle))
+            self._comm = (st, handle)
+        return self._comm
 
     def branch(self) -> "Branch":
         """Fork a branch of independent work onto the side stream:
@@ -145,7 +163,7 @@ class Runtime:
     def allreduce_small_(self, t: torch.Tensor) -> torch.Tensor:
         """SUM all-reduce of a SMALL fp32 / fp64 vector (BN statistics, loss sums): one-shot exchange over NVLink peer
         memory on the compute stream (csrc/peer.cu) when available, NCCL otherwise."""
-        if self.world_size <= 1:
+        if self.world_size <= 1 or self.diag_local_small:
             return t
         pe = self.peer
         if pe is not None and t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and \
@@ -160,13 +178,19 @@ class Runtime:
             self._peer_max_bytes = int(_abi.load().sg_peer_max_payload_bytes())
         return self._peer_max_bytes
 
-    def allreduce_async_(self, t: torch.Tensor):
+    def allreduce_async_(self, t: torch.Tensor, store=None):
         """Start a SUM all-reduce of `t` on NCCL's own stream (ordered after everything already enqueued on the compute
         stream) and return a handle; compute enqueued afterwards overlaps with the transfer.  `wait()` orders the compute
         stream after the collective.  Returns None on a single replica."""
         if self.world_size <= 1:
             return None
         import torch.distributed as dist
+        if store is not None:
+            from . import dp
+            h = dp.bucket_allreduce_async(self, store)      # copy engines over NVLink peer memory: no SMs taken from the step
+            if h is not None:
+                return h
+            t = store.g
         if os.environ.get("SGAN_DP_SYNC_ALLREDUCE", "0") == "1":      # diagnostic: no overlap with the backward passes
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
             return None

@@ -131,6 +131,42 @@ def _peer_worker(rank, world, port, tmp):
         gathered = [torch.empty_like(got) for _ in range(world)]
         dist.all_gather(gathered, got)
         assert all(torch.equal(gathered[0], t) for t in gathered), "replicas must hold bit-identical sums"
+    # gradient buckets: copy-engine reduce-scatter + all-gather over peer memory == NCCL's sum, bit-identical on every replica,
+    # repeatable (sequence numbers), also for sizes that do not divide by the world size or by 4, and inside a CUDA graph
+    class _Store:
+        pass
+    for n in (1000003, 5, 4096):
+        st = _Store()
+        st.g = torch.zeros(n, device=rt.device)
+        for rep in range(3):
+            vals = torch.randn(n, generator=g).to(rt.device)
+            st.g.copy_(vals)
+            ref = vals.clone()
+            dist.all_reduce(ref)
+            h = rt.allreduce_async_(st.g, store=st)
+            assert h is not None and type(h).__name__ == "_StreamWork", "the copy-engine path must be the one that runs"
+            h.wait()
+            torch.cuda.synchronize()
+            assert torch.allclose(st.g, ref, rtol=1e-6, atol=1e-6), (n, rep)
+            gathered = [torch.empty_like(st.g) for _ in range(world)]
+            dist.all_gather(gathered, st.g)
+            assert all(torch.equal(gathered[0], t) for t in gathered), "replicas must hold bit-identical buckets"
+    stg = _Store()
+    stg.g = torch.zeros(70001, device=rt.device)
+    rt.allreduce_async_(stg.g, store=stg).wait()            # first call (moves the bucket to symmetric memory) outside the capture
+    torch.cuda.synchronize()
+    src = torch.randn(70001, generator=g).to(rt.device)
+    graph = torch.cuda.CUDAGraph()
+    cap = torch.cuda.Stream(device=rt.device)
+    with torch.cuda.graph(graph, stream=cap):
+        stg.g.copy_(src)
+        rt.allreduce_async_(stg.g, store=stg).wait()
+    for rep in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = src.clone()
+        dist.all_reduce(ref)
+        assert torch.allclose(stg.g, ref, rtol=1e-6, atol=1e-6), "bucket all-reduce inside a replayed graph"
     # fused sync-BN statistics == statistics of the concatenated batch
     xs = [torch.randn(3, 8, 10, 64, generator=torch.Generator().manual_seed(7 + r)) * 2 + 0.5 for r in range(world)]
     full = torch.cat(xs, 0).double()

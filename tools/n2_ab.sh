@@ -1,6 +1,17 @@
-run() { timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | grep "^{" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$2', d['ms_per_step'], d['value'])"; }
-run 29511 default
-NCCL_MAX_CTAS=4 run 29512 max_ctas4
-NCCL_MAX_CTAS=2 run 29513 max_ctas2
-SGAN_DP_SYNC_ALLREDUCE=1 run 29514 sync
-SGAN_NO_PEER=1 run 29515 nopeer
+#!/bin/bash
+# A/B of the 2-replica step under different exchange settings: prints ms/step per variant
+run() {
+  name="$1"; shift
+  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus ${NG:-2} --no-cpu-baseline --no-secondary 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('$name', round(d['ms_per_step'], 3), 'ms/step', round(d['value'], 1), 'img/s')"
+}
+run default A=1
+run independent SGAN_BENCH_INDEPENDENT=1
+run nccl_buckets SGAN_NO_CE_ALLREDUCE=1
+run diag_no_small_exchanges SGAN_DIAG_LOCAL_SMALL=1
+run diag_no_g_bucket SGAN_DIAG_SKIP_G_BUCKET=1
+run diag_neither SGAN_DIAG_LOCAL_SMALL=1 SGAN_DIAG_SKIP_G_BUCKET=1
