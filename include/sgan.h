@@ -205,11 +205,13 @@ int sg_peer_allreduce_sum(sg_ctx* ctx, void* data, int n, int is_f64, const unsi
  * barrier.  All on ctx's stream: enqueue it on a stream of its own and it overlaps with whatever the compute stream runs.
  *   g_ptrs[r]   = replica r's bucket as mapped in this process (g_ptrs[rank] == g)
  *   flag_bufs   = a sg_peer_buffer_bytes() exchange buffer per replica, used by no other stream (barrier flags)
- *   staging     = (world - 1) * sg_peer_bucket_shard(n, world) floats of local scratch */
+ *   staging     = (world - 1) * sg_peer_bucket_shard(n, world) floats of local scratch
+ *   use_sms     = 1: the same exchange with kernels reading the peers over NVLink (k_bucket_pull_reduce / k_bucket_gather,
+ *                 4 CTAs per SM) -- for a bucket whose all-reduce is exposed, i.e. nothing is left to overlap with */
 long long sg_peer_bucket_shard(long long n, int world);
 int sg_peer_barrier(sg_ctx* ctx, const unsigned long long* peer_bufs, int world, int rank);
 int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging, const unsigned long long* g_ptrs,
-                             const unsigned long long* flag_bufs, int world, int rank);
+                             const unsigned long long* flag_bufs, int world, int rank, int use_sms);
 /* sync-BN forward statistics in one launch after the per-block partial sums: stage-2 reduction + exchange + mean /
  * rstd / moving-average finalisation (FusedBatchNormV3 training statistics, resnet_ops.py:14-17) */
 int sg_bn_stats_partial(sg_ctx* ctx, const float* x, long long rows, int c, void* scratch, size_t scratch_bytes,

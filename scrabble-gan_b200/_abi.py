@@ -103,7 +103,7 @@ _PROTOS = {
     "sg_peer_allreduce_sum": (_I, [_P, _P, _I, _I, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_peer_bucket_shard": (_L, [_L, _I]),
     "sg_peer_barrier": (_I, [_P, C.POINTER(C.c_ulonglong), _I, _I]),
-    "sg_peer_bucket_allreduce": (_I, [_P, _P, _L, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _I, _I]),
+    "sg_peer_bucket_allreduce": (_I, [_P, _P, _L, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _I, _I, _I]),
     "sg_bn_stats_partial": (_I, [_P, _P, _L, _I, _P, _Z, C.POINTER(_I)]),
     "sg_bn_finalize_peer": (_I, [_P, _P, _I, _I, _D, _F, _F, _P, _P, _P, _P, _P, C.POINTER(C.c_ulonglong), _I, _I]),
     "sg_gemm": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I]),

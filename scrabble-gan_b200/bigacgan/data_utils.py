@@ -368,7 +368,10 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
             recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
             pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g, store=recognizer.store)))
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
-        discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
+        if update_g and rt.merge_d_backward:
+            dimg_d_merged = discriminator.backward_merged(rt, dfc, up_d_fake_d, b, up_d_fake_g, 1.0)     # the whole batch is "fake"
+        else:
+            discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
         pending.append((id(discriminator), rt.allreduce_async_(discriminator.store.g, store=discriminator.store)))
     if use_w:
@@ -420,7 +423,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         generator.backward(rt, g_cache, dimg)
         generator.sn_backward(rt)
         if not rt.diag_skip_g_bucket:
-            pending.append((id(generator), rt.allreduce_async_(generator.store.g, store=generator.store)))
+            pending.append((id(generator), rt.allreduce_async_(generator.store.g, store=generator.store, exposed=True)))
         bo.join()
         _apply_all(rt, pending, [(generator_optimizer, generator)])
     else:

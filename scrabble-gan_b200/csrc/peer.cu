@@ -167,6 +167,45 @@ __global__ void __launch_bounds__(256) k_bucket_reduce(float* __restrict__ g, co
   }
 }
 
+// The same reduce-scatter / all-gather with the SMs doing the NVLink reads (for a bucket whose all-reduce is EXPOSED -- nothing
+// else left to run beside it -- the whole machine pulling over NVLink beats one copy engine per peer).
+struct BucketPtrs { unsigned long long g[SG_PEER_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(256) k_bucket_pull_reduce(BucketPtrs bp, long long lo, long long len, int world, int rank) {
+  sg_pdl_prologue();
+  float* mine = reinterpret_cast<float*>(bp.g[rank]) + lo;
+  const long long n4 = len / 4, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {            // rank order: the same additions whichever replica owns the shard
+      float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bp.g[r]) + lo) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    __stcg(reinterpret_cast<float4*>(mine) + i, acc);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) acc += __ldcg(reinterpret_cast<const float*>(bp.g[r]) + lo + i);
+    mine[i] = acc;
+  }
+}
+
+// all-gather: blockIdx.y = peer index (skipping myself); copy that peer's reduced shard into my bucket
+__global__ void __launch_bounds__(256) k_bucket_gather(BucketPtrs bp, long long shard, long long n, int world, int rank) {
+  sg_pdl_prologue();
+  const int r = (int)blockIdx.y < rank ? (int)blockIdx.y : (int)blockIdx.y + 1;
+  long long lo = (long long)r * shard, hi = lo + shard;
+  if (lo > n) lo = n;
+  if (hi > n) hi = n;
+  const long long len = hi - lo;
+  const float* src = reinterpret_cast<const float*>(bp.g[r]) + lo;
+  float* dst = reinterpret_cast<float*>(bp.g[rank]) + lo;
+  const long long n4 = len / 4, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    __stcg(reinterpret_cast<float4*>(dst) + i, __ldcg(reinterpret_cast<const float4*>(src) + i));
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) dst[i] = __ldcg(src + i);
+}
+
 static int make_table(PeerTable* pt, const unsigned long long* peer_bufs, int world, int rank, const char* who) {
   SG_REQUIRE(peer_bufs && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "%s: bad peer table", who);
   memset(pt, 0, sizeof(*pt));
@@ -215,7 +254,7 @@ long long sg_peer_bucket_shard(long long n, int world) {
 }
 
 int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging, const unsigned long long* g_ptrs,
-                             const unsigned long long* flag_bufs, int world, int rank) {
+                             const unsigned long long* flag_bufs, int world, int rank, int use_sms) {
   SG_REQUIRE(ctx && g && n >= 0 && world >= 1 && world <= SG_PEER_MAX_WORLD && rank >= 0 && rank < world, "sg_peer_bucket_allreduce: bad args");
   if (world == 1 || n == 0) return SG_OK;
   SG_REQUIRE(staging && g_ptrs && flag_bufs && (float*)(uintptr_t)g_ptrs[rank] == g && ((uintptr_t)g & 15) == 0 && ((uintptr_t)staging & 15) == 0,
@@ -226,6 +265,26 @@ int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging,
   // (1) every replica's bucket is complete (stream order on each rank + barrier)
   int rc = sg_peer_barrier(ctx, flag_bufs, world, rank);
   if (rc != SG_OK) return rc;
+  if (use_sms) {
+    BucketPtrs bp;
+    memset(&bp, 0, sizeof(bp));
+    for (int r = 0; r < world; ++r) bp.g[r] = g_ptrs[r];
+    const long long mylen_ = len(rank);
+    if (mylen_ > 0) {
+      long long need = (mylen_ / 4 + 255) / 256, cap = (long long)ctx->num_sms * 4;
+      sg_launch(ctx, k_bucket_pull_reduce, (int)(need < cap ? (need < 1 ? 1 : need) : cap), 256, 0, bp, lo(rank), mylen_, world, rank);
+      SG_POST_LAUNCH(ctx);
+    }
+    rc = sg_peer_barrier(ctx, flag_bufs, world, rank);
+    if (rc != SG_OK) return rc;
+    {
+      long long need = (shard / 4 + 255) / 256, cap = (long long)ctx->num_sms * 4 / (world - 1) + 1;
+      dim3 grid((unsigned)(need < cap ? (need < 1 ? 1 : need) : cap), (unsigned)(world - 1));
+      sg_launch(ctx, k_bucket_gather, grid, 256, 0, bp, shard, n, world, rank);
+      SG_POST_LAUNCH(ctx);
+    }
+    return sg_peer_barrier(ctx, flag_bufs, world, rank);
+  }
   // (2) reduce-scatter, pull side: the copy engines fetch MY shard of every peer's bucket over NVLink (no SM involved)
   const long long mylen = len(rank);
   int slot = 0;

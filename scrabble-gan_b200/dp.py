@@ -137,9 +137,10 @@ class _StreamWork:
         torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
 
 
-def bucket_allreduce_async(rt, store):
+def bucket_allreduce_async(rt, store, exposed: bool = False):
     """SUM all-reduce of store.g over the replicas by the copy engines, on the runtime's communication stream, ordered after
     everything enqueued on the current stream; returns a handle whose wait() orders the current stream after the reduction.
+    exposed=True: nothing is left to run beside this reduction (the last bucket of a step), so the SMs do the NVLink reads.
     First call per store: moves the bucket into symmetric memory (collective; must happen before any CUDA-graph capture --
     it does: the first steps run eagerly).  None when the peer-memory path is not up (caller falls back to NCCL)."""
     import ctypes as C
@@ -157,7 +158,7 @@ def bucket_allreduce_async(rt, store):
     comm.wait_stream(torch.cuda.current_stream(rt.device))
     with torch.cuda.stream(comm):
         _abi.call.sg_peer_bucket_allreduce(ctx, C.c_void_p(store.g.data_ptr()), ex.n, C.c_void_p(ex.staging.data_ptr()), ex.ptrs,
-                                           rt.peer_comm.ptrs, rt.world_size, rt.rank)
+                                           rt.peer_comm.ptrs, rt.world_size, rt.rank, int(exposed and os.environ.get("SGAN_CE_ONLY", "0") != "1"))
     return _StreamWork(comm)
 
 

@@ -369,16 +369,13 @@ def bn_stats(rt, x) -> torch.Tensor:
 
 
 def bn_stats_finalize_peer(rt, x, count_total, c, moving_mean=None, moving_var=None, eps=1e-3, momentum=0.99, pe=None):
-    """sync-BN statistics with the cross-replica exchange fused in (needs rt.peer): per-block partial sums, then ONE
-    launch doing stage-2 reduction + NVLink exchange + mean / rstd / moving averages."""
+    """sync-BN statistics with the cross-replica exchange fused into the finalisation (needs rt.peer): the wide two-stage sum
+    of this replica (sg_bn_stats), then ONE small launch doing NVLink exchange + mean / rstd / moving averages.  (Stage 2
+    used to run inside that one-block launch as well: 16 us per layer slower than the wide stage-2 kernel, measured.)"""
     pe = rt.peer if pe is None else pe
-    rows = x.numel() // c
-    nbytes = rt.num_sms * 2 * c * 4
-    scratch = rt.scratch("bn_peer", nbytes)
-    nblocks = C.c_int(0)
-    call.sg_bn_stats_partial(rt.ctx, _p(x), rows, c, _p(scratch), nbytes, C.byref(nblocks))
+    sums = bn_stats(rt, x)
     mean, rstd = rt.empty((c,), SG_F32), rt.empty((c,), SG_F32)
-    call.sg_bn_finalize_peer(rt.ctx, _p(scratch), nblocks.value, c, float(count_total), eps, momentum, _V(None), _p(mean), _p(rstd),
+    call.sg_bn_finalize_peer(rt.ctx, _p(sums), 1, c, float(count_total), eps, momentum, _V(None), _p(mean), _p(rstd),
                              _p(moving_mean), _p(moving_var), pe.ptrs, pe.world, pe.rank)
     return mean, rstd
 

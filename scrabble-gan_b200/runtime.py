@@ -178,7 +178,7 @@ class Runtime:
             self._peer_max_bytes = int(_abi.load().sg_peer_max_payload_bytes())
         return self._peer_max_bytes
 
-    def allreduce_async_(self, t: torch.Tensor, store=None):
+    def allreduce_async_(self, t: torch.Tensor, store=None, exposed: bool = False):
         """Start a SUM all-reduce of `t` on NCCL's own stream (ordered after everything already enqueued on the compute
         stream) and return a handle; compute enqueued afterwards overlaps with the transfer.  `wait()` orders the compute
         stream after the collective.  Returns None on a single replica."""
@@ -187,7 +187,7 @@ class Runtime:
         import torch.distributed as dist
         if store is not None:
             from . import dp
-            h = dp.bucket_allreduce_async(self, store)      # copy engines over NVLink peer memory: no SMs taken from the step
+            h = dp.bucket_allreduce_async(self, store, exposed)      # copy engines over NVLink peer memory: no SMs taken from the step
             if h is not None:
                 return h
             t = store.g

@@ -143,8 +143,8 @@ def _peer_worker(rank, world, port, tmp):
             st.g.copy_(vals)
             ref = vals.clone()
             dist.all_reduce(ref)
-            h = rt.allreduce_async_(st.g, store=st)
-            assert h is not None and type(h).__name__ == "_StreamWork", "the copy-engine path must be the one that runs"
+            h = rt.allreduce_async_(st.g, store=st, exposed=(rep == 1))       # rep 1: the SM pull kernels instead of the copy engines
+            assert h is not None and type(h).__name__ == "_StreamWork", "the peer-memory path must be the one that runs"
             h.wait()
             torch.cuda.synchronize()
             assert torch.allclose(st.g, ref, rtol=1e-6, atol=1e-6), (n, rep)

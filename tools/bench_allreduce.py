@@ -27,10 +27,10 @@ def main():
         st.g = torch.randn(n, device=rt.device)
         ref = st.g.clone()
         res = {}
-        for name in ("ce", "nccl"):
+        for name in ("ce", "sm", "nccl"):
             def one():
-                if name == "ce":
-                    rt.allreduce_async_(st.g, store=st).wait()
+                if name in ("ce", "sm"):
+                    rt.allreduce_async_(st.g, store=st, exposed=(name == "sm")).wait()
                 else:
                     dist.all_reduce(ref)
             for _ in range(3):
@@ -44,7 +44,8 @@ def main():
             torch.cuda.synchronize()
             res[name] = e0.elapsed_time(e1) / 10
         if rt.rank == 0:
-            print("bucket {:4d} MB, world {}: copy engines {:.3f} ms   NCCL {:.3f} ms".format(mb, rt.world_size, res["ce"], res["nccl"]), flush=True)
+            print("bucket {:4d} MB, world {}: copy engines {:.3f} ms   SM pull kernels {:.3f} ms   NCCL {:.3f} ms".format(
+                mb, rt.world_size, res["ce"], res["sm"], res["nccl"]), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
