@@ -53,10 +53,14 @@ def _interp(tab, l):
     return tab[lo] + (tab[hi] - tab[lo]) * (l - lo) / (hi - lo)
 
 
-def step_gflop_per_image(lr, lf):
-    """Mode A (G+D+R) algorithmic FLOPs of one step per image: fwd + 2x fwd for trainable backward + 1x for frozen."""
+def step_gflop_per_image(lr, lf, executed=True):
+    """Mode A (G+D+R) FLOPs of one step per image: fwd + 2x fwd for a trainable backward + 1x for a frozen one.
+    executed=False: the reference's own tapes (data_utils.py:449-468: D is back-propagated twice over the fake images, once
+    for its filter gradients and once, frozen, for the G loss).  executed=True (what every TFLOP/s figure of this file uses):
+    libsgan back-propagates D once for both losses (Discriminator.backward_merged), so the frozen D pass is not executed."""
     gc, dlf, dlr, rlf, rlr = _interp(GF_GC, lf), _interp(GF_D, lf), _interp(GF_D, lr), _interp(GF_R, lf), _interp(GF_R, lr)
-    return (gc + dlf + rlf + dlr + rlr) + 2 * (dlr + dlf) + 2 * rlr + (dlf + rlf) + 2 * gc
+    total = (gc + dlf + rlf + dlr + rlr) + 2 * (dlr + dlf) + 2 * rlr + (dlf + rlf) + 2 * gc
+    return total - dlf if executed else total
 
 
 def workload_name(batch, length):
@@ -615,12 +619,15 @@ def main():
             avg_ms, achieved = None, None
         peak = peaks["bf16_tflops_sustained"]
         roofline = {"bound": "tensor", "kernel": "k_conv_tc<bf16> (tcgen05 implicit-GEMM conv), largest launch shape: D.B3.conv2 dgrad, "
-                    "M=%d (D-loss pass, fused [fake;real] batch) / %d (G-loss pass), K=9216, N=1024; timed in 2 eager steps"
-                    % (2 * B * 8 * 4 * L, B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "M=%d (the fused [fake;real] batch of the merged D backward), K=9216, N=1024; timed in 2 eager steps"
+                    % (2 * B * 8 * 4 * L), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": (traffic or {}).get("traffic_bytes"),
                     "traffic_source": (traffic or {}).get("source"), "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                     "launches_timed": len(kern_ms), "avg_launch_ms": avg_ms,
-                    "step": {"achieved": step_tflops, "frac": step_tflops / peak, "gflop_per_image": gf_img}}
+                    "step": {"achieved": step_tflops, "frac": step_tflops / peak, "gflop_per_image": gf_img,
+                             "gflop_per_image_reference_tapes": step_gflop_per_image(L, L, executed=False),
+                             "note": "executed FLOPs: one merged D backward serves the D and the G loss (the reference's tapes "
+                                     "back-propagate D twice over the fake images)"}}
         line = {"metric": "train images/sec (32x16*len words)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
