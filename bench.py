@@ -541,6 +541,25 @@ def main():
         step(i, dev, True)
     prof["on"] = False
     barrier()
+    # ... and of EVERY tensor-core conv / filter-gradient launch of two more eager steps (ops' launch tracer): the kernels'
+    # averages over all their launch shapes, next to the figure of the largest shape
+    rt.trace = []
+    for i in range(2):
+        step(i, dev, True)
+    barrier()
+    traced, rt.trace = rt.trace, None
+    kern_all = {}
+    for role, dsc, ev0, ev1 in traced:
+        name = None
+        if role in ("tc", "tc_direct", "tc_dual", "tc_rank1"):
+            name = "k_conv_tc"
+        elif role == "wgrad" and dsc["ci"] >= 32 and dsc["co"] >= 32 and args.dtype != "fp32":
+            name = "k_wgrad_tc"
+        if name:
+            e = kern_all.setdefault(name, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += ev0.elapsed_time(ev1)
+            e[2] += 2.0 * dsc["m"] * dsc["k"] * dsc["co"]
     du.GRAPH_ENABLED = graph_default
 
     for i in range(args.warmup):
@@ -624,6 +643,9 @@ def main():
                     "frac": (achieved / peak) if achieved else None, "traffic": (traffic or {}).get("traffic_bytes"),
                     "traffic_source": (traffic or {}).get("source"), "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                     "launches_timed": len(kern_ms), "avg_launch_ms": avg_ms,
+                    "all_launch_shapes": {k: {"launches_per_step": v[0] // 2, "avg_launch_ms": v[1] / v[0],
+                                              "achieved": v[2] / (v[1] * 1e-3) / 1e12, "frac": v[2] / (v[1] * 1e-3) / 1e12 / peak}
+                                          for k, v in kern_all.items()},
                     "step": {"achieved": step_tflops, "frac": step_tflops / peak, "gflop_per_image": gf_img,
                              "gflop_per_image_reference_tapes": step_gflop_per_image(L, L, executed=False),
                              "note": "executed FLOPs: one merged D backward serves the D and the G loss (the reference's tapes "

@@ -82,3 +82,96 @@ def test_prefetcher_and_device_loader(rt):
         l = labels.shape[1]
         assert imgs.shape == (8, 32, 16 * l, 1) and imgs.is_cuda and float(imgs.min()) >= -1.0 and float(imgs.max()) < 1.0
         assert labels.dtype == torch.int32 and int(labels.min()) >= 0 and int(labels.max()) < 52
+
+
+# ---- a DLPack producer that is NOT torch: device memory from the CUDA runtime (cuda-python), capsule built with ctypes --------
+class _RawDeviceArray:
+    """Minimal DLPack (v0.x `dltensor` capsule) producer over cudaMalloc'ed memory: what a TF2 tensor
+    (tf.experimental.dlpack.to_dlpack), a cupy array or any other framework hands over."""
+    _keep = {}
+
+    def __init__(self, host: np.ndarray):
+        import ctypes as C
+        from cuda.bindings import runtime as cudart
+        self.C, self.cudart = C, cudart
+        host = np.ascontiguousarray(host)
+        self.shape, self.dtype, self.nbytes = host.shape, host.dtype, host.nbytes
+        err, self.dptr = cudart.cudaMalloc(max(self.nbytes, 1))
+        assert int(err) == 0
+        (err,) = cudart.cudaMemcpy(self.dptr, host.ctypes.data, self.nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+        assert int(err) == 0
+
+    def __dlpack_device__(self):
+        return (2, 0)                                    # kDLCUDA, device 0
+
+    def __dlpack__(self, stream=None, **kwargs):
+        C = self.C
+
+        class DLDevice(C.Structure):
+            _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+        class DLDataType(C.Structure):
+            _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+        class DLTensor(C.Structure):
+            _fields_ = [("data", C.c_void_p), ("device", DLDevice), ("ndim", C.c_int32), ("dtype", DLDataType),
+                        ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+        class DLManagedTensor(C.Structure):
+            pass
+        deleter_t = C.CFUNCTYPE(None, C.POINTER(DLManagedTensor))
+        DLManagedTensor._fields_ = [("dl_tensor", DLTensor), ("manager_ctx", C.c_void_p), ("deleter", deleter_t)]
+        shape = (C.c_int64 * len(self.shape))(*self.shape)
+        mt = DLManagedTensor()
+        code, bits = (2, 32) if self.dtype == np.float32 else (0, 32)        # kDLFloat / kDLInt
+        mt.dl_tensor = DLTensor(C.c_void_p(int(self.dptr)), DLDevice(2, 0), len(self.shape), DLDataType(code, bits, 1), shape, None, 0)
+        key = id(mt)
+
+        def _deleter(_p, key=key):
+            _RawDeviceArray._keep.pop(key, None)
+        mt.deleter = deleter_t(_deleter)
+        _RawDeviceArray._keep[key] = (mt, shape, mt.deleter, self)          # owner and C structs outlive the consumer's view
+        C.pythonapi.PyCapsule_New.restype = C.py_object
+        C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        return C.pythonapi.PyCapsule_New(C.addressof(mt), b"dltensor", None)
+
+
+def test_non_torch_dlpack_producer_feeds_the_api(rt):
+    """The drop-in boundary takes tensors of OTHER frameworks: a generator call and a train step fed with DLPack
+    producers that are not torch tensors give exactly what the same data as numpy / torch gives."""
+    pytest.importorskip("cuda.bindings.runtime")
+    na = importlib.import_module("scrabble-gan_b200.bigacgan.net_architecture")
+    nl = importlib.import_module("scrabble-gan_b200.bigacgan.net_loss")
+    optim = importlib.import_module("scrabble-gan_b200.optim")
+    rt.set_mode("fp32")
+    rng = np.random.RandomState(3)
+    b, l = 4, 3
+    z = rng.standard_normal((b, 128)).astype(np.float32)
+    labels = rng.randint(0, 52, (b, l)).astype(np.int32)
+    imgs = rng.uniform(-1, 1, (b, 32, 16 * l, 1)).astype(np.float32)
+
+    def build():
+        G = na.make_generator(128, (32, 160, 1), (32, 8192), None, "B3", 52, vis_model=False, rt=rt, seed=5)
+        D = na.make_discriminator((32, 160, 1), None, "B1", vis_model=False, rt=rt, seed=6)
+        R = na.make_recognizer((32, 160, 1), None, 53, vis_model=False, rt=rt, seed=7)
+        return G, D, R
+    G, D, R = build()
+    ref_img = G([z, labels], training=False)
+    got_img = G([_RawDeviceArray(z), _RawDeviceArray(labels)], training=False)
+    assert torch.equal(ref_img, got_img)
+
+    def one_step(nets, images, lab, fake, noise):
+        G, D, R = nets
+        gan = na.make_gan(G, D, R, None, vis_model=False)
+        g_opt, d_opt, r_opt, w_opt, loss_fn, disc_iters, agb = optim.setup_optimizer(2e-4, 2e-4, 2e-4, 2e-4, 0.0, 0.999, nl.hinge, 1, 1, 0)
+        old = du.GRAPH_ENABLED
+        du.GRAPH_ENABLED = False
+        try:
+            return du.train_step(0, 0, 1, images, lab, D, R, None, gan, g_opt, d_opt, r_opt, w_opt, None, b, 128, loss_fn, disc_iters, agb,
+                                 None, 10, "", fake_labels=fake, noise=noise)
+        finally:
+            du.GRAPH_ENABLED = old
+    fake = rng.randint(0, 52, (b, l)).astype(np.int32)
+    a = one_step(build(), imgs, labels, fake, z)
+    c = one_step(build(), _RawDeviceArray(imgs), _RawDeviceArray(labels), _RawDeviceArray(fake), _RawDeviceArray(z))
+    assert a == c, "same data through numpy and through a foreign DLPack producer must give the same 16 statistics"
