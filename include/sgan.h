@@ -104,6 +104,12 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
  * whole output.  r1_x: fp32 [n, out_h, out_w]; r1_w: fp32 [c_out]; unit output stride only. */
 int sg_conv_fwd_tc_rank1(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
                          const void* mask, void* out, const float* r1_x, const float* r1_w);
+/* The output phases of a Conv2DTranspose forward (resnet_ops.py:57,69; phase-decomposed: no zero-stuffed MACs) as ONE launch.
+ * descs[i] (1..4) are the per-phase descriptors: same tensors, pixel grid and dtypes, different taps and output offsets
+ * (out_py, out_px); the filter is read in place from the bf16 mirror of the master weights.  A stride-2 3x3 transposed conv
+ * is 4 + 2 + 2 + 1 taps = one launch of 4x the tiles instead of four launches that each fill a fraction of the SMs. */
+int sg_conv_fwd_tc_phases(sg_ctx* ctx, int nphase, const sg_conv_desc* const* descs, const void* in, const void* w_mirror_bf16,
+                          const float* bias, void* out);
 int sg_conv_fwd_tc_dual(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed,
                         const sg_conv_desc* d2, const void* in2, const void* w_packed2, const float* bias,
                         const void* mask, void* out);

@@ -177,20 +177,34 @@ struct alignas(64) TcFwdParams {
   // tile meet at `cnt`, and each finishes its own share of the tile's 32-column chunks: own accumulators + the peers' partials
   // added in unit order (deterministic), then the usual epilogue.
   int t_full, split, total_units;
+  // phases of a transposed conv in ONE launch (sg_conv_fwd_tc_phases): tile / tiles_per_phase selects the phase, which owns
+  // taps [ph_tap0, ph_tap0 + ph_ntaps) of the tap tables and writes at output offset (ph_py, ph_px).  nphase == 1: plain conv.
+  int nphase, tiles_per_phase;
+  int ph_tap0[4], ph_ntaps[4], ph_py[4], ph_px[4];
   float* part;                  // [tail unit][BN/32 chunks][8][128 rows] float4
   unsigned int* cnt;            // [tail tile][2]: arrivals, departures; zero between launches
 };
 
-// unit v of the launch -> (tile, k-block range); si = index of the unit inside its tile (0 for whole tiles)
-struct TcUnit { int tile, kb0, kb1, si; };
-__device__ __forceinline__ TcUnit tc_unit(const TcFwdParams& p, int v, int nkb) {
+// unit v of the launch -> (tile inside its phase, phase, k-block range); si = index of the unit inside its tile (0 for whole tiles)
+struct TcUnit { int tile, ph, kb0, kb1, si, tail_tile; };
+__device__ __forceinline__ TcUnit tc_unit(const TcFwdParams& p, int v) {
   TcUnit u;
-  if (v < p.t_full) { u.tile = v; u.kb0 = 0; u.kb1 = nkb; u.si = 0; return u; }
-  const int w = v - p.t_full;
-  u.tile = p.t_full + w / p.split;
-  u.si = w % p.split;
-  u.kb0 = (int)((long long)nkb * u.si / p.split);
-  u.kb1 = (int)((long long)nkb * (u.si + 1) / p.split);
+  int gt;                               // global tile index
+  if (v < p.t_full) { gt = v; u.si = 0; u.tail_tile = -1; }
+  else {
+    const int w = v - p.t_full;
+    gt = p.t_full + w / p.split;
+    u.si = w % p.split;
+    u.tail_tile = w / p.split;
+  }
+  u.ph = gt / p.tiles_per_phase;
+  u.tile = gt - u.ph * p.tiles_per_phase;
+  const int nkb = p.ph_ntaps[u.ph] * p.kc_per_tap + p.kc2;
+  if (v < p.t_full) { u.kb0 = 0; u.kb1 = nkb; }
+  else {
+    u.kb0 = (int)((long long)nkb * u.si / p.split);
+    u.kb1 = (int)((long long)nkb * (u.si + 1) / p.split);
+  }
   return u;
 }
 
@@ -235,23 +249,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
   sg_pdl_prologue();        // barriers, descriptors and TMEM are set up while the preceding kernel drains; global memory from here on
   const uint32_t tmem_base = tmem_slot;
 
-  const int nkb = p.ntaps * p.kc_per_tap + p.kc2;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const int nkb1 = p.ntaps * p.kc_per_tap;
       for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
-        const TcUnit u = tc_unit(p, v, nkb);
+        const TcUnit u = tc_unit(p, v);
         const int tile = u.tile;
+        const int nkb1 = p.ph_ntaps[u.ph] * p.kc_per_tap;
         int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
         int tx = mt % p.tiles_x;
         int r = mt / p.tiles_x;
         int ty = r % p.tiles_y, tn = r / p.tiles_y;
         int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, col0 = col_t * p.BN;
-        int t = u.kb0 / p.kc_per_tap, c = u.kb0 % p.kc_per_tap;      // (tap, channel chunk) of k-block kb < nkb1
+        int t = p.ph_tap0[u.ph] + u.kb0 / p.kc_per_tap, c = u.kb0 % p.kc_per_tap;      // (tap, channel chunk) of k-block kb < nkb1
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
-      const TcUnit u = tc_unit(p, v, nkb);
+      const TcUnit u = tc_unit(p, v);
       mbar_wait(bar_tempty + 8 * as, aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -326,8 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint32_t aph = 0;
     const int nchunks = p.BN / 32;
     for (int v = blockIdx.x; v < p.total_units; v += gridDim.x) {
-      const TcUnit u = tc_unit(p, v, nkb);
+      const TcUnit u = tc_unit(p, v);
       const int tile = u.tile;
+      const int out_py = p.ph_py[u.ph], out_px = p.ph_px[u.ph];
       int col_t = tile % p.tiles_col, mt = tile / p.tiles_col;
       int tx = mt % p.tiles_x;
       int r = mt / p.tiles_x;
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
       bool valid = row < rows_in_tile && ni < p.n && oy < p.grid_h && ox < p.grid_w;
       long long base = -1;                                  // < 0 = no such output pixel
       if (valid)
-        base = (((long long)ni * p.out_h + oy * p.out_sy + p.out_py) * p.out_w + ox * p.out_sx + p.out_px) * p.c_out +
+        base = (((long long)ni * p.out_h + oy * p.out_sy + out_py) * p.out_w + ox * p.out_sx + out_px) * p.c_out +
                col_t * p.BN;
       long long rbase[4];
 #pragma unroll
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // a split tile: park the chunks the peers will finish, meet them, then finish chunks [ch_lo, ch_hi) of the tile
         ch_lo = nchunks * u.si / p.split;
         ch_hi = nchunks * (u.si + 1) / p.split;
-        const int tail_tile = tile - p.t_full;
+        const int tail_tile = u.tail_tile;
         const long long unit_f4 = (long long)nchunks * 8 * 128;
         peers = reinterpret_cast<const float4*>(p.part) + (long long)tail_tile * p.split * unit_f4;
         float4* mine = reinterpret_cast<float4*>(p.part) + ((long long)tail_tile * p.split + u.si) * unit_f4;
@@ -501,7 +514,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // the last unit to leave the tile re-arms its counters for the next launch (every peer has read the partials it needs)
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) {
-          unsigned int* cn = p.cnt + 2 * (tile - p.t_full);
+          unsigned int* cn = p.cnt + 2 * u.tail_tile;
           if (atomicAdd(cn + 1, 1u) == (unsigned int)p.split - 1u) { cn[0] = 0u; cn[1] = 0u; __threadfence(); }
         }
       }
@@ -1250,7 +1263,8 @@ static double tc_split_plan(long long tiles, int sms, int nkb, int bn, int enabl
 
 static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, int b_mode, const float* bias,
                             const void* mask, void* out, const sg_conv_desc* d2 = nullptr, const void* in2 = nullptr,
-                            const void* w_packed2 = nullptr, const float* r1_x = nullptr, const float* r1_w = nullptr) {
+                            const void* w_packed2 = nullptr, const float* r1_x = nullptr, const float* r1_w = nullptr,
+                            const sg_conv_desc* const* phases = nullptr, int nphase = 1) {
   SG_REQUIRE(ctx && in && w_packed && out, "sg_conv_fwd_tc: NULL");
   int rc = tc_check(d, "sg_conv_fwd_tc");
   if (rc != SG_OK) return rc;
@@ -1294,9 +1308,9 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
     for (int i = 0; i < 4; ++i) {
       if (d->c_out % cand[i]) continue;
       if (b_mode == 2 && cand[i] < 64) continue;
-      long long tiles = m_tiles * (d->c_out / cand[i]);
+      long long tiles = m_tiles * (d->c_out / cand[i]) * nphase;
       int split = 1;
-      double cost = tc_split_plan(tiles, ctx->num_sms, nkb_total, cand[i], ctx->conv_split_tail, &split) * rel[i];
+      double cost = tc_split_plan(tiles, ctx->num_sms, nkb_total, cand[i], ctx->conv_split_tail && nphase == 1, &split) * rel[i];
       if (best < 0 || cost < best * 0.97) { best = cost; p.BN = cand[i]; best_split = split; }
     }
   }
@@ -1313,13 +1327,26 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   p.stages = stages;
 
   bool used[4] = {false, false, false, false};
-  for (int t = 0; t < d->ntaps; ++t) {
-    int py = posmod(d->tap_dy[t], d->in_sy), px = posmod(d->tap_dx[t], d->in_sx);
-    int v = py * 2 + px;
-    p.tap_view[t] = v;
-    p.tap_oy[t] = floordiv(d->tap_dy[t], d->in_sy);
-    p.tap_ox[t] = floordiv(d->tap_dx[t], d->in_sx);
-    used[v] = true;
+  // tap tables: one phase = the descriptor's own taps; several phases = their taps back to back
+  long long tap_w_off_all[SG_MAX_TAPS];
+  {
+    int nt = 0;
+    p.nphase = nphase;
+    for (int ph = 0; ph < nphase; ++ph) {
+      const sg_conv_desc* dp = phases ? phases[ph] : d;
+      p.ph_tap0[ph] = nt; p.ph_ntaps[ph] = dp->ntaps; p.ph_py[ph] = dp->out_py; p.ph_px[ph] = dp->out_px;
+      for (int t = 0; t < dp->ntaps; ++t, ++nt) {
+        SG_REQUIRE(nt < SG_MAX_TAPS, "sg_conv_fwd_tc_phases: more than %d taps in total", SG_MAX_TAPS);
+        int py = posmod(dp->tap_dy[t], dp->in_sy), px = posmod(dp->tap_dx[t], dp->in_sx);
+        int v = py * 2 + px;
+        p.tap_view[nt] = v;
+        p.tap_oy[nt] = floordiv(dp->tap_dy[t], dp->in_sy);
+        p.tap_ox[nt] = floordiv(dp->tap_dx[t], dp->in_sx);
+        tap_w_off_all[nt] = dp->tap_w_off[t];
+        used[v] = true;
+      }
+    }
+    p.ntaps = nt;
   }
   int first_used = -1;
   for (int v = 0; v < 4; ++v) {
@@ -1351,8 +1378,8 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   } else {
     const long long ts = (long long)d->c_in * d->c_out;
     long long tmax = 0;
-    for (int t = 0; t < d->ntaps; ++t) {
-      p.tap_wt[t] = (int)(d->tap_w_off[t] / ts);
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.tap_wt[t] = (int)(tap_w_off_all[t] / ts);
       if (p.tap_wt[t] > tmax) tmax = p.tap_wt[t];
     }
     if (b_mode == 1) rc = encode_3d(enc, &p.map_b, w_packed, d->c_in, d->c_out, tmax + 1, d->w_co_stride, ts, KC, p.BN);
@@ -1360,7 +1387,8 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   }
   if (rc != SG_OK) return rc;
 
-  long long total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
+  p.tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
+  long long total_tiles = (long long)p.tiles_per_phase * nphase;
   p.split = best_split;
   p.t_full = (int)(best_split > 1 ? total_tiles / ctx->num_sms * ctx->num_sms : total_tiles);
   p.total_units = (int)(p.t_full + (total_tiles - p.t_full) * p.split);
@@ -1410,6 +1438,26 @@ int sg_conv_fwd_tc_direct(sg_ctx* ctx, const sg_conv_desc* d, const void* in, co
   int mode = direct_mode(d);
   SG_REQUIRE(mode != 0, "sg_conv_fwd_tc_direct: this descriptor cannot read the master filter in place");
   return conv_fwd_tc_impl(ctx, d, in, w_mirror_bf16, mode, bias, mask, out);
+}
+
+/* the output phases of a transposed conv (Conv2DTranspose forward, resnet_ops.py:57,69) as ONE launch: descs[i] are the
+ * phase descriptors (ops.desc_convT_phase: same tensors and pixel grid, different taps and output offsets) */
+int sg_conv_fwd_tc_phases(sg_ctx* ctx, int nphase, const sg_conv_desc* const* descs, const void* in, const void* w_mirror_bf16,
+                          const float* bias, void* out) {
+  SG_REQUIRE(descs && nphase >= 1 && nphase <= 4, "sg_conv_fwd_tc_phases: 1..4 phases");
+  const sg_conv_desc* d = descs[0];
+  int mode = direct_mode(d);
+  SG_REQUIRE(mode != 0, "sg_conv_fwd_tc_phases: the phases must be able to read the master filter in place (bf16 mirror)");
+  for (int i = 1; i < nphase; ++i) {
+    const sg_conv_desc* e = descs[i];
+    SG_REQUIRE(e && direct_mode(e) == mode && e->n == d->n && e->in_h == d->in_h && e->in_w == d->in_w && e->c_in == d->c_in &&
+                   e->out_h == d->out_h && e->out_w == d->out_w && e->c_out == d->c_out && e->grid_h == d->grid_h &&
+                   e->grid_w == d->grid_w && e->in_sy == d->in_sy && e->in_sx == d->in_sx && e->out_sy == d->out_sy &&
+                   e->out_sx == d->out_sx && e->in_dt == d->in_dt && e->out_dt == d->out_dt && e->relu == d->relu &&
+                   e->accumulate == d->accumulate && e->w_ci_stride == d->w_ci_stride && e->w_co_stride == d->w_co_stride,
+               "sg_conv_fwd_tc_phases: phase %d differs from phase 0 in more than taps and output offset", i);
+  }
+  return conv_fwd_tc_impl(ctx, d, in, w_mirror_bf16, mode, bias, nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr, descs, nphase);
 }
 
 size_t sg_conv_wgrad_tc_workspace(const sg_conv_desc* d, int num_sms) {

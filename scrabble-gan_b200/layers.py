@@ -195,6 +195,7 @@ class ConvTransposeLayer:
         b = self.b.data if isinstance(bias, str) else bias
         full_cover = len(self.phases) == self.sy * self.sx
         assert accumulate or full_cover, "a transposed conv whose phases do not tile the output must accumulate"
+        descs = []
         for (py, px) in self.phases:
             key = ("ph", py, px, n, h, w, dt_of(x), int(accumulate))
             d = self._descs.get(key)
@@ -202,6 +203,11 @@ class ConvTransposeLayer:
                 d = ops.desc_convT_phase(n, h, w, self.ci, self.co, self.k, self.sy, self.sx, py, px, dt_of(x), SG_F32, 0,
                                          int(accumulate))
                 self._descs[key] = d
+            descs.append(d)
+        if rt.merge_phases and len(descs) > 1 and all(ops.direct_ok(rt, d) for d in descs):
+            ops.conv_run_phases(rt, descs, x, self.w.mirror(rt), b, out)       # every phase in ONE launch
+            return out
+        for (py, px), d in zip(self.phases, descs):
             if ops.direct_ok(rt, d):
                 ops.conv_run(rt, d, x, self.w.eff, None, b, None, out, w_mirror=self.w.mirror(rt))
             else:

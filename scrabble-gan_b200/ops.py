@@ -204,6 +204,23 @@ def conv_run_rank1(rt: Runtime, d: ConvDesc, x, w_packed, bias, mask, out, r1_x,
         call.sg_conv_fwd_tc_rank1(rt.ctx, C.byref(d), _p(x), _p(w_packed), _p(bias), _p(mask), _p(out), _p(r1_x), _p(r1_w))
 
 
+def conv_run_phases(rt: Runtime, descs, x, w_mirror, bias, out) -> None:
+    """All output phases of a transposed conv in ONE tensor-core launch (filter read in place from the bf16 mirror)."""
+    k = len(descs)
+    arr = (C.POINTER(ConvDesc) * k)(*[C.pointer(d) for d in descs])
+    if rt.trace is not None:
+        import copy
+        dsum = copy.copy(descs[0])
+        d2 = None
+        with _Traced(rt, "tc_phases", dsum, d2) as tr:
+            call.sg_conv_fwd_tc_phases(rt.ctx, k, arr, _p(x), _p(w_mirror), _p(bias), _p(out))
+        role, info, e0, e1 = rt.trace[-1]
+        info["taps"] = sum(d.ntaps for d in descs)
+        info["k"] = info["taps"] * descs[0].c_in
+        return
+    call.sg_conv_fwd_tc_phases(rt.ctx, k, arr, _p(x), _p(w_mirror), _p(bias), _p(out))
+
+
 def conv_run_dual(rt: Runtime, d: ConvDesc, x, w_packed, d2: ConvDesc, x2, w_packed2, bias, mask, out) -> None:
     """Main conv + 1x1 shortcut conv accumulated in ONE tensor-core launch (both filters packed)."""
     with _Traced(rt, "tc_dual", d, d2):

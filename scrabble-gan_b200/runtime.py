@@ -82,6 +82,8 @@ class Runtime:
         # the generator's 12 conditional-batch-norm Dense layers (and their filter gradients) as one grouped launch each
         self.group_cbn_dense = os.environ.get("SGAN_NO_GROUPED_CBN", "0") != "1"
         self.trace = None                       # diagnostics: a list makes ops.conv_* record (role, shape, events) per launch
+        # all output phases of a transposed conv in one tensor-core launch
+        self.merge_phases = os.environ.get("SGAN_NO_MERGED_PHASES", "0") != "1"
         # one packing launch per network and step instead of one per layer
         self.batch_packs = os.environ.get("SGAN_NO_BATCHED_PACKS", "0") != "1"
         for c in (self._main_ctx, self._side_ctx):

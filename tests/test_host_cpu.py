@@ -100,8 +100,10 @@ def test_keras_adam_step_size_and_channel_tables():
 def test_bench_flop_model_matches_the_survey():
     import bench
     # Mode A step = 79.71 GF/img at L=5/5 and 160.32 at L=10/10
-    assert abs(bench.step_gflop_per_image(5, 5) - 79.714) < 0.01
-    assert abs(bench.step_gflop_per_image(10, 10) - 160.32) < 0.05
+    assert abs(bench.step_gflop_per_image(5, 5, executed=False) - 79.714) < 0.01
+    assert abs(bench.step_gflop_per_image(10, 10, executed=False) - 160.32) < 0.05
+    # executed FLOPs: the merged D backward does not run the reference's frozen D pass over the fake images (one D forward's worth)
+    assert abs(bench.step_gflop_per_image(5, 5) - (79.714 - 9.938)) < 0.01
 
 
 def test_synthetic_loaders_keep_the_reference_interfaces():
