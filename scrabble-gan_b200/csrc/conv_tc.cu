@@ -384,7 +384,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         unsigned int* cn = p.cnt + 2 * tail_tile;
         if (threadIdx.x == 64) {
           atomicAdd(cn, 1u);
-          while (*reinterpret_cast<volatile unsigned int*>(cn) < (unsigned int)p.split) __nanosleep(64);
+          unsigned int spins = 0;
+          while (*reinterpret_cast<volatile unsigned int*>(cn) < (unsigned int)p.split) {
+            if (++spins > (1u << 26)) __trap();          // a protocol bug must fault, never hang the GPU
+            __nanosleep(64);
+          }
           __threadfence();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");

@@ -726,3 +726,23 @@ def test_spectral_norm(rt, shape):
     exp = O.spectral_norm(w, u, 1)
     got, u_hat, sigma = ops.spectral_norm(rt, dev(rt, w), dev(rt, u.view(-1)), 1)
     check(got, exp, 1e-4, "spectral norm")
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_scale_samples(rt, dt):
+    """x[i] *= up[i] * mult per sample; factor 1 leaves the sample untouched, factor 0 zero-fills it WITHOUT reading it (the two
+    values the hinge loss produces in the merged discriminator backward), anything else is a plain multiply."""
+    g = torch.Generator().manual_seed(31)
+    n, per = 7, 4 * 10 * 64
+    x = rnd(g, n, 4, 10, 64)
+    up = torch.tensor([0.5, 0.0, 0.185, 0.5, 0.0, 1.0, 0.5], dtype=torch.float64)        # * mult 2 -> 1, 0, 0.37, 1, 0, 2, 1
+    xd = dev(rt, x, F32 if dt == "f32" else BF16)
+    xd[1].fill_(float("nan"))                       # a zero factor must not propagate what was there
+    before = xd.clone()
+    ops.scale_samples_(rt, xd, dev(rt, up), 2.0)
+    exp = before.double().cpu() * (up * 2.0).view(-1, 1, 1, 1)
+    exp[1] = 0.0
+    exp[4] = 0.0
+    assert torch.equal(xd[0], before[0]) and torch.equal(xd[3], before[3]) and torch.equal(xd[6], before[6]), "factor 1: untouched"
+    assert float(xd[1].float().abs().max()) == 0.0 and float(xd[4].float().abs().max()) == 0.0, "factor 0: zero-filled"
+    check(xd, exp, 1e-6 if dt == "f32" else 8e-3, "scale_samples")
