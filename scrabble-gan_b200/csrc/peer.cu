@@ -77,8 +77,16 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(T* __restrict__ data, in
   for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = data[i];
   peer_publish_and_wait(pt);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // all remote reads first (independent, in flight together: one NVLink round trip instead of world - 1), then the sum in
+    // rank order
+    T vals[SG_PEER_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < pt.world) vals[r] = __ldcv(reinterpret_cast<const T*>(pt.buf[r] + slot) + i);
     T acc = 0;
-    for (int r = 0; r < pt.world; ++r) acc += __ldcv(reinterpret_cast<const T*>(pt.buf[r] + slot) + i);
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < pt.world) acc += vals[r];
     data[i] = acc;
   }
   peer_commit_seq(pt);
@@ -115,12 +123,18 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_peer(const float* __restri
   if (pt.world > 1) peer_publish_and_wait(pt);
   else __syncthreads();
   for (int j = threadIdx.x; j < c; j += blockDim.x) {
+    float v1[SG_PEER_MAX_WORLD], v2[SG_PEER_MAX_WORLD];            // all remote reads in flight together, then the sums in rank order
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < pt.world) {
+        const float* pr = reinterpret_cast<const float*>(pt.buf[r] + slot);
+        v1[r] = __ldcv(pr + j);
+        v2[r] = __ldcv(pr + c + j);
+      }
     double s = 0.0, ss = 0.0;
-    for (int r = 0; r < pt.world; ++r) {
-      const float* pr = reinterpret_cast<const float*>(pt.buf[r] + slot);
-      s += (double)__ldcv(pr + j);
-      ss += (double)__ldcv(pr + c + j);
-    }
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < pt.world) { s += (double)v1[r]; ss += (double)v2[r]; }
     if (sums_out) { sums_out[j] = (float)s; sums_out[c + j] = (float)ss; }
     double m = s / count_total;
     double var = ss / count_total - m * m;
@@ -176,11 +190,16 @@ __global__ void __launch_bounds__(256) k_bucket_pull_reduce(BucketPtrs bp, long 
   float* mine = reinterpret_cast<float*>(bp.g[rank]) + lo;
   const long long n4 = len / 4, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    // every replica's copy first (independent NVLink reads in flight together), then the sum in rank order: the same
+    // additions whichever replica owns the shard
+    float4 v[SG_PEER_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < world) v[r] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bp.g[r]) + lo) + i);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {            // rank order: the same additions whichever replica owns the shard
-      float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bp.g[r]) + lo) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+#pragma unroll
+    for (int r = 0; r < SG_PEER_MAX_WORLD; ++r)
+      if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
     __stcg(reinterpret_cast<float4*>(mine) + i, acc);
   }
   for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {

@@ -133,6 +133,15 @@ class Runtime:
         self.stream = torch.cuda.current_stream(self.device)
         call.sg_ctx_set_stream(self._main_ctx, C.c_void_p(self.stream.cuda_stream))
 
+    def close(self) -> None:
+        """Release the libsgan contexts (each owns a 48 MB device workspace).  The runtime must not be used afterwards."""
+        torch.cuda.synchronize(self.device)
+        for h in (self._main_ctx, self._side_ctx, self._comm[1] if self._comm is not None else None):
+            if h is not None:
+                _abi.load().sg_ctx_destroy(h)
+        self._main_ctx = self._side_ctx = self.ctx = None
+        self._comm = None
+
     def comm_stream_ctx(self):
         """The communication stream and its libsgan context (created on first use): gradient-bucket all-reduces run there."""
         if self._comm is None:
