@@ -20,6 +20,11 @@ struct sg_ctx {
   float* det_scratch;        // SG_DET_SCRATCH_BYTES of per-block partial sums
   unsigned int* det_tickets; // SG_DET_TICKETS arrival counters / turn semaphores, all zero between launches
   int conv_split_tail;       // k_conv_tc: split the k-range of the tiles of a partial last wave (SGAN_NO_SPLIT_TAIL=1 disables)
+  // auxiliary streams of the copy-engine gradient-bucket all-reduce (peer.cu): one peer pull per stream, so that the pulls
+  // from different peers run on different copy engines at the same time; created on first use
+  cudaStream_t aux_stream[8];
+  cudaEvent_t aux_fork, aux_join[8];
+  int n_aux;
   int edge_q4;               // edge-layer convs (Cin = 1 / Cout = 1, C = 64): the 4-pixels-per-thread kernels (SGAN_NO_EDGE_Q4=1 disables)
   int pdl;                   // launch kernels with programmatic stream serialization (SGAN_PDL=1 enables; off: measured slower), see sg_launch
 };

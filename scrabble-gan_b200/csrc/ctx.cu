@@ -62,6 +62,11 @@ int sg_ctx_create(int device, void* cuda_stream, sg_ctx** out) {
 
 int sg_ctx_destroy(sg_ctx* ctx) {
   if (ctx) {
+    for (int i = 0; i < ctx->n_aux; ++i) {
+      cudaStreamDestroy(ctx->aux_stream[i]);
+      cudaEventDestroy(ctx->aux_join[i]);
+    }
+    if (ctx->n_aux) cudaEventDestroy(ctx->aux_fork);
     if (ctx->det_scratch) cudaFree(ctx->det_scratch);
     if (ctx->det_tickets) cudaFree(ctx->det_tickets);
     free(ctx);

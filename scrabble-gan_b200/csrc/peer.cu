@@ -267,6 +267,18 @@ int sg_peer_barrier(sg_ctx* ctx, const unsigned long long* peer_bufs, int world,
   return SG_OK;
 }
 
+static int bucket_aux_streams(sg_ctx* ctx, int want) {
+  if (want > 8) want = 8;
+  if (want < 1) want = 1;
+  while (ctx->n_aux < want) {
+    if (ctx->n_aux == 0) SG_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    SG_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream[ctx->n_aux], cudaStreamNonBlocking));
+    SG_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->aux_join[ctx->n_aux], cudaEventDisableTiming));
+    ++ctx->n_aux;
+  }
+  return SG_OK;
+}
+
 long long sg_peer_bucket_shard(long long n, int world) {
   long long s = (n + world - 1) / world;
   return (s + 3) / 4 * 4;                 // 16-byte aligned shard starts
@@ -304,17 +316,26 @@ int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging,
     }
     return sg_peer_barrier(ctx, flag_bufs, world, rank);
   }
-  // (2) reduce-scatter, pull side: the copy engines fetch MY shard of every peer's bucket over NVLink (no SM involved)
+  // (2) reduce-scatter, pull side: the copy engines fetch MY shard of every peer's bucket over NVLink (no SM involved), one
+  //     pull per auxiliary stream so that the pulls from different peers run concurrently (fork / join by events: capturable)
+  rc = bucket_aux_streams(ctx, world - 1);
+  if (rc != SG_OK) return rc;
   const long long mylen = len(rank);
-  int slot = 0;
-  for (int r = 0; r < world; ++r) {
-    if (r == rank) continue;
-    if (mylen > 0)
-      SG_CHECK_CUDA(cudaMemcpyAsync(staging + (long long)slot * shard, (const float*)(uintptr_t)g_ptrs[r] + lo(rank), (size_t)mylen * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, ctx->stream));
-    ++slot;
-  }
   if (mylen > 0) {
+    SG_CHECK_CUDA(cudaEventRecord(ctx->aux_fork, ctx->stream));
+    int slot = 0;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      cudaStream_t st = ctx->aux_stream[slot % ctx->n_aux];
+      if (slot < ctx->n_aux) SG_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->aux_fork, 0));
+      SG_CHECK_CUDA(cudaMemcpyAsync(staging + (long long)slot * shard, (const float*)(uintptr_t)g_ptrs[r] + lo(rank), (size_t)mylen * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+      ++slot;
+    }
+    for (int k = 0; k < ctx->n_aux && k < world - 1; ++k) {
+      SG_CHECK_CUDA(cudaEventRecord(ctx->aux_join[k], ctx->aux_stream[k]));
+      SG_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join[k], 0));
+    }
     long long need = (mylen / 4 + 255) / 256;
     int grid = (int)(need < 64 ? (need < 1 ? 1 : need) : 64);       // a small grid: this runs under the step's compute kernels
     sg_launch(ctx, k_bucket_reduce, grid, 256, 0, g + lo(rank), staging, mylen, shard, world, rank);
@@ -323,11 +344,22 @@ int sg_peer_bucket_allreduce(sg_ctx* ctx, float* g, long long n, float* staging,
   // (3) every shard is reduced on its owner
   rc = sg_peer_barrier(ctx, flag_bufs, world, rank);
   if (rc != SG_OK) return rc;
-  // (4) all-gather, pull side
-  for (int r = 0; r < world; ++r) {
-    if (r == rank || len(r) <= 0) continue;
-    SG_CHECK_CUDA(cudaMemcpyAsync(g + lo(r), (const float*)(uintptr_t)g_ptrs[r] + lo(r), (size_t)len(r) * sizeof(float), cudaMemcpyDeviceToDevice,
-                                  ctx->stream));
+  // (4) all-gather, pull side, again one peer per auxiliary stream
+  {
+    SG_CHECK_CUDA(cudaEventRecord(ctx->aux_fork, ctx->stream));
+    int slot = 0;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      cudaStream_t st = ctx->aux_stream[slot % ctx->n_aux];
+      if (slot < ctx->n_aux) SG_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->aux_fork, 0));
+      if (len(r) > 0)
+        SG_CHECK_CUDA(cudaMemcpyAsync(g + lo(r), (const float*)(uintptr_t)g_ptrs[r] + lo(r), (size_t)len(r) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      ++slot;
+    }
+    for (int k = 0; k < ctx->n_aux && k < world - 1; ++k) {
+      SG_CHECK_CUDA(cudaEventRecord(ctx->aux_join[k], ctx->aux_stream[k]));
+      SG_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join[k], 0));
+    }
   }
   // (5) nobody touches its bucket again before every peer has read its shard
   return sg_peer_barrier(ctx, flag_bufs, world, rank);
