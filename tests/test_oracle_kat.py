@@ -5,7 +5,6 @@ gradient-balance derivative, exhaustive filter-bank index map."""
 import math
 
 import numpy as np
-import pytest
 import torch
 
 import sgan_oracle as O

@@ -6,7 +6,6 @@
 Both against the fp64 oracle's statement of the same option, in exact-fp32 mode."""
 import importlib
 
-import numpy as np
 import pytest
 import torch
 
