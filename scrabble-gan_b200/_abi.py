@@ -66,6 +66,7 @@ _PROTOS = {
     "sg_conv_pack_weights_multi": (_I, [_P, _I, C.POINTER(_DP), C.POINTER(_P), C.POINTER(_P)]),
     "sg_conv_fwd_tc": (_I, [_P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_fwd_tc_rank1": (_I, [_P, _DP, _P, _P, _P, _P, _P, _P, _P]),
+    "sg_conv_tc_plan": (_I, [_DP, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "sg_conv_fwd_tc_phases": (_I, [_P, _I, C.POINTER(_DP), _P, _P, _P, _P]),
     "sg_conv_fwd_tc_dual": (_I, [_P, _DP, _P, _P, _DP, _P, _P, _P, _P, _P]),
     "sg_conv_tc_direct_supported": (_I, [_DP]),

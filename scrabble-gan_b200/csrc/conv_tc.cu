@@ -1421,6 +1421,31 @@ int sg_conv_fwd_tc(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const voi
 
 /* out = epilogue( conv(d, in, w_packed) + conv1x1(d2, in2, w_packed2) ): the ResNet block's shortcut (resnet_ops.py:109-114)
  * accumulated in TMEM as extra k-blocks of the main conv instead of a second read-modify-write pass over the output */
+/* host-only: the N tile and tail split sg_conv_fwd_tc would choose for this descriptor on a device with num_sms SMs */
+int sg_conv_tc_plan(const sg_conv_desc* d, int num_sms, int split_tail_enabled, int* bn_out, int* split_out, int* tiles_out) {
+  SG_REQUIRE(d && num_sms > 0 && bn_out && split_out && tiles_out, "sg_conv_tc_plan: bad args");
+  int rc = tc_check(d, "sg_conv_tc_plan");
+  if (rc != SG_OK) return rc;
+  const int KC = 128 / (d->in_dt == SG_F32 ? 4 : 2);
+  int TW, TH, TN;
+  choose_box(d->grid_w, d->grid_h, d->n, 128, 1, &TW, &TH, &TN);
+  const long long m_tiles = (long long)sg_div_up(d->grid_w, TW) * sg_div_up(d->grid_h, TH) * sg_div_up(d->n, TN);
+  const int nkb = d->ntaps * (d->c_in / KC);
+  const int cand[4] = {256, 128, 64, 32};
+  const double rel[4] = {1.0, 0.85, 0.75, 0.7};
+  double best = -1.0;
+  *bn_out = 32; *split_out = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (d->c_out % cand[i]) continue;
+    long long tiles = m_tiles * (d->c_out / cand[i]);
+    int split = 1;
+    double cost = tc_split_plan(tiles, num_sms, nkb, cand[i], split_tail_enabled, &split) * rel[i];
+    if (best < 0 || cost < best * 0.97) { best = cost; *bn_out = cand[i]; *split_out = split; }
+  }
+  *tiles_out = (int)(m_tiles * (d->c_out / *bn_out));
+  return SG_OK;
+}
+
 int sg_conv_fwd_tc_rank1(sg_ctx* ctx, const sg_conv_desc* d, const void* in, const void* w_packed, const float* bias,
                          const void* mask, void* out, const float* r1_x, const float* r1_w) {
   SG_REQUIRE(r1_x && r1_w, "sg_conv_fwd_tc_rank1: NULL rank-1 operands");

@@ -123,3 +123,36 @@ def test_synthetic_loaders_keep_the_reference_interfaces():
     words = du.synthetic_random_words(10, char_vec, words_per_bucket=7)
     assert len(words) == 10 and all(len(words[i]) == 7 and all(len(w) == i + 1 for w in words[i]) for i in range(10))
     assert du.STAT_NAMES[:3] == ("r_loss_fake", "r_loss_real", "r_loss_balanced") and len(du.STAT_NAMES) == 16
+
+
+def test_conv_tile_plan_and_bucket_shards_host_only():
+    """Host-only planning of the tensor-core conv launch (no GPU): wave quantisation is answered by splitting the k-range of the
+    tiles of a partial last wave, never for short-k launches; and the shards of the gradient-bucket all-reduce tile the bucket."""
+    import ctypes as C
+    abi = importlib.import_module("scrabble-gan_b200._abi")
+    ops = importlib.import_module("scrabble-gan_b200.ops")
+    lib = abi.load()
+
+    def plan(n, h, w, ci, co, k, sms=148, enabled=1):
+        d = ops.desc_conv_fwd(n, h, w, ci, co, k, k, "same", in_dt=abi.SG_BF16)
+        bn, split, tiles = C.c_int(), C.c_int(), C.c_int()
+        assert lib.sg_conv_tc_plan(C.byref(d), sms, enabled, C.byref(bn), C.byref(split), C.byref(tiles)) == 0, abi.last_error()
+        return bn.value, split.value, tiles.value
+    # D.B4 on the fused batch: 128 images of 4x10 = 40 full pixel tiles x 4 column tiles = 160 tiles on 148 SMs: the 12 tiles of
+    # the second wave are split along k (K = 9216 = 144 k-blocks) instead of running a second wave at 8 % occupancy
+    bn, split, tiles = plan(128, 4, 10, 1024, 1024, 3)
+    assert (bn, tiles) == (256, 160) and 4 <= split <= 8 and 12 * split <= 148
+    assert plan(128, 4, 10, 1024, 1024, 3, enabled=0)[1] == 1
+    # the half batch: 80 tiles on 148 SMs -> every tile is split (more, shorter units fill the machine)
+    bn, split, tiles = plan(64, 4, 10, 1024, 1024, 3)
+    assert (bn, tiles) == (256, 80) and split >= 2
+    assert plan(128, 8, 20, 1024, 1024, 3)[1] > 1                      # 640 tiles = 4.32 waves: the tail is split
+    assert plan(148, 8, 20, 1024, 1024, 3, sms=185)[1] == 1            # 740 tiles on 185 SMs: whole waves, nothing to split
+    assert plan(128, 16, 40, 64, 512, 3)[1] == 1                       # K = 576 (9 k-blocks): the exchange would cost more
+    assert plan(2, 4, 10, 64, 64, 3)[1] == 1
+    # bucket shards: 16-byte aligned starts, cover [0, n) exactly once
+    for n, world in ((1000003, 2), (5, 8), (4096, 3), (37336384, 8)):
+        shard = int(lib.sg_peer_bucket_shard(n, world))
+        assert shard % 4 == 0 and shard * world >= n and shard * (world - 1) < n + 4 * world
+        covered = sum(max(0, min(n, (r + 1) * shard) - min(n, r * shard)) for r in range(world))
+        assert covered == n
