@@ -1300,7 +1300,7 @@ static int conv_fwd_tc_impl(sg_ctx* ctx, const sg_conv_desc* d, const void* in, 
   int best_split = 1;
   {
     // N tile and tail split.  With a static persistent schedule a launch costs ceil(tiles / #SMs) tile-times, so a launch whose
-    // last wave is mostly empty (D.B4: 43 pixel tiles x 4 = 172 tiles of 256 columns on 148 SMs = 2 waves for 1.16 waves of work)
+    // last wave is mostly empty (D.B4: 40 pixel tiles x 4 = 160 tiles of 256 columns on 148 SMs = 2 waves for 1.08 waves of work)
     // runs at half speed.  Two remedies, costed together: a narrower N tile (relative tile times from tools/bench_conv.py on
     // B200: the main loop is operand-load bound, a 128-column tile costs ~0.85 of a 256-column one), and splitting the k-range of
     // the tiles of the last, partial wave over `split` CTAs each (tc_split_plan).
