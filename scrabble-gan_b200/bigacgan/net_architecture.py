@@ -554,7 +554,13 @@ class Generator(_Model):
         want_dz = self.style is not None
         n = net.shape[0]
         dpre = ops.tanh_bwd(rt, dimg, img)
-        self.out.wgrad(rt, act, dpre)
+        # filter gradients are off the input-gradient chain: on the side stream, next to the chain (ResNetBlockUp.backward)
+        side = [dpre] if (rt.concurrent_branches and rt.side_wgrads) else None
+        if side is not None:
+            with rt.branch():
+                self.out.wgrad(rt, act, dpre)
+        else:
+            self.out.wgrad(rt, act, dpre)
         dact = self.out.dgrad(rt, dpre, (net.shape[1], net.shape[2]))
         s1, s2 = ops.bn_bwd_reduce(rt, dact, act, net, mean, rstd)
         ops.colsum_into(rt, s2, self.bn.c, self.bn.gamma.grad, accumulate=1)
@@ -570,7 +576,8 @@ class Generator(_Model):
             c, ca = caches[i]
             if ca is not None:
                 d = self.attn[i].backward(rt, ca, d, True)
-            d = self.blocks[i].backward(rt, c, d, dz[:, self.zchunk * (i + 1):] if want_dz else None, self.latent_dim, defer=defer)
+            d = self.blocks[i].backward(rt, c, d, dz[:, self.zchunk * (i + 1):] if want_dz else None, self.latent_dim, defer=defer,
+                                        side=side)
         if defer:
             # the 12 Dense filter gradients dW = z_block^T @ (d gamma | d beta) in ONE launch
             by_layer = {id(cbn): (s1, s2) for cbn, s1, s2 in defer}
@@ -585,6 +592,10 @@ class Generator(_Model):
             feats, tc = sc
             dfeats = self.style_dense.backward(rt, feats, dz, n, want_dx=True, wgrad=True)
             self.style.backward(rt, tc, dfeats, True, False)
+        if side is not None:
+            br = rt.branch()
+            br.join()                  # all filter gradients are in the bucket; only now may their operands be released
+            side.clear()
 
     def _cbn_segments(self, grad: bool = False):
         """(C, column offset of the block's z slice, offset of the Dense kernel in the flat store, (layer, which)) for the

@@ -97,19 +97,30 @@ class ResNetBlockUp:
         self.short.forward(rt, xs, out=h, accumulate=True, bias=None)
         return h, (c1, c2, a1, a2, xs, x.shape)
 
-    def backward(self, rt: Runtime, cache, dh, dz_out=None, dz_ld: int = 0, defer=None):
+    def backward(self, rt: Runtime, cache, dh, dz_out=None, dz_ld: int = 0, defer=None, side=None):
+        """side: a list -- the three filter gradients of the block are not on the input-gradient chain, so they are enqueued on
+        the runtime's side stream (rt.branch) and run next to the chain's (small, latency-bound) kernels; the list collects
+        the temporaries they read, which the caller keeps alive until it has joined the side stream."""
         c1, c2, a1, a2, xs, xshape = cache
         n, hh, ww, _ = xshape
         dh_op = ops.cast(rt, dh, rt.op_dt)
+
+        def off_chain(fn, *keep):
+            if side is None:
+                fn()
+                return
+            side.extend(keep)
+            with rt.branch():
+                fn()
         # main branch, back to front
-        self.conv.wgrad(rt, a2, dh_op, also_bias=self.short.b.grad)      # the shortcut bias sees the same upstream gradient
+        off_chain(lambda: self.conv.wgrad(rt, a2, dh_op, also_bias=self.short.b.grad), dh_op)   # the shortcut bias sees the same upstream gradient
         da2 = self.conv.dgrad(rt, dh_op, (hh * self.stride[0], ww * self.stride[1]))
         du = self.cbn2.backward(rt, c2, da2, out_dt=rt.op_dt, dz_out=dz_out, dz_ld=dz_ld, defer=defer)
-        self.up.wgrad(rt, a1, du)
+        off_chain(lambda: self.up.wgrad(rt, a1, du), du)
         da1 = self.up.dgrad(rt, du)
         dx = self.cbn1.backward(rt, c1, da1, out_dt=SG_F32, dz_out=dz_out, dz_ld=dz_ld, defer=defer)
         # shortcut branch
-        self.short.wgrad(rt, xs, dh_op, bias_grad=False)
+        off_chain(lambda: self.short.wgrad(rt, xs, dh_op, bias_grad=False), dh_op)
         self.short.dgrad(rt, dh_op, out=dx, accumulate=True)
         return dx
 

@@ -43,6 +43,8 @@ class Runtime:
         self.side_stream = None
         self._side_ctx = None
         self.concurrent_branches = os.environ.get("SGAN_NO_BRANCHES", "0") != "1"
+        # G's filter gradients on the side stream, next to its input-gradient chain
+        self.side_wgrads = os.environ.get("SGAN_NO_SIDE_WGRADS", "0") != "1"
         self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
         self.set_mode(mode)
         # data-parallel state (see dp.py)
