@@ -340,6 +340,7 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
     # filter gradients are complete, on NCCL's stream, overlapping with the backward passes that follow.
     pending = []
     dimg_r_merged = dimg_d_merged = None
+    d_side = None
     discriminator.trainable = True
     recognizer.trainable = True
     br = rt.branch()                     # R's backward (side stream) next to D's two backward passes (main stream)
@@ -356,8 +357,14 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
                 rfc = recognizer.slice_cache(rcc, 0, b)
             pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g, store=recognizer.store)))
         if update_g and rt.merge_d_backward:
-            # ONE backward pass of D over the fused batch for both losses (Discriminator.backward_merged)
-            dimg_d_merged = discriminator.backward_merged(rt, dcc, ups[0:2].view(-1), b, up_d_fake_g, 1.0)
+            # ONE backward pass of D over the fused batch for both losses (Discriminator.backward_merged); its filter gradients
+            # run on the side stream next to the input-gradient chain and -- on one replica without spectral norm, where
+            # nothing reads D's bucket before D's optimizer launch (side stream too) -- next to G's backward pass as well
+            d_side = [] if (rt.concurrent_branches and rt.side_d_wgrads) else None
+            dimg_d_merged = discriminator.backward_merged(rt, dcc, ups[0:2].view(-1), b, up_d_fake_g, 1.0, side=d_side)
+            if d_side is not None and (rt.world_size > 1 or discriminator.store.sn is not None):
+                rt.branch().join()
+                d_side = None
         else:
             discriminator.backward(rt, dcc, ups[0:2].view(-1), wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)

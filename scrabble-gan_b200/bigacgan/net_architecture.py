@@ -236,8 +236,9 @@ class _DownTrunk:
             out.append((ResNetBlockDown.slice_cache(c, a, b), NonLocalBlock.slice_cache(ca, a, b) if ca is not None else None))
         return (out, net[a:b])
 
-    def backward(self, rt: Runtime, cache, dfeats, wgrad: bool, want_dx: bool, fake=None):
-        """fake = (b, up, mult): merged backward (see ResNetBlockDown.backward); returns the image gradient of rows [0, b)."""
+    def backward(self, rt: Runtime, cache, dfeats, wgrad: bool, want_dx: bool, fake=None, side=None):
+        """fake = (b, up, mult): merged backward (see ResNetBlockDown.backward); returns the image gradient of rows [0, b).
+        side: list -- with `fake`, the blocks' filter gradients run on the side stream (their operands are collected here)."""
         caches, net = cache
         d = ops.gap_relu_bwd(rt, dfeats, net)
         for i in reversed(range(len(self.blocks))):
@@ -254,7 +255,7 @@ class _DownTrunk:
                     ops.scale_samples_(rt, d[:b], up, mult)
                     d = self.attn[i].backward(rt, ca, d, wgrad)
                     d[:b].copy_(d_fake)
-            d = self.blocks[i].backward(rt, c, d, wgrad, want_dx or i > 0, fake=fake)
+            d = self.blocks[i].backward(rt, c, d, wgrad, want_dx or i > 0, fake=fake, side=side)
         return d
 
 
@@ -286,20 +287,22 @@ class Discriminator(_Model):
         dfeats = self.dense.backward(rt, feats, up, n, want_dx=True, wgrad=wgrad)
         return self.trunk.backward(rt, c, dfeats, wgrad, want_dx)
 
-    def backward_merged(self, rt, cache, up_all, b: int, up_fake_g, mult: float):
+    def backward_merged(self, rt, cache, up_all, b: int, up_fake_g, mult: float, side=None):
         """ONE backward pass over a [fake ; real] batch that serves both the D loss and the G loss (data_utils.py:449-468
         differentiates them separately; frozen weights make the second tape the same linear map).  Back-propagation is linear
         in a sample's upstream weight, so rows [0, b) -- the fake images -- travel with the constant weight 1 / mult; the
         filter gradients of the D loss see them rescaled by up_all[i] * mult (hinge: exactly 0 or 1), and the image gradient
         of the G loss is the returned d/d(fake image) rescaled by up_fake_g[i] * mult.  up_all [2b] = d(D loss)/d(logit) for
-        [fake ; real].  Accumulates D's parameter gradients; returns d(G loss)/d(fake images) [b, H, W, 1]."""
+        [fake ; real].  Accumulates D's parameter gradients; returns d(G loss)/d(fake images) [b, H, W, 1].
+        side: a list -- the blocks' filter gradients are enqueued on the runtime's side stream and are complete only after the
+        caller has joined it (rt.branch().join()); the list holds their operands and must stay alive until then."""
         feats, c = cache
         n = feats.shape[0]
         self.dense.backward(rt, feats, up_all, n, want_dx=False, wgrad=True)
         up_chain = up_all.clone()
         up_chain[:b].fill_(1.0 / mult)
         dfeats = self.dense.backward(rt, feats, up_chain, n, want_dx=True, wgrad=False)
-        dimg = self.trunk.backward(rt, c, dfeats, True, True, fake=(b, up_all, mult))
+        dimg = self.trunk.backward(rt, c, dfeats, True, True, fake=(b, up_all, mult), side=side)
         ops.scale_samples_(rt, dimg, up_fake_g, mult)
         return dimg
 

@@ -166,7 +166,7 @@ class ResNetBlockDown:
         xr, xs, h1, hw = cache
         return (xr[a:b], xs[a:b], h1[a:b], hw)
 
-    def backward(self, rt: Runtime, cache, dout, wgrad: bool = True, want_dx: bool = True, fake=None):
+    def backward(self, rt: Runtime, cache, dout, wgrad: bool = True, want_dx: bool = True, fake=None, side=None):
         """fake = (b, up, mult) -- the merged discriminator backward (Discriminator.backward_merged): rows [0, b) of the batch
         carry a CONSTANT upstream weight through the input-gradient chain; the filter gradients need the per-sample weights
         up[i] * mult of the D loss instead, so the block first computes its input gradients from the unscaled tensors, then
@@ -196,12 +196,21 @@ class ResNetBlockDown:
             dx = self.conv1.dgrad(rt, dh1[rows], (h, w), mask=xr[rows])
             self.short.dgrad(rt, dpre[rows], (h, w), out=dx, accumulate=True)
         if wgrad:
-            seen = set()
-            for t in (dpre, dh1, dout):
-                if t.data_ptr() not in seen:                 # last block in fp32 mode: dpre IS dout (no cast, no pooling)
-                    seen.add(t.data_ptr())
-                    ops.scale_samples_(rt, t[:b], up, mult)
-            self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad, bias_src=dout)
-            self.short.wgrad(rt, xs, dpre, bias_grad=False)
-            self.conv1.wgrad(rt, xr, dh1)
+            def filter_grads():
+                seen = set()
+                for t in (dpre, dh1, dout):
+                    if t.data_ptr() not in seen:             # last block in fp32 mode: dpre IS dout (no cast, no pooling)
+                        seen.add(t.data_ptr())
+                        ops.scale_samples_(rt, t[:b], up, mult)
+                self.conv2.wgrad(rt, h1, dpre, also_bias=self.short.b.grad, bias_src=dout)
+                self.short.wgrad(rt, xs, dpre, bias_grad=False)
+                self.conv1.wgrad(rt, xr, dh1)
+            if side is None:
+                filter_grads()
+            else:
+                # off the input-gradient chain: the rescale and the three filter gradients go to the side stream (everything
+                # the chain reads from these tensors has been enqueued above); the caller keeps the tensors alive until it joins
+                side.extend((dpre, dh1, dout))
+                with rt.branch():
+                    filter_grads()
         return dx

@@ -101,6 +101,14 @@ int sg_ctx_set_speed_mode(sg_ctx* ctx, int on) {
   return SG_OK;
 }
 
+int sg_ctx_set_sm_limit(sg_ctx* ctx, int sms) {
+  SG_REQUIRE(ctx != nullptr && sms >= 1, "sg_ctx_set_sm_limit: bad args");
+  cudaDeviceProp prop;
+  SG_CHECK_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->num_sms = sms < prop.multiProcessorCount ? sms : prop.multiProcessorCount;
+  return SG_OK;
+}
+
 int sg_ctx_set_conv_split_tail(sg_ctx* ctx, int on) {
   SG_REQUIRE(ctx != nullptr, "ctx is NULL");
   ctx->conv_split_tail = on ? 1 : 0;

@@ -43,6 +43,10 @@ class Runtime:
         self.side_stream = None
         self._side_ctx = None
         self.concurrent_branches = os.environ.get("SGAN_NO_BRANCHES", "0") != "1"
+        # D's filter gradients (merged backward) on the side stream, next to D's input-gradient chain and G's backward pass;
+        # side_sms > 0 sizes the side stream's grids for that many SMs, leaving the rest to the main stream's chain
+        self.side_d_wgrads = os.environ.get("SGAN_NO_SIDE_D_WGRADS", "0") != "1"
+        self.side_sms = int(os.environ.get("SGAN_SIDE_SMS", "0"))
         # G's filter gradients on the side stream, next to its input-gradient chain
         self.side_wgrads = os.environ.get("SGAN_NO_SIDE_WGRADS", "0") != "1"
         self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
@@ -215,6 +219,7 @@ class Branch:
         self.rt = rt
         self.active = rt.concurrent_branches
         self._ctxmgr = None
+        self._done = None               # event recorded on the side stream at the end of the last `with` block of this branch
         if not self.active:
             return
         if rt.side_stream is None:
@@ -223,6 +228,8 @@ class Branch:
             call.sg_ctx_create(rt.device_index, C.c_void_p(rt.side_stream.cuda_stream), C.byref(handle))
             rt._side_ctx = handle
             call.sg_ctx_set_speed_mode(handle, int(rt.mode == "bf16" and os.environ.get("SGAN_NO_NL_TC", "0") != "1"))
+            if rt.side_sms > 0:
+                call.sg_ctx_set_sm_limit(handle, rt.side_sms)
         self.main = torch.cuda.current_stream(rt.device)
         rt.side_stream.wait_stream(self.main)
 
@@ -235,13 +242,21 @@ class Branch:
 
     def __exit__(self, *exc):
         if self.active:
+            self._done = torch.cuda.Event()
+            self._done.record(self.rt.side_stream)
             self._ctxmgr.__exit__(*exc)
             self.rt.ctx = self.rt._main_ctx
         return False
 
     def join(self) -> None:
+        """The current stream waits for what THIS branch enqueued (its `with` blocks) -- not for work other branches put on
+        the side stream afterwards; a branch without a `with` block joins the whole side stream."""
         if self.active:
-            torch.cuda.current_stream(self.rt.device).wait_stream(self.rt.side_stream)
+            cur = torch.cuda.current_stream(self.rt.device)
+            if self._done is not None:
+                cur.wait_event(self._done)
+            else:
+                cur.wait_stream(self.rt.side_stream)
 
 
 _default: Optional[Runtime] = None
