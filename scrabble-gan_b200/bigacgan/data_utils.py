@@ -374,9 +374,17 @@ def _step_device(rt, args, x_real, y_real, y_fake, g_in, style_imgs):
         with br:
             recognizer.backward(rt, rrc, None, wgrad=True, want_dx=False)
             pending.append((id(recognizer), rt.allreduce_async_(recognizer.store.g, store=recognizer.store)))
+            if update_g:
+                # R's image gradient of the fake batch (frozen R, G loss) right away: D's filter gradients queue up behind it
+                # on the side stream, and G's backward pass must not wait for those
+                dimg_r_merged = recognizer.backward(rt, rfc, up_r_fake_g, wgrad=False, want_dx=True)
         discriminator.backward(rt, drc, up_d_real, wgrad=True, want_dx=False)
         if update_g and rt.merge_d_backward:
-            dimg_d_merged = discriminator.backward_merged(rt, dfc, up_d_fake_d, b, up_d_fake_g, 1.0)     # the whole batch is "fake"
+            d_side = [] if (rt.concurrent_branches and rt.side_d_wgrads) else None
+            dimg_d_merged = discriminator.backward_merged(rt, dfc, up_d_fake_d, b, up_d_fake_g, 1.0, side=d_side)   # the whole batch is "fake"
+            if d_side is not None and (rt.world_size > 1 or discriminator.store.sn is not None):
+                rt.branch().join()
+                d_side = None
         else:
             discriminator.backward(rt, dfc, up_d_fake_d, wgrad=True, want_dx=False)
         discriminator.sn_backward(rt)
