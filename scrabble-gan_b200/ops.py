@@ -379,7 +379,7 @@ def bn_stats(rt, x) -> torch.Tensor:
     c = x.shape[-1]
     rows = x.numel() // c
     nbytes = _abi.load().sg_bn_stats_scratch_bytes(rows, c)
-    scratch = rt.scratch("bn", nbytes)
+    scratch = rt.scratch("bn" if rt.ctx is rt._main_ctx else "bn_side", nbytes)      # one scratch per stream: never shared by concurrent kernels
     sums = rt.empty((2 * c,), SG_F32)
     call.sg_bn_stats(rt.ctx, _p(x), rows, c, _p(sums), _p(scratch), nbytes)
     return sums
